@@ -1,0 +1,10 @@
+"""B200-native Tacotron mel-synthesis hot path (drop-in for the reference's models/tacotron.py).
+
+The directory name carries a hyphen (it is fixed by the project layout), so import it with
+``importlib.import_module("multi-speaker-tacotron-tensorflow_b200")`` or through the root-level
+``tacotron_b200`` shim, which does exactly that.
+"""
+from .hparams import HParams, hparams, hparams_debug_string, load_hparams, save_hparams  # noqa: F401
+from . import params  # noqa: F401
+
+__all__ = ["HParams", "hparams", "hparams_debug_string", "load_hparams", "save_hparams", "params"]
