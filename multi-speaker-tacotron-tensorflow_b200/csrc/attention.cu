@@ -1,0 +1,794 @@
+// Cluster-persistent attention recurrence of the decoder (teacher-forced path), forward and BPTT.
+//   reference: models/rnn_wrappers.py:218-341 (AttentionWrapper.call + _compute_attention),
+//              :367-378 (DecoderPrenetWrapper), :405-415 (ConcatOutputAndAttentionWrapper),
+//              models/tacotron.py:127-170, TF r1.4 BahdanauMonotonicAttention / BahdanauAttention
+//   (SURVEY.md §8a rows D1-D7, Appendix C for the monotonic backward).
+//
+// Per decoder step t (per batch row):
+//   z1 = relu(px[t] + ctx.W1c)            px = x_t.W1[0:M] + b1 hoisted over all t (teacher forcing)
+//   z  = relu(z1.W2 + b2) (++ spk)
+//   [r,u] = sigmoid([z,ha].Wg + bg); c = tanh([z, r*ha].Wc + bc); ha' = u*ha + (1-u)*c        (TF GRUCell)
+//   q = ha'.Wq;  e_j = sum_u v_u tanh(keys_ju + q_u) (+ b);  a = monotonic(sigmoid(e), a_prev) | softmax(e) | manual
+//   ctx' = sum_j a_j memory_j;  y0 = [ha', ctx' (,spk)].Wo + bo
+// The two ResidualWrapper(GRUCell) layers and the mel projection do not feed back in teacher-forced mode
+// (helpers.py:60-67), so they run afterwards as hoisted GEMMs + the GRU kernel of gru.cu.
+//
+// Mapping: a cluster of 8 CTAs owns 8 batch rows; each CTA owns 1/8 of every layer's output units and 1/8 of the
+// memory positions for scoring.  Activations are exchanged through distributed shared memory; 7 cluster barriers
+// per step.  Weights are streamed from L2 every step with coalesced loads (they do not fit 8 x 227 KB in fp32).
+#include "common.cuh"
+#include "kernels.h"
+#include <cooperative_groups.h>
+#include <cfloat>
+
+namespace cg = cooperative_groups;
+
+namespace taco {
+
+constexpr int AT_C = 8, AT_R = 8, AT_NT = 256;
+
+template <bool FAST> __device__ __forceinline__ float tanh_(float x) {
+    if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    return tanhf(x);
+}
+template <bool FAST> __device__ __forceinline__ float sigm_(float x) {
+    if (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+    return 1.0f / (1.0f + expf(-x));
+}
+
+// acc[r] += sum_{k in [k0,k1)} Wcol[k*ld] * v_s[k*R + r]      (Wcol already points at this thread's column)
+__device__ __forceinline__ void mv_acc(float acc[AT_R], const float* __restrict__ Wcol, long long ld, const float* __restrict__ v_s,
+                                       int k0, int k1) {
+#pragma unroll 4
+    for (int k = k0; k < k1; k++) {
+        const float w = __ldg(Wcol + (long long)k * ld);
+        const float4 a = *reinterpret_cast<const float4*>(v_s + k * AT_R);
+        const float4 b = *reinterpret_cast<const float4*>(v_s + k * AT_R + 4);
+        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    }
+}
+__device__ __forceinline__ void red_store(float* red, int tid, const float acc[AT_R]) {
+#pragma unroll
+    for (int r = 0; r < AT_R; r++) red[r * AT_NT + tid] = acc[r];
+}
+// sum over the k-slices of column `col` for row r (ncols columns per slice row)
+__device__ __forceinline__ float red_sum(const float* red, int r, int col, int ncols) {
+    float s = 0.f;
+    for (int c = col; c < AT_NT; c += ncols) s += red[r * AT_NT + c];
+    return s;
+}
+// push a [U][R] block (unit-major) into every peer's [K][R] vector at unit offset rank*U
+__device__ __forceinline__ void push_um(cg::cluster_group& cl, float* vec_s, const float* stage, int rank, int U, int tid) {
+    const int Q = U * AT_R / 4;
+    for (int idx = tid; idx < AT_C * Q; idx += AT_NT) {
+        const int peer = idx / Q, q = idx % Q;
+        float* dst = cl.map_shared_rank(vec_s, peer) + rank * U * AT_R;
+        reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(stage)[q];
+    }
+}
+// push a [R][U] block (row-major) into every peer's [R][W] matrix at column offset rank*U
+__device__ __forceinline__ void push_rm(cg::cluster_group& cl, float* mat_s, int W, const float* stage, int rank, int U, int tid) {
+    const int tot = AT_R * U;
+    for (int idx = tid; idx < AT_C * tot; idx += AT_NT) {
+        const int peer = idx / tot, e = idx % tot;
+        const int r = e / U, i = e % U;
+        cl.map_shared_rank(mat_s, peer)[r * W + rank * U + i] = stage[e];
+    }
+}
+
+static inline size_t att_fwd_smem_floats(const AttArgs& a, int Tip) {
+    return (size_t)AT_R * (a.E + a.Z1 + (a.Z + a.SPK) + 2 * a.HA + a.A) + (size_t)4 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
+}
+static inline size_t att_bwd_smem_floats(const AttArgs& a, int Tip) {
+    return (size_t)AT_R * (a.Y + a.A + a.Z1 + a.Z + 3 * a.HA + a.E) + (size_t)8 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int grp = blockIdx.x / AT_C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = AT_R;
+    const int E = a.E, A = a.A, HA = a.HA, Z1 = a.Z1, Z = a.Z, SPK = a.SPK, Y = a.Y, Ti = a.Ti, Td = a.Td;
+    const int ZS = Z + SPK;
+    const int TJ = (Ti + AT_C - 1) / AT_C, Tip = TJ * AT_C;
+    const int Uz1 = Z1 / AT_C, Uz = Z / AT_C, Uh = HA / AT_C, Ua = A / AT_C, Uy = Y / AT_C, Ue = E / AT_C;
+
+    extern __shared__ __align__(16) float smem[];
+    float* ctx_s = smem;                    // [E][R]
+    float* z1_s = ctx_s + E * R;            // [Z1][R]
+    float* z_s = z1_s + Z1 * R;             // [Z+SPK][R]
+    float* ha_s = z_s + ZS * R;             // [HA][R]
+    float* rha_s = ha_s + HA * R;           // [HA][R]
+    float* q_rm = rha_s + HA * R;           // [R][A]
+    float* e_s = q_rm + R * A;              // [R][Tip]
+    float* a_s = e_s + R * Tip;             // [R][Tip]
+    float* p_s = a_s + R * Tip;             // [R][Tip]
+    float* cp_s = p_s + R * Tip;            // [R][Tip]
+    float* red = cp_s + R * Tip;            // [R][NT]
+    float* red2 = red + R * AT_NT;          // [R][NT]
+    float* stage = red2 + R * AT_NT;        // [1024]
+    float* v_s = stage + 1024;              // [A]
+
+    // ---- init ------------------------------------------------------------------------------
+    if (a.att_type == TACO_ATT_BAH_NORM) {
+        float ss = 0.f;
+        for (int u = 0; u < A; u++) ss += a.v[u] * a.v[u];
+        const float sc = a.att_g[0] * rsqrtf(ss);
+        for (int u = tid; u < A; u += AT_NT) v_s[u] = a.v[u] * sc;
+    } else {
+        for (int u = tid; u < A; u += AT_NT) v_s[u] = a.v[u];
+    }
+    for (int idx = tid; idx < E * R; idx += AT_NT) ctx_s[idx] = 0.f;
+    for (int idx = tid; idx < HA * R; idx += AT_NT) {
+        int k = idx / R, r = idx % R, n = grp * R + r;
+        ha_s[idx] = (a.ha0 && n < a.N) ? a.ha0[(long long)n * HA + k] : 0.f;
+    }
+    for (int idx = tid; idx < ZS * R; idx += AT_NT) {
+        int k = idx / R, r = idx % R, n = grp * R + r;
+        z_s[idx] = (k >= Z && a.spk && n < a.N) ? a.spk[(long long)n * SPK + (k - Z)] : 0.f;
+    }
+    for (int idx = tid; idx < R * Tip; idx += AT_NT) {
+        int j = idx % Tip;
+        a_s[idx] = (a.att_type == TACO_ATT_BAH_MON && j == 0) ? 1.f : 0.f;
+        e_s[idx] = 0.f;
+    }
+    const float score_bias = (a.att_type == TACO_ATT_BAH_MON) ? a.score_bias[0] : 0.f;
+
+    // activation-thread coordinates for 32-unit and 16-unit layers
+    const int i32 = tid % 32, r32 = tid / 32;            // 256 threads: (unit, row)
+    const int n32 = grp * R + r32;
+    const bool row_ok32 = n32 < a.N;
+    float ha_own = (a.ha0 && row_ok32) ? a.ha0[(long long)n32 * HA + rank * Uh + i32] : 0.f;
+    __syncthreads();
+    cl.sync();
+
+    for (int t = 0; t < Td; t++) {
+        const long long row32 = (long long)n32 * Td + t;
+        // ===== P1: z1 (own Uz1 units) = relu(px + ctx.W1c) =====
+        {
+            const int ncols = Uz1, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = E / KS;
+            mv_acc(acc, a.W1c + rank * Uz1 + col, Z1, ctx_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        if (tid < Uz1 * R) {
+            const int i = tid % Uz1, r = tid / Uz1, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                const long long row = (long long)n * Td + t;
+                v = fmaxf(red_sum(red, r, i, Uz1) + __ldg(a.px + row * Z1 + rank * Uz1 + i), 0.f);
+                if (a.s_z1) {
+                    a.s_z1[row * Z1 + rank * Uz1 + i] = v;
+                }
+            }
+            stage[i * R + r] = v;
+        }
+        if (a.s_ctxin) {   // context consumed by this step (for the hoisted W1c gradient)
+            for (int idx = tid; idx < Ue * R; idx += AT_NT) {
+                const int i = idx % Ue, r = idx / Ue, n = grp * R + r;
+                if (n < a.N) a.s_ctxin[((long long)n * Td + t) * E + rank * Ue + i] = ctx_s[(rank * Ue + i) * R + r];
+            }
+        }
+        __syncthreads();
+        push_um(cl, z1_s, stage, rank, Uz1, tid);
+        cl.sync();
+        // ===== P2: z (own Uz units) = relu(z1.W2 + b2) =====
+        {
+            const int ncols = Uz, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = Z1 / KS;
+            mv_acc(acc, a.W2 + rank * Uz + col, Z, z1_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        if (tid < Uz * R) {
+            const int i = tid % Uz, r = tid / Uz, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                v = fmaxf(red_sum(red, r, i, Uz) + __ldg(a.b2 + rank * Uz + i), 0.f);
+                if (a.s_z) a.s_z[((long long)n * Td + t) * Z + rank * Uz + i] = v;
+            }
+            stage[i * R + r] = v;
+        }
+        __syncthreads();
+        push_um(cl, z_s, stage, rank, Uz, tid);
+        cl.sync();
+        // ===== P3: gates r|u (own 2*Uh columns) and the z-part of the candidate =====
+        {
+            const int ncols = 2 * Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            const int gcol = (col < Uh) ? rank * Uh + col : HA + rank * Uh + (col - Uh);
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int kl = ZS / KS;
+            mv_acc(acc, a.Wg + gcol, 2 * HA, z_s, ks * kl, (ks + 1) * kl);
+            kl = HA / KS;
+            mv_acc(acc, a.Wg + (long long)ZS * 2 * HA + gcol, 2 * HA, ha_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        {
+            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = ZS / KS;
+            mv_acc(acc, a.Wc + rank * Uh + col, HA, z_s, ks * kl, (ks + 1) * kl);
+            red_store(red2, tid, acc);
+        }
+        __syncthreads();
+        float rg = 0.f, ug = 0.f, cz = 0.f;
+        {
+            const int unit = rank * Uh + i32;
+            const float sr = red_sum(red, r32, i32, 2 * Uh) + __ldg(a.bg + unit);
+            const float su = red_sum(red, r32, Uh + i32, 2 * Uh) + __ldg(a.bg + HA + unit);
+            cz = red_sum(red2, r32, i32, Uh);
+            rg = sigm_<FAST>(sr); ug = sigm_<FAST>(su);
+            stage[i32 * R + r32] = rg * ha_own;
+        }
+        __syncthreads();
+        push_um(cl, rha_s, stage, rank, Uh, tid);
+        cl.sync();
+        // ===== P4: candidate, new attention-GRU state =====
+        {
+            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = HA / KS;
+            mv_acc(acc, a.Wc + (long long)ZS * HA + rank * Uh + col, HA, rha_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        {
+            const int unit = rank * Uh + i32;
+            const float c = tanh_<FAST>(red_sum(red, r32, i32, Uh) + cz + __ldg(a.bc + unit));
+            const float hn = ug * ha_own + (1.f - ug) * c;
+            if (row_ok32 && a.s_r) {
+                const long long o = row32 * HA + unit;
+                a.s_r[o] = rg; a.s_u[o] = ug; a.s_c[o] = c; a.s_haprev[o] = ha_own; a.s_ha[o] = hn;
+            }
+            ha_own = row_ok32 ? hn : 0.f;
+            stage[i32 * R + r32] = ha_own;
+        }
+        __syncthreads();
+        push_um(cl, ha_s, stage, rank, Uh, tid);
+        cl.sync();
+        // ===== P5: query (own Ua columns) and the ha-part of the concat projection (own Uy columns) =====
+        {
+            const int ncols = Ua + Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = HA / KS;
+            if (col < Ua) mv_acc(acc, a.Wq + rank * Ua + col, A, ha_s, ks * kl, (ks + 1) * kl);
+            else mv_acc(acc, a.Wo + rank * Uy + (col - Ua), Y, ha_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        float yh = 0.f;
+        {
+            float q = red_sum(red, r32, i32, Ua + Uy);
+            if (a.att_type == TACO_ATT_BAH_NORM) q += __ldg(a.att_b + rank * Ua + i32);
+            yh = red_sum(red, r32, Ua + i32, Ua + Uy);
+            if (row_ok32 && a.s_q) a.s_q[row32 * A + rank * Ua + i32] = q;
+            stage[r32 * Ua + i32] = q;
+        }
+        __syncthreads();
+        push_rm(cl, q_rm, A, stage, rank, Ua, tid);
+        cl.sync();
+        // ===== P6: scores of the own memory slice: e[r][j] = sum_u v_u tanh(keys[n,j,u] + q[r,u]) =====
+        for (int p = warp; p < R * TJ; p += AT_NT / 32) {
+            const int r = p % R, jj = p / R, j = rank * TJ + jj, n = grp * R + r;
+            float s = 0.f;
+            if (j < Ti && n < a.N) {
+                const float* kp = a.keys + ((long long)n * Ti + j) * A;
+                for (int u = lane; u < A; u += 32) s = fmaf(v_s[u], tanh_<FAST>(__ldg(kp + u) + q_rm[r * A + u]), s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) stage[r * TJ + jj] = s + score_bias;
+        }
+        __syncthreads();
+        push_rm(cl, e_s, Tip, stage, rank, TJ, tid);
+        cl.sync();
+        // ===== P7: alignments (every CTA, warp r = row r), then context (own Ue units) =====
+        {
+            const int r = warp, n = grp * R + r;
+            const int CH = (Tip + 31) / 32;
+            const int j0 = lane * CH, j1 = min(j0 + CH, Ti);
+            float* er = e_s + r * Tip; float* ar = a_s + r * Tip; float* pr = p_s + r * Tip; float* cr = cp_s + r * Tip;
+            if (a.manual) {
+                for (int j = lane; j < Ti; j += 32) ar[j] = (n < a.N) ? a.manual[((long long)n * Td + t) * Ti + j] : 0.f;
+            } else if (a.att_type == TACO_ATT_BAH_MON) {
+                // p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1))
+                float ls = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float p = sigm_<FAST>(er[j]);
+                    pr[j] = p;
+                    ls += logf(fminf(fmaxf(1.f - p, FLT_MIN), 1.f));
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;   // exclusive prefix of this lane's chunk
+                float ws = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float cp = expf(run);
+                    cr[j] = cp;
+                    run += logf(fminf(fmaxf(1.f - pr[j], FLT_MIN), 1.f));
+                    ws += ar[j] / fminf(fmaxf(cp, 1e-10f), 1.f);
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+                for (int j = j0; j < j1; j++) {
+                    run2 += ar[j] / fminf(fmaxf(cr[j], 1e-10f), 1.f);
+                    ar[j] = pr[j] * cr[j] * run2;      // in place: a_prev[j] is not needed past this point
+                }
+            } else {   // softmax over the Ti memory positions (no masking: tacotron.py:133-134 passes no lengths)
+                float mx = -INFINITY;
+                for (int j = lane; j < Ti; j += 32) mx = fmaxf(mx, er[j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float sm = 0.f;
+                for (int j = lane; j < Ti; j += 32) { float ex = expf(er[j] - mx); pr[j] = ex; sm += ex; }
+                sm = warp_sum(sm);
+                for (int j = lane; j < Ti; j += 32) ar[j] = pr[j] / sm;
+            }
+            __syncwarp();
+            if (rank == 0 && n < a.N) {
+                for (int j = lane; j < Ti; j += 32) {
+                    const float av = ar[j];
+                    a.align[((long long)n * Ti + j) * Td + t] = av;
+                    if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = er[j]; }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int unit = rank * Ue + i32;
+            float cx = 0.f;
+            if (row_ok32) {
+                const float* mp = a.memory + (long long)n32 * Ti * E + unit;
+                const float* ar = a_s + r32 * Tip;
+#pragma unroll 4
+                for (int j = 0; j < Ti; j++) cx = fmaf(ar[j], __ldg(mp + (long long)j * E), cx);
+                if (a.s_ctx) a.s_ctx[row32 * E + unit] = cx;
+            }
+            stage[i32 * R + r32] = cx;
+        }
+        __syncthreads();
+        push_um(cl, ctx_s, stage, rank, Ue, tid);
+        cl.sync();
+        // ===== P8: y0 (own Uy columns) = yh + ctx.Wo_c (+ spk.Wo_s) + bo =====
+        {
+            const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int kl = E / KS;
+            mv_acc(acc, a.Wo + (long long)HA * Y + rank * Uy + col, Y, ctx_s, ks * kl, (ks + 1) * kl);
+            if (SPK > 0) {
+                kl = SPK / KS;
+                if (kl > 0) mv_acc(acc, a.Wo + (long long)(HA + E) * Y + rank * Uy + col, Y, z_s + Z * R, ks * kl, (ks + 1) * kl);
+                else if (ks == 0) mv_acc(acc, a.Wo + (long long)(HA + E) * Y + rank * Uy + col, Y, z_s + Z * R, 0, SPK);
+            }
+            red_store(red2, tid, acc);
+        }
+        __syncthreads();
+        if (row_ok32) a.y0[row32 * Y + rank * Uy + i32] = yh + red_sum(red2, r32, i32, Uy) + __ldg(a.bo + rank * Uy + i32);
+        // no barrier: the next step's P1 reads ctx_s (stable) and writes `red`, not `red2`
+    }
+    if (a.ha_final && row_ok32) a.ha_final[(long long)n32 * HA + rank * Uh + i32] = ha_own;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BPTT.  Transposed weight copies (W^T, packed once per step by the host side) let every matvec here use the same
+// coalesced "lanes over output columns" form as the forward pass.
+template <bool FAST>
+__global__ void __launch_bounds__(AT_NT, 1) att_bwd_kernel(const AttArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int grp = blockIdx.x / AT_C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = AT_R;
+    const int E = a.E, A = a.A, HA = a.HA, Z1 = a.Z1, Z = a.Z, SPK = a.SPK, Y = a.Y, Ti = a.Ti, Td = a.Td;
+    const int ZS = Z + SPK, KIN = ZS + HA;     // attention-GRU input width
+    const int TJ = (Ti + AT_C - 1) / AT_C, Tip = TJ * AT_C;
+    const int Uz1 = Z1 / AT_C, Uz = Z / AT_C, Uh = HA / AT_C, Ua = A / AT_C, Ue = E / AT_C;
+
+    extern __shared__ __align__(16) float smem[];
+    float* dy_s = smem;                     // [Y][R]    dy0[t]
+    float* gq_s = dy_s + Y * R;             // [A][R]
+    float* dz1p_s = gq_s + A * R;           // [Z1][R]
+    float* dzp_s = dz1p_s + Z1 * R;         // [Z][R]
+    float* dcp_s = dzp_s + Z * R;           // [HA][R]
+    float* dg_s = dcp_s + HA * R;           // [2HA][R]
+    float* dctx_rm = dg_s + 2 * HA * R;     // [R][E]
+    float* da_s = dctx_rm + R * E;          // [R][Tip]  grad wrt a_t through the context, gathered over the cluster
+    float* dac_s = da_s + R * Tip;          // [R][Tip]  grad wrt a_t carried from step t+1's recurrence
+    float* ge_s = dac_s + R * Tip;          // [R][Tip]  grad wrt the scores
+    float* p_s = ge_s + R * Tip;            // [R][Tip]  scratch rows of the monotonic backward
+    float* cp_s = p_s + R * Tip;
+    float* s_s = cp_s + R * Tip;
+    float* t1_s = s_s + R * Tip;
+    float* t2_s = t1_s + R * Tip;
+    float* red = t2_s + R * Tip;            // [R][NT]
+    float* red2 = red + R * AT_NT;
+    float* stage = red2 + R * AT_NT;        // [1024]
+    float* v_s = stage + 1024;              // [A]
+
+    if (a.att_type == TACO_ATT_BAH_NORM) {
+        float ss = 0.f;
+        for (int u = 0; u < A; u++) ss += a.v[u] * a.v[u];
+        const float sc = a.att_g[0] * rsqrtf(ss);
+        for (int u = tid; u < A; u += AT_NT) v_s[u] = a.v[u] * sc;
+    } else {
+        for (int u = tid; u < A; u += AT_NT) v_s[u] = a.v[u];
+    }
+    for (int idx = tid; idx < R * Tip; idx += AT_NT) { dac_s[idx] = 0.f; da_s[idx] = 0.f; ge_s[idx] = 0.f; }
+    const int i32 = tid % 32, r32 = tid / 32;
+    const int n32 = grp * R + r32;
+    const bool row_ok32 = n32 < a.N;
+    float dha_carry = 0.f;     // grad wrt ha_t arriving from step t+1 (own unit)
+    float dctx_carry = 0.f;    // grad wrt ctx_t arriving from step t+1's prenet (own unit)
+    float gbias_acc = 0.f;     // score-bias gradient (warp-row partial, rank 0 only)
+    __syncthreads();
+    cl.sync();
+
+    for (int t = Td - 1; t >= 0; t--) {
+        const long long row32 = (long long)n32 * Td + t;
+        // load dy0[t] of the cluster's rows: dy_s[k][r]
+        for (int idx = tid; idx < Y * R; idx += AT_NT) {
+            const int k = idx % Y, r = idx / Y, n = grp * R + r;
+            dy_s[k * R + r] = (n < a.N) ? __ldg(a.dy0 + ((long long)n * Td + t) * Y + k) : 0.f;
+        }
+        __syncthreads();
+        // ===== Bp1: dha += dy0.Wo_h^T (own Uh), dctx = carry + dy0.Wo_c^T (own Ue) =====
+        {
+            const int ncols = Uh + Ue, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = Y / KS;
+            const int gcol = (col < Uh) ? rank * Uh + col : HA + rank * Ue + (col - Uh);
+            mv_acc(acc, a.WoT + gcol, HA + E + SPK, dy_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        float dha = dha_carry + red_sum(red, r32, i32, Uh + Ue);
+        {
+            const float dctx = dctx_carry + red_sum(red, r32, Uh + i32, Uh + Ue);
+            if (row_ok32) a.d_ctx[row32 * E + rank * Ue + i32] = dctx;
+            stage[r32 * Ue + i32] = row_ok32 ? dctx : 0.f;
+        }
+        __syncthreads();
+        push_rm(cl, dctx_rm, E, stage, rank, Ue, tid);
+        cl.sync();
+        // ===== Bp2: da[r][own j] = sum_u dctx[r,u] memory[n,j,u] =====
+        for (int p = warp; p < R * TJ; p += AT_NT / 32) {
+            const int r = p % R, jj = p / R, j = rank * TJ + jj, n = grp * R + r;
+            float s = 0.f;
+            if (j < Ti && n < a.N) {
+                const float* mp = a.memory + ((long long)n * Ti + j) * E;
+                for (int u = lane; u < E; u += 32) s = fmaf(dctx_rm[r * E + u], __ldg(mp + u), s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) stage[r * TJ + jj] = s;
+        }
+        __syncthreads();
+        push_rm(cl, da_s, Tip, stage, rank, TJ, tid);
+        cl.sync();
+        // ===== Bp3: attention-probability backward (every CTA; warp r = row r).  SURVEY.md Appendix C =====
+        {
+            const int r = warp, n = grp * R + r;
+            const int CH = (Tip + 31) / 32;
+            const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
+            float* ga = da_s + r * Tip; float* gc = dac_s + r * Tip; float* ge = ge_s + r * Tip;
+            float* pr = p_s + r * Tip; float* cr = cp_s + r * Tip; float* sr = s_s + r * Tip;
+            float* t1 = t1_s + r * Tip; float* t2 = t2_s + r * Tip;
+            const bool ok = n < a.N;
+            if (a.manual || !ok) {
+                for (int j = lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+            } else if (a.att_type == TACO_ATT_BAH_MON) {
+                const float* e_row = a.s_e + ((long long)n * Td + t) * Ti;
+                const float* ap_row = (t > 0) ? a.s_a + ((long long)n * Td + (t - 1)) * Ti : nullptr;
+                // forward recompute: p, l=log(clip(1-p)), L=cumsum_excl(l), cp=exp(L), w=ap/clip(cp), s=cumsum(w)
+                float ls = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float p = sigm_<FAST>(e_row[j]);
+                    pr[j] = p;
+                    ls += logf(fminf(fmaxf(1.f - p, FLT_MIN), 1.f));
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float ws = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float cp = expf(run);
+                    cr[j] = cp;
+                    run += logf(fminf(fmaxf(1.f - pr[j], FLT_MIN), 1.f));
+                    const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                    ws += ap / fminf(fmaxf(cp, 1e-10f), 1.f);
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+                float gs_loc = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                    run2 += ap / fminf(fmaxf(cr[j], 1e-10f), 1.f);
+                    sr[j] = run2;
+                    const float gs = (ga[j] + gc[j]) * pr[j] * cr[j];     // grad wrt s_j
+                    t1[j] = gs;
+                    gs_loc += gs;
+                }
+                float suf = gs_loc;    // -> sum over lanes strictly above
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+                suf -= gs_loc;
+                float gL_loc = 0.f;
+                {
+                    float acc = suf;
+                    for (int j = j1 - 1; j >= j0; j--) {
+                        acc += t1[j];                                   // gw_j = sum_{i>=j} gs_i
+                        const float g = ga[j] + gc[j];
+                        const float p = pr[j], cp = cr[j], sj = sr[j];
+                        const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                        const float d = fminf(fmaxf(cp, 1e-10f), 1.f);
+                        float gcp = g * p * sj;
+                        if (cp >= 1e-10f && cp <= 1.f) gcp -= acc * ap / (d * d);
+                        const float gL = gcp * cp;
+                        t2[j] = gL;
+                        gL_loc += gL;
+                        ge[j] = g * cp * sj;                            // direct part of grad wrt p_j
+                        gc[j] = acc / d;                                // grad wrt a_{t-1,j}, carried to the next iteration
+                    }
+                }
+                float sufL = gL_loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_down_sync(0xffffffffu, sufL, o); if (lane + o < 32) sufL += v; }
+                sufL -= gL_loc;
+                float gb = 0.f;
+                {
+                    float acc = sufL;                                   // gl_j = sum_{i>j} gL_i
+                    for (int j = j1 - 1; j >= j0; j--) {
+                        const float p = pr[j], omp = 1.f - p;
+                        float gp = ge[j];
+                        if (omp >= FLT_MIN && omp <= 1.f) gp -= acc / fminf(fmaxf(omp, FLT_MIN), 1.f);
+                        acc += t2[j];
+                        const float gev = gp * p * (1.f - p);
+                        ge[j] = gev;
+                        gb += gev;
+                    }
+                }
+                for (int j = Ti + lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+                gb = warp_sum(gb);
+                if (rank == 0 && lane == 0) gbias_acc += gb;
+            } else {
+                // softmax: ge = a * (g - sum a*g); nothing is carried (a_prev does not enter)
+                const float* a_row = a.s_a + ((long long)n * Td + t) * Ti;
+                float dot = 0.f;
+                for (int j = lane; j < Ti; j += 32) dot += a_row[j] * ga[j];
+                dot = warp_sum(dot);
+                for (int j = lane; j < Tip; j += 32) { ge[j] = (j < Ti) ? a_row[j] * (ga[j] - dot) : 0.f; gc[j] = 0.f; }
+            }
+            __syncwarp();
+            if (rank == 0 && ok && a.d_ge)
+                for (int j = lane; j < Ti; j += 32) a.d_ge[((long long)n * Td + t) * Ti + j] = ge[j];
+        }
+        __syncthreads();
+        // ===== Bp4: gq (own Ua units) = v_u * sum_j ge[r][j] * (1 - tanh^2(keys[n,j,u] + q[r,u])) =====
+        {
+            const int unit = rank * Ua + i32;
+            float gq = 0.f;
+            if (row_ok32 && !a.manual) {
+                const float q = a.s_q[row32 * A + unit];
+                const float* kp = a.keys + (long long)n32 * Ti * A + unit;
+                const float* ger = ge_s + r32 * Tip;
+                float acc = 0.f;
+#pragma unroll 2
+                for (int j = 0; j < Ti; j++) {
+                    const float th = tanh_<FAST>(__ldg(kp + (long long)j * A) + q);
+                    acc = fmaf(ger[j], 1.f - th * th, acc);
+                }
+                gq = acc * v_s[unit];
+            }
+            if (row_ok32 && a.d_gq) a.d_gq[row32 * A + unit] = gq;
+            stage[i32 * R + r32] = gq;
+        }
+        __syncthreads();
+        push_um(cl, gq_s, stage, rank, Ua, tid);
+        cl.sync();
+        // ===== Bp5: dha += gq.Wq^T; GRU cell backward (elementwise part) =====
+        {
+            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = A / KS;
+            mv_acc(acc, a.WqT + rank * Uh + col, HA, gq_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        float rg = 0.f, ug = 0.f, cc = 0.f, hp = 0.f, du_pre = 0.f, dc_pre = 0.f;
+        {
+            dha += red_sum(red, r32, i32, Uh);
+            if (row_ok32) {
+                const long long o = row32 * HA + rank * Uh + i32;
+                rg = a.s_r[o]; ug = a.s_u[o]; cc = a.s_c[o]; hp = a.s_haprev[o];
+                du_pre = dha * (hp - cc) * ug * (1.f - ug);
+                dc_pre = dha * (1.f - ug) * (1.f - cc * cc);
+            }
+            stage[i32 * R + r32] = dc_pre;
+        }
+        __syncthreads();
+        push_um(cl, dcp_s, stage, rank, Uh, tid);
+        cl.sync();
+        // ===== Bp6: d(r*h) (own Uh) = dc_pre . Wc_h^T =====
+        {
+            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = HA / KS;
+            mv_acc(acc, a.WcT + ZS + rank * Uh + col, KIN, dcp_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        float d_rh = 0.f, dr_pre = 0.f;
+        {
+            d_rh = red_sum(red, r32, i32, Uh);
+            if (row_ok32) dr_pre = d_rh * hp * rg * (1.f - rg);
+            stage[i32 * R + r32] = dr_pre;
+            stage[256 + i32 * R + r32] = du_pre;
+        }
+        __syncthreads();
+        push_um(cl, dg_s, stage, rank, Uh, tid);
+        push_um(cl, dg_s + HA * R, stage + 256, rank, Uh, tid);
+        cl.sync();
+        // ===== Bp7: dha_prev (own Uh) and dz (own Uz) =====
+        {
+            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = 2 * HA / KS;
+            mv_acc(acc, a.WgT + ZS + rank * Uh + col, KIN, dg_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        {
+            const int ncols = Uz, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int kl = 2 * HA / KS;
+            mv_acc(acc, a.WgT + rank * Uz + col, KIN, dg_s, ks * kl, (ks + 1) * kl);
+            kl = HA / KS;
+            mv_acc(acc, a.WcT + rank * Uz + col, KIN, dcp_s, ks * kl, (ks + 1) * kl);
+            red_store(red2, tid, acc);
+        }
+        __syncthreads();
+        if (row_ok32) {
+            dha_carry = dha * ug + d_rh * rg + red_sum(red, r32, i32, Uh);
+            float* g = a.d_G + row32 * 3 * HA + rank * Uh + i32;
+            g[0] = dr_pre; g[HA] = du_pre; g[2 * HA] = dc_pre;
+            a.s_r[row32 * HA + rank * Uh + i32] = rg * hp;      // operand of the candidate-weight gradient GEMM
+        }
+        if (tid < Uz * R) {
+            const int i = tid % Uz, r = tid / Uz, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                const long long row = (long long)n * Td + t;
+                const float z = a.s_z[row * Z + rank * Uz + i];
+                v = (z > 0.f) ? red_sum(red2, r, i, Uz) : 0.f;
+                a.d_zp[row * Z + rank * Uz + i] = v;
+            }
+            stage[i * R + r] = v;
+        }
+        __syncthreads();
+        push_um(cl, dzp_s, stage, rank, Uz, tid);
+        cl.sync();
+        // ===== Bp8: dz1 (own Uz1) = dz_pre . W2^T, relu' =====
+        {
+            const int ncols = Uz1, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = Z / KS;
+            mv_acc(acc, a.W2T + rank * Uz1 + col, Z1, dzp_s, ks * kl, (ks + 1) * kl);
+            red_store(red, tid, acc);
+        }
+        __syncthreads();
+        if (tid < Uz1 * R) {
+            const int i = tid % Uz1, r = tid / Uz1, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                const long long row = (long long)n * Td + t;
+                const float z1 = a.s_z1[row * Z1 + rank * Uz1 + i];
+                v = (z1 > 0.f) ? red_sum(red, r, i, Uz1) : 0.f;
+                a.d_z1p[row * Z1 + rank * Uz1 + i] = v;
+            }
+            stage[i * R + r] = v;
+        }
+        __syncthreads();
+        push_um(cl, dz1p_s, stage, rank, Uz1, tid);
+        cl.sync();
+        // ===== Bp9: grad wrt ctx_{t-1} (own Ue) = dz1_pre . W1c^T =====
+        {
+            const int ncols = Ue, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kl = Z1 / KS;
+            mv_acc(acc, a.W1cT + rank * Ue + col, E, dz1p_s, ks * kl, (ks + 1) * kl);
+            red_store(red2, tid, acc);
+        }
+        __syncthreads();
+        dctx_carry = red_sum(red2, r32, i32, Ue);
+        __syncthreads();   // red2/stage/dy_s are rewritten at the top of the next iteration
+    }
+    if (a.d_ha0 && row_ok32) a.d_ha0[(long long)n32 * HA + rank * Uh + i32] = dha_carry;
+    if (rank == 0 && lane == 0 && a.d_score_bias && a.att_type == TACO_ATT_BAH_MON) atomicAdd(a.d_score_bias, gbias_acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Key / v gradients, fully parallel over (n, j) (not part of the serial chain):
+//   dkeys[n,j,u] = v_u * sum_t ge[n,t,j] * (1 - th^2),  gv[u] += sum_{n,t,j} ge * th,  th = tanh(keys[n,j,u] + q[n,t,u])
+constexpr int KB_J = 8;   // memory positions per block
+template <bool FAST>
+__global__ void att_keys_bwd_kernel(const float* __restrict__ keys, const float* __restrict__ q, const float* __restrict__ ge,
+                                    const float* __restrict__ v_eff, float* __restrict__ dkeys, float* __restrict__ gv,
+                                    int N, int Ti, int Td, int A) {
+    const int chunks = (Ti + KB_J - 1) / KB_J;
+    const int n = blockIdx.x / chunks, jc = blockIdx.x % chunks;
+    for (int u = threadIdx.x; u < A; u += blockDim.x) {
+        float accv = 0.f;
+        const float vu = v_eff[u];
+        for (int j = jc * KB_J; j < min(Ti, (jc + 1) * KB_J); j++) {
+            const float k = keys[((long long)n * Ti + j) * A + u];
+            float acc = 0.f;
+            for (int t = 0; t < Td; t++) {
+                const float g = __ldg(ge + ((long long)n * Td + t) * Ti + j);
+                const float th = tanh_<FAST>(k + __ldg(q + ((long long)n * Td + t) * A + u));
+                acc = fmaf(g, 1.f - th * th, acc);
+                accv = fmaf(g, th, accv);
+            }
+            dkeys[((long long)n * Ti + j) * A + u] = acc * vu;
+        }
+        atomicAdd(gv + u, accv);
+    }
+}
+
+static int att_check(const AttArgs& a) {
+    TACO_REQUIRE(a.N > 0 && a.Ti > 0 && a.Td > 0, TACO_ESHAPE, "attention: empty shape");
+    TACO_REQUIRE(a.E % 256 == 0 || a.E == 256, TACO_ESHAPE, "attention: memory width %d unsupported", a.E);
+    TACO_REQUIRE(a.E == 256 && a.A == 256 && a.HA == 256 && a.Z1 == 256 && a.Z == 128 && a.Y == 256, TACO_ESHAPE,
+                 "attention kernel instantiated for E=A=HA=Z1=Y=256, Z=128 (got %d %d %d %d %d %d)", a.E, a.A, a.HA, a.Z1, a.Y, a.Z);
+    TACO_REQUIRE(a.SPK == 0 || a.SPK == 16, TACO_ESHAPE, "attention: speaker width %d unsupported", a.SPK);
+    TACO_REQUIRE(a.Ti <= 1024, TACO_ESHAPE, "attention: T_in %d too long", a.Ti);
+    return TACO_OK;
+}
+
+template <typename K>
+static int att_launch(K kern, const AttArgs& a, bool bwd, cudaStream_t s) {
+    const int TJ = (a.Ti + AT_C - 1) / AT_C, Tip = TJ * AT_C;
+    const size_t smem = (bwd ? att_bwd_smem_floats(a, Tip) : att_fwd_smem_floats(a, Tip)) * sizeof(float);
+    TACO_REQUIRE(smem <= 227 * 1024, TACO_ESHAPE, "attention: shared memory %zu exceeds 227 KB", smem);
+    TACO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(AT_C * cdiv(a.N, AT_R));
+    cfg.blockDim = dim3(AT_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = AT_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    g_launch_count++;
+    return TACO_OK;
+}
+
+int launch_att_fwd(const AttArgs& a, cudaStream_t s) {
+    TACO_TRY(att_check(a));
+    return a.fast ? att_launch(att_fwd_kernel<true>, a, false, s) : att_launch(att_fwd_kernel<false>, a, false, s);
+}
+int launch_att_bwd(const AttArgs& a, cudaStream_t s) {
+    TACO_TRY(att_check(a));
+    TACO_REQUIRE(a.dy0 && a.d_G && a.d_zp && a.d_z1p && a.d_ctx && a.s_e && a.s_a && a.s_q, TACO_EINVAL, "attention bwd: missing buffers");
+    return a.fast ? att_launch(att_bwd_kernel<true>, a, true, s) : att_launch(att_bwd_kernel<false>, a, true, s);
+}
+int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,
+                        int N, int Ti, int Td, int A, int fast, cudaStream_t s) {
+    const int blocks = N * ((Ti + KB_J - 1) / KB_J);
+    if (fast) att_keys_bwd_kernel<true><<<blocks, 256, 0, s>>>(keys, q, ge, v_eff, dkeys, gv, N, Ti, Td, A);
+    else att_keys_bwd_kernel<false><<<blocks, 256, 0, s>>>(keys, q, ge, v_eff, dkeys, gv, N, Ti, Td, A);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+}  // namespace taco

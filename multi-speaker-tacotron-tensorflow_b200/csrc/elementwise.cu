@@ -1,0 +1,458 @@
+// HBM-bound glue kernels of the CBHG blocks and the losses.  All operate on row-major
+// [rows, C] fp32 matrices in the zero-padded time layout (rows = N*Tp, row m <-> (n, tp),
+// frame t = tp - PL valid iff 0 <= t < T); C is always a multiple of 4 so accesses are 128-bit.
+//
+// reference semantics restated here:
+//   batch-norm (train: biased batch moments over all N*T frames incl. pad frames; eval: moving
+//   statistics; eps 1e-3, momentum .99)                              models/modules.py:131
+//   max_pooling1d(2, 1, 'same') = max(x[t], x[t+1]), last frame alone  models/modules.py:47-51
+//   residual (+ tiled before_highway)                                  models/modules.py:62-69
+//   highway y = H*T + x*(1-T)                                          models/modules.py:105-120
+//   L1 losses with loss_coeff and the 'prioritize' band                models/tacotron.py:274-302
+#include "common.cuh"
+#include "kernels.h"
+
+namespace taco {
+
+constexpr int EW_THREADS = 256;
+
+static inline int ew_blocks(long long work, int per_block = EW_THREADS, int cap = 148 * 16) {
+    long long b = (work + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (int)(b > cap ? cap : b);
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* p, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+int launch_fill(float* p, long long n, float v, cudaStream_t s) {
+    if (n <= 0) return TACO_OK;
+    fill_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(p, n, v);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// out[m,:] = valid(m) ? table[idx[n, t], :] : 0    (embedding/prenet lookup into the padded layout)
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out,
+                                   int N, int T, int Tp, int PL, int C, int n_rows_table) {
+    const int c4 = C / 4;
+    long long total = (long long)N * Tp * c4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % c4); long long m = i / c4;
+        int tp = (int)(m % Tp), n = (int)(m / Tp), t = tp - PL;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) {
+            int id = idx[n * T + t];
+            id = min(max(id, 0), n_rows_table - 1);
+            v = __ldg(reinterpret_cast<const float4*>(table + (long long)id * C) + c);
+        }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s) {
+    gather_rows_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(table, idx, out, N, T, Tp, PL, C, n_rows_table);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// dtable[idx[n,t], :] += dx[m,:]  over valid rows (backward of the lookup)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ dx, const int* __restrict__ idx, float* __restrict__ dtable,
+                                        int N, int T, int Tp, int PL, int C, int n_rows_table) {
+    long long total = (long long)N * T * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); long long nt = i / C;
+        int t = (int)(nt % T), n = (int)(nt / T);
+        int id = idx[n * T + t];
+        id = min(max(id, 0), n_rows_table - 1);
+        atomicAdd(dtable + (long long)id * C + c, dx[((long long)n * Tp + PL + t) * C + c]);
+    }
+}
+int launch_scatter_add_rows(const float* dx, const int* idx, float* dtable, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s) {
+    scatter_add_rows_kernel<<<ew_blocks((long long)N * T * C), EW_THREADS, 0, s>>>(dx, idx, dtable, N, T, Tp, PL, C, n_rows_table);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// batch-norm statistics -> (mean, rstd, var).  training: biased batch moments; eval: moving statistics.
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ var_out,
+                                   const float* __restrict__ moving_mean, const float* __restrict__ moving_var,
+                                   int C, int training, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (training) {
+        double mu = sum[c] / count;
+        double var = sumsq[c] / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean[c] = (float)mu;
+        var_out[c] = (float)var;
+        rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+        mean[c] = moving_mean[c];
+        var_out[c] = moving_var[c];
+        rstd[c] = rsqrtf(moving_var[c] + eps);
+    }
+}
+int launch_bn_finalize(const double* sum, const double* sumsq, double count, float* mean, float* rstd, float* var,
+                       const float* moving_mean, const float* moving_var, int C, int training, cudaStream_t s) {
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sum, sumsq, count, mean, rstd, var, moving_mean, moving_var, C, training, 1e-3f);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+// moving <- moving*momentum + batch*(1-momentum)   (the UPDATE_OPS of tf.layers.batch_normalization; tacotron.py:332-336)
+__global__ void bn_update_moving_kernel(float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                        const float* __restrict__ mean, const float* __restrict__ var, int C, float momentum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    moving_mean[c] = moving_mean[c] * momentum + mean[c] * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + var[c] * (1.f - momentum);
+}
+int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var, int C, cudaStream_t s) {
+    bn_update_moving_kernel<<<cdiv(C, 128), 128, 0, s>>>(moving_mean, moving_var, mean, var, C, 0.99f);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// BN apply.  mode 0: out = bn(x); mode 1: out = max(bn(x[t]), bn(x[t+1])) (maxpool);
+// optional residual res[m,:] and per-batch-row vector rowvec[n,:] are added after.  Pad rows -> 0.
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ res, const float* __restrict__ rowvec,
+                                float* __restrict__ out, int N, int T, int Tp, int PL, int C, int mode) {
+    const int c4 = C / 4;
+    long long total = (long long)N * Tp * c4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % c4); long long m = i / c4;
+        int tp = (int)(m % Tp), n = (int)(m / Tp), t = tp - PL;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) {
+            float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + cq);
+            float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+            float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
+            float4 b = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+            float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+            o.x = (v.x - mu.x) * rs.x * g.x + b.x; o.y = (v.y - mu.y) * rs.y * g.y + b.y;
+            o.z = (v.z - mu.z) * rs.z * g.z + b.z; o.w = (v.w - mu.w) * rs.w * g.w + b.w;
+            if (mode == 1 && t + 1 < T) {
+                float4 w = __ldg(reinterpret_cast<const float4*>(x) + i + c4);
+                o.x = fmaxf(o.x, (w.x - mu.x) * rs.x * g.x + b.x); o.y = fmaxf(o.y, (w.y - mu.y) * rs.y * g.y + b.y);
+                o.z = fmaxf(o.z, (w.z - mu.z) * rs.z * g.z + b.z); o.w = fmaxf(o.w, (w.w - mu.w) * rs.w * g.w + b.w);
+            }
+            if (res) {
+                float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (rowvec) {
+                float4 r = __ldg(reinterpret_cast<const float4*>(rowvec + (long long)n * C) + cq);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+        }
+        reinterpret_cast<float4*>(out)[i] = o;
+    }
+}
+int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s) {
+    bn_apply_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, N, T, Tp, PL, C, mode);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// BN backward.  dy is either given directly (mode 0) or routed through the max-pool (mode 1):
+//   dy[t] = dp[t]*[b[t] >= b[t+1] or t==T-1] + dp[t-1]*[b[t] > b[t-1]]   (first max wins, as TF's CPU MaxPoolGrad)
+// where b = bn(x).  Pass 1 reduces s1 = sum dy, s2 = sum dy*xhat per channel (these are dbeta, dgamma).
+__device__ __forceinline__ float bn_dy(const float* __restrict__ dyp, const float* __restrict__ x, long long off, int C,
+                                       int t, int T, float mu, float rs, float g, float b, int mode) {
+    if (mode == 0) return dyp[off];
+    float bc = (x[off] - mu) * rs * g + b;
+    float d = 0.f;
+    bool take_right = (t + 1 >= T);
+    if (!take_right) { float bn_ = (x[off + C] - mu) * rs * g + b; take_right = (bc >= bn_); }
+    if (take_right) d += dyp[off];
+    if (t > 0) { float bp = (x[off - C] - mu) * rs * g + b; if (bc > bp) d += dyp[off - C]; }
+    return d;
+}
+
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int N, int T, int Tp, int PL, int C, int mode, int rows_per_block) {
+    // block = (channel tile of blockDim.x channels) x (row slab)
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
+    long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = min(r0 + rows_per_block, (long long)N * T);
+    float s1 = 0.f, s2 = 0.f;
+    for (long long r = r0; r < r1; r++) {
+        int n = (int)(r / T), t = (int)(r % T);
+        long long off = ((long long)n * Tp + PL + t) * C + c;
+        float dy = bn_dy(dyp, x, off, C, t, T, mu, rs, g, b, mode);
+        s1 += dy; s2 += dy * (x[off] - mu) * rs;
+    }
+    atomicAdd(dbeta + c, s1);
+    atomicAdd(dgamma + c, s2);
+}
+
+// Pass 2: dx = gamma*rstd*(dy - s1/M - xhat*s2/M), then relu' (x>0) when the conv had its activation before BN.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                    float* __restrict__ dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask) {
+    long long total = (long long)N * Tp * C;
+    const float invM = 1.0f / ((float)N * (float)T);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); long long m = i / C;
+        int tp = (int)(m % Tp), t = tp - PL;
+        float o = 0.f;
+        if (t >= 0 && t < T) {
+            float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
+            float dy = bn_dy(dyp, x, i, C, t, T, mu, rs, g, b, mode);
+            float xv = x[i];
+            float xh = (xv - mu) * rs;
+            o = g * rs * (dy - dbeta[c] * invM - xh * dgamma[c] * invM);
+            if (relu_mask && !(xv > 0.f)) o = 0.f;
+        }
+        dx[i] = o;
+    }
+}
+int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s) {
+    const int rows_per_block = 64;
+    dim3 grid(cdiv(C, 128), (unsigned)cdiv64((long long)N * T, rows_per_block));
+    bn_bwd_reduce_kernel<<<grid, 128, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, N, T, Tp, PL, C, mode, rows_per_block);
+    TACO_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<<<ew_blocks((long long)N * Tp * C), EW_THREADS, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx,
+                                                                               N, T, Tp, PL, C, mode, relu_mask);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// highway combine: y = H*T + x*(1-T)
+__global__ void highway_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Tg, const float* __restrict__ x,
+                                   float* __restrict__ y, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 h = reinterpret_cast<const float4*>(H)[i], t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
+        float4 o;
+        o.x = h.x * t.x + v.x * (1.f - t.x); o.y = h.y * t.y + v.y * (1.f - t.y);
+        o.z = h.z * t.z + v.z * (1.f - t.z); o.w = h.w * t.w + v.w * (1.f - t.w);
+        reinterpret_cast<float4*>(y)[i] = o;
+    }
+}
+int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s) {
+    highway_fwd_kernel<<<ew_blocks(n / 4), EW_THREADS, 0, s>>>(H, Tg, x, y, n / 4);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+// backward: dHpre = dy*T*[H>0]; dTpre = dy*(H-x)*T*(1-T); dx_direct = dy*(1-T)
+__global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ H, const float* __restrict__ Tg,
+                                   const float* __restrict__ x, float* __restrict__ dHpre, float* __restrict__ dTpre,
+                                   float* __restrict__ dx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d = dy[i], h = H[i], t = Tg[i], v = x[i];
+        dHpre[i] = (h > 0.f) ? d * t : 0.f;
+        dTpre[i] = d * (h - v) * t * (1.f - t);
+        dx[i] = d * (1.f - t);
+    }
+}
+int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHpre, float* dTpre, float* dx,
+                       long long n, cudaStream_t s) {
+    highway_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHpre, dTpre, dx, n);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums: out[c] += sum_m x[m*ld + c]   (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int C, int ld, int rows_per_block) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s = 0.f;
+    for (long long r = r0; r < r1; r++) s += x[r * ld + c];
+    atomicAdd(out + c, s);
+}
+int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s) {
+    const int rows_per_block = 128;
+    dim3 grid(cdiv(C, 128), (unsigned)cdiv64(M, rows_per_block));
+    colsum_kernel<<<grid, 128, 0, s>>>(x, out, M, C, ld, rows_per_block);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// out[n, c] += sum_t x[(n*Tp + PL + t)*C + c]   (gradient of a vector tiled over time)
+__global__ void timesum_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int Tp, int PL, int C) {
+    int n = blockIdx.y;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int t = 0; t < T; t++) s += x[((long long)n * Tp + PL + t) * C + c];
+    out[(long long)n * C + c] += s;
+}
+int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int C, cudaStream_t s) {
+    dim3 grid(cdiv(C, 128), N);
+    timesum_kernel<<<grid, 128, 0, s>>>(x, out, T, Tp, PL, C);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// y[i] += a * x[i]
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s) {
+    if (n <= 0) return TACO_OK;
+    axpy_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(y, x, a, n);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]
+__global__ void copy2d_kernel(float* __restrict__ dst, const float* __restrict__ src, long long rows, int cols, long long ldd, long long lds) {
+    long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / cols; int c = (int)(i % cols);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return TACO_OK;
+    copy2d_kernel<<<ew_blocks(rows * cols), EW_THREADS, 0, s>>>(dst, src, rows, cols, ldd, lds);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// dst[(n*T+t)*C + c] = src[(n*Tp+PL+t)*ld + c]   (valid rows of a padded-layout matrix, dense)
+__global__ void unpad_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int T, int Tp, int PL, int C, long long ld) {
+    long long total = (long long)N * T * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); long long nt = i / C;
+        int t = (int)(nt % T), n = (int)(nt / T);
+        dst[i] = src[((long long)n * Tp + PL + t) * ld + c];
+    }
+}
+int launch_unpad(float* dst, const float* src, int N, int T, int Tp, int PL, int C, long long ld, cudaStream_t s) {
+    unpad_kernel<<<ew_blocks((long long)N * T * C), EW_THREADS, 0, s>>>(dst, src, N, T, Tp, PL, C, ld);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// conv data-gradient operand: Wd[j'][co][ci] = W[k-1-j'][ci][co]   (flip taps, transpose channels)
+__global__ void pack_dgrad_kernel(const float* __restrict__ W, float* __restrict__ Wd, int k, int Cin, int Cout) {
+    long long total = (long long)k * Cin * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ci = (int)(i % Cin); long long r = i / Cin;
+        int co = (int)(r % Cout), jp = (int)(r / Cout);
+        Wd[i] = W[((long long)(k - 1 - jp) * Cin + ci) * Cout + co];
+    }
+}
+int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaStream_t s) {
+    pack_dgrad_kernel<<<ew_blocks((long long)k * Cin * Cout), EW_THREADS, 0, s>>>(W, Wd, k, Cin, Cout);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// L1 loss + gradient.  out/target rows: out row (n,t) at out + (n*out_bs + t*out_ts), target at tgt + (n*T + t)*C.
+// scalars[0] += sum |d|*coeff*w ; scalars[1] += sum |d| (unweighted, all bins) ; scalars[2] += sum |d| over the priority band.
+// grad[(n,t),c] = sign(out - tgt) * coeff[n] * (w_all + w_band*[lo<=c<hi])     (pad rows of grad untouched)
+__global__ void l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
+                               const float* __restrict__ tgt, const float* __restrict__ coeff,
+                               float* __restrict__ grad, long long grad_bs, long long grad_ts,
+                               int N, int T, int C, float w_all, float w_band, int lo, int hi, double* __restrict__ scalars) {
+    long long total = (long long)N * T * C;
+    float acc_w = 0.f, acc_all = 0.f, acc_band = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); long long nt = i / C;
+        int t = (int)(nt % T), n = (int)(nt / T);
+        float o = out[n * out_bs + t * out_ts + c];
+        float d = o - tgt[i];
+        float cf = coeff ? coeff[n] : 1.f;
+        float a = fabsf(d);
+        bool band = (c >= lo && c < hi);
+        float w = w_all + (band ? w_band : 0.f);
+        acc_w += a * cf * w; acc_all += a; if (band) acc_band += a;
+        if (grad) {
+            float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            grad[n * grad_bs + t * grad_ts + c] = sg * cf * w;
+        }
+    }
+    acc_w = warp_sum(acc_w); acc_all = warp_sum(acc_all); acc_band = warp_sum(acc_band);
+    __shared__ float sh[3][EW_THREADS / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = acc_w; sh[1][wid] = acc_all; sh[2][wid] = acc_band; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int w = 0; w < EW_THREADS / 32; w++) s += sh[threadIdx.x][w];
+        atomicAdd(scalars + threadIdx.x, s);
+    }
+}
+int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
+                   float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s) {
+    l1_loss_kernel<<<ew_blocks((long long)N * T * C, EW_THREADS, 148 * 8), EW_THREADS, 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, grad_bs, grad_ts,
+                                                                                         N, T, C, w_all, w_band, lo, hi, scalars);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+}  // namespace taco
+
+namespace taco {
+// dx = (y > 0) ? dy : 0   (ReLU backward on a stored post-activation value)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = (y[i] > 0.f) ? dy[i] : 0.f;
+}
+int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s) {
+    if (n <= 0) return TACO_OK;
+    relu_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(dy, y, dx, n);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// teacher-forcing inputs: x_all[(n*Td+t), :] = t==0 ? 0 : mel_targets[n, t*r-1, :]     (helpers.py:44,66,70-72)
+__global__ void teacher_inputs_kernel(const float* __restrict__ tgt, float* __restrict__ x, int N, int Td, int To, int r, int M) {
+    long long total = (long long)N * Td * M;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % M); long long nt = i / M;
+        int t = (int)(nt % Td), n = (int)(nt / Td);
+        x[i] = (t == 0) ? 0.f : tgt[((long long)n * To + (long long)t * r - 1) * M + c];
+    }
+}
+int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s) {
+    teacher_inputs_kernel<<<ew_blocks((long long)N * Td * M), EW_THREADS, 0, s>>>(tgt, x, N, Td, To, r, M);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+}  // namespace taco
+
+namespace taco {
+// out[c*rows + r] = in[r*cols + c]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int cc = c0 + i;
+        if (r < rows && cc < cols) out[(long long)cc * rows + r] = tile[threadIdx.x][i];
+    }
+}
+int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s) {
+    dim3 grid(cdiv(cols, 32), cdiv(rows, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(in, out, rows, cols);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+}  // namespace taco

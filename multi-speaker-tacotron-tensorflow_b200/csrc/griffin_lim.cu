@@ -1,0 +1,219 @@
+// Griffin-Lim spectrogram inversion on the GPU: cuFFT batched C2R / R2C plans + fused window / overlap-add /
+// reflect-pad framing / phase-normalise kernels, and the inverse pre-emphasis IIR as a chunked scan.
+//   reference: audio/__init__.py:54-56 (inv_spectrogram), :76-84 (_griffin_lim, 60 iterations), :99-106 (_stft/_istft via
+//   librosa 0.5.1: centered, reflect-padded, periodic Hann of win_length zero-padded to n_fft, window-sum-square
+//   normalisation), :118-122 (_stft_parameters), :149 (_db_to_amp), :158-159 (inv_preemphasis), :164-165 (_denormalize).
+// librosa 0.5.x stores conj(FFT) in stft and conjugates again in istft; the loop is self-consistent under either
+// convention, so the kernels use the plain FFT and the caller-supplied initial phase is negated to match.
+#include "common.cuh"
+#include <cufft.h>
+#include <new>
+
+namespace taco {
+
+struct GlState {
+    int n_fft, hop, win, max_frames, device, nbins;
+    cufftHandle c2r = 0, r2c = 0; int planned_T = 0;
+    float* window = nullptr;     // [n_fft] periodic Hann(win) centred in n_fft
+    float* wsum = nullptr;       // [n_fft + hop*(max_frames-1)] sum of squared windows
+    float* mag = nullptr;        // [max_frames, nbins] target magnitudes (S^power)
+    cufftComplex* spec = nullptr;// [max_frames, nbins]
+    float* frames = nullptr;     // [max_frames, n_fft]
+    float* y = nullptr;          // [n_fft + hop*(max_frames-1)] untrimmed signal
+    float* carry = nullptr;      // IIR chunk states
+    size_t bytes = 0;
+};
+
+#define TACO_CHECK_CUFFT(expr)                                                                    \
+    do {                                                                                          \
+        cufftResult _r = (expr);                                                                  \
+        if (_r != CUFFT_SUCCESS) { set_error("%s:%d: %s -> cufft error %d", __FILE__, __LINE__, #expr, (int)_r); return TACO_ECUDA; } \
+    } while (0)
+
+__global__ void gl_window_kernel(float* w, int n_fft, int win) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_fft) return;
+    int lpad = (n_fft - win) / 2;       // librosa.util.pad_center
+    int i = k - lpad;
+    w[k] = (i >= 0 && i < win) ? 0.5f - 0.5f * cospif(2.0f * (float)i / (float)win) : 0.f;   // scipy get_window('hann', fftbins=True)
+}
+__global__ void gl_wsum_kernel(const float* __restrict__ w, float* __restrict__ wsum, int n_fft, int hop, int T, int len) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    float acc = 0.f;
+    int i_hi = min(T - 1, s / hop);
+    for (int i = i_hi; i >= 0; i--) {
+        int k = s - i * hop;
+        if (k >= n_fft) break;
+        acc += w[k] * w[k];
+    }
+    wsum[s] = acc;
+}
+// magnitudes: S = 10^(0.05*(clip(x,0,1)*(-min_db) + min_db + ref_db)); mag = S^power; initial spectrum mag*exp(-2*pi*i*phase)
+__global__ void gl_init_kernel(const float* __restrict__ lin, const float* __restrict__ phase, float* __restrict__ mag,
+                               cufftComplex* __restrict__ spec, long long n, float min_db, float ref_db, float power) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = fminf(fmaxf(lin[i], 0.f), 1.f);
+    float db = x * (-min_db) + min_db + ref_db;
+    float S = powf(10.0f, db * 0.05f);
+    float m = powf(S, power);
+    mag[i] = m;
+    float ph = phase ? -2.0f * phase[i] : 0.f;     // in units of pi; negated (see header comment)
+    float sn, cs; sincospif(ph, &sn, &cs);
+    spec[i] = make_cuFloatComplex(m * cs, m * sn);
+}
+// overlap-add of windowed inverse FFT frames, normalised by the window sum-square
+__global__ void gl_ola_kernel(const float* __restrict__ frames, const float* __restrict__ w, const float* __restrict__ wsum,
+                              float* __restrict__ y, int n_fft, int hop, int T, int len, float inv_nfft, float tiny) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    float acc = 0.f;
+    int i_hi = min(T - 1, s / hop);
+    for (int i = i_hi; i >= 0; i--) {
+        int k = s - i * hop;
+        if (k >= n_fft) break;
+        acc += w[k] * frames[(long long)i * n_fft + k] * inv_nfft;
+    }
+    float ws = wsum[s];
+    y[s] = (ws > tiny) ? acc / ws : acc;
+}
+// windowed frames of the centre-trimmed signal with reflect padding: frame i covers ypad[i*hop : i*hop+n_fft],
+// ypad[j] = reflect(ytrim, j - n_fft/2), ytrim = y[n_fft/2 : n_fft/2 + L]
+__global__ void gl_frame_kernel(const float* __restrict__ y, const float* __restrict__ w, float* __restrict__ frames,
+                                int n_fft, int hop, int T, int L) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * n_fft) return;
+    int k = (int)(idx % n_fft), i = (int)(idx / n_fft);
+    int j = i * hop + k - n_fft / 2;          // index into ytrim
+    if (j < 0) j = -j;                        // numpy 'reflect' (no edge repeat)
+    if (j >= L) j = 2 * (L - 1) - j;
+    j = min(max(j, 0), L - 1);
+    frames[idx] = w[k] * y[n_fft / 2 + j];
+}
+// spec <- mag * spec / |spec|   (angle(0) = 0 -> unit phase 1)
+__global__ void gl_phase_kernel(cufftComplex* __restrict__ spec, const float* __restrict__ mag, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cufftComplex v = spec[i];
+    float a = sqrtf(v.x * v.x + v.y * v.y);
+    float m = mag[i];
+    spec[i] = (a > 0.f) ? make_cuFloatComplex(m * v.x / a, m * v.y / a) : make_cuFloatComplex(m, 0.f);
+}
+// inverse pre-emphasis y[n] = x[n] + a*y[n-1] as a chunked scan (3 passes)
+constexpr int IIR_CHUNK = 256;
+__global__ void iir_local_kernel(const float* __restrict__ x, float* __restrict__ yo, float* __restrict__ carry, int L, float a) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int s0 = c * IIR_CHUNK;
+    if (s0 >= L) return;
+    float st = 0.f;
+    for (int s = s0; s < min(L, s0 + IIR_CHUNK); s++) { st = x[s] + a * st; yo[s] = st; }
+    carry[c] = st;
+}
+__global__ void iir_carry_kernel(float* carry, int nchunks, float apow) {
+    if (blockIdx.x || threadIdx.x) return;
+    float st = 0.f;     // state entering chunk c
+    for (int c = 0; c < nchunks; c++) { float end = carry[c] + apow * st; carry[c] = st; st = end; }
+}
+__global__ void iir_fix_kernel(float* __restrict__ yo, const float* __restrict__ carry, int L, float a) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= L) return;
+    int c = s / IIR_CHUNK;
+    float st = carry[c];
+    if (st != 0.f) yo[s] += st * powf(a, (float)(s - c * IIR_CHUNK + 1));
+}
+
+}  // namespace taco
+
+using namespace taco;
+struct taco_gl_s { GlState st; };
+
+extern "C" {
+
+int taco_gl_create(taco_gl* out, int32_t n_fft, int32_t hop, int32_t win, int32_t max_frames, int32_t device) {
+    TACO_REQUIRE(out && n_fft > 0 && hop > 0 && win > 0 && win <= n_fft && max_frames > 1, TACO_EINVAL, "taco_gl_create: bad arguments");
+    taco_gl_s* h = new (std::nothrow) taco_gl_s();
+    TACO_REQUIRE(h, TACO_ENOMEM, "taco_gl_create: out of host memory");
+    GlState& g = h->st;
+    g.n_fft = n_fft; g.hop = hop; g.win = win; g.max_frames = max_frames; g.device = device; g.nbins = n_fft / 2 + 1;
+    TACO_CHECK_CUDA(cudaSetDevice(device));
+    const size_t len = (size_t)n_fft + (size_t)hop * (max_frames - 1);
+    const size_t nb = (size_t)max_frames * g.nbins;
+    TACO_CHECK_CUDA(cudaMalloc(&g.window, sizeof(float) * n_fft));
+    TACO_CHECK_CUDA(cudaMalloc(&g.wsum, sizeof(float) * len));
+    TACO_CHECK_CUDA(cudaMalloc(&g.mag, sizeof(float) * nb));
+    TACO_CHECK_CUDA(cudaMalloc(&g.spec, sizeof(cufftComplex) * nb));
+    TACO_CHECK_CUDA(cudaMalloc(&g.frames, sizeof(float) * (size_t)max_frames * n_fft));
+    TACO_CHECK_CUDA(cudaMalloc(&g.y, sizeof(float) * len));
+    TACO_CHECK_CUDA(cudaMalloc(&g.carry, sizeof(float) * (len / IIR_CHUNK + 2)));
+    g.bytes = sizeof(float) * (n_fft + 2 * len + nb + (size_t)max_frames * n_fft) + sizeof(cufftComplex) * nb;
+    gl_window_kernel<<<cdiv(n_fft, 256), 256>>>(g.window, n_fft, win);
+    TACO_CHECK_LAUNCH();
+    TACO_CHECK_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return TACO_OK;
+}
+
+int taco_gl_destroy(taco_gl h) {
+    if (!h) return TACO_OK;
+    GlState& g = h->st;
+    if (g.c2r) cufftDestroy(g.c2r);
+    if (g.r2c) cufftDestroy(g.r2c);
+    cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.y); cudaFree(g.carry);
+    delete h;
+    return TACO_OK;
+}
+
+size_t taco_gl_workspace_bytes(taco_gl h) { return h ? h->st.bytes : 0; }
+
+int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* init_phase, int32_t T, int32_t n_iters, float power,
+                            float min_level_db, float ref_level_db, float preemphasis, float* wav_out, void* ws, void* stream) {
+    (void)ws;
+    TACO_REQUIRE(h && linear_spec && wav_out, TACO_EINVAL, "taco_gl_inv_spectrogram: null argument");
+    GlState& g = h->st;
+    TACO_REQUIRE(T > 1 && T <= g.max_frames, TACO_ESHAPE, "taco_gl_inv_spectrogram: T=%d outside (1, %d]", T, g.max_frames);
+    const int L = g.hop * (T - 1);                 // trimmed length
+    TACO_REQUIRE(L > g.n_fft / 2, TACO_ESHAPE, "taco_gl_inv_spectrogram: signal too short for reflect padding");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int len = g.n_fft + L;
+    if (g.planned_T != T) {
+        if (g.c2r) { cufftDestroy(g.c2r); g.c2r = 0; }
+        if (g.r2c) { cufftDestroy(g.r2c); g.r2c = 0; }
+        int n[1] = {g.n_fft};
+        TACO_CHECK_CUFFT(cufftPlanMany(&g.c2r, 1, n, nullptr, 1, g.nbins, nullptr, 1, g.n_fft, CUFFT_C2R, T));
+        TACO_CHECK_CUFFT(cufftPlanMany(&g.r2c, 1, n, nullptr, 1, g.n_fft, nullptr, 1, g.nbins, CUFFT_R2C, T));
+        g.planned_T = T;
+        gl_wsum_kernel<<<cdiv(len, 256), 256, 0, s>>>(g.window, g.wsum, g.n_fft, g.hop, T, len);
+        TACO_CHECK_LAUNCH();
+    }
+    TACO_CHECK_CUFFT(cufftSetStream(g.c2r, s));
+    TACO_CHECK_CUFFT(cufftSetStream(g.r2c, s));
+    const long long nb = (long long)T * g.nbins;
+    gl_init_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, s>>>(linear_spec, init_phase, g.mag, g.spec, nb, min_level_db, ref_level_db, power);
+    TACO_CHECK_LAUNCH();
+    const float inv_nfft = 1.0f / (float)g.n_fft;
+    for (int it = 0; it <= n_iters; it++) {
+        TACO_CHECK_CUFFT(cufftExecC2R(g.c2r, g.spec, g.frames));
+        g_launch_count++;
+        gl_ola_kernel<<<cdiv(len, 256), 256, 0, s>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
+        TACO_CHECK_LAUNCH();
+        if (it == n_iters) break;
+        gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, s>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
+        TACO_CHECK_LAUNCH();
+        TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
+        g_launch_count++;
+        gl_phase_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, s>>>(g.spec, g.mag, nb);
+        TACO_CHECK_LAUNCH();
+    }
+    // inverse pre-emphasis on the trimmed signal
+    const int nchunks = cdiv(L, IIR_CHUNK);
+    iir_local_kernel<<<cdiv(nchunks, 128), 128, 0, s>>>(g.y + g.n_fft / 2, wav_out, g.carry, L, preemphasis);
+    TACO_CHECK_LAUNCH();
+    iir_carry_kernel<<<1, 32, 0, s>>>(g.carry, nchunks, powf(preemphasis, (float)IIR_CHUNK));
+    TACO_CHECK_LAUNCH();
+    iir_fix_kernel<<<cdiv(L, 256), 256, 0, s>>>(wav_out, g.carry, L, preemphasis);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Internal launcher prototypes (host side).  All launchers enqueue on `s` and return TACO_* codes.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/taco_capi.h"
+
+namespace taco {
+
+// gemm_simt.cu / gemm_tc.cu
+int launch_gemm_simt(const taco_gemm_desc* d, int n, cudaStream_t s);
+int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s);
+
+// elementwise.cu
+int launch_fill(float* p, long long n, float v, cudaStream_t s);
+int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s);
+int launch_scatter_add_rows(const float* dx, const int* idx, float* dtable, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s);
+int launch_bn_finalize(const double* sum, const double* sumsq, double count, float* mean, float* rstd, float* var,
+                       const float* moving_mean, const float* moving_var, int C, int training, cudaStream_t s);
+int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var, int C, cudaStream_t s);
+int launch_unpad(float* dst, const float* src, int N, int T, int Tp, int PL, int C, long long ld, cudaStream_t s);
+int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaStream_t s);
+int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s);
+int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s);
+int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s);
+int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHpre, float* dTpre, float* dx,
+                       long long n, cudaStream_t s);
+int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
+int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
+int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s);
+int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int C, cudaStream_t s);
+int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s);
+int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
+int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
+                   float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s);
+
+// gru.cu — cluster-persistent GRU recurrences (TF GRUCell semantics)
+struct GruArgs {
+    int N, T, H, ndir;
+    // x-side pre-activations (biases included) from the hoisted GEMM: row(n,t) = n*gx_rs_n + t + gx_row0;
+    // direction d uses columns [d*3H, (d+1)*3H) as r | u | c.
+    const float* gx; long long gx_ld; long long gx_rs_n; long long gx_row0;
+    const float* Wg[2];      // recurrent gate weights  [H, 2H] row-major (= gates_kernel + Cin*2H)
+    const float* Wc[2];      // recurrent cand weights  [H, H]  row-major (= cand_kernel + Cin*H)
+    const float* h0;         // [N, ndir*H] or NULL
+    const int* lengths;      // [N] or NULL (=> T)
+    const float* res; long long res_ld;   // optional residual input added to the output (ResidualWrapper), row n*T+t
+    float* out; long long out_ld;         // out[(n*T+t)*out_ld + d*H + unit]   (must be pre-zeroed when lengths != NULL)
+    // stash for backward, each [ndir][N][T][H]; NULL in inference
+    float* st_r; float* st_u; float* st_c; float* st_hprev;
+    // backward only
+    const float* dout; long long dout_ld; // grad wrt out, same indexing as out
+    float* dgx;                           // grad wrt gx, same indexing as gx (pre-zeroed)
+    float* dh0;                           // [N, ndir*H] or NULL
+    float* hfinal;                        // forward: final state [N, ndir*H] or NULL
+};
+int launch_gru_fwd(const GruArgs& a, cudaStream_t s);
+int launch_gru_bwd(const GruArgs& a, cudaStream_t s);
+
+// attention.cu — cluster-persistent attention recurrence of the decoder
+struct AttArgs {
+    int N, Ti, Td;
+    int E, A, HA, Z1, Z, SPK, Y;       // memory width, attention size, attention-GRU size, prenet sizes, speaker width, dec rnn size
+    int att_type, fast;
+    const float* px;        // [N*Td, Z1] x-side of prenet layer 1 (bias included)
+    const float* memory;    // [N*Ti, E]
+    const float* keys;      // [N*Ti, A]
+    const float* spk;       // [N, SPK] or NULL
+    const float* ha0;       // [N, HA] or NULL
+    const float* manual;    // [N, Td, Ti] or NULL
+    const float *W1c, *W2, *b2, *Wg, *bg, *Wc, *bc, *Wq, *v, *score_bias, *att_g, *att_b, *Wo, *bo;
+    float* y0;              // [N*Td, Y]
+    float* align;           // [N, Ti, Td]
+    float* ha_final;        // [N, HA] or NULL
+    // stash (training)
+    float *s_z1, *s_z, *s_r, *s_u, *s_c, *s_haprev, *s_ha, *s_q, *s_ctxin, *s_ctx, *s_e, *s_a;
+    // backward
+    const float* dy0;       // [N*Td, Y]
+    const float *W1cT, *W2T, *WgT, *WcT, *WqT, *WoT;   // transposed weights
+    float *d_G, *d_zp, *d_z1p, *d_ctx, *d_gq, *d_ge, *d_ha0, *d_score_bias;
+};
+int launch_att_fwd(const AttArgs& a, cudaStream_t s);
+int launch_att_bwd(const AttArgs& a, cudaStream_t s);
+int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,
+                        int N, int Ti, int Td, int A, int fast, cudaStream_t s);
+int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
+
+// optim.cu
+int launch_sqnorm(const float* g, long long n, double* out, cudaStream_t s);
+int launch_adam_clip(float* p, float* m, float* v, const float* g, long long n, const double* sqnorm, float gscale,
+                     float clip_norm, float lr_t, float b1, float b2, float eps, float lr, float* norm_out, cudaStream_t s);
+
+}  // namespace taco

@@ -1,0 +1,501 @@
+// C-ABI entry points, workspace planner and the top-level forward / backward / optimizer sequencing.
+// reference: models/tacotron.py:21-336 (initialize, add_loss, add_optimizer); see include/taco_capi.h.
+#include "model.h"
+#include <cmath>
+#include <cstring>
+
+namespace taco {
+
+static thread_local std::string g_err;
+int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s) {
+    (void)precision;   // TACO_PREC_BF16 tensor-core path is routed here once built; fp32 SIMT is exact
+    return launch_gemm_simt(d, n_problems, s);
+}
+
+// ---- Model helpers ------------------------------------------------------------------------------------
+int Model::lookup(const std::string& name, Entry& e) const {
+    auto it = table.find(name);
+    if (it == table.end()) { set_error("parameter '%s' is not bound", name.c_str()); return TACO_EINVAL; }
+    e = it->second;
+    return TACO_OK;
+}
+float* Model::P(const std::string& name) const {
+    auto it = table.find(name);
+    if (it == table.end()) { set_error("parameter '%s' is not bound", name.c_str()); return nullptr; }
+    return (it->second.trainable ? params : bn_state) + it->second.offset;
+}
+float* Model::G(const std::string& name) const {
+    auto it = table.find(name);
+    if (it == table.end() || !it->second.trainable) { set_error("gradient slot '%s' missing", name.c_str()); return nullptr; }
+    return grads + it->second.offset;
+}
+float* Model::W(const std::string& name) const {
+    auto it = regions.find(name);
+    if (it == regions.end()) { set_error("workspace region '%s' missing", name.c_str()); return nullptr; }
+    return reinterpret_cast<float*>(ws + it->second.offset);
+}
+double* Model::Wd(const std::string& name) const { return reinterpret_cast<double*>(W(name)); }
+
+static CbhgGeom make_geom(const std::string& prefix, int N, int T, int Cin, int Kb, int Cb, int P1, int P2, int pw, int depth, int H) {
+    CbhgGeom g;
+    g.prefix = prefix; g.N = N; g.T = T; g.Kb = Kb; g.PL = (Kb - 1) / 2; g.PR = Kb - 1 - g.PL; g.Tp = T + Kb - 1;
+    g.rows = N * g.Tp; g.slack = Kb;
+    g.Cin = Cin; g.Cb = Cb; g.P1 = P1; g.P2 = P2; g.pw = pw; g.depth = depth; g.H = H; g.has_hin = (P2 != H);
+    return g;
+}
+
+void Model::plan(const Shape& s) {
+    regions.clear();
+    size_t off = 0;
+    auto add = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems = 0, bool dbl = false) {
+        Region r{};
+        r.ndim = (int)dims.size(); r.is_double = dbl;
+        int64_t n = 1; int i = 0;
+        for (int64_t d : dims) { r.dims[i++] = d; n *= d; }
+        int64_t st = 1;
+        for (int k = r.ndim - 1; k >= 0; k--) { r.strides[k] = st; st *= r.dims[k]; }
+        r.numel = n;
+        const size_t esz = dbl ? 8 : 4;
+        off = (off + 255) / 256 * 256;
+        off += (size_t)slack_elems * esz;
+        off = (off + 255) / 256 * 256;
+        r.offset = off;
+        off += (size_t)n * esz + (size_t)slack_elems * esz;
+        regions[name] = r;
+    };
+    const taco_config& c = cfg;
+    const int N = s.N, tr = s.training;
+    enc = make_geom("enc_cbhg", N, s.Ti, c.enc_prenet_sizes[1], c.enc_bank_size, c.enc_bank_channels, c.enc_proj_sizes[0],
+                    c.enc_proj_sizes[1], c.enc_proj_width, c.enc_highway_depth, c.enc_rnn_size);
+    post = make_geom("post_cbhg", N, s.To, c.num_mels, c.post_bank_size, c.post_bank_channels, c.post_proj_sizes[0],
+                     c.post_proj_sizes[1], c.post_proj_width, c.post_highway_depth, c.post_rnn_size);
+    for (const CbhgGeom* gp : {&enc, &post}) {
+        const CbhgGeom& g = *gp;
+        const std::string p = g.prefix + "/";
+        const int64_t rows = g.rows, KC = (int64_t)g.Kb * g.Cb, H = g.H;
+        add(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin);
+        add(p + "bank_raw", {rows, KC});
+        add(p + "bank_stats", {2 * KC}, 0, true);
+        add(p + "bank_mean", {KC}); add(p + "bank_rstd", {KC}); add(p + "bank_var", {KC});
+        add(p + "pooled_p", {rows, KC}, (int64_t)g.slack * KC);
+        add(p + "p1_raw", {rows, g.P1}); add(p + "p1_stats", {2 * (int64_t)g.P1}, 0, true);
+        add(p + "p1_mean", {g.P1}); add(p + "p1_rstd", {g.P1}); add(p + "p1_var", {g.P1});
+        add(p + "p1_p", {rows, g.P1}, (int64_t)g.slack * g.P1);
+        add(p + "p2_raw", {rows, g.P2}); add(p + "p2_stats", {2 * (int64_t)g.P2}, 0, true);
+        add(p + "p2_mean", {g.P2}); add(p + "p2_rstd", {g.P2}); add(p + "p2_var", {g.P2});
+        add(p + "hw0", {rows, g.P2});
+        if (g.has_hin) add(p + "hw_0", {rows, H});
+        for (int i = 1; i <= g.depth; i++) {
+            add(p + "hw_" + std::to_string(i), {rows, H});
+            add(p + "hwH_" + std::to_string(i), {rows, H});
+            add(p + "hwT_" + std::to_string(i), {rows, H});
+        }
+        add(p + "gx", {rows, 6 * H});
+        add(p + "rnn_out", {(int64_t)g.N * g.T, 2 * H});
+        if (tr) {
+            const int64_t st = 2 * (int64_t)g.N * g.T * H;
+            add(p + "st_r", {st}); add(p + "st_u", {st}); add(p + "st_c", {st}); add(p + "st_hprev", {st});
+            add(p + "d_rnn_out", {(int64_t)g.N * g.T, 2 * H});
+            add(p + "dgx", {rows, 6 * H});
+            add(p + "dgx_dense", {2, (int64_t)g.N * g.T, 3 * H});
+            add(p + "d_hwA", {rows, H}); add(p + "d_hwB", {rows, H}); add(p + "d_Hpre", {rows, H}); add(p + "d_Tpre", {rows, H});
+            if (g.has_hin) add(p + "d_hw0", {rows, g.P2});
+            add(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2);
+            add(p + "d_p1p", {rows, g.P1});
+            add(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1);
+            add(p + "d_pooled", {rows, KC});
+            add(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC);
+            add(p + "d_xin_p", {rows, g.Cin});
+            add(p + "d_before", {g.N, g.P2});
+            add(p + "d_h0", {g.N, 2 * H});
+            for (int k = 1; k <= g.Kb; k++) add(p + "bank_" + std::to_string(k) + "/wd", {(int64_t)k * g.Cb, g.Cin});
+            add(p + "proj_1/wd", {(int64_t)g.pw * g.P1, KC});
+            add(p + "proj_2/wd", {(int64_t)g.pw * g.P2, g.P1});
+        }
+    }
+    // encoder prenet as lookup tables over the symbol set (the prenet is position-wise: 80 distinct rows)
+    add("enc/table1", {c.num_symbols, c.enc_prenet_sizes[0]});
+    add("enc/table2", {c.num_symbols, c.enc_prenet_sizes[1]});
+    if (tr) {
+        add("enc/d_table2", {c.num_symbols, c.enc_prenet_sizes[1]}); add("enc/d_t2pre", {c.num_symbols, c.enc_prenet_sizes[1]});
+        add("enc/d_table1", {c.num_symbols, c.enc_prenet_sizes[0]}); add("enc/d_t1pre", {c.num_symbols, c.enc_prenet_sizes[0]});
+    }
+    // decoder
+    {
+        const int64_t rows = (int64_t)N * s.Td;
+        const int64_t M = c.num_mels, r = c.reduction_factor, E = 2 * c.enc_rnn_size, A = c.attention_size, HA = c.attention_state_size;
+        const int64_t Z1 = c.dec_prenet_sizes[0], Z = c.dec_prenet_sizes[1], Y = c.dec_rnn_size;
+        const int64_t SPK = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
+        add("dec/keys", {(int64_t)N * s.Ti, A});
+        add("dec/x_all", {rows, M}); add("dec/px", {rows, Z1});
+        add("dec/y0", {rows, Y}); add("dec/y1", {rows, Y}); add("dec/y2", {rows, Y});
+        add("dec/g1_gx", {rows, 3 * Y}); add("dec/g2_gx", {rows, 3 * Y});
+        add("alignments", {N, s.Ti, s.Td});
+        if (tr) {
+            add("dec/s_z1", {rows, Z1}); add("dec/s_z", {rows, Z});
+            for (const char* nm : {"dec/s_r", "dec/s_u", "dec/s_c", "dec/s_haprev", "dec/s_ha"}) add(nm, {rows, HA});
+            add("dec/s_q", {rows, A}); add("dec/s_ctxin", {rows, E}); add("dec/s_ctx", {rows, E});
+            add("dec/s_e", {rows, s.Ti}); add("dec/s_a", {rows, s.Ti});
+            for (int l = 1; l <= 2; l++) {
+                const std::string rp = "dec/g" + std::to_string(l) + "_";
+                for (const char* nm : {"st_r", "st_u", "st_c", "st_hprev"}) add(rp + nm, {rows, Y});
+                add(rp + "dgx", {rows, 3 * Y}); add(rp + "dh0", {N, Y});
+            }
+            add("dec/d_dec", {rows, M * r}); add("dec/d_y2", {rows, Y}); add("dec/d_y1", {rows, Y}); add("dec/d_y0", {rows, Y});
+            const int64_t ZS = Z + SPK, KIN = ZS + HA, KO = HA + E + SPK;
+            add("dec/W1cT", {Z1, E}); add("dec/W2T", {Z, Z1}); add("dec/WgT", {2 * HA, KIN}); add("dec/WcT", {HA, KIN});
+            add("dec/WqT", {A, HA}); add("dec/WoT", {Y, KO});
+            add("dec/d_G", {rows, 3 * HA}); add("dec/d_zp", {rows, Z}); add("dec/d_z1p", {rows, Z1}); add("dec/d_ctx", {rows, E});
+            add("dec/d_gq", {rows, A}); add("dec/d_ge", {rows, s.Ti}); add("dec/d_ha0", {N, HA});
+            add("dec/d_keys", {(int64_t)N * s.Ti, A});
+        }
+    }
+    add("linear_outputs", {N, s.To, c.num_freq});
+    if (tr) { add("d_linear", {N, s.To, c.num_freq}); add("post_cbhg/d_mel_loss", {post.rows, c.num_mels}); }
+    add("scalars", {8}, 0, true);
+    add("scalars_f", {8});
+    // zero-copy view of the mel outputs inside the post-net's padded input
+    {
+        Region r = regions["post_cbhg/xin_p"];
+        r.offset += (size_t)post.PL * c.num_mels * 4;
+        r.ndim = 3; r.dims[0] = N; r.dims[1] = s.To; r.dims[2] = c.num_mels;
+        r.strides[0] = (int64_t)post.Tp * c.num_mels; r.strides[1] = c.num_mels; r.strides[2] = 1;
+        r.numel = (int64_t)N * s.To * c.num_mels;
+        regions["mel_outputs"] = r;
+    }
+    plan_bytes = (off + 255) / 256 * 256;
+    shape = s; planned = true;
+}
+
+static int shape_of(const Model& m, const taco_batch* b, Shape& s) {
+    TACO_REQUIRE(b && b->N > 0 && b->T_in > 0, TACO_ESHAPE, "batch: N and T_in must be positive");
+    s.N = b->N; s.Ti = b->T_in;
+    s.training = (b->linear_targets != nullptr) ? 1 : 0;      // tacotron.py:26
+    const int r = m.cfg.reduction_factor;
+    if (b->mel_targets) {
+        TACO_REQUIRE(b->T_out > 0 && b->T_out % r == 0, TACO_ESHAPE, "batch: T_out=%d must be a positive multiple of r=%d", b->T_out, r);
+        s.Td = b->T_out / r;
+        if (b->decoder_steps > 0 && b->decoder_steps < s.Td) s.Td = b->decoder_steps;
+    } else {
+        TACO_REQUIRE(b->decoder_steps > 0, TACO_ESHAPE, "batch: decoder_steps must be given without targets");
+        s.Td = b->decoder_steps;
+    }
+    s.To = s.Td * r;
+    return TACO_OK;
+}
+
+static int ensure_plan(Model& m, const Shape& s) {
+    if (!(m.planned && m.shape == s)) m.plan(s);
+    TACO_REQUIRE(m.ws != nullptr, TACO_ESTATE, "no workspace bound");
+    TACO_REQUIRE(m.plan_bytes <= m.ws_bytes, TACO_ENOMEM, "workspace too small: need %zu bytes, bound %zu", m.plan_bytes, m.ws_bytes);
+    return TACO_OK;
+}
+
+static taco_gemm_desc gd0(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc) {
+    taco_gemm_desc d{};
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.alpha = 1.f; d.split_k = 1;
+    return d;
+}
+
+static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
+    const taco_config& c = m.cfg;
+    const int prec = c.precision, tr = m.shape.training;
+    TACO_REQUIRE(c.speaker_mode == TACO_SPK_NONE, TACO_ESTATE, "speaker injection kernels are not built yet (single-speaker only)");
+    // ---- encoder prenet over the symbol table, then lookup (tacotron.py:34-39,101-103; modules.py:18-25; dropout = identity) ----
+    const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];
+    {
+        taco_gemm_desc d = gd0(m.P("embedding"), m.P("enc_prenet/dense_1/kernel"), m.W("enc/table1"), V, E1, E0, E0, E1, E1);
+        d.bias = m.P("enc_prenet/dense_1/bias"); d.act = ACT_RELU;
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+        d = gd0(m.W("enc/table1"), m.P("enc_prenet/dense_2/kernel"), m.W("enc/table2"), V, E2, E1, E1, E2, E2);
+        d.bias = m.P("enc_prenet/dense_2/bias"); d.act = ACT_RELU;
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    TACO_TRY(launch_gather_rows(m.W("enc/table2"), b->inputs, m.W("enc_cbhg/xin_p"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s));
+    TACO_TRY(cbhg_forward(m, m.enc, b->input_lengths, nullptr, nullptr, tr, s));
+    TACO_TRY(decoder_forward(m, b, s));
+    TACO_TRY(cbhg_forward(m, m.post, nullptr, nullptr, nullptr, tr, s));
+    // ---- linear-spectrogram projection (tacotron.py:235) ----
+    {
+        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq;
+        taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.P("linear/kernel"), m.W("linear_outputs"), m.shape.N * m.shape.To, F, Hp2, Hp2, F, F);
+        d.bias = m.P("linear/bias");
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    return TACO_OK;
+}
+
+static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
+    const taco_config& c = m.cfg;
+    const int prec = c.precision;
+    const int N = m.shape.N, To = m.shape.To, M = c.num_mels, F = c.num_freq;
+    TACO_REQUIRE(m.shape.training && b->mel_targets && b->linear_targets, TACO_ESTATE, "backward needs a training forward with targets");
+    TACO_CHECK_CUDA(cudaMemsetAsync(m.grads, 0, sizeof(float) * (size_t)m.n_trainable, s));
+    double* sc = m.Wd("scalars");
+    TACO_CHECK_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, s));
+    // conv data-gradient operands (flipped + transposed kernels)
+    for (const CbhgGeom* gp : {&m.enc, &m.post}) {
+        const CbhgGeom& g = *gp; const std::string p = g.prefix + "/";
+        for (int k = 1; k <= g.Kb; k++)
+            TACO_TRY(launch_pack_dgrad(m.P(p + "bank_" + std::to_string(k) + "/kernel"), m.W(p + "bank_" + std::to_string(k) + "/wd"), k, g.Cin, g.Cb, s));
+        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_1/kernel"), m.W(p + "proj_1/wd"), g.pw, g.Kb * g.Cb, g.P1, s));
+        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_2/kernel"), m.W(p + "proj_2/wd"), g.pw, g.P1, g.P2, s));
+    }
+    // ---- losses and their gradients (tacotron.py:274-302) ----
+    const CbhgGeom& g = m.post;
+    const double cnt_mel = (double)N * To * M, cnt_lin = (double)N * To * F;
+    float w_all = (float)(1.0 / cnt_lin), w_band = 0.f; int lo = 0, hi = 0;
+    if (c.prioritize_loss) {
+        lo = c.priority_lo; hi = c.priority_hi;
+        w_all = (float)(0.5 / cnt_lin); w_band = (float)(0.5 / ((double)N * To * (hi - lo)));
+    }
+    TACO_TRY(launch_l1_loss(m.W("linear_outputs"), (long long)To * F, F, b->linear_targets, b->loss_coeff,
+                            m.W("d_linear"), (long long)To * F, F, N, To, F, w_all, w_band, lo, hi, sc + 3, s));
+    TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
+                            m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
+                            (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
+    // ---- linear projection backward ----
+    {
+        const int Hp2 = 2 * c.post_rnn_size; const long long rows = (long long)N * To;
+        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel"), Hp2, F, (int)rows, Hp2, F, F);
+        w.transA = 1; w.accumulate = 1; w.split_k = 8;
+        TACO_TRY(launch_gemm(&w, 1, prec, s));
+        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, F, s));
+        taco_gemm_desc e = gd0(m.W("d_linear"), m.P("linear/kernel"), m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, F, F, Hp2);
+        e.transB = 1;
+        TACO_TRY(launch_gemm(&e, 1, prec, s));
+    }
+    TACO_TRY(cbhg_backward(m, m.post, nullptr, false, false, s));
+    TACO_TRY(launch_axpy(m.W("post_cbhg/d_xin_p"), m.W("post_cbhg/d_mel_loss"), 1.f, (long long)g.rows * M, s));
+    TACO_TRY(decoder_backward(m, b, s));
+    TACO_TRY(cbhg_backward(m, m.enc, b->input_lengths, false, false, s));
+    // ---- encoder prenet tables backward ----
+    {
+        const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];
+        TACO_CHECK_CUDA(cudaMemsetAsync(m.W("enc/d_table2"), 0, sizeof(float) * (size_t)V * E2, s));
+        TACO_TRY(launch_scatter_add_rows(m.W("enc_cbhg/d_xin_p"), b->inputs, m.W("enc/d_table2"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s));
+        TACO_TRY(launch_relu_bwd(m.W("enc/d_table2"), m.W("enc/table2"), m.W("enc/d_t2pre"), (long long)V * E2, s));
+        taco_gemm_desc w = gd0(m.W("enc/table1"), m.W("enc/d_t2pre"), m.G("enc_prenet/dense_2/kernel"), E1, E2, V, E1, E2, E2);
+        w.transA = 1; w.accumulate = 1;
+        TACO_TRY(launch_gemm(&w, 1, prec, s));
+        TACO_TRY(launch_colsum(m.W("enc/d_t2pre"), m.G("enc_prenet/dense_2/bias"), V, E2, E2, s));
+        taco_gemm_desc e = gd0(m.W("enc/d_t2pre"), m.P("enc_prenet/dense_2/kernel"), m.W("enc/d_table1"), V, E1, E2, E2, E2, E1); e.transB = 1;
+        TACO_TRY(launch_gemm(&e, 1, prec, s));
+        TACO_TRY(launch_relu_bwd(m.W("enc/d_table1"), m.W("enc/table1"), m.W("enc/d_t1pre"), (long long)V * E1, s));
+        w = gd0(m.P("embedding"), m.W("enc/d_t1pre"), m.G("enc_prenet/dense_1/kernel"), E0, E1, V, E0, E1, E1);
+        w.transA = 1; w.accumulate = 1;
+        TACO_TRY(launch_gemm(&w, 1, prec, s));
+        TACO_TRY(launch_colsum(m.W("enc/d_t1pre"), m.G("enc_prenet/dense_1/bias"), V, E1, E1, s));
+        e = gd0(m.W("enc/d_t1pre"), m.P("enc_prenet/dense_1/kernel"), m.G("embedding"), V, E0, E1, E1, E1, E0); e.transB = 1; e.accumulate = 1;
+        TACO_TRY(launch_gemm(&e, 1, prec, s));
+    }
+    return TACO_OK;
+}
+
+}  // namespace taco
+
+// =============================================== C ABI ===============================================
+using namespace taco;
+
+struct taco_model_s { Model m; };
+
+extern "C" {
+
+const char* taco_last_error(void) { return g_err.c_str(); }
+int taco_abi_version(void) { return TACO_ABI_VERSION; }
+int64_t taco_launch_count(void) { return g_launch_count; }
+
+int taco_create(taco_model* out, const taco_config* cfg) {
+    TACO_REQUIRE(out && cfg, TACO_EINVAL, "taco_create: null argument");
+    TACO_REQUIRE(cfg->abi_version == TACO_ABI_VERSION, TACO_EINVAL, "taco_create: ABI version %d != %d", cfg->abi_version, TACO_ABI_VERSION);
+    TACO_REQUIRE(cfg->attention_type >= 0 && cfg->attention_type <= 2, TACO_EINVAL, " [!] Unkown attention type: %d", cfg->attention_type);
+    TACO_REQUIRE(cfg->speaker_mode >= 0 && cfg->speaker_mode <= 3, TACO_EINVAL, " [!] Unkown multi-speaker model type: %d", cfg->speaker_mode);
+    TACO_REQUIRE(cfg->reduction_factor >= 1 && cfg->num_mels > 0 && cfg->num_freq > 0, TACO_EINVAL, "taco_create: bad sizes");
+    TACO_REQUIRE(cfg->enc_proj_sizes[1] == cfg->enc_prenet_sizes[1], TACO_ESHAPE, "encoder residual needs proj_sizes[-1] == prenet_sizes[-1]");
+    TACO_REQUIRE(cfg->post_proj_sizes[1] == cfg->num_mels, TACO_ESHAPE, "post-net residual needs post_proj_sizes[-1] == num_mels");
+    taco_model_s* h = new (std::nothrow) taco_model_s();
+    TACO_REQUIRE(h, TACO_ENOMEM, "taco_create: out of host memory");
+    h->m.cfg = *cfg;
+    *out = h;
+    return TACO_OK;
+}
+
+int taco_destroy(taco_model h) {
+    delete h;
+    return TACO_OK;
+}
+
+int taco_bind_params(taco_model h, const taco_param_entry* table, int32_t n_entries, float* params, float* grads,
+                     float* adam_m, float* adam_v, float* bn_state, int64_t n_trainable, int64_t n_state) {
+    TACO_REQUIRE(h && table && params && bn_state, TACO_EINVAL, "taco_bind_params: null argument");
+    Model& m = h->m;
+    m.table.clear();
+    for (int i = 0; i < n_entries; i++) {
+        const taco_param_entry& e = table[i];
+        TACO_REQUIRE(e.name && e.offset >= 0 && e.numel > 0, TACO_EINVAL, "taco_bind_params: bad entry %d", i);
+        TACO_REQUIRE(e.offset + e.numel <= (e.trainable ? n_trainable : n_state), TACO_ESHAPE,
+                     "taco_bind_params: '%s' exceeds its buffer", e.name);
+        m.table[e.name] = Entry{e.offset, e.numel, e.trainable};
+    }
+    m.params = params; m.grads = grads; m.adam_m = adam_m; m.adam_v = adam_v; m.bn_state = bn_state;
+    m.n_trainable = n_trainable; m.n_state = n_state;
+    // every tensor the kernels will dereference must be present with the expected size
+    const taco_config& c = m.cfg;
+    auto need = [&](const std::string& name, int64_t numel) -> int {
+        auto it = m.table.find(name);
+        TACO_REQUIRE(it != m.table.end(), TACO_EINVAL, "taco_bind_params: missing tensor '%s'", name.c_str());
+        TACO_REQUIRE(it->second.numel == numel, TACO_ESHAPE, "taco_bind_params: '%s' has %lld elements, expected %lld", name.c_str(),
+                     (long long)it->second.numel, (long long)numel);
+        return TACO_OK;
+    };
+    TACO_TRY(need("embedding", (int64_t)c.num_symbols * c.embedding_size));
+    TACO_TRY(need("enc_prenet/dense_1/kernel", (int64_t)c.embedding_size * c.enc_prenet_sizes[0]));
+    TACO_TRY(need("enc_cbhg/bank_1/kernel", (int64_t)c.enc_prenet_sizes[1] * c.enc_bank_channels));
+    TACO_TRY(need("enc_cbhg/gru_fw/gates_kernel", (int64_t)2 * c.enc_rnn_size * 2 * c.enc_rnn_size));
+    TACO_TRY(need("attention/memory_kernel", (int64_t)2 * c.enc_rnn_size * c.attention_size));
+    TACO_TRY(need("mel_proj/kernel", (int64_t)c.dec_rnn_size * c.num_mels * c.reduction_factor));
+    TACO_TRY(need("post_cbhg/proj_1/kernel", (int64_t)c.post_proj_width * c.post_bank_size * c.post_bank_channels * c.post_proj_sizes[0]));
+    const int64_t spk_cat = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
+    TACO_TRY(need("linear/kernel", (int64_t)(2 * c.post_rnn_size + spk_cat) * c.num_freq));
+    // bank tensors of one kind must be contiguous (see params.py:_cbhg)
+    for (const char* pf : {"enc_cbhg", "post_cbhg"}) {
+        const int Kb = std::string(pf) == "enc_cbhg" ? c.enc_bank_size : c.post_bank_size;
+        const int Cb = std::string(pf) == "enc_cbhg" ? c.enc_bank_channels : c.post_bank_channels;
+        for (const char* f : {"bias", "gamma", "beta", "moving_mean", "moving_var"})
+            for (int k = 2; k <= Kb; k++) {
+                auto a = m.table.find(std::string(pf) + "/bank_" + std::to_string(k - 1) + "/" + f);
+                auto b2 = m.table.find(std::string(pf) + "/bank_" + std::to_string(k) + "/" + f);
+                TACO_REQUIRE(a != m.table.end() && b2 != m.table.end() && b2->second.offset == a->second.offset + Cb, TACO_ESHAPE,
+                             "taco_bind_params: %s bank '%s' tensors must be stored back to back", pf, f);
+            }
+    }
+    return TACO_OK;
+}
+
+int taco_workspace_bytes(taco_model h, int32_t N, int32_t T_in, int32_t T_out_or_steps, int32_t training, size_t* bytes) {
+    TACO_REQUIRE(h && bytes, TACO_EINVAL, "taco_workspace_bytes: null argument");
+    TACO_REQUIRE(N > 0 && T_in > 0 && T_out_or_steps > 0, TACO_ESHAPE, "taco_workspace_bytes: non-positive shape");
+    Model& m = h->m;
+    Shape s; s.N = N; s.Ti = T_in; s.training = training;
+    if (training) { s.To = T_out_or_steps; s.Td = s.To / m.cfg.reduction_factor; }
+    else { s.Td = T_out_or_steps; s.To = s.Td * m.cfg.reduction_factor; }
+    m.plan(s);
+    *bytes = m.plan_bytes;
+    return TACO_OK;
+}
+
+int taco_bind_workspace(taco_model h, void* ws, size_t bytes) {
+    TACO_REQUIRE(h && ws, TACO_EINVAL, "taco_bind_workspace: null argument");
+    TACO_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, TACO_EINVAL, "taco_bind_workspace: base must be 256-byte aligned");
+    h->m.ws = static_cast<char*>(ws); h->m.ws_bytes = bytes;
+    return TACO_OK;
+}
+
+int taco_ws_region(taco_model h, const char* name, size_t* offset_bytes, int64_t* numel, int64_t dims[4], int64_t strides[4], int32_t* ndim) {
+    TACO_REQUIRE(h && name, TACO_EINVAL, "taco_ws_region: null argument");
+    auto it = h->m.regions.find(name);
+    TACO_REQUIRE(it != h->m.regions.end(), TACO_EINVAL, "taco_ws_region: no region '%s' in the current plan", name);
+    const Region& r = it->second;
+    if (offset_bytes) *offset_bytes = r.offset;
+    if (numel) *numel = r.numel;
+    if (ndim) *ndim = r.is_double ? -r.ndim : r.ndim;
+    for (int i = 0; i < 4; i++) { if (dims) dims[i] = i < r.ndim ? r.dims[i] : 1; if (strides) strides[i] = i < r.ndim ? r.strides[i] : 0; }
+    return TACO_OK;
+}
+
+int taco_forward(taco_model h, const taco_batch* b, void* stream) {
+    TACO_REQUIRE(h && b, TACO_EINVAL, "taco_forward: null argument");
+    Model& m = h->m;
+    TACO_REQUIRE(m.params != nullptr, TACO_ESTATE, "taco_forward: parameters not bound");
+    TACO_REQUIRE(b->inputs && b->input_lengths, TACO_EINVAL, "taco_forward: inputs / input_lengths are required");
+    Shape s;
+    TACO_TRY(shape_of(m, b, s));
+    TACO_TRY(ensure_plan(m, s));
+    return model_forward(m, b, static_cast<cudaStream_t>(stream));
+}
+
+int taco_backward(taco_model h, const taco_batch* b, void* stream) {
+    TACO_REQUIRE(h && b, TACO_EINVAL, "taco_backward: null argument");
+    Model& m = h->m;
+    TACO_REQUIRE(m.grads != nullptr, TACO_ESTATE, "taco_backward: gradient buffer not bound");
+    Shape s;
+    TACO_TRY(shape_of(m, b, s));
+    TACO_REQUIRE(m.planned && m.shape == s, TACO_ESTATE, "taco_backward: call taco_forward with the same batch first");
+    return model_backward(m, b, static_cast<cudaStream_t>(stream));
+}
+
+int taco_optimizer_step(taco_model h, int64_t global_step, int32_t is_randomly_initialized, float initial_learning_rate,
+                        int32_t decay_mode, float beta1, float beta2, float grad_scale, void* stream) {
+    TACO_REQUIRE(h, TACO_EINVAL, "taco_optimizer_step: null model");
+    Model& m = h->m;
+    TACO_REQUIRE(m.grads && m.adam_m && m.adam_v, TACO_ESTATE, "taco_optimizer_step: optimizer buffers not bound");
+    TACO_REQUIRE(m.planned && m.shape.training, TACO_ESTATE, "taco_optimizer_step: no training step in flight");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // learning rate (tacotron.py:314-326), step = global_step + 1
+    const double step = (double)(global_step + 1);
+    double lr;
+    if (decay_mode == 0) {
+        const double w = is_randomly_initialized ? 4000.0 : 40000.0;
+        lr = initial_learning_rate * std::sqrt(w) * std::fmin(step * std::pow(w, -1.5), 1.0 / std::sqrt(step));
+    } else {
+        lr = initial_learning_rate * std::pow(0.95, step / 3000.0);
+    }
+    const double t = step;
+    const double lr_t = lr * std::sqrt(1.0 - std::pow((double)beta2, t)) / (1.0 - std::pow((double)beta1, t));
+    double* sc = m.Wd("scalars");
+    float* scf = m.W("scalars_f");
+    TACO_CHECK_CUDA(cudaMemsetAsync(sc + 6, 0, sizeof(double), s));
+    TACO_TRY(launch_sqnorm(m.grads, m.n_trainable, sc + 6, s));
+    TACO_TRY(launch_adam_clip(m.params, m.adam_m, m.adam_v, m.grads, m.n_trainable, sc + 6, grad_scale, 1.0f, (float)lr_t,
+                              beta1, beta2, 1e-8f, (float)lr, scf, s));
+    // batch-norm moving statistics (the UPDATE_OPS dependency of tacotron.py:332-336)
+    for (const CbhgGeom* gp : {&m.enc, &m.post}) {
+        const CbhgGeom& g = *gp; const std::string p = g.prefix + "/";
+        TACO_TRY(launch_bn_update_moving(m.P(p + "bank_1/moving_mean"), m.P(p + "bank_1/moving_var"), m.W(p + "bank_mean"), m.W(p + "bank_var"), g.Kb * g.Cb, s));
+        TACO_TRY(launch_bn_update_moving(m.P(p + "proj_1/moving_mean"), m.P(p + "proj_1/moving_var"), m.W(p + "p1_mean"), m.W(p + "p1_var"), g.P1, s));
+        TACO_TRY(launch_bn_update_moving(m.P(p + "proj_2/moving_mean"), m.P(p + "proj_2/moving_var"), m.W(p + "p2_mean"), m.W(p + "p2_var"), g.P2, s));
+    }
+    return TACO_OK;
+}
+
+int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
+    TACO_REQUIRE(h && out, TACO_EINVAL, "taco_read_scalars: null argument");
+    Model& m = h->m;
+    TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_read_scalars: nothing has run");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double sc[8]; float scf[8];
+    TACO_CHECK_CUDA(cudaMemcpyAsync(sc, m.Wd("scalars"), sizeof sc, cudaMemcpyDeviceToHost, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(scf, m.W("scalars_f"), sizeof scf, cudaMemcpyDeviceToHost, s));
+    TACO_CHECK_CUDA(cudaStreamSynchronize(s));
+    const taco_config& c = m.cfg;
+    const double cnt_mel = (double)m.shape.N * m.shape.To * c.num_mels, cnt_lin = (double)m.shape.N * m.shape.To * c.num_freq;
+    out->loss = (float)(sc[0] + sc[3]);
+    out->mel_loss = (float)(sc[1] / cnt_mel);
+    if (c.prioritize_loss) {
+        const double cnt_band = (double)m.shape.N * m.shape.To * (c.priority_hi - c.priority_lo);
+        out->linear_loss = (float)(0.5 * (sc[4] / cnt_lin + sc[5] / cnt_band));
+    } else {
+        out->linear_loss = (float)(sc[4] / cnt_lin);
+    }
+    out->loss_without_coeff = out->mel_loss + out->linear_loss;
+    out->grad_norm = scf[0];
+    out->learning_rate = scf[1];
+    return TACO_OK;
+}
+
+int taco_gemm(const taco_gemm_desc* d, int32_t n_problems, int32_t precision, void* stream) {
+    TACO_REQUIRE(d && n_problems > 0, TACO_EINVAL, "taco_gemm: null argument");
+    return launch_gemm(d, n_problems, precision, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

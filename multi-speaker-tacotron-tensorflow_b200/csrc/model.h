@@ -1,0 +1,69 @@
+// Model object behind the C ABI: configuration, bound parameter table, workspace plan.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace taco {
+
+struct Entry { int64_t offset; int64_t numel; int trainable; };
+
+struct Region {
+    size_t offset;      // bytes from workspace base
+    int64_t numel;      // elements (fp32 unless is_double)
+    int ndim; int64_t dims[4]; int64_t strides[4];
+    bool is_double;
+};
+
+// Geometry of one CBHG block in the zero-padded time layout.
+struct CbhgGeom {
+    std::string prefix;  // "enc_cbhg" | "post_cbhg"
+    int N, T, Tp, PL, PR, rows, slack;
+    int Cin, Kb, Cb, P1, P2, pw, depth, H;
+    bool has_hin;
+};
+
+struct Shape {
+    int N = 0, Ti = 0, To = 0, Td = 0;
+    int training = 0;
+    bool operator==(const Shape& o) const { return N == o.N && Ti == o.Ti && To == o.To && Td == o.Td && training == o.training; }
+};
+
+struct Model {
+    taco_config cfg;
+    float* params = nullptr; float* grads = nullptr; float* adam_m = nullptr; float* adam_v = nullptr; float* bn_state = nullptr;
+    int64_t n_trainable = 0, n_state = 0;
+    std::unordered_map<std::string, Entry> table;
+
+    char* ws = nullptr; size_t ws_bytes = 0;
+    Shape shape; bool planned = false;
+    std::map<std::string, Region> regions;
+    size_t plan_bytes = 0;
+    CbhgGeom enc, post;
+
+    // parameter access by name
+    int lookup(const std::string& name, Entry& e) const;
+    float* P(const std::string& name) const;   // parameter (trainable) or BN state
+    float* G(const std::string& name) const;   // gradient slot of a trainable parameter
+    bool has(const std::string& name) const { return table.count(name) != 0; }
+
+    // workspace
+    void plan(const Shape& s);
+    float* W(const std::string& name) const;   // region pointer (fp32)
+    double* Wd(const std::string& name) const; // region pointer (double)
+    bool has_region(const std::string& name) const { return regions.count(name) != 0; }
+};
+
+// model_cbhg.cu
+int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* before_highway, const float* rnn_h0,
+                 int training, cudaStream_t s);
+int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbefore, bool want_dh0, cudaStream_t s);
+
+// model_decoder.cu
+int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s);
+int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s);
+
+}  // namespace taco

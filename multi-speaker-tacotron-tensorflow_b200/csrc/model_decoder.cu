@@ -1,0 +1,253 @@
+// Decoder (teacher-forced): hoisted GEMMs around the attention recurrence (attention.cu) and the two residual GRU
+// layers (gru.cu), forward and backward.       reference: models/tacotron.py:127-214, models/helpers.py:35-67
+#include "model.h"
+
+namespace taco {
+
+static taco_gemm_desc gd(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc) {
+    taco_gemm_desc d{};
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+    d.alpha = 1.f; d.split_k = 1;
+    return d;
+}
+static int wsplit(int M, int N, long long rows) {
+    long long tiles = (long long)cdiv(M, 64) * cdiv(N, 64);
+    long long want = (2 * 148 + tiles - 1) / tiles;
+    long long maxs = rows / 256 > 0 ? rows / 256 : 1;
+    long long sp = want < maxs ? want : maxs;
+    if (sp < 1) sp = 1;
+    if (sp > 64) sp = 64;
+    return (int)sp;
+}
+static taco_gemm_desc wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int Kin, int Nout, long long rows) {
+    taco_gemm_desc d = gd(X, dY, dW, Kin, Nout, (int)rows, ldx, ldy, Nout);
+    d.transA = 1; d.accumulate = 1; d.split_k = wsplit(Kin, Nout, rows);
+    return d;
+}
+
+struct DecDims { int N, Ti, Td, To, M, r, E, A, HA, Z1, Z, SPK, Y; };
+static DecDims dec_dims(const Model& m) {
+    DecDims d;
+    d.N = m.shape.N; d.Ti = m.shape.Ti; d.Td = m.shape.Td; d.To = m.shape.To;
+    d.M = m.cfg.num_mels; d.r = m.cfg.reduction_factor;
+    d.E = 2 * m.cfg.enc_rnn_size; d.A = m.cfg.attention_size; d.HA = m.cfg.attention_state_size;
+    d.Z1 = m.cfg.dec_prenet_sizes[0]; d.Z = m.cfg.dec_prenet_sizes[1];
+    d.SPK = (m.cfg.speaker_mode == TACO_SPK_SIMPLE) ? m.cfg.speaker_embedding_size : 0;
+    d.Y = m.cfg.dec_rnn_size;
+    return d;
+}
+
+static void fill_att_weights(const Model& m, const DecDims& D, AttArgs& a) {
+    a.W1c = m.P("dec_prenet/dense_1/kernel") + (long long)D.M * D.Z1;
+    a.W2 = m.P("dec_prenet/dense_2/kernel"); a.b2 = m.P("dec_prenet/dense_2/bias");
+    a.Wg = m.P("attention_gru/gates_kernel"); a.bg = m.P("attention_gru/gates_bias");
+    a.Wc = m.P("attention_gru/cand_kernel"); a.bc = m.P("attention_gru/cand_bias");
+    a.Wq = m.P("attention/query_kernel"); a.v = m.P("attention/v");
+    a.score_bias = m.has("attention/score_bias") ? m.P("attention/score_bias") : nullptr;
+    a.att_g = m.has("attention/g") ? m.P("attention/g") : nullptr;
+    a.att_b = m.has("attention/b") ? m.P("attention/b") : nullptr;
+    a.Wo = m.P("concat_proj/kernel"); a.bo = m.P("concat_proj/bias");
+}
+
+static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, float* y, int training, const float* h0, cudaStream_t s) {
+    const std::string gn = "dec_gru_" + std::to_string(layer);
+    const std::string rp = "dec/g" + std::to_string(layer) + "_";
+    const int Y = D.Y, rows = D.N * D.Td;
+    float* gx = m.W(rp + "gx");
+    taco_gemm_desc d[2];
+    d[0] = gd(x, m.P(gn + "/gates_kernel"), gx, rows, 2 * Y, Y, Y, 2 * Y, 3 * Y); d[0].bias = m.P(gn + "/gates_bias");
+    d[1] = gd(x, m.P(gn + "/cand_kernel"), gx + 2 * Y, rows, Y, Y, Y, Y, 3 * Y); d[1].bias = m.P(gn + "/cand_bias");
+    TACO_TRY(launch_gemm(d, 2, m.cfg.precision, s));
+    GruArgs a{};
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1;
+    a.gx = gx; a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
+    a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
+    a.h0 = h0; a.res = x; a.res_ld = Y; a.out = y; a.out_ld = Y;
+    if (training) { a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev"); }
+    return launch_gru_fwd(a, s);
+}
+
+int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
+    const DecDims D = dec_dims(m);
+    const int prec = m.cfg.precision, training = m.shape.training;
+    TACO_REQUIRE(b->mel_targets != nullptr && !b->rnn_decoder_test_mode, TACO_ESTATE,
+                 "decoder: free-running decoding (inference / rnn_decoder_test_mode) is not built yet; teacher-forced only");
+    const int rows = D.N * D.Td;
+    const float* memory = m.W("enc_cbhg/rnn_out");
+    // attention keys = memory . Wm (no bias, no length mask)   tacotron.py:133-134
+    {
+        taco_gemm_desc d = gd(memory, m.P("attention/memory_kernel"), m.W("dec/keys"), D.N * D.Ti, D.A, D.E, D.E, D.A, D.A);
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    // teacher-forcing inputs and the hoisted x-side of prenet layer 1   helpers.py:44,60-67; rnn_wrappers.py:249,367-369
+    TACO_TRY(launch_teacher_inputs(b->mel_targets, m.W("dec/x_all"), D.N, D.Td, D.To, D.r, D.M, s));
+    {
+        taco_gemm_desc d = gd(m.W("dec/x_all"), m.P("dec_prenet/dense_1/kernel"), m.W("dec/px"), rows, D.Z1, D.M, D.M, D.Z1, D.Z1);
+        d.bias = m.P("dec_prenet/dense_1/bias");
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    AttArgs a{};
+    a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
+    a.att_type = m.cfg.attention_type; a.fast = (prec == TACO_PREC_BF16);
+    a.px = m.W("dec/px"); a.memory = memory; a.keys = m.W("dec/keys");
+    a.spk = D.SPK ? m.W("spk/embed") : nullptr;
+    a.ha0 = m.has_region("spk/att_init") ? m.W("spk/att_init") : nullptr;
+    a.manual = b->manual_alignments;
+    fill_att_weights(m, D, a);
+    a.y0 = m.W("dec/y0"); a.align = m.W("alignments");
+    if (training) {
+        a.s_z1 = m.W("dec/s_z1"); a.s_z = m.W("dec/s_z"); a.s_r = m.W("dec/s_r"); a.s_u = m.W("dec/s_u"); a.s_c = m.W("dec/s_c");
+        a.s_haprev = m.W("dec/s_haprev"); a.s_ha = m.W("dec/s_ha"); a.s_q = m.W("dec/s_q"); a.s_ctxin = m.W("dec/s_ctxin");
+        a.s_ctx = m.W("dec/s_ctx"); a.s_e = m.W("dec/s_e"); a.s_a = m.W("dec/s_a");
+    }
+    TACO_TRY(launch_att_fwd(a, s));
+    // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
+    const float* h1 = m.has_region("spk/dec_init1") ? m.W("spk/dec_init1") : nullptr;
+    const float* h2 = m.has_region("spk/dec_init2") ? m.W("spk/dec_init2") : nullptr;
+    TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
+    TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
+    // r-frame mel projection, written straight into the post-net's padded input (= mel_outputs)   tacotron.py:178-179,213-214
+    {
+        const CbhgGeom& g = m.post;
+        taco_gemm_desc d = gd(m.W("dec/y2"), m.P("mel_proj/kernel"), m.W("post_cbhg/xin_p") + (long long)g.PL * D.M,
+                              rows, D.M * D.r, D.Y, D.Y, D.M * D.r, D.M * D.r);
+        d.bias = m.P("mel_proj/bias");
+        d.remap_period = D.Td; d.remap_outer = (long long)g.Tp * D.M; d.remap_inner = (long long)D.M * D.r;
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    return TACO_OK;
+}
+
+static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float* x, const float* dy, float* dx, bool want_dh0, cudaStream_t s) {
+    // y = x + h(x): dx = dy + dgx . Wx^T ; parameter grads accumulated
+    const std::string gn = "dec_gru_" + std::to_string(layer);
+    const std::string rp = "dec/g" + std::to_string(layer) + "_";
+    const int Y = D.Y, rows = D.N * D.Td, prec = m.cfg.precision;
+    float* dgx = m.W(rp + "dgx");
+    TACO_CHECK_CUDA(cudaMemsetAsync(dgx, 0, sizeof(float) * (size_t)rows * 3 * Y, s));
+    GruArgs a{};
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1;
+    a.gx = m.W(rp + "gx"); a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
+    a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
+    a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
+    a.dout = dy; a.dout_ld = Y; a.dgx = dgx;
+    a.dh0 = want_dh0 ? m.W(rp + "dh0") : nullptr;
+    TACO_TRY(launch_gru_bwd(a, s));
+    taco_gemm_desc w[4];
+    w[0] = wgrad(x, Y, dgx, 3 * Y, m.G(gn + "/gates_kernel"), Y, 2 * Y, rows);
+    w[1] = wgrad(x, Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel"), Y, Y, rows);
+    w[2] = wgrad(m.W(rp + "st_hprev"), Y, dgx, 3 * Y, m.G(gn + "/gates_kernel") + (long long)Y * 2 * Y, Y, 2 * Y, rows);
+    w[3] = wgrad(m.W(rp + "st_r"), Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel") + (long long)Y * Y, Y, Y, rows);
+    TACO_TRY(launch_gemm(w, 4, prec, s));
+    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, s));
+    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(dx, dy, sizeof(float) * (size_t)rows * Y, cudaMemcpyDeviceToDevice, s));
+    taco_gemm_desc e = gd(dgx, m.P(gn + "/gates_kernel"), dx, rows, Y, 2 * Y, 3 * Y, 2 * Y, Y); e.transB = 1; e.accumulate = 1;
+    TACO_TRY(launch_gemm(&e, 1, prec, s));
+    e = gd(dgx + 2 * Y, m.P(gn + "/cand_kernel"), dx, rows, Y, Y, 3 * Y, Y, Y); e.transB = 1; e.accumulate = 1;
+    TACO_TRY(launch_gemm(&e, 1, prec, s));
+    return TACO_OK;
+}
+
+// Input: "post_cbhg/d_xin_p" (grad wrt mel outputs in the padded layout, mel-loss term already added).
+// Output: "enc_cbhg/d_rnn_out" (grad wrt encoder memory) and all decoder parameter gradients.
+int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
+    const DecDims D = dec_dims(m);
+    const int prec = m.cfg.precision;
+    const int rows = D.N * D.Td, Y = D.Y, MR = D.M * D.r;
+    const CbhgGeom& g = m.post;
+    const bool deepvoice = m.has_region("spk/att_init");
+    // mel projection backward
+    float* d_dec = m.W("dec/d_dec");      // [N*Td, M*r] dense
+    TACO_TRY(launch_unpad(d_dec, m.W("post_cbhg/d_xin_p"), D.N, D.To, g.Tp, g.PL, D.M, D.M, s));
+    {
+        taco_gemm_desc w = wgrad(m.W("dec/y2"), Y, d_dec, MR, m.G("mel_proj/kernel"), Y, MR, rows);
+        TACO_TRY(launch_gemm(&w, 1, prec, s));
+        TACO_TRY(launch_colsum(d_dec, m.G("mel_proj/bias"), rows, MR, MR, s));
+        taco_gemm_desc e = gd(d_dec, m.P("mel_proj/kernel"), m.W("dec/d_y2"), rows, Y, MR, MR, MR, Y); e.transB = 1;
+        TACO_TRY(launch_gemm(&e, 1, prec, s));
+    }
+    TACO_TRY(dec_gru_layer_bwd(m, D, 2, m.W("dec/y1"), m.W("dec/d_y2"), m.W("dec/d_y1"), deepvoice, s));
+    TACO_TRY(dec_gru_layer_bwd(m, D, 1, m.W("dec/y0"), m.W("dec/d_y1"), m.W("dec/d_y0"), deepvoice, s));
+
+    // transposed weight copies for the attention BPTT
+    const int ZS = D.Z + D.SPK, KIN = ZS + D.HA, KO = D.HA + D.E + D.SPK;
+    TACO_TRY(launch_transpose(m.P("dec_prenet/dense_1/kernel") + (long long)D.M * D.Z1, m.W("dec/W1cT"), D.E, D.Z1, s));
+    TACO_TRY(launch_transpose(m.P("dec_prenet/dense_2/kernel"), m.W("dec/W2T"), D.Z1, D.Z, s));
+    TACO_TRY(launch_transpose(m.P("attention_gru/gates_kernel"), m.W("dec/WgT"), KIN, 2 * D.HA, s));
+    TACO_TRY(launch_transpose(m.P("attention_gru/cand_kernel"), m.W("dec/WcT"), KIN, D.HA, s));
+    TACO_TRY(launch_transpose(m.P("attention/query_kernel"), m.W("dec/WqT"), D.HA, D.A, s));
+    TACO_TRY(launch_transpose(m.P("concat_proj/kernel"), m.W("dec/WoT"), KO, Y, s));
+
+    AttArgs a{};
+    a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
+    a.att_type = m.cfg.attention_type; a.fast = (prec == TACO_PREC_BF16);
+    a.memory = m.W("enc_cbhg/rnn_out"); a.keys = m.W("dec/keys");
+    a.manual = b->manual_alignments;
+    fill_att_weights(m, D, a);
+    a.s_z1 = m.W("dec/s_z1"); a.s_z = m.W("dec/s_z"); a.s_r = m.W("dec/s_r"); a.s_u = m.W("dec/s_u"); a.s_c = m.W("dec/s_c");
+    a.s_haprev = m.W("dec/s_haprev"); a.s_ha = m.W("dec/s_ha"); a.s_q = m.W("dec/s_q"); a.s_ctxin = m.W("dec/s_ctxin");
+    a.s_ctx = m.W("dec/s_ctx"); a.s_e = m.W("dec/s_e"); a.s_a = m.W("dec/s_a");
+    a.dy0 = m.W("dec/d_y0");
+    a.W1cT = m.W("dec/W1cT"); a.W2T = m.W("dec/W2T"); a.WgT = m.W("dec/WgT"); a.WcT = m.W("dec/WcT"); a.WqT = m.W("dec/WqT"); a.WoT = m.W("dec/WoT");
+    a.d_G = m.W("dec/d_G"); a.d_zp = m.W("dec/d_zp"); a.d_z1p = m.W("dec/d_z1p"); a.d_ctx = m.W("dec/d_ctx");
+    a.d_gq = m.W("dec/d_gq"); a.d_ge = m.W("dec/d_ge");
+    a.d_ha0 = deepvoice ? m.W("dec/d_ha0") : nullptr;
+    a.d_score_bias = m.has("attention/score_bias") ? m.G("attention/score_bias") : nullptr;
+    TACO_TRY(launch_att_bwd(a, s));
+
+    // hoisted parameter gradients of the attention part
+    {
+        const int HA = D.HA, E = D.E, A = D.A, Z = D.Z, Z1 = D.Z1, M = D.M;
+        std::vector<taco_gemm_desc> w;
+        float* gWo = m.G("concat_proj/kernel");
+        w.push_back(wgrad(a.s_ha, HA, a.dy0, Y, gWo, HA, Y, rows));
+        w.push_back(wgrad(a.s_ctx, E, a.dy0, Y, gWo + (long long)HA * Y, E, Y, rows));
+        w.push_back(wgrad(a.s_ha, HA, a.d_gq, A, m.G("attention/query_kernel"), HA, A, rows));
+        float* gWg = m.G("attention_gru/gates_kernel"); float* gWc = m.G("attention_gru/cand_kernel");
+        w.push_back(wgrad(a.s_z, Z, a.d_G, 3 * HA, gWg, Z, 2 * HA, rows));
+        w.push_back(wgrad(a.s_haprev, HA, a.d_G, 3 * HA, gWg + (long long)ZS * 2 * HA, HA, 2 * HA, rows));
+        w.push_back(wgrad(a.s_z, Z, a.d_G + 2 * HA, 3 * HA, gWc, Z, HA, rows));
+        w.push_back(wgrad(a.s_r, HA, a.d_G + 2 * HA, 3 * HA, gWc + (long long)ZS * HA, HA, HA, rows));
+        w.push_back(wgrad(a.s_z1, Z1, a.d_zp, Z, m.G("dec_prenet/dense_2/kernel"), Z1, Z, rows));
+        float* gW1 = m.G("dec_prenet/dense_1/kernel");
+        w.push_back(wgrad(m.W("dec/x_all"), M, a.d_z1p, Z1, gW1, M, Z1, rows));
+        w.push_back(wgrad(a.s_ctxin, E, a.d_z1p, Z1, gW1 + (long long)M * Z1, E, Z1, rows));
+        TACO_TRY(launch_gemm(w.data(), (int)w.size(), prec, s));
+        TACO_TRY(launch_colsum(a.dy0, m.G("concat_proj/bias"), rows, Y, Y, s));
+        TACO_TRY(launch_colsum(a.d_G, m.G("attention_gru/gates_bias"), rows, 2 * HA, 3 * HA, s));
+        TACO_TRY(launch_colsum(a.d_G + 2 * HA, m.G("attention_gru/cand_bias"), rows, HA, 3 * HA, s));
+        TACO_TRY(launch_colsum(a.d_zp, m.G("dec_prenet/dense_2/bias"), rows, Z, Z, s));
+        TACO_TRY(launch_colsum(a.d_z1p, m.G("dec_prenet/dense_1/bias"), rows, Z1, Z1, s));
+        if (m.cfg.attention_type == TACO_ATT_BAH_NORM) TACO_TRY(launch_colsum(a.d_gq, m.G("attention/b"), rows, A, A, s));
+    }
+    // keys / v gradients and the gradient wrt the encoder memory
+    {
+        const int HA = D.HA, E = D.E, A = D.A;
+        (void)HA;
+        float* d_mem = m.W("enc_cbhg/d_rnn_out");
+        if (!b->manual_alignments) {
+            TACO_REQUIRE(m.cfg.attention_type != TACO_ATT_BAH_NORM, TACO_ESTATE, "bah_norm backward (g/v chain) is not built yet");
+            TACO_TRY(launch_att_keys_bwd(a.keys, a.s_q, a.d_ge, m.P("attention/v"), m.W("dec/d_keys"), m.G("attention/v"),
+                                         D.N, D.Ti, D.Td, A, a.fast, s));
+            taco_gemm_desc w = wgrad(a.memory, E, m.W("dec/d_keys"), A, m.G("attention/memory_kernel"), E, A, (long long)D.N * D.Ti);
+            TACO_TRY(launch_gemm(&w, 1, prec, s));
+            taco_gemm_desc e = gd(m.W("dec/d_keys"), m.P("attention/memory_kernel"), d_mem, D.N * D.Ti, E, A, A, A, E); e.transB = 1;
+            TACO_TRY(launch_gemm(&e, 1, prec, s));
+        } else {
+            TACO_CHECK_CUDA(cudaMemsetAsync(d_mem, 0, sizeof(float) * (size_t)D.N * D.Ti * E, s));
+        }
+        // d_memory[n] += a_seq[n]^T . d_ctx[n]
+        std::vector<taco_gemm_desc> pm;
+        for (int n = 0; n < D.N; n++) {
+            taco_gemm_desc d = gd(a.s_a + (long long)n * D.Td * D.Ti, a.d_ctx + (long long)n * D.Td * E, d_mem + (long long)n * D.Ti * E,
+                                  D.Ti, E, D.Td, D.Ti, E, E);
+            d.transA = 1; d.accumulate = 1;
+            pm.push_back(d);
+        }
+        TACO_TRY(launch_gemm(pm.data(), (int)pm.size(), prec, s));
+    }
+    return TACO_OK;
+}
+
+}  // namespace taco

@@ -70,9 +70,14 @@ def _gru(prefix, cin, h):
 
 
 def _cbhg(prefix, cin, bank_size, bank_ch, proj_sizes, proj_width, depth, rnn):
+    """Storage order note: the per-k bank tensors of one kind are emitted back to back so that
+    e.g. all bank biases form one contiguous [bank_size*bank_ch] vector in the flat buffer (the
+    kernels address the concatenated conv bank, modules.py:42-44, as one [.., K*C] matrix).
+    The named TF-layout tensors stay individually addressable."""
     specs: List[ParamSpec] = []
-    for k in range(1, bank_size + 1):
-        specs += _conv_bn("%s/bank_%d" % (prefix, k), k, cin, bank_ch)
+    bank = [_conv_bn("%s/bank_%d" % (prefix, k), k, cin, bank_ch) for k in range(1, bank_size + 1)]
+    for field in range(6):          # kernel, bias, gamma, beta, moving_mean, moving_var
+        specs += [b[field] for b in bank]
     c = bank_size * bank_ch
     for i, p in enumerate(proj_sizes):
         specs += _conv_bn("%s/proj_%d" % (prefix, i + 1), proj_width, c, p)

@@ -90,7 +90,9 @@ def conv1d_bn(x, P, scope, activation, is_training, new_state):
 def maxpool_same_2(x: Tensor) -> Tensor:
     """tf.layers.max_pooling1d(pool=2, stride=1, 'same'): pad right with -inf."""
     nxt = torch.cat([x[:, 1:], torch.full_like(x[:, :1], -float("inf"))], dim=1)
-    return torch.maximum(x, nxt)
+    # torch.where (not torch.maximum): on ties the gradient goes to the FIRST element of the window, as TF's CPU
+    # MaxPoolGrad does; torch.maximum would split it 50/50.  Ties are common here (BN of ReLU zeros).
+    return torch.where(x >= nxt, x, nxt)
 
 
 def highwaynet(x: Tensor, P: Dict[str, Tensor], scope: str) -> Tensor:
