@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — mel-frames/sec of one Tacotron training step (BASELINE.json metric, config C2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference arm: CPU oracle restatement on host cores
+
+A "step" = forward + L1 losses + backward (BPTT) + gradient all-reduce (N>1) + global-norm clip + Adam + BN update on
+one synthetic batch: batch=32/GPU, text_len=128, mel_len=800, 80 mel bins, 1025 linear bins, r=5.
+`value` times K steps with inputs resident in HBM; `e2e` repeats the run through the public Engine API with the
+step's inputs copied from pinned host memory and the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mel-frames/sec (train, batch=32/GPU)"
+UNIT = "mel-frames/s"
+CFG = dict(N=32, T_in=128, T_out=800, num_mels=80, num_freq=1025, r=5)
+# algorithmic HBM bytes of one training step per GPU (targets + params fwd/bwd + grads + clip/Adam)
+ALGO_BYTES_PER_STEP = 486.6e6
+
+
+def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    L = torch.randint(96, Ti + 1, (N,), generator=g, dtype=torch.int32)
+    L[0] = Ti
+    inp = torch.randint(2, 80, (N, Ti), generator=g, dtype=torch.int32)
+    for n in range(N):
+        inp[n, L[n] - 1] = 1
+        inp[n, L[n]:] = 0
+    mel = torch.rand(N, To, CFG["num_mels"], generator=g)
+    lin = torch.rand(N, To, CFG["num_freq"], generator=g)
+    return dict(inputs=inp, input_lengths=L, mel_targets=mel, linear_targets=lin, loss_coeff=torch.ones(N))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tacotron_b200 as tb
+    from importlib import import_module
+    Engine = import_module("multi-speaker-tacotron-tensorflow_b200.engine").Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hp = tb.hparams.override(reduction_factor=CFG["r"], batch_size=CFG["N"])
+    eng = Engine(hp, 1, precision=args.precision, device=local, seed=4321)
+    host = synth_batch(rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.to(eng.dev) for k, v in host.items()}
+
+    def allreduce(flat):
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            return 1.0 / world
+        return 1.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=eng.dev)   # > 126 MB L2
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        eng.train_step(dev, allreduce=allreduce)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.time()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (not timed)
+        ev[i][0].record()
+        eng.train_step(dev, allreduce=allreduce)
+        ev[i][1].record()
+    barrier()
+    t_wall1 = time.time()
+    launches = eng.launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=eng.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    sc = eng.scalars()
+
+    # ---- end to end through the public API: pinned host inputs -> device every step, loss read back every step ----
+    stream_copy = torch.cuda.Stream(device=eng.dev)
+    bufs = [{k: torch.empty_like(v, device=eng.dev) for k, v in host.items()} for _ in range(2)]
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def stage(i):
+        with torch.cuda.stream(stream_copy):
+            for k in pinned:
+                bufs[i % 2][k].copy_(pinned[k], non_blocking=True)
+            e = torch.cuda.Event(); e.record(stream_copy)
+        return e
+
+    def e2e_loop(n):
+        ready = stage(0)
+        losses = []
+        for i in range(n):
+            torch.cuda.current_stream().wait_event(ready)
+            nxt = stage(i + 1) if i + 1 < n else None
+            eng.train_step(bufs[i % 2], allreduce=allreduce)
+            losses.append(eng.scalars()["loss"])       # device -> host read of the step's loss (synchronises)
+            ready = nxt
+        return losses
+
+    e2e_loop(max(1, min(2, args.warmup)))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    frames = world * CFG["N"] * CFG["T_out"] * args.steps
+    if rank == 0:
+        peaks, which = measured_peaks()
+        ms_step = total_ms / args.steps
+        ach = ALGO_BYTES_PER_STEP / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel, 1025-bin linear, r=5, single-speaker",
+                       "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
+                       "timing": "CUDA events per step on the compute stream, max over ranks"},
+            "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
+                    "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream) + loss read-back each step"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": which,
+                         "note": "whole-step algorithmic bytes (486.6 MB, SURVEY.md 8d) / step time; the step is bound by serial recurrence latency, see DESIGN.md"},
+            "loss": sc["loss"],
+        }
+        if args.cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_steps: int = 1, threads: int = 0):
+    """The CPU oracle restatement (torch-CPU, all host cores) timed on one full C2 training step."""
+    import torch
+    import tacotron_b200 as tb
+    from oracle import tacotron_oracle as O
+    n = threads or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    hp = tb.hparams.override(reduction_factor=CFG["r"], batch_size=CFG["N"])
+    P = tb.params.init_params(hp, 1, seed=4321)
+    names = [k for k in P if not (k.endswith("moving_mean") or k.endswith("moving_var"))]
+    m = {k: torch.zeros_like(P[k]) for k in names}
+    v = {k: torch.zeros_like(P[k]) for k in names}
+    b = synth_batch(0)
+    times = []
+    for i in range(sample_steps):
+        t0 = time.perf_counter()
+        res = O.train_step(P, m, v, hp, b, i, True, 1, "none")
+        times.append(time.perf_counter() - t0)
+        P, m, v = res["params"], res["m"], res["v"]
+    sec = sum(times) / len(times)
+    return {"value": CFG["N"] * CFG["T_out"] / sec, "unit": UNIT, "cores": n, "kind": "port",
+            "sample": "%d full C2 training step(s) (fwd+bwd+clip+Adam, fp32) of the TF-semantics oracle on torch-CPU, %.1f s/step" % (sample_steps, sec)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    base = cpu_baseline(sample_steps=steps)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 0, "ms_per_step": 1e3 * CFG["N"] * CFG["T_out"] / base["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "C2: train step, batch=32, text_len=128, mel_len=800, r=5 (CPU restatement of the TF graph; TF 1.x itself cannot be installed)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
