@@ -195,7 +195,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel, 1025-bin linear, r=5, single-speaker",
                        "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
                        "timing": "CUDA events per step on the compute stream, max over ranks"},
@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

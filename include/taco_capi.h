@@ -49,9 +49,11 @@ extern "C" {
 #define TACO_SPK_DEEPVOICE       2   /* five dense(16->d, softsign) sites */
 #define TACO_SPK_DEEPVOICE_TABLE 3   /* speaker_embedding_size == 1: five lookup tables */
 
-/* compute precision of the contraction kernels (state, statistics, scans stay fp32) */
+/* compute precision of the contraction kernels (state, statistics, scans stay fp32):
+ *   FP32: every contraction in fp32 FMA (exact-parity mode)
+ *   TF32: GEMM-shaped work on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM), fast tanh/sigmoid in the recurrences */
 #define TACO_PREC_FP32 0
-#define TACO_PREC_BF16 1
+#define TACO_PREC_TF32 1
 
 /* POD mirror of the hparams the hot path reads (reference: hparams.py:31-69,83-94). */
 typedef struct taco_config {

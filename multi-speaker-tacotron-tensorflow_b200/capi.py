@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libtaco_b200.so")
 TACO_ABI_VERSION = 1
 ATT_TYPES = {"bah_mon": 0, "bah": 1, "bah_norm": 2}
 SPK_MODES = {"none": 0, "simple": 1, "deepvoice": 2, "deepvoice_table": 3}
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "tf32": 1}
 
 
 class TacoConfig(C.Structure):

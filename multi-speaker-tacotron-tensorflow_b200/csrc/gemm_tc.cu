@@ -1,0 +1,363 @@
+// Tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma kind::tf32
+// with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.  It serves the same descriptor (taco_gemm_desc) as the
+// SIMT kernel: dense layers, conv1d as implicit GEMM (tap addressing expressed as TMA coordinates over the zero-padded
+// activation buffer), data gradients and split-K weight gradients, with bias / activation / pad-row mask / row remap /
+// batch-norm column statistics fused in the epilogue.      reference ops covered: see gemm_simt.cu header.
+//
+// Operands stay fp32 in HBM (TF32 rounding happens inside the tensor core), so no cast or repack pass exists:
+//   A(m,k) row-major [M,K]      -> K-major  SW128 tile  (one TMA box  {32 k, 128 m})
+//   A^T    stored [K(rows), M]  -> MN-major SW128 tile  (four TMA boxes {32 m, 32 k})     (weight gradients)
+//   B[k*ldb+n] (TF [in,out])    -> MN-major SW128 tile  (four TMA boxes {32 n, 32 k})
+//   B[n*ldb+k]                  -> K-major  SW128 tile  (one TMA box  {32 k, 128 n})     (data gradients)
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue (one TMEM
+// lane quarter each).  4-stage mbarrier ring; one 128x128 output tile (x one K split) per CTA.
+#include "common.cuh"
+#include "kernels.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace taco {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand per stage
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+    float* C;
+    int M, N, K, ldc;
+    int a_mn_major, b_mn_major;          // 1: MN-major (four boxes), 0: K-major (one box)
+    int a_tap, a_ctap;                   // strided-tap addressing for A (lda > ctap)
+    float alpha; int accumulate;
+    const float* bias; int act;
+    int mask_period, mask_lo, mask_hi;
+    int remap_period; long long remap_outer, remap_inner;
+    double* colsum; double* colsumsq;
+    int split_k, vecC;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only swizzled layout for MN-major 32-bit
+// operands: 128 B x 4-row atoms, Swizzle<2,5,2>; TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// lane l ends with sum over the warp's lanes of v[l]
+__device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const bool up = (lane & s) != 0;
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                         // [STAGES][16 KB]
+    uint8_t* sB = smem + TC_STAGES * TC_TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * TC_STAGES * TC_TILE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* tmem_full = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tilesN = (p.N + TC_BN - 1) / TC_BN;
+    const int tm = blockIdx.x / tilesN, tn = blockIdx.x % tilesN;
+    const int m0 = tm * TC_BM, n0 = tn * TC_BN;
+    const int ktiles = (p.K + TC_BK - 1) / TC_BK;
+    const int kt_per = (ktiles + p.split_k - 1) / p.split_k;
+    const int kt0 = blockIdx.y * kt_per, kt1 = min(ktiles, kt0 + kt_per);
+    const int nkt = kt1 - kt0;
+    if (nkt <= 0) return;      // uniform per CTA
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int it = 0; it < nkt; it++) {
+                const int stage = it % TC_STAGES, round = it / TC_STAGES;
+                if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
+                mbar_expect_tx(&full_bar[stage], 2 * TC_TILE_BYTES);
+                const int k0 = (kt0 + it) * TC_BK;
+                uint8_t* a = sA + stage * TC_TILE_BYTES;
+                uint8_t* b = sB + stage * TC_TILE_BYTES;
+                if (!p.a_mn_major) {
+                    if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
+                    else tma_load_2d(a, &mapA, k0, m0, &full_bar[stage]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int mm = m0 + g * 32;
+                        if (p.a_tap) tma_load_2d(a + g * 4096, &mapA, mm % p.a_ctap, k0 + mm / p.a_ctap, &full_bar[stage]);
+                        else tma_load_2d(a + g * 4096, &mapA, mm, k0, &full_bar[stage]);
+                    }
+                }
+                if (!p.b_mn_major) {
+                    tma_load_2d(b, &mapB, k0, n0, &full_bar[stage]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) tma_load_2d(b + g * 4096, &mapB, n0 + g * 32, k0, &full_bar[stage]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=TF32 [7,10)/[10,13), majors [15],[16], N>>3 [17,23), M>>4 [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) | ((uint32_t)p.b_mn_major << 16) |
+                               ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int it = 0; it < nkt; it++) {
+            const int stage = it % TC_STAGES, round = it / TC_STAGES;
+            mbar_wait(&full_bar[stage], round & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a = smem_u32(sA + stage * TC_TILE_BYTES), b = smem_u32(sB + stage * TC_TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; kk++) {
+                    // K-major: 8 tf32 = 32 B along the swizzled 128 B row, 8-row groups 1024 B apart (SBO).
+                    // MN-major: one 8-row k-group (1024 B) per MMA; 32-element MN groups 4096 B apart (LBO); SBO = 1024 B.
+                    //           (32-bit MN-major uses 4-row swizzle atoms: two 512 B k-groups per MMA, SBO = 512 B)
+                    const uint64_t ad = p.a_mn_major ? umma_desc(a + kk * 1024, 4096, 512, 1) : umma_desc(a + kk * 32, 16, 1024, 2);
+                    const uint64_t bd = p.b_mn_major ? umma_desc(b + kk * 1024, 4096, 512, 1) : umma_desc(b + kk * 32, 16, 1024, 2);
+                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
+                if (it == nkt - 1) umma_commit(tmem_full);       // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int gm = m0 + q * 32 + lane;
+        const bool row_ok = gm < p.M;
+        bool masked = false;
+        if (p.mask_period > 0) { const int t = gm % p.mask_period; masked = (t < p.mask_lo) || (t >= p.mask_hi); }
+        float* crow = nullptr;
+        if (row_ok)
+            crow = p.remap_period > 0
+                ? p.C + (long long)(gm / p.remap_period) * p.remap_outer + (long long)(gm % p.remap_period) * p.remap_inner
+                : p.C + (long long)gm * p.ldc;
+        const bool atomic = (p.split_k > 1) || (p.accumulate == 2);
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            if (n0 + c0 >= p.N) break;                           // warp-uniform
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int gn = n0 + c0 + j;
+                float x = p.alpha * v[j];
+                if (gn < p.N) {
+                    if (!atomic) { if (p.bias) x += __ldg(p.bias + gn); x = apply_act(x, p.act); }
+                    else if (p.bias && blockIdx.y == 0) x += __ldg(p.bias + gn);
+                } else x = 0.f;
+                v[j] = (masked || !row_ok) ? 0.f : x;
+            }
+            if (row_ok) {
+                if (atomic) {
+                    if (!masked) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) atomicAdd(crow + n0 + c0 + j, v[j]);
+                    }
+                } else {
+                    if (p.accumulate == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) v[j] += crow[n0 + c0 + j];
+                    }
+                    if (p.vecC && n0 + c0 + 31 < p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(crow + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) crow[n0 + c0 + j] = v[j];
+                    }
+                }
+            }
+            if (p.colsum) {                                     // kernel-uniform
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) sq[j] = v[j] * v[j];
+                const float s1 = warp_transpose_reduce(v, lane);
+                const float s2 = warp_transpose_reduce(sq, lane);
+                if (n0 + c0 + lane < p.N) {
+                    atomicAdd(p.colsum + n0 + c0 + lane, (double)s1);
+                    atomicAdd(p.colsumsq + n0 + c0 + lane, (double)s2);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int get_encode() {
+    static std::once_flag once;
+    static int rc = TACO_OK;
+    std::call_once(once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { rc = TACO_ECUDA; return; }
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    });
+    if (rc != TACO_OK) set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return rc;
+}
+
+// fp32 2-D tensor map: dim0 contiguous (extent d0), dim1 rows (extent d1, stride ld elements), box {b0, b1}, 128B swizzle
+static int make_map(CUtensorMap* map, const float* base, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1, bool mn_major, bool soft = false) {
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && soft) return TACO_ENOTSUP;
+    TACO_REQUIRE(r == CUDA_SUCCESS, TACO_ECUDA, "cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r,
+                 (const void*)base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+    return TACO_OK;
+}
+
+// Can this problem run on the tensor-core path?  (TMA needs 16-byte aligned bases and row pitches; taps must align to tiles.)
+bool gemm_tc_eligible(const taco_gemm_desc& g) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (!al16(g.A) || !al16(g.B)) return false;
+    if (g.lda % 4 != 0 || g.ldb % 4 != 0) return false;
+    const bool tap = g.ctap > 0 && (g.lda != g.ctap || g.ctap % 32 == 0);
+    if (tap && g.ctap % 32 != 0) return false;
+    if ((long long)g.M * g.N * g.K < (1ll << 21)) return false;      // tiny problems: launch-bound either way, keep exact fp32
+    return true;
+}
+
+int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
+    TACO_TRY(get_encode());
+    static bool configured = false;
+    if (!configured) {
+        TACO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        configured = true;
+    }
+    TACO_REQUIRE(!((g.split_k > 1 || g.accumulate == 2) && (g.act != 0 || g.colsum != nullptr)), TACO_EINVAL,
+                 "gemm: atomic accumulation cannot carry an activation or column statistics");
+    const float* A = static_cast<const float*>(g.A);
+    const float* B = static_cast<const float*>(g.B);
+    // lda == ctap with ctap % 32 != 0 (80-channel mel input): im2col rows are contiguous, so the map uses overlapping
+    // rows (pitch lda < extent K); if the driver rejects that the caller falls back to the SIMT kernel.
+    const bool tap = g.ctap > 0 && (g.lda != g.ctap || g.ctap % 32 == 0);
+    const bool overlap = g.ctap > 0 && !tap;
+    const int ntaps = g.ctap > 0 ? ((g.transA ? g.M : g.K) + g.ctap - 1) / g.ctap : 1;
+    CUtensorMap mapA, mapB;
+    if (!g.transA) {
+        // K-major A: box {32 k, 128 m}
+        if (tap) TACO_TRY(make_map(&mapA, A, (uint64_t)g.ctap, (uint64_t)g.M + ntaps - 1, (uint64_t)g.lda, TC_BK, TC_BM, false));
+        else TACO_TRY(make_map(&mapA, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TC_BK, TC_BM, false, overlap));
+    } else {
+        // A^T: stored [rows = K, cols = M (taps)]: MN-major, boxes {32 m, 32 k}
+        if (tap) TACO_TRY(make_map(&mapA, A, (uint64_t)g.ctap, (uint64_t)g.K + ntaps - 1, (uint64_t)g.lda, 32, TC_BK, true));
+        else TACO_TRY(make_map(&mapA, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TC_BK, true, overlap));
+    }
+    if (!g.transB) TACO_TRY(make_map(&mapB, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TC_BK, true));     // MN-major
+    else TACO_TRY(make_map(&mapB, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TC_BK, TC_BN, false));            // K-major
+    TcParams p{};
+    p.C = g.C; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc;
+    p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1;
+    p.a_tap = tap ? 1 : 0; p.a_ctap = tap ? g.ctap : 1;
+    p.alpha = g.alpha; p.accumulate = g.accumulate; p.bias = g.bias; p.act = g.act;
+    p.mask_period = g.mask_period; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
+    p.remap_period = g.remap_period; p.remap_outer = g.remap_outer; p.remap_inner = g.remap_inner;
+    p.colsum = g.colsum; p.colsumsq = g.colsumsq;
+    const int ktiles = cdiv(g.K, TC_BK);
+    p.split_k = g.split_k < ktiles ? g.split_k : ktiles;
+    if (p.split_k < 1) p.split_k = 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    p.vecC = g.remap_period > 0 ? (al16(g.C) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al16(g.C) && g.ldc % 4 == 0);
+    dim3 grid(cdiv(g.M, TC_BM) * cdiv(g.N, TC_BN), p.split_k);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mapA, mapB, p);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+}  // namespace taco

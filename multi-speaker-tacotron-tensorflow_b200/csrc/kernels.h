@@ -8,6 +8,9 @@ namespace taco {
 // gemm_simt.cu / gemm_tc.cu
 int launch_gemm_simt(const taco_gemm_desc* d, int n, cudaStream_t s);
 int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s);
+bool gemm_tc_eligible(const taco_gemm_desc& g);
+int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s);   // TACO_ENOTSUP: caller falls back to SIMT
+constexpr int TACO_ENOTSUP = -100;
 
 // elementwise.cu
 int launch_fill(float* p, long long n, float v, cudaStream_t s);

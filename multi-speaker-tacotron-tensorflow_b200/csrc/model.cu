@@ -17,9 +17,21 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
+// Route each problem: tcgen05/TMA kernel in TF32 mode when its operands satisfy TMA's alignment rules, otherwise
+// (and always in FP32 mode) the exact fp32 SIMT kernel.
 int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s) {
-    (void)precision;   // TACO_PREC_BF16 tensor-core path is routed here once built; fp32 SIMT is exact
-    return launch_gemm_simt(d, n_problems, s);
+    if (precision == TACO_PREC_FP32) return launch_gemm_simt(d, n_problems, s);
+    std::vector<taco_gemm_desc> rest;
+    for (int i = 0; i < n_problems; i++) {
+        if (gemm_tc_eligible(d[i])) {
+            int rc = launch_gemm_tc(d[i], s);
+            if (rc == TACO_OK) continue;
+            if (rc != TACO_ENOTSUP) return rc;
+        }
+        rest.push_back(d[i]);
+    }
+    if (!rest.empty()) return launch_gemm_simt(rest.data(), (int)rest.size(), s);
+    return TACO_OK;
 }
 
 // ---- Model helpers ------------------------------------------------------------------------------------
@@ -160,8 +172,20 @@ void Model::plan(const Shape& s) {
             add("dec/d_keys", {(int64_t)N * s.Ti, A});
         }
     }
-    add("linear_outputs", {N, s.To, c.num_freq});
-    if (tr) { add("d_linear", {N, s.To, c.num_freq}); add("post_cbhg/d_mel_loss", {post.rows, c.num_mels}); }
+    // The linear-spectrogram tensors use a row pitch rounded up to 4 floats (1025 -> 1028) so TMA can address them
+    // (16-byte pitches); the pad columns stay zero.  "linear_outputs" is exposed as a strided [N,To,F] view.
+    {
+        const int64_t Fp = (c.num_freq + 3) / 4 * 4;
+        add("linear_buf", {(int64_t)N * s.To, Fp});
+        Region r = regions["linear_buf"];
+        r.ndim = 3; r.dims[0] = N; r.dims[1] = s.To; r.dims[2] = c.num_freq;
+        r.strides[0] = (int64_t)s.To * Fp; r.strides[1] = Fp; r.strides[2] = 1;
+        r.numel = (int64_t)N * s.To * c.num_freq;
+        regions["linear_outputs"] = r;
+        add("linear/w_pad", {2 * (int64_t)c.post_rnn_size + ((c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0), Fp});
+        if (tr) add("d_linear", {(int64_t)N * s.To, Fp});
+    }
+    if (tr) add("post_cbhg/d_mel_loss", {post.rows, c.num_mels});
     add("scalars", {8}, 0, true);
     add("scalars_f", {8});
     // zero-copy view of the mel outputs inside the post-net's padded input
@@ -227,8 +251,9 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     TACO_TRY(cbhg_forward(m, m.post, nullptr, nullptr, nullptr, tr, s));
     // ---- linear-spectrogram projection (tacotron.py:235) ----
     {
-        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq;
-        taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.P("linear/kernel"), m.W("linear_outputs"), m.shape.N * m.shape.To, F, Hp2, Hp2, F, F);
+        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 3) / 4 * 4;
+        TACO_TRY(launch_copy2d(m.W("linear/w_pad"), m.P("linear/kernel"), Hp2, F, Fp, F, s));     // 16-byte row pitch for TMA
+        taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.W("linear/w_pad"), m.W("linear_buf"), m.shape.N * m.shape.To, F, Hp2, Hp2, Fp, Fp);
         d.bias = m.P("linear/bias");
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
@@ -259,19 +284,20 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         lo = c.priority_lo; hi = c.priority_hi;
         w_all = (float)(0.5 / cnt_lin); w_band = (float)(0.5 / ((double)N * To * (hi - lo)));
     }
-    TACO_TRY(launch_l1_loss(m.W("linear_outputs"), (long long)To * F, F, b->linear_targets, b->loss_coeff,
-                            m.W("d_linear"), (long long)To * F, F, N, To, F, w_all, w_band, lo, hi, sc + 3, s));
+    const int Fp = (F + 3) / 4 * 4;
+    TACO_TRY(launch_l1_loss(m.W("linear_buf"), (long long)To * Fp, Fp, b->linear_targets, b->loss_coeff,
+                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s));
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
                             m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
                             (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
     // ---- linear projection backward ----
     {
         const int Hp2 = 2 * c.post_rnn_size; const long long rows = (long long)N * To;
-        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel"), Hp2, F, (int)rows, Hp2, F, F);
+        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel"), Hp2, F, (int)rows, Hp2, Fp, F);
         w.transA = 1; w.accumulate = 1; w.split_k = 8;
         TACO_TRY(launch_gemm(&w, 1, prec, s));
-        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, F, s));
-        taco_gemm_desc e = gd0(m.W("d_linear"), m.P("linear/kernel"), m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, F, F, Hp2);
+        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, s));
+        taco_gemm_desc e = gd0(m.W("d_linear"), m.W("linear/w_pad"), m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
         e.transB = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }

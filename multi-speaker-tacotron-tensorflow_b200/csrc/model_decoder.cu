@@ -88,7 +88,7 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     }
     AttArgs a{};
     a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
-    a.att_type = m.cfg.attention_type; a.fast = (prec == TACO_PREC_BF16);
+    a.att_type = m.cfg.attention_type; a.fast = (prec != TACO_PREC_FP32);
     a.px = m.W("dec/px"); a.memory = memory; a.keys = m.W("dec/keys");
     a.spk = D.SPK ? m.W("spk/embed") : nullptr;
     a.ha0 = m.has_region("spk/att_init") ? m.W("spk/att_init") : nullptr;
@@ -181,7 +181,7 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
 
     AttArgs a{};
     a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
-    a.att_type = m.cfg.attention_type; a.fast = (prec == TACO_PREC_BF16);
+    a.att_type = m.cfg.attention_type; a.fast = (prec != TACO_PREC_FP32);
     a.memory = m.W("enc_cbhg/rnn_out"); a.keys = m.W("dec/keys");
     a.manual = b->manual_alignments;
     fill_att_weights(m, D, a);
