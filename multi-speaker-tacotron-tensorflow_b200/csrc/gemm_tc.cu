@@ -16,10 +16,11 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace taco {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand per stage
 constexpr int TC_SMEM = TC_STAGES * 2 * TC_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -109,6 +110,70 @@ __device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
     return v[0];
 }
 
+template <int ACT> __device__ __forceinline__ float act_ct(float x) {
+    if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
+    if (ACT == ACT_TANH) return tanhf(x);
+    if (ACT == ACT_SOFTSIGN) return x / (1.0f + fabsf(x));
+    return x;
+}
+
+// One 32x32 chunk of the output tile: rows {4i+lr}, columns gn..gn+3 per lane, read back from the staging buffer.
+template <int ACT, bool ATOMIC>
+__device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, float* const crow[8], uint32_t okmask, uint32_t maskmask,
+                                          int lr, int lc, int gn, bool add_bias, float cs[4], float cq[4]) {
+    const bool full4 = gn + 3 < p.N;
+    const bool vec = p.vecC && full4;
+    float bz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias && add_bias) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (gn + e < p.N) bz[e] = __ldg(p.bias + gn + e);
+    }
+    const float alpha = p.alpha;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (!((okmask >> i) & 1u)) continue;
+        const float4 t4 = *reinterpret_cast<const float4*>(stg + (i * 4 + lr) * 36 + lc);
+        const bool msk = (maskmask >> i) & 1u;
+        float x[4];
+        x[0] = act_ct<ACT>(fmaf(alpha, t4.x, bz[0])); x[1] = act_ct<ACT>(fmaf(alpha, t4.y, bz[1]));
+        x[2] = act_ct<ACT>(fmaf(alpha, t4.z, bz[2])); x[3] = act_ct<ACT>(fmaf(alpha, t4.w, bz[3]));
+        if (msk) { x[0] = 0.f; x[1] = 0.f; x[2] = 0.f; x[3] = 0.f; }
+        float* dst = crow[i] + gn;
+        if (ATOMIC) {
+            if (!msk) {
+                if (vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) if (gn + e < p.N) atomicAdd(dst + e, x[e]);
+                }
+            }
+        } else {
+            if (vec) {
+                if (p.accumulate == 1) { const float4 o = *reinterpret_cast<const float4*>(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
+                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (gn + e < p.N) { if (p.accumulate == 1) x[e] += dst[e]; dst[e] = x[e]; } else x[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
+        }
+    }
+}
+
+// debug timeline (ns, %globaltimer) of CTA 0: 0 start, 1 setup done, 3 first tile landed, 4 last MMA issued, 5 accumulator ready,
+// 6 epilogue done, 7 teardown.  Read with taco_debug_timeline().
+__device__ unsigned long long g_tc_stamp[8];
+#define TC_STAMP(i)                                                                                       \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) {                              \
+            unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                  \
+            g_tc_stamp[i] = _t;                                                                           \
+        }                                                                                                 \
+    } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -129,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int kt0 = blockIdx.y * kt_per, kt1 = min(ktiles, kt0 + kt_per);
     const int nkt = kt1 - kt0;
     if (nkt <= 0) return;      // uniform per CTA
+    TC_STAMP(0);
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
@@ -145,6 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    TC_STAMP(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -183,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int it = 0; it < nkt; it++) {
             const int stage = it % TC_STAGES, round = it / TC_STAGES;
             mbar_wait(&full_bar[stage], round & 1);
+            if (it == 0) TC_STAMP(3);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t a = smem_u32(sA + stage * TC_TILE_BYTES), b = smem_u32(sB + stage * TC_TILE_BYTES);
@@ -197,77 +265,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
                 if (it == nkt - 1) umma_commit(tmem_full);       // accumulator complete
+                if (it == nkt - 1) TC_STAMP(4);
             }
             __syncwarp();
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // TMEM -> registers (row per lane) -> 32x32 transpose through shared memory -> coalesced 128-byte row segments.
+        // Warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the four 32-column chunks.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         mbar_wait(tmem_full, 0);
+        if (warp == 4) TC_STAMP(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int gm = m0 + q * 32 + lane;
-        const bool row_ok = gm < p.M;
-        bool masked = false;
-        if (p.mask_period > 0) { const int t = gm % p.mask_period; masked = (t < p.mask_lo) || (t >= p.mask_hi); }
-        float* crow = nullptr;
-        if (row_ok)
-            crow = p.remap_period > 0
-                ? p.C + (long long)(gm / p.remap_period) * p.remap_outer + (long long)(gm % p.remap_period) * p.remap_inner
-                : p.C + (long long)gm * p.ldc;
+        float* stg = reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 36);   // pipeline smem is idle once the accumulator is complete
+        const int lr = lane >> 3, lc = (lane & 7) * 4;
         const bool atomic = (p.split_k > 1) || (p.accumulate == 2);
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        float* crow[8];
+        uint32_t okmask = 0, maskmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int gm = m0 + q * 32 + i * 4 + lr;
+            crow[i] = p.C;
+            if (gm < p.M) {
+                okmask |= 1u << i;
+                if (p.mask_period > 0) { const int t = gm % p.mask_period; if (t < p.mask_lo || t >= p.mask_hi) maskmask |= 1u << i; }
+                crow[i] = p.remap_period > 0
+                    ? p.C + (long long)(gm / p.remap_period) * p.remap_outer + (long long)(gm % p.remap_period) * p.remap_inner
+                    : p.C + (long long)gm * p.ldc;
+            }
+        }
+        for (int cc = 0; cc < 2; cc++) {
+            const int c0 = (half * 2 + cc) * 32;
             if (n0 + c0 >= p.N) break;                           // warp-uniform
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int gn = n0 + c0 + j;
-                float x = p.alpha * v[j];
-                if (gn < p.N) {
-                    if (!atomic) { if (p.bias) x += __ldg(p.bias + gn); x = apply_act(x, p.act); }
-                    else if (p.bias && blockIdx.y == 0) x += __ldg(p.bias + gn);
-                } else x = 0.f;
-                v[j] = (masked || !row_ok) ? 0.f : x;
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-            if (row_ok) {
-                if (atomic) {
-                    if (!masked) {
+            __syncwarp();
+            const int gn = n0 + c0 + lc;
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (atomic) epi_chunk<ACT_NONE, true>(p, stg, crow, okmask, maskmask, lr, lc, gn, blockIdx.y == 0, cs, cq);
+            else switch (p.act) {                                // kernel-uniform
+                case ACT_RELU:     epi_chunk<ACT_RELU, false>(p, stg, crow, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
+                case ACT_SIGMOID:  epi_chunk<ACT_SIGMOID, false>(p, stg, crow, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
+                case ACT_TANH:     epi_chunk<ACT_TANH, false>(p, stg, crow, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
+                case ACT_SOFTSIGN: epi_chunk<ACT_SOFTSIGN, false>(p, stg, crow, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
+                default:           epi_chunk<ACT_NONE, false>(p, stg, crow, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
+            }
+            __syncwarp();                                        // staging buffer is rewritten by the next chunk
+            if (p.colsum) {                                      // kernel-uniform
 #pragma unroll
-                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) atomicAdd(crow + n0 + c0 + j, v[j]);
-                    }
-                } else {
-                    if (p.accumulate == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) v[j] += crow[n0 + c0 + j];
-                    }
-                    if (p.vecC && n0 + c0 + 31 < p.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(crow + n0 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (n0 + c0 + j < p.N) crow[n0 + c0 + j] = v[j];
-                    }
+                for (int e = 0; e < 4; e++) {
+                    cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
+                    cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
                 }
-            }
-            if (p.colsum) {                                     // kernel-uniform
-                float sq[32];
+                if (lane < 8) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) sq[j] = v[j] * v[j];
-                const float s1 = warp_transpose_reduce(v, lane);
-                const float s2 = warp_transpose_reduce(sq, lane);
-                if (n0 + c0 + lane < p.N) {
-                    atomicAdd(p.colsum + n0 + c0 + lane, (double)s1);
-                    atomicAdd(p.colsumsq + n0 + c0 + lane, (double)s2);
+                    for (int e = 0; e < 4; e++)
+                        if (gn + e < p.N) { atomicAdd(p.colsum + gn + e, (double)cs[e]); atomicAdd(p.colsumsq + gn + e, (double)cq[e]); }
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (warp == 4) TC_STAMP(6);
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+        TC_STAMP(7);
     }
 }
 
@@ -360,4 +429,11 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     return TACO_OK;
 }
 
+int debug_timeline(unsigned long long out[8]) {
+    TACO_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_tc_stamp, sizeof(unsigned long long) * 8));
+    return TACO_OK;
+}
+
 }  // namespace taco
+
+extern "C" int taco_debug_timeline(unsigned long long out[8]) { return taco::debug_timeline(out); }
