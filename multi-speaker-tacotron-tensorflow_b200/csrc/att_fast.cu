@@ -1,0 +1,863 @@
+// Fast attention recurrence for the tensor-core precision mode (same maths, arguments and stash layout as attention.cu).
+//   reference: models/rnn_wrappers.py:218-341,367-378,405-415; models/tacotron.py:127-170; SURVEY.md §8a D1-D7, App. C.
+//
+// A non-portable cluster of 16 CTAs owns 8 batch rows.  Everything the serial chain touches is shared-memory resident
+// for all decoder steps: each CTA's bf16 slice of the decoder weights (1/16 of every layer's output units), its slice
+// of the attention keys and of the encoder memory.  Per-step products run on mma.sync.m16n8k16 (weight rows = M, the 8
+// batch rows = N); state, scores, the monotonic scan and all accumulation stay fp32.  Slices are exchanged with
+// st.async DSMEM stores that complete on the receiver's mbarrier (7 exchanges per step, no cluster barriers).
+#include "common.cuh"
+#include "kernels.h"
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cfloat>
+
+namespace cg = cooperative_groups;
+
+namespace taco {
+
+constexpr int AF_C = 16, AF_R = 8, AF_NT = 256;
+constexpr int AF_E = 256, AF_A = 256, AF_HA = 256, AF_Z1 = 256, AF_Z = 128, AF_Y = 256;   // instantiated sizes
+constexpr int AF_U = 16;                 // units per CTA of the 256-wide layers
+constexpr int AF_UZ = AF_Z / AF_C;       // 8
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ uint32_t af_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void af_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(af_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void af_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(af_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void af_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(af_u32(bar)), "r"(parity) : "memory");
+}
+// send this CTA's staged block (nbytes, multiple of 16) to the same offset `dst` in every peer, completing on the peer's `bar`
+__device__ __forceinline__ void af_push(const void* stage, void* dst, uint64_t* bar, int nbytes, int tid) {
+    const int nq = nbytes / 16;
+    for (int idx = tid; idx < AF_C * nq; idx += AF_NT) {
+        const uint32_t peer = idx / nq, q = idx % nq;
+        const uint4 v = *(reinterpret_cast<const uint4*>(stage) + q);
+        uint32_t d, b;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(af_u32(dst) + q * 16), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(af_u32(bar)), "r"(peer));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                     ::"r"(d), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(b) : "memory");
+    }
+}
+__device__ __forceinline__ void af_ldm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void af_mma(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float af_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float af_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// acc += Wt[m0 .. m0+15][kw0 + 16*kt ...] . vec   for nk k-tiles;  Wt: bf16 [rows][KP]; vec: bf16 blocked [K/UB][R][UB], k index kv0 + ...
+template <int UB>
+__device__ __forceinline__ void af_mma_run(float acc[4], const bf16* Wt, int KP, int m0, int kw0, const bf16* vec, int kv0, int nk, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t a_base = af_u32(Wt + (size_t)(m0 + (lane & 15)) * KP + kw0 + (lane >> 4) * 8);
+    for (int kk = 0; kk < nk; kk++) {
+        uint32_t a0, a1, a2, a3;
+        af_ldm4(a_base + (uint32_t)kk * 32, a0, a1, a2, a3);
+        const int ka = kv0 + kk * 16 + 2 * t, kb = ka + 8;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vec + ((ka / UB) * AF_R + g) * UB + (ka % UB));
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vec + ((kb / UB) * AF_R + g) * UB + (kb % UB));
+        af_mma(acc, a0, a1, a2, a3, b0, b1);
+    }
+}
+// fragment -> red[slot][m][r]  (16 rows x 8 batch rows per slot)
+__device__ __forceinline__ void af_red_store(float* red, int slot, const float acc[4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    float* rp = red + slot * 128;
+    *reinterpret_cast<float2*>(rp + g * 8 + 2 * t) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(rp + (g + 8) * 8 + 2 * t) = make_float2(acc[2], acc[3]);
+}
+__device__ __forceinline__ float af_red_sum(const float* red, int slot0, int nslots, int stride, int m, int r) {
+    float s = 0.f;
+    for (int k = 0; k < nslots; k++) s += red[(slot0 + k * stride) * 128 + m * 8 + r];
+    return s;
+}
+// load W[(r0 + m)*ld + c0 + k] (m < rows, k < K) -> dst[m*KP + k] as bf16 (natural orientation: rows of W are A rows)
+__device__ void af_load_rows(bf16* dst, int KP, const float* W, long long ld, int r0, int rows, int rows_pad, int c0, int K, int tid) {
+    for (int idx = tid; idx < rows_pad * K; idx += AF_NT) {
+        const int m = idx / K, k = idx % K;
+        dst[m * KP + k] = __float2bfloat16(m < rows ? __ldg(W + (long long)(r0 + m) * ld + c0 + k) : 0.f);
+    }
+}
+// load W[(r0 + k)*ld + c0 + m] -> dst[m*KP + k]  (transposed: columns of W become A rows)
+__device__ void af_load_cols(bf16* dst, int KP, const float* W, long long ld, int r0, int K, int c0, int cols, int cols_pad, int tid) {
+    for (int idx = tid; idx < cols_pad * K; idx += AF_NT) {
+        const int k = idx / cols_pad, m = idx % cols_pad;
+        dst[m * KP + k] = __float2bfloat16(m < cols ? __ldg(W + (long long)(r0 + k) * ld + c0 + m) : 0.f);
+    }
+}
+
+struct AfFwdSmem {
+    // bf16 weight slices (A operands, [rows][K+8])
+    static constexpr int KP256 = 264, KP384 = 392, KP128 = 136;
+    static constexpr size_t W1c = 0;                                   // [16][264]
+    static constexpr size_t W2 = W1c + 16 * KP256 * 2;                 // [16][264] (8 valid rows)
+    static constexpr size_t Wg = W2 + 16 * KP256 * 2;                  // [32][392]  rows: r units | u units; k: z(128) | ha(256)
+    static constexpr size_t Wcz = Wg + 32 * KP384 * 2;                 // [16][136]
+    static constexpr size_t Wch = Wcz + 16 * KP128 * 2;                // [16][264]
+    static constexpr size_t Wq = Wch + 16 * KP256 * 2;                 // [16][264]
+    static constexpr size_t Woh = Wq + 16 * KP256 * 2;                 // [16][264]
+    static constexpr size_t Woc = Woh + 16 * KP256 * 2;                // [16][264]
+    static constexpr size_t w_end = Woc + 16 * KP256 * 2;
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int grp = blockIdx.x / AF_C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int R = AF_R, U = AF_U, UZ = AF_UZ, E = AF_E, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
+    const int Ti = a.Ti, Td = a.Td;
+    const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    using S = AfFwdSmem;
+
+    extern __shared__ __align__(128) uint8_t sm[];
+    bf16* W1c_s = reinterpret_cast<bf16*>(sm + S::W1c); bf16* W2_s = reinterpret_cast<bf16*>(sm + S::W2);
+    bf16* Wg_s = reinterpret_cast<bf16*>(sm + S::Wg);   bf16* Wcz_s = reinterpret_cast<bf16*>(sm + S::Wcz);
+    bf16* Wch_s = reinterpret_cast<bf16*>(sm + S::Wch); bf16* Wq_s = reinterpret_cast<bf16*>(sm + S::Wq);
+    bf16* Woh_s = reinterpret_cast<bf16*>(sm + S::Woh); bf16* Woc_s = reinterpret_cast<bf16*>(sm + S::Woc);
+    uint8_t* p = sm + S::w_end;
+    bf16* keys_s = reinterpret_cast<bf16*>(p); p += (size_t)R * TJ * A * 2;          // [R][TJ][A]   own memory positions
+    bf16* mem_s = reinterpret_cast<bf16*>(p);  p += (size_t)R * Ti * U * 2;          // [R][Ti][U]   own context units
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    bf16* ctx_s = reinterpret_cast<bf16*>(p); p += R * E * 2;                        // blocked [C][R][U]
+    bf16* z1_s = reinterpret_cast<bf16*>(p);  p += R * Z1 * 2;
+    bf16* z_s = reinterpret_cast<bf16*>(p);   p += R * Z * 2;                        // blocked [C][R][UZ]
+    bf16* ha_s = reinterpret_cast<bf16*>(p);  p += R * HA * 2;
+    bf16* rha_s = reinterpret_cast<bf16*>(p); p += R * HA * 2;
+    float* q_s = reinterpret_cast<float*>(p); p += R * A * 4;                        // fp32 blocked [C][R][U]
+    float* e_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;              // fp32 blocked [C][R][TJ]
+    float* a_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;              // [R][Tip]
+    float* p_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;
+    float* cp_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;
+    float* red = reinterpret_cast<float*>(p); p += 16 * 128 * 4;                     // 16 slots of [16][8]
+    float* v_s = reinterpret_cast<float*>(p); p += A * 4;
+    uint8_t* stage = p; p += 1024;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p);                                 // 7 barriers
+    uint64_t *b_z1 = bars, *b_z = bars + 1, *b_rha = bars + 2, *b_ha = bars + 3, *b_q = bars + 4, *b_e = bars + 5, *b_ctx = bars + 6;
+
+    // ---- one-time loads --------------------------------------------------------------------------------------
+    af_load_cols(W1c_s, S::KP256, a.W1c, Z1, 0, E, rank * U, U, 16, tid);
+    af_load_cols(W2_s, S::KP256, a.W2, Z, 0, Z1, rank * UZ, UZ, 16, tid);
+    af_load_cols(Wg_s, S::KP384, a.Wg, 2 * HA, 0, Z + HA, rank * U, U, 16, tid);                      // r units
+    af_load_cols(Wg_s + 16 * S::KP384, S::KP384, a.Wg, 2 * HA, 0, Z + HA, HA + rank * U, U, 16, tid); // u units
+    af_load_cols(Wcz_s, S::KP128, a.Wc, HA, 0, Z, rank * U, U, 16, tid);
+    af_load_cols(Wch_s, S::KP256, a.Wc, HA, Z, HA, rank * U, U, 16, tid);
+    af_load_cols(Wq_s, S::KP256, a.Wq, A, 0, HA, rank * U, U, 16, tid);
+    af_load_cols(Woh_s, S::KP256, a.Wo, Y, 0, HA, rank * U, U, 16, tid);
+    af_load_cols(Woc_s, S::KP256, a.Wo, Y, HA, E, rank * U, U, 16, tid);
+    for (int idx = tid; idx < R * TJ * A; idx += AF_NT) {
+        const int u = idx % A, jj = (idx / A) % TJ, r = idx / (A * TJ), n = grp * R + r, j = rank * TJ + jj;
+        keys_s[idx] = __float2bfloat16((n < a.N && j < Ti) ? a.keys[((long long)n * Ti + j) * A + u] : 0.f);
+    }
+    for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
+        const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
+        mem_s[idx] = __float2bfloat16(n < a.N ? a.memory[((long long)n * Ti + j) * E + rank * U + i] : 0.f);
+    }
+    for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
+    for (int idx = tid; idx < R * E; idx += AF_NT) ctx_s[idx] = __float2bfloat16(0.f);
+    for (int idx = tid; idx < R * HA; idx += AF_NT) {       // blocked [C][R][U]
+        const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
+        ha_s[idx] = __float2bfloat16((a.ha0 && n < a.N) ? a.ha0[(long long)n * HA + blk * U + i] : 0.f);
+    }
+    for (int idx = tid; idx < R * Tip; idx += AF_NT) a_s[idx] = (a.att_type == TACO_ATT_BAH_MON && (idx % Tip) == 0) ? 1.f : 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const float score_bias = (a.att_type == TACO_ATT_BAH_MON) ? a.score_bias[0] : 0.f;
+    // activation-thread coordinates: 16-unit layers use threads [0,128): (i, r)
+    const bool act = tid < U * R;
+    const int ai = tid % U, ar = (tid / U) % R;
+    const int an = grp * R + ar;
+    const bool aok = act && an < a.N;
+    const int unit = rank * U + ai;
+    float ha_own = (aok && a.ha0) ? a.ha0[(long long)an * HA + unit] : 0.f;
+    float px_next = aok ? __ldg(a.px + ((long long)an * Td + 0) * Z1 + unit) : 0.f;
+    __syncthreads();
+    cl.sync();
+
+    for (int t = 0; t < Td; t++) {
+        const uint32_t par = t & 1;
+        const long long row = (long long)an * Td + t;
+        const float px_cur = px_next;
+        if (tid == 0) {
+            af_expect(b_z1, AF_C * R * U * 2); af_expect(b_z, AF_C * R * UZ * 2); af_expect(b_rha, AF_C * R * U * 2);
+            af_expect(b_ha, AF_C * R * U * 2); af_expect(b_q, AF_C * R * U * 4); af_expect(b_e, AF_C * R * TJ * 4);
+            af_expect(b_ctx, AF_C * R * U * 2);
+        }
+        if (aok && t + 1 < Td) px_next = __ldg(a.px + (row + 1) * Z1 + unit);
+        // ===== P1: z1 = relu(px + ctx.W1c)   (ctx_s holds ctx_{t-1}) =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, W1c_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (act) {
+            float v = 0.f;
+            if (aok) {
+                v = fmaxf(af_red_sum(red, 0, 8, 1, ai, ar) + px_cur, 0.f);
+                if (a.s_z1) a.s_z1[row * Z1 + unit] = v;
+            }
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(v);
+        }
+        if (a.s_ctxin && aok) {
+            // context consumed by this step (for the hoisted W1c gradient); ctx_s is bf16-rounded, the fp32 value sits in s_ctx[t-1]
+            a.s_ctxin[row * E + unit] = (t == 0) ? 0.f : a.s_ctx[(row - 1) * E + unit];
+        }
+        __syncthreads();
+        af_push(stage, z1_s + rank * R * U, b_z1, R * U * 2, tid);
+        af_wait(b_z1, par);
+        // ===== P2: z = relu(z1.W2 + b2)  (own UZ = 8 units) =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, W2_s, S::KP256, 0, warp * 32, z1_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (tid < UZ * R) {
+            const int i = tid % UZ, r = tid / UZ, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                v = fmaxf(af_red_sum(red, 0, 8, 1, i, r) + __ldg(a.b2 + rank * UZ + i), 0.f);
+                if (a.s_z) a.s_z[((long long)n * Td + t) * Z + rank * UZ + i] = v;
+            }
+            reinterpret_cast<bf16*>(stage)[r * UZ + i] = __float2bfloat16(v);
+        }
+        __syncthreads();
+        af_push(stage, z_s + rank * R * UZ, b_z, R * UZ * 2, tid);
+        af_wait(b_z, par);
+        // ===== P3: gates (own 2U columns: r | u) over [z ; ha], and the z part of the candidate =====
+        {
+            const int mt = warp & 1, ks = warp >> 1;             // 2 m-tiles x 4 k-splits of 6 k-tiles (k-tiles 0..7 = z, 8..23 = ha)
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kt = ks * 6; kt < ks * 6 + 6; kt++) {
+                if (kt < 8) af_mma_run<UZ>(acc, Wg_s, S::KP384, mt * 16, kt * 16, z_s, kt * 16, 1, lane);
+                else af_mma_run<U>(acc, Wg_s, S::KP384, mt * 16, kt * 16, ha_s, (kt - 8) * 16, 1, lane);
+            }
+            af_red_store(red, warp, acc, lane);                  // slot = ks*2 + mt
+            float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<UZ>(acc2, Wcz_s, S::KP128, 0, warp * 16, z_s, warp * 16, 1, lane);
+            af_red_store(red, 8 + warp, acc2, lane);
+        }
+        __syncthreads();
+        float rg = 0.f, ug = 0.f, cz = 0.f;
+        if (act) {
+            const float sr = af_red_sum(red, 0, 4, 2, ai, ar) + __ldg(a.bg + unit);
+            const float su = af_red_sum(red, 1, 4, 2, ai, ar) + __ldg(a.bg + HA + unit);
+            cz = af_red_sum(red, 8, 8, 1, ai, ar);
+            rg = af_sigmoid(sr); ug = af_sigmoid(su);
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(rg * ha_own);
+        }
+        __syncthreads();
+        af_push(stage, rha_s + rank * R * U, b_rha, R * U * 2, tid);
+        af_wait(b_rha, par);
+        // ===== P4: candidate and new attention-GRU state =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, Wch_s, S::KP256, 0, warp * 32, rha_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (act) {
+            const float c = af_tanh(af_red_sum(red, 0, 8, 1, ai, ar) + cz + __ldg(a.bc + unit));
+            const float hn = ug * ha_own + (1.f - ug) * c;
+            if (aok && a.s_r) {
+                const long long o = row * HA + unit;
+                a.s_r[o] = rg; a.s_u[o] = ug; a.s_c[o] = c; a.s_haprev[o] = ha_own; a.s_ha[o] = hn;
+            }
+            ha_own = aok ? hn : 0.f;
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(ha_own);
+        }
+        __syncthreads();
+        af_push(stage, ha_s + rank * R * U, b_ha, R * U * 2, tid);
+        af_wait(b_ha, par);
+        // ===== P5: query (own U columns) and the ha part of the concat projection (own U columns) =====
+        {
+            const int mt = warp & 1, ks = warp >> 1;             // m-tile 0 = Wq, 1 = Wo_h; 4 k-splits of 4 k-tiles
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, mt ? Woh_s : Wq_s, S::KP256, 0, ks * 64, ha_s, ks * 64, 4, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        float yh = 0.f;
+        if (act) {
+            const float q = af_red_sum(red, 0, 4, 2, ai, ar);
+            yh = af_red_sum(red, 1, 4, 2, ai, ar);
+            if (aok && a.s_q) a.s_q[row * A + unit] = q;
+            reinterpret_cast<float*>(stage)[ar * U + ai] = q;
+        }
+        __syncthreads();
+        af_push(stage, q_s + rank * R * U, b_q, R * U * 4, tid);
+        af_wait(b_q, par);
+        // ===== P6: scores of the own TJ memory positions: e[r][j] = sum_u v_u tanh(keys[r,j,u] + q[r,u]) + b =====
+        for (int pr = warp; pr < R * TJ; pr += AF_NT / 32) {
+            const int r = pr % R, jj = pr / R;
+            const uint4 kk = *reinterpret_cast<const uint4*>(keys_s + ((size_t)(r * TJ + jj)) * A + lane * 8);
+            const float* qp = q_s + ((lane >> 1) * R + r) * U + (lane & 1) * 8;
+            const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
+            const float4 v0 = *reinterpret_cast<const float4*>(v_s + lane * 8), v1 = *reinterpret_cast<const float4*>(v_s + lane * 8 + 4);
+            const __nv_bfloat162* kb = reinterpret_cast<const __nv_bfloat162*>(&kk);
+            const float2 k0 = __bfloat1622float2(kb[0]), k1 = __bfloat1622float2(kb[1]), k2 = __bfloat1622float2(kb[2]), k3 = __bfloat1622float2(kb[3]);
+            float s = v0.x * af_tanh(k0.x + q0.x);
+            s = fmaf(v0.y, af_tanh(k0.y + q0.y), s); s = fmaf(v0.z, af_tanh(k1.x + q0.z), s); s = fmaf(v0.w, af_tanh(k1.y + q0.w), s);
+            s = fmaf(v1.x, af_tanh(k2.x + q1.x), s); s = fmaf(v1.y, af_tanh(k2.y + q1.y), s);
+            s = fmaf(v1.z, af_tanh(k3.x + q1.z), s); s = fmaf(v1.w, af_tanh(k3.y + q1.w), s);
+            s = warp_sum(s);
+            if (lane == 0) reinterpret_cast<float*>(stage)[r * TJ + jj] = s + score_bias;
+        }
+        __syncthreads();
+        af_push(stage, e_s + rank * R * TJ, b_e, R * TJ * 4, tid);
+        af_wait(b_e, par);
+        // ===== P7: alignments (every CTA redundantly; warp r = row r), then the own U context units =====
+        {
+            const int r = warp, n = grp * R + r;
+            const int CH = (Tip + 31) / 32;
+            const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
+            float* ar_ = a_s + r * Tip; float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip;
+            auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+            if (a.manual) {
+                for (int j = lane; j < Ti; j += 32) ar_[j] = (n < a.N) ? a.manual[((long long)n * Td + t) * Ti + j] : 0.f;
+            } else if (a.att_type == TACO_ATT_BAH_MON) {
+                float ls = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float pv = af_sigmoid(E_(j));
+                    pr_[j] = pv;
+                    ls += __logf(fminf(fmaxf(1.f - pv, FLT_MIN), 1.f));
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float ws = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float cp = __expf(run);
+                    cr_[j] = cp;
+                    run += __logf(fminf(fmaxf(1.f - pr_[j], FLT_MIN), 1.f));
+                    ws += __fdividef(ar_[j], fminf(fmaxf(cp, 1e-10f), 1.f));
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+                for (int j = j0; j < j1; j++) {
+                    run2 += __fdividef(ar_[j], fminf(fmaxf(cr_[j], 1e-10f), 1.f));
+                    ar_[j] = pr_[j] * cr_[j] * run2;
+                }
+            } else {
+                float mx = -INFINITY;
+                for (int j = lane; j < Ti; j += 32) mx = fmaxf(mx, E_(j));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float smv = 0.f;
+                for (int j = lane; j < Ti; j += 32) { const float ex = __expf(E_(j) - mx); pr_[j] = ex; smv += ex; }
+                smv = warp_sum(smv);
+                for (int j = lane; j < Ti; j += 32) ar_[j] = __fdividef(pr_[j], smv);
+            }
+            __syncwarp();
+            if (rank == (r % AF_C) && n < a.N) {                 // spread the alignment/stash writes over the cluster
+                for (int j = lane; j < Ti; j += 32) {
+                    const float av = ar_[j];
+                    a.align[((long long)n * Ti + j) * Td + t] = av;
+                    if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = E_(j); }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            // ctx[r][own units]: thread = (j-quarter, row, unit pair); partials reduced through `red`
+            const int jq = tid >> 6, r = (tid >> 3) & 7, ip = tid & 7;
+            const int jn = (Ti + 3) / 4, ja = jq * jn, jb = min(Ti, ja + jn);
+            float c0 = 0.f, c1 = 0.f;
+            const float* arow = a_s + r * Tip;
+            const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(mem_s + (size_t)r * Ti * U) + ip;
+#pragma unroll 4
+            for (int j = ja; j < jb; j++) {
+                const float2 m2 = __bfloat1622float2(mp[(size_t)j * (U / 2)]);
+                const float av = arow[j];
+                c0 = fmaf(av, m2.x, c0); c1 = fmaf(av, m2.y, c1);
+            }
+            red[jq * 128 + (2 * ip) * 8 + r] = c0;
+            red[jq * 128 + (2 * ip + 1) * 8 + r] = c1;
+        }
+        __syncthreads();
+        if (act) {
+            float cx = 0.f;
+            if (aok) {
+                cx = af_red_sum(red, 0, 4, 1, ai, ar);
+                if (a.s_ctx) a.s_ctx[row * E + unit] = cx;
+            }
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(cx);
+        }
+        __syncthreads();
+        af_push(stage, ctx_s + rank * R * U, b_ctx, R * U * 2, tid);
+        af_wait(b_ctx, par);
+        // ===== P8: y0 (own U columns) = yh + ctx.Wo_c + bo =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, Woc_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (aok) a.y0[row * Y + unit] = yh + af_red_sum(red, 0, 8, 1, ai, ar) + __ldg(a.bo + unit);
+        __syncthreads();     // `red` is rewritten by the next step's P1
+    }
+    if (a.ha_final && aok) a.ha_final[(long long)an * HA + unit] = ha_own;
+    cl.sync();
+}
+
+struct AfBwdSmem {
+    static constexpr int KP256 = 264, KP512 = 520, KP128 = 136;
+    static constexpr size_t Wo = 0;                                    // [32][264]  rows: ha units | ctx units ; k over Y
+    static constexpr size_t Wq = Wo + 32 * KP256 * 2;                  // [16][264]  k over A
+    static constexpr size_t Wch = Wq + 16 * KP256 * 2;                 // [16][264]  rows Z+unit of cand kernel, k over HA
+    static constexpr size_t Wcz = Wch + 16 * KP256 * 2;                // [16][264]  rows z units (8 valid), k over HA
+    static constexpr size_t W1c = Wcz + 16 * KP256 * 2;                // [16][264]  rows ctx units of dense_1, k over Z1
+    static constexpr size_t Wgh = W1c + 16 * KP256 * 2;                // [16][520]  rows Z+unit of gates kernel, k over 2HA
+    static constexpr size_t Wgz = Wgh + 16 * KP512 * 2;                // [16][520]  rows z units (8 valid)
+    static constexpr size_t W2 = Wgz + 16 * KP512 * 2;                 // [16][136]  rows z1 units of dense_2, k over Z
+    static constexpr size_t w_end = W2 + 16 * KP128 * 2;
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int grp = blockIdx.x / AF_C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int R = AF_R, U = AF_U, UZ = AF_UZ, E = AF_E, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
+    const int Ti = a.Ti, Td = a.Td;
+    const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    using S = AfBwdSmem;
+
+    extern __shared__ __align__(128) uint8_t sm[];
+    bf16* Wo_s = reinterpret_cast<bf16*>(sm + S::Wo);   bf16* Wq_s = reinterpret_cast<bf16*>(sm + S::Wq);
+    bf16* Wch_s = reinterpret_cast<bf16*>(sm + S::Wch); bf16* Wcz_s = reinterpret_cast<bf16*>(sm + S::Wcz);
+    bf16* W1c_s = reinterpret_cast<bf16*>(sm + S::W1c); bf16* Wgh_s = reinterpret_cast<bf16*>(sm + S::Wgh);
+    bf16* Wgz_s = reinterpret_cast<bf16*>(sm + S::Wgz); bf16* W2_s = reinterpret_cast<bf16*>(sm + S::W2);
+    uint8_t* p = sm + S::w_end;
+    bf16* memj_s = reinterpret_cast<bf16*>(p); p += (size_t)R * TJ * E * 2;          // [R][TJ][E]   own memory positions
+    bf16* keyu_s = reinterpret_cast<bf16*>(p); p += (size_t)R * Ti * U * 2;          // [R][Ti][U]   own attention units
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    float* dctx_s = reinterpret_cast<float*>(p); p += R * E * 4;                     // fp32 blocked [C][R][U]
+    float* da_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;           // fp32 blocked [C][R][TJ]
+    bf16* gq_s = reinterpret_cast<bf16*>(p);   p += R * A * 2;                       // bf16 blocked [C][R][U]
+    bf16* dcp_s = reinterpret_cast<bf16*>(p);  p += R * HA * 2;
+    bf16* dg_s = reinterpret_cast<bf16*>(p);   p += 2 * R * HA * 2;                  // [2C][R][U]
+    bf16* dzp_s = reinterpret_cast<bf16*>(p);  p += R * Z * 2;                       // blocked [C][R][UZ]
+    bf16* dz1p_s = reinterpret_cast<bf16*>(p); p += R * Z1 * 2;
+    bf16* dy_s = reinterpret_cast<bf16*>(p);   p += R * Y * 2;                       // blocked [Y/16][R][16]
+    float* dac_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;            // carried grad wrt a_t
+    float* ge_s = reinterpret_cast<float*>(p);  p += (size_t)R * Tip * 4;            // grad wrt scores (also scratch t1)
+    float* p_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;
+    float* cp_s = reinterpret_cast<float*>(p);  p += (size_t)R * Tip * 4;
+    float* s_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;            // (also scratch t2)
+    float* red = reinterpret_cast<float*>(p);   p += 16 * 128 * 4;
+    float* v_s = reinterpret_cast<float*>(p);   p += A * 4;
+    uint8_t* stage = p; p += 1024;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p);
+    uint64_t *b_dctx = bars, *b_da = bars + 1, *b_gq = bars + 2, *b_dcp = bars + 3, *b_dg = bars + 4, *b_dzp = bars + 5, *b_dz1p = bars + 6;
+
+    // natural-orientation weight rows (data-gradient products): A row = weight row of the owned input unit
+    af_load_rows(Wo_s, S::KP256, a.Wo, Y, rank * U, U, 16, 0, Y, tid);
+    af_load_rows(Wo_s + 16 * S::KP256, S::KP256, a.Wo, Y, HA + rank * U, U, 16, 0, Y, tid);
+    af_load_rows(Wq_s, S::KP256, a.Wq, A, rank * U, U, 16, 0, A, tid);
+    af_load_rows(Wch_s, S::KP256, a.Wc, HA, Z + rank * U, U, 16, 0, HA, tid);
+    af_load_rows(Wcz_s, S::KP256, a.Wc, HA, rank * UZ, UZ, 16, 0, HA, tid);
+    af_load_rows(W1c_s, S::KP256, a.W1c, Z1, rank * U, U, 16, 0, Z1, tid);
+    af_load_rows(Wgh_s, S::KP512, a.Wg, 2 * HA, Z + rank * U, U, 16, 0, 2 * HA, tid);
+    af_load_rows(Wgz_s, S::KP512, a.Wg, 2 * HA, rank * UZ, UZ, 16, 0, 2 * HA, tid);
+    af_load_rows(W2_s, S::KP128, a.W2, Z, rank * U, U, 16, 0, Z, tid);
+    for (int idx = tid; idx < R * TJ * E; idx += AF_NT) {
+        const int u = idx % E, jj = (idx / E) % TJ, r = idx / (E * TJ), n = grp * R + r, j = rank * TJ + jj;
+        memj_s[idx] = __float2bfloat16((n < a.N && j < Ti) ? a.memory[((long long)n * Ti + j) * E + u] : 0.f);
+    }
+    for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
+        const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
+        keyu_s[idx] = __float2bfloat16(n < a.N ? a.keys[((long long)n * Ti + j) * A + rank * U + i] : 0.f);
+    }
+    for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
+    for (int idx = tid; idx < R * Tip; idx += AF_NT) { dac_s[idx] = 0.f; ge_s[idx] = 0.f; }
+    if (tid == 0) {
+        for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool act = tid < U * R;
+    const int ai = tid % U, ar = (tid / U) % R;
+    const int an = grp * R + ar;
+    const bool aok = act && an < a.N;
+    const int unit = rank * U + ai;
+    // (j-quarter, row, unit pair) mapping of the score-gradient phase
+    const int jq = tid >> 6, jr = (tid >> 3) & 7, jip = tid & 7;
+    const int jn_ = grp * R + jr;
+    float dha_carry = 0.f, dctx_carry = 0.f, gbias_acc = 0.f;
+    __syncthreads();
+    cl.sync();
+
+    int it = 0;
+    for (int t = Td - 1; t >= 0; t--, it++) {
+        const uint32_t par = it & 1;
+        const long long row = (long long)an * Td + t;
+        if (tid == 0) {
+            af_expect(b_dctx, AF_C * R * U * 4); af_expect(b_da, AF_C * R * TJ * 4); af_expect(b_gq, AF_C * R * U * 2);
+            af_expect(b_dcp, AF_C * R * U * 2); af_expect(b_dg, 2 * AF_C * R * U * 2); af_expect(b_dzp, AF_C * R * UZ * 2);
+            af_expect(b_dz1p, AF_C * R * U * 2);
+        }
+        // stash of this step (latency hidden behind Bp1-Bp4)
+        float rg = 0.f, ug = 0.f, cc = 0.f, hp = 0.f, z1v = 0.f;
+        if (aok) {
+            const long long o = row * HA + unit;
+            rg = a.s_r[o]; ug = a.s_u[o]; cc = a.s_c[o]; hp = a.s_haprev[o];
+            z1v = a.s_z1[row * Z1 + unit];
+        }
+        float q0 = 0.f, q1 = 0.f;
+        if (jn_ < a.N && !a.manual) {
+            const float* qp = a.s_q + ((long long)jn_ * Td + t) * A + rank * U + 2 * jip;
+            q0 = qp[0]; q1 = qp[1];
+        }
+        for (int idx = tid; idx < R * Y; idx += AF_NT) {
+            const int k = idx % Y, r = idx / Y, n = grp * R + r;
+            dy_s[((k >> 4) * R + r) * 16 + (k & 15)] = __float2bfloat16((n < a.N) ? __ldg(a.dy0 + ((long long)n * Td + t) * Y + k) : 0.f);
+        }
+        __syncthreads();
+        // ===== Bp1: dha += dy0.Wo_h^T (own U ha units), dctx = carry + dy0.Wo_c^T (own U ctx units) =====
+        {
+            const int mt = warp & 1, ks = warp >> 1;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<16>(acc, Wo_s, S::KP256, mt * 16, ks * 64, dy_s, ks * 64, 4, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        float dha = 0.f;
+        if (act) {
+            dha = dha_carry + af_red_sum(red, 0, 4, 2, ai, ar);
+            const float dctx = aok ? dctx_carry + af_red_sum(red, 1, 4, 2, ai, ar) : 0.f;
+            if (aok) a.d_ctx[row * E + unit] = dctx;
+            reinterpret_cast<float*>(stage)[ar * U + ai] = dctx;
+        }
+        __syncthreads();
+        af_push(stage, dctx_s + rank * R * U, b_dctx, R * U * 4, tid);
+        af_wait(b_dctx, par);
+        // ===== Bp2: da[r][own j] = sum_u dctx[r,u] memory[r,j,u] =====
+        for (int pr = warp; pr < R * TJ; pr += AF_NT / 32) {
+            const int r = pr % R, jj = pr / R;
+            const uint4 mm = *reinterpret_cast<const uint4*>(memj_s + ((size_t)(r * TJ + jj)) * E + lane * 8);
+            const float* dp = dctx_s + ((lane >> 1) * R + r) * U + (lane & 1) * 8;
+            const float4 d0 = *reinterpret_cast<const float4*>(dp), d1 = *reinterpret_cast<const float4*>(dp + 4);
+            const __nv_bfloat162* mb = reinterpret_cast<const __nv_bfloat162*>(&mm);
+            const float2 m0 = __bfloat1622float2(mb[0]), m1 = __bfloat1622float2(mb[1]), m2 = __bfloat1622float2(mb[2]), m3 = __bfloat1622float2(mb[3]);
+            float s = d0.x * m0.x;
+            s = fmaf(d0.y, m0.y, s); s = fmaf(d0.z, m1.x, s); s = fmaf(d0.w, m1.y, s);
+            s = fmaf(d1.x, m2.x, s); s = fmaf(d1.y, m2.y, s); s = fmaf(d1.z, m3.x, s); s = fmaf(d1.w, m3.y, s);
+            s = warp_sum(s);
+            if (lane == 0) reinterpret_cast<float*>(stage)[r * TJ + jj] = s;
+        }
+        __syncthreads();
+        af_push(stage, da_s + rank * R * TJ, b_da, R * TJ * 4, tid);
+        af_wait(b_da, par);
+        // ===== Bp3: attention-probability backward (every CTA; warp r = row r).  SURVEY.md Appendix C =====
+        {
+            const int r = warp, n = grp * R + r;
+            const int CH = (Tip + 31) / 32;
+            const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
+            float* gc = dac_s + r * Tip; float* ge = ge_s + r * Tip;
+            float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip; float* sr_ = s_s + r * Tip;
+            float* t1 = ge; float* t2 = sr_;
+            auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+            const bool ok = n < a.N;
+            if (a.manual || !ok) {
+                for (int j = lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+            } else if (a.att_type == TACO_ATT_BAH_MON) {
+                const float* e_row = a.s_e + ((long long)n * Td + t) * Ti;
+                const float* ap_row = (t > 0) ? a.s_a + ((long long)n * Td + (t - 1)) * Ti : nullptr;
+                float ls = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float pv = af_sigmoid(e_row[j]);
+                    pr_[j] = pv;
+                    ls += __logf(fminf(fmaxf(1.f - pv, FLT_MIN), 1.f));
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float ws = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float cp = __expf(run);
+                    cr_[j] = cp;
+                    run += __logf(fminf(fmaxf(1.f - pr_[j], FLT_MIN), 1.f));
+                    const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                    ws += __fdividef(ap, fminf(fmaxf(cp, 1e-10f), 1.f));
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+                float gs_loc = 0.f;
+                for (int j = j0; j < j1; j++) {
+                    const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                    run2 += __fdividef(ap, fminf(fmaxf(cr_[j], 1e-10f), 1.f));
+                    const float g = GA(j) + gc[j];
+                    gc[j] = g;                                            // total grad wrt a_t[j]
+                    sr_[j] = run2;
+                    const float gs = g * pr_[j] * cr_[j];
+                    t1[j] = gs;
+                    gs_loc += gs;
+                }
+                float suf = gs_loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+                suf -= gs_loc;
+                float gL_loc = 0.f;
+                {
+                    float acc = suf;
+                    for (int j = j1 - 1; j >= j0; j--) {
+                        acc += t1[j];
+                        const float g = gc[j];
+                        const float pv = pr_[j], cp = cr_[j], sj = sr_[j];
+                        const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
+                        const float d = fminf(fmaxf(cp, 1e-10f), 1.f);
+                        float gcp = g * pv * sj;
+                        if (cp >= 1e-10f && cp <= 1.f) gcp -= acc * ap / (d * d);
+                        const float gL = gcp * cp;
+                        gL_loc += gL;
+                        ge[j] = g * cp * sj;                               // direct part of grad wrt p_j  (t1[j] consumed above)
+                        t2[j] = gL;                                        // (s_j consumed above)
+                        gc[j] = acc / d;                                   // grad wrt a_{t-1,j}, carried
+                    }
+                }
+                float sufL = gL_loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { float v = __shfl_down_sync(0xffffffffu, sufL, o); if (lane + o < 32) sufL += v; }
+                sufL -= gL_loc;
+                float gb = 0.f;
+                {
+                    float acc = sufL;
+                    for (int j = j1 - 1; j >= j0; j--) {
+                        const float pv = pr_[j], omp = 1.f - pv;
+                        float gp = ge[j];
+                        if (omp >= FLT_MIN && omp <= 1.f) gp -= acc / fminf(fmaxf(omp, FLT_MIN), 1.f);
+                        acc += t2[j];
+                        const float gev = gp * pv * (1.f - pv);
+                        ge[j] = gev;
+                        gb += gev;
+                    }
+                }
+                for (int j = Ti + lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+                gb = warp_sum(gb);
+                if (rank == 0 && lane == 0) gbias_acc += gb;
+            } else {
+                const float* a_row = a.s_a + ((long long)n * Td + t) * Ti;
+                float dot = 0.f;
+                for (int j = lane; j < Ti; j += 32) dot += a_row[j] * GA(j);
+                dot = warp_sum(dot);
+                for (int j = lane; j < Tip; j += 32) { ge[j] = (j < Ti) ? a_row[j] * (GA(j) - dot) : 0.f; gc[j] = 0.f; }
+            }
+            __syncwarp();
+            if (rank == (r % AF_C) && ok && a.d_ge)
+                for (int j = lane; j < Ti; j += 32) a.d_ge[((long long)n * Td + t) * Ti + j] = ge[j];
+        }
+        __syncthreads();
+        // ===== Bp4: gq (own U units) = v_u * sum_j ge[r][j] * (1 - tanh^2(keys[r,j,u] + q[r,u])) =====
+        {
+            const int jn = (Ti + 3) / 4, ja = jq * jn, jb = min(Ti, ja + jn);
+            float c0 = 0.f, c1 = 0.f;
+            if (!a.manual) {
+                const float* ger = ge_s + jr * Tip;
+                const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(keyu_s + (size_t)jr * Ti * U) + jip;
+#pragma unroll 2
+                for (int j = ja; j < jb; j++) {
+                    const float2 k2 = __bfloat1622float2(kp[(size_t)j * (U / 2)]);
+                    const float g = ger[j];
+                    const float th0 = af_tanh(k2.x + q0), th1 = af_tanh(k2.y + q1);
+                    c0 = fmaf(g, 1.f - th0 * th0, c0); c1 = fmaf(g, 1.f - th1 * th1, c1);
+                }
+            }
+            red[jq * 128 + (2 * jip) * 8 + jr] = c0;
+            red[jq * 128 + (2 * jip + 1) * 8 + jr] = c1;
+        }
+        __syncthreads();
+        if (act) {
+            float gq = 0.f;
+            if (aok) {
+                gq = af_red_sum(red, 0, 4, 1, ai, ar) * v_s[unit];
+                if (a.d_gq) a.d_gq[row * A + unit] = gq;
+            }
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(gq);
+        }
+        __syncthreads();
+        af_push(stage, gq_s + rank * R * U, b_gq, R * U * 2, tid);
+        af_wait(b_gq, par);
+        // ===== Bp5: dha += gq.Wq^T; GRU cell backward (elementwise part) =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, Wq_s, S::KP256, 0, warp * 32, gq_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        float du_pre = 0.f, dc_pre = 0.f;
+        if (act) {
+            dha += af_red_sum(red, 0, 8, 1, ai, ar);
+            if (aok) {
+                du_pre = dha * (hp - cc) * ug * (1.f - ug);
+                dc_pre = dha * (1.f - ug) * (1.f - cc * cc);
+            }
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(dc_pre);
+        }
+        __syncthreads();
+        af_push(stage, dcp_s + rank * R * U, b_dcp, R * U * 2, tid);
+        af_wait(b_dcp, par);
+        // ===== Bp6: d(r*h) (own U) = dc_pre . Wc_h^T =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, Wch_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        float d_rh = 0.f, dr_pre = 0.f;
+        if (act) {
+            d_rh = af_red_sum(red, 0, 8, 1, ai, ar);
+            if (aok) dr_pre = d_rh * hp * rg * (1.f - rg);
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(dr_pre);
+            reinterpret_cast<bf16*>(stage + 256)[ar * U + ai] = __float2bfloat16(du_pre);
+        }
+        __syncthreads();
+        af_push(stage, dg_s + rank * R * U, b_dg, R * U * 2, tid);
+        af_push(stage + 256, dg_s + (AF_C + rank) * R * U, b_dg, R * U * 2, tid);
+        af_wait(b_dg, par);
+        // ===== Bp7: dha_prev (own U ha units) and dz (own UZ z units) =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, Wgh_s, S::KP512, 0, warp * 64, dg_s, warp * 64, 4, lane);
+            af_red_store(red, warp, acc, lane);
+            float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc2, Wgz_s, S::KP512, 0, warp * 64, dg_s, warp * 64, 4, lane);
+            af_mma_run<U>(acc2, Wcz_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, 2, lane);
+            af_red_store(red, 8 + warp, acc2, lane);
+        }
+        __syncthreads();
+        if (aok) {
+            dha_carry = dha * ug + d_rh * rg + af_red_sum(red, 0, 8, 1, ai, ar);
+            float* g = a.d_G + row * 3 * HA + unit;
+            g[0] = dr_pre; g[HA] = du_pre; g[2 * HA] = dc_pre;
+            a.s_r[row * HA + unit] = rg * hp;                   // operand of the candidate-weight gradient GEMM
+        }
+        if (tid < UZ * R) {
+            const int i = tid % UZ, r = tid / UZ, n = grp * R + r;
+            float v = 0.f;
+            if (n < a.N) {
+                const long long rw = (long long)n * Td + t;
+                const float z = a.s_z[rw * Z + rank * UZ + i];
+                v = (z > 0.f) ? af_red_sum(red, 8, 8, 1, i, r) : 0.f;
+                a.d_zp[rw * Z + rank * UZ + i] = v;
+            }
+            reinterpret_cast<bf16*>(stage)[r * UZ + i] = __float2bfloat16(v);
+        }
+        __syncthreads();
+        af_push(stage, dzp_s + rank * R * UZ, b_dzp, R * UZ * 2, tid);
+        af_wait(b_dzp, par);
+        // ===== Bp8: dz1 (own U) = dz_pre . W2^T, relu' =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<UZ>(acc, W2_s, S::KP128, 0, warp * 16, dzp_s, warp * 16, 1, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (act) {
+            float v = 0.f;
+            if (aok) {
+                v = (z1v > 0.f) ? af_red_sum(red, 0, 8, 1, ai, ar) : 0.f;
+                a.d_z1p[row * Z1 + unit] = v;
+            }
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(v);
+        }
+        __syncthreads();
+        af_push(stage, dz1p_s + rank * R * U, b_dz1p, R * U * 2, tid);
+        af_wait(b_dz1p, par);
+        // ===== Bp9: grad wrt ctx_{t-1} (own U) = dz1_pre . W1c^T =====
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            af_mma_run<U>(acc, W1c_s, S::KP256, 0, warp * 32, dz1p_s, warp * 32, 2, lane);
+            af_red_store(red, warp, acc, lane);
+        }
+        __syncthreads();
+        if (act) dctx_carry = af_red_sum(red, 0, 8, 1, ai, ar);
+        __syncthreads();
+    }
+    if (a.d_ha0 && aok) a.d_ha0[(long long)an * HA + unit] = dha_carry;
+    if (rank == 0 && lane == 0 && a.d_score_bias && a.att_type == TACO_ATT_BAH_MON) atomicAdd(a.d_score_bias, gbias_acc);
+    cl.sync();
+}
+
+static size_t af_bwd_smem(int Ti) {
+    const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    size_t b = AfBwdSmem::w_end + (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * Ti * AF_U * 2 + 16;
+    b += (size_t)AF_R * AF_E * 4 + (size_t)AF_R * Tip * 4 + (size_t)AF_R * (AF_A + AF_HA + 2 * AF_HA + AF_Z + AF_Z1 + AF_Y) * 2;
+    b += (size_t)5 * AF_R * Tip * 4 + 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
+    return b;
+}
+
+static size_t af_fwd_smem(int Ti) {
+    const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    size_t b = AfFwdSmem::w_end + (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * Ti * AF_U * 2 + 16;
+    b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * Tip * 4;
+    b += 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
+    return b;
+}
+
+bool att_fast_supported(const AttArgs& a) {
+    return a.E == AF_E && a.A == AF_A && a.HA == AF_HA && a.Z1 == AF_Z1 && a.Z == AF_Z && a.Y == AF_Y && a.SPK == 0 &&
+           a.att_type != TACO_ATT_BAH_NORM && af_fwd_smem(a.Ti) <= 227 * 1024 && af_bwd_smem(a.Ti) <= 227 * 1024;
+}
+
+template <typename K>
+static int af_launch(K kern, const AttArgs& a, size_t smem, int& configured, cudaStream_t s) {
+    if (configured == 0) {       // 0 unknown, 1 ok, -1 unsupported (a cluster of 16 CTAs is not launchable here)
+        cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : -1;
+        if (configured < 0) cudaGetLastError();
+    }
+    if (configured < 0) return TACO_ENOTSUP;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(AF_C * cdiv(a.N, AF_R));
+    cfg.blockDim = dim3(AF_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = AF_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e != cudaSuccess) { cudaGetLastError(); configured = -1; return TACO_ENOTSUP; }
+    g_launch_count++;
+    return TACO_OK;
+}
+
+int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s) {
+    static int configured = 0;
+    return af_launch(att_fast_fwd_kernel<0>, a, af_fwd_smem(a.Ti), configured, s);
+}
+int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s) {
+    static int configured = 0;
+    return af_launch(att_fast_bwd_kernel<0>, a, af_bwd_smem(a.Ti), configured, s);
+}
+
+}  // namespace taco

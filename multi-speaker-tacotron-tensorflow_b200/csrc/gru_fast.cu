@@ -1,0 +1,428 @@
+// Fast GRU recurrence for the tensor-core precision mode (same contract and stash layout as gru.cu; TF GRUCell
+// semantics, reference: models/modules.py:82-96, models/tacotron.py:171-175).
+//
+// Differences from the exact fp32 kernel in gru.cu:
+//   * the recurrent weight slice of each CTA stays resident in shared memory as bf16 for the whole sequence and the
+//     per-step products run on mma.sync.m16n8k16 (weight columns = M, the cluster's 8 batch rows = N=8), fp32 accumulate;
+//     the hidden state itself is carried in fp32 registers, only the matvec operand is rounded to bf16;
+//   * the r*h / h' slices are exchanged with cp.async.bulk shared::cta -> shared::cluster copies that complete on the
+//     receiver's mbarrier (one 512-byte copy per peer and phase) instead of two full cluster barriers per step.
+// Single receive buffers are sufficient: a CTA can only send phase p+2 data after it has received every peer's phase p+1
+// data, which each peer sends after its last read of the phase-p buffer ("exchange protocol").
+#include "common.cuh"
+#include "kernels.h"
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+
+namespace cg = cooperative_groups;
+
+namespace taco {
+
+constexpr int GF_C = 8, GF_R = 8, GF_NT = 256;
+
+__device__ __forceinline__ uint32_t gf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gf_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gf_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gf_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gf_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(gf_smem_u32(bar)), "r"(parity) : "memory");
+}
+// bulk copy local shared -> peer CTA's shared (same offsets), completing `bytes` on the peer's mbarrier
+__device__ __forceinline__ void gf_push(const void* src_local, void* dst_local_alias, uint64_t* bar_local_alias, uint32_t bytes, uint32_t peer) {
+    uint32_t dst, bar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias)), "r"(peer));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "r"(gf_smem_u32(src_local)), "r"(bytes), "r"(bar) : "memory");
+}
+// Exchange variant 2: every thread forwards 16 bytes of the staged block to one peer with st.async (data + tx-count in
+// one DSMEM transaction, no async-proxy fence needed).  NQ = 16-byte chunks per block; threads [0, C*NQ) participate.
+template <int NQ>
+__device__ __forceinline__ void gf_push_stasync(const void* stage, void* dst_local_alias, uint64_t* bar_local_alias, int tid) {
+    if (tid < GF_C * NQ) {
+        const uint32_t peer = tid / NQ, q = tid % NQ;
+        const uint4 v = *(reinterpret_cast<const uint4*>(stage) + q);
+        uint32_t dst, bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias) + q * 16), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                     ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
+    }
+}
+#ifndef GF_USE_STASYNC
+#define GF_USE_STASYNC 1
+#endif
+
+__device__ __forceinline__ void gf_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void gf_mma(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float gf_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gf_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// acc (16 x 8 fp32 fragment) += Wt[m0..m0+15][k0 .. k0+16*nk) . v[k][n]     Wt: bf16 [rows][KP]; v: bf16 [C][R][U] blocked
+template <int U, int KP>
+__device__ __forceinline__ void gf_mma_slice(float acc[4], const __nv_bfloat16* Wt, int m0, const __nv_bfloat16* v, int k0, int nk, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t a_base = gf_smem_u32(Wt + (size_t)(m0 + (lane & 15)) * KP + (lane >> 4) * 8);
+#pragma unroll 4
+    for (int kk = 0; kk < nk; kk++) {
+        const int k = k0 + kk * 16;
+        uint32_t a0, a1, a2, a3;
+        gf_ldmatrix_x4(a_base + (uint32_t)k * 2, a0, a1, a2, a3);
+        const int ka = k + 2 * t, kb = ka + 8;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(v + ((ka / U) * GF_R + g) * U + (ka % U));
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(v + ((kb / U) * GF_R + g) * U + (kb % U));
+        gf_mma(acc, a0, a1, a2, a3, b0, b1);
+    }
+}
+
+template <int H>
+struct GfCfg {
+    static constexpr int U = H / GF_C, GC = 2 * U, KP = H + 8, KP2 = 2 * H + 8;
+    static constexpr int ACT = U * GF_R;
+    static constexpr int BLK_BYTES = GF_R * U * 2;                 // one CTA's bf16 slice of a vector
+    // forward: Wg [GC][KP] + Wc [U][KP]; backward: WcT [U][KP] + WgT [U][KP2]
+    static constexpr size_t w_bytes = (size_t)3 * U * KP2 * 2;     // upper bound for both directions
+    static constexpr size_t smem_bytes = w_bytes + (size_t)3 * GF_R * H * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
+                                         4096 /*red*/ + 64 /*barriers*/ + 256;
+};
+
+template <int H>
+__global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a) {
+    using Cfg = GfCfg<H>;
+    constexpr int U = Cfg::U, GC = Cfg::GC, KP = Cfg::KP, R = GF_R;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / GF_C;
+    const int d = cid % a.ndir, grp = cid / a.ndir;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __nv_bfloat16* Wg_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [GC][KP]
+    __nv_bfloat16* Wc_s = Wg_s + GC * KP;                                         // [U][KP]
+    __nv_bfloat16* hb_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);   // [C][R][U]
+    __nv_bfloat16* rhb_s = hb_s + R * H;
+    __nv_bfloat16* spare = rhb_s + R * H;
+    __nv_bfloat16* stage_rh = spare + R * H;                                      // [R][U]
+    __nv_bfloat16* stage_h = stage_rh + R * U;
+    float* red = reinterpret_cast<float*>(stage_h + 2 * R * U);                   // 1024 floats
+    uint64_t* bar_rh = reinterpret_cast<uint64_t*>(red + 1024);
+    uint64_t* bar_h = bar_rh + 1;
+
+    const float* __restrict__ Wg = a.Wg[d];
+    const float* __restrict__ Wc = a.Wc[d];
+    for (int idx = tid; idx < GC * H; idx += GF_NT) {
+        const int k = idx / GC, col = idx % GC;
+        const int gcol = (col < U) ? rank * U + col : H + rank * U + (col - U);
+        Wg_s[col * KP + k] = __float2bfloat16(__ldg(Wg + (long long)k * 2 * H + gcol));
+    }
+    for (int idx = tid; idx < U * H; idx += GF_NT) {
+        const int k = idx / U, col = idx % U;
+        Wc_s[col * KP + k] = __float2bfloat16(__ldg(Wc + (long long)k * H + rank * U + col));
+    }
+    for (int idx = tid; idx < R * H; idx += GF_NT) {       // hb_s[(k/U)][r][k%U]
+        const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
+        const int k = blk * U + i;
+        hb_s[idx] = __float2bfloat16((a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + k] : 0.f);
+    }
+    if (tid == 0) {
+        gf_mbar_init(bar_rh, 1); gf_mbar_init(bar_h, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool act = tid < Cfg::ACT;
+    const int i = tid % U, r = tid / U;
+    const int n = grp * R + r;
+    int L = 0;
+    if (act && n < a.N) L = a.lengths ? min(max(a.lengths[n], 0), a.T) : a.T;
+    int Lmax = 0;
+    for (int rr = 0; rr < R; rr++) {
+        const int nn = grp * R + rr;
+        if (nn < a.N) Lmax = max(Lmax, a.lengths ? min(max(a.lengths[nn], 0), a.T) : a.T);
+    }
+    const int unit = rank * U + i;
+    float h_own = (act && a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + unit] : 0.f;
+    const long long st_base = ((long long)d * a.N + n) * a.T;
+    __syncthreads();
+    cluster.sync();
+
+    // mma work split: gate phase 4 m-tiles (GC=64) x 2 k-halves (H=256) | for H=128: GC=32 -> 2 m-tiles x 4 k-quarters
+    constexpr int MT_G = GC / 16, KS_G = 8 / MT_G, NK_G = H / 16 / KS_G;
+    constexpr int MT_C = U / 16, KS_C = 8 / MT_C, NK_C = H / 16 / KS_C;
+    const int g4 = lane >> 2, t4 = lane & 3;
+
+    float gr = 0.f, gu = 0.f, gc = 0.f;
+    auto load_gx = [&](int s) {
+        if (act && s < L) {
+            const int t = (d == 0) ? s : (L - 1 - s);
+            const float* g = a.gx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
+            gr = __ldg(g); gu = __ldg(g + H); gc = __ldg(g + 2 * H);
+        }
+    };
+    load_gx(0);
+    for (int s = 0; s < Lmax; s++) {
+        const uint32_t par = s & 1;
+        const bool valid = act && (s < L);
+        const int t = (d == 0) ? s : (L - 1 - s);
+        const float cgr = gr, cgu = gu, cgc = gc;
+        if (tid == 0) { gf_mbar_expect_tx(bar_rh, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h, GF_C * Cfg::BLK_BYTES); }
+        load_gx(s + 1);                                          // prefetch next step's x-side pre-activations
+        // ---- gate phase ----
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mt = warp % MT_G, ks = warp / MT_G;
+            gf_mma_slice<U, KP>(acc, Wg_s, mt * 16, hb_s, ks * NK_G * 16, NK_G, lane);
+            float* rp = red + ks * (GC * R);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+        }
+        __syncthreads();
+        float rg = 0.f, ug = 0.f;
+        if (act) {
+            float sr = cgr, su = cgu;
+#pragma unroll
+            for (int ks = 0; ks < KS_G; ks++) { sr += red[ks * (GC * R) + i * R + r]; su += red[ks * (GC * R) + (U + i) * R + r]; }
+            rg = gf_sigmoid(sr); ug = gf_sigmoid(su);
+            stage_rh[r * U + i] = __float2bfloat16(rg * h_own);
+        }
+#if GF_USE_STASYNC
+        __syncthreads();
+        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_rh, rhb_s + rank * R * U, bar_rh, tid);
+#else
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < GF_C) gf_push(stage_rh, rhb_s + rank * R * U, bar_rh, Cfg::BLK_BYTES, tid);
+#endif
+        gf_mbar_wait(bar_rh, par);
+        // ---- candidate phase ----
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mt = warp % MT_C, ks = warp / MT_C;
+            gf_mma_slice<U, KP>(acc, Wc_s, mt * 16, rhb_s, ks * NK_C * 16, NK_C, lane);
+            float* rp = red + ks * (U * R);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+        }
+        __syncthreads();
+        if (act) {
+            float sc = cgc;
+#pragma unroll
+            for (int ks = 0; ks < KS_C; ks++) sc += red[ks * (U * R) + i * R + r];
+            const float c = gf_tanh(sc);
+            const float hn = ug * h_own + (1.f - ug) * c;
+            if (valid) {
+                const long long o = (long long)n * a.T + t;
+                float y = hn;
+                if (a.res) y += a.res[o * a.res_ld + unit];
+                a.out[o * a.out_ld + d * H + unit] = y;
+                if (a.st_r) {
+                    const long long so = (st_base + t) * H + unit;
+                    a.st_r[so] = rg; a.st_u[so] = ug; a.st_c[so] = c; a.st_hprev[so] = h_own;
+                }
+                h_own = hn;
+            }
+            stage_h[r * U + i] = __float2bfloat16(h_own);
+        }
+#if GF_USE_STASYNC
+        __syncthreads();
+        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_h, hb_s + rank * R * U, bar_h, tid);
+#else
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < GF_C) gf_push(stage_h, hb_s + rank * R * U, bar_h, Cfg::BLK_BYTES, tid);
+#endif
+        gf_mbar_wait(bar_h, par);
+    }
+    if (act && a.hfinal && n < a.N) a.hfinal[(long long)n * a.ndir * H + d * H + unit] = h_own;
+    cluster.sync();      // no CTA may exit while a peer's copy into it could still be in flight
+}
+
+// BPTT (same maths as gru_bwd_kernel in gru.cu).
+template <int H>
+__global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a) {
+    using Cfg = GfCfg<H>;
+    constexpr int U = Cfg::U, KP = Cfg::KP, KP2 = Cfg::KP2, R = GF_R;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / GF_C;
+    const int d = cid % a.ndir, grp = cid / a.ndir;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __nv_bfloat16* WcT_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [U][KP]   WcT_s[i][cu] = Wc[unit_i][cu]
+    __nv_bfloat16* WgT_s = WcT_s + U * KP;                                        // [U][KP2]  WgT_s[i][gc] = Wg[unit_i][gc]
+    __nv_bfloat16* dcp_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);  // [C][R][U]       dc_pre, all units
+    __nv_bfloat16* dg_s = dcp_s + R * H;                                          // [2C][R][U]      [dr_pre ; du_pre]
+    __nv_bfloat16* stage_c = dg_s + 2 * R * H;                                    // [R][U]
+    __nv_bfloat16* stage_r = stage_c + R * U;
+    __nv_bfloat16* stage_u = stage_r + R * U;
+    float* red = reinterpret_cast<float*>(stage_u + R * U);                       // 1024 floats
+    uint64_t* bar_c = reinterpret_cast<uint64_t*>(red + 1024);
+    uint64_t* bar_g = bar_c + 1;
+
+    const float* __restrict__ Wg = a.Wg[d];
+    const float* __restrict__ Wc = a.Wc[d];
+    for (int idx = tid; idx < U * H; idx += GF_NT) {
+        const int ii = idx / H, cu = idx % H;
+        WcT_s[ii * KP + cu] = __float2bfloat16(__ldg(Wc + (long long)(rank * U + ii) * H + cu));
+    }
+    for (int idx = tid; idx < U * 2 * H; idx += GF_NT) {
+        const int ii = idx / (2 * H), gcol = idx % (2 * H);
+        WgT_s[ii * KP2 + gcol] = __float2bfloat16(__ldg(Wg + (long long)(rank * U + ii) * 2 * H + gcol));
+    }
+    if (tid == 0) {
+        gf_mbar_init(bar_c, 1); gf_mbar_init(bar_g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool act = tid < Cfg::ACT;
+    const int i = tid % U, r = tid / U;
+    const int n = grp * R + r;
+    int L = 0;
+    if (act && n < a.N) L = a.lengths ? min(max(a.lengths[n], 0), a.T) : a.T;
+    int Lmax = 0;
+    for (int rr = 0; rr < R; rr++) {
+        const int nn = grp * R + rr;
+        if (nn < a.N) Lmax = max(Lmax, a.lengths ? min(max(a.lengths[nn], 0), a.T) : a.T);
+    }
+    const int unit = rank * U + i;
+    const long long st_base = ((long long)d * a.N + n) * a.T;
+    float dh_carry = 0.f;
+    __syncthreads();
+    cluster.sync();
+
+    constexpr int MT = U / 16, KS = 8 / MT;          // output tiles (own units) and k-splits over the 8 warps
+    constexpr int NK_C = H / 16 / KS, NK_G = 2 * H / 16 / KS;
+    const int g4 = lane >> 2, t4 = lane & 3;
+
+    float rg = 0.f, ug = 0.f, cc = 0.f, hp = 0.f, dout = 0.f;
+    auto load_step = [&](int s) {
+        if (act && s >= 0 && s < L) {
+            const int t = (d == 0) ? s : (L - 1 - s);
+            const long long so = (st_base + t) * H + unit;
+            rg = a.st_r[so]; ug = a.st_u[so]; cc = a.st_c[so]; hp = a.st_hprev[so];
+            dout = a.dout[((long long)n * a.T + t) * a.dout_ld + d * H + unit];
+        }
+    };
+    load_step(Lmax - 1);
+    int it = 0;
+    for (int s = Lmax - 1; s >= 0; s--, it++) {
+        const uint32_t par = it & 1;
+        const bool valid = act && (s < L);
+        const int t = (d == 0) ? s : (L - 1 - s);
+        const float r_ = rg, u_ = ug, c_ = cc, hp_ = hp;
+        float dh = dh_carry + (valid ? dout : 0.f);
+        if (tid == 0) { gf_mbar_expect_tx(bar_c, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_g, 2 * GF_C * Cfg::BLK_BYTES); }
+        load_step(s - 1);
+        float du_pre = 0.f, dc_pre = 0.f;
+        if (valid) {
+            du_pre = dh * (hp_ - c_) * u_ * (1.f - u_);
+            dc_pre = dh * (1.f - u_) * (1.f - c_ * c_);
+        }
+        if (act) stage_c[r * U + i] = __float2bfloat16(dc_pre);
+#if GF_USE_STASYNC
+        __syncthreads();
+        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_c, dcp_s + rank * R * U, bar_c, tid);
+#else
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < GF_C) gf_push(stage_c, dcp_s + rank * R * U, bar_c, Cfg::BLK_BYTES, tid);
+#endif
+        gf_mbar_wait(bar_c, par);
+        // d(r*h)[own units] = sum_cu dc_pre[cu] * Wc[unit][cu]
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mt = warp % MT, ks = warp / MT;
+            gf_mma_slice<U, KP>(acc, WcT_s, mt * 16, dcp_s, ks * NK_C * 16, NK_C, lane);
+            float* rp = red + ks * (U * R);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+        }
+        __syncthreads();
+        float d_rh = 0.f, dr_pre = 0.f;
+        if (act) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) d_rh += red[ks * (U * R) + i * R + r];
+            if (valid) dr_pre = d_rh * hp_ * r_ * (1.f - r_);
+            stage_r[r * U + i] = __float2bfloat16(dr_pre);
+            stage_u[r * U + i] = __float2bfloat16(du_pre);
+        }
+#if GF_USE_STASYNC
+        __syncthreads();
+        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_r, dg_s + rank * R * U, bar_g, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, tid);
+#else
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < GF_C) gf_push(stage_r, dg_s + rank * R * U, bar_g, Cfg::BLK_BYTES, tid);
+        else if (tid < 2 * GF_C) gf_push(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, Cfg::BLK_BYTES, tid - GF_C);
+#endif
+        gf_mbar_wait(bar_g, par);
+        // dh_prev += sum_gc [dr_pre;du_pre][gc] * Wg[unit][gc]      (dg_s is blocked [2C][R][U]: k = gc, K = 2H)
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mt = warp % MT, ks = warp / MT;
+            gf_mma_slice<U, KP2>(acc, WgT_s, mt * 16, dg_s, ks * NK_G * 16, NK_G, lane);
+            float* rp = red + ks * (U * R);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
+            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+        }
+        __syncthreads();
+        if (act) {
+            float sg = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) sg += red[ks * (U * R) + i * R + r];
+            if (valid) {
+                dh_carry = dh * u_ + d_rh * r_ + sg;
+                float* g = a.dgx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
+                g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre;
+                a.st_r[(st_base + t) * H + unit] = r_ * hp_;
+            }
+        }
+        __syncthreads();      // `red` / stages are rewritten at the top of the next iteration
+    }
+    if (act && a.dh0 && n < a.N) a.dh0[(long long)n * a.ndir * H + d * H + unit] = dh_carry;
+    cluster.sync();
+}
+
+template <int H>
+static int launch_gru_fast_t(const GruArgs& a, bool bwd, cudaStream_t s) {
+    using Cfg = GfCfg<H>;
+    const size_t smem = Cfg::smem_bytes;
+    auto kern = bwd ? gru_fast_bwd_kernel<H> : gru_fast_fwd_kernel<H>;
+    TACO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(GF_C * a.ndir * cdiv(a.N, GF_R));
+    cfg.blockDim = dim3(GF_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GF_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    g_launch_count++;
+    return TACO_OK;
+}
+
+int launch_gru_fast_fwd(const GruArgs& a, cudaStream_t s) {
+    TACO_REQUIRE(a.H == 128 || a.H == 256, TACO_ESHAPE, "gru: hidden size %d not instantiated (128, 256)", a.H);
+    return a.H == 128 ? launch_gru_fast_t<128>(a, false, s) : launch_gru_fast_t<256>(a, false, s);
+}
+int launch_gru_fast_bwd(const GruArgs& a, cudaStream_t s) {
+    TACO_REQUIRE(a.H == 128 || a.H == 256, TACO_ESHAPE, "gru: hidden size %d not instantiated (128, 256)", a.H);
+    return a.H == 128 ? launch_gru_fast_t<128>(a, true, s) : launch_gru_fast_t<256>(a, true, s);
+}
+
+}  // namespace taco

@@ -41,6 +41,7 @@ int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const f
 // gru.cu — cluster-persistent GRU recurrences (TF GRUCell semantics)
 struct GruArgs {
     int N, T, H, ndir;
+    int fast;                // 1: bf16-weight mma + mbarrier-exchange kernels (gru_fast.cu); 0: exact fp32 kernels (gru.cu)
     // x-side pre-activations (biases included) from the hoisted GEMM: row(n,t) = n*gx_rs_n + t + gx_row0;
     // direction d uses columns [d*3H, (d+1)*3H) as r | u | c.
     const float* gx; long long gx_ld; long long gx_rs_n; long long gx_row0;
@@ -60,6 +61,8 @@ struct GruArgs {
 };
 int launch_gru_fwd(const GruArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruArgs& a, cudaStream_t s);
+int launch_gru_fast_fwd(const GruArgs& a, cudaStream_t s);
+int launch_gru_fast_bwd(const GruArgs& a, cudaStream_t s);
 
 // attention.cu — cluster-persistent attention recurrence of the decoder
 struct AttArgs {
@@ -85,6 +88,9 @@ struct AttArgs {
 };
 int launch_att_fwd(const AttArgs& a, cudaStream_t s);
 int launch_att_bwd(const AttArgs& a, cudaStream_t s);
+bool att_fast_supported(const AttArgs& a);
+int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s);   // TACO_ENOTSUP when 16-CTA clusters cannot be launched
+int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s);
 int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,
                         int N, int Ti, int Td, int A, int fast, cudaStream_t s);
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);

@@ -123,7 +123,7 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
         }
         TACO_TRY(launch_gemm(d, 4, prec, s));
         GruArgs a{};
-        a.N = g.N; a.T = g.T; a.H = H; a.ndir = 2;
+        a.N = g.N; a.T = g.T; a.H = H; a.ndir = 2; a.fast = (m.cfg.precision != TACO_PREC_FP32);
         a.gx = R("gx"); a.gx_ld = 6 * H; a.gx_rs_n = g.Tp; a.gx_row0 = g.PL;
         a.Wg[0] = m.P(px + "gru_fw/gates_kernel") + (long long)H * 2 * H; a.Wc[0] = m.P(px + "gru_fw/cand_kernel") + (long long)H * H;
         a.Wg[1] = m.P(px + "gru_bw/gates_kernel") + (long long)H * 2 * H; a.Wc[1] = m.P(px + "gru_bw/cand_kernel") + (long long)H * H;
@@ -150,7 +150,7 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
     TACO_CHECK_CUDA(cudaMemsetAsync(R("dgx"), 0, sizeof(float) * (size_t)rows * 6 * H, s));
     {
         GruArgs a{};
-        a.N = g.N; a.T = g.T; a.H = H; a.ndir = 2;
+        a.N = g.N; a.T = g.T; a.H = H; a.ndir = 2; a.fast = (m.cfg.precision != TACO_PREC_FP32);
         a.gx = R("gx"); a.gx_ld = 6 * H; a.gx_rs_n = g.Tp; a.gx_row0 = g.PL;
         a.Wg[0] = m.P(px + "gru_fw/gates_kernel") + (long long)H * 2 * H; a.Wc[0] = m.P(px + "gru_fw/cand_kernel") + (long long)H * H;
         a.Wg[1] = m.P(px + "gru_bw/gates_kernel") + (long long)H * 2 * H; a.Wc[1] = m.P(px + "gru_bw/cand_kernel") + (long long)H * H;

@@ -59,7 +59,7 @@ static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, 
     d[1] = gd(x, m.P(gn + "/cand_kernel"), gx + 2 * Y, rows, Y, Y, Y, Y, 3 * Y); d[1].bias = m.P(gn + "/cand_bias");
     TACO_TRY(launch_gemm(d, 2, m.cfg.precision, s));
     GruArgs a{};
-    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1;
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1; a.fast = (m.cfg.precision != TACO_PREC_FP32);
     a.gx = gx; a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
     a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
     a.h0 = h0; a.res = x; a.res_ld = Y; a.out = y; a.out_ld = Y;
@@ -126,7 +126,7 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     float* dgx = m.W(rp + "dgx");
     TACO_CHECK_CUDA(cudaMemsetAsync(dgx, 0, sizeof(float) * (size_t)rows * 3 * Y, s));
     GruArgs a{};
-    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1;
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1; a.fast = (m.cfg.precision != TACO_PREC_FP32);
     a.gx = m.W(rp + "gx"); a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
     a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
     a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
