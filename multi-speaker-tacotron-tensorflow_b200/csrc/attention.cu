@@ -78,7 +78,8 @@ __device__ __forceinline__ void push_rm(cg::cluster_group& cl, float* mat_s, int
 }
 
 static inline size_t att_fwd_smem_floats(const AttArgs& a, int Tip) {
-    return (size_t)AT_R * (a.E + a.Z1 + (a.Z + a.SPK) + 2 * a.HA + a.A) + (size_t)4 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
+    const size_t fr = a.free_run ? (size_t)AT_R * (a.M + 6 * a.Y) : 0;
+    return fr + (size_t)AT_R * (a.E + a.Z1 + (a.Z + a.SPK) + 2 * a.HA + a.A) + (size_t)4 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
 }
 static inline size_t att_bwd_smem_floats(const AttArgs& a, int Tip) {
     return (size_t)AT_R * (a.Y + a.A + a.Z1 + a.Z + 3 * a.HA + a.E) + (size_t)8 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
@@ -111,6 +112,10 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
     float* red2 = red + R * AT_NT;          // [R][NT]
     float* stage = red2 + R * AT_NT;        // [1024]
     float* v_s = stage + 1024;              // [A]
+    // free-running mode only
+    float* x_s = v_s + A;                   // [M][R]   step input (last frame of the previous step)
+    float* y0_s = x_s + (a.free_run ? a.M * R : 0);   // [Y][R]
+    float* h1_s = y0_s + Y * R; float* rhd_s = h1_s + Y * R; float* y1_s = rhd_s + Y * R; float* h2_s = y1_s + Y * R; float* y2_s = h2_s + Y * R;
 
     // ---- init ------------------------------------------------------------------------------
     if (a.att_type == TACO_ATT_BAH_NORM) {
@@ -136,12 +141,22 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         e_s[idx] = 0.f;
     }
     const float score_bias = (a.att_type == TACO_ATT_BAH_MON) ? a.score_bias[0] : 0.f;
+    if (a.free_run) {
+        for (int idx = tid; idx < a.M * R; idx += AT_NT) x_s[idx] = 0.f;                    // <GO> frame (helpers.py:70-72)
+        for (int idx = tid; idx < Y * R; idx += AT_NT) {
+            int k = idx / R, r = idx % R, n = grp * R + r;
+            h1_s[idx] = (a.h1_0 && n < a.N) ? a.h1_0[(long long)n * Y + k] : 0.f;
+            h2_s[idx] = (a.h2_0 && n < a.N) ? a.h2_0[(long long)n * Y + k] : 0.f;
+        }
+    }
 
     // activation-thread coordinates for 32-unit and 16-unit layers
     const int i32 = tid % 32, r32 = tid / 32;            // 256 threads: (unit, row)
     const int n32 = grp * R + r32;
     const bool row_ok32 = n32 < a.N;
     float ha_own = (a.ha0 && row_ok32) ? a.ha0[(long long)n32 * HA + rank * Uh + i32] : 0.f;
+    float h1_own = (a.free_run && a.h1_0 && row_ok32) ? a.h1_0[(long long)n32 * Y + rank * Uy + i32] : 0.f;
+    float h2_own = (a.free_run && a.h2_0 && row_ok32) ? a.h2_0[(long long)n32 * Y + rank * Uy + i32] : 0.f;
     __syncthreads();
     cl.sync();
 
@@ -153,6 +168,7 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kl = E / KS;
             mv_acc(acc, a.W1c + rank * Uz1 + col, Z1, ctx_s, ks * kl, (ks + 1) * kl);
+            if (a.free_run) { const int kx = a.M / KS; mv_acc(acc, a.W1x + rank * Uz1 + col, Z1, x_s, ks * kx, (ks + 1) * kx); }
             red_store(red, tid, acc);
         }
         __syncthreads();
@@ -161,7 +177,8 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
             float v = 0.f;
             if (n < a.N) {
                 const long long row = (long long)n * Td + t;
-                v = fmaxf(red_sum(red, r, i, Uz1) + __ldg(a.px + row * Z1 + rank * Uz1 + i), 0.f);
+                const float xb = a.free_run ? __ldg(a.b1 + rank * Uz1 + i) : __ldg(a.px + row * Z1 + rank * Uz1 + i);
+                v = fmaxf(red_sum(red, r, i, Uz1) + xb, 0.f);
                 if (a.s_z1) {
                     a.s_z1[row * Z1 + rank * Uz1 + i] = v;
                 }
@@ -371,8 +388,89 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
             red_store(red2, tid, acc);
         }
         __syncthreads();
-        if (row_ok32) a.y0[row32 * Y + rank * Uy + i32] = yh + red_sum(red2, r32, i32, Uy) + __ldg(a.bo + rank * Uy + i32);
-        // no barrier: the next step's P1 reads ctx_s (stable) and writes `red`, not `red2`
+        const float y0v = row_ok32 ? yh + red_sum(red2, r32, i32, Uy) + __ldg(a.bo + rank * Uy + i32) : 0.f;
+        if (row_ok32 && a.y0) a.y0[row32 * Y + rank * Uy + i32] = y0v;
+        // (teacher-forced mode) no barrier: the next step's P1 reads ctx_s (stable) and writes `red`, not `red2`
+        if (a.free_run) {
+            // ===== decoder RNN stack and mel projection inside the loop (tacotron.py:171-179; helpers.py:26-32) =====
+            stage[i32 * R + r32] = y0v;
+            __syncthreads();
+            push_um(cl, y0_s, stage, rank, Uy, tid);
+            cl.sync();
+            float yin = y0v;
+            for (int layer = 0; layer < 2; layer++) {
+                const float* Wg_ = layer ? a.Wg2 : a.Wg1; const float* bg_ = layer ? a.bg2 : a.bg1;
+                const float* Wc_ = layer ? a.Wc2 : a.Wc1; const float* bc_ = layer ? a.bc2 : a.bc1;
+                float* xin_s = layer ? y1_s : y0_s; float* hst_s = layer ? h2_s : h1_s; float* yout_s = layer ? y2_s : y1_s;
+                float& h_own = layer ? h2_own : h1_own;
+                {   // gates over [x ; h]
+                    const int ncols = 2 * Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                    const int gcol = (col < Uy) ? rank * Uy + col : Y + rank * Uy + (col - Uy);
+                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const int kl = Y / KS;
+                    mv_acc(acc, Wg_ + gcol, 2 * Y, xin_s, ks * kl, (ks + 1) * kl);
+                    mv_acc(acc, Wg_ + (long long)Y * 2 * Y + gcol, 2 * Y, hst_s, ks * kl, (ks + 1) * kl);
+                    red_store(red, tid, acc);
+                }
+                {   // x part of the candidate
+                    const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const int kl = Y / KS;
+                    mv_acc(acc, Wc_ + rank * Uy + col, Y, xin_s, ks * kl, (ks + 1) * kl);
+                    red_store(red2, tid, acc);
+                }
+                __syncthreads();
+                const int unit = rank * Uy + i32;
+                const float rgd = sigm_<FAST>(red_sum(red, r32, i32, 2 * Uy) + __ldg(bg_ + unit));
+                const float ugd = sigm_<FAST>(red_sum(red, r32, Uy + i32, 2 * Uy) + __ldg(bg_ + Y + unit));
+                const float cxd = red_sum(red2, r32, i32, Uy);
+                stage[i32 * R + r32] = rgd * h_own;
+                __syncthreads();
+                push_um(cl, rhd_s, stage, rank, Uy, tid);
+                cl.sync();
+                {
+                    const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const int kl = Y / KS;
+                    mv_acc(acc, Wc_ + (long long)Y * Y + rank * Uy + col, Y, rhd_s, ks * kl, (ks + 1) * kl);
+                    red_store(red, tid, acc);
+                }
+                __syncthreads();
+                const float cd = tanh_<FAST>(red_sum(red, r32, i32, Uy) + cxd + __ldg(bc_ + unit));
+                const float hn = ugd * h_own + (1.f - ugd) * cd;
+                h_own = row_ok32 ? hn : 0.f;
+                yin = yin + h_own;                                  // ResidualWrapper: y = x + GRU(x, h)
+                stage[i32 * R + r32] = h_own;
+                stage[256 + i32 * R + r32] = yin;
+                __syncthreads();
+                push_um(cl, hst_s, stage, rank, Uy, tid);
+                push_um(cl, yout_s, stage + 256, rank, Uy, tid);
+                cl.sync();
+            }
+            {   // r-frame mel projection (own MR/C columns, padded to 64 for the thread mapping)
+                const int MR = a.M * a.r, UO = MR / AT_C;
+                const int col = tid % 64, ks = tid / 64;
+                float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const int kl = Y / 4;
+                if (col < UO) mv_acc(acc, a.Wmel + rank * UO + col, MR, y2_s, ks * kl, (ks + 1) * kl);
+                red_store(red, tid, acc);
+                __syncthreads();
+                for (int idx = tid; idx < UO * R; idx += AT_NT) {
+                    const int i = idx % UO, r = idx / UO, n = grp * R + r;
+                    const int c = rank * UO + i;
+                    float o = 0.f;
+                    if (n < a.N) {
+                        o = red_sum(red, r, i, 64) + __ldg(a.bmel + c);
+                        a.mel_out[(long long)n * a.mel_bs + (long long)t * MR + c] = o;
+                    }
+                    if (c >= MR - a.M) {                            // last of the r frames feeds the next step
+                        const int xi = c - (MR - a.M);
+                        for (int peer = 0; peer < AT_C; peer++) cl.map_shared_rank(x_s, peer)[xi * R + r] = o;
+                    }
+                }
+                cl.sync();
+            }
+        }
     }
     if (a.ha_final && row_ok32) a.ha_final[(long long)n32 * HA + rank * Uh + i32] = ha_own;
 }
@@ -750,6 +848,8 @@ static int att_check(const AttArgs& a) {
                  "attention kernel instantiated for E=A=HA=Z1=Y=256, Z=128 (got %d %d %d %d %d %d)", a.E, a.A, a.HA, a.Z1, a.Y, a.Z);
     TACO_REQUIRE(a.SPK == 0 || a.SPK == 16, TACO_ESHAPE, "attention: speaker width %d unsupported", a.SPK);
     TACO_REQUIRE(a.Ti <= 1024, TACO_ESHAPE, "attention: T_in %d too long", a.Ti);
+    if (a.free_run) TACO_REQUIRE(a.M % 8 == 0 && (a.M * a.r) % AT_C == 0 && (a.M * a.r) / AT_C <= 64 && a.W1x && a.Wg1 && a.Wg2 && a.Wmel && a.mel_out,
+                                 TACO_ESHAPE, "free-running decoder: unsupported mel/r sizes or missing weights");
     return TACO_OK;
 }
 
@@ -775,7 +875,7 @@ static int att_launch(K kern, const AttArgs& a, bool bwd, cudaStream_t s) {
 
 int launch_att_fwd(const AttArgs& a, cudaStream_t s) {
     TACO_TRY(att_check(a));
-    if (a.fast && att_fast_supported(a)) { int rc = launch_att_fast_fwd(a, s); if (rc != TACO_ENOTSUP) return rc; }
+    if (a.fast && !a.free_run && att_fast_supported(a)) { int rc = launch_att_fast_fwd(a, s); if (rc != TACO_ENOTSUP) return rc; }
     return a.fast ? att_launch(att_fwd_kernel<true>, a, false, s) : att_launch(att_fwd_kernel<false>, a, false, s);
 }
 int launch_att_bwd(const AttArgs& a, cudaStream_t s) {

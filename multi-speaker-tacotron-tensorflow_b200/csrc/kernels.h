@@ -81,6 +81,14 @@ struct AttArgs {
     float* ha_final;        // [N, HA] or NULL
     // stash (training)
     float *s_z1, *s_z, *s_r, *s_u, *s_c, *s_haprev, *s_ha, *s_q, *s_ctxin, *s_ctx, *s_e, *s_a;
+    // free-running decoding (inference / rnn_decoder_test_mode; helpers.py:26-32,63-64): the step input is the last of the r
+    // frames the previous step produced, so prenet x-part, both residual GRUs and the mel projection run inside the loop
+    int free_run, M, r;
+    const float *W1x, *b1;                                   // dense_1 rows [0,M) and bias
+    const float *Wg1, *bg1, *Wc1, *bc1, *Wg2, *bg2, *Wc2, *bc2;  // full TF kernels of the two decoder GRUs
+    const float *Wmel, *bmel;                                // [Y, M*r], [M*r]
+    const float *h1_0, *h2_0;                                // [N, Y] or NULL
+    float* mel_out; long long mel_bs;                        // mel_out[n*mel_bs + t*M*r + c]
     // backward
     const float* dy0;       // [N*Td, Y]
     const float *W1cT, *W2T, *WgT, *WcT, *WqT, *WoT;   // transposed weights

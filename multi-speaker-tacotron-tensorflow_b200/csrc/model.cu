@@ -265,6 +265,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     const int prec = c.precision;
     const int N = m.shape.N, To = m.shape.To, M = c.num_mels, F = c.num_freq;
     TACO_REQUIRE(m.shape.training && b->mel_targets && b->linear_targets, TACO_ESTATE, "backward needs a training forward with targets");
+    TACO_REQUIRE(!b->rnn_decoder_test_mode, TACO_ESTATE, "backward through the free-running decoder is not defined (train.py:158-166 builds that model forward-only)");
     TACO_CHECK_CUDA(cudaMemsetAsync(m.grads, 0, sizeof(float) * (size_t)m.n_trainable, s));
     double* sc = m.Wd("scalars");
     TACO_CHECK_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, s));

@@ -70,8 +70,7 @@ static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, 
 int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const DecDims D = dec_dims(m);
     const int prec = m.cfg.precision, training = m.shape.training;
-    TACO_REQUIRE(b->mel_targets != nullptr && !b->rnn_decoder_test_mode, TACO_ESTATE,
-                 "decoder: free-running decoding (inference / rnn_decoder_test_mode) is not built yet; teacher-forced only");
+    const bool free_run = (b->mel_targets == nullptr) || b->rnn_decoder_test_mode;      // helpers.py:26-32,63-64
     const int rows = D.N * D.Td;
     const float* memory = m.W("enc_cbhg/rnn_out");
     // attention keys = memory . Wm (no bias, no length mask)   tacotron.py:133-134
@@ -80,8 +79,8 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
     // teacher-forcing inputs and the hoisted x-side of prenet layer 1   helpers.py:44,60-67; rnn_wrappers.py:249,367-369
-    TACO_TRY(launch_teacher_inputs(b->mel_targets, m.W("dec/x_all"), D.N, D.Td, D.To, D.r, D.M, s));
-    {
+    if (!free_run) {
+        TACO_TRY(launch_teacher_inputs(b->mel_targets, m.W("dec/x_all"), D.N, D.Td, D.To, D.r, D.M, s));
         taco_gemm_desc d = gd(m.W("dec/x_all"), m.P("dec_prenet/dense_1/kernel"), m.W("dec/px"), rows, D.Z1, D.M, D.M, D.Z1, D.Z1);
         d.bias = m.P("dec_prenet/dense_1/bias");
         TACO_TRY(launch_gemm(&d, 1, prec, s));
@@ -95,6 +94,21 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     a.manual = b->manual_alignments;
     fill_att_weights(m, D, a);
     a.y0 = m.W("dec/y0"); a.align = m.W("alignments");
+    const float* h1 = m.has_region("spk/dec_init1") ? m.W("spk/dec_init1") : nullptr;
+    const float* h2 = m.has_region("spk/dec_init2") ? m.W("spk/dec_init2") : nullptr;
+    if (free_run) {
+        // the whole decoder step (prenet x-part, both residual GRUs, mel projection) runs inside the recurrence kernel
+        const CbhgGeom& g = m.post;
+        a.free_run = 1; a.M = D.M; a.r = D.r; a.fast = 0;
+        a.W1x = m.P("dec_prenet/dense_1/kernel"); a.b1 = m.P("dec_prenet/dense_1/bias");
+        a.Wg1 = m.P("dec_gru_1/gates_kernel"); a.bg1 = m.P("dec_gru_1/gates_bias"); a.Wc1 = m.P("dec_gru_1/cand_kernel"); a.bc1 = m.P("dec_gru_1/cand_bias");
+        a.Wg2 = m.P("dec_gru_2/gates_kernel"); a.bg2 = m.P("dec_gru_2/gates_bias"); a.Wc2 = m.P("dec_gru_2/cand_kernel"); a.bc2 = m.P("dec_gru_2/cand_bias");
+        a.Wmel = m.P("mel_proj/kernel"); a.bmel = m.P("mel_proj/bias");
+        a.h1_0 = h1; a.h2_0 = h2;
+        a.mel_out = m.W("post_cbhg/xin_p") + (long long)g.PL * D.M; a.mel_bs = (long long)g.Tp * D.M;
+        a.y0 = nullptr;
+        return launch_att_fwd(a, s);
+    }
     if (training) {
         a.s_z1 = m.W("dec/s_z1"); a.s_z = m.W("dec/s_z"); a.s_r = m.W("dec/s_r"); a.s_u = m.W("dec/s_u"); a.s_c = m.W("dec/s_c");
         a.s_haprev = m.W("dec/s_haprev"); a.s_ha = m.W("dec/s_ha"); a.s_q = m.W("dec/s_q"); a.s_ctxin = m.W("dec/s_ctxin");
@@ -102,8 +116,6 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     }
     TACO_TRY(launch_att_fwd(a, s));
     // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
-    const float* h1 = m.has_region("spk/dec_init1") ? m.W("spk/dec_init1") : nullptr;
-    const float* h2 = m.has_region("spk/dec_init2") ? m.W("spk/dec_init2") : nullptr;
     TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
     TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
     // r-frame mel projection, written straight into the post-net's padded input (= mel_outputs)   tacotron.py:178-179,213-214

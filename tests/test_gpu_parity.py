@@ -1,0 +1,255 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every check goes through the C ABI (ctypes) and compares the CUDA
+path with the CPU oracle on identical seeded inputs, with the committed golden fixtures, or through size-independent
+properties at the full BASELINE size.
+
+Stated tolerances (values are O(1): normalised spectrogram range [0,1]):
+  fp32 mode : outputs max-abs <= 1e-4, loss 1e-5, per-tensor gradient rel-L2 <= 1e-2 (argmax/ReLU routing flips) with the
+              whole-gradient cosine >= 0.99999, Adam update 1e-6
+  tf32 mode : (TF32 tensor-core GEMMs, bf16 recurrent weights, fast tanh/sigmoid) outputs max-abs <= 3e-2, loss rel 1e-3,
+              whole-gradient cosine >= 0.995, grad-norm rel 2e-2
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+
+from oracle import tacotron_oracle as O  # noqa: E402
+from oracle import griffin_lim_oracle as G  # noqa: E402
+
+TOL = {"fp32": dict(out=1e-4, loss=1e-5, cos=0.99999, gn=1e-4), "tf32": dict(out=3e-2, loss=1e-3, cos=0.995, gn=2e-2)}
+
+
+def _batch(N, Ti, To, lengths, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    inp = torch.randint(2, 80, (N, Ti), generator=g, dtype=torch.int32)
+    L = torch.tensor(lengths, dtype=torch.int32)
+    for n in range(N):
+        inp[n, L[n] - 1] = 1
+        inp[n, L[n]:] = 0
+    return dict(inputs=inp, input_lengths=L, mel_targets=torch.rand(N, To, 80, generator=g),
+                linear_targets=torch.rand(N, To, 1025, generator=g), loss_coeff=torch.rand(N, generator=g) + 0.5)
+
+
+def _oracle_step(named, hp, b):
+    names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
+    out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"], speaker_mode="none")
+    ls = O.losses(out, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(named[k])) for k, g in zip(names, gl)}
+    return out, {k: float(v) for k, v in ls.items()}, grads
+
+
+def _cosine(got, ref, names):
+    a = torch.cat([got[k].float().cpu().reshape(-1) for k in names])
+    b = torch.cat([ref[k].reshape(-1) for k in names])
+    return float((a @ b) / (a.norm() * b.norm())), float(a.norm()), float(b.norm())
+
+
+@pytest.fixture(scope="module")
+def golden_setup(tb, hp5):
+    import make_golden as mg
+    return mg.golden_params(hp5), mg.golden_batch()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_train_step_matches_golden_fixture(tb, hp5, golden_setup, prec):
+    named, b = golden_setup
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_train_small.npz"))
+    tol = TOL[prec]
+    eng = tb.Engine(hp5, 1, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    eng.backward()
+    sc = eng.scalars()
+    assert np.abs(out["mel_outputs"].cpu().numpy() - gold["mel_outputs"]).max() <= tol["out"]
+    assert np.abs(out["linear_outputs"].cpu().numpy() - gold["linear_outputs"]).max() <= tol["out"]
+    assert np.abs(out["alignments"].cpu().numpy() - gold["alignments"]).max() <= tol["out"]
+    assert abs(sc["loss"] - gold["scalars"][0]) <= tol["loss"] * max(1, gold["scalars"][0])
+    assert abs(sc["mel_loss"] - gold["scalars"][1]) <= tol["loss"] and abs(sc["linear_loss"] - gold["scalars"][2]) <= tol["loss"]
+    g = eng.named_gradients()
+    for key, name in (("grad_attention_v", "attention/v"), ("grad_mel_proj_bias", "mel_proj/bias"), ("grad_embedding", "embedding")):
+        ref = gold[key]
+        rel = np.linalg.norm(g[name].cpu().numpy() - ref) / np.linalg.norm(ref)
+        assert rel <= (2e-3 if prec == "fp32" else 1e-1), (name, rel)
+    eng.optimizer_step(True)
+    sc = eng.scalars()
+    assert abs(sc["grad_norm"] - gold["scalars"][4]) <= tol["gn"] * gold["scalars"][4]
+    assert abs(sc["learning_rate"] - gold["scalars"][5]) <= 1e-12
+    if prec == "fp32":
+        newp = eng.named_parameters()
+        assert np.abs(newp["attention/v"].cpu().numpy() - gold["param_after_attention_v"]).max() <= 1e-6
+        assert np.abs(newp["enc_cbhg/proj_1/moving_mean"].cpu().numpy() - gold["bn_after_enc_p1_mean"]).max() <= 1e-6
+    eng.close()
+
+
+@pytest.mark.parametrize("prec,shape", [("fp32", (3, 13, 20, [13, 9, 5])), ("fp32", (9, 17, 10, [17, 1, 2, 17, 8, 9, 16, 3, 5])),
+                                        ("fp32", (1, 8, 5, [8])), ("tf32", (3, 13, 20, [13, 9, 5])), ("fp32", (2, 50, 200, [50, 50]))])
+def test_forward_backward_vs_oracle(tb, hp5, prec, shape):
+    """Ragged lengths, batch sizes that do not fill a row group, T_in not a multiple of the cluster size, one decoder step."""
+    import make_golden as mg
+    N, Ti, To, lengths = shape
+    named = mg.golden_params(hp5, seed=31)
+    b = _batch(N, Ti, To, lengths)
+    ref_out, ref_ls, ref_g = _oracle_step(named, hp5, b)
+    tol = TOL[prec]
+    eng = tb.Engine(hp5, 1, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        err = (out[k].cpu() - ref_out[k].detach()).abs().max().item()
+        assert err <= tol["out"], (k, err)
+    mem = eng.region("enc_cbhg/rnn_out").view(N, Ti, -1).cpu()
+    for n, L in enumerate(lengths):
+        assert mem[n, L:].abs().max().item() == 0 if L < Ti else True      # padded encoder steps emit exact zeros (modules.py:92)
+    eng.backward()
+    sc = eng.scalars()
+    assert abs(sc["loss"] - ref_ls["loss"]) <= tol["loss"] * max(1.0, ref_ls["loss"])
+    got = eng.named_gradients()
+    names = sorted(ref_g)
+    cos, na, nb = _cosine(got, ref_g, names)
+    assert cos >= tol["cos"], cos
+    assert abs(na - nb) <= tol["gn"] * nb
+    if prec == "fp32":
+        for k in names:
+            dn = ref_g[k].norm().item()
+            if dn > 1e-7:
+                rel = (got[k].cpu() - ref_g[k]).norm().item() / dn
+                assert rel <= 1e-2, (k, rel)
+    eng.close()
+
+
+def test_optimizer_sequence_fp32(tb, hp5, golden_setup):
+    """Three consecutive steps: parameters, Adam moments and BN moving statistics track the oracle."""
+    named, b = golden_setup
+    P = {k: v.clone() for k, v in named.items()}
+    names = [k for k in P if not k.endswith(("moving_mean", "moving_var"))]
+    m = {k: torch.zeros_like(P[k]) for k in names}; v = {k: torch.zeros_like(P[k]) for k in names}
+    eng = tb.Engine(hp5, 1, precision="fp32", named_params=named)
+    for step in range(3):
+        res = O.train_step(P, m, v, hp5, b, step, True, 1, "none")
+        P, m, v = res["params"], res["m"], res["v"]
+        eng.train_step(b)
+        sc = eng.scalars()
+        assert abs(sc["loss"] - res["loss"]) <= 2e-5 and abs(sc["grad_norm"] - res["grad_norm"]) <= 1e-4 * res["grad_norm"]
+        assert abs(sc["learning_rate"] - res["lr"]) <= 1e-12
+    newp = eng.named_parameters()
+    worst = max((newp[k].cpu() - P[k]).abs().max().item() for k in P)
+    assert worst <= 5e-6, worst
+    assert eng.global_step == 3
+    eng.close()
+
+
+def test_loss_is_linear_in_loss_coeff_full_size(tb, hp5):
+    """BASELINE size (C2), TF32 mode: size-independent properties instead of an oracle run."""
+    N, Ti, To = 32, 128, 800
+    g = torch.Generator().manual_seed(5)
+    lengths = torch.randint(96, 129, (N,), generator=g).tolist(); lengths[0] = 128
+    b = _batch(N, Ti, To, lengths, seed=77)
+    eng = tb.Engine(hp5, 1, precision="tf32", seed=4321)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], torch.ones(N))
+    al = out["alignments"]
+    assert torch.isfinite(al).all() and (al >= 0).all() and (al.sum(1) <= 1 + 1e-3).all()     # monotonic attention mass <= 1
+    assert torch.isfinite(out["linear_outputs"]).all() and torch.isfinite(out["mel_outputs"]).all()
+    mem = eng.region("enc_cbhg/rnn_out").view(N, Ti, -1)
+    for n in (1, 7, 31):
+        if lengths[n] < Ti:
+            assert mem[n, lengths[n]:].abs().max().item() == 0
+    # training-mode batch norm: the normalised projection has per-channel mean beta and variance gamma^2 over valid frames
+    p2 = eng.region("enc_cbhg/p2_raw").view(N, Ti + 15, -1)[:, 7:7 + Ti]
+    mean, var = eng.region("enc_cbhg/p2_mean"), eng.region("enc_cbhg/p2_var")
+    assert (p2.mean((0, 1)) - mean).abs().max().item() <= 1e-3 and (p2.var((0, 1), unbiased=False) - var).abs().max().item() <= 1e-3
+    eng.backward()
+    l1 = eng.scalars()
+    g1 = eng.grads.clone()
+    assert torch.isfinite(g1).all()
+    eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], torch.full((N,), 2.0))
+    eng.backward()
+    l2 = eng.scalars()
+    assert abs(l2["loss"] - 2 * l1["loss"]) <= 1e-4 * l1["loss"]
+    assert abs(l2["loss_without_coeff"] - l1["loss_without_coeff"]) <= 1e-5
+    cos = float((eng.grads @ g1) / (eng.grads.norm() * g1.norm()))
+    assert cos >= 0.9999 and abs(float(eng.grads.norm() / g1.norm()) - 2.0) <= 1e-2
+    eng.close()
+
+
+def test_free_running_inference_matches_golden_and_oracle(tb, hp5, golden_setup):
+    named, b = golden_setup
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_infer_small.npz"))
+    eng = tb.Engine(hp5, 1, precision="fp32", named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], decoder_steps=6)
+    assert out["mel_outputs"].shape == (2, 30, 80) and out["alignments"].shape == (2, 11, 6)
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert np.abs(out[k].cpu().numpy() - gold[k]).max() <= 2e-4, k
+    # rnn_decoder_test_mode inside a training-mode graph (train.py:158-166): batch-norm uses batch statistics
+    ref = O.forward(named, hp5, b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"],
+                    rnn_decoder_test_mode=True, speaker_mode="none")
+    out2 = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], rnn_decoder_test_mode=True)
+    assert (out2["linear_outputs"].cpu() - ref["linear_outputs"]).abs().max().item() <= 2e-4
+    with pytest.raises(tb.capi.TacoError):
+        eng.backward()
+    eng.close()
+
+
+def test_reference_facing_model_api(tb, hp5, golden_setup):
+    named, b = golden_setup
+    model = tb.create_model(hp5)
+    model._precision = "fp32"
+    model.initialize(b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"], b["loss_coeff"], is_randomly_initialized=True)
+    model.engine.load_named(named)
+    model.initialize(b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"], b["loss_coeff"], is_randomly_initialized=True)
+    model.add_loss()
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_train_small.npz"))
+    assert abs(model.loss - gold["scalars"][0]) <= 1e-5 and abs(model.loss_without_coeff - gold["scalars"][3]) <= 1e-5
+    model.add_optimizer(0)
+    assert abs(model.learning_rate - gold["scalars"][5]) <= 1e-12
+    with pytest.raises(Exception, match="Unkown multi-speaker model type"):
+        tb.create_model(hp5).initialize(b["inputs"], b["input_lengths"], 2, torch.zeros(2, dtype=torch.int32))
+    sd = model.state_dict()
+    m2 = tb.create_model(hp5); m2._precision = "fp32"
+    m2.initialize(b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.engine.params, model.engine.params) and m2.engine.global_step == 1
+
+
+def test_error_behaviour(tb, hp5, golden_setup):
+    named, b = golden_setup
+    eng = tb.Engine(hp5, 1, precision="fp32", named_params=named)
+    with pytest.raises(tb.capi.TacoError, match="multiple of r"):
+        eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"][:, :14], b["linear_targets"][:, :14])
+    with pytest.raises(tb.capi.TacoError):
+        eng.backward()
+    eng.close()
+
+
+def test_griffin_lim_matches_oracle(tb):
+    from importlib import import_module
+    audio = import_module("multi-speaker-tacotron-tensorflow_b200.audio")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "griffin_lim_small.npz"))
+    gl = audio.GriffinLim(tb.hparams, max_frames=256)
+    wav = gl.inv_spectrogram(torch.from_numpy(gold["spec"]), torch.from_numpy(gold["phase"]), n_iters=int(gold["n_iters"])).cpu().numpy()
+    assert wav.shape == gold["wav"].shape == (300 * 11,)
+    scale = np.abs(gold["wav"]).max()
+    assert np.abs(wav - gold["wav"]).max() <= 2e-3 * scale, (np.abs(wav - gold["wav"]).max(), scale)
+    # properties at the C4 size: 1000 frames -> 299 700 samples, finite, spectral error decreases with iterations
+    rng = np.random.RandomState(3)
+    T = 1000
+    gl2 = audio.GriffinLim(tb.hparams, max_frames=1000)
+    y = (rng.randn(300 * (T - 1)) * 0.05).astype(np.float32)
+    mag = np.abs(G.stft(y, 2048, 300, 1200)).T
+    spec = np.clip((20 * np.log10(np.maximum(1e-5, mag)) - 20 + 100) / 100, 0, 1).astype(np.float32)
+    tgt = np.power(10.0, (spec * 100 - 100 + 20) * 0.05) ** 1.5
+    errs = []
+    for iters in (0, 10, 60):
+        w = gl2.inv_spectrogram(torch.from_numpy(spec), torch.from_numpy(rng.rand(T, 1025).astype(np.float32)), n_iters=iters)
+        assert w.shape == (299700,) and torch.isfinite(w).all()
+        # undo the pre-emphasis inverse before measuring the spectrum: x[n] = y[n] - 0.97 y[n-1]
+        wn = w.cpu().numpy(); x = wn.copy(); x[1:] -= 0.97 * wn[:-1]
+        est = np.abs(G.stft(x, 2048, 300, 1200)).T
+        errs.append(np.linalg.norm(est - tgt) / np.linalg.norm(tgt))
+    assert errs[2] < errs[1] < errs[0]
