@@ -417,6 +417,20 @@ int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cud
     return TACO_OK;
 }
 
+// dx = dy * (1 - |y|)^2 with y = softsign(x) = x / (1 + |x|)
+__global__ void softsign_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = 1.f - fabsf(y[i]);
+        dx[i] = dy[i] * t * t;
+    }
+}
+int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s) {
+    if (n <= 0) return TACO_OK;
+    softsign_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(dy, y, dx, n);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 // teacher-forcing inputs: x_all[(n*Td+t), :] = t==0 ? 0 : mel_targets[n, t*r-1, :]     (helpers.py:44,66,70-72)
 __global__ void teacher_inputs_kernel(const float* __restrict__ tgt, float* __restrict__ x, int N, int Td, int To, int r, int M) {
     long long total = (long long)N * Td * M;

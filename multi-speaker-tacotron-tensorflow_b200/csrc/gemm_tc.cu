@@ -20,7 +20,7 @@
 
 namespace taco {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand per stage
 constexpr int TC_SMEM = TC_STAGES * 2 * TC_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -174,7 +174,7 @@ __device__ unsigned long long g_tc_stamp[8];
         }                                                                                                 \
     } while (0)
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -378,7 +378,7 @@ bool gemm_tc_eligible(const taco_gemm_desc& g) {
     if (g.lda % 4 != 0 || g.ldb % 4 != 0) return false;
     const bool tap = g.ctap > 0 && (g.lda != g.ctap || g.ctap % 32 == 0);
     if (tap && g.ctap % 32 != 0) return false;
-    if ((long long)g.M * g.N * g.K < (1ll << 21)) return false;      // tiny problems: launch-bound either way, keep exact fp32
+    if ((long long)g.M * g.N * g.K < (1ll << 24)) return false;      // small problems: launch-bound either way; the grouped fp32 kernel batches them
     return true;
 }
 

@@ -28,6 +28,7 @@ int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const flo
 int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s);
 int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHpre, float* dTpre, float* dx,
                        long long n, cudaStream_t s);
+int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
 int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s);

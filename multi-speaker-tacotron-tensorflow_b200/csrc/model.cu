@@ -186,6 +186,13 @@ void Model::plan(const Shape& s) {
         if (tr) add("d_linear", {(int64_t)N * s.To, Fp});
     }
     if (tr) add("post_cbhg/d_mel_loss", {post.rows, c.num_mels});
+    if (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE) {
+        const int64_t S = c.speaker_embedding_size, Y = c.dec_rnn_size;
+        add("spk/embed", {N, S});
+        add("spk/before", {N, c.enc_prenet_sizes[1]}); add("spk/enc_init", {N, 2 * (int64_t)c.enc_rnn_size});
+        add("spk/att_init", {N, c.attention_state_size}); add("spk/dec_init1", {N, Y}); add("spk/dec_init2", {N, Y});
+        if (tr) { add("spk/d_pre", {N, 2 * (int64_t)c.enc_rnn_size + c.attention_state_size + Y}); add("spk/d_embed", {N, S}); }
+    }
     add("scalars", {8}, 0, true);
     add("scalars_f", {8});
     // zero-copy view of the mel outputs inside the post-net's padded input
@@ -234,7 +241,28 @@ static taco_gemm_desc gd0(const float* A, const float* B, float* C, int M, int N
 static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const taco_config& c = m.cfg;
     const int prec = c.precision, tr = m.shape.training;
-    TACO_REQUIRE(c.speaker_mode == TACO_SPK_NONE, TACO_ESTATE, "speaker injection kernels are not built yet (single-speaker only)");
+    TACO_REQUIRE(c.speaker_mode != TACO_SPK_SIMPLE, TACO_ESTATE, "model_type 'simple' (speaker-embedding concatenation) is not built yet");
+    const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
+    struct Site { const char* name; const char* region; int dim; };
+    const Site sites[5] = {{"before_highway", "spk/before", c.enc_prenet_sizes[1]}, {"encoder_rnn_init_state", "spk/enc_init", 2 * c.enc_rnn_size},
+                           {"attention_rnn_init_state", "spk/att_init", c.attention_state_size},
+                           {"decoder_rnn_init_states1", "spk/dec_init1", c.dec_rnn_size}, {"decoder_rnn_init_states2", "spk/dec_init2", c.dec_rnn_size}};
+    if (spk) {
+        // DeepVoice-2 style injection (tacotron.py:41-81): five vectors per utterance from the speaker id
+        TACO_REQUIRE(b->speaker_id != nullptr, TACO_EINVAL, "speaker_id is required when num_speakers > 1");
+        const int S = c.speaker_embedding_size;
+        if (c.speaker_mode == TACO_SPK_DEEPVOICE) {
+            TACO_TRY(launch_gather_rows(m.P("speaker_embedding"), b->speaker_id, m.W("spk/embed"), m.shape.N, 1, 1, 0, S, c.num_speakers, s));
+            for (const Site& st : sites) {
+                taco_gemm_desc d = gd0(m.W("spk/embed"), m.P(std::string("speaker/") + st.name + "/kernel"), m.W(st.region), m.shape.N, st.dim, S, S, st.dim, st.dim);
+                d.bias = m.P(std::string("speaker/") + st.name + "/bias"); d.act = ACT_SOFTSIGN;
+                TACO_TRY(launch_gemm(&d, 1, TACO_PREC_FP32, s));
+            }
+        } else {
+            for (const Site& st : sites)
+                TACO_TRY(launch_gather_rows(m.P(std::string("speaker/") + st.name + "/table"), b->speaker_id, m.W(st.region), m.shape.N, 1, 1, 0, st.dim, c.num_speakers, s));
+        }
+    }
     // ---- encoder prenet over the symbol table, then lookup (tacotron.py:34-39,101-103; modules.py:18-25; dropout = identity) ----
     const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];
     {
@@ -246,7 +274,7 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
     TACO_TRY(launch_gather_rows(m.W("enc/table2"), b->inputs, m.W("enc_cbhg/xin_p"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s));
-    TACO_TRY(cbhg_forward(m, m.enc, b->input_lengths, nullptr, nullptr, tr, s));
+    TACO_TRY(cbhg_forward(m, m.enc, b->input_lengths, spk ? m.W("spk/before") : nullptr, spk ? m.W("spk/enc_init") : nullptr, tr, s));
     TACO_TRY(decoder_forward(m, b, s));
     TACO_TRY(cbhg_forward(m, m.post, nullptr, nullptr, nullptr, tr, s));
     // ---- linear-spectrogram projection (tacotron.py:235) ----
@@ -305,7 +333,37 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     TACO_TRY(cbhg_backward(m, m.post, nullptr, false, false, s));
     TACO_TRY(launch_axpy(m.W("post_cbhg/d_xin_p"), m.W("post_cbhg/d_mel_loss"), 1.f, (long long)g.rows * M, s));
     TACO_TRY(decoder_backward(m, b, s));
-    TACO_TRY(cbhg_backward(m, m.enc, b->input_lengths, false, false, s));
+    const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
+    TACO_TRY(cbhg_backward(m, m.enc, b->input_lengths, spk, spk, s));
+    if (spk) {
+        // gradients of the five injected vectors -> their dense layers / tables -> the speaker embedding table
+        struct Site { const char* name; const char* region; const char* grad; int dim; };
+        const Site sites[5] = {{"before_highway", "spk/before", "enc_cbhg/d_before", c.enc_prenet_sizes[1]},
+                               {"encoder_rnn_init_state", "spk/enc_init", "enc_cbhg/d_h0", 2 * c.enc_rnn_size},
+                               {"attention_rnn_init_state", "spk/att_init", "dec/d_ha0", c.attention_state_size},
+                               {"decoder_rnn_init_states1", "spk/dec_init1", "dec/g1_dh0", c.dec_rnn_size},
+                               {"decoder_rnn_init_states2", "spk/dec_init2", "dec/g2_dh0", c.dec_rnn_size}};
+        const int S = c.speaker_embedding_size, Nb = m.shape.N;
+        if (c.speaker_mode == TACO_SPK_DEEPVOICE) {
+            TACO_CHECK_CUDA(cudaMemsetAsync(m.W("spk/d_embed"), 0, sizeof(float) * (size_t)Nb * S, s));
+            for (const Site& st : sites) {
+                float* dpre = m.W("spk/d_pre");
+                TACO_TRY(launch_softsign_bwd(m.W(st.grad), m.W(st.region), dpre, (long long)Nb * st.dim, s));
+                const std::string pn = std::string("speaker/") + st.name;
+                taco_gemm_desc w = gd0(m.W("spk/embed"), dpre, m.G(pn + "/kernel"), S, st.dim, Nb, S, st.dim, st.dim);
+                w.transA = 1; w.accumulate = 1;
+                TACO_TRY(launch_gemm(&w, 1, TACO_PREC_FP32, s));
+                TACO_TRY(launch_colsum(dpre, m.G(pn + "/bias"), Nb, st.dim, st.dim, s));
+                taco_gemm_desc e = gd0(dpre, m.P(pn + "/kernel"), m.W("spk/d_embed"), Nb, S, st.dim, st.dim, st.dim, S);
+                e.transB = 1; e.accumulate = 1;
+                TACO_TRY(launch_gemm(&e, 1, TACO_PREC_FP32, s));
+            }
+            TACO_TRY(launch_scatter_add_rows(m.W("spk/d_embed"), b->speaker_id, m.G("speaker_embedding"), Nb, 1, 1, 0, S, c.num_speakers, s));
+        } else {
+            for (const Site& st : sites)
+                TACO_TRY(launch_scatter_add_rows(m.W(st.grad), b->speaker_id, m.G(std::string("speaker/") + st.name + "/table"), Nb, 1, 1, 0, st.dim, c.num_speakers, s));
+        }
+    }
     // ---- encoder prenet tables backward ----
     {
         const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];

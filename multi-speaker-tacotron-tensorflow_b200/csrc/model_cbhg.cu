@@ -18,7 +18,7 @@ static void set_mask(taco_gemm_desc& d, const CbhgGeom& g) { d.mask_period = g.T
 
 // split-K factor for weight-gradient GEMMs (reduction over `rows`): enough CTAs to fill the machine
 static int wgrad_split(int M, int N, long long rows) {
-    long long tiles = (long long)cdiv(M, 64) * cdiv(N, 64);
+    long long tiles = (long long)cdiv(M, 128) * cdiv(N, 128);      // 128x128 tensor-core tiles, two CTAs per SM
     long long want = (2 * 148 + tiles - 1) / tiles;
     long long maxs = rows / 256 > 0 ? rows / 256 : 1;
     long long sp = want < maxs ? want : maxs;

@@ -11,7 +11,7 @@ static taco_gemm_desc gd(const float* A, const float* B, float* C, int M, int N,
     return d;
 }
 static int wsplit(int M, int N, long long rows) {
-    long long tiles = (long long)cdiv(M, 64) * cdiv(N, 64);
+    long long tiles = (long long)cdiv(M, 128) * cdiv(N, 128);      // 128x128 tensor-core tiles, two CTAs per SM
     long long want = (2 * 148 + tiles - 1) / tiles;
     long long maxs = rows / 256 > 0 ? rows / 256 : 1;
     long long sp = want < maxs ? want : maxs;

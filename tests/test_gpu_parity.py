@@ -253,3 +253,44 @@ def test_griffin_lim_matches_oracle(tb):
         est = np.abs(G.stft(x, 2048, 300, 1200)).T
         errs.append(np.linalg.norm(est - tgt) / np.linalg.norm(tgt))
     assert errs[2] < errs[1] < errs[0]
+
+
+@pytest.mark.parametrize("prec,emb", [("fp32", 16), ("fp32", 1), ("tf32", 16)])
+def test_deepvoice_speaker_injection_vs_oracle(tb, prec, emb):
+    """model_type='deepvoice' (tacotron.py:41-81,183-197): before_highway, encoder / attention / decoder initial states."""
+    hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice", speaker_embedding_size=emb)
+    S = 3
+    mode = tb.params.speaker_mode(hp, S)
+    named = tb.params.init_params(hp, S, seed=17, randomize_bn_state=True)
+    g = torch.Generator().manual_seed(3)
+    for k, v in named.items():
+        if k.startswith("speaker/") and k.endswith("/table"):
+            v.mul_(5.0)                                            # make the injected vectors matter
+    N, Ti, To = 5, 12, 15
+    b = _batch(N, Ti, To, [12, 7, 12, 3, 9], seed=9)
+    spk = torch.tensor([0, 2, 1, 2, 0], dtype=torch.int32)
+    names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
+    ref = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, spk, b["mel_targets"], b["linear_targets"], speaker_mode=mode)
+    ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    ref_g = {k: (gg if gg is not None else torch.zeros_like(named[k])) for k, gg in zip(names, gl)}
+    tol = TOL[prec]
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert (out[k].cpu() - ref[k].detach()).abs().max().item() <= tol["out"], k
+    eng.backward()
+    got = eng.named_gradients()
+    cos, na, nb = _cosine(got, ref_g, sorted(ref_g))
+    assert cos >= tol["cos"] and abs(na - nb) <= tol["gn"] * nb
+    if prec == "fp32":
+        spk_names = [k for k in names if k.startswith("speaker")]
+        assert spk_names
+        for k in spk_names:
+            dn = ref_g[k].norm().item()
+            assert dn > 0
+            assert (got[k].cpu() - ref_g[k]).norm().item() / dn <= 2e-3, k
+    with pytest.raises(tb.capi.TacoError, match="speaker_id"):
+        eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"])
+    eng.close()
