@@ -53,28 +53,32 @@ __device__ __forceinline__ void af_push(const void* stage, void* dst, uint64_t* 
     }
 }
 __device__ __forceinline__ void af_ldm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+    // not volatile: the weight tiles are never written after the prologue, so the loads may be hoisted and batched
+    asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 __device__ __forceinline__ void af_mma(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float af_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float af_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // acc += Wt[m0 .. m0+15][kw0 + 16*kt ...] . vec   for nk k-tiles;  Wt: bf16 [rows][KP]; vec: bf16 blocked [K/UB][R][UB], k index kv0 + ...
-template <int UB>
-__device__ __forceinline__ void af_mma_run(float acc[4], const bf16* Wt, int KP, int m0, int kw0, const bf16* vec, int kv0, int nk, int lane) {
+// All operand fragments of the NK k-tiles are fetched before the (dependent) mma chain starts.
+template <int UB, int NK>
+__device__ __forceinline__ void af_mma_run(float acc[4], const bf16* Wt, int KP, int m0, int kw0, const bf16* vec, int kv0, int lane) {
     const int g = lane >> 2, t = lane & 3;
     const uint32_t a_base = af_u32(Wt + (size_t)(m0 + (lane & 15)) * KP + kw0 + (lane >> 4) * 8);
-    for (int kk = 0; kk < nk; kk++) {
-        uint32_t a0, a1, a2, a3;
-        af_ldm4(a_base + (uint32_t)kk * 32, a0, a1, a2, a3);
+    uint32_t af[NK][4], bfr[NK][2];
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) {
+        af_ldm4(a_base + (uint32_t)kk * 32, af[kk][0], af[kk][1], af[kk][2], af[kk][3]);
         const int ka = kv0 + kk * 16 + 2 * t, kb = ka + 8;
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vec + ((ka / UB) * AF_R + g) * UB + (ka % UB));
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vec + ((kb / UB) * AF_R + g) * UB + (kb % UB));
-        af_mma(acc, a0, a1, a2, a3, b0, b1);
+        bfr[kk][0] = *reinterpret_cast<const uint32_t*>(vec + ((ka / UB) * AF_R + g) * UB + (ka % UB));
+        bfr[kk][1] = *reinterpret_cast<const uint32_t*>(vec + ((kb / UB) * AF_R + g) * UB + (kb % UB));
     }
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) af_mma(acc, af[kk][0], af[kk][1], af[kk][2], af[kk][3], bfr[kk][0], bfr[kk][1]);
 }
 // fragment -> red[slot][m][r]  (16 rows x 8 batch rows per slot)
 __device__ __forceinline__ void af_red_store(float* red, int slot, const float acc[4], int lane) {
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         // ===== P1: z1 = relu(px + ctx.W1c)   (ctx_s holds ctx_{t-1}) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, W1c_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, W1c_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         // ===== P2: z = relu(z1.W2 + b2)  (own UZ = 8 units) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, W2_s, S::KP256, 0, warp * 32, z1_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, W2_s, S::KP256, 0, warp * 32, z1_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -249,13 +253,12 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         {
             const int mt = warp & 1, ks = warp >> 1;             // 2 m-tiles x 4 k-splits of 6 k-tiles (k-tiles 0..7 = z, 8..23 = ha)
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int kt = ks * 6; kt < ks * 6 + 6; kt++) {
-                if (kt < 8) af_mma_run<UZ>(acc, Wg_s, S::KP384, mt * 16, kt * 16, z_s, kt * 16, 1, lane);
-                else af_mma_run<U>(acc, Wg_s, S::KP384, mt * 16, kt * 16, ha_s, (kt - 8) * 16, 1, lane);
-            }
+            // k-split ks takes z k-tiles [2ks, 2ks+2) and ha k-tiles [4ks, 4ks+4) (weight columns 128 + ...)
+            af_mma_run<UZ, 2>(acc, Wg_s, S::KP384, mt * 16, ks * 32, z_s, ks * 32, lane);
+            af_mma_run<U, 4>(acc, Wg_s, S::KP384, mt * 16, Z + ks * 64, ha_s, ks * 64, lane);
             af_red_store(red, warp, acc, lane);                  // slot = ks*2 + mt
             float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<UZ>(acc2, Wcz_s, S::KP128, 0, warp * 16, z_s, warp * 16, 1, lane);
+            af_mma_run<UZ, 1>(acc2, Wcz_s, S::KP128, 0, warp * 16, z_s, warp * 16, lane);
             af_red_store(red, 8 + warp, acc2, lane);
         }
         __syncthreads();
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         // ===== P4: candidate and new attention-GRU state =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, Wch_s, S::KP256, 0, warp * 32, rha_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, Wch_s, S::KP256, 0, warp * 32, rha_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         {
             const int mt = warp & 1, ks = warp >> 1;             // m-tile 0 = Wq, 1 = Wo_h; 4 k-splits of 4 k-tiles
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, mt ? Woh_s : Wq_s, S::KP256, 0, ks * 64, ha_s, ks * 64, 4, lane);
+            af_mma_run<U, 4>(acc, mt ? Woh_s : Wq_s, S::KP256, 0, ks * 64, ha_s, ks * 64, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         // ===== P8: y0 (own U columns) = yh + ctx.Wo_c + bo =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, Woc_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, Woc_s, S::KP256, 0, warp * 32, ctx_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         {
             const int mt = warp & 1, ks = warp >> 1;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<16>(acc, Wo_s, S::KP256, mt * 16, ks * 64, dy_s, ks * 64, 4, lane);
+            af_mma_run<16, 4>(acc, Wo_s, S::KP256, mt * 16, ks * 64, dy_s, ks * 64, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         // ===== Bp5: dha += gq.Wq^T; GRU cell backward (elementwise part) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, Wq_s, S::KP256, 0, warp * 32, gq_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, Wq_s, S::KP256, 0, warp * 32, gq_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         // ===== Bp6: d(r*h) (own U) = dc_pre . Wc_h^T =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, Wch_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, Wch_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -745,11 +748,11 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         // ===== Bp7: dha_prev (own U ha units) and dz (own UZ z units) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, Wgh_s, S::KP512, 0, warp * 64, dg_s, warp * 64, 4, lane);
+            af_mma_run<U, 4>(acc, Wgh_s, S::KP512, 0, warp * 64, dg_s, warp * 64, lane);
             af_red_store(red, warp, acc, lane);
             float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc2, Wgz_s, S::KP512, 0, warp * 64, dg_s, warp * 64, 4, lane);
-            af_mma_run<U>(acc2, Wcz_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, 2, lane);
+            af_mma_run<U, 4>(acc2, Wgz_s, S::KP512, 0, warp * 64, dg_s, warp * 64, lane);
+            af_mma_run<U, 2>(acc2, Wcz_s, S::KP256, 0, warp * 32, dcp_s, warp * 32, lane);
             af_red_store(red, 8 + warp, acc2, lane);
         }
         __syncthreads();
@@ -776,7 +779,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         // ===== Bp8: dz1 (own U) = dz_pre . W2^T, relu' =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<UZ>(acc, W2_s, S::KP128, 0, warp * 16, dzp_s, warp * 16, 1, lane);
+            af_mma_run<UZ, 1>(acc, W2_s, S::KP128, 0, warp * 16, dzp_s, warp * 16, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
@@ -794,7 +797,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         // ===== Bp9: grad wrt ctx_{t-1} (own U) = dz1_pre . W1c^T =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            af_mma_run<U>(acc, W1c_s, S::KP256, 0, warp * 32, dz1p_s, warp * 32, 2, lane);
+            af_mma_run<U, 2>(acc, W1c_s, S::KP256, 0, warp * 32, dz1p_s, warp * 32, lane);
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();

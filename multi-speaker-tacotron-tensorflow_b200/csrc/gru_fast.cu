@@ -66,8 +66,35 @@ __device__ __forceinline__ void gf_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 __device__ __forceinline__ void gf_mma(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// The weight slice never changes during the sequence: its mma A fragments are loaded into registers ONCE.
+template <int NK>
+__device__ __forceinline__ void gf_load_afrags(uint32_t (&af)[NK][4], const __nv_bfloat16* Wt, int KP, int m0, int k0, int lane) {
+    const uint32_t a_base = gf_smem_u32(Wt + (size_t)(m0 + (lane & 15)) * KP + k0 + (lane >> 4) * 8);
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) gf_ldmatrix_x4(a_base + (uint32_t)kk * 32, af[kk][0], af[kk][1], af[kk][2], af[kk][3]);
+}
+// acc = sum over NK k-tiles; B fragments are fetched up front, two independent accumulator chains
+template <int U, int NK>
+__device__ __forceinline__ void gf_mma_regs(float acc[4], const uint32_t (&af)[NK][4], const __nv_bfloat16* v, int k0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t b[NK][2];
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) {
+        const int ka = k0 + kk * 16 + 2 * t, kb = ka + 8;
+        b[kk][0] = *reinterpret_cast<const uint32_t*>(v + ((ka / U) * GF_R + g) * U + (ka % U));
+        b[kk][1] = *reinterpret_cast<const uint32_t*>(v + ((kb / U) * GF_R + g) * U + (kb % U));
+    }
+    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) {
+        if (kk & 1) gf_mma(acc2, af[kk][0], af[kk][1], af[kk][2], af[kk][3], b[kk][0], b[kk][1]);
+        else gf_mma(acc, af[kk][0], af[kk][1], af[kk][2], af[kk][3], b[kk][0], b[kk][1]);
+    }
+    acc[0] += acc2[0]; acc[1] += acc2[1]; acc[2] += acc2[2]; acc[3] += acc2[3];
 }
 __device__ __forceinline__ float gf_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gf_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -99,6 +126,9 @@ struct GfCfg {
     static constexpr size_t smem_bytes = w_bytes + (size_t)3 * GF_R * H * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
                                          4096 /*red*/ + 64 /*barriers*/ + 256;
 };
+
+__device__ long long g_gf_prof[16];
+#define GF_T(i) do { if (prof) { long long _c = clock64(); pacc[i] += _c - plast; plast = _c; } } while (0)
 
 template <int H>
 __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a) {
@@ -162,7 +192,12 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     constexpr int MT_G = GC / 16, KS_G = 8 / MT_G, NK_G = H / 16 / KS_G;
     constexpr int MT_C = U / 16, KS_C = 8 / MT_C, NK_C = H / 16 / KS_C;
     const int g4 = lane >> 2, t4 = lane & 3;
+    uint32_t afG[NK_G][4], afC[NK_C][4];
+    gf_load_afrags<NK_G>(afG, Wg_s, KP, (warp % MT_G) * 16, (warp / MT_G) * NK_G * 16, lane);
+    gf_load_afrags<NK_C>(afC, Wc_s, KP, (warp % MT_C) * 16, (warp / MT_C) * NK_C * 16, lane);
 
+    const bool prof = (blockIdx.x == 0 && tid == 0);
+    long long pacc[10] = {0,0,0,0,0,0,0,0,0,0}; long long plast = clock64();
     float gr = 0.f, gu = 0.f, gc = 0.f;
     auto load_gx = [&](int s) {
         if (act && s < L) {
@@ -179,16 +214,19 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         const float cgr = gr, cgu = gu, cgc = gc;
         if (tid == 0) { gf_mbar_expect_tx(bar_rh, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h, GF_C * Cfg::BLK_BYTES); }
         load_gx(s + 1);                                          // prefetch next step's x-side pre-activations
+        GF_T(0);
         // ---- gate phase ----
         {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4];
             const int mt = warp % MT_G, ks = warp / MT_G;
-            gf_mma_slice<U, KP>(acc, Wg_s, mt * 16, hb_s, ks * NK_G * 16, NK_G, lane);
+            gf_mma_regs<U, NK_G>(acc, afG, hb_s, ks * NK_G * 16, lane);
             float* rp = red + ks * (GC * R);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
         }
+        GF_T(1);
         __syncthreads();
+        GF_T(2);
         float rg = 0.f, ug = 0.f;
         if (act) {
             float sr = cgr, su = cgu;
@@ -197,20 +235,24 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
             rg = gf_sigmoid(sr); ug = gf_sigmoid(su);
             stage_rh[r * U + i] = __float2bfloat16(rg * h_own);
         }
+        GF_T(3);
 #if GF_USE_STASYNC
         __syncthreads();
+        GF_T(4);
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_rh, rhb_s + rank * R * U, bar_rh, tid);
+        GF_T(5);
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid < GF_C) gf_push(stage_rh, rhb_s + rank * R * U, bar_rh, Cfg::BLK_BYTES, tid);
 #endif
         gf_mbar_wait(bar_rh, par);
+        GF_T(6);
         // ---- candidate phase ----
         {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4];
             const int mt = warp % MT_C, ks = warp / MT_C;
-            gf_mma_slice<U, KP>(acc, Wc_s, mt * 16, rhb_s, ks * NK_C * 16, NK_C, lane);
+            gf_mma_regs<U, NK_C>(acc, afC, rhb_s, ks * NK_C * 16, lane);
             float* rp = red + ks * (U * R);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
@@ -244,7 +286,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         if (tid < GF_C) gf_push(stage_h, hb_s + rank * R * U, bar_h, Cfg::BLK_BYTES, tid);
 #endif
         gf_mbar_wait(bar_h, par);
+        GF_T(7);
     }
+    if (prof) { for (int q = 0; q < 10; q++) g_gf_prof[q] = pacc[q]; g_gf_prof[10] = Lmax; }
     if (act && a.hfinal && n < a.N) a.hfinal[(long long)n * a.ndir * H + d * H + unit] = h_own;
     cluster.sync();      // no CTA may exit while a peer's copy into it could still be in flight
 }
@@ -305,6 +349,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     constexpr int MT = U / 16, KS = 8 / MT;          // output tiles (own units) and k-splits over the 8 warps
     constexpr int NK_C = H / 16 / KS, NK_G = 2 * H / 16 / KS;
     const int g4 = lane >> 2, t4 = lane & 3;
+    uint32_t afC[NK_C][4], afG[NK_G][4];
+    gf_load_afrags<NK_C>(afC, WcT_s, KP, (warp % MT) * 16, (warp / MT) * NK_C * 16, lane);
+    gf_load_afrags<NK_G>(afG, WgT_s, KP2, (warp % MT) * 16, (warp / MT) * NK_G * 16, lane);
 
     float rg = 0.f, ug = 0.f, cc = 0.f, hp = 0.f, dout = 0.f;
     auto load_step = [&](int s) {
@@ -342,9 +389,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         gf_mbar_wait(bar_c, par);
         // d(r*h)[own units] = sum_cu dc_pre[cu] * Wc[unit][cu]
         {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4];
             const int mt = warp % MT, ks = warp / MT;
-            gf_mma_slice<U, KP>(acc, WcT_s, mt * 16, dcp_s, ks * NK_C * 16, NK_C, lane);
+            gf_mma_regs<U, NK_C>(acc, afC, dcp_s, ks * NK_C * 16, lane);
             float* rp = red + ks * (U * R);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
@@ -371,9 +418,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         gf_mbar_wait(bar_g, par);
         // dh_prev += sum_gc [dr_pre;du_pre][gc] * Wg[unit][gc]      (dg_s is blocked [2C][R][U]: k = gc, K = 2H)
         {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4];
             const int mt = warp % MT, ks = warp / MT;
-            gf_mma_slice<U, KP2>(acc, WgT_s, mt * 16, dg_s, ks * NK_G * 16, NK_G, lane);
+            gf_mma_regs<U, NK_G>(acc, afG, dg_s, ks * NK_G * 16, lane);
             float* rp = red + ks * (U * R);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
@@ -425,4 +472,8 @@ int launch_gru_fast_bwd(const GruArgs& a, cudaStream_t s) {
     return a.H == 128 ? launch_gru_fast_t<128>(a, true, s) : launch_gru_fast_t<256>(a, true, s);
 }
 
+int gf_debug_prof(long long out[16]) { TACO_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_gf_prof, sizeof(long long) * 16)); return TACO_OK; }
+
 }  // namespace taco
+
+extern "C" int taco_debug_gru_prof(long long out[16]) { return taco::gf_debug_prof(out); }
