@@ -27,6 +27,8 @@ UNIT = "mel-frames/s"
 CFG = dict(N=32, T_in=128, T_out=800, num_mels=80, num_freq=1025, r=5)
 # algorithmic HBM bytes of one training step per GPU (targets + params fwd/bwd + grads + clip/Adam)
 ALGO_BYTES_PER_STEP = 486.6e6
+# algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
+ALGO_FLOPS_PER_STEP = 784.8e9
 
 
 def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
@@ -153,6 +155,17 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     sc = eng.scalars()
 
+    # ---- roofline leg: per-class device time of the dominant kernels, CUDA events on the launching stream (outside the timed region) ----
+    import ctypes as C
+    prof_ms = (C.c_double * 4)(); prof_n = (C.c_int64 * 4)()
+    PROF_STEPS = 3
+    eng.lib.taco_profile(1, None, None)
+    for _ in range(PROF_STEPS):
+        eng.train_step(dev, allreduce=allreduce)
+    eng.lib.taco_profile(0, prof_ms, prof_n)
+    gemm_ms = prof_ms[0] / PROF_STEPS
+    barrier()
+
     # ---- end to end through the public API: pinned host inputs -> device every step, loss read back every step ----
     stream_copy = torch.cuda.Stream(device=eng.dev)
     bufs = [{k: torch.empty_like(v, device=eng.dev) for k, v in host.items()} for _ in range(2)]
@@ -203,9 +216,18 @@ def run_ours(args):
                     "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream) + loss read-back each step"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                         "traffic": None, "peak_source": which,
-                         "note": "whole-step algorithmic bytes (486.6 MB, SURVEY.md 8d) / step time; the step is bound by serial recurrence latency, see DESIGN.md"},
+            # dominant kernel class by device time: the tcgen05 GEMM (all GEMM-shaped work of the step)
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed; fp32 SIMT in fp32 mode)",
+                         "achieved": ALGO_FLOPS_PER_STEP / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                         "unit": "TFLOP/s", "frac": ALGO_FLOPS_PER_STEP / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                         "traffic": None, "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
+                         "launches_per_step": int(prof_n[0] // PROF_STEPS), "ms_per_step": gemm_ms,
+                         "algorithmic_flops_per_step": ALGO_FLOPS_PER_STEP,
+                         "note": "algorithmic FLOPs of the step (784.8 GFLOP, SURVEY.md 8d) / summed GEMM device time per step, CUDA events around every GEMM launch"},
+            "recurrence_ms_per_step": {"gru_fwd_bwd": prof_ms[1] / PROF_STEPS, "attention_fwd_bwd": prof_ms[2] / PROF_STEPS,
+                                       "note": "serial chains: 2 656 dependent recurrence steps per training step (latency bound)"},
+            "roofline_step_hbm": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                                  "note": "whole-step algorithmic bytes (486.6 MB, SURVEY.md 8d) / step time"},
             "loss": sc["loss"],
         }
         if args.cpu_baseline:
@@ -243,6 +265,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use all host cores, so undo that BEFORE torch is imported
+    ncpu = str(os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = ncpu
+    os.environ["MKL_NUM_THREADS"] = ncpu
     steps = max(1, min(args.steps, 3))
     base = cpu_baseline(sample_steps=steps)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,

@@ -179,6 +179,10 @@ int taco_gl_inv_spectrogram(taco_gl g, const float* linear_spec, const float* in
                             int32_t n_iters, float power, float min_level_db, float ref_level_db,
                             float preemphasis, float* wav_out, void* ws, void* stream);
 
+/* Per-class device timing with CUDA events on the launching stream (bench.py's roofline leg).  enable=1 starts collecting;
+ * enable=0 stops, synchronises the device and returns totals per class: 0 GEMMs, 1 GRU recurrences, 2 attention recurrences. */
+int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]);
+
 /* ---- operator-level entry points (unit parity tests; same kernels the model uses) ---- */
 typedef struct taco_gemm_desc {
     const void* A; const void* B; float* C;

@@ -107,6 +107,48 @@ __device__ void af_load_cols(bf16* dst, int KP, const float* W, long long ld, in
     }
 }
 
+__device__ long long g_af_prof[40];
+#define AF_T(i) do { if (prof) { long long _c = clock64(); pacc[i] += _c - plast; plast = _c; } } while (0)
+
+// Monotonic attention forward for one row by one warp, lane owns the CH contiguous positions [lane*CH, lane*CH+CH):
+// p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1))   (in place in ar_)
+template <int CH>
+__device__ __forceinline__ void af_mono_scan_fwd(const float* e_s, const int* eoff, float* ar_, int lane, int Ti) {
+    const int j0 = lane * CH;
+    float pv[CH], lv[CH], av[CH], wv[CH], cpv[CH];
+    float ls = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        const bool ok = j0 + k < Ti;
+        const float pk = af_sigmoid(ok ? e_s[eoff[k]] : 0.f);
+        av[k] = ok ? ar_[j0 + k] : 0.f;
+        pv[k] = ok ? pk : 0.f;
+        lv[k] = ok ? __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)) : 0.f;
+        ls += lv[k];
+    }
+    float run = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+    run -= ls;
+    float ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        cpv[k] = __expf(run);
+        run += lv[k];
+        wv[k] = __fdividef(av[k], fminf(fmaxf(cpv[k], 1e-10f), 1.f));
+        ws += wv[k];
+    }
+    float run2 = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+    run2 -= ws;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        run2 += wv[k];
+        if (j0 + k < Ti) ar_[j0 + k] = pv[k] * cpv[k] * run2;
+    }
+}
+
 struct AfFwdSmem {
     // bf16 weight slices (A operands, [rows][K+8])
     static constexpr int KP256 = 264, KP384 = 392, KP128 = 136;
@@ -130,6 +172,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     constexpr int R = AF_R, U = AF_U, UZ = AF_UZ, E = AF_E, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
     const int Ti = a.Ti, Td = a.Td;
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    const int TipP = Tip + 4;                 // row pitch of the alignment rows (bank-conflict padding)
+    const int MRS = Ti * AF_U + 16;           // row pitch (elements) of the per-row memory slice
     using S = AfFwdSmem;
 
     extern __shared__ __align__(128) uint8_t sm[];
@@ -139,7 +183,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     bf16* Woh_s = reinterpret_cast<bf16*>(sm + S::Woh); bf16* Woc_s = reinterpret_cast<bf16*>(sm + S::Woc);
     uint8_t* p = sm + S::w_end;
     bf16* keys_s = reinterpret_cast<bf16*>(p); p += (size_t)R * TJ * A * 2;          // [R][TJ][A]   own memory positions
-    bf16* mem_s = reinterpret_cast<bf16*>(p);  p += (size_t)R * Ti * U * 2;          // [R][Ti][U]   own context units
+    bf16* mem_s = reinterpret_cast<bf16*>(p);  p += (size_t)R * MRS * 2;             // [R][Ti][U] (+pad)   own context units
     p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
     bf16* ctx_s = reinterpret_cast<bf16*>(p); p += R * E * 2;                        // blocked [C][R][U]
     bf16* z1_s = reinterpret_cast<bf16*>(p);  p += R * Z1 * 2;
@@ -148,9 +192,9 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     bf16* rha_s = reinterpret_cast<bf16*>(p); p += R * HA * 2;
     float* q_s = reinterpret_cast<float*>(p); p += R * A * 4;                        // fp32 blocked [C][R][U]
     float* e_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;              // fp32 blocked [C][R][TJ]
-    float* a_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;              // [R][Tip]
-    float* p_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;
-    float* cp_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;
+    float* a_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;             // [R][Tip+4]
+    float* p_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
+    float* cp_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
     float* red = reinterpret_cast<float*>(p); p += 16 * 128 * 4;                     // 16 slots of [16][8]
     float* v_s = reinterpret_cast<float*>(p); p += A * 4;
     uint8_t* stage = p; p += 1024;
@@ -173,7 +217,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     }
     for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
         const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
-        mem_s[idx] = __float2bfloat16(n < a.N ? a.memory[((long long)n * Ti + j) * E + rank * U + i] : 0.f);
+        mem_s[(size_t)r * MRS + j * U + i] = __float2bfloat16(n < a.N ? a.memory[((long long)n * Ti + j) * E + rank * U + i] : 0.f);
     }
     for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
     for (int idx = tid; idx < R * E; idx += AF_NT) ctx_s[idx] = __float2bfloat16(0.f);
@@ -181,7 +225,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
         ha_s[idx] = __float2bfloat16((a.ha0 && n < a.N) ? a.ha0[(long long)n * HA + blk * U + i] : 0.f);
     }
-    for (int idx = tid; idx < R * Tip; idx += AF_NT) a_s[idx] = (a.att_type == TACO_ATT_BAH_MON && (idx % Tip) == 0) ? 1.f : 0.f;
+    for (int idx = tid; idx < R * TipP; idx += AF_NT) a_s[idx] = (a.att_type == TACO_ATT_BAH_MON && (idx % TipP) == 0) ? 1.f : 0.f;
     if (tid == 0) {
         for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,9 +239,22 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     const int unit = rank * U + ai;
     float ha_own = (aok && a.ha0) ? a.ha0[(long long)an * HA + unit] : 0.f;
     float px_next = aok ? __ldg(a.px + ((long long)an * Td + 0) * Z1 + unit) : 0.f;
+    const float bg_r = act ? __ldg(a.bg + unit) : 0.f, bg_u = act ? __ldg(a.bg + HA + unit) : 0.f;
+    const float bc_own = act ? __ldg(a.bc + unit) : 0.f, bo_own = act ? __ldg(a.bo + unit) : 0.f;
+    const float b2_own = (tid < UZ * R) ? __ldg(a.b2 + rank * UZ + (tid % UZ)) : 0.f;
+    float ctx_prev = 0.f;                     // fp32 context of the previous step (own unit), for the W1c-gradient stash
     __syncthreads();
     cl.sync();
 
+    const bool prof = (blockIdx.x == 0 && tid == 0);
+    long long pacc[20]; for (int q = 0; q < 20; q++) pacc[q] = 0; long long plast = clock64();
+    // per-lane constants of the alignment scan (warp r = row r, lane owns the contiguous chunk [lane*CH, lane*CH+CH))
+    constexpr int CHM = 8;
+    const int CH = (Tip + 31) / 32;
+    int eoff[CHM];
+#pragma unroll
+    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = ((j / TJ) * R + warp) * TJ + (j % TJ); }
+    const bool writer = (rank == (warp % AF_C)) && (grp * R + warp < a.N);     // this warp stores row `warp`'s alignments / stash
     for (int t = 0; t < Td; t++) {
         const uint32_t par = t & 1;
         const long long row = (long long)an * Td + t;
@@ -215,21 +272,20 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
+        float z1v = 0.f;
         if (act) {
-            float v = 0.f;
-            if (aok) {
-                v = fmaxf(af_red_sum(red, 0, 8, 1, ai, ar) + px_cur, 0.f);
-                if (a.s_z1) a.s_z1[row * Z1 + unit] = v;
-            }
-            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(v);
-        }
-        if (a.s_ctxin && aok) {
-            // context consumed by this step (for the hoisted W1c gradient); ctx_s is bf16-rounded, the fp32 value sits in s_ctx[t-1]
-            a.s_ctxin[row * E + unit] = (t == 0) ? 0.f : a.s_ctx[(row - 1) * E + unit];
+            if (aok) z1v = fmaxf(af_red_sum(red, 0, 8, 1, ai, ar) + px_cur, 0.f);
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(z1v);
         }
         __syncthreads();
         af_push(stage, z1_s + rank * R * U, b_z1, R * U * 2, tid);
+        if (aok && a.s_z1) {       // stash stores ride in the shadow of the exchange
+            a.s_z1[row * Z1 + unit] = z1v;
+            a.s_ctxin[row * E + unit] = ctx_prev;
+        }
+        AF_T(0);
         af_wait(b_z1, par);
+        AF_T(1);
         // ===== P2: z = relu(z1.W2 + b2)  (own UZ = 8 units) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -237,21 +293,21 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
+        float zv = 0.f;
+        const int zi = tid % UZ, zr = tid / UZ, zn = grp * R + zr;
         if (tid < UZ * R) {
-            const int i = tid % UZ, r = tid / UZ, n = grp * R + r;
-            float v = 0.f;
-            if (n < a.N) {
-                v = fmaxf(af_red_sum(red, 0, 8, 1, i, r) + __ldg(a.b2 + rank * UZ + i), 0.f);
-                if (a.s_z) a.s_z[((long long)n * Td + t) * Z + rank * UZ + i] = v;
-            }
-            reinterpret_cast<bf16*>(stage)[r * UZ + i] = __float2bfloat16(v);
+            if (zn < a.N) zv = fmaxf(af_red_sum(red, 0, 8, 1, zi, zr) + b2_own, 0.f);
+            reinterpret_cast<bf16*>(stage)[zr * UZ + zi] = __float2bfloat16(zv);
         }
         __syncthreads();
         af_push(stage, z_s + rank * R * UZ, b_z, R * UZ * 2, tid);
+        if (tid < UZ * R && zn < a.N && a.s_z) a.s_z[((long long)zn * Td + t) * Z + rank * UZ + zi] = zv;
+        AF_T(2);
         af_wait(b_z, par);
+        AF_T(3);
         // ===== P3: gates (own 2U columns: r | u) over [z ; ha], and the z part of the candidate =====
         {
-            const int mt = warp & 1, ks = warp >> 1;             // 2 m-tiles x 4 k-splits of 6 k-tiles (k-tiles 0..7 = z, 8..23 = ha)
+            const int mt = warp & 1, ks = warp >> 1;             // 2 m-tiles x 4 k-splits
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             // k-split ks takes z k-tiles [2ks, 2ks+2) and ha k-tiles [4ks, 4ks+4) (weight columns 128 + ...)
             af_mma_run<UZ, 2>(acc, Wg_s, S::KP384, mt * 16, ks * 32, z_s, ks * 32, lane);
@@ -264,15 +320,17 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         __syncthreads();
         float rg = 0.f, ug = 0.f, cz = 0.f;
         if (act) {
-            const float sr = af_red_sum(red, 0, 4, 2, ai, ar) + __ldg(a.bg + unit);
-            const float su = af_red_sum(red, 1, 4, 2, ai, ar) + __ldg(a.bg + HA + unit);
+            const float sr = af_red_sum(red, 0, 4, 2, ai, ar) + bg_r;
+            const float su = af_red_sum(red, 1, 4, 2, ai, ar) + bg_u;
             cz = af_red_sum(red, 8, 8, 1, ai, ar);
             rg = af_sigmoid(sr); ug = af_sigmoid(su);
             reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(rg * ha_own);
         }
         __syncthreads();
         af_push(stage, rha_s + rank * R * U, b_rha, R * U * 2, tid);
+        AF_T(4);
         af_wait(b_rha, par);
+        AF_T(5);
         // ===== P4: candidate and new attention-GRU state =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -280,19 +338,22 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
+        float cc = 0.f, hprev = ha_own;
         if (act) {
-            const float c = af_tanh(af_red_sum(red, 0, 8, 1, ai, ar) + cz + __ldg(a.bc + unit));
-            const float hn = ug * ha_own + (1.f - ug) * c;
-            if (aok && a.s_r) {
-                const long long o = row * HA + unit;
-                a.s_r[o] = rg; a.s_u[o] = ug; a.s_c[o] = c; a.s_haprev[o] = ha_own; a.s_ha[o] = hn;
-            }
+            cc = af_tanh(af_red_sum(red, 0, 8, 1, ai, ar) + cz + bc_own);
+            const float hn = ug * ha_own + (1.f - ug) * cc;
             ha_own = aok ? hn : 0.f;
             reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(ha_own);
         }
         __syncthreads();
         af_push(stage, ha_s + rank * R * U, b_ha, R * U * 2, tid);
+        if (aok && a.s_r) {
+            const long long o = row * HA + unit;
+            a.s_r[o] = rg; a.s_u[o] = ug; a.s_c[o] = cc; a.s_haprev[o] = hprev; a.s_ha[o] = ha_own;
+        }
+        AF_T(6);
         af_wait(b_ha, par);
+        AF_T(7);
         // ===== P5: query (own U columns) and the ha part of the concat projection (own U columns) =====
         {
             const int mt = warp & 1, ks = warp >> 1;             // m-tile 0 = Wq, 1 = Wo_h; 4 k-splits of 4 k-tiles
@@ -301,50 +362,106 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
-        float yh = 0.f;
+        float yh = 0.f, qv = 0.f;
         if (act) {
-            const float q = af_red_sum(red, 0, 4, 2, ai, ar);
+            qv = af_red_sum(red, 0, 4, 2, ai, ar);
             yh = af_red_sum(red, 1, 4, 2, ai, ar);
-            if (aok && a.s_q) a.s_q[row * A + unit] = q;
-            reinterpret_cast<float*>(stage)[ar * U + ai] = q;
+            reinterpret_cast<float*>(stage)[ar * U + ai] = qv;
         }
         __syncthreads();
         af_push(stage, q_s + rank * R * U, b_q, R * U * 4, tid);
+        if (aok && a.s_q) a.s_q[row * A + unit] = qv;
+        AF_T(8);
         af_wait(b_q, par);
-        // ===== P6: scores of the own TJ memory positions: e[r][j] = sum_u v_u tanh(keys[r,j,u] + q[r,u]) + b =====
-        for (int pr = warp; pr < R * TJ; pr += AF_NT / 32) {
-            const int r = pr % R, jj = pr / R;
-            const uint4 kk = *reinterpret_cast<const uint4*>(keys_s + ((size_t)(r * TJ + jj)) * A + lane * 8);
+        AF_T(9);
+        // ===== P6: scores of the own TJ memory positions (warp r = row r): e[r][j] = sum_u v_u tanh(keys[r,j,u] + q[r,u]) + b =====
+        {
+            const int r = warp;
             const float* qp = q_s + ((lane >> 1) * R + r) * U + (lane & 1) * 8;
             const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
             const float4 v0 = *reinterpret_cast<const float4*>(v_s + lane * 8), v1 = *reinterpret_cast<const float4*>(v_s + lane * 8 + 4);
-            const __nv_bfloat162* kb = reinterpret_cast<const __nv_bfloat162*>(&kk);
-            const float2 k0 = __bfloat1622float2(kb[0]), k1 = __bfloat1622float2(kb[1]), k2 = __bfloat1622float2(kb[2]), k3 = __bfloat1622float2(kb[3]);
-            float s = v0.x * af_tanh(k0.x + q0.x);
-            s = fmaf(v0.y, af_tanh(k0.y + q0.y), s); s = fmaf(v0.z, af_tanh(k1.x + q0.z), s); s = fmaf(v0.w, af_tanh(k1.y + q0.w), s);
-            s = fmaf(v1.x, af_tanh(k2.x + q1.x), s); s = fmaf(v1.y, af_tanh(k2.y + q1.y), s);
-            s = fmaf(v1.z, af_tanh(k3.x + q1.z), s); s = fmaf(v1.w, af_tanh(k3.y + q1.w), s);
-            s = warp_sum(s);
-            if (lane == 0) reinterpret_cast<float*>(stage)[r * TJ + jj] = s + score_bias;
+            for (int jb = 0; jb < TJ; jb += 4) {
+                float sc4[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; u4++) {                 // four independent positions in flight
+                    const int jj = min(jb + u4, TJ - 1);
+                    const uint4 kk = *reinterpret_cast<const uint4*>(keys_s + ((size_t)(r * TJ + jj)) * A + lane * 8);
+                    const __nv_bfloat162* kb = reinterpret_cast<const __nv_bfloat162*>(&kk);
+                    const float2 k0 = __bfloat1622float2(kb[0]), k1 = __bfloat1622float2(kb[1]), k2 = __bfloat1622float2(kb[2]), k3 = __bfloat1622float2(kb[3]);
+                    float s0 = v0.x * af_tanh(k0.x + q0.x), s1 = v0.y * af_tanh(k0.y + q0.y);
+                    s0 = fmaf(v0.z, af_tanh(k1.x + q0.z), s0); s1 = fmaf(v0.w, af_tanh(k1.y + q0.w), s1);
+                    s0 = fmaf(v1.x, af_tanh(k2.x + q1.x), s0); s1 = fmaf(v1.y, af_tanh(k2.y + q1.y), s1);
+                    s0 = fmaf(v1.z, af_tanh(k3.x + q1.z), s0); s1 = fmaf(v1.w, af_tanh(k3.y + q1.w), s1);
+                    sc4[u4] = s0 + s1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; u4++) sc4[u4] += __shfl_xor_sync(0xffffffffu, sc4[u4], o);
+                }
+                const float mine = lane == 0 ? sc4[0] : (lane == 1 ? sc4[1] : (lane == 2 ? sc4[2] : sc4[3]));
+                if (lane < 4 && jb + lane < TJ) reinterpret_cast<float*>(stage)[r * TJ + jb + lane] = mine + score_bias;
+            }
         }
         __syncthreads();
         af_push(stage, e_s + rank * R * TJ, b_e, R * TJ * 4, tid);
+        AF_T(10);
         af_wait(b_e, par);
+        AF_T(11);
         // ===== P7: alignments (every CTA redundantly; warp r = row r), then the own U context units =====
         {
             const int r = warp, n = grp * R + r;
-            const int CH = (Tip + 31) / 32;
-            const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
-            float* ar_ = a_s + r * Tip; float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip;
-            auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+            float* ar_ = a_s + r * TipP;
             if (a.manual) {
                 for (int j = lane; j < Ti; j += 32) ar_[j] = (n < a.N) ? a.manual[((long long)n * Td + t) * Ti + j] : 0.f;
+            } else if (a.att_type == TACO_ATT_BAH_MON && CH == 4) {
+                af_mono_scan_fwd<4>(e_s, eoff, ar_, lane, Ti);
+            } else if (a.att_type == TACO_ATT_BAH_MON && CH <= CHM) {
+                // p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1)), fully unrolled
+                const int j0 = lane * CH;
+                float pv[CHM], lv[CHM], av[CHM];
+                float ls = 0.f;
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    const bool ok = (k < CH) && (j0 + k < Ti);
+                    const float ev = ok ? e_s[eoff[k]] : 0.f;
+                    av[k] = ok ? ar_[j0 + k] : 0.f;
+                    const float pk = af_sigmoid(ev);
+                    pv[k] = ok ? pk : 0.f;
+                    lv[k] = ok ? __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)) : 0.f;
+                    ls += lv[k];
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float wv[CHM], cpv[CHM];
+                float ws = 0.f;
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    cpv[k] = __expf(run);
+                    run += lv[k];
+                    wv[k] = __fdividef(av[k], fminf(fmaxf(cpv[k], 1e-10f), 1.f));
+                    ws += wv[k];
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    run2 += wv[k];
+                    if ((k < CH) && (j0 + k < Ti)) ar_[j0 + k] = pv[k] * cpv[k] * run2;
+                }
             } else if (a.att_type == TACO_ATT_BAH_MON) {
+                const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
+                float* pr_ = p_s + r * TipP; float* cr_ = cp_s + r * TipP;
+                auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
                 float ls = 0.f;
                 for (int j = j0; j < j1; j++) {
-                    const float pv = af_sigmoid(E_(j));
-                    pr_[j] = pv;
-                    ls += __logf(fminf(fmaxf(1.f - pv, FLT_MIN), 1.f));
+                    const float pk = af_sigmoid(E_(j));
+                    pr_[j] = pk;
+                    ls += __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f));
                 }
                 float run = ls;
 #pragma unroll
@@ -366,6 +483,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
                     ar_[j] = pr_[j] * cr_[j] * run2;
                 }
             } else {
+                float* pr_ = p_s + r * TipP;
+                auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
                 float mx = -INFINITY;
                 for (int j = lane; j < Ti; j += 32) mx = fmaxf(mx, E_(j));
 #pragma unroll
@@ -375,44 +494,48 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
                 smv = warp_sum(smv);
                 for (int j = lane; j < Ti; j += 32) ar_[j] = __fdividef(pr_[j], smv);
             }
-            __syncwarp();
-            if (rank == (r % AF_C) && n < a.N) {                 // spread the alignment/stash writes over the cluster
-                for (int j = lane; j < Ti; j += 32) {
-                    const float av = ar_[j];
-                    a.align[((long long)n * Ti + j) * Td + t] = av;
-                    if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = E_(j); }
-                }
-            }
         }
         __syncthreads();
         {
             // ctx[r][own units]: thread = (j-quarter, row, unit pair); partials reduced through `red`
             const int jq = tid >> 6, r = (tid >> 3) & 7, ip = tid & 7;
             const int jn = (Ti + 3) / 4, ja = jq * jn, jb = min(Ti, ja + jn);
-            float c0 = 0.f, c1 = 0.f;
-            const float* arow = a_s + r * Tip;
-            const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(mem_s + (size_t)r * Ti * U) + ip;
-#pragma unroll 4
-            for (int j = ja; j < jb; j++) {
-                const float2 m2 = __bfloat1622float2(mp[(size_t)j * (U / 2)]);
-                const float av = arow[j];
-                c0 = fmaf(av, m2.x, c0); c1 = fmaf(av, m2.y, c1);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            const float* arow = a_s + r * TipP;
+            const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(mem_s + (size_t)r * MRS) + ip;
+            int j = ja;
+            for (; j + 1 < jb; j += 2) {
+                const float2 m2 = __bfloat1622float2(mp[(size_t)j * (U / 2)]), m3 = __bfloat1622float2(mp[(size_t)(j + 1) * (U / 2)]);
+                const float av0 = arow[j], av1 = arow[j + 1];
+                c0 = fmaf(av0, m2.x, c0); c1 = fmaf(av0, m2.y, c1); c2 = fmaf(av1, m3.x, c2); c3 = fmaf(av1, m3.y, c3);
             }
-            red[jq * 128 + (2 * ip) * 8 + r] = c0;
-            red[jq * 128 + (2 * ip + 1) * 8 + r] = c1;
+            if (j < jb) { const float2 m2 = __bfloat1622float2(mp[(size_t)j * (U / 2)]); c0 = fmaf(arow[j], m2.x, c0); c1 = fmaf(arow[j], m2.y, c1); }
+            red[jq * 128 + (2 * ip) * 8 + r] = c0 + c2;
+            red[jq * 128 + (2 * ip + 1) * 8 + r] = c1 + c3;
         }
         __syncthreads();
+        float cx = 0.f;
         if (act) {
-            float cx = 0.f;
-            if (aok) {
-                cx = af_red_sum(red, 0, 4, 1, ai, ar);
-                if (a.s_ctx) a.s_ctx[row * E + unit] = cx;
-            }
+            if (aok) cx = af_red_sum(red, 0, 4, 1, ai, ar);
             reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(cx);
         }
         __syncthreads();
         af_push(stage, ctx_s + rank * R * U, b_ctx, R * U * 2, tid);
+        // stores in the shadow of the exchange: context stash, alignments, scores
+        ctx_prev = cx;
+        if (aok && a.s_ctx) a.s_ctx[row * E + unit] = cx;
+        if (writer) {
+            const int r = warp, n = grp * R + r;
+            const float* ar_ = a_s + r * TipP;
+            for (int j = lane; j < Ti; j += 32) {
+                const float av = ar_[j];
+                a.align[((long long)n * Ti + j) * Td + t] = av;
+                if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; }
+            }
+        }
+        AF_T(12);
         af_wait(b_ctx, par);
+        AF_T(13);
         // ===== P8: y0 (own U columns) = yh + ctx.Wo_c + bo =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -420,9 +543,11 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
-        if (aok) a.y0[row * Y + unit] = yh + af_red_sum(red, 0, 8, 1, ai, ar) + __ldg(a.bo + unit);
+        if (aok) a.y0[row * Y + unit] = yh + af_red_sum(red, 0, 8, 1, ai, ar) + bo_own;
         __syncthreads();     // `red` is rewritten by the next step's P1
+        AF_T(14);
     }
+    if (prof) { for (int q = 0; q < 20; q++) g_af_prof[q] = pacc[q]; }
     if (a.ha_final && aok) a.ha_final[(long long)an * HA + unit] = ha_own;
     cl.sync();
 }
@@ -449,6 +574,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     constexpr int R = AF_R, U = AF_U, UZ = AF_UZ, E = AF_E, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
     const int Ti = a.Ti, Td = a.Td;
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
+    const int TipP = Tip + 4;                 // row pitch of ge_s (bank-conflict padding)
+    const int KRS = Ti * AF_U + 16;           // row pitch (elements) of the per-row key slice
     using S = AfBwdSmem;
 
     extern __shared__ __align__(128) uint8_t sm[];
@@ -458,7 +585,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     bf16* Wgz_s = reinterpret_cast<bf16*>(sm + S::Wgz); bf16* W2_s = reinterpret_cast<bf16*>(sm + S::W2);
     uint8_t* p = sm + S::w_end;
     bf16* memj_s = reinterpret_cast<bf16*>(p); p += (size_t)R * TJ * E * 2;          // [R][TJ][E]   own memory positions
-    bf16* keyu_s = reinterpret_cast<bf16*>(p); p += (size_t)R * Ti * U * 2;          // [R][Ti][U]   own attention units
+    bf16* keyu_s = reinterpret_cast<bf16*>(p); p += (size_t)R * KRS * 2;             // [R][Ti][U] (+pad)   own attention units
     p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
     float* dctx_s = reinterpret_cast<float*>(p); p += R * E * 4;                     // fp32 blocked [C][R][U]
     float* da_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;           // fp32 blocked [C][R][TJ]
@@ -469,7 +596,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     bf16* dz1p_s = reinterpret_cast<bf16*>(p); p += R * Z1 * 2;
     bf16* dy_s = reinterpret_cast<bf16*>(p);   p += R * Y * 2;                       // blocked [Y/16][R][16]
     float* dac_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;            // carried grad wrt a_t
-    float* ge_s = reinterpret_cast<float*>(p);  p += (size_t)R * Tip * 4;            // grad wrt scores (also scratch t1)
+    float* ge_s = reinterpret_cast<float*>(p);  p += (size_t)R * TipP * 4;           // grad wrt scores (also scratch t1)
     float* p_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;
     float* cp_s = reinterpret_cast<float*>(p);  p += (size_t)R * Tip * 4;
     float* s_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;            // (also scratch t2)
@@ -495,10 +622,11 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     }
     for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
         const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
-        keyu_s[idx] = __float2bfloat16(n < a.N ? a.keys[((long long)n * Ti + j) * A + rank * U + i] : 0.f);
+        keyu_s[(size_t)r * KRS + j * U + i] = __float2bfloat16(n < a.N ? a.keys[((long long)n * Ti + j) * A + rank * U + i] : 0.f);
     }
     for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
-    for (int idx = tid; idx < R * Tip; idx += AF_NT) { dac_s[idx] = 0.f; ge_s[idx] = 0.f; }
+    for (int idx = tid; idx < R * Tip; idx += AF_NT) dac_s[idx] = 0.f;
+    for (int idx = tid; idx < R * TipP; idx += AF_NT) ge_s[idx] = 0.f;
     if (tid == 0) {
         for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -515,6 +643,50 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     __syncthreads();
     cl.sync();
 
+    const bool prof = (blockIdx.x == 0 && tid == 0);
+    long long pacc[20]; for (int q = 0; q < 20; q++) pacc[q] = 0; long long plast = clock64();
+    // ---- per-thread constants and the one-step-ahead prefetch of everything this loop reads from global memory ----
+    constexpr int CHM = 8;
+    const int CH = (Tip + 31) / 32;
+    int eoff[CHM];
+#pragma unroll
+    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = ((j / TJ) * R + warp) * TJ + (j % TJ); }
+    const int wn = grp * R + warp;                                // batch row of this warp in the scan phases
+    const bool wok = wn < a.N;
+    const bool writer = (rank == (warp % AF_C)) && wok;
+    const bool mono_fast = (a.att_type == TACO_ATT_BAH_MON) && (CH <= CHM) && !a.manual;
+    const int zi = tid % UZ, zr = tid / UZ, zn = grp * R + zr;
+    const bool zok = (tid < UZ * R) && zn < a.N;
+    float n_rg = 0.f, n_ug = 0.f, n_cc = 0.f, n_hp = 0.f, n_z1 = 0.f, n_z = 0.f, n_q0 = 0.f, n_q1 = 0.f;
+    float n_dy[R], n_e[CHM], n_ap[CHM];
+    auto prefetch = [&](int tt) {
+        if (tt < 0) return;
+        if (aok) {
+            const long long o = ((long long)an * Td + tt) * HA + unit;
+            n_rg = a.s_r[o]; n_ug = a.s_u[o]; n_cc = a.s_c[o]; n_hp = a.s_haprev[o];
+            n_z1 = a.s_z1[((long long)an * Td + tt) * Z1 + unit];
+        }
+        if (zok) n_z = a.s_z[((long long)zn * Td + tt) * Z + rank * UZ + zi];
+        if (jn_ < a.N && !a.manual) {
+            const float* qp = a.s_q + ((long long)jn_ * Td + tt) * A + rank * U + 2 * jip;
+            n_q0 = qp[0]; n_q1 = qp[1];
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int n = grp * R + r;
+            n_dy[r] = (n < a.N) ? __ldg(a.dy0 + ((long long)n * Td + tt) * Y + tid) : 0.f;      // Y == AF_NT
+        }
+        if (mono_fast && wok) {
+#pragma unroll
+            for (int k = 0; k < CHM; k++) {
+                const int j = lane * CH + k;
+                const bool ok = (k < CH) && (j < Ti);
+                n_e[k] = ok ? a.s_e[((long long)wn * Td + tt) * Ti + j] : 0.f;
+                n_ap[k] = ok ? (tt > 0 ? a.s_a[((long long)wn * Td + (tt - 1)) * Ti + j] : (j == 0 ? 1.f : 0.f)) : 0.f;
+            }
+        }
+    };
+    prefetch(Td - 1);
     int it = 0;
     for (int t = Td - 1; t >= 0; t--, it++) {
         const uint32_t par = it & 1;
@@ -524,22 +696,13 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             af_expect(b_dcp, AF_C * R * U * 2); af_expect(b_dg, 2 * AF_C * R * U * 2); af_expect(b_dzp, AF_C * R * UZ * 2);
             af_expect(b_dz1p, AF_C * R * U * 2);
         }
-        // stash of this step (latency hidden behind Bp1-Bp4)
-        float rg = 0.f, ug = 0.f, cc = 0.f, hp = 0.f, z1v = 0.f;
-        if (aok) {
-            const long long o = row * HA + unit;
-            rg = a.s_r[o]; ug = a.s_u[o]; cc = a.s_c[o]; hp = a.s_haprev[o];
-            z1v = a.s_z1[row * Z1 + unit];
-        }
-        float q0 = 0.f, q1 = 0.f;
-        if (jn_ < a.N && !a.manual) {
-            const float* qp = a.s_q + ((long long)jn_ * Td + t) * A + rank * U + 2 * jip;
-            q0 = qp[0]; q1 = qp[1];
-        }
-        for (int idx = tid; idx < R * Y; idx += AF_NT) {
-            const int k = idx % Y, r = idx / Y, n = grp * R + r;
-            dy_s[((k >> 4) * R + r) * 16 + (k & 15)] = __float2bfloat16((n < a.N) ? __ldg(a.dy0 + ((long long)n * Td + t) * Y + k) : 0.f);
-        }
+        const float rg = n_rg, ug = n_ug, cc = n_cc, hp = n_hp, z1v = n_z1, zval = n_z, q0 = n_q0, q1 = n_q1;
+        float ev[CHM], apv[CHM];
+#pragma unroll
+        for (int k = 0; k < CHM; k++) { ev[k] = n_e[k]; apv[k] = n_ap[k]; }
+#pragma unroll
+        for (int r = 0; r < R; r++) dy_s[((tid >> 4) * R + r) * 16 + (tid & 15)] = __float2bfloat16(n_dy[r]);
+        prefetch(t - 1);                                          // next iteration's inputs are in flight during this whole step
         __syncthreads();
         // ===== Bp1: dha += dy0.Wo_h^T (own U ha units), dctx = carry + dy0.Wo_c^T (own U ctx units) =====
         {
@@ -549,62 +712,152 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
-        float dha = 0.f;
+        float dha = 0.f, dctx = 0.f;
         if (act) {
             dha = dha_carry + af_red_sum(red, 0, 4, 2, ai, ar);
-            const float dctx = aok ? dctx_carry + af_red_sum(red, 1, 4, 2, ai, ar) : 0.f;
-            if (aok) a.d_ctx[row * E + unit] = dctx;
+            dctx = aok ? dctx_carry + af_red_sum(red, 1, 4, 2, ai, ar) : 0.f;
             reinterpret_cast<float*>(stage)[ar * U + ai] = dctx;
         }
         __syncthreads();
         af_push(stage, dctx_s + rank * R * U, b_dctx, R * U * 4, tid);
+        if (aok) a.d_ctx[row * E + unit] = dctx;
+        AF_T(0);
         af_wait(b_dctx, par);
-        // ===== Bp2: da[r][own j] = sum_u dctx[r,u] memory[r,j,u] =====
-        for (int pr = warp; pr < R * TJ; pr += AF_NT / 32) {
-            const int r = pr % R, jj = pr / R;
-            const uint4 mm = *reinterpret_cast<const uint4*>(memj_s + ((size_t)(r * TJ + jj)) * E + lane * 8);
+        AF_T(1);
+        // ===== Bp2: da[r][own j] = sum_u dctx[r,u] memory[r,j,u]   (warp r = row r, four positions in flight) =====
+        {
+            const int r = warp;
             const float* dp = dctx_s + ((lane >> 1) * R + r) * U + (lane & 1) * 8;
             const float4 d0 = *reinterpret_cast<const float4*>(dp), d1 = *reinterpret_cast<const float4*>(dp + 4);
-            const __nv_bfloat162* mb = reinterpret_cast<const __nv_bfloat162*>(&mm);
-            const float2 m0 = __bfloat1622float2(mb[0]), m1 = __bfloat1622float2(mb[1]), m2 = __bfloat1622float2(mb[2]), m3 = __bfloat1622float2(mb[3]);
-            float s = d0.x * m0.x;
-            s = fmaf(d0.y, m0.y, s); s = fmaf(d0.z, m1.x, s); s = fmaf(d0.w, m1.y, s);
-            s = fmaf(d1.x, m2.x, s); s = fmaf(d1.y, m2.y, s); s = fmaf(d1.z, m3.x, s); s = fmaf(d1.w, m3.y, s);
-            s = warp_sum(s);
-            if (lane == 0) reinterpret_cast<float*>(stage)[r * TJ + jj] = s;
+            for (int jb = 0; jb < TJ; jb += 4) {
+                float sc4[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; u4++) {
+                    const int jj = min(jb + u4, TJ - 1);
+                    const uint4 mm = *reinterpret_cast<const uint4*>(memj_s + ((size_t)(r * TJ + jj)) * E + lane * 8);
+                    const __nv_bfloat162* mb = reinterpret_cast<const __nv_bfloat162*>(&mm);
+                    const float2 m0 = __bfloat1622float2(mb[0]), m1 = __bfloat1622float2(mb[1]), m2 = __bfloat1622float2(mb[2]), m3 = __bfloat1622float2(mb[3]);
+                    float s0 = d0.x * m0.x, s1 = d0.y * m0.y;
+                    s0 = fmaf(d0.z, m1.x, s0); s1 = fmaf(d0.w, m1.y, s1); s0 = fmaf(d1.x, m2.x, s0); s1 = fmaf(d1.y, m2.y, s1);
+                    s0 = fmaf(d1.z, m3.x, s0); s1 = fmaf(d1.w, m3.y, s1);
+                    sc4[u4] = s0 + s1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; u4++) sc4[u4] += __shfl_xor_sync(0xffffffffu, sc4[u4], o);
+                }
+                const float mine = lane == 0 ? sc4[0] : (lane == 1 ? sc4[1] : (lane == 2 ? sc4[2] : sc4[3]));
+                if (lane < 4 && jb + lane < TJ) reinterpret_cast<float*>(stage)[r * TJ + jb + lane] = mine;
+            }
         }
         __syncthreads();
         af_push(stage, da_s + rank * R * TJ, b_da, R * TJ * 4, tid);
+        AF_T(2);
         af_wait(b_da, par);
+        AF_T(3);
         // ===== Bp3: attention-probability backward (every CTA; warp r = row r).  SURVEY.md Appendix C =====
         {
-            const int r = warp, n = grp * R + r;
-            const int CH = (Tip + 31) / 32;
-            const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
-            float* gc = dac_s + r * Tip; float* ge = ge_s + r * Tip;
-            float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip; float* sr_ = s_s + r * Tip;
-            float* t1 = ge; float* t2 = sr_;
-            auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
-            const bool ok = n < a.N;
-            if (a.manual || !ok) {
+            const int r = warp;
+            float* gc = dac_s + r * Tip; float* ge = ge_s + r * TipP;
+            if (a.manual || !wok) {
                 for (int j = lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+            } else if (mono_fast) {
+                // forward: q=clip(1-p); L=cumsum_excl(log q); cp=exp(L); d=clip(cp,1e-10,1); w=aprev/d; s=cumsum(w); a=p*cp*s  -- all in registers
+                const int j0 = lane * CH;
+                float pv[CHM], lv[CHM], cpv[CHM], sv[CHM], gv[CHM], gsv[CHM], gLv[CHM], gpd[CHM];
+                float ls = 0.f;
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    const bool ok = (k < CH) && (j0 + k < Ti);
+                    const float pk = af_sigmoid(ev[k]);
+                    pv[k] = ok ? pk : 0.f;
+                    lv[k] = ok ? __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)) : 0.f;
+                    gv[k] = ok ? da_s[eoff[k]] + gc[j0 + k] : 0.f;       // total grad wrt a_t[j]
+                    ls += lv[k];
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float ws = 0.f, wv[CHM];
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    cpv[k] = __expf(run);
+                    run += lv[k];
+                    wv[k] = __fdividef(apv[k], fminf(fmaxf(cpv[k], 1e-10f), 1.f));
+                    ws += wv[k];
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+                float gs_loc = 0.f;
+#pragma unroll
+                for (int k = 0; k < CHM; k++) {
+                    run2 += wv[k];
+                    sv[k] = run2;
+                    gsv[k] = gv[k] * pv[k] * cpv[k];
+                    gs_loc += gsv[k];
+                }
+                float suf = gs_loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+                suf -= gs_loc;
+                float gL_loc = 0.f;
+                {
+                    float acc = suf;
+#pragma unroll
+                    for (int k = CHM - 1; k >= 0; k--) {
+                        acc += gsv[k];                                   // gw_j = sum_{i>=j} gs_i
+                        const float d = fminf(fmaxf(cpv[k], 1e-10f), 1.f);
+                        const float rd = __fdividef(1.f, d);
+                        float gcp = gv[k] * pv[k] * sv[k];
+                        if (cpv[k] >= 1e-10f && cpv[k] <= 1.f) gcp -= acc * apv[k] * rd * rd;
+                        gLv[k] = gcp * cpv[k];
+                        gL_loc += gLv[k];
+                        gpd[k] = gv[k] * cpv[k] * sv[k];
+                        if ((k < CH) && (j0 + k < Ti)) gc[j0 + k] = acc * rd;   // grad wrt a_{t-1,j}, carried to the next iteration
+                    }
+                }
+                float sufL = gL_loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_down_sync(0xffffffffu, sufL, o); if (lane + o < 32) sufL += v; }
+                sufL -= gL_loc;
+                float gb = 0.f;
+                {
+                    float acc = sufL;
+#pragma unroll
+                    for (int k = CHM - 1; k >= 0; k--) {
+                        const float omp = 1.f - pv[k];
+                        float gp = gpd[k];
+                        if (omp >= FLT_MIN && omp <= 1.f) gp -= __fdividef(acc, fminf(fmaxf(omp, FLT_MIN), 1.f));
+                        acc += gLv[k];
+                        const float gev = gp * pv[k] * omp;
+                        if ((k < CH) && (j0 + k < Ti)) { ge[j0 + k] = gev; gb += gev; }
+                    }
+                }
+                for (int j = Ti + lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
+                gb = warp_sum(gb);
+                if (rank == 0 && lane == 0) gbias_acc += gb;
             } else if (a.att_type == TACO_ATT_BAH_MON) {
+                // generic path for very long memories (T_in > 256)
+                const int n = wn;
+                const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
+                float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip; float* sr_ = s_s + r * Tip;
+                float* t1 = ge; float* t2 = sr_;
+                auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
                 const float* e_row = a.s_e + ((long long)n * Td + t) * Ti;
                 const float* ap_row = (t > 0) ? a.s_a + ((long long)n * Td + (t - 1)) * Ti : nullptr;
                 float ls = 0.f;
-                for (int j = j0; j < j1; j++) {
-                    const float pv = af_sigmoid(e_row[j]);
-                    pr_[j] = pv;
-                    ls += __logf(fminf(fmaxf(1.f - pv, FLT_MIN), 1.f));
-                }
+                for (int j = j0; j < j1; j++) { const float pk = af_sigmoid(e_row[j]); pr_[j] = pk; ls += __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)); }
                 float run = ls;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
                 run -= ls;
                 float ws = 0.f;
                 for (int j = j0; j < j1; j++) {
-                    const float cp = __expf(run);
-                    cr_[j] = cp;
+                    const float cp = __expf(run); cr_[j] = cp;
                     run += __logf(fminf(fmaxf(1.f - pr_[j], FLT_MIN), 1.f));
                     const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
                     ws += __fdividef(ap, fminf(fmaxf(cp, 1e-10f), 1.f));
@@ -618,11 +871,9 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                     const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
                     run2 += __fdividef(ap, fminf(fmaxf(cr_[j], 1e-10f), 1.f));
                     const float g = GA(j) + gc[j];
-                    gc[j] = g;                                            // total grad wrt a_t[j]
-                    sr_[j] = run2;
+                    gc[j] = g; sr_[j] = run2;
                     const float gs = g * pr_[j] * cr_[j];
-                    t1[j] = gs;
-                    gs_loc += gs;
+                    t1[j] = gs; gs_loc += gs;
                 }
                 float suf = gs_loc;
 #pragma unroll
@@ -633,17 +884,13 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                     float acc = suf;
                     for (int j = j1 - 1; j >= j0; j--) {
                         acc += t1[j];
-                        const float g = gc[j];
-                        const float pv = pr_[j], cp = cr_[j], sj = sr_[j];
+                        const float g = gc[j], pk = pr_[j], cp = cr_[j], sj = sr_[j];
                         const float ap = ap_row ? ap_row[j] : (j == 0 ? 1.f : 0.f);
                         const float d = fminf(fmaxf(cp, 1e-10f), 1.f);
-                        float gcp = g * pv * sj;
+                        float gcp = g * pk * sj;
                         if (cp >= 1e-10f && cp <= 1.f) gcp -= acc * ap / (d * d);
                         const float gL = gcp * cp;
-                        gL_loc += gL;
-                        ge[j] = g * cp * sj;                               // direct part of grad wrt p_j  (t1[j] consumed above)
-                        t2[j] = gL;                                        // (s_j consumed above)
-                        gc[j] = acc / d;                                   // grad wrt a_{t-1,j}, carried
+                        gL_loc += gL; ge[j] = g * cp * sj; t2[j] = gL; gc[j] = acc / d;
                     }
                 }
                 float sufL = gL_loc;
@@ -654,60 +901,67 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                 {
                     float acc = sufL;
                     for (int j = j1 - 1; j >= j0; j--) {
-                        const float pv = pr_[j], omp = 1.f - pv;
+                        const float pk = pr_[j], omp = 1.f - pk;
                         float gp = ge[j];
                         if (omp >= FLT_MIN && omp <= 1.f) gp -= acc / fminf(fmaxf(omp, FLT_MIN), 1.f);
                         acc += t2[j];
-                        const float gev = gp * pv * (1.f - pv);
-                        ge[j] = gev;
-                        gb += gev;
+                        const float gev = gp * pk * (1.f - pk);
+                        ge[j] = gev; gb += gev;
                     }
                 }
                 for (int j = Ti + lane; j < Tip; j += 32) { ge[j] = 0.f; gc[j] = 0.f; }
                 gb = warp_sum(gb);
                 if (rank == 0 && lane == 0) gbias_acc += gb;
             } else {
-                const float* a_row = a.s_a + ((long long)n * Td + t) * Ti;
+                auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+                const float* a_row = a.s_a + ((long long)wn * Td + t) * Ti;
                 float dot = 0.f;
                 for (int j = lane; j < Ti; j += 32) dot += a_row[j] * GA(j);
                 dot = warp_sum(dot);
                 for (int j = lane; j < Tip; j += 32) { ge[j] = (j < Ti) ? a_row[j] * (GA(j) - dot) : 0.f; gc[j] = 0.f; }
             }
-            __syncwarp();
-            if (rank == (r % AF_C) && ok && a.d_ge)
-                for (int j = lane; j < Ti; j += 32) a.d_ge[((long long)n * Td + t) * Ti + j] = ge[j];
         }
         __syncthreads();
         // ===== Bp4: gq (own U units) = v_u * sum_j ge[r][j] * (1 - tanh^2(keys[r,j,u] + q[r,u])) =====
         {
             const int jn = (Ti + 3) / 4, ja = jq * jn, jb = min(Ti, ja + jn);
-            float c0 = 0.f, c1 = 0.f;
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
             if (!a.manual) {
-                const float* ger = ge_s + jr * Tip;
-                const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(keyu_s + (size_t)jr * Ti * U) + jip;
-#pragma unroll 2
-                for (int j = ja; j < jb; j++) {
-                    const float2 k2 = __bfloat1622float2(kp[(size_t)j * (U / 2)]);
-                    const float g = ger[j];
-                    const float th0 = af_tanh(k2.x + q0), th1 = af_tanh(k2.y + q1);
-                    c0 = fmaf(g, 1.f - th0 * th0, c0); c1 = fmaf(g, 1.f - th1 * th1, c1);
+                const float* ger = ge_s + jr * TipP;
+                const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(keyu_s + (size_t)jr * KRS) + jip;
+                int j = ja;
+                for (; j + 1 < jb; j += 2) {
+                    const float2 ka = __bfloat1622float2(kp[(size_t)j * (U / 2)]), kb = __bfloat1622float2(kp[(size_t)(j + 1) * (U / 2)]);
+                    const float g0 = ger[j], g1 = ger[j + 1];
+                    const float ta = af_tanh(ka.x + q0), tb = af_tanh(ka.y + q1), tc = af_tanh(kb.x + q0), td = af_tanh(kb.y + q1);
+                    c0 = fmaf(g0, 1.f - ta * ta, c0); c1 = fmaf(g0, 1.f - tb * tb, c1);
+                    c2 = fmaf(g1, 1.f - tc * tc, c2); c3 = fmaf(g1, 1.f - td * td, c3);
+                }
+                if (j < jb) {
+                    const float2 ka = __bfloat1622float2(kp[(size_t)j * (U / 2)]);
+                    const float ta = af_tanh(ka.x + q0), tb = af_tanh(ka.y + q1);
+                    c0 = fmaf(ger[j], 1.f - ta * ta, c0); c1 = fmaf(ger[j], 1.f - tb * tb, c1);
                 }
             }
-            red[jq * 128 + (2 * jip) * 8 + jr] = c0;
-            red[jq * 128 + (2 * jip + 1) * 8 + jr] = c1;
+            red[jq * 128 + (2 * jip) * 8 + jr] = c0 + c2;
+            red[jq * 128 + (2 * jip + 1) * 8 + jr] = c1 + c3;
         }
         __syncthreads();
+        float gq = 0.f;
         if (act) {
-            float gq = 0.f;
-            if (aok) {
-                gq = af_red_sum(red, 0, 4, 1, ai, ar) * v_s[unit];
-                if (a.d_gq) a.d_gq[row * A + unit] = gq;
-            }
+            if (aok) gq = af_red_sum(red, 0, 4, 1, ai, ar) * v_s[unit];
             reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(gq);
         }
         __syncthreads();
         af_push(stage, gq_s + rank * R * U, b_gq, R * U * 2, tid);
+        if (aok && a.d_gq) a.d_gq[row * A + unit] = gq;
+        if (writer && a.d_ge) {
+            const float* ge = ge_s + warp * TipP;
+            for (int j = lane; j < Ti; j += 32) a.d_ge[((long long)wn * Td + t) * Ti + j] = ge[j];
+        }
+        AF_T(4);
         af_wait(b_gq, par);
+        AF_T(5);
         // ===== Bp5: dha += gq.Wq^T; GRU cell backward (elementwise part) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -726,7 +980,9 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         }
         __syncthreads();
         af_push(stage, dcp_s + rank * R * U, b_dcp, R * U * 2, tid);
+        AF_T(6);
         af_wait(b_dcp, par);
+        AF_T(7);
         // ===== Bp6: d(r*h) (own U) = dc_pre . Wc_h^T =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -744,7 +1000,14 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         __syncthreads();
         af_push(stage, dg_s + rank * R * U, b_dg, R * U * 2, tid);
         af_push(stage + 256, dg_s + (AF_C + rank) * R * U, b_dg, R * U * 2, tid);
+        if (aok) {
+            float* g = a.d_G + row * 3 * HA + unit;
+            g[0] = dr_pre; g[HA] = du_pre; g[2 * HA] = dc_pre;
+            a.s_r[row * HA + unit] = rg * hp;                   // operand of the candidate-weight gradient GEMM
+        }
+        AF_T(8);
         af_wait(b_dg, par);
+        AF_T(9);
         // ===== Bp7: dha_prev (own U ha units) and dz (own UZ z units) =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -756,26 +1019,18 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             af_red_store(red, 8 + warp, acc2, lane);
         }
         __syncthreads();
-        if (aok) {
-            dha_carry = dha * ug + d_rh * rg + af_red_sum(red, 0, 8, 1, ai, ar);
-            float* g = a.d_G + row * 3 * HA + unit;
-            g[0] = dr_pre; g[HA] = du_pre; g[2 * HA] = dc_pre;
-            a.s_r[row * HA + unit] = rg * hp;                   // operand of the candidate-weight gradient GEMM
-        }
+        if (aok) dha_carry = dha * ug + d_rh * rg + af_red_sum(red, 0, 8, 1, ai, ar);
+        float dzv = 0.f;
         if (tid < UZ * R) {
-            const int i = tid % UZ, r = tid / UZ, n = grp * R + r;
-            float v = 0.f;
-            if (n < a.N) {
-                const long long rw = (long long)n * Td + t;
-                const float z = a.s_z[rw * Z + rank * UZ + i];
-                v = (z > 0.f) ? af_red_sum(red, 8, 8, 1, i, r) : 0.f;
-                a.d_zp[rw * Z + rank * UZ + i] = v;
-            }
-            reinterpret_cast<bf16*>(stage)[r * UZ + i] = __float2bfloat16(v);
+            if (zok) dzv = (zval > 0.f) ? af_red_sum(red, 8, 8, 1, zi, zr) : 0.f;
+            reinterpret_cast<bf16*>(stage)[zr * UZ + zi] = __float2bfloat16(dzv);
         }
         __syncthreads();
         af_push(stage, dzp_s + rank * R * UZ, b_dzp, R * UZ * 2, tid);
+        if (zok) a.d_zp[((long long)zn * Td + t) * Z + rank * UZ + zi] = dzv;
+        AF_T(10);
         af_wait(b_dzp, par);
+        AF_T(11);
         // ===== Bp8: dz1 (own U) = dz_pre . W2^T, relu' =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -783,17 +1038,17 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             af_red_store(red, warp, acc, lane);
         }
         __syncthreads();
+        float dz1v = 0.f;
         if (act) {
-            float v = 0.f;
-            if (aok) {
-                v = (z1v > 0.f) ? af_red_sum(red, 0, 8, 1, ai, ar) : 0.f;
-                a.d_z1p[row * Z1 + unit] = v;
-            }
-            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(v);
+            if (aok) dz1v = (z1v > 0.f) ? af_red_sum(red, 0, 8, 1, ai, ar) : 0.f;
+            reinterpret_cast<bf16*>(stage)[ar * U + ai] = __float2bfloat16(dz1v);
         }
         __syncthreads();
         af_push(stage, dz1p_s + rank * R * U, b_dz1p, R * U * 2, tid);
+        if (aok) a.d_z1p[row * Z1 + unit] = dz1v;
+        AF_T(12);
         af_wait(b_dz1p, par);
+        AF_T(13);
         // ===== Bp9: grad wrt ctx_{t-1} (own U) = dz1_pre . W1c^T =====
         {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -803,7 +1058,9 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         __syncthreads();
         if (act) dctx_carry = af_red_sum(red, 0, 8, 1, ai, ar);
         __syncthreads();
+        AF_T(14);
     }
+    if (prof) { for (int q = 0; q < 20; q++) g_af_prof[20 + q] = pacc[q]; }
     if (a.d_ha0 && aok) a.d_ha0[(long long)an * HA + unit] = dha_carry;
     if (rank == 0 && lane == 0 && a.d_score_bias && a.att_type == TACO_ATT_BAH_MON) atomicAdd(a.d_score_bias, gbias_acc);
     cl.sync();
@@ -811,7 +1068,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
 
 static size_t af_bwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
-    size_t b = AfBwdSmem::w_end + (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * Ti * AF_U * 2 + 16;
+    size_t b = AfBwdSmem::w_end + (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16 + (size_t)AF_R * 4 * 4;
     b += (size_t)AF_R * AF_E * 4 + (size_t)AF_R * Tip * 4 + (size_t)AF_R * (AF_A + AF_HA + 2 * AF_HA + AF_Z + AF_Z1 + AF_Y) * 2;
     b += (size_t)5 * AF_R * Tip * 4 + 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
@@ -819,8 +1076,8 @@ static size_t af_bwd_smem(int Ti) {
 
 static size_t af_fwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
-    size_t b = AfFwdSmem::w_end + (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * Ti * AF_U * 2 + 16;
-    b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * Tip * 4;
+    size_t b = AfFwdSmem::w_end + (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16;
+    b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * (Tip + 4) * 4;
     b += 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
 }
@@ -829,6 +1086,8 @@ bool att_fast_supported(const AttArgs& a) {
     return a.E == AF_E && a.A == AF_A && a.HA == AF_HA && a.Z1 == AF_Z1 && a.Z == AF_Z && a.Y == AF_Y && a.SPK == 0 &&
            a.att_type != TACO_ATT_BAH_NORM && af_fwd_smem(a.Ti) <= 227 * 1024 && af_bwd_smem(a.Ti) <= 227 * 1024;
 }
+
+int af_debug_prof(long long out[40]) { TACO_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_af_prof, sizeof(long long) * 40)); return TACO_OK; }
 
 template <typename K>
 static int af_launch(K kern, const AttArgs& a, size_t smem, int& configured, cudaStream_t s) {
@@ -864,3 +1123,5 @@ int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s) {
 }
 
 }  // namespace taco
+
+extern "C" int taco_debug_att_prof(long long out[40]) { return taco::af_debug_prof(out); }

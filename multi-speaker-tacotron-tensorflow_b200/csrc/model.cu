@@ -17,19 +17,76 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
+// ---- optional per-class device timing (CUDA events on the launching stream; used by bench.py's roofline leg) ----
+static bool g_prof_on = false;
+struct ProfSpan { cudaEvent_t a, b; int cls; };
+static std::vector<ProfSpan> g_prof_spans;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+    cudaStream_t s; int idx = -1;
+    ProfScope(int cls, cudaStream_t st) : s(st) {
+        if (!g_prof_on) return;
+        ProfSpan sp{prof_event(), prof_event(), cls};
+        cudaEventRecord(sp.a, s);
+        g_prof_spans.push_back(sp); idx = (int)g_prof_spans.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof_spans[idx].b, s); }
+};
+int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s) { ProfScope p(1, s); return bwd ? launch_gru_bwd(a, s) : launch_gru_fwd(a, s); }
+int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s) { ProfScope p(2, s); return bwd ? launch_att_bwd(a, s) : launch_att_fwd(a, s); }
+
 // Route each problem: tcgen05/TMA kernel in TF32 mode when its operands satisfy TMA's alignment rules, otherwise
 // (and always in FP32 mode) the exact fp32 SIMT kernel.
+// Problems of one call are independent (or accumulate atomically), so the tensor-core launches are spread over a few
+// auxiliary streams (event fork / join on the caller's stream): the 36-tile encoder GEMMs and the conv-bank members
+// then overlap instead of running one under-filled grid after another.
+static constexpr int kAuxStreams = 4;
+static cudaStream_t g_aux[kAuxStreams];
+static cudaEvent_t g_fork, g_join[kAuxStreams];
+static bool g_aux_ready = false;
+static int aux_init() {
+    if (g_aux_ready) return TACO_OK;
+    for (int i = 0; i < kAuxStreams; i++) {
+        TACO_CHECK_CUDA(cudaStreamCreateWithFlags(&g_aux[i], cudaStreamNonBlocking));
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+    }
+    TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    g_aux_ready = true;
+    return TACO_OK;
+}
+
 int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s) {
+    ProfScope prof_scope(0, s);
     if (precision == TACO_PREC_FP32) return launch_gemm_simt(d, n_problems, s);
     std::vector<taco_gemm_desc> rest;
+    std::vector<int> tc;
     for (int i = 0; i < n_problems; i++) {
-        if (gemm_tc_eligible(d[i])) {
-            int rc = launch_gemm_tc(d[i], s);
-            if (rc == TACO_OK) continue;
-            if (rc != TACO_ENOTSUP) return rc;
-        }
-        rest.push_back(d[i]);
+        if (gemm_tc_eligible(d[i])) tc.push_back(i); else rest.push_back(d[i]);
     }
+    const bool fan_out = tc.size() >= 2;
+    if (fan_out) {
+        TACO_TRY(aux_init());
+        TACO_CHECK_CUDA(cudaEventRecord(g_fork, s));
+        for (int i = 0; i < kAuxStreams; i++) TACO_CHECK_CUDA(cudaStreamWaitEvent(g_aux[i], g_fork, 0));
+    }
+    int rc_all = TACO_OK;
+    for (size_t k = 0; k < tc.size(); k++) {
+        cudaStream_t st = fan_out ? g_aux[k % kAuxStreams] : s;
+        int rc = launch_gemm_tc(d[tc[k]], st);
+        if (rc == TACO_ENOTSUP) rest.push_back(d[tc[k]]);
+        else if (rc != TACO_OK && rc_all == TACO_OK) rc_all = rc;
+    }
+    if (fan_out) {
+        for (int i = 0; i < kAuxStreams; i++) {
+            TACO_CHECK_CUDA(cudaEventRecord(g_join[i], g_aux[i]));
+            TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_join[i], 0));
+        }
+    }
+    if (rc_all != TACO_OK) return rc_all;
     if (!rest.empty()) return launch_gemm_simt(rest.data(), (int)rest.size(), s);
     return TACO_OK;
 }
@@ -575,6 +632,26 @@ int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
     out->loss_without_coeff = out->mel_loss + out->linear_loss;
     out->grad_norm = scf[0];
     out->learning_rate = scf[1];
+    return TACO_OK;
+}
+
+int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]) {
+    // enable=1: start collecting; enable=0: stop, synchronise and return per-class totals (0 GEMM, 1 GRU recurrences, 2 attention recurrences)
+    if (enable) {
+        for (auto& sp : g_prof_spans) { g_prof_pool.push_back(sp.a); g_prof_pool.push_back(sp.b); }
+        g_prof_spans.clear(); g_prof_on = true;
+        return TACO_OK;
+    }
+    g_prof_on = false;
+    TACO_CHECK_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 4; i++) { if (ms_out) ms_out[i] = 0.0; if (count_out) count_out[i] = 0; }
+    for (auto& sp : g_prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < 4) {
+            if (ms_out) ms_out[sp.cls] += ms;
+            if (count_out) count_out[sp.cls] += 1;
+        }
+    }
     return TACO_OK;
 }
 

@@ -57,6 +57,9 @@ struct Model {
     bool has_region(const std::string& name) const { return regions.count(name) != 0; }
 };
 
+int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s);
+int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s);
+
 // model_cbhg.cu
 int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* before_highway, const float* rnn_h0,
                  int training, cudaStream_t s);

@@ -131,7 +131,7 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
         a.out = R("rnn_out"); a.out_ld = 2 * H;
         if (lengths) TACO_CHECK_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)g.N * g.T * 2 * H, s));
         if (training) { a.st_r = R("st_r"); a.st_u = R("st_u"); a.st_c = R("st_c"); a.st_hprev = R("st_hprev"); }
-        TACO_TRY(launch_gru_fwd(a, s));
+        TACO_TRY(prof_launch_gru(a, false, s));
     }
     return TACO_OK;
 }
@@ -158,7 +158,7 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         a.st_r = R("st_r"); a.st_u = R("st_u"); a.st_c = R("st_c"); a.st_hprev = R("st_hprev");
         a.dout = R("d_rnn_out"); a.dout_ld = 2 * H; a.dgx = R("dgx");
         a.dh0 = want_dh0 ? R("d_h0") : nullptr;
-        TACO_TRY(launch_gru_bwd(a, s));
+        TACO_TRY(prof_launch_gru(a, true, s));
     }
     // GRU weight gradients.  Recurrent parts reduce over the unpadded [N*T] stash rows; dgx lives in the padded
     // layout, so gather its valid rows once into a dense [2][N*T, 3H] matrix first.

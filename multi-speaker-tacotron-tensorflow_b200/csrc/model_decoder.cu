@@ -64,7 +64,7 @@ static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, 
     a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
     a.h0 = h0; a.res = x; a.res_ld = Y; a.out = y; a.out_ld = Y;
     if (training) { a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev"); }
-    return launch_gru_fwd(a, s);
+    return prof_launch_gru(a, false, s);
 }
 
 int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
@@ -107,14 +107,14 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         a.h1_0 = h1; a.h2_0 = h2;
         a.mel_out = m.W("post_cbhg/xin_p") + (long long)g.PL * D.M; a.mel_bs = (long long)g.Tp * D.M;
         a.y0 = nullptr;
-        return launch_att_fwd(a, s);
+        return prof_launch_att(a, false, s);
     }
     if (training) {
         a.s_z1 = m.W("dec/s_z1"); a.s_z = m.W("dec/s_z"); a.s_r = m.W("dec/s_r"); a.s_u = m.W("dec/s_u"); a.s_c = m.W("dec/s_c");
         a.s_haprev = m.W("dec/s_haprev"); a.s_ha = m.W("dec/s_ha"); a.s_q = m.W("dec/s_q"); a.s_ctxin = m.W("dec/s_ctxin");
         a.s_ctx = m.W("dec/s_ctx"); a.s_e = m.W("dec/s_e"); a.s_a = m.W("dec/s_a");
     }
-    TACO_TRY(launch_att_fwd(a, s));
+    TACO_TRY(prof_launch_att(a, false, s));
     // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
     TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
     TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
@@ -144,7 +144,7 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
     a.dout = dy; a.dout_ld = Y; a.dgx = dgx;
     a.dh0 = want_dh0 ? m.W(rp + "dh0") : nullptr;
-    TACO_TRY(launch_gru_bwd(a, s));
+    TACO_TRY(prof_launch_gru(a, true, s));
     taco_gemm_desc w[4];
     w[0] = wgrad(x, Y, dgx, 3 * Y, m.G(gn + "/gates_kernel"), Y, 2 * Y, rows);
     w[1] = wgrad(x, Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel"), Y, Y, rows);
@@ -206,7 +206,7 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     a.d_gq = m.W("dec/d_gq"); a.d_ge = m.W("dec/d_ge");
     a.d_ha0 = deepvoice ? m.W("dec/d_ha0") : nullptr;
     a.d_score_bias = m.has("attention/score_bias") ? m.G("attention/score_bias") : nullptr;
-    TACO_TRY(launch_att_bwd(a, s));
+    TACO_TRY(prof_launch_att(a, true, s));
 
     // hoisted parameter gradients of the attention part
     {
