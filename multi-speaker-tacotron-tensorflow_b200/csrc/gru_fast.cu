@@ -198,12 +198,13 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
 
     const bool prof = (blockIdx.x == 0 && tid == 0);
     long long pacc[10] = {0,0,0,0,0,0,0,0,0,0}; long long plast = clock64();
-    float gr = 0.f, gu = 0.f, gc = 0.f;
+    float gr = 0.f, gu = 0.f, gc = 0.f, gres = 0.f;
     auto load_gx = [&](int s) {
         if (act && s < L) {
             const int t = (d == 0) ? s : (L - 1 - s);
             const float* g = a.gx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
             gr = __ldg(g); gu = __ldg(g + H); gc = __ldg(g + 2 * H);
+            if (a.res) gres = __ldg(a.res + ((long long)n * a.T + t) * a.res_ld + unit);
         }
     };
     load_gx(0);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         const uint32_t par = s & 1;
         const bool valid = act && (s < L);
         const int t = (d == 0) ? s : (L - 1 - s);
-        const float cgr = gr, cgu = gu, cgc = gc;
+        const float cgr = gr, cgu = gu, cgc = gc, cres = gres;
         if (tid == 0) { gf_mbar_expect_tx(bar_rh, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h, GF_C * Cfg::BLK_BYTES); }
         load_gx(s + 1);                                          // prefetch next step's x-side pre-activations
         GF_T(0);
@@ -258,29 +259,28 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
             *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
         }
         __syncthreads();
+        float cnd = 0.f, hprev = h_own;
         if (act) {
             float sc = cgc;
 #pragma unroll
             for (int ks = 0; ks < KS_C; ks++) sc += red[ks * (U * R) + i * R + r];
-            const float c = gf_tanh(sc);
-            const float hn = ug * h_own + (1.f - ug) * c;
-            if (valid) {
-                const long long o = (long long)n * a.T + t;
-                float y = hn;
-                if (a.res) y += a.res[o * a.res_ld + unit];
-                a.out[o * a.out_ld + d * H + unit] = y;
-                if (a.st_r) {
-                    const long long so = (st_base + t) * H + unit;
-                    a.st_r[so] = rg; a.st_u[so] = ug; a.st_c[so] = c; a.st_hprev[so] = h_own;
-                }
-                h_own = hn;
-            }
+            cnd = gf_tanh(sc);
+            if (valid) h_own = ug * h_own + (1.f - ug) * cnd;
             stage_h[r * U + i] = __float2bfloat16(h_own);
         }
 #if GF_USE_STASYNC
         __syncthreads();
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_h, hb_s + rank * R * U, bar_h, tid);
+        if (valid) {      // output and stash stores ride in the shadow of the exchange
+            const long long o = (long long)n * a.T + t;
+            a.out[o * a.out_ld + d * H + unit] = h_own + cres;
+            if (a.st_r) {
+                const long long so = (st_base + t) * H + unit;
+                a.st_r[so] = rg; a.st_u[so] = ug; a.st_c[so] = cnd; a.st_hprev[so] = hprev;
+            }
+        }
 #else
+#error "bulk-copy exchange variant is not maintained"
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid < GF_C) gf_push(stage_h, hb_s + rank * R * U, bar_h, Cfg::BLK_BYTES, tid);
@@ -409,6 +409,11 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         __syncthreads();
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_r, dg_s + rank * R * U, bar_g, tid);
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, tid);
+        if (valid) {      // gradient / stash stores in the shadow of the exchange
+            float* g = a.dgx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
+            g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre;
+            a.st_r[(st_base + t) * H + unit] = r_ * hp_;
+        }
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -430,12 +435,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
             float sg = 0.f;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) sg += red[ks * (U * R) + i * R + r];
-            if (valid) {
-                dh_carry = dh * u_ + d_rh * r_ + sg;
-                float* g = a.dgx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
-                g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre;
-                a.st_r[(st_base + t) * H + unit] = r_ * hp_;
-            }
+            if (valid) dh_carry = dh * u_ + d_rh * r_ + sg;
         }
         __syncthreads();      // `red` / stages are rewritten at the top of the next iteration
     }
