@@ -841,6 +841,31 @@ __global__ void att_keys_bwd_kernel(const float* __restrict__ keys, const float*
     }
 }
 
+// bah_norm (TF BahdanauAttention normalize=True): v_eff = g * v / ||v||, and the chain back to v and g.
+__global__ void att_vnorm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ v_eff,
+                                 const float* __restrict__ gveff, float* __restrict__ gv, float* __restrict__ gg, int A) {
+    __shared__ float red[2][32];
+    float ss = 0.f, sd = 0.f;
+    for (int u = threadIdx.x; u < A; u += blockDim.x) { const float x = v[u]; ss = fmaf(x, x, ss); if (gveff) sd = fmaf(x, gveff[u], sd); }
+    for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = sd; }
+    __syncthreads();
+    ss = 0.f; sd = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { ss += red[0][w]; sd += red[1][w]; }
+    const float rn = rsqrtf(ss), gs = g[0];
+    if (!gveff) {
+        for (int u = threadIdx.x; u < A; u += blockDim.x) v_eff[u] = gs * v[u] * rn;
+    } else {
+        if (threadIdx.x == 0) gg[0] += sd * rn;
+        for (int u = threadIdx.x; u < A; u += blockDim.x) gv[u] += gs * rn * (gveff[u] - v[u] * sd * rn * rn);
+    }
+}
+int launch_att_vnorm(const float* v, const float* g, float* v_eff, const float* gveff, float* gv, float* gg, int A, cudaStream_t s) {
+    att_vnorm_kernel<<<1, 256, 0, s>>>(v, g, v_eff, gveff, gv, gg, A);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 static int att_check(const AttArgs& a) {
     TACO_REQUIRE(a.N > 0 && a.Ti > 0 && a.Td > 0, TACO_ESHAPE, "attention: empty shape");
     TACO_REQUIRE(a.E % 256 == 0 || a.E == 256, TACO_ESHAPE, "attention: memory width %d unsupported", a.E);

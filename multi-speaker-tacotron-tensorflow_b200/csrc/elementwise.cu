@@ -301,6 +301,21 @@ int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int
     return TACO_OK;
 }
 
+// dst[(n*T + t)*ld + c] = src[n*ld + c]   (a per-utterance vector tiled over time; the speaker term of a dense layer)
+__global__ void bcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int C, long long ld, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long row = i / C; int c = (int)(i % C);
+        dst[row * ld + c] = __ldg(src + (row / T) * ld + c);
+    }
+}
+int launch_bcast_rows(const float* src, float* dst, int N, int T, int C, long long ld, cudaStream_t s) {
+    const long long total = (long long)N * T * C;
+    if (total <= 0) return TACO_OK;
+    bcast_rows_kernel<<<ew_blocks(total), EW_THREADS, 0, s>>>(src, dst, T, C, ld, total);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 // y[i] += a * x[i]
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];

@@ -322,11 +322,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
                     cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
                 }
-                if (lane < 8) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (gn + e < p.N) { atomicAdd(p.colsum + gn + e, (double)cs[e]); atomicAdd(p.colsumsq + gn + e, (double)cq[e]); }
+                if (lane < 8) {                                  // per-quarter partials, reduced over the CTA below
+                    float* red = reinterpret_cast<float*>(sB) + q * (2 * TC_BN) + c0 + lc;
+                    *reinterpret_cast<float4*>(red) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                    *reinterpret_cast<float4*>(red + TC_BN) = make_float4(cq[0], cq[1], cq[2], cq[3]);
                 }
+            }
+        }
+        if (p.colsum) {
+            // one double atomic per column and statistic per CTA (the four lane quarters are summed here first: the
+            // statistics land on a few hundred addresses, so their atomics serialise in L2)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int et = threadIdx.x - 64, col = et & (TC_BN - 1), which = et >> 7;
+            if (n0 + col < p.N) {
+                const float* red = reinterpret_cast<const float*>(sB) + which * TC_BN + col;
+                const float v = (red[0] + red[2 * TC_BN]) + (red[4 * TC_BN] + red[6 * TC_BN]);
+                atomicAdd((which ? p.colsumsq : p.colsum) + n0 + col, (double)v);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

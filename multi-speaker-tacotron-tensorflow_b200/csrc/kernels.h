@@ -32,6 +32,7 @@ int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n,
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
 int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s);
+int launch_bcast_rows(const float* src, float* dst, int N, int T, int C, long long ld, cudaStream_t s);
 int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int C, cudaStream_t s);
 int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s);
 int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
@@ -102,6 +103,8 @@ int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s);   // TACO_ENOTSUP whe
 int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s);
 int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,
                         int N, int Ti, int Td, int A, int fast, cudaStream_t s);
+// forward (gveff == NULL): v_eff = g v/||v||;  backward: gv += d v_eff/d v . gveff, gg += d v_eff/d g . gveff
+int launch_att_vnorm(const float* v, const float* g, float* v_eff, const float* gveff, float* gv, float* gg, int A, cudaStream_t s);
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
 
 // optim.cu

@@ -227,6 +227,7 @@ void Model::plan(const Shape& s) {
             add("dec/d_G", {rows, 3 * HA}); add("dec/d_zp", {rows, Z}); add("dec/d_z1p", {rows, Z1}); add("dec/d_ctx", {rows, E});
             add("dec/d_gq", {rows, A}); add("dec/d_ge", {rows, s.Ti}); add("dec/d_ha0", {N, HA});
             add("dec/d_keys", {(int64_t)N * s.Ti, A});
+            add("dec/v_eff", {A}); add("dec/g_veff", {A});
         }
     }
     // The linear-spectrogram tensors use a row pitch rounded up to 4 floats (1025 -> 1028) so TMA can address them
@@ -249,6 +250,14 @@ void Model::plan(const Shape& s) {
         add("spk/before", {N, c.enc_prenet_sizes[1]}); add("spk/enc_init", {N, 2 * (int64_t)c.enc_rnn_size});
         add("spk/att_init", {N, c.attention_state_size}); add("spk/dec_init1", {N, Y}); add("spk/dec_init2", {N, Y});
         if (tr) { add("spk/d_pre", {N, 2 * (int64_t)c.enc_rnn_size + c.attention_state_size + Y}); add("spk/d_embed", {N, S}); }
+    }
+    if (c.speaker_mode == TACO_SPK_SIMPLE) {
+        const int64_t S = c.speaker_embedding_size, Fp = (c.num_freq + 3) / 4 * 4;
+        add("spk/embed", {N, S}); add("spk/lin_bias", {N, Fp});
+        if (tr) {
+            add("spk/d_embed", {N, S}); add("spk/s_lin", {N, Fp});
+            add("spk/s_y0", {N, c.dec_rnn_size}); add("spk/s_G", {N, 3 * (int64_t)c.attention_state_size});
+        }
     }
     add("scalars", {8}, 0, true);
     add("scalars_f", {8});
@@ -298,7 +307,12 @@ static taco_gemm_desc gd0(const float* A, const float* B, float* C, int M, int N
 static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const taco_config& c = m.cfg;
     const int prec = c.precision, tr = m.shape.training;
-    TACO_REQUIRE(c.speaker_mode != TACO_SPK_SIMPLE, TACO_ESTATE, "model_type 'simple' (speaker-embedding concatenation) is not built yet");
+    const bool simple = (c.speaker_mode == TACO_SPK_SIMPLE);
+    if (simple) {
+        // 'simple' injection: one embedding row per utterance, concatenated at three sites (tacotron.py:44-49,82-86)
+        TACO_REQUIRE(b->speaker_id != nullptr, TACO_EINVAL, "speaker_id is required when num_speakers > 1");
+        TACO_TRY(launch_gather_rows(m.P("speaker_embedding"), b->speaker_id, m.W("spk/embed"), m.shape.N, 1, 1, 0, c.speaker_embedding_size, c.num_speakers, s));
+    }
     const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
     struct Site { const char* name; const char* region; int dim; };
     const Site sites[5] = {{"before_highway", "spk/before", c.enc_prenet_sizes[1]}, {"encoder_rnn_init_state", "spk/enc_init", 2 * c.enc_rnn_size},
@@ -337,9 +351,19 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     // ---- linear-spectrogram projection (tacotron.py:235) ----
     {
         const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 3) / 4 * 4;
-        TACO_TRY(launch_copy2d(m.W("linear/w_pad"), m.P("linear/kernel"), Hp2, F, Fp, F, s));     // 16-byte row pitch for TMA
-        taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.W("linear/w_pad"), m.W("linear_buf"), m.shape.N * m.shape.To, F, Hp2, Hp2, Fp, Fp);
-        d.bias = m.P("linear/bias");
+        const int S = simple ? c.speaker_embedding_size : 0;
+        TACO_TRY(launch_copy2d(m.W("linear/w_pad"), m.P("linear/kernel"), Hp2 + S, F, Fp, F, s));     // 16-byte row pitch for TMA
+        taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.W("linear/w_pad") + (long long)S * Fp, m.W("linear_buf"), m.shape.N * m.shape.To, F, Hp2, Hp2, Fp, Fp);
+        if (simple) {
+            // concat([tiled speaker_embed, post_outputs]) . W  ==  post . W[S:] + (embed . W[:S] + b) tiled over time   tacotron.py:226-235
+            taco_gemm_desc e = gd0(m.W("spk/embed"), m.W("linear/w_pad"), m.W("spk/lin_bias"), m.shape.N, F, S, S, Fp, Fp);
+            e.bias = m.P("linear/bias");
+            TACO_TRY(launch_gemm(&e, 1, TACO_PREC_FP32, s));
+            TACO_TRY(launch_bcast_rows(m.W("spk/lin_bias"), m.W("linear_buf"), m.shape.N, m.shape.To, F, Fp, s));
+            d.accumulate = 1;
+        } else {
+            d.bias = m.P("linear/bias");
+        }
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
     return TACO_OK;
@@ -379,11 +403,24 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     // ---- linear projection backward ----
     {
         const int Hp2 = 2 * c.post_rnn_size; const long long rows = (long long)N * To;
-        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel"), Hp2, F, (int)rows, Hp2, Fp, F);
+        const int S = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
+        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel") + (long long)S * F, Hp2, F, (int)rows, Hp2, Fp, F);
         w.transA = 1; w.accumulate = 1; w.split_k = 8;
         TACO_TRY(launch_gemm(&w, 1, prec, s));
         TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, s));
-        taco_gemm_desc e = gd0(m.W("d_linear"), m.W("linear/w_pad"), m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
+        if (S) {
+            // speaker rows of the kernel and the embedding gradient see d_linear only through its sum over time
+            TACO_CHECK_CUDA(cudaMemsetAsync(m.W("spk/s_lin"), 0, sizeof(float) * (size_t)N * Fp, s));
+            TACO_CHECK_CUDA(cudaMemsetAsync(m.W("spk/d_embed"), 0, sizeof(float) * (size_t)N * S, s));
+            TACO_TRY(launch_timesum(m.W("d_linear"), m.W("spk/s_lin"), N, To, To, 0, Fp, s));
+            taco_gemm_desc ws = gd0(m.W("spk/embed"), m.W("spk/s_lin"), m.G("linear/kernel"), S, F, N, S, Fp, F);
+            ws.transA = 1; ws.accumulate = 1;
+            TACO_TRY(launch_gemm(&ws, 1, TACO_PREC_FP32, s));
+            taco_gemm_desc es = gd0(m.W("spk/s_lin"), m.W("linear/w_pad"), m.W("spk/d_embed"), N, S, F, Fp, Fp, S);
+            es.transB = 1; es.accumulate = 1;
+            TACO_TRY(launch_gemm(&es, 1, TACO_PREC_FP32, s));
+        }
+        taco_gemm_desc e = gd0(m.W("d_linear"), m.W("linear/w_pad") + (long long)S * Fp, m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
         e.transB = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
@@ -421,6 +458,9 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
                 TACO_TRY(launch_scatter_add_rows(m.W(st.grad), b->speaker_id, m.G(std::string("speaker/") + st.name + "/table"), Nb, 1, 1, 0, st.dim, c.num_speakers, s));
         }
     }
+    if (c.speaker_mode == TACO_SPK_SIMPLE)      // "spk/d_embed" now holds the linear, concat-projection and attention-GRU terms
+        TACO_TRY(launch_scatter_add_rows(m.W("spk/d_embed"), b->speaker_id, m.G("speaker_embedding"), m.shape.N, 1, 1, 0,
+                                         c.speaker_embedding_size, c.num_speakers, s));
     // ---- encoder prenet tables backward ----
     {
         const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];

@@ -232,6 +232,28 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         TACO_TRY(launch_colsum(a.d_zp, m.G("dec_prenet/dense_2/bias"), rows, Z, Z, s));
         TACO_TRY(launch_colsum(a.d_z1p, m.G("dec_prenet/dense_1/bias"), rows, Z1, Z1, s));
         if (m.cfg.attention_type == TACO_ATT_BAH_NORM) TACO_TRY(launch_colsum(a.d_gq, m.G("attention/b"), rows, A, A, s));
+        if (D.SPK) {
+            // 'simple' speaker rows (rnn_wrappers.py:372-376,408-413): the embedding is constant over time, so its kernel rows
+            // and its own gradient need only the time sums of the pre-activation gradients
+            const int S = D.SPK, Nb = D.N;
+            float* sy = m.W("spk/s_y0"); float* sG = m.W("spk/s_G"); float* de = m.W("spk/d_embed");
+            TACO_CHECK_CUDA(cudaMemsetAsync(sy, 0, sizeof(float) * (size_t)Nb * Y, s));
+            TACO_CHECK_CUDA(cudaMemsetAsync(sG, 0, sizeof(float) * (size_t)Nb * 3 * HA, s));
+            TACO_TRY(launch_timesum(a.dy0, sy, Nb, D.Td, D.Td, 0, Y, s));
+            TACO_TRY(launch_timesum(a.d_G, sG, Nb, D.Td, D.Td, 0, 3 * HA, s));
+            const float* emb = m.W("spk/embed");
+            struct Term { const float* sum; int ld; int n; const float* W; float* gW; };
+            const Term terms[3] = {
+                {sy, Y, Y, m.P("concat_proj/kernel") + (long long)(HA + E) * Y, gWo + (long long)(HA + E) * Y},
+                {sG, 3 * HA, 2 * HA, m.P("attention_gru/gates_kernel") + (long long)Z * 2 * HA, gWg + (long long)Z * 2 * HA},
+                {sG + 2 * HA, 3 * HA, HA, m.P("attention_gru/cand_kernel") + (long long)Z * HA, gWc + (long long)Z * HA}};
+            for (const Term& t : terms) {
+                taco_gemm_desc ws = gd(emb, t.sum, t.gW, S, t.n, Nb, S, t.ld, t.n); ws.transA = 1; ws.accumulate = 1;
+                TACO_TRY(launch_gemm(&ws, 1, TACO_PREC_FP32, s));
+                taco_gemm_desc es = gd(t.sum, t.W, de, Nb, S, t.n, t.ld, t.n, S); es.transB = 1; es.accumulate = 1;
+                TACO_TRY(launch_gemm(&es, 1, TACO_PREC_FP32, s));
+            }
+        }
     }
     // keys / v gradients and the gradient wrt the encoder memory
     {
@@ -239,9 +261,17 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         (void)HA;
         float* d_mem = m.W("enc_cbhg/d_rnn_out");
         if (!b->manual_alignments) {
-            TACO_REQUIRE(m.cfg.attention_type != TACO_ATT_BAH_NORM, TACO_ESTATE, "bah_norm backward (g/v chain) is not built yet");
-            TACO_TRY(launch_att_keys_bwd(a.keys, a.s_q, a.d_ge, m.P("attention/v"), m.W("dec/d_keys"), m.G("attention/v"),
-                                         D.N, D.Ti, D.Td, A, a.fast, s));
+            if (m.cfg.attention_type == TACO_ATT_BAH_NORM) {
+                // e = sum_u (g v_u/||v||) tanh(k + q + b): keys see the normalised vector; its gradient chains to v and g
+                float* ve = m.W("dec/v_eff"); float* gve = m.W("dec/g_veff");
+                TACO_TRY(launch_att_vnorm(m.P("attention/v"), m.P("attention/g"), ve, nullptr, nullptr, nullptr, A, s));
+                TACO_CHECK_CUDA(cudaMemsetAsync(gve, 0, sizeof(float) * A, s));
+                TACO_TRY(launch_att_keys_bwd(a.keys, a.s_q, a.d_ge, ve, m.W("dec/d_keys"), gve, D.N, D.Ti, D.Td, A, a.fast, s));
+                TACO_TRY(launch_att_vnorm(m.P("attention/v"), m.P("attention/g"), nullptr, gve, m.G("attention/v"), m.G("attention/g"), A, s));
+            } else {
+                TACO_TRY(launch_att_keys_bwd(a.keys, a.s_q, a.d_ge, m.P("attention/v"), m.W("dec/d_keys"), m.G("attention/v"),
+                                             D.N, D.Ti, D.Td, A, a.fast, s));
+            }
             taco_gemm_desc w = wgrad(a.memory, E, m.W("dec/d_keys"), A, m.G("attention/memory_kernel"), E, A, (long long)D.N * D.Ti);
             TACO_TRY(launch_gemm(&w, 1, prec, s));
             taco_gemm_desc e = gd(m.W("dec/d_keys"), m.P("attention/memory_kernel"), d_mem, D.N * D.Ti, E, A, A, A, E); e.transB = 1;

@@ -294,3 +294,84 @@ def test_deepvoice_speaker_injection_vs_oracle(tb, prec, emb):
     with pytest.raises(tb.capi.TacoError, match="speaker_id"):
         eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"])
     eng.close()
+
+
+def _oracle_grads(named, hp, b, S, spk, mode):
+    names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
+    ref = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, spk, b["mel_targets"], b["linear_targets"], speaker_mode=mode)
+    ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    return ref, {k: (gg if gg is not None else torch.zeros_like(named[k])) for k, gg in zip(names, gl)}, names
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_simple_speaker_concat_vs_oracle(tb, prec):
+    """model_type='simple' (tacotron.py:44-49,82-86,226-233; rnn_wrappers.py:372-376,408-413): the speaker embedding is
+    concatenated at the attention-GRU input, the concat projection and (first) before the linear projection."""
+    hp = tb.hparams.override(reduction_factor=5, model_type="simple", speaker_embedding_size=16)
+    S = 4
+    mode = tb.params.speaker_mode(hp, S)
+    assert mode == "simple"
+    named = tb.params.init_params(hp, S, seed=23, randomize_bn_state=True)
+    assert named["attention_gru/gates_kernel"].shape[0] == 128 + 16 + 256 and named["linear/kernel"].shape[0] == 512 + 16
+    N, Ti, To = 5, 12, 15
+    b = _batch(N, Ti, To, [12, 7, 12, 3, 9], seed=11)
+    spk = torch.tensor([0, 3, 1, 3, 2], dtype=torch.int32)
+    ref, ref_g, names = _oracle_grads(named, hp, b, S, spk, mode)
+    tol = TOL[prec]
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert (out[k].cpu() - ref[k].detach()).abs().max().item() <= tol["out"], k
+    eng.backward()
+    got = eng.named_gradients()
+    cos, na, nb = _cosine(got, ref_g, sorted(ref_g))
+    assert cos >= tol["cos"] and abs(na - nb) <= tol["gn"] * nb
+    if prec == "fp32":
+        for k in ("speaker_embedding", "attention_gru/gates_kernel", "attention_gru/cand_kernel", "concat_proj/kernel", "linear/kernel"):
+            dn = ref_g[k].norm().item()
+            assert dn > 0
+            assert (got[k].cpu() - ref_g[k]).norm().item() / dn <= 2e-3, k
+        # the speaker rows of each kernel on their own
+        rows = {"attention_gru/gates_kernel": slice(128, 144), "concat_proj/kernel": slice(512, 528), "linear/kernel": slice(0, 16)}
+        for k, sl in rows.items():
+            dn = ref_g[k][sl].norm().item()
+            assert dn > 0 and (got[k].cpu()[sl] - ref_g[k][sl]).norm().item() / dn <= 2e-3, k
+    # free-running synthesis with the same speaker ids (synthesizer.py:47-54,166)
+    with torch.no_grad():
+        inf = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, None, None, speaker_mode=mode, max_iters=4)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=4)
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert (out[k].cpu() - inf[k]).abs().max().item() <= (2e-3 if prec == "fp32" else 6e-2), k
+    eng.close()
+
+
+@pytest.mark.parametrize("prec,att", [("fp32", "bah"), ("fp32", "bah_norm"), ("tf32", "bah"), ("tf32", "bah_norm")])
+def test_attention_variants_vs_oracle(tb, prec, att):
+    """attention_type 'bah' (softmax BahdanauAttention) and 'bah_norm' (normalize=True: g, b) — tacotron.py:136-146."""
+    hp = tb.hparams.override(reduction_factor=5, attention_type=att)
+    named = tb.params.init_params(hp, 1, seed=29, randomize_bn_state=True)
+    if att == "bah_norm":
+        g = torch.Generator().manual_seed(5)
+        named["attention/b"] = torch.randn(named["attention/b"].shape, generator=g) * 0.3
+        named["attention/g"] = torch.tensor(0.7).reshape(named["attention/g"].shape)
+    N, Ti, To = 4, 14, 20
+    b = _batch(N, Ti, To, [14, 9, 14, 5], seed=13)
+    ref, ref_g, names = _oracle_grads(named, hp, b, 1, None, "none")
+    tol = TOL[prec]
+    eng = tb.Engine(hp, 1, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert (out[k].cpu() - ref[k].detach()).abs().max().item() <= tol["out"], k
+    eng.backward()
+    got = eng.named_gradients()
+    cos, na, nb = _cosine(got, ref_g, sorted(ref_g))
+    assert cos >= tol["cos"] and abs(na - nb) <= tol["gn"] * nb
+    if prec == "fp32":
+        keys = ["attention/v", "attention/query_kernel", "attention/memory_kernel"] + (["attention/g", "attention/b"] if att == "bah_norm" else [])
+        for k in keys:
+            dn = ref_g[k].norm().item()
+            assert dn > 0
+            assert (got[k].cpu() - ref_g[k]).norm().item() / dn <= 5e-3, k
+    eng.close()
