@@ -175,59 +175,132 @@ __device__ __forceinline__ float bn_dy(const float* __restrict__ dyp, const floa
     return d;
 }
 
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     int N, int T, int Tp, int PL, int C, int mode, int rows_per_block) {
-    // block = (channel tile of blockDim.x channels) x (row slab)
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
-    long long r0 = (long long)blockIdx.y * rows_per_block;
-    long long r1 = min(r0 + rows_per_block, (long long)N * T);
-    float s1 = 0.f, s2 = 0.f;
-    for (long long r = r0; r < r1; r++) {
-        int n = (int)(r / T), t = (int)(r % T);
-        long long off = ((long long)n * Tp + PL + t) * C + c;
-        float dy = bn_dy(dyp, x, off, C, t, T, mu, rs, g, b, mode);
-        s1 += dy; s2 += dy * (x[off] - mu) * rs;
-    }
-    atomicAdd(dbeta + c, s1);
-    atomicAdd(dgamma + c, s2);
+// Both passes use one thread per (4 channels) x (BNB_R consecutive time steps of one utterance): the neighbouring rows the
+// max-pool routing needs (mode 1) are then already in registers, every load is a coalesced float4 and all of a thread's
+// loads are issued before the arithmetic.  Blocks are (tx channel lanes) x (ty row lanes), 256 threads.
+constexpr int BNB_R = 8;
+
+__device__ __forceinline__ float4 f4_ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_bn(float4 x, float4 mu, float4 rs, float4 g, float4 b) {
+    return make_float4((x.x - mu.x) * rs.x * g.x + b.x, (x.y - mu.y) * rs.y * g.y + b.y, (x.z - mu.z) * rs.z * g.z + b.z, (x.w - mu.w) * rs.w * g.w + b.w);
 }
 
-// Pass 2: dx = gamma*rstd*(dy - s1/M - xhat*s2/M), then relu' (x>0) when the conv had its activation before BN.
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    float* __restrict__ dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask) {
-    long long total = (long long)N * Tp * C;
-    const float invM = 1.0f / ((float)N * (float)T);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C); long long m = i / C;
-        int tp = (int)(m % Tp), t = tp - PL;
-        float o = 0.f;
-        if (t >= 0 && t < T) {
-            float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
-            float dy = bn_dy(dyp, x, i, C, t, T, mu, rs, g, b, mode);
-            float xv = x[i];
-            float xh = (xv - mu) * rs;
-            o = g * rs * (dy - dbeta[c] * invM - xh * dgamma[c] * invM);
-            if (relu_mask && !(xv > 0.f)) o = 0.f;
+template <int MODE, bool APPLY>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
+                                                     int N, int T, int Tp, int PL, int C, int relu_mask, int chunks) {
+    const int tx = blockDim.x, ty = blockDim.y;
+    const int c = (blockIdx.x * tx + threadIdx.x) * 4;
+    const int n = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+    const bool cok = c < C;
+    const int tp0 = (chunk * ty + threadIdx.y) * BNB_R;
+    float4 s1 = f4_zero(), s2 = f4_zero();
+    if (cok && tp0 < Tp) {
+        const float4 mu = f4_ld(mean + c), rs = f4_ld(rstd + c), g = f4_ld(gamma + c), b = f4_ld(beta + c);
+        const long long base = ((long long)n * Tp) * C + c;
+        // rows tp0-1 .. tp0+BNB_R of x (mode 1) / tp0 .. tp0+BNB_R-1 (mode 0); rows tp0-1 .. tp0+BNB_R-1 of dy (mode 1)
+        float4 xv[BNB_R + 2], dv[BNB_R + 1];
+#pragma unroll
+        for (int j = 0; j < BNB_R + 2; j++) {
+            const int tp = tp0 - 1 + j, t = tp - PL;
+            const bool need = (MODE == 1) ? (t >= 0 && t < T) : (j >= 1 && j <= BNB_R && t >= 0 && t < T);
+            xv[j] = need ? f4_ld(x + base + (long long)tp * C) : f4_zero();
         }
-        dx[i] = o;
+#pragma unroll
+        for (int j = 0; j < BNB_R + 1; j++) {
+            const int tp = tp0 - 1 + j, t = tp - PL;
+            const bool need = (t >= 0 && t < T) && (MODE == 1 || j >= 1);
+            dv[j] = need ? f4_ld(dyp + base + (long long)tp * C) : f4_zero();
+        }
+        float4 dg4 = f4_zero(), db4 = f4_zero();
+        if (APPLY) { dg4 = f4_ld(dgamma + c); db4 = f4_ld(dbeta + c); }
+        const float invM = 1.0f / ((float)N * (float)T);
+        float4 bnv[BNB_R + 2];
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < BNB_R + 2; j++) bnv[j] = f4_bn(xv[j], mu, rs, g, b);
+        }
+#pragma unroll
+        for (int j = 1; j <= BNB_R; j++) {
+            const int tp = tp0 - 1 + j, t = tp - PL;
+            if (tp >= Tp) break;
+            const bool valid = (t >= 0 && t < T);
+            float4 dy = dv[j];
+            if (MODE == 1) {
+                // y[t] = max(bn[t], bn[t+1]) (right pad -inf): row t receives dy[t] when it wins (ties go to the first
+                // element) and dy[t-1] when it beats bn[t-1] strictly
+                const bool last = (t + 1 >= T), first = (t <= 0);
+                const float4 bc = bnv[j], bn_ = bnv[j + 1], bp = bnv[j - 1], dp = dv[j - 1], dc = dv[j];
+                dy.x = ((last || bc.x >= bn_.x) ? dc.x : 0.f) + ((!first && bc.x > bp.x) ? dp.x : 0.f);
+                dy.y = ((last || bc.y >= bn_.y) ? dc.y : 0.f) + ((!first && bc.y > bp.y) ? dp.y : 0.f);
+                dy.z = ((last || bc.z >= bn_.z) ? dc.z : 0.f) + ((!first && bc.z > bp.z) ? dp.z : 0.f);
+                dy.w = ((last || bc.w >= bn_.w) ? dc.w : 0.f) + ((!first && bc.w > bp.w) ? dp.w : 0.f);
+            }
+            const float4 xc = xv[j];
+            const float4 xh = make_float4((xc.x - mu.x) * rs.x, (xc.y - mu.y) * rs.y, (xc.z - mu.z) * rs.z, (xc.w - mu.w) * rs.w);
+            if (!APPLY) {
+                if (valid) {
+                    s1.x += dy.x; s1.y += dy.y; s1.z += dy.z; s1.w += dy.w;
+                    s2.x = fmaf(dy.x, xh.x, s2.x); s2.y = fmaf(dy.y, xh.y, s2.y); s2.z = fmaf(dy.z, xh.z, s2.z); s2.w = fmaf(dy.w, xh.w, s2.w);
+                }
+            } else {
+                float4 o = f4_zero();
+                if (valid) {
+                    o.x = g.x * rs.x * (dy.x - db4.x * invM - xh.x * dg4.x * invM);
+                    o.y = g.y * rs.y * (dy.y - db4.y * invM - xh.y * dg4.y * invM);
+                    o.z = g.z * rs.z * (dy.z - db4.z * invM - xh.z * dg4.z * invM);
+                    o.w = g.w * rs.w * (dy.w - db4.w * invM - xh.w * dg4.w * invM);
+                    if (relu_mask) {
+                        if (!(xc.x > 0.f)) o.x = 0.f;
+                        if (!(xc.y > 0.f)) o.y = 0.f;
+                        if (!(xc.z > 0.f)) o.z = 0.f;
+                        if (!(xc.w > 0.f)) o.w = 0.f;
+                    }
+                }
+                *reinterpret_cast<float4*>(dx + base + (long long)tp * C) = o;
+            }
+        }
+    }
+    if (!APPLY) {
+        __shared__ float4 red[2][256];
+        const int tid = threadIdx.y * tx + threadIdx.x;
+        red[0][tid] = s1; red[1][tid] = s2;
+        __syncthreads();
+        if (threadIdx.y == 0 && cok) {
+            for (int y = 1; y < ty; y++) {
+                const float4 a = red[0][y * tx + threadIdx.x], q = red[1][y * tx + threadIdx.x];
+                s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+                s2.x += q.x; s2.y += q.y; s2.z += q.z; s2.w += q.w;
+            }
+            atomicAdd(dbeta + c, s1.x); atomicAdd(dbeta + c + 1, s1.y); atomicAdd(dbeta + c + 2, s1.z); atomicAdd(dbeta + c + 3, s1.w);
+            atomicAdd(dgamma + c, s2.x); atomicAdd(dgamma + c + 1, s2.y); atomicAdd(dgamma + c + 2, s2.z); atomicAdd(dgamma + c + 3, s2.w);
+        }
     }
 }
+
+// lanes over float4 channel groups (power of two, <= 64) x row lanes, 256 threads
+static inline void lanes_2d(int C4, int& tx, int& ty) {
+    tx = 1; while (tx < C4 && tx < 64) tx <<= 1;
+    if (tx < 8) tx = 8;
+    ty = 256 / tx;
+}
+
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s) {
-    const int rows_per_block = 64;
-    dim3 grid(cdiv(C, 128), (unsigned)cdiv64((long long)N * T, rows_per_block));
-    bn_bwd_reduce_kernel<<<grid, 128, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, N, T, Tp, PL, C, mode, rows_per_block);
-    TACO_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<<<ew_blocks((long long)N * Tp * C), EW_THREADS, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx,
-                                                                               N, T, Tp, PL, C, mode, relu_mask);
+    TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "bn_bwd: channel count %d must be a multiple of 4", C);
+    int tx, ty; lanes_2d(C / 4, tx, ty);
+    const int chunks = cdiv(Tp, ty * BNB_R);
+    dim3 block(tx, ty), grid(cdiv(C / 4, tx), (unsigned)(N * chunks));
+    if (mode == 1) {
+        bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
+        bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
+    } else {
+        bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
+        bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
+    }
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -277,10 +350,56 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
     for (long long r = r0; r < r1; r++) s += x[r * ld + c];
     atomicAdd(out + c, s);
 }
+// float4 variant: (tx channel lanes) x (ty row lanes); needs 16-byte aligned rows (ld % 4 == 0, ld >= 4*ceil(C/4))
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int C, int ld,
+                                                      int rows_per_block) {
+    const int tx = blockDim.x, ty = blockDim.y;
+    const int c = (blockIdx.x * tx + threadIdx.x) * 4;
+    const bool cok = c < C;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok) {
+        long long r = r0 + threadIdx.y;
+        for (; r + 3LL * ty < r1; r += 4LL * ty) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + ty) * ld + c));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(x + (r + 2LL * ty) * ld + c));
+            const float4 e = __ldg(reinterpret_cast<const float4*>(x + (r + 3LL * ty) * ld + c));
+            s.x += (a.x + b.x) + (d.x + e.x); s.y += (a.y + b.y) + (d.y + e.y);
+            s.z += (a.z + b.z) + (d.z + e.z); s.w += (a.w + b.w) + (d.w + e.w);
+        }
+        for (; r < r1; r += ty) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    __shared__ float4 red[256];
+    red[threadIdx.y * tx + threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && cok) {
+        for (int y = 1; y < ty; y++) { const float4 a = red[y * tx + threadIdx.x]; s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+        atomicAdd(out + c, s.x);
+        if (c + 1 < C) atomicAdd(out + c + 1, s.y);
+        if (c + 2 < C) atomicAdd(out + c + 2, s.z);
+        if (c + 3 < C) atomicAdd(out + c + 3, s.w);
+    }
+}
 int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s) {
-    const int rows_per_block = 128;
-    dim3 grid(cdiv(C, 128), (unsigned)cdiv64(M, rows_per_block));
-    colsum_kernel<<<grid, 128, 0, s>>>(x, out, M, C, ld, rows_per_block);
+    const int C4 = cdiv(C, 4);
+    if (ld % 4 == 0 && ld >= 4 * C4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        int tx, ty; lanes_2d(C4, tx, ty);
+        const int bx = cdiv(C4, tx);
+        long long by = cdiv64(148 * 8, bx);
+        long long rpb = cdiv64(M, by);
+        if (rpb < 4LL * ty) rpb = 4LL * ty;
+        rpb = cdiv64(rpb, ty) * ty;
+        dim3 block(tx, ty), grid(bx, (unsigned)cdiv64(M, rpb));
+        colsum4_kernel<<<grid, block, 0, s>>>(x, out, M, C, ld, (int)rpb);
+    } else {
+        const int rows_per_block = 128;
+        dim3 grid(cdiv(C, 128), (unsigned)cdiv64(M, rows_per_block));
+        colsum_kernel<<<grid, 128, 0, s>>>(x, out, M, C, ld, rows_per_block);
+    }
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -351,8 +470,27 @@ __global__ void unpad_kernel(float* __restrict__ dst, const float* __restrict__ 
         dst[i] = src[((long long)n * Tp + PL + t) * ld + c];
     }
 }
+// float4 rows: block = (tx float4 lanes) x (ty rows), grid-stride over rows
+__global__ void __launch_bounds__(256) unpad4_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int T, int Tp, int PL,
+                                                     int C4, long long ld) {
+    const int ty = blockDim.y;
+    for (int row = blockIdx.x * ty + threadIdx.y; row < rows; row += gridDim.x * ty) {
+        const int n = row / T, t = row - n * T;
+        const float* sp = src + ((long long)n * Tp + PL + t) * ld;
+        float* dp = dst + (long long)row * C4 * 4;
+        for (int c = threadIdx.x; c < C4; c += blockDim.x)
+            reinterpret_cast<float4*>(dp)[c] = __ldg(reinterpret_cast<const float4*>(sp) + c);
+    }
+}
 int launch_unpad(float* dst, const float* src, int N, int T, int Tp, int PL, int C, long long ld, cudaStream_t s) {
-    unpad_kernel<<<ew_blocks((long long)N * T * C), EW_THREADS, 0, s>>>(dst, src, N, T, Tp, PL, C, ld);
+    if (C % 4 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        int tx, ty; lanes_2d(C / 4, tx, ty);
+        const int rows = N * T;
+        int blocks = cdiv(rows, ty); if (blocks > 148 * 16) blocks = 148 * 16;
+        unpad4_kernel<<<blocks, dim3(tx, ty), 0, s>>>(dst, src, rows, T, Tp, PL, C / 4, ld);
+    } else {
+        unpad_kernel<<<ew_blocks((long long)N * T * C), EW_THREADS, 0, s>>>(dst, src, N, T, Tp, PL, C, ld);
+    }
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -376,43 +514,49 @@ int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaS
 // L1 loss + gradient.  out/target rows: out row (n,t) at out + (n*out_bs + t*out_ts), target at tgt + (n*T + t)*C.
 // scalars[0] += sum |d|*coeff*w ; scalars[1] += sum |d| (unweighted, all bins) ; scalars[2] += sum |d| over the priority band.
 // grad[(n,t),c] = sign(out - tgt) * coeff[n] * (w_all + w_band*[lo<=c<hi])     (pad rows of grad untouched)
-__global__ void l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
                                const float* __restrict__ tgt, const float* __restrict__ coeff,
                                float* __restrict__ grad, long long grad_bs, long long grad_ts,
                                int N, int T, int C, float w_all, float w_band, int lo, int hi, double* __restrict__ scalars) {
-    long long total = (long long)N * T * C;
+    // block = (tx column lanes) x (ty rows); rows (n,t) are strided over the grid, columns over tx: no per-element division
+    const int tx = blockDim.x, ty = blockDim.y, rows = N * T;
     float acc_w = 0.f, acc_all = 0.f, acc_band = 0.f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C); long long nt = i / C;
-        int t = (int)(nt % T), n = (int)(nt / T);
-        float o = out[n * out_bs + t * out_ts + c];
-        float d = o - tgt[i];
-        float cf = coeff ? coeff[n] : 1.f;
-        float a = fabsf(d);
-        bool band = (c >= lo && c < hi);
-        float w = w_all + (band ? w_band : 0.f);
-        acc_w += a * cf * w; acc_all += a; if (band) acc_band += a;
-        if (grad) {
-            float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-            grad[n * grad_bs + t * grad_ts + c] = sg * cf * w;
+    for (int row = blockIdx.x * ty + threadIdx.y; row < rows; row += gridDim.x * ty) {
+        const int n = row / T, t = row - n * T;
+        const float* op = out + n * out_bs + t * out_ts;
+        const float* tp = tgt + (long long)row * C;
+        float* gp = grad ? grad + n * grad_bs + t * grad_ts : nullptr;
+        const float cf = coeff ? __ldg(coeff + n) : 1.f;
+        float rw = 0.f;
+        for (int c = threadIdx.x; c < C; c += tx) {
+            const float d = op[c] - __ldg(tp + c);
+            const float a = fabsf(d);
+            const bool band = (c >= lo && c < hi);
+            const float w = w_all + (band ? w_band : 0.f);
+            rw = fmaf(a, w, rw); acc_all += a; if (band) acc_band += a;
+            if (gp) gp[c] = ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f)) * cf * w;
         }
+        acc_w = fmaf(rw, cf, acc_w);
     }
     acc_w = warp_sum(acc_w); acc_all = warp_sum(acc_all); acc_band = warp_sum(acc_band);
-    __shared__ float sh[3][EW_THREADS / 32];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ float sh[3][8];
+    const int tid = threadIdx.y * tx + threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (lane == 0) { sh[0][wid] = acc_w; sh[1][wid] = acc_all; sh[2][wid] = acc_band; }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (tid < 3) {
         double s = 0.0;
-        for (int w = 0; w < EW_THREADS / 32; w++) s += sh[threadIdx.x][w];
-        atomicAdd(scalars + threadIdx.x, s);
+        for (int w = 0; w < 8; w++) s += sh[tid][w];
+        atomicAdd(scalars + tid, s);
     }
 }
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
                    float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s) {
-    l1_loss_kernel<<<ew_blocks((long long)N * T * C, EW_THREADS, 148 * 8), EW_THREADS, 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, grad_bs, grad_ts,
-                                                                                         N, T, C, w_all, w_band, lo, hi, scalars);
+    int tx = 32; while (tx < C && tx < 256) tx <<= 1;
+    const int ty = 256 / tx;
+    int blocks = cdiv(N * T, ty); if (blocks > 148 * 8) blocks = 148 * 8;
+    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, grad_bs, grad_ts,
+                                                   N, T, C, w_all, w_band, lo, hi, scalars);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }

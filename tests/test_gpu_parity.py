@@ -375,3 +375,77 @@ def test_attention_variants_vs_oracle(tb, prec, att):
             assert dn > 0
             assert (got[k].cpu() - ref_g[k]).norm().item() / dn <= 5e-3, k
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_manual_attention_override_vs_oracle(tb, hp5, prec):
+    """is_manual_attention: alignments = manual[:, t, :] (rnn_wrappers.py:313-317; synthesizer.py:171-205), training and
+    free-running; the override also cuts the score/keys gradient path."""
+    named = tb.params.init_params(hp5, 1, seed=31, randomize_bn_state=True)
+    N, Ti, To = 3, 10, 20
+    Td = To // 5
+    b = _batch(N, Ti, To, [10, 6, 8], seed=15)
+    g = torch.Generator().manual_seed(8)
+    manual = torch.softmax(torch.randn(N, Td, Ti, generator=g) * 2.0, -1)
+    names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
+    ref = O.forward(leaf, hp5, b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"],
+                    manual_alignments=manual, speaker_mode="none")
+    ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp5)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    ref_g = {k: (gg if gg is not None else torch.zeros_like(named[k])) for k, gg in zip(names, gl)}
+    tol = TOL[prec]
+    eng = tb.Engine(hp5, 1, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"], manual_alignments=manual)
+    assert (out["alignments"].cpu() - manual.transpose(1, 2)).abs().max().item() <= 1e-6
+    for k in ("mel_outputs", "linear_outputs"):
+        assert (out[k].cpu() - ref[k].detach()).abs().max().item() <= tol["out"], k
+    eng.backward()
+    got = eng.named_gradients()
+    cos, na, nb = _cosine(got, ref_g, sorted(ref_g))
+    assert cos >= tol["cos"] and abs(na - nb) <= tol["gn"] * nb
+    for k in ("attention/v", "attention/query_kernel", "attention/memory_kernel"):   # no gradient reaches the score path
+        assert ref_g[k].abs().max().item() == 0.0 and got[k].abs().max().item() == 0.0, k
+    with torch.no_grad():
+        inf = O.forward(named, hp5, b["inputs"], b["input_lengths"], 1, None, None, None, manual_alignments=manual,
+                        max_iters=Td, speaker_mode="none")
+    out = eng.forward(b["inputs"], b["input_lengths"], None, decoder_steps=Td, manual_alignments=manual)
+    for k in ("mel_outputs", "linear_outputs"):
+        assert (out[k].cpu() - inf[k]).abs().max().item() <= (2e-3 if prec == "fp32" else 6e-2), k
+    eng.close()
+
+
+def test_prioritize_loss_band_vs_oracle(tb):
+    """prioritize_loss (tacotron.py:283-295): 0.5*mean|.| over all bins + 0.5*mean|.| over the 165 Hz..5 kHz band."""
+    hp = tb.hparams.override(reduction_factor=5, prioritize_loss=True)
+    named = tb.params.init_params(hp, 1, seed=37)
+    b = _batch(3, 9, 10, [9, 4, 7], seed=17)
+    ref, ref_g, names = _oracle_grads(named, hp, b, 1, None, "none")
+    ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    eng = tb.Engine(hp, 1, precision="fp32", named_params=named)
+    eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    eng.backward()
+    sc = eng.scalars()
+    for k in ("loss", "mel_loss", "linear_loss", "loss_without_coeff"):
+        assert abs(sc[k] - float(ls[k])) <= 1e-5, k
+    cos, na, nb = _cosine(eng.named_gradients(), ref_g, sorted(ref_g))
+    assert cos >= 0.99999 and abs(na - nb) <= 1e-4 * nb
+    dn = ref_g["linear/kernel"].norm().item()
+    assert (eng.named_gradients()["linear/kernel"].cpu() - ref_g["linear/kernel"]).norm().item() / dn <= 2e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("mode,fresh", [(0, True), (0, False), (1, True)])
+def test_learning_rate_schedules(tb, hp5, golden_setup, mode, fresh):
+    """tacotron.py:305-326: mode 0 Noam-style warm-up (4 000 steps from scratch, 40 000 on a warm start), mode 1 0.95^(step/3000)."""
+    named, b = golden_setup
+    hp = tb.hparams.override(reduction_factor=5, decay_learning_rate_mode=mode)
+    eng = tb.Engine(hp, 1, precision="fp32", named_params=named)
+    for step in (0, 3999, 50000):
+        eng.global_step = step
+        eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+        eng.backward()
+        eng.optimizer_step(is_randomly_initialized=fresh)
+        want = O.learning_rate(hp, step, fresh)
+        assert abs(eng.scalars()["learning_rate"] - want) <= 1e-6 * want, (step, want)
+    eng.close()
