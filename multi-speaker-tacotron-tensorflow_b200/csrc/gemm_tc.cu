@@ -112,9 +112,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
 
 template <int ACT> __device__ __forceinline__ float act_ct(float x) {
     if (ACT == ACT_RELU) return fmaxf(x, 0.f);
-    if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
-    if (ACT == ACT_TANH) return tanhf(x);
-    if (ACT == ACT_SOFTSIGN) return x / (1.0f + fabsf(x));
+    // MUFU-based forms: this kernel only runs in TF32 mode, whose stated tolerance covers approximate transcendentals
+    if (ACT == ACT_SIGMOID) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x)); return fmaf(0.5f, t, 0.5f); }
+    if (ACT == ACT_TANH) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
+    if (ACT == ACT_SOFTSIGN) return __fdividef(x, 1.0f + fabsf(x));
     return x;
 }
 
@@ -215,30 +216,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int it = 0; it < nkt; it++) {
-                const int stage = it % TC_STAGES, round = it / TC_STAGES;
+        // lane 0 arms the barrier; the boxes of a stage (one per K-major operand, four per MN-major operand) are then
+        // issued by different lanes so that a weight-gradient stage (8 boxes) does not serialise on one thread
+        for (int it = 0; it < nkt; it++) {
+            const int stage = it % TC_STAGES, round = it / TC_STAGES;
+            if (lane == 0) {
                 if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
                 mbar_expect_tx(&full_bar[stage], 2 * TC_TILE_BYTES);
-                const int k0 = (kt0 + it) * TC_BK;
-                uint8_t* a = sA + stage * TC_TILE_BYTES;
-                uint8_t* b = sB + stage * TC_TILE_BYTES;
+            }
+            __syncwarp();
+            const int k0 = (kt0 + it) * TC_BK;
+            uint8_t* a = sA + stage * TC_TILE_BYTES;
+            uint8_t* b = sB + stage * TC_TILE_BYTES;
+            if (lane < 4) {
                 if (!p.a_mn_major) {
-                    if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
-                    else tma_load_2d(a, &mapA, k0, m0, &full_bar[stage]);
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const int mm = m0 + g * 32;
-                        if (p.a_tap) tma_load_2d(a + g * 4096, &mapA, mm % p.a_ctap, k0 + mm / p.a_ctap, &full_bar[stage]);
-                        else tma_load_2d(a + g * 4096, &mapA, mm, k0, &full_bar[stage]);
+                    if (lane == 0) {
+                        if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
+                        else tma_load_2d(a, &mapA, k0, m0, &full_bar[stage]);
                     }
-                }
-                if (!p.b_mn_major) {
-                    tma_load_2d(b, &mapB, k0, n0, &full_bar[stage]);
                 } else {
-#pragma unroll
-                    for (int g = 0; g < 4; g++) tma_load_2d(b + g * 4096, &mapB, n0 + g * 32, k0, &full_bar[stage]);
+                    const int g = lane, mm = m0 + g * 32;
+                    if (p.a_tap) tma_load_2d(a + g * 4096, &mapA, mm % p.a_ctap, k0 + mm / p.a_ctap, &full_bar[stage]);
+                    else tma_load_2d(a + g * 4096, &mapA, mm, k0, &full_bar[stage]);
+                }
+            } else if (lane < 8) {
+                if (!p.b_mn_major) {
+                    if (lane == 4) tma_load_2d(b, &mapB, k0, n0, &full_bar[stage]);
+                } else {
+                    const int g = lane - 4;
+                    tma_load_2d(b + g * 4096, &mapB, n0 + g * 32, k0, &full_bar[stage]);
                 }
             }
         }
@@ -430,8 +436,21 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     p.remap_period = g.remap_period; p.remap_outer = g.remap_outer; p.remap_inner = g.remap_inner;
     p.colsum = g.colsum; p.colsumsq = g.colsumsq;
     const int ktiles = cdiv(g.K, TC_BK);
-    p.split_k = g.split_k < ktiles ? g.split_k : ktiles;
-    if (p.split_k < 1) p.split_k = 1;
+    const int tiles = cdiv(g.M, TC_BM) * cdiv(g.N, TC_BN);
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev)); TACO_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    // A caller that allows K splitting (split_k > 1: C is accumulated atomically) gets the split that balances whole waves
+    // of CTAs (two resident per SM): waves x (k-blocks per CTA + a fixed per-CTA cost in k-block units).
+    p.split_k = 1;
+    if (g.split_k > 1) {
+        double best = 1e30;
+        for (int sp = 1; sp <= 64 && sp <= ktiles; sp++) {
+            const int per = cdiv(ktiles, sp);
+            if (sp > 1 && per < 8) break;
+            const double cost = (double)cdiv(tiles * sp, 2 * n_sm) * (per + 10.0);
+            if (cost < best - 1e-9) { best = cost; p.split_k = sp; }
+        }
+    }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     p.vecC = g.remap_period > 0 ? (al16(g.C) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al16(g.C) && g.ldc % 4 == 0);
     dim3 grid(cdiv(g.M, TC_BM) * cdiv(g.N, TC_BN), p.split_k);

@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- optional per-class device timing (CUDA events on the launching stream; used by bench.py's roofline leg) ----
 static bool g_prof_on = false;
-struct ProfSpan { cudaEvent_t a, b; int cls; };
+struct ProfSpan { cudaEvent_t a, b; int cls; int tag[4]; };
 static std::vector<ProfSpan> g_prof_spans;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
@@ -30,11 +30,12 @@ struct ProfScope {
     cudaStream_t s; int idx = -1;
     ProfScope(int cls, cudaStream_t st) : s(st) {
         if (!g_prof_on) return;
-        ProfSpan sp{prof_event(), prof_event(), cls};
+        ProfSpan sp{prof_event(), prof_event(), cls, {0, 0, 0, 0}};
         cudaEventRecord(sp.a, s);
         g_prof_spans.push_back(sp); idx = (int)g_prof_spans.size() - 1;
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof_spans[idx].b, s); }
+    void tag(int a, int b, int c, int d) { if (idx >= 0) { int* t = g_prof_spans[idx].tag; t[0] = a; t[1] = b; t[2] = c; t[3] = d; } }
 };
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s) { ProfScope p(1, s); return bwd ? launch_gru_bwd(a, s) : launch_gru_fwd(a, s); }
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s) { ProfScope p(2, s); return bwd ? launch_att_bwd(a, s) : launch_att_fwd(a, s); }
@@ -61,6 +62,7 @@ static int aux_init() {
 
 int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s) {
     ProfScope prof_scope(0, s);
+    prof_scope.tag(d[0].M, d[0].N, d[0].K, n_problems);
     if (precision == TACO_PREC_FP32) return launch_gemm_simt(d, n_problems, s);
     std::vector<taco_gemm_desc> rest;
     std::vector<int> tc;
@@ -693,6 +695,20 @@ int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]) {
         }
     }
     return TACO_OK;
+}
+
+// debug: per-span listing of the last profile window, "cls ms tag0 tag1 tag2 tag3" per line (GEMM spans: M N K n_problems)
+int taco_debug_profile_spans(char* buf, int64_t cap) {
+    std::string out;
+    for (auto& sp : g_prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) continue;
+        char line[128];
+        snprintf(line, sizeof line, "%d %.4f %d %d %d %d\n", sp.cls, ms, sp.tag[0], sp.tag[1], sp.tag[2], sp.tag[3]);
+        out += line;
+    }
+    if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", out.c_str()); }
+    return (int)out.size();
 }
 
 int taco_gemm(const taco_gemm_desc* d, int32_t n_problems, int32_t precision, void* stream) {
