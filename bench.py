@@ -29,6 +29,8 @@ CFG = dict(N=32, T_in=128, T_out=800, num_mels=80, num_freq=1025, r=5)
 ALGO_BYTES_PER_STEP = 486.6e6
 # algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
 ALGO_FLOPS_PER_STEP = 784.8e9
+# ncu (profiles/r1_step_metrics_v4.summary.txt): 4975.3 MB of DRAM traffic over the 203 gemm_tc_kernel launches of one step
+GEMM_DRAM_BYTES_PER_LAUNCH = 4975.3e6 / 203
 
 
 def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
@@ -164,6 +166,7 @@ def run_ours(args):
         eng.train_step(dev, allreduce=allreduce)
     eng.lib.taco_profile(0, prof_ms, prof_n)
     gemm_ms = prof_ms[0] / PROF_STEPS
+    gemm_flops = prof_ms[3] * 1e9 / PROF_STEPS          # sum of 2*M*N*K over the step's GEMM problems, counted at launch
     barrier()
 
     # ---- end to end through the public API: pinned host inputs -> device every step, loss read back every step ----
@@ -218,23 +221,108 @@ def run_ours(args):
             "clocks": clocks,
             # dominant kernel class by device time: the tcgen05 GEMM (all GEMM-shaped work of the step)
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed; fp32 SIMT in fp32 mode)",
-                         "achieved": ALGO_FLOPS_PER_STEP / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                         "unit": "TFLOP/s", "frac": ALGO_FLOPS_PER_STEP / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                         "traffic": None, "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
-                         "launches_per_step": int(prof_n[0] // PROF_STEPS), "ms_per_step": gemm_ms,
-                         "algorithmic_flops_per_step": ALGO_FLOPS_PER_STEP,
-                         "note": "algorithmic FLOPs of the step (784.8 GFLOP, SURVEY.md 8d) / summed GEMM device time per step, CUDA events around every GEMM launch"},
+                         "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                         "unit": "TFLOP/s", "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v4.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
+                         "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
+                         "launches_per_step": int(prof_n[0] // PROF_STEPS), "problems_per_step": int(prof_n[3] // PROF_STEPS), "ms_per_step": gemm_ms,
+                         "algorithmic_flops_per_step": gemm_flops, "algorithmic_flops_per_launch": gemm_flops / max(1, prof_n[3] // PROF_STEPS),
+                         "avg_launch_us": 1e3 * gemm_ms / max(1, prof_n[3] // PROF_STEPS),
+                         "note": "algorithmic FLOPs (2MNK summed over the GEMM problems of one step, counted where they are launched) / summed GEMM device time per step; CUDA events around every GEMM call on its launching stream, taken in a serialised window (the two-stream backward schedule is off while profiling)"},
             "recurrence_ms_per_step": {"gru_fwd_bwd": prof_ms[1] / PROF_STEPS, "attention_fwd_bwd": prof_ms[2] / PROF_STEPS,
                                        "note": "serial chains: 2 656 dependent recurrence steps per training step (latency bound)"},
             "roofline_step_hbm": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                                   "note": "whole-step algorithmic bytes (486.6 MB, SURVEY.md 8d) / step time"},
             "loss": sc["loss"],
         }
+        if args.synth and world == 1:
+            eng.close()
+            line["synth_rtf"] = synth_rtf_ours(hp, local, args.precision)
         if args.cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+            if args.synth and world == 1:
+                line["cpu_baseline"]["synth_rtf"] = synth_rtf_cpu()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+SYNTH = dict(N=1, T_in=128, steps=200, gl_iters=60)      # config C4: 200 free-running steps -> 1000 frames
+
+
+def synth_inputs():
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    tok = torch.randint(2, 80, (SYNTH["N"], SYNTH["T_in"]), generator=g, dtype=torch.int32)
+    tok[:, -1] = 1
+    L = torch.full((SYNTH["N"],), SYNTH["T_in"], dtype=torch.int32)
+    phase = torch.rand(SYNTH["steps"] * CFG["r"], CFG["num_freq"], generator=g)
+    return tok, L, phase
+
+
+def synth_rtf_ours(hp, device, precision, reps=5):
+    """Second half of BASELINE.json's metric: real-time factor of synthesis (C4): tokens -> free-running decoder (200 steps,
+    1000 mel frames) -> post-net -> linear spectrogram -> 60-iteration Griffin-Lim -> 299 700 samples (12.49 s at 24 kHz).
+    Timed through the public API with the tokens on the host and the waveform copied back (synthesizer.py:166-167,264)."""
+    import torch
+    from importlib import import_module
+    Engine = import_module("multi-speaker-tacotron-tensorflow_b200.engine").Engine
+    GriffinLim = import_module("multi-speaker-tacotron-tensorflow_b200.audio").GriffinLim
+    eng = Engine(hp, 1, precision=precision, device=device, seed=4321, randomize_bn_state=True)
+    gl = GriffinLim(hp, max_frames=SYNTH["steps"] * CFG["r"], device=device)
+    tok, L, phase = synth_inputs()
+    tok, L = tok.pin_memory(), L.pin_memory()
+    phase = phase.to(eng.dev)
+    n0 = eng.launch_count()
+
+    def once():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t0 = time.perf_counter()
+        e[0].record()
+        out = eng.forward(tok, L, decoder_steps=SYNTH["steps"])
+        e[1].record()
+        wav = gl.inv_spectrogram(out["linear_outputs"][0], phase, n_iters=SYNTH["gl_iters"])
+        e[2].record()
+        host = wav.cpu()
+        wall = time.perf_counter() - t0
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), wall, host
+
+    for _ in range(2):
+        once()
+    launches_per_call = (eng.launch_count() - n0) // 2
+    rows = [once() for _ in range(reps)]
+    host = rows[-1][3]
+    audio_s = host.numel() / float(hp.sample_rate)
+    med = lambda xs: sorted(xs)[len(xs) // 2]
+    fwd, glt, wall = med([r[0] for r in rows]), med([r[1] for r in rows]), med([r[2] for r in rows])
+    eng.close(); gl.close()
+    return {"workload": "C4: batch=1, text_len=128, 200 free-running decoder steps -> 1000 frames, post-net, 60-iter Griffin-Lim",
+            "rtf": wall / audio_s, "audio_s": audio_s, "samples": int(host.numel()), "ms_total_e2e": wall * 1e3,
+            "ms_forward": fwd, "ms_griffin_lim": glt, "launches_per_call": int(launches_per_call), "reps": reps,
+            "finite": bool(torch.isfinite(host).all()), "higher_is_better": False,
+            "note": "rtf = wall time (host tokens in, host waveform out) / audio duration; lower is better"}
+
+
+def synth_rtf_cpu(threads: int = 0):
+    """The same C4 synthesis on the host cores with the oracle restatement (torch-CPU forward + numpy Griffin-Lim)."""
+    import torch
+    import tacotron_b200 as tb
+    from oracle import tacotron_oracle as O
+    from oracle import griffin_lim_oracle as G
+    n = threads or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    hp = tb.hparams.override(reduction_factor=CFG["r"])
+    P = tb.params.init_params(hp, 1, seed=4321, randomize_bn_state=True)
+    tok, L, phase = synth_inputs()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.forward(P, hp, tok, L, 1, None, max_iters=SYNTH["steps"], speaker_mode="none")
+    t1 = time.perf_counter()
+    wav = G.inv_spectrogram(out["linear_outputs"][0].numpy(), phase.numpy(), n_iters=SYNTH["gl_iters"])
+    t2 = time.perf_counter()
+    audio_s = len(wav) / float(hp.sample_rate)
+    return {"rtf": (t2 - t0) / audio_s, "s_forward": t1 - t0, "s_griffin_lim": t2 - t1, "audio_s": audio_s, "cores": n, "kind": "port",
+            "sample": "one full C4 synthesis (oracle forward on torch-CPU + numpy/pocketfft Griffin-Lim, 60 iterations)"}
 
 
 def cpu_baseline(sample_steps: int = 1, threads: int = 0):
@@ -288,6 +376,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-synth", dest="synth", action="store_false", help="skip the C4 synthesis real-time-factor leg (N=1 only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

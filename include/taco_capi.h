@@ -36,7 +36,7 @@ extern "C" {
 #define TACO_ENOMEM   (-4)
 #define TACO_ESTATE   (-5)
 
-#define TACO_ABI_VERSION 1
+#define TACO_ABI_VERSION 2
 
 /* attention_type (reference: models/tacotron.py:132-152; only these three are reachable) */
 #define TACO_ATT_BAH_MON  0
@@ -200,6 +200,11 @@ typedef struct taco_gemm_desc {
     int64_t remap_outer, remap_inner;
     double* colsum; double* colsumsq; /* optional per-column statistics of the stored values over unmasked rows */
     int32_t split_k;               /* >=1 */
+    /* Optional per-k-tile tap table (tensor-core path only, transA = 0, K % 32 == 0): device array of K/32 (col, row)
+     * int32 pairs; k-tile i of A row m is A[(m + row_i) * lda + col_i .. + 32).  Lets one GEMM walk several convolutions
+     * of different widths that read column blocks of one activation matrix (the conv-bank data gradient).  tap_rows =
+     * number of rows addressable from A (rows beyond it read as zero). */
+    const int32_t* tap_table; int32_t tap_rows;
 } taco_gemm_desc;
 int taco_gemm(const taco_gemm_desc* d, int32_t n_problems, int32_t precision, void* stream);
 

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence, Tuple
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtaco_b200.so")
 
-TACO_ABI_VERSION = 1
+TACO_ABI_VERSION = 2
 ATT_TYPES = {"bah_mon": 0, "bah": 1, "bah_norm": 2}
 SPK_MODES = {"none": 0, "simple": 1, "deepvoice": 2, "deepvoice_table": 3}
 PREC = {"fp32": 0, "tf32": 1}
@@ -63,6 +63,7 @@ class TacoGemmDesc(C.Structure):
         ("mask_period", C.c_int32), ("mask_lo", C.c_int32), ("mask_hi", C.c_int32),
         ("remap_period", C.c_int32), ("remap_outer", C.c_int64), ("remap_inner", C.c_int64),
         ("colsum", C.c_void_p), ("colsumsq", C.c_void_p), ("split_k", C.c_int32),
+        ("tap_table", C.c_void_p), ("tap_rows", C.c_int32),
     ]
 
 

@@ -323,19 +323,30 @@ int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y
     return TACO_OK;
 }
 // backward: dHpre = dy*T*[H>0]; dTpre = dy*(H-x)*T*(1-T); dx_direct = dy*(1-T)
+// The two pre-activation gradients are written side by side into one [rows, 2C] matrix (dHpre | dTpre) so that the data
+// gradient dx += dHpre.WH^T + dTpre.WT^T is ONE GEMM with K = 2C against the packed [C, 2C] weight (model_cbhg.cu).
 __global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ H, const float* __restrict__ Tg,
-                                   const float* __restrict__ x, float* __restrict__ dHpre, float* __restrict__ dTpre,
-                                   float* __restrict__ dx, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float d = dy[i], h = H[i], t = Tg[i], v = x[i];
-        dHpre[i] = (h > 0.f) ? d * t : 0.f;
-        dTpre[i] = d * (h - v) * t * (1.f - t);
-        dx[i] = d * (1.f - t);
+                                   const float* __restrict__ x, float* __restrict__ dHT, float* __restrict__ dx, long long n4, int c4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 d = reinterpret_cast<const float4*>(dy)[i], h = reinterpret_cast<const float4*>(H)[i];
+        const float4 t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
+        const long long row = i / c4; const int cq = (int)(i - row * c4);
+        float4 a, b, o;
+        a.x = (h.x > 0.f) ? d.x * t.x : 0.f; a.y = (h.y > 0.f) ? d.y * t.y : 0.f;
+        a.z = (h.z > 0.f) ? d.z * t.z : 0.f; a.w = (h.w > 0.f) ? d.w * t.w : 0.f;
+        b.x = d.x * (h.x - v.x) * t.x * (1.f - t.x); b.y = d.y * (h.y - v.y) * t.y * (1.f - t.y);
+        b.z = d.z * (h.z - v.z) * t.z * (1.f - t.z); b.w = d.w * (h.w - v.w) * t.w * (1.f - t.w);
+        o.x = d.x * (1.f - t.x); o.y = d.y * (1.f - t.y); o.z = d.z * (1.f - t.z); o.w = d.w * (1.f - t.w);
+        float4* out = reinterpret_cast<float4*>(dHT) + row * (2 * c4) + cq;
+        out[0] = a; out[c4] = b;
+        reinterpret_cast<float4*>(dx)[i] = o;
     }
 }
-int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHpre, float* dTpre, float* dx,
-                       long long n, cudaStream_t s) {
-    highway_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHpre, dTpre, dx, n);
+int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT, float* dx,
+                       long long rows, int C, cudaStream_t s) {
+    TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "highway_bwd: width %d must be a multiple of 4", C);
+    const long long n4 = rows * (C / 4);
+    highway_bwd_kernel<<<ew_blocks(n4), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHT, dx, n4, C / 4);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }

@@ -304,6 +304,7 @@ int launch_gemm_simt(const taco_gemm_desc* d, int n, cudaStream_t s) {
             const taco_gemm_desc& g = d[done + cnt];
             TACO_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, TACO_ESHAPE, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
             TACO_REQUIRE(g.split_k >= 1, TACO_EINVAL, "gemm: split_k must be >= 1");
+            TACO_REQUIRE(g.tap_table == nullptr, TACO_EINVAL, "gemm: tap tables are only served by the tensor-core kernel (TF32 mode, aligned operands)");
             TACO_REQUIRE(!((g.split_k > 1 || g.accumulate == 2) && (g.act != 0 || g.colsum != nullptr)),
                          TACO_EINVAL, "gemm: atomic accumulation cannot carry an activation or column statistics");
             GemmP& p = b.p[cnt];

@@ -29,6 +29,7 @@ struct TcParams {
     int M, N, K, ldc;
     int a_mn_major, b_mn_major;          // 1: MN-major (four boxes), 0: K-major (one box)
     int a_tap, a_ctap;                   // strided-tap addressing for A (lda > ctap)
+    const int2* tap_table;               // optional per-k-tile (column, row offset) of A (K-major A only)
     float alpha; int accumulate;
     const float* bias; int act;
     int mask_period, mask_lo, mask_hi;
@@ -231,7 +232,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane < 4) {
                 if (!p.a_mn_major) {
                     if (lane == 0) {
-                        if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
+                        if (p.tap_table) { const int2 tc = __ldg(p.tap_table + kt0 + it); tma_load_2d(a, &mapA, tc.x, m0 + tc.y, &full_bar[stage]); }
+                        else if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
                         else tma_load_2d(a, &mapA, k0, m0, &full_bar[stage]);
                     }
                 } else {
@@ -395,6 +397,7 @@ bool gemm_tc_eligible(const taco_gemm_desc& g) {
     if (g.lda % 4 != 0 || g.ldb % 4 != 0) return false;
     const bool tap = g.ctap > 0 && (g.lda != g.ctap || g.ctap % 32 == 0);
     if (tap && g.ctap % 32 != 0) return false;
+    if (g.tap_table && (g.transA || g.K % TC_BK != 0 || g.ctap != 0 || (reinterpret_cast<uintptr_t>(g.tap_table) & 7u) != 0)) return false;
     if ((long long)g.M * g.N * g.K < (1ll << 24)) return false;      // small problems: launch-bound either way; the grouped fp32 kernel batches them
     return true;
 }
@@ -416,7 +419,10 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     const bool overlap = g.ctap > 0 && !tap;
     const int ntaps = g.ctap > 0 ? ((g.transA ? g.M : g.K) + g.ctap - 1) / g.ctap : 1;
     CUtensorMap mapA, mapB;
-    if (!g.transA) {
+    if (g.tap_table) {
+        // table-driven taps: the map spans whole rows of the activation matrix; the producer supplies (column, row) per k-tile
+        TACO_TRY(make_map(&mapA, A, (uint64_t)g.lda, (uint64_t)g.tap_rows, (uint64_t)g.lda, TC_BK, TC_BM, false));
+    } else if (!g.transA) {
         // K-major A: box {32 k, 128 m}
         if (tap) TACO_TRY(make_map(&mapA, A, (uint64_t)g.ctap, (uint64_t)g.M + ntaps - 1, (uint64_t)g.lda, TC_BK, TC_BM, false));
         else TACO_TRY(make_map(&mapA, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TC_BK, TC_BM, false, overlap));
@@ -431,6 +437,7 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     p.C = g.C; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc;
     p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1;
     p.a_tap = tap ? 1 : 0; p.a_ctap = tap ? g.ctap : 1;
+    p.tap_table = reinterpret_cast<const int2*>(g.tap_table);
     p.alpha = g.alpha; p.accumulate = g.accumulate; p.bias = g.bias; p.act = g.act;
     p.mask_period = g.mask_period; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
     p.remap_period = g.remap_period; p.remap_outer = g.remap_outer; p.remap_inner = g.remap_inner;

@@ -26,8 +26,8 @@ int launch_bn_apply(const float* x, const float* mean, const float* rstd, const 
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s);
 int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s);
-int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHpre, float* dTpre, float* dx,
-                       long long n, cudaStream_t s);
+int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT /*[rows,2C]: dHpre | dTpre*/, float* dx,
+                       long long rows, int C, cudaStream_t s);
 int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);

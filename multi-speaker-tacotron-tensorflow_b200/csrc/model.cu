@@ -3,6 +3,7 @@
 #include "model.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace taco {
 
@@ -19,7 +20,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- optional per-class device timing (CUDA events on the launching stream; used by bench.py's roofline leg) ----
 static bool g_prof_on = false;
-struct ProfSpan { cudaEvent_t a, b; int cls; int tag[4]; };
+struct ProfSpan { cudaEvent_t a, b; int cls; int tag[4]; double gflop; const char* name; cudaStream_t stream; };
 static std::vector<ProfSpan> g_prof_spans;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
@@ -30,39 +31,85 @@ struct ProfScope {
     cudaStream_t s; int idx = -1;
     ProfScope(int cls, cudaStream_t st) : s(st) {
         if (!g_prof_on) return;
-        ProfSpan sp{prof_event(), prof_event(), cls, {0, 0, 0, 0}};
+        ProfSpan sp{prof_event(), prof_event(), cls, {0, 0, 0, 0}, 0.0, "", st};
         cudaEventRecord(sp.a, s);
         g_prof_spans.push_back(sp); idx = (int)g_prof_spans.size() - 1;
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof_spans[idx].b, s); }
     void tag(int a, int b, int c, int d) { if (idx >= 0) { int* t = g_prof_spans[idx].tag; t[0] = a; t[1] = b; t[2] = c; t[3] = d; } }
+    void work(double gflop) { if (idx >= 0) g_prof_spans[idx].gflop = gflop; }
 };
+// stage marker for the timeline listing (taco_debug_profile_spans): class 9, zero length
+void prof_mark(const char* name, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfSpan sp{prof_event(), nullptr, 9, {0, 0, 0, 0}, 0.0, name, s};
+    cudaEventRecord(sp.a, s);
+    sp.b = sp.a;
+    g_prof_spans.push_back(sp);
+}
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s) { ProfScope p(1, s); return bwd ? launch_gru_bwd(a, s) : launch_gru_fwd(a, s); }
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s) { ProfScope p(2, s); return bwd ? launch_att_bwd(a, s) : launch_att_fwd(a, s); }
+
+// ---- stream scheduler --------------------------------------------------------------------------------------
+// The backward pass has one long dependent chain (loss -> post-net BPTT -> decoder BPTT -> encoder BPTT) whose recurrence
+// kernels occupy at most 64 of the 148 SMs, while every weight / bias gradient is a leaf of the dependency graph.  So
+// backward runs on two internal streams: `crit` (highest priority) carries the chain, `side` (lowest priority) the
+// leaves; each leaf is forked behind the producer of its operands (fork_side) and all of them are joined once at the end
+// of taco_backward.  Priorities make the block scheduler hand freed SMs to the chain first, so leaves only fill idle SMs.
+// TACO_OVERLAP=0 (or an active taco_profile window, whose per-launch times must not overlap) runs everything in order.
+static constexpr int kAuxStreams = 4;
+struct StreamSet {
+    cudaStream_t aux[kAuxStreams]; cudaEvent_t fork, join[kAuxStreams];
+};
+static StreamSet g_set[2];                 // 0: chain (high priority), 1: leaves (low priority)
+static cudaStream_t g_crit = nullptr, g_side = nullptr;
+static cudaEvent_t g_ev_in, g_ev_out, g_ev_fork, g_ev_side, g_ev_prep;
+static bool g_sched_ready = false;
+static int g_overlap = -1;
+static bool g_prof_keep_overlap = false;     // TACO_PROF_OVERLAP=1: timeline of the real two-stream schedule (tools/timeline.py)
+static int sched_init() {
+    if (g_sched_ready) return TACO_OK;
+    int lo = 0, hi = 0;
+    TACO_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically greatest)
+    for (int k = 0; k < 2; k++) {
+        for (int i = 0; i < kAuxStreams; i++) {
+            TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_set[k].aux[i], cudaStreamNonBlocking, k == 0 ? hi : lo));
+            TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_set[k].join[i], cudaEventDisableTiming));
+        }
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_set[k].fork, cudaEventDisableTiming));
+    }
+    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_crit, cudaStreamNonBlocking, hi));
+    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, lo));
+    for (cudaEvent_t* e : {&g_ev_in, &g_ev_out, &g_ev_fork, &g_ev_side, &g_ev_prep}) TACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    const char* env = getenv("TACO_OVERLAP");
+    g_overlap = (env && env[0] == '0') ? 0 : 1;
+    const char* env2 = getenv("TACO_PROF_OVERLAP");
+    g_prof_keep_overlap = (env2 && env2[0] == '1');
+    g_sched_ready = true;
+    return TACO_OK;
+}
+static bool overlap_on() { return g_sched_ready && g_overlap == 1 && (!g_prof_on || g_prof_keep_overlap); }
+
+// Stream for leaf work whose operands were produced by what is already enqueued on `main`.
+cudaStream_t fork_side(cudaStream_t main) {
+    if (!overlap_on() || main != g_crit) return main;
+    if (cudaEventRecord(g_ev_fork, main) != cudaSuccess || cudaStreamWaitEvent(g_side, g_ev_fork, 0) != cudaSuccess) return main;
+    return g_side;
+}
 
 // Route each problem: tcgen05/TMA kernel in TF32 mode when its operands satisfy TMA's alignment rules, otherwise
 // (and always in FP32 mode) the exact fp32 SIMT kernel.
 // Problems of one call are independent (or accumulate atomically), so the tensor-core launches are spread over a few
 // auxiliary streams (event fork / join on the caller's stream): the 36-tile encoder GEMMs and the conv-bank members
 // then overlap instead of running one under-filled grid after another.
-static constexpr int kAuxStreams = 4;
-static cudaStream_t g_aux[kAuxStreams];
-static cudaEvent_t g_fork, g_join[kAuxStreams];
-static bool g_aux_ready = false;
-static int aux_init() {
-    if (g_aux_ready) return TACO_OK;
-    for (int i = 0; i < kAuxStreams; i++) {
-        TACO_CHECK_CUDA(cudaStreamCreateWithFlags(&g_aux[i], cudaStreamNonBlocking));
-        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
-    }
-    TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    g_aux_ready = true;
-    return TACO_OK;
-}
-
 int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStream_t s) {
     ProfScope prof_scope(0, s);
     prof_scope.tag(d[0].M, d[0].N, d[0].K, n_problems);
+    if (g_prof_on) {
+        double fl = 0.0;
+        for (int i = 0; i < n_problems; i++) fl += 2.0 * d[i].M * d[i].N * d[i].K;
+        prof_scope.work(fl * 1e-9);
+    }
     if (precision == TACO_PREC_FP32) return launch_gemm_simt(d, n_problems, s);
     std::vector<taco_gemm_desc> rest;
     std::vector<int> tc;
@@ -70,22 +117,23 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
         if (gemm_tc_eligible(d[i])) tc.push_back(i); else rest.push_back(d[i]);
     }
     const bool fan_out = tc.size() >= 2;
+    TACO_TRY(sched_init());
+    StreamSet& set = g_set[(s == g_side) ? 1 : 0];
     if (fan_out) {
-        TACO_TRY(aux_init());
-        TACO_CHECK_CUDA(cudaEventRecord(g_fork, s));
-        for (int i = 0; i < kAuxStreams; i++) TACO_CHECK_CUDA(cudaStreamWaitEvent(g_aux[i], g_fork, 0));
+        TACO_CHECK_CUDA(cudaEventRecord(set.fork, s));
+        for (int i = 0; i < kAuxStreams; i++) TACO_CHECK_CUDA(cudaStreamWaitEvent(set.aux[i], set.fork, 0));
     }
     int rc_all = TACO_OK;
     for (size_t k = 0; k < tc.size(); k++) {
-        cudaStream_t st = fan_out ? g_aux[k % kAuxStreams] : s;
+        cudaStream_t st = fan_out ? set.aux[k % kAuxStreams] : s;
         int rc = launch_gemm_tc(d[tc[k]], st);
         if (rc == TACO_ENOTSUP) rest.push_back(d[tc[k]]);
         else if (rc != TACO_OK && rc_all == TACO_OK) rc_all = rc;
     }
     if (fan_out) {
         for (int i = 0; i < kAuxStreams; i++) {
-            TACO_CHECK_CUDA(cudaEventRecord(g_join[i], g_aux[i]));
-            TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_join[i], 0));
+            TACO_CHECK_CUDA(cudaEventRecord(set.join[i], set.aux[i]));
+            TACO_CHECK_CUDA(cudaStreamWaitEvent(s, set.join[i], 0));
         }
     }
     if (rc_all != TACO_OK) return rc_all;
@@ -179,7 +227,10 @@ void Model::plan(const Shape& s) {
             add(p + "d_rnn_out", {(int64_t)g.N * g.T, 2 * H});
             add(p + "dgx", {rows, 6 * H});
             add(p + "dgx_dense", {2, (int64_t)g.N * g.T, 3 * H});
-            add(p + "d_hwA", {rows, H}); add(p + "d_hwB", {rows, H}); add(p + "d_Hpre", {rows, H}); add(p + "d_Tpre", {rows, H});
+            add(p + "d_hwA", {rows, H}); add(p + "d_hwB", {rows, H});
+            // per layer: (dHpre | dTpre) side by side and the packed [H, 2H] weight their shared data gradient uses
+            for (int i = 1; i <= g.depth; i++) { add(p + "d_HT_" + std::to_string(i), {rows, 2 * H}); add(p + "hw_wcat_" + std::to_string(i), {H, 2 * H}); }
+            add(p + "gru_wxcat", {H, 6 * H});                   // x-side rows of the four GRU kernels: fw r|u, fw c, bw r|u, bw c
             if (g.has_hin) add(p + "d_hw0", {rows, g.P2});
             add(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2);
             add(p + "d_p1p", {rows, g.P1});
@@ -189,7 +240,10 @@ void Model::plan(const Shape& s) {
             add(p + "d_xin_p", {rows, g.Cin});
             add(p + "d_before", {g.N, g.P2});
             add(p + "d_h0", {g.N, 2 * H});
-            for (int k = 1; k <= g.Kb; k++) add(p + "bank_" + std::to_string(k) + "/wd", {(int64_t)k * g.Cb, g.Cin});
+            // flipped + transposed bank kernels, stored back to back ([sum_k k*Cb, Cin]) so that the bank's data gradient is
+            // ONE GEMM; "bank_taps" is its per-k-tile (column, row offset) table (int32 pairs)
+            add(p + "bank_wd", {(int64_t)g.Cb * g.Kb * (g.Kb + 1) / 2, g.Cin});
+            add(p + "bank_taps", {(int64_t)2 * (g.Cb / 32 + 1) * g.Kb * (g.Kb + 1) / 2});
             add(p + "proj_1/wd", {(int64_t)g.pw * g.P1, KC});
             add(p + "proj_2/wd", {(int64_t)g.pw * g.P2, g.P1});
         }
@@ -220,7 +274,7 @@ void Model::plan(const Shape& s) {
             for (int l = 1; l <= 2; l++) {
                 const std::string rp = "dec/g" + std::to_string(l) + "_";
                 for (const char* nm : {"st_r", "st_u", "st_c", "st_hprev"}) add(rp + nm, {rows, Y});
-                add(rp + "dgx", {rows, 3 * Y}); add(rp + "dh0", {N, Y});
+                add(rp + "dgx", {rows, 3 * Y}); add(rp + "dh0", {N, Y}); add(rp + "wxcat", {Y, 3 * Y});
             }
             add("dec/d_dec", {rows, M * r}); add("dec/d_y2", {rows, Y}); add("dec/d_y1", {rows, Y}); add("dec/d_y0", {rows, Y});
             const int64_t ZS = Z + SPK, KIN = ZS + HA, KO = HA + E + SPK;
@@ -273,7 +327,7 @@ void Model::plan(const Shape& s) {
         regions["mel_outputs"] = r;
     }
     plan_bytes = (off + 255) / 256 * 256;
-    shape = s; planned = true;
+    shape = s; planned = true; tables_ready = false; prep_done = false;
 }
 
 static int shape_of(const Model& m, const taco_batch* b, Shape& s) {
@@ -304,6 +358,69 @@ static taco_gemm_desc gd0(const float* A, const float* B, float* C, int M, int N
     taco_gemm_desc d{};
     d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.alpha = 1.f; d.split_k = 1;
     return d;
+}
+
+float* bank_wd(const Model& m, const CbhgGeom& g, int k) {
+    return m.W(g.prefix + "/bank_wd") + (long long)g.Cb * g.Cin * (k - 1) * k / 2;
+}
+
+// Operands of the backward pass that depend only on the parameters: flipped + transposed convolution kernels, packed
+// x-side GRU / highway weights, transposed attention weights, the bank tap tables.  Runs on the leaf stream beside the
+// forward pass (taco_forward), or in line at the start of the backward pass when the two-stream schedule is off.
+static int backward_prep(Model& m, cudaStream_t s) {
+    const taco_config& c = m.cfg;
+    for (const CbhgGeom* gp : {&m.enc, &m.post}) {
+        const CbhgGeom& g = *gp; const std::string p = g.prefix + "/";
+        const int H = g.H;
+        for (int k = 1; k <= g.Kb; k++)
+            TACO_TRY(launch_pack_dgrad(m.P(p + "bank_" + std::to_string(k) + "/kernel"), bank_wd(m, g, k), k, g.Cin, g.Cb, s));
+        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_1/kernel"), m.W(p + "proj_1/wd"), g.pw, g.Kb * g.Cb, g.P1, s));
+        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_2/kernel"), m.W(p + "proj_2/wd"), g.pw, g.P1, g.P2, s));
+        float* wx = m.W(p + "gru_wxcat");
+        const char* dirs[2] = {"gru_fw", "gru_bw"};
+        for (int dd = 0; dd < 2; dd++) {
+            TACO_TRY(launch_copy2d(wx + dd * 3 * H, m.P(p + dirs[dd] + "/gates_kernel"), H, 2 * H, 6 * H, 2 * H, s));
+            TACO_TRY(launch_copy2d(wx + dd * 3 * H + 2 * H, m.P(p + dirs[dd] + "/cand_kernel"), H, H, 6 * H, H, s));
+        }
+        for (int i = 1; i <= g.depth; i++) {
+            const std::string hn = p + "highway_" + std::to_string(i);
+            float* wc = m.W(p + "hw_wcat_" + std::to_string(i));
+            TACO_TRY(launch_copy2d(wc, m.P(hn + "/H_kernel"), H, H, 2 * H, H, s));
+            TACO_TRY(launch_copy2d(wc + H, m.P(hn + "/T_kernel"), H, H, 2 * H, H, s));
+        }
+        if (!m.tables_ready && g.Cb % 32 == 0) {
+            // k-tile i of the merged bank data gradient: member k, tap j, 32-channel block q  ->  column (k-1)*Cb + 32q of
+            // d_bank, row offset j - r_k (+ Kb: the operand base sits Kb slack rows before the buffer)
+            std::vector<int>& tab = (gp == &m.enc) ? m.taps_enc : m.taps_post;
+            tab.clear();
+            for (int k = 1; k <= g.Kb; k++) {
+                const int l = (k - 1) / 2, r = k - 1 - l;
+                for (int j = 0; j < k; j++)
+                    for (int q = 0; q < g.Cb / 32; q++) { tab.push_back((k - 1) * g.Cb + 32 * q); tab.push_back(j - r + g.Kb); }
+            }
+            TACO_CHECK_CUDA(cudaMemcpyAsync(m.W(p + "bank_taps"), tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        }
+    }
+    m.tables_ready = true;
+    {
+        const int M = c.num_mels, E = 2 * c.enc_rnn_size, A = c.attention_size, HA = c.attention_state_size;
+        const int Z1 = c.dec_prenet_sizes[0], Z = c.dec_prenet_sizes[1], Y = c.dec_rnn_size;
+        const int SPK = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
+        const int KIN = Z + SPK + HA, KO = HA + E + SPK;
+        TACO_TRY(launch_transpose(m.P("dec_prenet/dense_1/kernel") + (long long)M * Z1, m.W("dec/W1cT"), E, Z1, s));
+        TACO_TRY(launch_transpose(m.P("dec_prenet/dense_2/kernel"), m.W("dec/W2T"), Z1, Z, s));
+        TACO_TRY(launch_transpose(m.P("attention_gru/gates_kernel"), m.W("dec/WgT"), KIN, 2 * HA, s));
+        TACO_TRY(launch_transpose(m.P("attention_gru/cand_kernel"), m.W("dec/WcT"), KIN, HA, s));
+        TACO_TRY(launch_transpose(m.P("attention/query_kernel"), m.W("dec/WqT"), HA, A, s));
+        TACO_TRY(launch_transpose(m.P("concat_proj/kernel"), m.W("dec/WoT"), KO, Y, s));
+        for (int l = 1; l <= 2; l++) {
+            const std::string gn = "dec_gru_" + std::to_string(l);
+            float* wx = m.W("dec/g" + std::to_string(l) + "_wxcat");
+            TACO_TRY(launch_copy2d(wx, m.P(gn + "/gates_kernel"), Y, 2 * Y, 3 * Y, 2 * Y, s));
+            TACO_TRY(launch_copy2d(wx + 2 * Y, m.P(gn + "/cand_kernel"), Y, Y, 3 * Y, Y, s));
+        }
+    }
+    return TACO_OK;
 }
 
 static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
@@ -347,9 +464,13 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
     TACO_TRY(launch_gather_rows(m.W("enc/table2"), b->inputs, m.W("enc_cbhg/xin_p"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s));
+    prof_mark("fwd:enc_cbhg", s);
     TACO_TRY(cbhg_forward(m, m.enc, b->input_lengths, spk ? m.W("spk/before") : nullptr, spk ? m.W("spk/enc_init") : nullptr, tr, s));
+    prof_mark("fwd:decoder", s);
     TACO_TRY(decoder_forward(m, b, s));
+    prof_mark("fwd:post_cbhg", s);
     TACO_TRY(cbhg_forward(m, m.post, nullptr, nullptr, nullptr, tr, s));
+    prof_mark("fwd:linear", s);
     // ---- linear-spectrogram projection (tacotron.py:235) ----
     {
         const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 3) / 4 * 4;
@@ -368,6 +489,7 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         }
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
+    prof_mark("fwd:end", s);
     return TACO_OK;
 }
 
@@ -377,17 +499,17 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     const int N = m.shape.N, To = m.shape.To, M = c.num_mels, F = c.num_freq;
     TACO_REQUIRE(m.shape.training && b->mel_targets && b->linear_targets, TACO_ESTATE, "backward needs a training forward with targets");
     TACO_REQUIRE(!b->rnn_decoder_test_mode, TACO_ESTATE, "backward through the free-running decoder is not defined (train.py:158-166 builds that model forward-only)");
+    prof_mark("bwd:start", s);
     TACO_CHECK_CUDA(cudaMemsetAsync(m.grads, 0, sizeof(float) * (size_t)m.n_trainable, s));
     double* sc = m.Wd("scalars");
     TACO_CHECK_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, s));
-    // conv data-gradient operands (flipped + transposed kernels)
-    for (const CbhgGeom* gp : {&m.enc, &m.post}) {
-        const CbhgGeom& g = *gp; const std::string p = g.prefix + "/";
-        for (int k = 1; k <= g.Kb; k++)
-            TACO_TRY(launch_pack_dgrad(m.P(p + "bank_" + std::to_string(k) + "/kernel"), m.W(p + "bank_" + std::to_string(k) + "/wd"), k, g.Cin, g.Cb, s));
-        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_1/kernel"), m.W(p + "proj_1/wd"), g.pw, g.Kb * g.Cb, g.P1, s));
-        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_2/kernel"), m.W(p + "proj_2/wd"), g.pw, g.P1, g.P2, s));
+    if (m.prep_done) {
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_ev_prep, 0));   // packed operands were produced beside the forward pass
+    } else {
+        TACO_TRY(backward_prep(m, s));
     }
+    m.prep_done = false;
+    prof_mark("bwd:loss", s);
     // ---- losses and their gradients (tacotron.py:274-302) ----
     const CbhgGeom& g = m.post;
     const double cnt_mel = (double)N * To * M, cnt_lin = (double)N * To * F;
@@ -402,14 +524,16 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
                             m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
                             (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
+    prof_mark("bwd:linear", s);
     // ---- linear projection backward ----
     {
         const int Hp2 = 2 * c.post_rnn_size; const long long rows = (long long)N * To;
         const int S = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
         taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel") + (long long)S * F, Hp2, F, (int)rows, Hp2, Fp, F);
         w.transA = 1; w.accumulate = 1; w.split_k = 8;
-        TACO_TRY(launch_gemm(&w, 1, prec, s));
-        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, s));
+        cudaStream_t leaf = fork_side(s);
+        TACO_TRY(launch_gemm(&w, 1, prec, leaf));
+        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, leaf));
         if (S) {
             // speaker rows of the kernel and the embedding gradient see d_linear only through its sum over time
             TACO_CHECK_CUDA(cudaMemsetAsync(m.W("spk/s_lin"), 0, sizeof(float) * (size_t)N * Fp, s));
@@ -426,9 +550,12 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         e.transB = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
+    prof_mark("bwd:post_cbhg", s);
     TACO_TRY(cbhg_backward(m, m.post, nullptr, false, false, s));
     TACO_TRY(launch_axpy(m.W("post_cbhg/d_xin_p"), m.W("post_cbhg/d_mel_loss"), 1.f, (long long)g.rows * M, s));
+    prof_mark("bwd:decoder", s);
     TACO_TRY(decoder_backward(m, b, s));
+    prof_mark("bwd:enc_cbhg", s);
     const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
     TACO_TRY(cbhg_backward(m, m.enc, b->input_lengths, spk, spk, s));
     if (spk) {
@@ -483,6 +610,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         e = gd0(m.W("enc/d_t1pre"), m.P("enc_prenet/dense_1/kernel"), m.G("embedding"), V, E0, E1, E1, E1, E0); e.transB = 1; e.accumulate = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
+    prof_mark("bwd:end", s);
     return TACO_OK;
 }
 
@@ -581,7 +709,7 @@ int taco_workspace_bytes(taco_model h, int32_t N, int32_t T_in, int32_t T_out_or
 int taco_bind_workspace(taco_model h, void* ws, size_t bytes) {
     TACO_REQUIRE(h && ws, TACO_EINVAL, "taco_bind_workspace: null argument");
     TACO_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, TACO_EINVAL, "taco_bind_workspace: base must be 256-byte aligned");
-    h->m.ws = static_cast<char*>(ws); h->m.ws_bytes = bytes;
+    h->m.ws = static_cast<char*>(ws); h->m.ws_bytes = bytes; h->m.tables_ready = false; h->m.prep_done = false;
     return TACO_OK;
 }
 
@@ -605,7 +733,18 @@ int taco_forward(taco_model h, const taco_batch* b, void* stream) {
     Shape s;
     TACO_TRY(shape_of(m, b, s));
     TACO_TRY(ensure_plan(m, s));
-    return model_forward(m, b, static_cast<cudaStream_t>(stream));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    TACO_TRY(sched_init());
+    m.prep_done = false;
+    if (s.training && overlap_on()) {
+        // parameter-only operands of the backward pass are packed on the leaf stream while the forward pass runs
+        TACO_CHECK_CUDA(cudaEventRecord(g_ev_in, user));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_in, 0));
+        TACO_TRY(backward_prep(m, g_side));
+        TACO_CHECK_CUDA(cudaEventRecord(g_ev_prep, g_side));
+        m.prep_done = true;
+    }
+    return model_forward(m, b, user);
 }
 
 int taco_backward(taco_model h, const taco_batch* b, void* stream) {
@@ -615,7 +754,21 @@ int taco_backward(taco_model h, const taco_batch* b, void* stream) {
     Shape s;
     TACO_TRY(shape_of(m, b, s));
     TACO_REQUIRE(m.planned && m.shape == s, TACO_ESTATE, "taco_backward: call taco_forward with the same batch first");
-    return model_backward(m, b, static_cast<cudaStream_t>(stream));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    TACO_TRY(sched_init());
+    if (!overlap_on()) return model_backward(m, b, user);
+    // chain on the high-priority stream, leaves on the low-priority one (see "stream scheduler"); both are ordered
+    // after everything already enqueued on the caller's stream and joined back into it before returning
+    TACO_CHECK_CUDA(cudaEventRecord(g_ev_in, user));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(g_crit, g_ev_in, 0));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_in, 0));
+    const int rc = model_backward(m, b, g_crit);
+    prof_mark("side:end", g_side);
+    TACO_CHECK_CUDA(cudaEventRecord(g_ev_side, g_side));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, g_ev_side, 0));
+    TACO_CHECK_CUDA(cudaEventRecord(g_ev_out, g_crit));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, g_ev_out, 0));
+    return rc;
 }
 
 int taco_optimizer_step(taco_model h, int64_t global_step, int32_t is_randomly_initialized, float initial_learning_rate,
@@ -678,9 +831,10 @@ int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
 }
 
 int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]) {
-    // enable=1: start collecting; enable=0: stop, synchronise and return per-class totals (0 GEMM, 1 GRU recurrences, 2 attention recurrences)
+    // enable=1: start collecting; enable=0: stop, synchronise and return per-class totals (0 GEMM, 1 GRU recurrences, 2 attention recurrences);
+    // slot 3 carries the work of the GEMM spans: ms_out[3] = sum of 2MNK in GFLOP, count_out[3] = number of GEMM problems
     if (enable) {
-        for (auto& sp : g_prof_spans) { g_prof_pool.push_back(sp.a); g_prof_pool.push_back(sp.b); }
+        for (auto& sp : g_prof_spans) { g_prof_pool.push_back(sp.a); if (sp.b != sp.a) g_prof_pool.push_back(sp.b); }
         g_prof_spans.clear(); g_prof_on = true;
         return TACO_OK;
     }
@@ -692,19 +846,24 @@ int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]) {
         if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < 4) {
             if (ms_out) ms_out[sp.cls] += ms;
             if (count_out) count_out[sp.cls] += 1;
+            if (sp.cls == 0) { if (ms_out) ms_out[3] += sp.gflop; if (count_out) count_out[3] += sp.tag[3]; }
         }
     }
     return TACO_OK;
 }
 
-// debug: per-span listing of the last profile window, "cls ms tag0 tag1 tag2 tag3" per line (GEMM spans: M N K n_problems)
+// debug: per-span listing of the last profile window, one line per span:
+//   "cls ms tag0 tag1 tag2 tag3 start_ms stream name"   (GEMM spans: M N K n_problems; start relative to the first span;
+//   stream 1 = the low-priority leaf stream; class 9 = stage markers)
 int taco_debug_profile_spans(char* buf, int64_t cap) {
     std::string out;
     for (auto& sp : g_prof_spans) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) continue;
-        char line[128];
-        snprintf(line, sizeof line, "%d %.4f %d %d %d %d\n", sp.cls, ms, sp.tag[0], sp.tag[1], sp.tag[2], sp.tag[3]);
+        float ms = 0.f, t0 = 0.f;
+        if (sp.b != sp.a && cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&t0, g_prof_spans.front().a, sp.a) != cudaSuccess) t0 = -1.f;
+        char line[192];
+        snprintf(line, sizeof line, "%d %.4f %d %d %d %d %.4f %d %s\n", sp.cls, ms, sp.tag[0], sp.tag[1], sp.tag[2], sp.tag[3], t0,
+                 sp.stream == g_side ? 1 : 0, sp.name[0] ? sp.name : "-");
         out += line;
     }
     if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", out.c_str()); }

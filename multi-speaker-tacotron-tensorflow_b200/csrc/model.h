@@ -43,6 +43,10 @@ struct Model {
     std::map<std::string, Region> regions;
     size_t plan_bytes = 0;
     CbhgGeom enc, post;
+    // backward operands that depend only on the parameters (model.cu: backward_prep)
+    bool prep_done = false;          // produced beside the current forward pass on the leaf stream
+    bool tables_ready = false;       // bank tap tables uploaded for the current plan / workspace
+    std::vector<int> taps_enc, taps_post;
 
     // parameter access by name
     int lookup(const std::string& name, Entry& e) const;
@@ -57,8 +61,15 @@ struct Model {
     bool has_region(const std::string& name) const { return regions.count(name) != 0; }
 };
 
+// Stream for leaf work (weight / bias gradients) whose operands are produced by what is already enqueued on `main`:
+// the low-priority side stream when taco_backward runs its two-stream schedule, otherwise `main` itself.
+cudaStream_t fork_side(cudaStream_t main);
+
+void prof_mark(const char* name, cudaStream_t s);   // timeline stage marker (no-op unless taco_profile is collecting)
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s);
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s);
+
+float* bank_wd(const Model& m, const CbhgGeom& g, int k);   // flipped + transposed kernel of bank member k (packed, contiguous over k)
 
 // model_cbhg.cu
 int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* before_highway, const float* rnn_h0,

@@ -58,6 +58,7 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
     TACO_TRY(launch_bn_apply(R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
                              nullptr, nullptr, R("pooled_p"), g.N, g.T, g.Tp, g.PL, KC, 1, s));
 
+    prof_mark("cbhg_f:proj", s);
     // ---- projection 1: conv k=pw, ReLU, BN (modules.py:54-59) ----
     const int lp = (g.pw - 1) / 2;
     double* p1s = m.Wd(px + "p1_stats");
@@ -89,6 +90,7 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
     TACO_TRY(launch_bn_apply(R("p2_raw"), R("p2_mean"), R("p2_rstd"), m.P(px + "proj_2/gamma"), m.P(px + "proj_2/beta"),
                              xin_p, before_highway, R("hw0"), g.N, g.T, g.Tp, g.PL, g.P2, 0, s));
 
+    prof_mark("cbhg_f:highway", s);
     // ---- dimension fix (modules.py:72-73) ----
     float* hw = R("hw0");
     if (g.has_hin) {
@@ -110,6 +112,7 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
         TACO_TRY(launch_highway_fwd(Hb, Tb, hw, out, (long long)rows * H, s));
         hw = out;
     }
+    prof_mark("cbhg_f:gru", s);
     // ---- bi-GRU: hoisted x-side GEMMs, then the cluster-persistent recurrence (modules.py:82-96) ----
     {
         taco_gemm_desc d[4];
@@ -160,11 +163,13 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         a.dh0 = want_dh0 ? R("d_h0") : nullptr;
         TACO_TRY(prof_launch_gru(a, true, s));
     }
+    prof_mark("cbhg_b:gru_dgrad", s);
     // GRU weight gradients.  Recurrent parts reduce over the unpadded [N*T] stash rows; dgx lives in the padded
     // layout, so gather its valid rows once into a dense [2][N*T, 3H] matrix first.
     float* dgd = R("dgx_dense");
+    cudaStream_t leaf = fork_side(s);       // weight / bias gradients are leaves: they run beside the chain (model.cu)
     for (int dd = 0; dd < 2; dd++)
-        TACO_TRY(launch_unpad(dgd + (long long)dd * g.N * g.T * 3 * H, R("dgx") + dd * 3 * H, g.N, g.T, g.Tp, g.PL, 3 * H, 6 * H, s));
+        TACO_TRY(launch_unpad(dgd + (long long)dd * g.N * g.T * 3 * H, R("dgx") + dd * 3 * H, g.N, g.T, g.Tp, g.PL, 3 * H, 6 * H, leaf));
     {
         const char* dirs[2] = {"gru_fw", "gru_bw"};
         std::vector<taco_gemm_desc> ds;
@@ -184,24 +189,20 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
             d = gemm_desc(R("st_r") + (long long)dd * NT * H, dG + 2 * H, gWc + (long long)H * H, H, H, (int)NT, H, 3 * H, H);
             d.transA = 1; d.accumulate = 1; d.split_k = wgrad_split(H, H, NT); ds.push_back(d);
         }
-        TACO_TRY(launch_gemm(ds.data(), (int)ds.size(), prec, s));
+        TACO_TRY(launch_gemm(ds.data(), (int)ds.size(), prec, leaf));
         for (int dd = 0; dd < 2; dd++) {
             const std::string gn = px + dirs[dd];
-            TACO_TRY(launch_colsum(R("dgx") + dd * 3 * H, m.G(gn + "/gates_bias"), rows, 2 * H, 6 * H, s));
-            TACO_TRY(launch_colsum(R("dgx") + dd * 3 * H + 2 * H, m.G(gn + "/cand_bias"), rows, H, 6 * H, s));
-        }
-        // d hw_top = sum over the four blocks dgx_blk . Wx_blk^T
-        float* dhw = R("d_hwA");
-        for (int dd = 0; dd < 2; dd++) {
-            const std::string gn = px + dirs[dd];
-            taco_gemm_desc d = gemm_desc(R("dgx") + dd * 3 * H, m.P(gn + "/gates_kernel"), dhw, rows, H, 2 * H, 6 * H, 2 * H, H);
-            d.transB = 1; d.accumulate = dd > 0 ? 1 : 0;
-            TACO_TRY(launch_gemm(&d, 1, prec, s));
-            d = gemm_desc(R("dgx") + dd * 3 * H + 2 * H, m.P(gn + "/cand_kernel"), dhw, rows, H, H, 6 * H, H, H);
-            d.transB = 1; d.accumulate = 1;
-            TACO_TRY(launch_gemm(&d, 1, prec, s));
+            TACO_TRY(launch_colsum(R("dgx") + dd * 3 * H, m.G(gn + "/gates_bias"), rows, 2 * H, 6 * H, leaf));
+            TACO_TRY(launch_colsum(R("dgx") + dd * 3 * H + 2 * H, m.G(gn + "/cand_bias"), rows, H, 6 * H, leaf));
         }
     }
+    {
+        // d hw_top = dgx . Wx^T over all four blocks at once: K = 6H against the packed [H, 6H] x-side weights (backward_prep)
+        taco_gemm_desc d = gemm_desc(R("dgx"), R("gru_wxcat"), R("d_hwA"), rows, H, 6 * H, 6 * H, 6 * H, H);
+        d.transB = 1;
+        TACO_TRY(launch_gemm(&d, 1, prec, s));
+    }
+    prof_mark("cbhg_b:highway", s);
     // ---- highway stack backward ----
     float* dcur = R("d_hwA");
     float* dnext = R("d_hwB");
@@ -210,16 +211,20 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         float* Hb = m.W(px + "hwH_" + std::to_string(i));
         float* Tb = m.W(px + "hwT_" + std::to_string(i));
         float* xin = (i == 1) ? (g.has_hin ? R("hw_0") : R("hw0")) : m.W(px + "hw_" + std::to_string(i - 1));
-        TACO_TRY(launch_highway_bwd(dcur, Hb, Tb, xin, R("d_Hpre"), R("d_Tpre"), dnext, (long long)rows * H, s));
+        // pre-activation gradients (dHpre | dTpre) get a buffer per layer: the leaf stream may still be reading layer i's
+        // while the chain already produces layer i-1's
+        float* dHT = m.W(px + "d_HT_" + std::to_string(i));
+        TACO_TRY(launch_highway_bwd(dcur, Hb, Tb, xin, dHT, dnext, rows, H, s));
+        cudaStream_t lf = fork_side(s);
         taco_gemm_desc d[2];
-        d[0] = gemm_desc(xin, R("d_Hpre"), m.G(hn + "/H_kernel"), H, H, rows, H, H, H); d[0].transA = 1; d[0].accumulate = 1; d[0].split_k = wgrad_split(H, H, rows);
-        d[1] = gemm_desc(xin, R("d_Tpre"), m.G(hn + "/T_kernel"), H, H, rows, H, H, H); d[1].transA = 1; d[1].accumulate = 1; d[1].split_k = d[0].split_k;
-        TACO_TRY(launch_gemm(d, 2, prec, s));
-        TACO_TRY(launch_colsum(R("d_Hpre"), m.G(hn + "/H_bias"), rows, H, H, s));
-        TACO_TRY(launch_colsum(R("d_Tpre"), m.G(hn + "/T_bias"), rows, H, H, s));
-        taco_gemm_desc e = gemm_desc(R("d_Hpre"), m.P(hn + "/H_kernel"), dnext, rows, H, H, H, H, H); e.transB = 1; e.accumulate = 1;
-        TACO_TRY(launch_gemm(&e, 1, prec, s));
-        e = gemm_desc(R("d_Tpre"), m.P(hn + "/T_kernel"), dnext, rows, H, H, H, H, H); e.transB = 1; e.accumulate = 1;
+        d[0] = gemm_desc(xin, dHT, m.G(hn + "/H_kernel"), H, H, rows, H, 2 * H, H); d[0].transA = 1; d[0].accumulate = 1; d[0].split_k = wgrad_split(H, H, rows);
+        d[1] = gemm_desc(xin, dHT + H, m.G(hn + "/T_kernel"), H, H, rows, H, 2 * H, H); d[1].transA = 1; d[1].accumulate = 1; d[1].split_k = d[0].split_k;
+        TACO_TRY(launch_gemm(d, 2, prec, lf));
+        TACO_TRY(launch_colsum(dHT, m.G(hn + "/H_bias"), rows, H, 2 * H, lf));
+        TACO_TRY(launch_colsum(dHT + H, m.G(hn + "/T_bias"), rows, H, 2 * H, lf));
+        // dx += dHpre.WH^T + dTpre.WT^T: one GEMM with K = 2H against the packed [H, 2H] weight
+        taco_gemm_desc e = gemm_desc(dHT, m.W(px + "hw_wcat_" + std::to_string(i)), dnext, rows, H, 2 * H, 2 * H, 2 * H, H);
+        e.transB = 1; e.accumulate = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
         std::swap(dcur, dnext);
     }
@@ -228,8 +233,9 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
     if (g.has_hin) {
         taco_gemm_desc d = gemm_desc(R("hw0"), dcur, m.G(px + "highway_in/kernel"), g.P2, H, rows, g.P2, H, H);
         d.transA = 1; d.accumulate = 1; d.split_k = wgrad_split(g.P2, H, rows);
-        TACO_TRY(launch_gemm(&d, 1, prec, s));
-        TACO_TRY(launch_colsum(dcur, m.G(px + "highway_in/bias"), rows, H, H, s));
+        cudaStream_t lf = fork_side(s);
+        TACO_TRY(launch_gemm(&d, 1, prec, lf));
+        TACO_TRY(launch_colsum(dcur, m.G(px + "highway_in/bias"), rows, H, H, lf));
         taco_gemm_desc e = gemm_desc(dcur, m.P(px + "highway_in/kernel"), R("d_hw0"), rows, g.P2, H, H, H, g.P2);
         e.transB = 1; set_mask(e, g);
         TACO_TRY(launch_gemm(&e, 1, prec, s));
@@ -239,6 +245,7 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         TACO_CHECK_CUDA(cudaMemsetAsync(R("d_before"), 0, sizeof(float) * (size_t)g.N * g.P2, s));
         TACO_TRY(launch_timesum(d_hw0, R("d_before"), g.N, g.T, g.Tp, g.PL, g.P2, s));
     }
+    prof_mark("cbhg_b:proj2", s);
     // ---- projection 2 backward: BN (no activation), conv ----
     const int lp = (g.pw - 1) / 2, rp = g.pw - 1 - lp;
     TACO_TRY(launch_bn_bwd(d_hw0, R("p2_raw"), R("p2_mean"), R("p2_rstd"), m.P(px + "proj_2/gamma"), m.P(px + "proj_2/beta"),
@@ -247,14 +254,16 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         taco_gemm_desc d = gemm_desc(R("p1_p") - (long long)lp * g.P1, R("d_p2raw"), m.G(px + "proj_2/kernel"),
                                      g.pw * g.P1, g.P2, rows, g.P1, g.P2, g.P2);
         d.transA = 1; d.ctap = g.P1; d.accumulate = 1; d.split_k = wgrad_split(g.pw * g.P1, g.P2, rows);
-        TACO_TRY(launch_gemm(&d, 1, prec, s));
-        TACO_TRY(launch_colsum(R("d_p2raw"), m.G(px + "proj_2/bias"), rows, g.P2, g.P2, s));
+        cudaStream_t lf = fork_side(s);
+        TACO_TRY(launch_gemm(&d, 1, prec, lf));
+        TACO_TRY(launch_colsum(R("d_p2raw"), m.G(px + "proj_2/bias"), rows, g.P2, g.P2, lf));
         // dgrad: d p1_p[s] = sum_j' d_p2raw[s - rp + j'] . Wd[j']  with Wd = flipped+transposed kernel (packed)
         taco_gemm_desc e = gemm_desc(R("d_p2raw") - (long long)rp * g.P2, m.W(px + "proj_2/wd"), R("d_p1p"),
                                      rows, g.P1, g.pw * g.P2, g.P2, g.P1, g.P1);
         e.ctap = g.P2; set_mask(e, g);
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
+    prof_mark("cbhg_b:proj1", s);
     // ---- projection 1 backward: BN + ReLU, conv ----
     TACO_TRY(launch_bn_bwd(R("d_p1p"), R("p1_raw"), R("p1_mean"), R("p1_rstd"), m.P(px + "proj_1/gamma"), m.P(px + "proj_1/beta"),
                            m.G(px + "proj_1/gamma"), m.G(px + "proj_1/beta"), R("d_p1raw"), g.N, g.T, g.Tp, g.PL, g.P1, 0, 1, s));
@@ -262,21 +271,25 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         taco_gemm_desc d = gemm_desc(R("pooled_p") - (long long)lp * KC, R("d_p1raw"), m.G(px + "proj_1/kernel"),
                                      g.pw * KC, g.P1, rows, KC, g.P1, g.P1);
         d.transA = 1; d.ctap = KC; d.accumulate = 1; d.split_k = wgrad_split(g.pw * KC, g.P1, rows);
-        TACO_TRY(launch_gemm(&d, 1, prec, s));
-        TACO_TRY(launch_colsum(R("d_p1raw"), m.G(px + "proj_1/bias"), rows, g.P1, g.P1, s));
+        cudaStream_t lf = fork_side(s);
+        TACO_TRY(launch_gemm(&d, 1, prec, lf));
+        TACO_TRY(launch_colsum(R("d_p1raw"), m.G(px + "proj_1/bias"), rows, g.P1, g.P1, lf));
         taco_gemm_desc e = gemm_desc(R("d_p1raw") - (long long)rp * g.P1, m.W(px + "proj_1/wd"), R("d_pooled"),
                                      rows, KC, g.pw * g.P1, g.P1, KC, KC);
         e.ctap = g.P1; set_mask(e, g);
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
+    prof_mark("cbhg_b:bank", s);
     // ---- max-pool + BN + ReLU backward of the bank ----
     TACO_TRY(launch_bn_bwd(R("d_pooled"), R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
                            m.G(px + "bank_1/gamma"), m.G(px + "bank_1/beta"), R("d_bank"), g.N, g.T, g.Tp, g.PL, KC, 1, 1, s));
-    TACO_TRY(launch_colsum(R("d_bank"), m.G(px + "bank_1/bias"), rows, KC, KC, s));
+    cudaStream_t lfb = fork_side(s);
+    TACO_TRY(launch_colsum(R("d_bank"), m.G(px + "bank_1/bias"), rows, KC, KC, lfb));
     {
         std::vector<taco_gemm_desc> wg, dg;
         // residual path first: d_xin_p = d_hw0 (masked already: d_hw0 is zero on pad rows)
         TACO_TRY(launch_copy2d(R("d_xin_p"), d_hw0, rows, g.Cin, g.Cin, g.P2, s));
+        const bool merged = (prec != TACO_PREC_FP32) && (g.Cb % 32 == 0) && (KC % 4 == 0);
         for (int k = 1; k <= g.Kb; k++) {
             const int l = (k - 1) / 2, r = k - 1 - l;
             const std::string b = px + "bank_" + std::to_string(k);
@@ -284,12 +297,22 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
                                          k * g.Cin, g.Cb, rows, g.Cin, KC, g.Cb);
             d.transA = 1; d.ctap = g.Cin; d.accumulate = 1; d.split_k = wgrad_split(k * g.Cin, g.Cb, rows);
             wg.push_back(d);
-            taco_gemm_desc e = gemm_desc(R("d_bank") + (k - 1) * g.Cb - (long long)r * KC, m.W(b + "/wd"), R("d_xin_p"),
+            if (merged) continue;
+            taco_gemm_desc e = gemm_desc(R("d_bank") + (k - 1) * g.Cb - (long long)r * KC, bank_wd(m, g, k), R("d_xin_p"),
                                          rows, g.Cin, k * g.Cb, KC, g.Cin, g.Cin);
             e.ctap = g.Cb; e.accumulate = 2; set_mask(e, g);
             dg.push_back(e);
         }
-        TACO_TRY(launch_gemm(wg.data(), (int)wg.size(), prec, s));
+        if (merged) {
+            // all Kb members in ONE GEMM: K walks (member, tap, channel block) through the tap table; the packed kernels of
+            // the members are contiguous, so B is a single [sum_k k*Cb, Cin] matrix (backward_prep)
+            const int KK = g.Cb * g.Kb * (g.Kb + 1) / 2;
+            taco_gemm_desc e = gemm_desc(R("d_bank") - (long long)g.Kb * KC, bank_wd(m, g, 1), R("d_xin_p"), rows, g.Cin, KK, KC, g.Cin, g.Cin);
+            e.tap_table = reinterpret_cast<const int32_t*>(R("bank_taps")); e.tap_rows = rows + 2 * g.Kb;
+            e.accumulate = 1; e.split_k = 16; set_mask(e, g);
+            dg.push_back(e);
+        }
+        TACO_TRY(launch_gemm(wg.data(), (int)wg.size(), prec, lfb));
         TACO_TRY(launch_gemm(dg.data(), (int)dg.size(), prec, s));
     }
     return TACO_OK;

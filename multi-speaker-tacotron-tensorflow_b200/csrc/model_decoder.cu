@@ -115,6 +115,7 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         a.s_ctx = m.W("dec/s_ctx"); a.s_e = m.W("dec/s_e"); a.s_a = m.W("dec/s_a");
     }
     TACO_TRY(prof_launch_att(a, false, s));
+    prof_mark("dec_f:gru", s);
     // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
     TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
     TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
@@ -150,13 +151,13 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     w[1] = wgrad(x, Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel"), Y, Y, rows);
     w[2] = wgrad(m.W(rp + "st_hprev"), Y, dgx, 3 * Y, m.G(gn + "/gates_kernel") + (long long)Y * 2 * Y, Y, 2 * Y, rows);
     w[3] = wgrad(m.W(rp + "st_r"), Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel") + (long long)Y * Y, Y, Y, rows);
-    TACO_TRY(launch_gemm(w, 4, prec, s));
-    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, s));
-    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, s));
+    cudaStream_t leaf = fork_side(s);       // parameter gradients are leaves of the backward graph (model.cu: stream scheduler)
+    TACO_TRY(launch_gemm(w, 4, prec, leaf));
+    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, leaf));
+    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, leaf));
     TACO_CHECK_CUDA(cudaMemcpyAsync(dx, dy, sizeof(float) * (size_t)rows * Y, cudaMemcpyDeviceToDevice, s));
-    taco_gemm_desc e = gd(dgx, m.P(gn + "/gates_kernel"), dx, rows, Y, 2 * Y, 3 * Y, 2 * Y, Y); e.transB = 1; e.accumulate = 1;
-    TACO_TRY(launch_gemm(&e, 1, prec, s));
-    e = gd(dgx + 2 * Y, m.P(gn + "/cand_kernel"), dx, rows, Y, Y, 3 * Y, Y, Y); e.transB = 1; e.accumulate = 1;
+    // dx += dgx . Wx^T in one GEMM (K = 3Y) against the packed x-side rows of both kernels (model.cu: backward_prep)
+    taco_gemm_desc e = gd(dgx, m.W(rp + "wxcat"), dx, rows, Y, 3 * Y, 3 * Y, 3 * Y, Y); e.transB = 1; e.accumulate = 1;
     TACO_TRY(launch_gemm(&e, 1, prec, s));
     return TACO_OK;
 }
@@ -174,23 +175,20 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     TACO_TRY(launch_unpad(d_dec, m.W("post_cbhg/d_xin_p"), D.N, D.To, g.Tp, g.PL, D.M, D.M, s));
     {
         taco_gemm_desc w = wgrad(m.W("dec/y2"), Y, d_dec, MR, m.G("mel_proj/kernel"), Y, MR, rows);
-        TACO_TRY(launch_gemm(&w, 1, prec, s));
-        TACO_TRY(launch_colsum(d_dec, m.G("mel_proj/bias"), rows, MR, MR, s));
+        cudaStream_t leaf = fork_side(s);
+        TACO_TRY(launch_gemm(&w, 1, prec, leaf));
+        TACO_TRY(launch_colsum(d_dec, m.G("mel_proj/bias"), rows, MR, MR, leaf));
         taco_gemm_desc e = gd(d_dec, m.P("mel_proj/kernel"), m.W("dec/d_y2"), rows, Y, MR, MR, MR, Y); e.transB = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
+    prof_mark("dec_b:gru2", s);
     TACO_TRY(dec_gru_layer_bwd(m, D, 2, m.W("dec/y1"), m.W("dec/d_y2"), m.W("dec/d_y1"), deepvoice, s));
+    prof_mark("dec_b:gru1", s);
     TACO_TRY(dec_gru_layer_bwd(m, D, 1, m.W("dec/y0"), m.W("dec/d_y1"), m.W("dec/d_y0"), deepvoice, s));
+    prof_mark("dec_b:attention", s);
 
-    // transposed weight copies for the attention BPTT
-    const int ZS = D.Z + D.SPK, KIN = ZS + D.HA, KO = D.HA + D.E + D.SPK;
-    TACO_TRY(launch_transpose(m.P("dec_prenet/dense_1/kernel") + (long long)D.M * D.Z1, m.W("dec/W1cT"), D.E, D.Z1, s));
-    TACO_TRY(launch_transpose(m.P("dec_prenet/dense_2/kernel"), m.W("dec/W2T"), D.Z1, D.Z, s));
-    TACO_TRY(launch_transpose(m.P("attention_gru/gates_kernel"), m.W("dec/WgT"), KIN, 2 * D.HA, s));
-    TACO_TRY(launch_transpose(m.P("attention_gru/cand_kernel"), m.W("dec/WcT"), KIN, D.HA, s));
-    TACO_TRY(launch_transpose(m.P("attention/query_kernel"), m.W("dec/WqT"), D.HA, D.A, s));
-    TACO_TRY(launch_transpose(m.P("concat_proj/kernel"), m.W("dec/WoT"), KO, Y, s));
-
+    // (the transposed weight copies the attention BPTT reads are produced by backward_prep, model.cu)
+    const int ZS = D.Z + D.SPK;
     AttArgs a{};
     a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
     a.att_type = m.cfg.attention_type; a.fast = (prec != TACO_PREC_FP32);
@@ -225,13 +223,14 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         float* gW1 = m.G("dec_prenet/dense_1/kernel");
         w.push_back(wgrad(m.W("dec/x_all"), M, a.d_z1p, Z1, gW1, M, Z1, rows));
         w.push_back(wgrad(a.s_ctxin, E, a.d_z1p, Z1, gW1 + (long long)M * Z1, E, Z1, rows));
-        TACO_TRY(launch_gemm(w.data(), (int)w.size(), prec, s));
-        TACO_TRY(launch_colsum(a.dy0, m.G("concat_proj/bias"), rows, Y, Y, s));
-        TACO_TRY(launch_colsum(a.d_G, m.G("attention_gru/gates_bias"), rows, 2 * HA, 3 * HA, s));
-        TACO_TRY(launch_colsum(a.d_G + 2 * HA, m.G("attention_gru/cand_bias"), rows, HA, 3 * HA, s));
-        TACO_TRY(launch_colsum(a.d_zp, m.G("dec_prenet/dense_2/bias"), rows, Z, Z, s));
-        TACO_TRY(launch_colsum(a.d_z1p, m.G("dec_prenet/dense_1/bias"), rows, Z1, Z1, s));
-        if (m.cfg.attention_type == TACO_ATT_BAH_NORM) TACO_TRY(launch_colsum(a.d_gq, m.G("attention/b"), rows, A, A, s));
+        cudaStream_t leaf = fork_side(s);
+        TACO_TRY(launch_gemm(w.data(), (int)w.size(), prec, leaf));
+        TACO_TRY(launch_colsum(a.dy0, m.G("concat_proj/bias"), rows, Y, Y, leaf));
+        TACO_TRY(launch_colsum(a.d_G, m.G("attention_gru/gates_bias"), rows, 2 * HA, 3 * HA, leaf));
+        TACO_TRY(launch_colsum(a.d_G + 2 * HA, m.G("attention_gru/cand_bias"), rows, HA, 3 * HA, leaf));
+        TACO_TRY(launch_colsum(a.d_zp, m.G("dec_prenet/dense_2/bias"), rows, Z, Z, leaf));
+        TACO_TRY(launch_colsum(a.d_z1p, m.G("dec_prenet/dense_1/bias"), rows, Z1, Z1, leaf));
+        if (m.cfg.attention_type == TACO_ATT_BAH_NORM) TACO_TRY(launch_colsum(a.d_gq, m.G("attention/b"), rows, A, A, leaf));
         if (D.SPK) {
             // 'simple' speaker rows (rnn_wrappers.py:372-376,408-413): the embedding is constant over time, so its kernel rows
             // and its own gradient need only the time sums of the pre-activation gradients
@@ -255,6 +254,7 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
             }
         }
     }
+    prof_mark("dec_b:keys", s);
     // keys / v gradients and the gradient wrt the encoder memory
     {
         const int HA = D.HA, E = D.E, A = D.A;
@@ -273,7 +273,7 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
                                              D.N, D.Ti, D.Td, A, a.fast, s));
             }
             taco_gemm_desc w = wgrad(a.memory, E, m.W("dec/d_keys"), A, m.G("attention/memory_kernel"), E, A, (long long)D.N * D.Ti);
-            TACO_TRY(launch_gemm(&w, 1, prec, s));
+            TACO_TRY(launch_gemm(&w, 1, prec, fork_side(s)));
             taco_gemm_desc e = gd(m.W("dec/d_keys"), m.P("attention/memory_kernel"), d_mem, D.N * D.Ti, E, A, A, A, E); e.transB = 1;
             TACO_TRY(launch_gemm(&e, 1, prec, s));
         } else {
