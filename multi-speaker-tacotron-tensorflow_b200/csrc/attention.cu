@@ -823,20 +823,31 @@ __global__ void att_keys_bwd_kernel(const float* __restrict__ keys, const float*
                                     int N, int Ti, int Td, int A) {
     const int chunks = (Ti + KB_J - 1) / KB_J;
     const int n = blockIdx.x / chunks, jc = blockIdx.x % chunks;
+    const int j0 = jc * KB_J, nj = min(KB_J, Ti - j0);
+    // t outer, the block's KB_J positions inner and in registers: q is read once per (t, u) and every load feeds KB_J
+    // independent tanh chains
     for (int u = threadIdx.x; u < A; u += blockDim.x) {
+        float k[KB_J], acc[KB_J];
+#pragma unroll
+        for (int jj = 0; jj < KB_J; jj++) { k[jj] = (jj < nj) ? keys[((long long)n * Ti + j0 + jj) * A + u] : 0.f; acc[jj] = 0.f; }
         float accv = 0.f;
         const float vu = v_eff[u];
-        for (int j = jc * KB_J; j < min(Ti, (jc + 1) * KB_J); j++) {
-            const float k = keys[((long long)n * Ti + j) * A + u];
-            float acc = 0.f;
-            for (int t = 0; t < Td; t++) {
-                const float g = __ldg(ge + ((long long)n * Td + t) * Ti + j);
-                const float th = tanh_<FAST>(k + __ldg(q + ((long long)n * Td + t) * A + u));
-                acc = fmaf(g, 1.f - th * th, acc);
-                accv = fmaf(g, th, accv);
+        const float* gep = ge + (long long)n * Td * Ti + j0;
+        const float* qp = q + (long long)n * Td * A + u;
+        for (int t = 0; t < Td; t++) {
+            const float qv = __ldg(qp + (long long)t * A);
+            float g[KB_J];
+#pragma unroll
+            for (int jj = 0; jj < KB_J; jj++) g[jj] = (jj < nj) ? __ldg(gep + (long long)t * Ti + jj) : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < KB_J; jj++) {
+                const float th = tanh_<FAST>(k[jj] + qv);
+                acc[jj] = fmaf(g[jj], 1.f - th * th, acc[jj]);
+                accv = fmaf(g[jj], th, accv);
             }
-            dkeys[((long long)n * Ti + j) * A + u] = acc * vu;
         }
+#pragma unroll
+        for (int jj = 0; jj < KB_J; jj++) if (jj < nj) dkeys[((long long)n * Ti + j0 + jj) * A + u] = acc[jj] * vu;
         atomicAdd(gv + u, accv);
     }
 }

@@ -187,13 +187,13 @@ __device__ __forceinline__ float4 f4_bn(float4 x, float4 mu, float4 rs, float4 g
 }
 
 template <int MODE, bool APPLY>
-__global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
-                                                     int N, int T, int Tp, int PL, int C, int relu_mask, int chunks) {
+                                                     int N, int T, int Tp, int PL, int C, int relu_mask, int chunks, int c_off) {
     const int tx = blockDim.x, ty = blockDim.y;
-    const int c = (blockIdx.x * tx + threadIdx.x) * 4;
+    const int c = c_off + (blockIdx.x * tx + threadIdx.x) * 4;
     const int n = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
     const bool cok = c < C;
     const int tp0 = (chunk * ty + threadIdx.y) * BNB_R;
@@ -293,13 +293,21 @@ int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const flo
     TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "bn_bwd: channel count %d must be a multiple of 4", C);
     int tx, ty; lanes_2d(C / 4, tx, ty);
     const int chunks = cdiv(Tp, ty * BNB_R);
-    dim3 block(tx, ty), grid(cdiv(C / 4, tx), (unsigned)(N * chunks));
-    if (mode == 1) {
-        bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
-        bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
-    } else {
-        bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
-        bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks);
+    const int gx = cdiv(C / 4, tx);
+    // (walking wide tensors in L2-sized column groups, reduce then apply per group, was measured SLOWER on B200: 1 KB row
+    // segments out of 8 KB rows waste DRAM pages; 0.65 ms vs 0.34 ms for the C2 conv bank.  Kept switchable for re-measurement.)
+    const bool grouped = false;
+    const int ngroups = grouped ? gx : 1;
+    dim3 block(tx, ty), grid(grouped ? 1 : gx, (unsigned)(N * chunks));
+    for (int gi = 0; gi < ngroups; gi++) {
+        const int c_off = gi * 4 * tx;
+        if (mode == 1) {
+            bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+        } else {
+            bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+        }
     }
     TACO_CHECK_LAUNCH();
     return TACO_OK;
@@ -539,13 +547,25 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
         float* gp = grad ? grad + n * grad_bs + t * grad_ts : nullptr;
         const float cf = coeff ? __ldg(coeff + n) : 1.f;
         float rw = 0.f;
-        for (int c = threadIdx.x; c < C; c += tx) {
-            const float d = op[c] - __ldg(tp + c);
-            const float a = fabsf(d);
-            const bool band = (c >= lo && c < hi);
-            const float w = w_all + (band ? w_band : 0.f);
-            rw = fmaf(a, w, rw); acc_all += a; if (band) acc_band += a;
-            if (gp) gp[c] = ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f)) * cf * w;
+        for (int c0 = threadIdx.x; c0 < C; c0 += 4 * tx) {       // four columns per trip: all eight loads issued before the arithmetic
+            float ov[4], tv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int c = c0 + e * tx; const bool ok = c < C;
+                ov[e] = ok ? op[c] : 0.f; tv[e] = ok ? __ldg(tp + c) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int c = c0 + e * tx;
+                if (c < C) {
+                    const float d = ov[e] - tv[e];
+                    const float a = fabsf(d);
+                    const bool band = (c >= lo && c < hi);
+                    const float w = w_all + (band ? w_band : 0.f);
+                    rw = fmaf(a, w, rw); acc_all += a; if (band) acc_band += a;
+                    if (gp) gp[c] = ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f)) * cf * w;
+                }
+            }
         }
         acc_w = fmaf(rw, cf, acc_w);
     }

@@ -24,8 +24,11 @@ lib.taco_debug_profile_spans.restype = C.c_int
 lib.taco_debug_profile_spans.argtypes = [C.c_char_p, C.c_int64]
 lib.taco_profile(1, None, None)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record()
+_h0 = time.perf_counter()
 eng.train_step(b)
+_host_ms = (time.perf_counter() - _h0) * 1e3
 e1.record()
 ms = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
 lib.taco_profile(0, ms, cnt)
@@ -36,7 +39,7 @@ for l in buf.value.decode().splitlines():
     f = l.split()
     rows.append(dict(cls=int(f[0]), ms=float(f[1]), tag=list(map(int, f[2:6])), t0=float(f[6]), side=int(f[7]), name=f[8]))
 rows.sort(key=lambda r: r["t0"])
-print("step %.3f ms (events around train_step, profiling events included); class totals ms %s" % (e0.elapsed_time(e1), list(ms)))
+print("step %.3f ms (events around train_step, profiling events included); host issue time %.3f ms; class totals ms %s" % (e0.elapsed_time(e1), _host_ms, list(ms)))
 names = {0: "gemm", 1: "gru", 2: "att", 9: "mark"}
 for r in rows:
     lane = "side" if r["side"] else "main"
