@@ -168,6 +168,14 @@ int taco_optimizer_step(taco_model m, int64_t global_step, int32_t is_randomly_i
 /* Copies the device scalars to host (synchronises the stream). */
 int taco_read_scalars(taco_model m, taco_step_scalars* out, void* stream);
 
+/* The same read-back without the synchronisation, for training loops that log step k while step k+1 is already
+ * enqueued (train.py:217-226 fetches the loss of every step): taco_copy_scalars_async enqueues the device->host copy of
+ * the raw accumulators into a caller-owned PINNED buffer of TACO_SCALARS_RAW_BYTES bytes; once the caller's own event
+ * after it has completed, taco_finish_scalars turns the raw values into the step scalars (host arithmetic only). */
+#define TACO_SCALARS_RAW_BYTES 128
+int taco_copy_scalars_async(taco_model m, void* pinned_raw, void* stream);
+int taco_finish_scalars(taco_model m, const void* pinned_raw, taco_step_scalars* out);
+
 /* ---- Griffin-Lim (replaces audio/__init__.py:54-56,76-84,99-106,149,158-165) -------- */
 typedef struct taco_gl_s* taco_gl;
 int taco_gl_create(taco_gl* out, int32_t n_fft, int32_t hop, int32_t win, int32_t max_frames, int32_t device);

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtaco_b200.so")
 
 TACO_ABI_VERSION = 2
+TACO_SCALARS_RAW_BYTES = 128
 ATT_TYPES = {"bah_mon": 0, "bah": 1, "bah_norm": 2}
 SPK_MODES = {"none": 0, "simple": 1, "deepvoice": 2, "deepvoice_table": 3}
 PREC = {"fp32": 0, "tf32": 1}
@@ -85,6 +86,8 @@ _SIGNATURES = {
     "taco_optimizer_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
     "taco_read_scalars": (C.c_int, [C.c_void_p, C.POINTER(TacoStepScalars), C.c_void_p]),
+    "taco_copy_scalars_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taco_finish_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TacoStepScalars)]),
     "taco_gl_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "taco_gl_destroy": (C.c_int, [C.c_void_p]),
     "taco_gl_workspace_bytes": (C.c_size_t, [C.c_void_p]),

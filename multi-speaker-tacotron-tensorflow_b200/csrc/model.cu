@@ -805,15 +805,7 @@ int taco_optimizer_step(taco_model h, int64_t global_step, int32_t is_randomly_i
     return TACO_OK;
 }
 
-int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
-    TACO_REQUIRE(h && out, TACO_EINVAL, "taco_read_scalars: null argument");
-    Model& m = h->m;
-    TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_read_scalars: nothing has run");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    double sc[8]; float scf[8];
-    TACO_CHECK_CUDA(cudaMemcpyAsync(sc, m.Wd("scalars"), sizeof sc, cudaMemcpyDeviceToHost, s));
-    TACO_CHECK_CUDA(cudaMemcpyAsync(scf, m.W("scalars_f"), sizeof scf, cudaMemcpyDeviceToHost, s));
-    TACO_CHECK_CUDA(cudaStreamSynchronize(s));
+static void finish_scalars(const Model& m, const double sc[8], const float scf[8], taco_step_scalars* out) {
     const taco_config& c = m.cfg;
     const double cnt_mel = (double)m.shape.N * m.shape.To * c.num_mels, cnt_lin = (double)m.shape.N * m.shape.To * c.num_freq;
     out->loss = (float)(sc[0] + sc[3]);
@@ -827,6 +819,39 @@ int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
     out->loss_without_coeff = out->mel_loss + out->linear_loss;
     out->grad_norm = scf[0];
     out->learning_rate = scf[1];
+}
+
+int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
+    TACO_REQUIRE(h && out, TACO_EINVAL, "taco_read_scalars: null argument");
+    Model& m = h->m;
+    TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_read_scalars: nothing has run");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double sc[8]; float scf[8];
+    TACO_CHECK_CUDA(cudaMemcpyAsync(sc, m.Wd("scalars"), sizeof sc, cudaMemcpyDeviceToHost, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(scf, m.W("scalars_f"), sizeof scf, cudaMemcpyDeviceToHost, s));
+    TACO_CHECK_CUDA(cudaStreamSynchronize(s));
+    finish_scalars(m, sc, scf, out);
+    return TACO_OK;
+}
+
+int taco_copy_scalars_async(taco_model h, void* pinned_raw, void* stream) {
+    TACO_REQUIRE(h && pinned_raw, TACO_EINVAL, "taco_copy_scalars_async: null argument");
+    Model& m = h->m;
+    TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_copy_scalars_async: nothing has run");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* raw = static_cast<char*>(pinned_raw);
+    static_assert(8 * sizeof(double) + 8 * sizeof(float) <= TACO_SCALARS_RAW_BYTES, "raw scalar block");
+    TACO_CHECK_CUDA(cudaMemcpyAsync(raw, m.Wd("scalars"), 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(raw + 8 * sizeof(double), m.W("scalars_f"), 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return TACO_OK;
+}
+
+int taco_finish_scalars(taco_model h, const void* pinned_raw, taco_step_scalars* out) {
+    TACO_REQUIRE(h && pinned_raw && out, TACO_EINVAL, "taco_finish_scalars: null argument");
+    const char* raw = static_cast<const char*>(pinned_raw);
+    double sc[8]; float scf[8];
+    memcpy(sc, raw, sizeof sc); memcpy(scf, raw + sizeof sc, sizeof scf);
+    finish_scalars(h->m, sc, scf, out);
     return TACO_OK;
 }
 

@@ -20,6 +20,19 @@ def _require_cuda(device: int) -> torch.device:
     return torch.device("cuda", device)
 
 
+class PendingScalars:
+    """Handle of an in-flight scalar read-back (Engine.scalars_async)."""
+
+    def __init__(self, engine, raw, event):
+        self._engine, self._raw, self._event = engine, raw, event
+
+    def get(self) -> Dict[str, float]:
+        self._event.synchronize()
+        out = capi.TacoStepScalars()
+        capi.check(self._engine.lib.taco_finish_scalars(self._engine._h, self._raw.data_ptr(), C.byref(out)))
+        return {k: float(getattr(out, k)) for k, _ in capi.TacoStepScalars._fields_}
+
+
 class Engine:
     def __init__(self, hp, num_speakers: int = 1, precision: str = "fp32", device: int = 0, seed: int = 4321,
                  named_params: Optional[Dict[str, torch.Tensor]] = None, randomize_bn_state: bool = False):
@@ -158,6 +171,19 @@ class Engine:
         out = capi.TacoStepScalars()
         capi.check(self.lib.taco_read_scalars(self._h, C.byref(out), self._stream()))
         return {k: float(getattr(out, k)) for k, _ in capi.TacoStepScalars._fields_}
+
+    def scalars_async(self) -> "PendingScalars":
+        """Enqueue the read-back of this step's scalars without synchronising; ``.get()`` on the returned handle waits for
+        it.  Lets a training loop fetch the loss of every step (train.py:217-226) while the next step is already enqueued."""
+        if not hasattr(self, "_raw_ring"):
+            self._raw_ring = [torch.empty(capi.TACO_SCALARS_RAW_BYTES, dtype=torch.uint8).pin_memory() for _ in range(8)]
+            self._raw_next = 0
+        raw = self._raw_ring[self._raw_next % len(self._raw_ring)]
+        self._raw_next += 1
+        capi.check(self.lib.taco_copy_scalars_async(self._h, raw.data_ptr(), self._stream()))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return PendingScalars(self, raw, ev)
 
     def train_step(self, batch: Dict[str, torch.Tensor], is_randomly_initialized: bool = True, allreduce=None) -> None:
         """forward + loss/backward + (gradient all-reduce) + clip/Adam/BN update — the body of train.py:217-219."""
