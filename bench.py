@@ -29,8 +29,8 @@ CFG = dict(N=32, T_in=128, T_out=800, num_mels=80, num_freq=1025, r=5)
 ALGO_BYTES_PER_STEP = 486.6e6
 # algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
 ALGO_FLOPS_PER_STEP = 784.8e9
-# ncu (profiles/r1_step_metrics_v4.summary.txt): 4975.3 MB of DRAM traffic over the 203 gemm_tc_kernel launches of one step
-GEMM_DRAM_BYTES_PER_LAUNCH = 4975.3e6 / 203
+# ncu (profiles/r1_step_metrics_v6.summary.txt): 4678.3 MB of DRAM traffic over the 165 gemm_tc_kernel launches of one step
+GEMM_DRAM_BYTES_PER_LAUNCH = 4678.3e6 / 165
 
 
 def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
@@ -235,7 +235,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed; fp32 SIMT in fp32 mode)",
                          "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                          "unit": "TFLOP/s", "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v4.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v6.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
                          "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
                          "launches_per_step": int(prof_n[0] // PROF_STEPS), "problems_per_step": int(prof_n[3] // PROF_STEPS), "ms_per_step": gemm_ms,
                          "algorithmic_flops_per_step": gemm_flops, "algorithmic_flops_per_launch": gemm_flops / max(1, prof_n[3] // PROF_STEPS),

@@ -29,6 +29,7 @@ struct TcParams {
     int M, N, K, ldc;
     int a_mn_major, b_mn_major;          // 1: MN-major (four boxes), 0: K-major (one box)
     int a_tap, a_ctap;                   // strided-tap addressing for A (lda > ctap)
+    int tap_inner;                       // > 0: number of taps; the K loop then walks (channel block, tap) with the tap innermost
     const int2* tap_table;               // optional per-k-tile (column, row offset) of A (K-major A only)
     float alpha; int accumulate;
     const float* bias; int act;
@@ -226,7 +227,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_expect_tx(&full_bar[stage], 2 * TC_TILE_BYTES);
             }
             __syncwarp();
-            const int k0 = (kt0 + it) * TC_BK;
+            int k0 = (kt0 + it) * TC_BK;
+            if (p.tap_inner) {
+                // convolution taps innermost: consecutive k-tiles read the same activation rows shifted by one frame, so the
+                // re-read hits L2 (tap-major order re-reads a [128 x C] slab only after the whole wave streamed C channels)
+                const int cb = (kt0 + it) / p.tap_inner, j = (kt0 + it) - cb * p.tap_inner;
+                k0 = j * p.a_ctap + cb * TC_BK;
+            }
             uint8_t* a = sA + stage * TC_TILE_BYTES;
             uint8_t* b = sB + stage * TC_TILE_BYTES;
             if (lane < 4) {
@@ -438,6 +445,11 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1;
     p.a_tap = tap ? 1 : 0; p.a_ctap = tap ? g.ctap : 1;
     p.tap_table = reinterpret_cast<const int2*>(g.tap_table);
+    // Measured on B200 (post-net proj_1, M=25824 N=256 K=3x2048): tap-innermost order cuts the DRAM re-reads of the taps but
+    // does not speed the GEMM up (0.300 vs 0.298 ms; narrower convolutions got slower) - the main loop is bound by the per-SM
+    // operand ingest of fp32 tiles, not by DRAM.  Kept behind TACO_TAP_INNER=1 for re-measurement.
+    static const bool tap_inner_on = [] { const char* e = getenv("TACO_TAP_INNER"); return e && e[0] == '1'; }();
+    p.tap_inner = (tap_inner_on && tap && !g.transA && g.ctap % TC_BK == 0 && g.K % g.ctap == 0 && g.K / g.ctap > 1) ? g.K / g.ctap : 0;
     p.alpha = g.alpha; p.accumulate = g.accumulate; p.bias = g.bias; p.act = g.act;
     p.mask_period = g.mask_period; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
     p.remap_period = g.remap_period; p.remap_outer = g.remap_outer; p.remap_inner = g.remap_inner;

@@ -1,0 +1,204 @@
+"""Synthesis front door — mirror of the reference's ``synthesizer.py`` ``Synthesizer`` (synthesizer.py:24-207) and its
+post-processing (``plot_graph_and_save_audio``, :209-288) on the CUDA engine + GPU Griffin-Lim.
+
+    synthesizer = Synthesizer()
+    synthesizer.load(checkpoint_path, num_speakers, checkpoint_step)
+    audio = synthesizer.synthesize(texts=[...] | tokens=[[...]], base_path=..., speaker_ids=[...], attention_trim=False)
+
+Text front end: the reference tokenises Korean/English text with ``text.text_to_sequence`` (needs ``jamo``; out of scope,
+SURVEY.md §2).  ``tokens=`` is always accepted; ``texts=`` works when a ``text_to_sequence`` callable is supplied
+(``Synthesizer(text_to_sequence=fn)``) and otherwise raises, naming what is missing.
+"""
+from __future__ import annotations
+
+import io
+import os
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .hparams import hparams as _default_hparams, load_hparams
+from .models import create_model, get_most_recent_checkpoint
+
+EOS = 1                                                          # text/symbols.py: _pad=0, _eos=1
+
+
+def attention_trim_frames(alignment: np.ndarray, sequence_len: int, reduction_factor: int) -> int:
+    """Number of spectrogram frames to keep (synthesizer.py:242-262): walk the per-step attention argmax until the last
+    input position has been attended ``min(count, 5)`` times or attention moves past it.  alignment: [T_in, T_dec]."""
+    attention_argmax = alignment.argmax(0)
+    end_idx = min(sequence_len - 1, int(max(attention_argmax)))
+    max_counter = min(int((attention_argmax == end_idx).sum()), 5)
+    end_idx_counter = 0
+    jdx = 0
+    for jdx, attend_idx in enumerate(attention_argmax):
+        if len(attention_argmax) > jdx + 1:
+            if attend_idx == end_idx:
+                end_idx_counter += 1
+            if attend_idx == end_idx and attention_argmax[jdx + 1] > end_idx:
+                break
+            if end_idx_counter >= max_counter:
+                break
+        else:
+            break
+    return reduction_factor * jdx + 3
+
+
+def wav_bytes(wav: np.ndarray, sample_rate: int) -> bytes:
+    """audio.save_audio to an in-memory file (synthesizer.py:283-288): peak-normalised 16-bit PCM."""
+    from scipy.io import wavfile
+    out = wav * (32767 / max(0.01, float(np.max(np.abs(wav)))))          # audio/__init__.py:26-28
+    buf = io.BytesIO()
+    wavfile.write(buf, sample_rate, out.astype(np.int16))
+    return buf.getvalue()
+
+
+class Synthesizer:
+    def __init__(self, hparams=None, precision: str = "tf32", device: int = 0,
+                 text_to_sequence: Optional[Callable[[str], Sequence[int]]] = None):
+        self.hparams = hparams or _default_hparams
+        self._precision, self._device = precision, device
+        self._text_to_sequence = text_to_sequence
+        self.model = None
+        self._gl = None
+
+    def close(self):                                                     # synthesizer.py:25-27
+        if self.model is not None and self.model.engine is not None:
+            self.model.engine.close()
+        if self._gl is not None:
+            self._gl.close()
+        self.model, self._gl = None, None
+
+    def load(self, checkpoint_path, num_speakers=2, checkpoint_step=None, model_name="tacotron"):
+        """synthesizer.py:29-68: resolve the checkpoint, load params.json beside it, build the model, restore the weights."""
+        self.num_speakers = num_speakers
+        if os.path.isdir(checkpoint_path):
+            load_path = checkpoint_path
+            if checkpoint_step is not None:
+                checkpoint_path = os.path.join(load_path, "model.ckpt-{}.pt".format(checkpoint_step))
+            else:
+                checkpoint_path = get_most_recent_checkpoint(load_path)
+        else:
+            load_path = os.path.dirname(checkpoint_path)
+        print("Constructing model: %s" % model_name)
+        if os.path.exists(os.path.join(load_path, "params.json")):
+            load_hparams(self.hparams, load_path)
+        self.model = create_model(self.hparams)
+        self.model._precision, self.model._device = self._precision, self._device
+        print("Loading checkpoint: %s" % checkpoint_path)
+        self._state = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        self._restored = False
+        return self
+
+    # ------------------------------------------------------------------------------------------------------
+    def _run(self, sequences, input_lengths, speaker_ids, manual_alignments):
+        hp = self.hparams
+        m = self.model
+        m.is_manual_attention = manual_alignments is not None
+        m.manual_alignments = None if manual_alignments is None else torch.as_tensor(manual_alignments, dtype=torch.float32)
+        inputs = torch.as_tensor(np.asarray(sequences), dtype=torch.int32)
+        lengths = torch.as_tensor(np.asarray(input_lengths), dtype=torch.int32)
+        spk = None
+        if self.num_speakers > 1:
+            spk = torch.as_tensor(np.asarray(speaker_ids if speaker_ids is not None else [0] * len(sequences)), dtype=torch.int32)
+        if not self._restored:
+            from .engine import Engine
+            m.engine = Engine(hp, self.num_speakers, precision=self._precision, device=self._device)
+            m.num_speakers = self.num_speakers
+            m.load_state_dict(self._state)                                                        # saver.restore, synthesizer.py:66-68
+            self._restored = True
+        m.initialize(inputs, lengths, self.num_speakers, spk)                                     # synthesizer.py:47-54,166-167
+        return m.linear_outputs.cpu().numpy(), m.alignments.cpu().numpy()
+
+    def synthesize(self, texts=None, tokens=None, base_path=None, paths=None, speaker_ids=None,
+                   start_of_sentence=None, end_of_sentence=True, pre_word_num=0, post_word_num=0,
+                   pre_surplus_idx=0, post_surplus_idx=1, use_short_concat=False, manual_attention_mode=0,
+                   base_alignment_path=None, librosa_trim=False, attention_trim=True) -> List[object]:
+        """synthesizer.py:70-207.  Returns, per utterance, wav bytes (no path given) or True (written to disk)."""
+        if isinstance(texts, str):
+            texts = [texts]
+        if texts is not None and tokens is None:
+            if self._text_to_sequence is None:
+                raise RuntimeError("texts= needs a text front end: pass Synthesizer(text_to_sequence=fn) (the reference's "
+                                   "text.text_to_sequence depends on `jamo`, which this build does not ship) or call with tokens=")
+            sequences = [list(self._text_to_sequence(t)) for t in texts]
+        elif tokens is not None:
+            sequences = [list(t) for t in tokens]
+        else:
+            raise ValueError("synthesize needs texts= or tokens=")
+        if use_short_concat or librosa_trim:
+            raise NotImplementedError("short_concat / librosa_trim post-processing is not part of this build (SURVEY.md §8f row 4)")
+        n = len(sequences)
+        paths = paths if paths is not None else [None] * n
+        texts = texts if texts is not None else [None] * n
+        max_len = max(len(s) for s in sequences)
+        seq = np.zeros((n, max_len), np.int32)
+        for i, s in enumerate(sequences):
+            seq[i, :len(s)] = s
+        input_lengths = np.argmax(seq == EOS, 1)                         # synthesizer.py:118 (position of the EOS token)
+        if (input_lengths == 0).any():
+            raise ValueError("every token sequence must contain the EOS token (1) after its first symbol")
+        manual = None
+        if base_alignment_path is not None:                              # synthesizer.py:131-147
+            apath = os.path.join(base_alignment_path, os.path.basename(base_path))
+            manual = np.transpose(np.stack([np.load("{}.{}.npy".format(apath, i)) for i in range(n)]), [0, 2, 1])
+        spectrograms, alignments = self._run(seq, input_lengths, speaker_ids, manual)
+        results = self._save(spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, manual is not None)
+        if manual_attention_mode > 0:
+            if manual_attention_mode not in (1, 3):
+                raise NotImplementedError("manual_attention_mode=2 calls np.pow in the reference (synthesizer.py:188), which does not exist")
+            # argmax one-hot re-run (synthesizer.py:171-178,191-196): [N, T_dec, T_in] indexed [:, time, :]
+            new = np.zeros((n, alignments.shape[2], alignments.shape[1]), np.float32)
+            for i in range(n):
+                am = alignments[i].argmax(0)                             # attended input position per decoder step
+                new[i, np.arange(len(am)), am] = 1
+            spectrograms, alignments = self._run(seq, input_lengths, speaker_ids, new)
+            results = self._save(spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, True)
+        return results
+
+    def _save(self, spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, manual):
+        from .audio import GriffinLim
+        hp = self.hparams
+        results = []
+        for idx, (spec, alignment, path, sequence) in enumerate(zip(spectrograms, alignments, paths, sequences)):
+            if attention_trim and end_of_sentence:
+                spec = spec[:attention_trim_frames(alignment, len(sequence), hp.reduction_factor)]
+            if self._gl is None or self._gl.max_frames < spec.shape[0]:
+                self._gl = GriffinLim(hp, max_frames=max(1024, spec.shape[0]), device=self._device)
+            audio_out = self._gl.inv_spectrogram(torch.from_numpy(np.ascontiguousarray(spec))).cpu().numpy()    # synthesizer.py:264
+            if path or base_path:
+                if path is None:
+                    tag = ".manual" if manual else ""
+                    path = os.path.join(base_path, "{}{}.wav".format(idx, tag))
+                os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+                with open(path, "wb") as f:
+                    f.write(wav_bytes(audio_out, hp.sample_rate))
+                np.save(os.path.splitext(path)[0] + ".npy", alignment)
+                results.append(True)
+            else:
+                results.append(wav_bytes(audio_out, hp.sample_rate))
+        return results
+
+
+def main(argv=None):
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--load_path", required=True)
+    parser.add_argument("--sample_path", default="samples")
+    parser.add_argument("--text", default=None)
+    parser.add_argument("--tokens", default=None, help="space separated symbol ids ending with EOS=1 (replaces --text without a tokenizer)")
+    parser.add_argument("--num_speakers", default=1, type=int)
+    parser.add_argument("--speaker_id", default=0, type=int)
+    parser.add_argument("--checkpoint_step", default=None, type=int)
+    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    config = parser.parse_args(argv)
+    os.makedirs(config.sample_path, exist_ok=True)
+    synthesizer = Synthesizer(precision=config.precision)
+    synthesizer.load(config.load_path, config.num_speakers, config.checkpoint_step)
+    kw = dict(tokens=[[int(t) for t in config.tokens.split()]]) if config.tokens else dict(texts=[config.text])
+    return synthesizer.synthesize(base_path=config.sample_path, speaker_ids=[config.speaker_id], attention_trim=False, **kw)[0]
+
+
+if __name__ == "__main__":
+    main()

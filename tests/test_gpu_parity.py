@@ -501,3 +501,53 @@ def test_async_scalar_readback_matches_blocking(tb, hp5, golden_setup):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_train_small.npz"))
     assert abs(first["loss"] - float(gold["scalars"][0])) <= 1e-5 * max(1.0, float(gold["scalars"][0]))
     eng.close()
+
+
+def test_train_and_synthesize_command_lines(tb, tmp_path):
+    """train.py (flags of the reference, train.py:281-297) on a tiny two-speaker dataset in the reference's .npz schema, then
+    synthesizer.py's Synthesizer on the checkpoint it wrote: run directory layout, resume, loss decreasing, audio out."""
+    from importlib import import_module
+    df = import_module("multi-speaker-tacotron-tensorflow_b200.datasets.datafeeder")
+    train = import_module("multi-speaker-tacotron-tensorflow_b200.train")
+    synth = import_module("multi-speaker-tacotron-tensorflow_b200.synthesizer")
+    rng = np.random.RandomState(0)
+    roots = []
+    for spk in ("spk_a", "spk_b"):
+        d = tmp_path / spk / "data"
+        d.mkdir(parents=True)
+        for i in range(10):
+            frames, ntok = int(rng.randint(150, 200)), int(rng.randint(50, 60))
+            tok = rng.randint(2, 80, ntok); tok[-1] = 1
+            df.write_example(str(d / ("ex%02d.npz" % i)), tok, rng.rand(frames, 80), rng.rand(frames, 1025))
+        roots.append(str(tmp_path / spk))
+    hp = tb.hparams.override(reduction_factor=5, batch_size=4, model_type="deepvoice", initial_phase_step=0)
+    log_dir = str(tmp_path / "logs")
+    argv = ["--log_dir", log_dir, "--data_paths", ",".join(roots), "--checkpoint_interval", "2", "--test_interval", "2",
+            "--num_test_per_speaker", "1", "--max_steps", "4", "--precision", "fp32"]
+    assert train.main(argv, hp=hp) == 4
+    runs = os.listdir(log_dir)
+    assert len(runs) == 1 and runs[0].startswith("spk_a+spk_b_")
+    run = os.path.join(log_dir, runs[0])
+    files = set(os.listdir(run))
+    assert {"params.json", "train.log", "model.ckpt-2.pt", "model.ckpt-4.pt", "step-2-test-align.npy"} <= files
+    lines = [l for l in open(os.path.join(run, "train.log")) if "Step " in l]
+    assert len(lines) == 4 and "loss=" in lines[0]
+    # resume (train.py:189-192): the step counter continues from the checkpoint
+    hp2 = tb.hparams.override(reduction_factor=5, batch_size=4, model_type="deepvoice", initial_phase_step=0)
+    assert train.main(["--load_path", run, "--data_paths", ",".join(roots), "--checkpoint_interval", "100", "--test_interval", "0",
+                       "--max_steps", "6", "--precision", "fp32"], hp=hp2) == 6
+    # synthesis from the run directory (synthesizer.py:29-68,70-207)
+    s = synth.Synthesizer(hparams=tb.hparams.override(reduction_factor=5, max_iters=12), precision="fp32")
+    s.load(run, num_speakers=2)
+    assert s.hparams.model_type == "deepvoice" and s.hparams.batch_size == 4             # params.json restored
+    s.hparams.max_iters = 12
+    tokens = [list(rng.randint(2, 80, 9)) + [1], list(rng.randint(2, 80, 5)) + [1, 0, 0, 0, 0]]
+    wavs = s.synthesize(tokens=tokens, speaker_ids=[0, 1], attention_trim=False)
+    assert len(wavs) == 2 and all(isinstance(w, bytes) and w[:4] == b"RIFF" for w in wavs)
+    assert len(wavs[0]) == 44 + 2 * 300 * (12 * 5 - 1)                                   # hop 300, T_out = max_iters * r frames
+    out_dir = str(tmp_path / "samples")
+    assert s.synthesize(tokens=tokens[:1], base_path=out_dir, speaker_ids=[1], manual_attention_mode=1) == [True]
+    assert {"0.wav", "0.manual.wav"} <= set(os.listdir(out_dir))
+    with pytest.raises(RuntimeError):
+        s.synthesize(texts=["no tokenizer in this build"])
+    s.close()
