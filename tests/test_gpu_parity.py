@@ -89,6 +89,75 @@ def test_train_step_matches_golden_fixture(tb, hp5, golden_setup, prec):
     eng.close()
 
 
+def _ref_cases():
+    import make_reference_golden as mr
+    return sorted(mr.CASES)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", _ref_cases())
+def test_cuda_path_matches_reference_run_fixtures(tb, name, prec):
+    """tests/golden/ref_*.npz were produced by the reference's own model code (tools/make_reference_golden.py: unmodified
+    /root/reference/models over the TF-API stand-in).  The CUDA path, through the C ABI, must reproduce them: outputs, losses,
+    gradients, the Adam update and the batch-norm statistics — every speaker mode, attention type, manual attention,
+    rnn_decoder_test_mode, prioritize_loss, LR mode 1, ragged lengths."""
+    import make_reference_golden as mr
+    over, S, bk, mode = mr.CASES[name]
+    hp = mr.our_hparams(tb, over)
+    named = mr.golden_params(tb, hp, S)
+    b = mr.golden_batch(**bk)
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    tol = TOL[prec]
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
+    spk = b.get("speaker_id")
+    if not mode.startswith("train"):
+        ma = mr.manual_alignments(b["inputs"].shape[0], hp.max_iters, b["inputs"].shape[1]) if mode == "infer_manual" else None
+        out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=hp.max_iters, manual_alignments=ma)
+        for k in ("mel_outputs", "linear_outputs", "alignments"):
+            err = np.abs(out[k].cpu().numpy() - g[k]).max()
+            assert err <= (2e-4 if prec == "fp32" else 6e-2), (k, err)      # free-running: errors feed back through the decoder
+        eng.close()
+        return
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"],
+                      rnn_decoder_test_mode=(mode == "train_test_mode"))
+    lim = tol["out"] if mode != "train_test_mode" else (2e-4 if prec == "fp32" else 6e-2)
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        err = np.abs(out[k].cpu().numpy() - g[k]).max()
+        assert err <= lim, (k, err)
+    if mode == "train_test_mode":
+        eng.close()
+        return
+    eng.backward()
+    sc = eng.scalars()
+    want = g["scalars"]
+    for key, i in (("loss", 0), ("mel_loss", 1), ("linear_loss", 2), ("loss_without_coeff", 3)):
+        assert abs(sc[key] - want[i]) <= tol["loss"] * max(1.0, want[i]), (key, sc[key], want[i])
+    got = eng.named_gradients()
+    assert sorted(got) == list(g["grad_names"])
+    if prec == "fp32":
+        for k, n in zip(g["grad_names"], g["grad_norms"]):
+            mine = float(got[k].double().norm())
+            assert abs(mine - n) <= max(1e-2 * n, 1e-6), (k, mine, n)
+    for key in g.files:
+        if key.startswith("grad:"):
+            ref = g[key]
+            dn = np.linalg.norm(ref)
+            if dn > 1e-7:
+                rel = np.linalg.norm(got[key[5:]].cpu().numpy() - ref) / dn
+                assert rel <= (2e-3 if prec == "fp32" else 1e-1), (key, rel)
+    eng.optimizer_step(True)
+    sc = eng.scalars()
+    assert abs(sc["grad_norm"] - want[4]) <= tol["gn"] * want[4]
+    assert abs(sc["learning_rate"] - want[5]) <= 1e-6 * want[5]
+    if prec == "fp32":
+        newp = eng.named_parameters()
+        for key in g.files:
+            if key.startswith("after:"):
+                assert np.abs(newp[key[6:]].cpu().numpy() - g[key]).max() <= 2e-6, key
+    assert eng.global_step == int(g["global_step_after"])
+    eng.close()
+
+
 @pytest.mark.parametrize("prec,shape", [("fp32", (3, 13, 20, [13, 9, 5])), ("fp32", (9, 17, 10, [17, 1, 2, 17, 8, 9, 16, 3, 5])),
                                         ("fp32", (1, 8, 5, [8])), ("tf32", (3, 13, 20, [13, 9, 5])), ("fp32", (2, 50, 200, [50, 50]))])
 def test_forward_backward_vs_oracle(tb, hp5, prec, shape):

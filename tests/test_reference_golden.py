@@ -1,0 +1,150 @@
+"""The CPU oracle against fixtures produced by the reference's OWN model code (tests/golden/ref_*.npz).
+
+The fixtures come from ``tools/make_reference_golden.py``: /root/reference's unmodified ``models/*.py`` + ``hparams.py``
+executed over ``oracle/tf1_shim`` (an eager stand-in for the TF r1.4 API — TensorFlow itself is not installable here).
+This is what pins ``oracle/tacotron_oracle.py``: every output, loss, gradient, Adam update and batch-norm statistic the
+reference's code produces on seeded inputs must be reproduced by the oracle restatement.
+
+Tolerances (fp32 on both sides, different summation orders): outputs 5e-6 max-abs, scalars 1e-6, per-tensor gradient
+norms 1e-4 relative (absolute 1e-7 for mathematically-zero gradients such as a conv bias in front of batch norm), full
+gradient tensors 2e-5 relative L2, post-step parameters / BN statistics 2e-6 max-abs.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import make_reference_golden as mr  # noqa: E402
+from oracle import tacotron_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+HAVE_REF = os.path.isdir(os.path.join(mr.REF, "models"))
+
+
+def _oracle_case(tb, name):
+    over, S, bk, mode = mr.CASES[name]
+    hp = mr.our_hparams(tb, over)
+    named = mr.golden_params(tb, hp, S)
+    b = mr.golden_batch(**bk)
+    if not mode.startswith("train"):
+        ma = mr.manual_alignments(b["inputs"].shape[0], hp.max_iters, b["inputs"].shape[1]) if mode == "infer_manual" else None
+        with torch.no_grad():
+            out = O.forward(named, hp, b["inputs"], b["input_lengths"], S, b.get("speaker_id"), manual_alignments=ma, max_iters=hp.max_iters)
+        return dict(outputs=out)
+    names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
+    out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, b.get("speaker_id"), b["mel_targets"], b["linear_targets"],
+                    rnn_decoder_test_mode=(mode == "train_test_mode"))
+    ls = O.losses(out, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(named[k])) for k, g in zip(names, gl)}
+    clipped, gn = O.clip_by_global_norm(grads, 1.0)
+    lr = O.learning_rate(hp, 0, True)
+    P = {k: named[k].detach().clone() for k in names}
+    m = {k: torch.zeros_like(P[k]) for k in names}
+    v = {k: torch.zeros_like(P[k]) for k in names}
+    P, m, v = O.adam_step(P, clipped, m, v, 1, lr, hp.adam_beta1, hp.adam_beta2)
+    after = dict(P)
+    after.update({k: t.detach() for k, t in out["new_bn_state"].items()})
+    return dict(outputs=out, losses={k: float(x) for k, x in ls.items()}, grads=grads, grad_norm=gn, lr=lr, after=after)
+
+
+@pytest.mark.parametrize("name", sorted(mr.CASES))
+def test_oracle_reproduces_reference_run(tb, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    res = _oracle_case(tb, name)
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        got = res["outputs"][k].detach().numpy()
+        assert got.shape == g[k].shape, (k, got.shape, g[k].shape)
+        assert np.abs(got - g[k]).max() <= 5e-6, (k, np.abs(got - g[k]).max())
+    if "scalars" not in g.files:
+        return
+    ls = res["losses"]
+    want = g["scalars"]
+    got = [ls["loss"], ls["mel_loss"], ls["linear_loss"], ls["loss_without_coeff"], res["grad_norm"], res["lr"]]
+    for a, b_, what in zip(got, want, ("loss", "mel_loss", "linear_loss", "loss_without_coeff", "grad_norm", "lr")):
+        assert abs(a - b_) <= 1e-6 * max(1.0, abs(b_)), (what, a, b_)
+    assert sorted(res["grads"]) == list(g["grad_names"])                  # the reference trains exactly our parameter set
+    for k, n in zip(g["grad_names"], g["grad_norms"]):
+        mine = float(res["grads"][k].double().norm())
+        assert abs(mine - n) <= max(1e-4 * n, 1e-7), (k, mine, n)
+    for key in g.files:
+        if key.startswith("grad:"):
+            ref = g[key]
+            d = np.linalg.norm(res["grads"][key[5:]].numpy() - ref)
+            assert d <= 2e-5 * max(np.linalg.norm(ref), 1e-3), (key, d)
+        elif key.startswith("after:"):
+            assert np.abs(res["after"][key[6:]].numpy() - g[key]).max() <= 2e-6, key
+    assert int(g["global_step_after"]) == 1
+
+
+def test_existing_oracle_fixture_equals_reference_run(tb):
+    """tests/golden/tacotron_train_small.npz (written from the oracle in an earlier round) and ref_train_single.npz (written
+    by the reference's code) describe the same parameters and batch: they must agree."""
+    a = np.load(os.path.join(GOLD, "tacotron_train_small.npz"))
+    b = np.load(os.path.join(GOLD, "ref_train_single.npz"))
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert np.abs(a[k] - b[k]).max() <= 5e-6, k
+    assert np.abs(a["scalars"] - b["scalars"]).max() <= 1e-6
+    assert np.abs(a["grad_attention_v"] - b["grad:attention/v"]).max() <= 1e-7
+    assert np.abs(a["param_after_attention_v"] - b["after:attention/v"]).max() <= 1e-6
+    assert np.abs(a["bn_after_enc_p1_mean"] - b["after:enc_cbhg/proj_1/moving_mean"]).max() <= 1e-6
+    c = np.load(os.path.join(GOLD, "tacotron_infer_small.npz"))
+    d = np.load(os.path.join(GOLD, "ref_infer_single.npz"))
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert np.abs(c[k] - d[k]).max() <= 5e-6, k
+
+
+def test_tf_variable_name_table_covers_every_parameter(tb):
+    """tf_names.tf_to_ours is a bijection onto params.param_specs for every speaker mode / attention type."""
+    for over, S in ((dict(), 1), (dict(model_type="deepvoice"), 3), (dict(model_type="simple"), 2),
+                    (dict(model_type="deepvoice", speaker_embedding_size=1), 3), (dict(attention_type="bah_norm"), 1),
+                    (dict(attention_type="bah"), 1)):
+        hp = mr.our_hparams(tb, over)
+        table = tb.tf_names.tf_to_ours(hp, S)
+        ours = [s.name for s in tb.params.param_specs(hp, S)]
+        assert sorted(table.values()) == sorted(ours), over
+        assert len(set(table.values())) == len(table)
+        assert all(k.startswith("model/inference/") for k in table)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("name", ["ref_train_deepvoice", "ref_infer_manual_attention"])
+def test_fixtures_regenerate_from_the_reference(tb, name):
+    """The committed fixtures are reproducible: re-running the reference's code here gives the stored arrays."""
+    over, S, bk, mode = mr.CASES[name]
+    hp = mr.our_hparams(tb, over)
+    res = mr.run_reference(tb, over, S, mr.golden_batch(**bk), mr.golden_params(tb, hp, S), mode)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert np.array_equal(res[k], g[k]), k
+    if "scalars" in g.files:
+        assert np.array_equal(res["scalars"], g["scalars"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_reference_run_in_float64_matches_oracle_in_float64(tb):
+    """Rounding-free structural check: the reference's code over the shim in float64 against the oracle in float64."""
+    over, S, bk, mode = mr.CASES["ref_train_deepvoice"]
+    hp = mr.our_hparams(tb, over)
+    named = mr.golden_params(tb, hp, S)
+    b = mr.golden_batch(**bk)
+    res = mr.run_reference(tb, over, S, b, named, mode, double=True)
+    P = {k: v.double() for k, v in named.items()}
+    names = [k for k in P if not k.endswith(("moving_mean", "moving_var"))]
+    leaf = {k: (P[k].clone().requires_grad_(True) if k in names else P[k]) for k in P}
+    out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, b["speaker_id"], b["mel_targets"].double(), b["linear_targets"].double())
+    ls = O.losses(out, b["mel_targets"].double(), b["linear_targets"].double(), b["loss_coeff"].double(), hp)
+    gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert np.abs(out[k].detach().numpy() - res[k]).max() <= 1e-12, k
+    assert abs(float(ls["loss"]) - res["scalars"][0]) <= 1e-13
+    for k, gg in zip(names, gl):
+        ref = res["grads"][k]
+        mine = np.zeros_like(ref) if gg is None else gg.numpy()
+        assert np.abs(mine - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
