@@ -187,6 +187,16 @@ int taco_gl_inv_spectrogram(taco_gl g, const float* linear_spec, const float* in
                             int32_t n_iters, float power, float min_level_db, float ref_level_db,
                             float preemphasis, float* wav_out, void* ws, void* stream);
 
+/* Analysis front end (replaces audio/__init__.py:48-51 spectrogram, :64-67 melspectrogram, :99-101 _stft,
+ * :127-131 _linear_to_mel, :145-146 _amp_to_db, :155-156 _preemphasis, :161-162 _normalize): pre-emphasis, centred
+ * reflect-padded STFT (cuFFT), magnitude, optional mel projection, dB, normalisation.  wav: [n_samples] device floats;
+ * T = 1 + n_samples / hop frames (<= max_frames of the handle).  linear_out: [T, 1 + n_fft/2] or NULL; mel_out:
+ * [T, num_mels] or NULL (then mel_basis[num_mels, 1 + n_fft/2], device, is required).  Note the reference subtracts
+ * ref_level_db for the linear spectrogram only. */
+int taco_audio_spectrogram(taco_gl g, const float* wav, int32_t n_samples, float preemphasis, float ref_level_db,
+                           float min_level_db, const float* mel_basis, int32_t num_mels, float* linear_out,
+                           float* mel_out, void* stream);
+
 /* Per-class device timing with CUDA events on the launching stream (bench.py's roofline leg).  enable=1 starts collecting;
  * enable=0 stops, synchronises the device and returns totals per class: 0 GEMMs, 1 GRU recurrences, 2 attention recurrences. */
 int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]);

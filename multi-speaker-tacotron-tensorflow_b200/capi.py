@@ -93,6 +93,8 @@ _SIGNATURES = {
     "taco_gl_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "taco_gl_inv_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taco_audio_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "taco_profile": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "taco_gemm": (C.c_int, [C.POINTER(TacoGemmDesc), C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -14,6 +14,7 @@ namespace taco {
 struct GlState {
     int n_fft, hop, win, max_frames, device, nbins;
     cufftHandle c2r = 0, r2c = 0; int planned_T = 0;
+    cufftHandle ana_r2c = 0; int ana_T = 0;      // analysis front end (taco_audio_spectrogram)
     float* window = nullptr;     // [n_fft] periodic Hann(win) centred in n_fft
     float* wsum = nullptr;       // [n_fft + hop*(max_frames-1)] sum of squared windows
     float* mag = nullptr;        // [max_frames, nbins] target magnitudes (S^power)
@@ -123,6 +124,57 @@ __global__ void iir_fix_kernel(float* __restrict__ yo, const float* __restrict__
     if (st != 0.f) yo[s] += st * powf(a, (float)(s - c * IIR_CHUNK + 1));
 }
 
+// ---- analysis front end (audio/__init__.py:48-51 spectrogram, :64-67 melspectrogram) ------------------------------------
+// windowed frames of the pre-emphasised, reflect-padded signal; pre-emphasis x[n] = y[n] - a*y[n-1] (x[0] = y[0], scipy
+// lfilter with zero initial state, :155-156) is applied on the fly so the filtered signal never exists in memory
+__global__ void ana_frame_kernel(const float* __restrict__ y, const float* __restrict__ w, float* __restrict__ frames,
+                                 int n_fft, int hop, int T, int L, float a) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * n_fft) return;
+    int k = (int)(idx % n_fft), i = (int)(idx / n_fft);
+    float wk = w[k];
+    float v = 0.f;
+    if (wk != 0.f) {                          // the Hann window covers win of the n_fft taps; the rest is exact zero padding
+        int j = i * hop + k - n_fft / 2;
+        if (j < 0) j = -j;
+        if (j >= L) j = 2 * (L - 1) - j;
+        j = min(max(j, 0), L - 1);
+        v = wk * (y[j] - (j > 0 ? a * y[j - 1] : 0.f));
+    }
+    frames[idx] = v;
+}
+// one block per frame: |D| -> normalised dB linear row, and (optionally) mel = basis . |D| -> normalised dB mel row.
+// The magnitudes of the frame are staged in shared memory; one warp per mel channel walks its basis row coalesced.
+__global__ void ana_db_mel_kernel(const cufftComplex* __restrict__ spec, const float* __restrict__ basis, float* __restrict__ lin_out,
+                                  float* __restrict__ mel_out, int nbins, int num_mels, float ref_db, float min_db) {
+    extern __shared__ float mag[];
+    const int i = blockIdx.x;
+    const float inv = -1.0f / min_db;
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+        cufftComplex v = spec[(long long)i * nbins + k];
+        float m = sqrtf(v.x * v.x + v.y * v.y);
+        mag[k] = m;
+        if (lin_out) {
+            float S = 20.0f * log10f(fmaxf(1e-5f, m)) - ref_db;
+            lin_out[(long long)i * nbins + k] = fminf(fmaxf((S - min_db) * inv, 0.f), 1.f);
+        }
+    }
+    if (!mel_out) return;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int c = warp; c < num_mels; c += nwarps) {
+        const float* b = basis + (long long)c * nbins;
+        float acc = 0.f;
+        for (int k = lane; k < nbins; k += 32) acc = fmaf(b[k], mag[k], acc);
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float S = 20.0f * log10f(fmaxf(1e-5f, acc));      // no ref_level_db here: the reference's melspectrogram omits it
+            mel_out[(long long)i * num_mels + c] = fminf(fmaxf((S - min_db) * inv, 0.f), 1.f);
+        }
+    }
+}
+
 }  // namespace taco
 
 using namespace taco;
@@ -159,6 +211,7 @@ int taco_gl_destroy(taco_gl h) {
     GlState& g = h->st;
     if (g.c2r) cufftDestroy(g.c2r);
     if (g.r2c) cufftDestroy(g.r2c);
+    if (g.ana_r2c) cufftDestroy(g.ana_r2c);
     cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.y); cudaFree(g.carry);
     delete h;
     return TACO_OK;
@@ -212,6 +265,33 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
     iir_carry_kernel<<<1, 32, 0, s>>>(g.carry, nchunks, powf(preemphasis, (float)IIR_CHUNK));
     TACO_CHECK_LAUNCH();
     iir_fix_kernel<<<cdiv(L, 256), 256, 0, s>>>(wav_out, g.carry, L, preemphasis);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+int taco_audio_spectrogram(taco_gl h, const float* wav, int32_t n_samples, float preemphasis, float ref_level_db, float min_level_db,
+                           const float* mel_basis, int32_t num_mels, float* linear_out, float* mel_out, void* stream) {
+    TACO_REQUIRE(h && wav && (linear_out || mel_out), TACO_EINVAL, "taco_audio_spectrogram: null argument");
+    TACO_REQUIRE(!mel_out || (mel_basis && num_mels > 0), TACO_EINVAL, "taco_audio_spectrogram: mel_out needs mel_basis[num_mels, 1 + n_fft/2]");
+    GlState& g = h->st;
+    const int L = n_samples;
+    const int T = 1 + L / g.hop;                   // librosa centred stft: 1 + (L + n_fft - n_fft) / hop
+    TACO_REQUIRE(L > g.n_fft / 2, TACO_ESHAPE, "taco_audio_spectrogram: %d samples are too few for reflect padding (need > %d)", L, g.n_fft / 2);
+    TACO_REQUIRE(T <= g.max_frames, TACO_ESHAPE, "taco_audio_spectrogram: %d frames exceed max_frames=%d", T, g.max_frames);
+    TACO_REQUIRE(min_level_db < 0.f, TACO_EINVAL, "taco_audio_spectrogram: min_level_db must be negative");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g.ana_T != T) {
+        if (g.ana_r2c) { cufftDestroy(g.ana_r2c); g.ana_r2c = 0; }
+        int n[1] = {g.n_fft};
+        TACO_CHECK_CUFFT(cufftPlanMany(&g.ana_r2c, 1, n, nullptr, 1, g.n_fft, nullptr, 1, g.nbins, CUFFT_R2C, T));
+        g.ana_T = T;
+    }
+    TACO_CHECK_CUFFT(cufftSetStream(g.ana_r2c, s));
+    ana_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, s>>>(wav, g.window, g.frames, g.n_fft, g.hop, T, L, preemphasis);
+    TACO_CHECK_LAUNCH();
+    TACO_CHECK_CUFFT(cufftExecR2C(g.ana_r2c, g.frames, g.spec));
+    g_launch_count++;
+    ana_db_mel_kernel<<<T, 256, sizeof(float) * g.nbins, s>>>(g.spec, mel_basis, linear_out, mel_out, g.nbins, num_mels, ref_level_db, min_level_db);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }

@@ -88,3 +88,59 @@ def inv_spectrogram(spec_TF, init_phase_TF=None, n_iters=60, power=1.5, min_leve
         angles = np.where(mag > 0, est / np.maximum(mag, 1e-30), 1.0).astype(np.complex64)   # exp(1j*angle(est)), angle(0)=0
         y = istft(Sc * angles, hop, win)
     return lfilter_inv_preemphasis(y, preemphasis)
+
+
+# --------------------------------------------------------------------------
+# analysis front end (reference: audio/__init__.py:48-51 spectrogram, :64-67 melspectrogram)
+# --------------------------------------------------------------------------
+def preemphasis(x, coef=0.97):
+    """scipy.signal.lfilter([1, -coef], [1], x): y[n] = x[n] - coef*x[n-1], y[0] = x[0]  (audio/__init__.py:155-156)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = x.copy()
+    y[1:] -= coef * x[:-1]
+    return y
+
+
+def slaney_mel_basis(sample_rate=24000, n_fft=2048, n_mels=80):
+    """librosa 0.5.1 filters.mel(sr, n_fft, n_mels) with its defaults (fmin 0, fmax sr/2, Slaney scale, area norm) as
+    called at audio/__init__.py:141-143.  Written bin by bin (triangles) rather than with librosa's ramp matrices."""
+    f_sp, brk = 200.0 / 3.0, 1000.0
+    step = np.log(6.4) / 27.0
+
+    def to_mel(f):
+        return f / f_sp if f < brk else brk / f_sp + np.log(f / brk) / step
+
+    def to_hz(m):
+        return m * f_sp if m < brk / f_sp else brk * np.exp(step * (m - brk / f_sp))
+
+    nb = 1 + n_fft // 2
+    edges = [to_hz(m) for m in np.linspace(to_mel(0.0), to_mel(sample_rate / 2.0), n_mels + 2)]
+    B = np.zeros((n_mels, nb))
+    for i in range(n_mels):
+        lo, ce, hi = edges[i], edges[i + 1], edges[i + 2]
+        for k in range(nb):
+            f = k * (sample_rate / 2.0) / (nb - 1)
+            if lo < f < hi:
+                B[i, k] = min((f - lo) / (ce - lo), (hi - f) / (hi - ce)) * 2.0 / (hi - lo)
+    return B
+
+
+def _normalize(S, min_level_db):
+    return np.clip((S - min_level_db) / -min_level_db, 0, 1)
+
+
+def spectrogram(y, ref_level_db=20.0, min_level_db=-100.0, coef=0.97, num_freq=1025, frame_shift_ms=12.5, frame_length_ms=50,
+                sample_rate=24000):
+    """-> [num_freq, T] normalised dB linear spectrogram (audio/__init__.py:48-51; T = 1 + len(y)//hop)."""
+    n_fft, hop, win = stft_parameters(num_freq, frame_shift_ms, frame_length_ms, sample_rate)
+    D = np.abs(stft(preemphasis(y, coef), n_fft, hop, win))
+    return _normalize(20 * np.log10(np.maximum(1e-5, D)) - ref_level_db, min_level_db)
+
+
+def melspectrogram(y, min_level_db=-100.0, coef=0.97, num_mels=80, num_freq=1025, frame_shift_ms=12.5, frame_length_ms=50,
+                   sample_rate=24000):
+    """-> [num_mels, T] (audio/__init__.py:64-67).  Unlike spectrogram() the reference does NOT subtract ref_level_db here."""
+    n_fft, hop, win = stft_parameters(num_freq, frame_shift_ms, frame_length_ms, sample_rate)
+    D = np.abs(stft(preemphasis(y, coef), n_fft, hop, win))
+    M = slaney_mel_basis(sample_rate, n_fft, num_mels) @ D
+    return _normalize(20 * np.log10(np.maximum(1e-5, M)), min_level_db)

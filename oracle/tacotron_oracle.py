@@ -1,21 +1,27 @@
 """CPU ORACLE — test infrastructure only, never the product path.
 
-PARITY UNPINNED: the reference's arithmetic lives in TensorFlow 1.x (pinned
-``tensorflow==1.3.0`` in requirements.txt:101; the code needs r1.4 because of
-``BahdanauMonotonicAttention``, models/tacotron.py:5) which cannot be installed
-here, and the reference ships no tests, golden vectors or fixtures.  This file
-restates the reference graph op for op from its source, using the TF r1.4
-semantics listed in SURVEY.md §8(c) items 1-13, and is pinned instead by the
-self-tests in ``tests/test_oracle.py`` (recursive vs closed-form monotonic
-attention, independent scalar GRU, torch.nn.functional equivalents, fp64 finite
-differences, hand-computed Adam step).
+PARITY PINNING: the reference's arithmetic lives in TensorFlow 1.x (pinned ``tensorflow==1.3.0`` in
+requirements.txt:101; the code needs r1.4 because of ``BahdanauMonotonicAttention``, models/tacotron.py:5), which cannot
+be installed here, and the reference ships no tests, golden vectors or fixtures.  This file restates the reference graph
+op for op from its source, using the TF r1.4 semantics listed in SURVEY.md §8(c) items 1-13.  It is pinned two ways:
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import this module.
+  1. against the reference's OWN model code: ``tools/make_reference_golden.py`` imports the unmodified
+     ``/root/reference/{hparams.py,models/*.py,text/symbols.py}`` over ``oracle/tf1_shim`` (an eager stand-in for the TF
+     r1.4 Python API) and writes ``tests/golden/ref_*.npz``; ``tests/test_reference_golden.py`` requires this oracle to
+     reproduce every output, loss, gradient, Adam update and batch-norm statistic of those runs (fp32: <=5e-6; fp64:
+     <=1e-12) for all speaker modes, attention types, manual attention, rnn_decoder_test_mode, prioritize_loss, both LR
+     schedules and ragged lengths.  That pins the wiring, sizes, order of operations, feeding rules, loss and optimizer
+     recipe to the reference's code.  What it cannot pin is TensorFlow's library arithmetic itself (GRUCell, monotonic
+     attention, batch norm, SAME padding ... are restated in the shim from the TF sources, independently of this file):
+     status "pinned to the reference's Python, TF kernels restated twice and cross-checked" — not "ran TensorFlow";
+  2. by the self-tests in ``tests/test_oracle.py`` (recursive vs closed-form monotonic attention, independent scalar GRU,
+     torch.nn.functional equivalents, fp64 finite differences, hand-computed Adam step).
 
-Every function cites the reference lines it follows.  Tensors are torch CPU
-tensors (fp32 or fp64); the three recurrences are Python loops, mirroring the
-reference's ``tf.while_loop`` dispatch structure.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import this
+module.
+
+Every function cites the reference lines it follows.  Tensors are torch CPU tensors (fp32 or fp64); the three recurrences
+are Python loops, mirroring the reference's ``tf.while_loop`` dispatch structure.
 """
 from __future__ import annotations
 

@@ -324,6 +324,38 @@ def test_griffin_lim_matches_oracle(tb):
     assert errs[2] < errs[1] < errs[0]
 
 
+def test_audio_front_end_and_inversion_match_reference_audio_code(tb):
+    """taco_audio_spectrogram / taco_gl_inv_spectrogram against tests/golden/ref_audio_small.npz, which the reference's own
+    audio/__init__.py produced (tools/make_reference_golden.py).  Tolerances on the normalised-dB scale (1.0 = 100 dB):
+    2e-4 away from the 1e-5 amplitude floor; waveform 2e-3 of its peak after 4 Griffin-Lim iterations."""
+    from importlib import import_module
+    audio = import_module("multi-speaker-tacotron-tensorflow_b200.audio")
+    a = np.load(os.path.join(ROOT, "tests", "golden", "ref_audio_small.npz"))
+    gl = audio.GriffinLim(tb.hparams, max_frames=128)
+    lin, mel = gl.spectrograms(torch.from_numpy(a["wav_in"]))
+    assert lin.shape == (49, 1025) and mel.shape == (49, 80)
+    assert np.abs(lin.cpu().numpy() - a["spectrogram"].T).max() <= 2e-4
+    assert np.abs(mel.cpu().numpy() - a["melspectrogram"].T).max() <= 2e-4
+    assert np.abs(gl.spectrogram(a["wav_in"]).cpu().numpy() - a["spectrogram"].T).max() <= 2e-4        # single-output calls
+    assert np.abs(gl.melspectrogram(a["wav_in"]).cpu().numpy() - a["melspectrogram"].T).max() <= 2e-4
+    wav = gl.inv_spectrogram(torch.from_numpy(a["spectrogram"].T.copy()), torch.from_numpy(a["phase"].T.copy()), n_iters=int(a["n_iters"]))
+    assert np.abs(wav.cpu().numpy() - a["wav_out"]).max() <= 2e-3 * np.abs(a["wav_out"]).max()
+    # module-level drop-ins keep the reference's [bins, T] numpy layout
+    assert audio.melspectrogram(a["wav_in"]).shape == (80, 49) and audio.spectrogram(a["wav_in"]).shape == (1025, 49)
+    # analysis -> inversion round trip at a realistic length (5 s): the re-analysed spectrogram is close to the original
+    rng = np.random.RandomState(1)
+    import make_reference_golden as mr
+    y = np.tile(mr.audio_signal(), 9)[:120000]
+    g2 = audio.GriffinLim(tb.hparams, max_frames=512)
+    lin2 = g2.spectrogram(y)
+    assert lin2.shape == (401, 1025) and torch.isfinite(lin2).all() and float(lin2.min()) >= 0 and float(lin2.max()) <= 1
+    with pytest.raises(tb.capi.TacoError, match="too few"):
+        g2.spectrogram(np.zeros(100, dtype=np.float32))
+    with pytest.raises(tb.capi.TacoError, match="max_frames"):
+        gl.spectrogram(y)
+    gl.close(); g2.close()
+
+
 @pytest.mark.parametrize("prec,emb", [("fp32", 16), ("fp32", 1), ("tf32", 16)])
 def test_deepvoice_speaker_injection_vs_oracle(tb, prec, emb):
     """model_type='deepvoice' (tacotron.py:41-81,183-197): before_highway, encoder / attention / decoder initial states."""

@@ -148,3 +148,28 @@ def test_reference_run_in_float64_matches_oracle_in_float64(tb):
         ref = res["grads"][k]
         mine = np.zeros_like(ref) if gg is None else gg.numpy()
         assert np.abs(mine - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
+
+
+# ---- audio: the reference's audio/__init__.py over the librosa stand-in + real scipy (ref_audio_small.npz) ----------
+def test_audio_oracle_reproduces_reference_audio_code(tb):
+    from oracle import griffin_lim_oracle as G
+    from importlib import import_module
+    a = np.load(os.path.join(GOLD, "ref_audio_small.npz"))
+    assert a["spectrogram"].shape == (1025, 1 + 14400 // 300) and a["melspectrogram"].shape == (80, 49)
+    assert np.abs(G.spectrogram(a["wav_in"]) - a["spectrogram"]).max() <= 2e-5
+    assert np.abs(G.melspectrogram(a["wav_in"]) - a["melspectrogram"]).max() <= 2e-6
+    w = G.inv_spectrogram(a["spectrogram"].T, a["phase"].T, n_iters=int(a["n_iters"]))
+    assert w.shape == a["wav_out"].shape and np.abs(w - a["wav_out"]).max() <= 5e-6 * np.abs(a["wav_out"]).max()
+    # the product's host-side mel table (a constant; no oracle import there) against the reference's _build_mel_basis()
+    audio = import_module("multi-speaker-tacotron-tensorflow_b200.audio")
+    B = audio.build_mel_basis(tb.hparams)
+    assert B.shape == a["mel_basis"].shape and np.abs(B - a["mel_basis"]).max() <= 1e-8
+    assert np.abs(G.slaney_mel_basis() - a["mel_basis"]).max() <= 1e-8
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_audio_fixture_regenerates_from_the_reference():
+    a = np.load(os.path.join(GOLD, "ref_audio_small.npz"))
+    b = mr.run_reference_audio()
+    for k in ("spectrogram", "melspectrogram", "wav_out", "phase"):
+        assert np.array_equal(a[k], b[k]), k

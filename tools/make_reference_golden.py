@@ -182,6 +182,45 @@ def pack(res, full_grads=FULL_SMALL):
     return out
 
 
+def audio_signal(n=14400, seed=11):
+    """A speech-like test signal: a few drifting harmonics under a slow envelope plus a little noise."""
+    rng = np.random.RandomState(seed)
+    t = np.arange(n) / 24000.0
+    f0 = 140.0 + 30.0 * np.sin(2 * np.pi * 1.5 * t)
+    ph = 2 * np.pi * np.cumsum(f0) / 24000.0
+    y = sum(a * np.sin(h * ph + rng.rand() * 6.28) for h, a in ((1, 0.5), (2, 0.3), (3, 0.2), (5, 0.1), (9, 0.05), (17, 0.02)))
+    y = y * (0.3 + 0.7 * np.sin(2 * np.pi * 2.0 * t) ** 2) + 0.01 * rng.randn(n)
+    return (0.5 * y / np.abs(y).max()).astype(np.float32)
+
+
+def run_reference_audio(gl_iters=4, seed=7):
+    """The reference's audio/__init__.py, unmodified, over the librosa 0.5.1 stand-in (oracle/tf1_shim/librosa) and the real
+    scipy.  ``np.complex`` (removed from numpy >= 1.24, used at audio/__init__.py:78) is re-attached for the import."""
+    shim = os.path.join(ROOT, "oracle", "tf1_shim")
+    for p in (REF, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    if not hasattr(np, "complex"):
+        np.complex = complex
+    import audio as ref_audio                                   # reference/audio/__init__.py
+    y = audio_signal()
+    spec = ref_audio.spectrogram(y)                             # [num_freq, T]
+    mel = ref_audio.melspectrogram(y)                           # [num_mels, T]
+    saved = ref_audio.hparams.griffin_lim_iters
+    ref_audio.hparams.set_hparam("griffin_lim_iters", gl_iters)
+    try:
+        np.random.seed(seed)
+        wav = ref_audio.inv_spectrogram(spec)                   # draws np.random.rand(*S.shape) once (audio/__init__.py:77)
+    finally:
+        ref_audio.hparams.set_hparam("griffin_lim_iters", saved)
+    np.random.seed(seed)
+    phase = np.random.rand(*spec.shape)
+    return dict(wav_in=y, spectrogram=spec.astype(np.float32), melspectrogram=mel.astype(np.float32), phase=phase.astype(np.float32),
+                wav_out=wav.astype(np.float32), n_iters=gl_iters, mel_basis=ref_audio._build_mel_basis().astype(np.float32))
+
+
 def main():
     sys.path.insert(0, ROOT)
     import tacotron_b200 as tb
@@ -193,6 +232,9 @@ def main():
         res = run_reference(tb, over, S, b, named, mode)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(res, FULL_MORE if name == "ref_train_single" else FULL_SMALL))
         print(name, "mel", res["mel_outputs"].shape, "loss" if "scalars" in res else "", res.get("scalars", [""])[0])
+    a = run_reference_audio()
+    np.savez_compressed(os.path.join(OUT, "ref_audio_small.npz"), **a)
+    print("ref_audio_small", a["spectrogram"].shape, a["melspectrogram"].shape, a["wav_out"].shape)
 
 
 if __name__ == "__main__":
