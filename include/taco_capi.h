@@ -36,7 +36,7 @@ extern "C" {
 #define TACO_ENOMEM   (-4)
 #define TACO_ESTATE   (-5)
 
-#define TACO_ABI_VERSION 2
+#define TACO_ABI_VERSION 3
 
 /* attention_type (reference: models/tacotron.py:132-152; only these three are reachable) */
 #define TACO_ATT_BAH_MON  0
@@ -159,9 +159,12 @@ int taco_forward(taco_model m, const taco_batch* b, void* stream);
 int taco_backward(taco_model m, const taco_batch* b, void* stream);
 
 /* replaces: clip_by_global_norm(1.0) + AdamOptimizer.apply_gradients + BN UPDATE_OPS
- * (tacotron.py:327-336).  global_step is the value BEFORE the update (step = global_step+1).
- * grad_scale multiplies gradients first (1/world after an all-reduce SUM). */
-int taco_optimizer_step(taco_model m, int64_t global_step, int32_t is_randomly_initialized,
+ * (tacotron.py:327-336).  global_step is the value BEFORE the update (step = global_step+1) and drives the learning-rate
+ * schedule; adam_step is the number of Adam updates already applied to these moments (TF keeps it as beta1_power /
+ * beta2_power) and drives the bias correction.  The two differ after `--initialize_path`, which restores the optimizer
+ * state and resets only global_step (train.py:194-205).  grad_scale multiplies gradients first (1/world after an
+ * all-reduce SUM). */
+int taco_optimizer_step(taco_model m, int64_t global_step, int64_t adam_step, int32_t is_randomly_initialized,
                         float initial_learning_rate, int32_t decay_mode,
                         float beta1, float beta2, float grad_scale, void* stream);
 
@@ -196,6 +199,11 @@ int taco_gl_inv_spectrogram(taco_gl g, const float* linear_spec, const float* in
 int taco_audio_spectrogram(taco_gl g, const float* wav, int32_t n_samples, float preemphasis, float ref_level_db,
                            float min_level_db, const float* mel_basis, int32_t num_mels, float* linear_out,
                            float* mel_out, void* stream);
+
+/* Host utility: CRC-32C (Castagnoli) of n bytes, continuing from `crc` (0 to start) — the checksum TensorFlow's checkpoint
+ * format uses (replaces the tf.train.Saver dependency of train.py:175,242-244 / synthesizer.py:56-58 when reference
+ * checkpoints are imported or exported by tf_checkpoint.py).  No GPU involved. */
+uint32_t taco_crc32c(const void* data, size_t n, uint32_t crc);
 
 /* Per-class device timing with CUDA events on the launching stream (bench.py's roofline leg).  enable=1 starts collecting;
  * enable=0 stops, synchronises the device and returns totals per class: 0 GEMMs, 1 GRU recurrences, 2 attention recurrences. */

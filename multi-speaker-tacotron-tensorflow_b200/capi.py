@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence, Tuple
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtaco_b200.so")
 
-TACO_ABI_VERSION = 2
+TACO_ABI_VERSION = 3
 TACO_SCALARS_RAW_BYTES = 128
 ATT_TYPES = {"bah_mon": 0, "bah": 1, "bah_norm": 2}
 SPK_MODES = {"none": 0, "simple": 1, "deepvoice": 2, "deepvoice_table": 3}
@@ -83,7 +83,7 @@ _SIGNATURES = {
                                  C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "taco_forward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p]),
     "taco_backward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p]),
-    "taco_optimizer_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
+    "taco_optimizer_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
     "taco_read_scalars": (C.c_int, [C.c_void_p, C.POINTER(TacoStepScalars), C.c_void_p]),
     "taco_copy_scalars_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -95,6 +95,7 @@ _SIGNATURES = {
                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "taco_audio_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taco_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t, C.c_uint32]),
     "taco_profile": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "taco_gemm": (C.c_int, [C.POINTER(TacoGemmDesc), C.c_int32, C.c_int32, C.c_void_p]),
 }

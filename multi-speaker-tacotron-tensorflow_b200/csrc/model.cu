@@ -771,7 +771,7 @@ int taco_backward(taco_model h, const taco_batch* b, void* stream) {
     return rc;
 }
 
-int taco_optimizer_step(taco_model h, int64_t global_step, int32_t is_randomly_initialized, float initial_learning_rate,
+int taco_optimizer_step(taco_model h, int64_t global_step, int64_t adam_step, int32_t is_randomly_initialized, float initial_learning_rate,
                         int32_t decay_mode, float beta1, float beta2, float grad_scale, void* stream) {
     TACO_REQUIRE(h, TACO_EINVAL, "taco_optimizer_step: null model");
     Model& m = h->m;
@@ -787,7 +787,7 @@ int taco_optimizer_step(taco_model h, int64_t global_step, int32_t is_randomly_i
     } else {
         lr = initial_learning_rate * std::pow(0.95, step / 3000.0);
     }
-    const double t = step;
+    const double t = (double)(adam_step + 1);     // AdamOptimizer's own update count (beta powers), not the global step
     const double lr_t = lr * std::sqrt(1.0 - std::pow((double)beta2, t)) / (1.0 - std::pow((double)beta1, t));
     double* sc = m.Wd("scalars");
     float* scf = m.W("scalars_f");

@@ -70,6 +70,7 @@ class Engine:
         self._batch = None
         self._keep = []
         self.global_step = 0
+        self.adam_step = 0          # Adam updates applied to adam_m / adam_v (TF: beta1_power, beta2_power)
 
     # ---- lifetime ---------------------------------------------------------------------------------------
     def close(self) -> None:
@@ -162,10 +163,11 @@ class Engine:
 
     def optimizer_step(self, is_randomly_initialized: bool = True, grad_scale: float = 1.0) -> None:
         hp = self.hp
-        capi.check(self.lib.taco_optimizer_step(self._h, self.global_step, 1 if is_randomly_initialized else 0,
+        capi.check(self.lib.taco_optimizer_step(self._h, self.global_step, self.adam_step, 1 if is_randomly_initialized else 0,
                                                 float(hp.initial_learning_rate), int(hp.decay_learning_rate_mode),
                                                 float(hp.adam_beta1), float(hp.adam_beta2), float(grad_scale), self._stream()))
         self.global_step += 1
+        self.adam_step += 1
 
     def scalars(self) -> Dict[str, float]:
         out = capi.TacoStepScalars()

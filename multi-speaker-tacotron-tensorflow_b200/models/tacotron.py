@@ -91,7 +91,7 @@ class Tacotron:
     def state_dict(self):
         e = self.engine
         return dict(params=e.params.cpu(), bn_state=e.bn_state.cpu(), adam_m=e.adam_m.cpu(), adam_v=e.adam_v.cpu(),
-                    global_step=e.global_step, names=[s.name for s in e.specs], hparams=self._hparams.values(),
+                    global_step=e.global_step, adam_step=e.adam_step, names=[s.name for s in e.specs], hparams=self._hparams.values(),
                     num_speakers=self.num_speakers)
 
     def load_state_dict(self, sd, reset_step: bool = False):
@@ -100,4 +100,5 @@ class Tacotron:
             raise RuntimeError("checkpoint tensor inventory does not match this model's hyper-parameters")
         e.params.copy_(sd["params"]); e.bn_state.copy_(sd["bn_state"])
         e.adam_m.copy_(sd["adam_m"]); e.adam_v.copy_(sd["adam_v"])
+        e.adam_step = int(sd.get("adam_step", sd["global_step"]))      # the optimizer state is restored either way
         e.global_step = 0 if reset_step else int(sd["global_step"])    # train.py:194-205 (--initialize_path resets the step)

@@ -20,6 +20,7 @@ import torch
 
 from .hparams import hparams as _default_hparams, load_hparams
 from .models import create_model, get_most_recent_checkpoint
+from .tf_checkpoint import load_any
 
 EOS = 1                                                          # text/symbols.py: _pad=0, _eos=1
 
@@ -77,6 +78,8 @@ class Synthesizer:
             load_path = checkpoint_path
             if checkpoint_step is not None:
                 checkpoint_path = os.path.join(load_path, "model.ckpt-{}.pt".format(checkpoint_step))
+                if not os.path.exists(checkpoint_path):                  # a reference (TensorFlow) checkpoint of that step
+                    checkpoint_path = checkpoint_path[:-3]
             else:
                 checkpoint_path = get_most_recent_checkpoint(load_path)
         else:
@@ -87,7 +90,7 @@ class Synthesizer:
         self.model = create_model(self.hparams)
         self.model._precision, self.model._device = self._precision, self._device
         print("Loading checkpoint: %s" % checkpoint_path)
-        self._state = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        self._state = load_any(checkpoint_path, self.hparams, num_speakers)
         self._restored = False
         return self
 

@@ -25,6 +25,7 @@ from . import dist as dp
 from .datasets import DataFeeder
 from .hparams import hparams, hparams_debug_string, load_hparams, save_hparams
 from .models import create_model, get_most_recent_checkpoint
+from .tf_checkpoint import load_any
 
 
 class ValueWindow:                                              # utils/__init__.py:15-37
@@ -138,7 +139,7 @@ def train(log_dir, config, hp=hparams):
             model.initialize(batch["inputs"], batch["input_lengths"], num_speakers, batch.get("speaker_id"), batch["mel_targets"],
                              batch["linear_targets"], batch["loss_coeff"], is_randomly_initialized=is_randomly_initialized)
             if first and restore:
-                sd = torch.load(restore, map_location="cpu", weights_only=False)
+                sd = load_any(restore, hp, num_speakers)        # our .pt state or a reference TensorFlow checkpoint
                 model.load_state_dict(sd, reset_step=bool(config.initialize_path))         # train.py:189-205
                 log(("Resuming from checkpoint: %s" if config.load_path else "Initialized from checkpoint: %s") % restore, slack=True)
                 if config.initialize_path:

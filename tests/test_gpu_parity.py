@@ -247,6 +247,72 @@ def test_loss_is_linear_in_loss_coeff_full_size(tb, hp5):
     eng.close()
 
 
+def test_baseline_config_c3_multispeaker_train_full_size_vs_oracle(tb):
+    """BASELINE.json configs[2] per GPU: deepvoice, 3 speakers, batch 32, text 128, 800 mel frames, r=5 — one whole training
+    forward/backward in the benchmarked precision (tf32 mode) against the CPU oracle at the SAME size (the oracle takes a few
+    seconds per step on the host cores).  160 teacher-forced decoder steps and an 800-step post-net GRU with bf16 recurrent
+    weights: outputs <= 5e-2 max-abs (normalised spectrogram units), loss 2e-3 relative, whole-gradient cosine >= 0.99."""
+    hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice", batch_size=32)
+    S, N, Ti, To = 3, 32, 128, 800
+    named = tb.params.init_params(hp, S, seed=41, randomize_bn_state=True)
+    g = torch.Generator().manual_seed(6)
+    lengths = torch.randint(96, Ti + 1, (N,), generator=g).tolist(); lengths[0] = Ti
+    b = _batch(N, Ti, To, lengths, seed=21)
+    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref, ref_g, names = _oracle_grads(named, hp, b, S, spk, "deepvoice")
+    ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
+    eng = tb.Engine(hp, S, precision="tf32", named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    errs = {k: (out[k].cpu() - ref[k].detach()).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
+    eng.backward()
+    sc = eng.scalars()
+    cos, na, nb = _cosine(eng.named_gradients(), ref_g, sorted(ref_g))
+    print("C3 full size: errs", errs, "loss", sc["loss"], float(ls["loss"]), "cos", cos, "norms", na, nb)
+    assert max(errs.values()) <= 5e-2, errs
+    assert abs(sc["loss"] - float(ls["loss"])) <= 2e-3 * float(ls["loss"])
+    assert cos >= 0.99 and abs(na - nb) <= 5e-2 * nb
+    spk_g = [k for k in names if k.startswith("speaker")]
+    assert spk_g and all(eng.named_gradients()[k].abs().max().item() > 0 for k in spk_g)
+    eng.close()
+
+
+def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb):
+    """configs[3]: batch 1, 200 free-running decoder steps (1000 frames) + post-net, single speaker; configs[4]: batch 64,
+    4 speakers, text 200 (20 free-running steps here to bound the oracle's time; the step count does not change the code
+    path).  fp32 mode against the oracle: a free-running decoder feeds its own outputs back, so the bound is 2e-3."""
+    hp = tb.hparams.override(reduction_factor=5)
+    named = tb.params.init_params(hp, 1, seed=43, randomize_bn_state=True)
+    g = torch.Generator().manual_seed(7)
+    tok = torch.randint(2, 80, (1, 128), generator=g, dtype=torch.int32); tok[0, -1] = 1
+    L = torch.tensor([128], dtype=torch.int32)
+    with torch.no_grad():
+        ref = O.forward(named, hp, tok, L, 1, None, max_iters=200, speaker_mode="none")
+    eng = tb.Engine(hp, 1, precision="fp32", named_params=named)
+    out = eng.forward(tok, L, decoder_steps=200)
+    assert out["mel_outputs"].shape == (1, 1000, 80) and out["linear_outputs"].shape == (1, 1000, 1025)
+    errs = {k: (out[k].cpu() - ref[k]).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
+    print("C4 full size: errs", errs)
+    assert max(errs.values()) <= 2e-3, errs
+    eng.close()
+    hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice")
+    S, N, Ti = 4, 64, 200
+    named = tb.params.init_params(hp, S, seed=47, randomize_bn_state=True)
+    lengths = torch.randint(120, Ti + 1, (N,), generator=g).tolist(); lengths[3] = Ti
+    b = _batch(N, Ti, 5, lengths, seed=23)
+    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32)
+    with torch.no_grad():
+        ref = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, max_iters=20, speaker_mode="deepvoice")
+    for prec, lim in (("fp32", 2e-3), ("tf32", 8e-2)):
+        eng = tb.Engine(hp, S, precision=prec, named_params=named)
+        out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=20)
+        assert out["linear_outputs"].shape == (N, 100, 1025) and out["alignments"].shape == (N, Ti, 20)
+        errs = {k: (out[k].cpu() - ref[k]).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
+        print("C5 full size (%s): errs" % prec, errs)
+        assert max(errs.values()) <= lim, (prec, errs)
+        eng.close()
+
+
 def test_free_running_inference_matches_golden_and_oracle(tb, hp5, golden_setup):
     named, b = golden_setup
     gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_infer_small.npz"))
@@ -652,3 +718,50 @@ def test_train_and_synthesize_command_lines(tb, tmp_path):
     with pytest.raises(RuntimeError):
         s.synthesize(texts=["no tokenizer in this build"])
     s.close()
+
+
+def test_tf_checkpoint_export_import_resumes_identically(tb, hp5, golden_setup, tmp_path):
+    """A reference-format (TensorFlow tensor-bundle) checkpoint written from a trained model and read back continues the
+    run bit-identically; with the --initialize_path semantics (train.py:194-205) the global step restarts while Adam's own
+    update count (TF: beta powers) carries on."""
+    named, b = golden_setup
+    model = tb.create_model(hp5); model._precision = "fp32"
+    args = (b["inputs"], b["input_lengths"], 1, None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+    model.initialize(*args, is_randomly_initialized=True)
+    model.engine.load_named(named)
+    for _ in range(2):
+        model.engine.train_step(b)
+    prefix = str(tmp_path / "model.ckpt-2")
+    tb.tf_checkpoint.export_state(prefix, model.state_dict(), hp5, 1)
+    model.engine.train_step(b)
+    want = model.engine.params.clone()
+    loss3 = model.engine.scalars()["loss"]
+
+    m2 = tb.create_model(hp5); m2._precision = "fp32"
+    m2.initialize(*args, is_randomly_initialized=True)
+    m2.load_state_dict(tb.tf_checkpoint.load_any(tb.get_most_recent_checkpoint(str(tmp_path)), hp5, 1))
+    assert m2.engine.global_step == 2 and m2.engine.adam_step == 2
+    m2.engine.train_step(b)
+    assert torch.equal(m2.engine.params, want) and m2.engine.scalars()["loss"] == loss3
+
+    m3 = tb.create_model(hp5); m3._precision = "fp32"
+    m3.initialize(*args, is_randomly_initialized=False)
+    m3.load_state_dict(tb.tf_checkpoint.load_any(prefix, hp5, 1), reset_step=True)
+    assert m3.engine.global_step == 0 and m3.engine.adam_step == 2
+    m3.engine.train_step(b, is_randomly_initialized=False)
+    sc = m3.engine.scalars()
+    assert abs(sc["learning_rate"] - O.learning_rate(hp5, 0, False)) <= 1e-12 and sc["loss"] == loss3
+    # Adam bias correction with t = 3 (not 1): the update differs from a fresh optimizer's by exactly that factor
+    import math
+    lr_t3 = O.learning_rate(hp5, 0, False) * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)
+    P0 = tb.tf_checkpoint.load_any(prefix, hp5, 1)
+    gk = "attention/v"
+    lay = m3.engine.layout
+    o, n = lay.offsets[gk], lay.spec(gk).numel
+    g = m3.engine.grads[o:o + n].cpu().double()
+    gn = float(m3.engine.grads.double().norm())
+    gc = g * min(1.0, 1.0 / gn)
+    mm = 0.9 * P0["adam_m"][o:o + n].double() + 0.1 * gc
+    vv = 0.999 * P0["adam_v"][o:o + n].double() + 0.001 * gc * gc
+    expect = P0["params"][o:o + n].double() - lr_t3 * mm / (vv.sqrt() + 1e-8)
+    assert (m3.engine.params[o:o + n].cpu().double() - expect).abs().max().item() <= 1e-7
