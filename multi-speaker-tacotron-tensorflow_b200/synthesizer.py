@@ -46,6 +46,27 @@ def attention_trim_frames(alignment: np.ndarray, sequence_len: int, reduction_fa
     return reduction_factor * jdx + 3
 
 
+def librosa_trim_end(audio: np.ndarray, top_db: float = 50.0, frame_length: int = 5120, hop_length: int = 256) -> int:
+    """End index of ``librosa.effects.trim(audio, frame_length=5120, hop_length=256, top_db=50)`` — the only part of its result
+    the reference uses (synthesizer.py:266-269: ``audio_out[:index[-1]]``).  librosa 0.5.1: frame-wise mean-square energy over
+    uncentred frames (``feature.rmse(y=, n_fft=frame_length, hop_length=)``), in dB relative to the loudest frame
+    (``logamplitude(mse, ref_power=np.max, top_db=None)``, floor 1e-10); frames above ``-top_db`` are non-silent; the end is
+    ``min(len, (last_non_silent_frame + 1) * hop_length)``.  (librosa >= 0.6 centres the frames, which moves the cut by up to
+    frame_length/2 samples; the reference pins 0.5.1.)  Host post-processing of a finished waveform, not GPU work."""
+    y = np.asarray(audio, dtype=np.float64)
+    if len(y) < frame_length:
+        return len(y)
+    n_frames = 1 + (len(y) - frame_length) // hop_length
+    csum = np.concatenate([[0.0], np.cumsum(y * y)])
+    starts = np.arange(n_frames) * hop_length
+    mse = (csum[starts + frame_length] - csum[starts]) / frame_length
+    db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(max(1e-10, float(mse.max())))
+    nz = np.flatnonzero(db > -top_db)
+    if len(nz) == 0:
+        return 0
+    return int(min(len(y), (nz[-1] + 1) * hop_length))
+
+
 def wav_bytes(wav: np.ndarray, sample_rate: int) -> bytes:
     """audio.save_audio to an in-memory file (synthesizer.py:283-288): peak-normalised 16-bit PCM."""
     from scipy.io import wavfile
@@ -130,8 +151,10 @@ class Synthesizer:
             sequences = [list(t) for t in tokens]
         else:
             raise ValueError("synthesize needs texts= or tokens=")
-        if use_short_concat or librosa_trim:
-            raise NotImplementedError("short_concat / librosa_trim post-processing is not part of this build (SURVEY.md §8f row 4)")
+        if use_short_concat:
+            # synthesizer.py:301-389 cuts at word boundaries found through the Korean text front end (decompose_ko_text) and reads
+            # an undefined name (`decomposed_text`, :324,:334) on most of its branches; it is not reproduced
+            raise NotImplementedError("use_short_concat depends on the reference's Korean text front end (out of scope, SURVEY.md §8f)")
         n = len(sequences)
         paths = paths if paths is not None else [None] * n
         texts = texts if texts is not None else [None] * n
@@ -147,6 +170,7 @@ class Synthesizer:
             apath = os.path.join(base_alignment_path, os.path.basename(base_path))
             manual = np.transpose(np.stack([np.load("{}.{}.npy".format(apath, i)) for i in range(n)]), [0, 2, 1])
         spectrograms, alignments = self._run(seq, input_lengths, speaker_ids, manual)
+        self._librosa_trim = bool(librosa_trim)
         results = self._save(spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, manual is not None)
         if manual_attention_mode > 0:
             if manual_attention_mode not in (1, 3):
@@ -170,6 +194,8 @@ class Synthesizer:
             if self._gl is None or self._gl.max_frames < spec.shape[0]:
                 self._gl = GriffinLim(hp, max_frames=max(1024, spec.shape[0]), device=self._device)
             audio_out = self._gl.inv_spectrogram(torch.from_numpy(np.ascontiguousarray(spec))).cpu().numpy()    # synthesizer.py:264
+            if getattr(self, "_librosa_trim", False) and end_of_sentence:                                      # synthesizer.py:266-269
+                audio_out = audio_out[:librosa_trim_end(audio_out)]
             if path or base_path:
                 if path is None:
                     tag = ".manual" if manual else ""

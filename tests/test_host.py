@@ -248,3 +248,21 @@ def test_datafeeder_groups_sorts_and_feeds(tmp_path):
     finally:
         f.stop()
     assert test_feeder.static_batches is not None and len(test_feeder.static_batches) == 2
+
+
+def test_librosa_trim_end_matches_framewise_definition(tb):
+    """synthesizer.librosa_trim_end against librosa 0.5.1's effects.trim written out frame by frame."""
+    from importlib import import_module
+    syn = import_module("multi-speaker-tacotron-tensorflow_b200.synthesizer")
+    rng = np.random.RandomState(0)
+    y = np.concatenate([rng.randn(30000) * 0.3, rng.randn(20000) * 1e-4]).astype(np.float32)      # speech, then near-silence
+    fl, hop, top_db = 5120, 256, 50.0
+    frames = [y[i:i + fl].astype(np.float64) for i in range(0, len(y) - fl + 1, hop)]
+    mse = np.array([np.mean(f * f) for f in frames])
+    db = 10 * np.log10(np.maximum(1e-10, mse)) - 10 * np.log10(max(1e-10, mse.max()))
+    last = np.flatnonzero(db > -top_db)[-1]
+    want = min(len(y), (last + 1) * hop)
+    got = syn.librosa_trim_end(y)
+    assert got == want and 24000 < got < 31000
+    assert syn.librosa_trim_end(np.zeros(100, np.float32)) == 100                 # shorter than a frame: untouched
+    assert syn.librosa_trim_end(rng.randn(20000).astype(np.float32)) >= 20000 - fl   # no silence: (almost) nothing cut
