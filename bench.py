@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 METRIC = "mel-frames/sec (train, batch=32/GPU)"
 UNIT = "mel-frames/s"
 CFG = dict(N=32, T_in=128, T_out=800, num_mels=80, num_freq=1025, r=5)
+WORKLOAD = "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel, 1025-bin linear, r=5, single-speaker"
 # algorithmic HBM bytes of one training step per GPU (targets + params fwd/bwd + grads + clip/Adam)
 ALGO_BYTES_PER_STEP = 486.6e6
 # algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
@@ -224,7 +225,7 @@ def run_ours(args):
             "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel, 1025-bin linear, r=5, single-speaker",
+            "config": {"workload": WORKLOAD,
                        "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
                        "timing": "CUDA events per step on the compute stream, max over ranks"},
             "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96,
@@ -374,7 +375,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": 0, "ms_per_step": 1e3 * CFG["N"] * CFG["T_out"] / base["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "C2: train step, batch=32, text_len=128, mel_len=800, r=5 (CPU restatement of the TF graph; TF 1.x itself cannot be installed)"},
+            "config": {"workload": WORKLOAD, "global_batch": CFG["N"], "parallelism": "cpu",
+                       "note": "the reference's train step restated on torch-CPU (oracle/tacotron_oracle.py, pinned to the reference's own "
+                               "model code by tests/golden/ref_*.npz); TensorFlow 1.x itself cannot be installed here"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -48,8 +48,8 @@ def _oracle_step(named, hp, b):
 
 
 def _cosine(got, ref, names):
-    a = torch.cat([got[k].float().cpu().reshape(-1) for k in names])
-    b = torch.cat([ref[k].reshape(-1) for k in names])
+    a = torch.cat([got[k].cpu().reshape(-1) for k in names]).double()      # float64: a 9-million-term fp32 dot product is not
+    b = torch.cat([ref[k].reshape(-1) for k in names]).double()            # accurate enough to resolve 1 - cos ~ 1e-3
     return float((a @ b) / (a.norm() * b.norm())), float(a.norm()), float(b.norm())
 
 
@@ -742,7 +742,11 @@ def test_tf_checkpoint_export_import_resumes_identically(tb, hp5, golden_setup, 
     m2.load_state_dict(tb.tf_checkpoint.load_any(tb.get_most_recent_checkpoint(str(tmp_path)), hp5, 1))
     assert m2.engine.global_step == 2 and m2.engine.adam_step == 2
     m2.engine.train_step(b)
-    assert torch.equal(m2.engine.params, want) and m2.engine.scalars()["loss"] == loss3
+    # (not bit-identical: split-K GEMMs accumulate with atomics, so two runs differ in the last fp32 bit of some gradients)
+    before = tb.tf_checkpoint.load_any(prefix, hp5, 1)["params"].to(want.device)
+    upd_a, upd_b = (want - before).double(), (m2.engine.params - before).double()
+    assert float((upd_a @ upd_b) / (upd_a.norm() * upd_b.norm())) >= 0.9999 and (upd_a - upd_b).abs().max().item() <= 5e-7
+    assert abs(m2.engine.scalars()["loss"] - loss3) <= 1e-6
 
     m3 = tb.create_model(hp5); m3._precision = "fp32"
     m3.initialize(*args, is_randomly_initialized=False)
@@ -750,7 +754,7 @@ def test_tf_checkpoint_export_import_resumes_identically(tb, hp5, golden_setup, 
     assert m3.engine.global_step == 0 and m3.engine.adam_step == 2
     m3.engine.train_step(b, is_randomly_initialized=False)
     sc = m3.engine.scalars()
-    assert abs(sc["learning_rate"] - O.learning_rate(hp5, 0, False)) <= 1e-12 and sc["loss"] == loss3
+    assert abs(sc["learning_rate"] - O.learning_rate(hp5, 0, False)) <= 1e-12 and abs(sc["loss"] - loss3) <= 1e-6
     # Adam bias correction with t = 3 (not 1): the update differs from a fresh optimizer's by exactly that factor
     import math
     lr_t3 = O.learning_rate(hp5, 0, False) * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)
@@ -765,3 +769,40 @@ def test_tf_checkpoint_export_import_resumes_identically(tb, hp5, golden_setup, 
     vv = 0.999 * P0["adam_v"][o:o + n].double() + 0.001 * gc * gc
     expect = P0["params"][o:o + n].double() - lr_t3 * mm / (vv.sqrt() + 1e-8)
     assert (m3.engine.params[o:o + n].cpu().double() - expect).abs().max().item() <= 1e-7
+
+
+def test_generate_data_on_gpu_writes_the_reference_schema(tb, tmp_path):
+    """datasets/generate_data.py mirror: wav files + metadata -> .npz examples (generate_data.py:156-172 schema) whose features
+    equal the oracle's spectrogram()/melspectrogram() of the same audio, and which the DataFeeder reads back."""
+    import json
+    from importlib import import_module
+    from scipy.io import wavfile
+    import make_reference_golden as mr
+    gd = import_module("multi-speaker-tacotron-tensorflow_b200.datasets.generate_data")
+    df = import_module("multi-speaker-tacotron-tensorflow_b200.datasets.datafeeder")
+    root = tmp_path / "spk"
+    (root / "audio").mkdir(parents=True)
+    meta = {}
+    sigs = {}
+    for i, (n, sr) in enumerate(((48000, 24000), (60300, 24000), (32000, 16000))):
+        y = np.tile(mr.audio_signal(seed=20 + i), 6)[:n]
+        wavfile.write(str(root / "audio" / ("u%d.wav" % i)), sr, (y * 32767).astype(np.int16))
+        sigs[i] = (y * 32767).astype(np.int16).astype(np.float32) / 32768.0
+        meta["audio/u%d.wav" % i] = [2 + i, 5, 9, 1]                       # token-id lists (no text front end in this build)
+    meta["audio/missing.wav"] = [2, 1]
+    (root / "recognition.json").write_text(json.dumps(meta))
+    cfg = type("Cfg", (), dict(metadata_path=str(root / "recognition.json"), data_dirname="data", num_workers=None))()
+    lines = []
+    n_frames = gd.build_from_path(cfg, hp=tb.hparams, log=lines.append)
+    assert n_frames == [1 + 48000 // 300, 1 + 60300 // 300, 1 + 48000 // 300]      # the 16 kHz file is resampled to 24 kHz
+    assert any("Audio not found" in l for l in lines) and any("Loaded metadata for 3 examples" in l for l in lines)
+    for i in (0, 1):
+        with np.load(str(root / "data" / ("u%d.npz" % i))) as d:
+            assert set(d.files) == {"tokens", "mel", "linear", "loss_coeff"}
+            assert d["linear"].dtype == np.float32 and d["linear"].shape == (n_frames[i], 1025) and d["mel"].shape == (n_frames[i], 80)
+            assert list(d["tokens"]) == [2 + i, 5, 9, 1] and float(d["loss_coeff"]) == 1.0
+            assert np.abs(d["linear"] - G.spectrogram(sigs[i]).T).max() <= 2e-4
+            assert np.abs(d["mel"] - G.melspectrogram(sigs[i]).T).max() <= 2e-4
+    path, frames, ntok = df._frame_info(str(root / "data" / "u1.npz"))
+    assert frames == n_frames[1] and ntok == 4
+    assert gd.build_from_path(cfg, hp=tb.hparams, log=lines.append) == n_frames      # second run: everything is found on disk
