@@ -92,19 +92,31 @@ __device__ __forceinline__ float af_red_sum(const float* red, int slot0, int nsl
     for (int k = 0; k < nslots; k++) s += red[(slot0 + k * stride) * 128 + m * 8 + r];
     return s;
 }
-// load W[(r0 + m)*ld + c0 + k] (m < rows, k < K) -> dst[m*KP + k] as bf16 (natural orientation: rows of W are A rows)
-__device__ void af_load_rows(bf16* dst, int KP, const float* W, long long ld, int r0, int rows, int rows_pad, int c0, int K, int tid) {
-    for (int idx = tid; idx < rows_pad * K; idx += AF_NT) {
-        const int m = idx / K, k = idx % K;
-        dst[m * KP + k] = __float2bfloat16(m < rows ? __ldg(W + (long long)(r0 + m) * ld + c0 + k) : 0.f);
+// One-time operand loads (weights, keys, memory -> bf16 shared memory).  AF_LB loads are issued back to back before the first
+// is consumed: with one load in flight per thread this set-up cost ~50 us (forward) / ~100 us (backward) per launch — paid
+// once per sequence before, but once per time chunk under the decoder wavefront.
+constexpr int AF_LB = 8;
+template <typename Src, typename Dst>
+__device__ __forceinline__ void af_batched_fill(int total, int tid, int nt, Src src, Dst dst) {
+    for (int base = tid; base < total; base += nt * AF_LB) {
+        float v[AF_LB];
+#pragma unroll
+        for (int u = 0; u < AF_LB; u++) { const int idx = base + u * nt; v[u] = idx < total ? src(idx) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < AF_LB; u++) { const int idx = base + u * nt; if (idx < total) dst(idx, v[u]); }
     }
 }
+// load W[(r0 + m)*ld + c0 + k] (m < rows, k < K) -> dst[m*KP + k] as bf16 (natural orientation: rows of W are A rows)
+__device__ void af_load_rows(bf16* dst, int KP, const float* W, long long ld, int r0, int rows, int rows_pad, int c0, int K, int tid, int nt = AF_NT) {
+    af_batched_fill(rows_pad * K, tid, nt,
+        [&](int idx) { const int m = idx / K, k = idx % K; return m < rows ? __ldg(W + (long long)(r0 + m) * ld + c0 + k) : 0.f; },
+        [&](int idx, float v) { const int m = idx / K, k = idx % K; dst[m * KP + k] = __float2bfloat16(v); });
+}
 // load W[(r0 + k)*ld + c0 + m] -> dst[m*KP + k]  (transposed: columns of W become A rows)
-__device__ void af_load_cols(bf16* dst, int KP, const float* W, long long ld, int r0, int K, int c0, int cols, int cols_pad, int tid) {
-    for (int idx = tid; idx < cols_pad * K; idx += AF_NT) {
-        const int k = idx / cols_pad, m = idx % cols_pad;
-        dst[m * KP + k] = __float2bfloat16(m < cols ? __ldg(W + (long long)(r0 + k) * ld + c0 + m) : 0.f);
-    }
+__device__ void af_load_cols(bf16* dst, int KP, const float* W, long long ld, int r0, int K, int c0, int cols, int cols_pad, int tid, int nt = AF_NT) {
+    af_batched_fill(cols_pad * K, tid, nt,
+        [&](int idx) { const int k = idx / cols_pad, m = idx % cols_pad; return m < cols ? __ldg(W + (long long)(r0 + k) * ld + c0 + m) : 0.f; },
+        [&](int idx, float v) { const int k = idx / cols_pad, m = idx % cols_pad; dst[m * KP + k] = __float2bfloat16(v); });
 }
 
 __device__ long long g_af_prof[40];
@@ -163,9 +175,72 @@ struct AfFwdSmem {
     static constexpr size_t w_end = Woc + 16 * KP256 * 2;
 };
 
+// The operand image of one forward CTA = the first bytes of its shared memory: the bf16 weight slices [0, w_end) (they
+// depend on the cluster rank only) followed by its key rows and memory columns (rank and row group).  The fill functions
+// write an image either straight into shared memory or — once per step, att_fast_pack_kernel — into global memory, from
+// where every (chunk) launch pulls it with bulk async copies instead of ~50 us of strided fp32 loads.
+__device__ void af_fwd_fill_w(uint8_t* sm, const AttArgs& a, int rank, int tid, int nt) {
+    using S = AfFwdSmem;
+    constexpr int U = AF_U, UZ = AF_UZ, E = AF_E, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
+    bf16* W1c_s = reinterpret_cast<bf16*>(sm + S::W1c); bf16* W2_s = reinterpret_cast<bf16*>(sm + S::W2);
+    bf16* Wg_s = reinterpret_cast<bf16*>(sm + S::Wg);   bf16* Wcz_s = reinterpret_cast<bf16*>(sm + S::Wcz);
+    bf16* Wch_s = reinterpret_cast<bf16*>(sm + S::Wch); bf16* Wq_s = reinterpret_cast<bf16*>(sm + S::Wq);
+    bf16* Woh_s = reinterpret_cast<bf16*>(sm + S::Woh); bf16* Woc_s = reinterpret_cast<bf16*>(sm + S::Woc);
+    af_load_cols(W1c_s, S::KP256, a.W1c, Z1, 0, E, rank * U, U, 16, tid, nt);
+    af_load_cols(W2_s, S::KP256, a.W2, Z, 0, Z1, rank * UZ, UZ, 16, tid, nt);
+    af_load_cols(Wg_s, S::KP384, a.Wg, 2 * HA, 0, Z + HA, rank * U, U, 16, tid, nt);                      // r units
+    af_load_cols(Wg_s + 16 * S::KP384, S::KP384, a.Wg, 2 * HA, 0, Z + HA, HA + rank * U, U, 16, tid, nt); // u units
+    af_load_cols(Wcz_s, S::KP128, a.Wc, HA, 0, Z, rank * U, U, 16, tid, nt);
+    af_load_cols(Wch_s, S::KP256, a.Wc, HA, Z, HA, rank * U, U, 16, tid, nt);
+    af_load_cols(Wq_s, S::KP256, a.Wq, A, 0, HA, rank * U, U, 16, tid, nt);
+    af_load_cols(Woh_s, S::KP256, a.Wo, Y, 0, HA, rank * U, U, 16, tid, nt);
+    af_load_cols(Woc_s, S::KP256, a.Wo, Y, HA, E, rank * U, U, 16, tid, nt);
+}
+__host__ __device__ inline size_t af_fwd_km_bytes(int Ti) {
+    const int TJ = (Ti + AF_C - 1) / AF_C;
+    return (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2;
+}
+__device__ void af_fwd_fill_km(uint8_t* km, const AttArgs& a, int rank, int grp, int tid, int nt) {
+    constexpr int R = AF_R, U = AF_U, E = AF_E, A = AF_A;
+    const int Ti = a.Ti, TJ = (Ti + AF_C - 1) / AF_C, MRS = Ti * AF_U + 16;
+    bf16* keys_s = reinterpret_cast<bf16*>(km);                                        // [R][TJ][A]
+    bf16* mem_s = reinterpret_cast<bf16*>(km + (size_t)R * TJ * A * 2);                // [R][Ti][U] (+pad)
+    af_batched_fill(R * TJ * A, tid, nt,
+        [&](int idx) { const int u = idx % A, jj = (idx / A) % TJ, r = idx / (A * TJ), n = grp * R + r, j = rank * TJ + jj;
+                       return (n < a.N && j < Ti) ? __ldg(a.keys + ((long long)n * Ti + j) * A + u) : 0.f; },
+        [&](int idx, float v) { keys_s[idx] = __float2bfloat16(v); });
+    af_batched_fill(R * Ti * U, tid, nt,
+        [&](int idx) { const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
+                       return n < a.N ? __ldg(a.memory + ((long long)n * Ti + j) * E + rank * U + i) : 0.f; },
+        [&](int idx, float v) { const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti); mem_s[(size_t)r * MRS + j * U + i] = __float2bfloat16(v); });
+    for (int idx = tid; idx < R * 16; idx += nt) mem_s[(size_t)(idx / 16) * MRS + Ti * U + (idx % 16)] = __float2bfloat16(0.f);   // row padding
+}
+// Pull an image from global memory into shared memory: thread 0 issues bulk async copies (<= 32 KB each) that complete on
+// `bar`; every thread then waits for the barrier's first phase.  dst / src / bytes are multiples of 16.
+__device__ __forceinline__ void af_pull_image(uint8_t* dst, const uint8_t* src, size_t bytes, uint8_t* dst2, const uint8_t* src2, size_t bytes2,
+                                              uint64_t* bar, int tid) {
+    if (tid == 0) {
+        af_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        af_expect(bar, (uint32_t)(bytes + bytes2));
+        for (int part = 0; part < 2; part++) {
+            uint8_t* d = part ? dst2 : dst; const uint8_t* g = part ? src2 : src; const size_t nb = part ? bytes2 : bytes;
+            for (size_t off = 0; off < nb; off += 32768) {
+                const uint32_t n = (uint32_t)((nb - off) < 32768 ? (nb - off) : 32768);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(af_u32(d + off)), "l"(g + off), "r"(n), "r"(af_u32(bar)) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    af_wait(bar, 0);
+}
+
 template <int DUMMY>
 __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a) {
     cg::cluster_group cl = cg::this_cluster();
+    const long long c_entry = clock64();
+    unsigned long long ns_entry; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_entry));
     const int rank = (int)cl.block_rank();
     const int grp = blockIdx.x / AF_C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,31 +276,35 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);                                 // 7 barriers
     uint64_t *b_z1 = bars, *b_z = bars + 1, *b_rha = bars + 2, *b_ha = bars + 3, *b_q = bars + 4, *b_e = bars + 5, *b_ctx = bars + 6;
 
-    // ---- one-time loads --------------------------------------------------------------------------------------
-    af_load_cols(W1c_s, S::KP256, a.W1c, Z1, 0, E, rank * U, U, 16, tid);
-    af_load_cols(W2_s, S::KP256, a.W2, Z, 0, Z1, rank * UZ, UZ, 16, tid);
-    af_load_cols(Wg_s, S::KP384, a.Wg, 2 * HA, 0, Z + HA, rank * U, U, 16, tid);                      // r units
-    af_load_cols(Wg_s + 16 * S::KP384, S::KP384, a.Wg, 2 * HA, 0, Z + HA, HA + rank * U, U, 16, tid); // u units
-    af_load_cols(Wcz_s, S::KP128, a.Wc, HA, 0, Z, rank * U, U, 16, tid);
-    af_load_cols(Wch_s, S::KP256, a.Wc, HA, Z, HA, rank * U, U, 16, tid);
-    af_load_cols(Wq_s, S::KP256, a.Wq, A, 0, HA, rank * U, U, 16, tid);
-    af_load_cols(Woh_s, S::KP256, a.Wo, Y, 0, HA, rank * U, U, 16, tid);
-    af_load_cols(Woc_s, S::KP256, a.Wo, Y, HA, E, rank * U, U, 16, tid);
-    for (int idx = tid; idx < R * TJ * A; idx += AF_NT) {
-        const int u = idx % A, jj = (idx / A) % TJ, r = idx / (A * TJ), n = grp * R + r, j = rank * TJ + jj;
-        keys_s[idx] = __float2bfloat16((n < a.N && j < Ti) ? a.keys[((long long)n * Ti + j) * A + u] : 0.f);
-    }
-    for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
-        const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
-        mem_s[(size_t)r * MRS + j * U + i] = __float2bfloat16(n < a.N ? a.memory[((long long)n * Ti + j) * E + rank * U + i] : 0.f);
+    // ---- one-time loads (see af_fwd_fill_w) -------------------------------------------------------------------
+    if (a.img_w && a.img_km) {
+        const size_t kmb = af_fwd_km_bytes(Ti);
+        af_pull_image(sm, a.img_w + (size_t)rank * S::w_end, S::w_end, sm + S::w_end, a.img_km + (size_t)blockIdx.x * kmb, kmb, bars + 7, tid);
+    } else {
+        af_fwd_fill_w(sm, a, rank, tid, AF_NT);
+        af_fwd_fill_km(sm + S::w_end, a, rank, grp, tid, AF_NT);
     }
     for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
-    for (int idx = tid; idx < R * E; idx += AF_NT) ctx_s[idx] = __float2bfloat16(0.f);
+    // time chunk [t_lo, t_hi): a chunk that does not start the sequence restores its state from the stash of step t_lo-1
+    // (s_ha / s_ctx / s_a hold exactly the fp32 values the loop carries, so a chunked run equals the unchunked one)
+    const int t_lo = a.t_begin, t_hi = a.t_end > 0 ? min(a.t_end, Td) : Td;
+    const bool resume = t_lo > 0;
+    for (int idx = tid; idx < R * E; idx += AF_NT) {        // blocked [C][R][U]
+        const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
+        ctx_s[idx] = __float2bfloat16((resume && n < a.N) ? a.s_ctx[((long long)n * Td + t_lo - 1) * E + blk * U + i] : 0.f);
+    }
     for (int idx = tid; idx < R * HA; idx += AF_NT) {       // blocked [C][R][U]
         const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
-        ha_s[idx] = __float2bfloat16((a.ha0 && n < a.N) ? a.ha0[(long long)n * HA + blk * U + i] : 0.f);
+        float hv = 0.f;
+        if (n < a.N) hv = resume ? a.s_ha[((long long)n * Td + t_lo - 1) * HA + blk * U + i] : (a.ha0 ? a.ha0[(long long)n * HA + blk * U + i] : 0.f);
+        ha_s[idx] = __float2bfloat16(hv);
     }
-    for (int idx = tid; idx < R * TipP; idx += AF_NT) a_s[idx] = (a.att_type == TACO_ATT_BAH_MON && (idx % TipP) == 0) ? 1.f : 0.f;
+    for (int idx = tid; idx < R * TipP; idx += AF_NT) {
+        const int j = idx % TipP, r = idx / TipP, n = grp * R + r;
+        float av = (a.att_type == TACO_ATT_BAH_MON && j == 0) ? 1.f : 0.f;
+        if (resume) av = (n < a.N && j < Ti) ? a.s_a[((long long)n * Td + t_lo - 1) * Ti + j] : 0.f;
+        a_s[idx] = av;
+    }
     if (tid == 0) {
         for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -237,17 +316,20 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     const int an = grp * R + ar;
     const bool aok = act && an < a.N;
     const int unit = rank * U + ai;
-    float ha_own = (aok && a.ha0) ? a.ha0[(long long)an * HA + unit] : 0.f;
-    float px_next = aok ? __ldg(a.px + ((long long)an * Td + 0) * Z1 + unit) : 0.f;
+    float ha_own = 0.f;
+    if (aok) ha_own = resume ? a.s_ha[((long long)an * Td + t_lo - 1) * HA + unit] : (a.ha0 ? a.ha0[(long long)an * HA + unit] : 0.f);
+    float px_next = aok ? __ldg(a.px + ((long long)an * Td + t_lo) * Z1 + unit) : 0.f;
     const float bg_r = act ? __ldg(a.bg + unit) : 0.f, bg_u = act ? __ldg(a.bg + HA + unit) : 0.f;
     const float bc_own = act ? __ldg(a.bc + unit) : 0.f, bo_own = act ? __ldg(a.bo + unit) : 0.f;
     const float b2_own = (tid < UZ * R) ? __ldg(a.b2 + rank * UZ + (tid % UZ)) : 0.f;
-    float ctx_prev = 0.f;                     // fp32 context of the previous step (own unit), for the W1c-gradient stash
+    float ctx_prev = (resume && aok) ? a.s_ctx[((long long)an * Td + t_lo - 1) * E + unit] : 0.f;   // fp32 context of the previous step (own unit), for the W1c-gradient stash
+    const long long c_loaded = clock64();
     __syncthreads();
     cl.sync();
 
     const bool prof = (blockIdx.x == 0 && tid == 0);
     long long pacc[20]; for (int q = 0; q < 20; q++) pacc[q] = 0; long long plast = clock64();
+    pacc[15] = c_loaded - c_entry; pacc[16] = plast - c_loaded;      // set-up: operand loads | first cluster barrier
     // per-lane constants of the alignment scan (warp r = row r, lane owns the contiguous chunk [lane*CH, lane*CH+CH))
     constexpr int CHM = 8;
     const int CH = (Tip + 31) / 32;
@@ -255,8 +337,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
 #pragma unroll
     for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = ((j / TJ) * R + warp) * TJ + (j % TJ); }
     const bool writer = (rank == (warp % AF_C)) && (grp * R + warp < a.N);     // this warp stores row `warp`'s alignments / stash
-    for (int t = 0; t < Td; t++) {
-        const uint32_t par = t & 1;
+    for (int t = t_lo; t < t_hi; t++) {
+        const uint32_t par = (t - t_lo) & 1;
         const long long row = (long long)an * Td + t;
         const float px_cur = px_next;
         if (tid == 0) {
@@ -547,7 +629,11 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
         __syncthreads();     // `red` is rewritten by the next step's P1
         AF_T(14);
     }
-    if (prof) { for (int q = 0; q < 20; q++) g_af_prof[q] = pacc[q]; }
+    if (prof) {
+        unsigned long long ns_exit; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_exit));
+        pacc[17] = (long long)(ns_exit - ns_entry);                     // nanoseconds inside the kernel (CTA 0)
+        for (int q = 0; q < 20; q++) g_af_prof[q] = pacc[q];
+    }
     if (a.ha_final && aok) a.ha_final[(long long)an * HA + unit] = ha_own;
     cl.sync();
 }
@@ -565,9 +651,66 @@ struct AfBwdSmem {
     static constexpr size_t w_end = W2 + 16 * KP128 * 2;
 };
 
+// backward operand image (same scheme as af_fwd_fill_w / af_fwd_fill_km)
+__device__ void af_bwd_fill_w(uint8_t* sm, const AttArgs& a, int rank, int tid, int nt) {
+    using S = AfBwdSmem;
+    constexpr int U = AF_U, UZ = AF_UZ, A = AF_A, HA = AF_HA, Z1 = AF_Z1, Z = AF_Z, Y = AF_Y;
+    bf16* Wo_s = reinterpret_cast<bf16*>(sm + S::Wo);   bf16* Wq_s = reinterpret_cast<bf16*>(sm + S::Wq);
+    bf16* Wch_s = reinterpret_cast<bf16*>(sm + S::Wch); bf16* Wcz_s = reinterpret_cast<bf16*>(sm + S::Wcz);
+    bf16* W1c_s = reinterpret_cast<bf16*>(sm + S::W1c); bf16* Wgh_s = reinterpret_cast<bf16*>(sm + S::Wgh);
+    bf16* Wgz_s = reinterpret_cast<bf16*>(sm + S::Wgz); bf16* W2_s = reinterpret_cast<bf16*>(sm + S::W2);
+    // natural-orientation weight rows (data-gradient products): A row = weight row of the owned input unit
+    af_load_rows(Wo_s, S::KP256, a.Wo, Y, rank * U, U, 16, 0, Y, tid, nt);
+    af_load_rows(Wo_s + 16 * S::KP256, S::KP256, a.Wo, Y, HA + rank * U, U, 16, 0, Y, tid, nt);
+    af_load_rows(Wq_s, S::KP256, a.Wq, A, rank * U, U, 16, 0, A, tid, nt);
+    af_load_rows(Wch_s, S::KP256, a.Wc, HA, Z + rank * U, U, 16, 0, HA, tid, nt);
+    af_load_rows(Wcz_s, S::KP256, a.Wc, HA, rank * UZ, UZ, 16, 0, HA, tid, nt);
+    af_load_rows(W1c_s, S::KP256, a.W1c, Z1, rank * U, U, 16, 0, Z1, tid, nt);
+    af_load_rows(Wgh_s, S::KP512, a.Wg, 2 * HA, Z + rank * U, U, 16, 0, 2 * HA, tid, nt);
+    af_load_rows(Wgz_s, S::KP512, a.Wg, 2 * HA, rank * UZ, UZ, 16, 0, 2 * HA, tid, nt);
+    af_load_rows(W2_s, S::KP128, a.W2, Z, rank * U, U, 16, 0, Z, tid, nt);
+}
+__host__ __device__ inline size_t af_bwd_km_bytes(int Ti) {
+    const int TJ = (Ti + AF_C - 1) / AF_C;
+    return (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2;
+}
+__device__ void af_bwd_fill_km(uint8_t* km, const AttArgs& a, int rank, int grp, int tid, int nt) {
+    constexpr int R = AF_R, U = AF_U, E = AF_E, A = AF_A;
+    const int Ti = a.Ti, TJ = (Ti + AF_C - 1) / AF_C, KRS = Ti * AF_U + 16;
+    bf16* memj_s = reinterpret_cast<bf16*>(km);                                        // [R][TJ][E]   own memory positions
+    bf16* keyu_s = reinterpret_cast<bf16*>(km + (size_t)R * TJ * E * 2);               // [R][Ti][U] (+pad)   own attention units
+    af_batched_fill(R * TJ * E, tid, nt,
+        [&](int idx) { const int u = idx % E, jj = (idx / E) % TJ, r = idx / (E * TJ), n = grp * R + r, j = rank * TJ + jj;
+                       return (n < a.N && j < Ti) ? __ldg(a.memory + ((long long)n * Ti + j) * E + u) : 0.f; },
+        [&](int idx, float v) { memj_s[idx] = __float2bfloat16(v); });
+    af_batched_fill(R * Ti * U, tid, nt,
+        [&](int idx) { const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
+                       return n < a.N ? __ldg(a.keys + ((long long)n * Ti + j) * A + rank * U + i) : 0.f; },
+        [&](int idx, float v) { const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti); keyu_s[(size_t)r * KRS + j * U + i] = __float2bfloat16(v); });
+    for (int idx = tid; idx < R * 16; idx += nt) keyu_s[(size_t)(idx / 16) * KRS + Ti * U + (idx % 16)] = __float2bfloat16(0.f);
+}
+
+// Builds the operand images once per step.  what: 0 = weight slices (grid = AF_C blocks, block = cluster rank),
+// 1 = key / memory slices (grid = one block per CTA of the recurrence kernel).
+template <int BWD>
+__global__ void __launch_bounds__(1024) att_fast_pack_kernel(const AttArgs a, uint8_t* img_w, uint8_t* img_km, int what) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (what == 0) {
+        const int rank = blockIdx.x;
+        if (BWD) af_bwd_fill_w(img_w + (size_t)rank * AfBwdSmem::w_end, a, rank, tid, nt);
+        else af_fwd_fill_w(img_w + (size_t)rank * AfFwdSmem::w_end, a, rank, tid, nt);
+    } else {
+        const int rank = blockIdx.x % AF_C, grp = blockIdx.x / AF_C;
+        if (BWD) af_bwd_fill_km(img_km + (size_t)blockIdx.x * af_bwd_km_bytes(a.Ti), a, rank, grp, tid, nt);
+        else af_fwd_fill_km(img_km + (size_t)blockIdx.x * af_fwd_km_bytes(a.Ti), a, rank, grp, tid, nt);
+    }
+}
+
 template <int DUMMY>
 __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a) {
     cg::cluster_group cl = cg::this_cluster();
+    const long long c_entry = clock64();
+    unsigned long long ns_entry; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_entry));
     const int rank = (int)cl.block_rank();
     const int grp = blockIdx.x / AF_C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -606,26 +749,22 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
     uint64_t *b_dctx = bars, *b_da = bars + 1, *b_gq = bars + 2, *b_dcp = bars + 3, *b_dg = bars + 4, *b_dzp = bars + 5, *b_dz1p = bars + 6;
 
-    // natural-orientation weight rows (data-gradient products): A row = weight row of the owned input unit
-    af_load_rows(Wo_s, S::KP256, a.Wo, Y, rank * U, U, 16, 0, Y, tid);
-    af_load_rows(Wo_s + 16 * S::KP256, S::KP256, a.Wo, Y, HA + rank * U, U, 16, 0, Y, tid);
-    af_load_rows(Wq_s, S::KP256, a.Wq, A, rank * U, U, 16, 0, A, tid);
-    af_load_rows(Wch_s, S::KP256, a.Wc, HA, Z + rank * U, U, 16, 0, HA, tid);
-    af_load_rows(Wcz_s, S::KP256, a.Wc, HA, rank * UZ, UZ, 16, 0, HA, tid);
-    af_load_rows(W1c_s, S::KP256, a.W1c, Z1, rank * U, U, 16, 0, Z1, tid);
-    af_load_rows(Wgh_s, S::KP512, a.Wg, 2 * HA, Z + rank * U, U, 16, 0, 2 * HA, tid);
-    af_load_rows(Wgz_s, S::KP512, a.Wg, 2 * HA, rank * UZ, UZ, 16, 0, 2 * HA, tid);
-    af_load_rows(W2_s, S::KP128, a.W2, Z, rank * U, U, 16, 0, Z, tid);
-    for (int idx = tid; idx < R * TJ * E; idx += AF_NT) {
-        const int u = idx % E, jj = (idx / E) % TJ, r = idx / (E * TJ), n = grp * R + r, j = rank * TJ + jj;
-        memj_s[idx] = __float2bfloat16((n < a.N && j < Ti) ? a.memory[((long long)n * Ti + j) * E + u] : 0.f);
-    }
-    for (int idx = tid; idx < R * Ti * U; idx += AF_NT) {
-        const int i = idx % U, j = (idx / U) % Ti, r = idx / (U * Ti), n = grp * R + r;
-        keyu_s[(size_t)r * KRS + j * U + i] = __float2bfloat16(n < a.N ? a.keys[((long long)n * Ti + j) * A + rank * U + i] : 0.f);
+    if (a.img_w && a.img_km) {
+        const size_t kmb = af_bwd_km_bytes(Ti);
+        af_pull_image(sm, a.img_w + (size_t)rank * S::w_end, S::w_end, sm + S::w_end, a.img_km + (size_t)blockIdx.x * kmb, kmb, bars + 7, tid);
+    } else {
+        af_bwd_fill_w(sm, a, rank, tid, AF_NT);
+        af_bwd_fill_km(sm + S::w_end, a, rank, grp, tid, AF_NT);
     }
     for (int u = tid; u < A; u += AF_NT) v_s[u] = a.v[u];
-    for (int idx = tid; idx < R * Tip; idx += AF_NT) dac_s[idx] = 0.f;
+    // time chunk [t_lo, t_hi), processed downwards; the gradients carried across steps (wrt ha, context, alignments) come in
+    // from the chunk above through c_dha / c_dctx / c_dac when c_in is set and are handed on the same way at the end
+    const int t_lo = a.t_begin, t_hi = a.t_end > 0 ? min(a.t_end, Td) : Td;
+    const bool carry_in = a.c_in != 0 && a.c_dha && a.c_dctx && a.c_dac;
+    for (int idx = tid; idx < R * Tip; idx += AF_NT) {
+        const int r = idx / Tip, j = idx % Tip, n = grp * R + r;
+        dac_s[idx] = (carry_in && n < a.N) ? a.c_dac[(long long)n * Tip + j] : 0.f;
+    }
     for (int idx = tid; idx < R * TipP; idx += AF_NT) ge_s[idx] = 0.f;
     if (tid == 0) {
         for (int i = 0; i < 7; i++) af_mbar_init(bars + i, 1);
@@ -640,11 +779,14 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     const int jq = tid >> 6, jr = (tid >> 3) & 7, jip = tid & 7;
     const int jn_ = grp * R + jr;
     float dha_carry = 0.f, dctx_carry = 0.f, gbias_acc = 0.f;
+    if (carry_in && aok) { dha_carry = a.c_dha[(long long)an * HA + unit]; dctx_carry = a.c_dctx[(long long)an * E + unit]; }
+    const long long c_loaded = clock64();
     __syncthreads();
     cl.sync();
 
     const bool prof = (blockIdx.x == 0 && tid == 0);
     long long pacc[20]; for (int q = 0; q < 20; q++) pacc[q] = 0; long long plast = clock64();
+    pacc[15] = c_loaded - c_entry; pacc[16] = plast - c_loaded;      // set-up: operand loads | first cluster barrier
     // ---- per-thread constants and the one-step-ahead prefetch of everything this loop reads from global memory ----
     constexpr int CHM = 8;
     const int CH = (Tip + 31) / 32;
@@ -660,7 +802,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     float n_rg = 0.f, n_ug = 0.f, n_cc = 0.f, n_hp = 0.f, n_z1 = 0.f, n_z = 0.f, n_q0 = 0.f, n_q1 = 0.f;
     float n_dy[R], n_e[CHM], n_ap[CHM];
     auto prefetch = [&](int tt) {
-        if (tt < 0) return;
+        if (tt < t_lo) return;
         if (aok) {
             const long long o = ((long long)an * Td + tt) * HA + unit;
             n_rg = a.s_r[o]; n_ug = a.s_u[o]; n_cc = a.s_c[o]; n_hp = a.s_haprev[o];
@@ -686,9 +828,9 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             }
         }
     };
-    prefetch(Td - 1);
+    prefetch(t_hi - 1);
     int it = 0;
-    for (int t = Td - 1; t >= 0; t--, it++) {
+    for (int t = t_hi - 1; t >= t_lo; t--, it++) {
         const uint32_t par = it & 1;
         const long long row = (long long)an * Td + t;
         if (tid == 0) {
@@ -1060,8 +1202,21 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         __syncthreads();
         AF_T(14);
     }
-    if (prof) { for (int q = 0; q < 20; q++) g_af_prof[20 + q] = pacc[q]; }
-    if (a.d_ha0 && aok) a.d_ha0[(long long)an * HA + unit] = dha_carry;
+    if (prof) {
+        unsigned long long ns_exit; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_exit));
+        pacc[17] = (long long)(ns_exit - ns_entry);
+        for (int q = 0; q < 20; q++) g_af_prof[20 + q] = pacc[q];
+    }
+    if (a.d_ha0 && aok && t_lo == 0) a.d_ha0[(long long)an * HA + unit] = dha_carry;
+    if (a.c_dha && a.c_dctx && a.c_dac) {                       // hand the carries to the chunk below
+        if (aok) { a.c_dha[(long long)an * HA + unit] = dha_carry; a.c_dctx[(long long)an * E + unit] = dctx_carry; }
+        if (rank == 0) {
+            for (int idx = tid; idx < R * Tip; idx += AF_NT) {
+                const int r = idx / Tip, j = idx % Tip, n = grp * R + r;
+                if (n < a.N) a.c_dac[(long long)n * Tip + j] = dac_s[idx];
+            }
+        }
+    }
     if (rank == 0 && lane == 0 && a.d_score_bias && a.att_type == TACO_ATT_BAH_MON) atomicAdd(a.d_score_bias, gbias_acc);
     cl.sync();
 }
@@ -1113,12 +1268,30 @@ static int af_launch(K kern, const AttArgs& a, size_t smem, int& configured, cud
     return TACO_OK;
 }
 
+void att_fast_image_bytes(int Ti, bool bwd, size_t* w_bytes, size_t* km_bytes_per_cta) {
+    *w_bytes = (size_t)AF_C * (bwd ? AfBwdSmem::w_end : AfFwdSmem::w_end);
+    *km_bytes_per_cta = bwd ? af_bwd_km_bytes(Ti) : af_fwd_km_bytes(Ti);
+}
+// what: 0 weight slices, 1 key / memory slices (see att_fast_pack_kernel)
+int launch_att_fast_pack(const AttArgs& a, bool bwd, int what, uint8_t* img_w, uint8_t* img_km, cudaStream_t s) {
+    const int blocks = what == 0 ? AF_C : AF_C * cdiv(a.N, AF_R);
+    if (bwd) att_fast_pack_kernel<1><<<blocks, 1024, 0, s>>>(a, img_w, img_km, what);
+    else att_fast_pack_kernel<0><<<blocks, 1024, 0, s>>>(a, img_w, img_km, what);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s) {
     static int configured = 0;
+    TACO_REQUIRE(a.t_begin >= 0 && (a.t_end == 0 || (a.t_begin < a.t_end && a.t_end <= a.Td)), TACO_EINVAL, "attention: bad time chunk [%d, %d)", a.t_begin, a.t_end);
+    TACO_REQUIRE(a.t_begin == 0 || (a.s_ha && a.s_ctx && a.s_a), TACO_EINVAL, "attention: a chunk with t_begin > 0 restores its state from the training stash");
     return af_launch(att_fast_fwd_kernel<0>, a, af_fwd_smem(a.Ti), configured, s);
 }
 int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s) {
     static int configured = 0;
+    TACO_REQUIRE(a.t_begin >= 0 && (a.t_end == 0 || (a.t_begin < a.t_end && a.t_end <= a.Td)), TACO_EINVAL, "attention: bad time chunk [%d, %d)", a.t_begin, a.t_end);
+    TACO_REQUIRE((a.t_begin == 0 && (a.t_end == 0 || a.t_end == a.Td) && !a.c_in) || (a.c_dha && a.c_dctx && a.c_dac), TACO_EINVAL,
+                 "attention: backward time chunks need the carry buffers");
     return af_launch(att_fast_bwd_kernel<0>, a, af_bwd_smem(a.Ti), configured, s);
 }
 

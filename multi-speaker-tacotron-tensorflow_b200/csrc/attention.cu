@@ -912,12 +912,14 @@ static int att_launch(K kern, const AttArgs& a, bool bwd, cudaStream_t s) {
 int launch_att_fwd(const AttArgs& a, cudaStream_t s) {
     TACO_TRY(att_check(a));
     if (a.fast && !a.free_run && att_fast_supported(a)) { int rc = launch_att_fast_fwd(a, s); if (rc != TACO_ENOTSUP) return rc; }
+    TACO_REQUIRE(a.t_begin == 0 && (a.t_end == 0 || a.t_end == a.Td), TACO_EINVAL, "attention: the exact kernels do not run time chunks");
     return a.fast ? att_launch(att_fwd_kernel<true>, a, false, s) : att_launch(att_fwd_kernel<false>, a, false, s);
 }
 int launch_att_bwd(const AttArgs& a, cudaStream_t s) {
     TACO_TRY(att_check(a));
     TACO_REQUIRE(a.dy0 && a.d_G && a.d_zp && a.d_z1p && a.d_ctx && a.s_e && a.s_a && a.s_q, TACO_EINVAL, "attention bwd: missing buffers");
     if (a.fast && att_fast_supported(a)) { int rc = launch_att_fast_bwd(a, s); if (rc != TACO_ENOTSUP) return rc; }
+    TACO_REQUIRE(a.t_begin == 0 && (a.t_end == 0 || a.t_end == a.Td) && !a.c_in, TACO_EINVAL, "attention: the exact kernels do not run time chunks");
     return a.fast ? att_launch(att_bwd_kernel<true>, a, true, s) : att_launch(att_bwd_kernel<false>, a, true, s);
 }
 int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,

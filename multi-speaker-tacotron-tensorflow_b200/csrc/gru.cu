@@ -336,11 +336,13 @@ static int check_gru_args(const GruArgs& a, bool bwd) {
 int launch_gru_fwd(const GruArgs& a, cudaStream_t s) {
     TACO_TRY(check_gru_args(a, false));
     if (a.fast) return launch_gru_fast_fwd(a, s);
+    TACO_REQUIRE(a.t_begin == 0 && a.t_end == 0 && !a.dh_in, TACO_EINVAL, "gru: the exact kernels do not run time chunks");
     return a.H == 128 ? launch_gru_t<128>(a, false, s) : launch_gru_t<256>(a, false, s);
 }
 int launch_gru_bwd(const GruArgs& a, cudaStream_t s) {
     TACO_TRY(check_gru_args(a, true));
     if (a.fast) return launch_gru_fast_bwd(a, s);
+    TACO_REQUIRE(a.t_begin == 0 && a.t_end == 0 && !a.dh_in, TACO_EINVAL, "gru: the exact kernels do not run time chunks");
     return a.H == 128 ? launch_gru_t<128>(a, true, s) : launch_gru_t<256>(a, true, s);
 }
 

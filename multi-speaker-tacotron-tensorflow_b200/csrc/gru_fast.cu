@@ -154,14 +154,24 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
 
     const float* __restrict__ Wg = a.Wg[d];
     const float* __restrict__ Wc = a.Wc[d];
-    for (int idx = tid; idx < GC * H; idx += GF_NT) {
-        const int k = idx / GC, col = idx % GC;
-        const int gcol = (col < U) ? rank * U + col : H + rank * U + (col - U);
-        Wg_s[col * KP + k] = __float2bfloat16(__ldg(Wg + (long long)k * 2 * H + gcol));
+    // (loads issued in batches of 8 before the first use: this set-up is paid once per time chunk under the decoder wavefront)
+    for (int base = tid; base < GC * H; base += GF_NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = base + u * GF_NT, k = idx / GC, col = idx % GC;
+            const int gcol = (col < U) ? rank * U + col : H + rank * U + (col - U);
+            v[u] = idx < GC * H ? __ldg(Wg + (long long)k * 2 * H + gcol) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; if (idx < GC * H) Wg_s[(idx % GC) * KP + idx / GC] = __float2bfloat16(v[u]); }
     }
-    for (int idx = tid; idx < U * H; idx += GF_NT) {
-        const int k = idx / U, col = idx % U;
-        Wc_s[col * KP + k] = __float2bfloat16(__ldg(Wc + (long long)k * H + rank * U + col));
+    for (int base = tid; base < U * H; base += GF_NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; v[u] = idx < U * H ? __ldg(Wc + (long long)(idx / U) * H + rank * U + idx % U) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; if (idx < U * H) Wc_s[(idx % U) * KP + idx / U] = __float2bfloat16(v[u]); }
     }
     for (int idx = tid; idx < R * H; idx += GF_NT) {       // hb_s[(k/U)][r][k%U]
         const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
@@ -207,9 +217,10 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
             if (a.res) gres = __ldg(a.res + ((long long)n * a.T + t) * a.res_ld + unit);
         }
     };
-    load_gx(0);
-    for (int s = 0; s < Lmax; s++) {
-        const uint32_t par = s & 1;
+    const int s_begin = a.t_begin, s_end = a.t_end > 0 ? min(a.t_end, Lmax) : Lmax;      // chunked: steps [t_begin, t_end)
+    load_gx(s_begin);
+    for (int s = s_begin; s < s_end; s++) {
+        const uint32_t par = (s - s_begin) & 1;
         const bool valid = act && (s < L);
         const int t = (d == 0) ? s : (L - 1 - s);
         const float cgr = gr, cgu = gu, cgc = gc, cres = gres;
@@ -318,13 +329,19 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
 
     const float* __restrict__ Wg = a.Wg[d];
     const float* __restrict__ Wc = a.Wc[d];
-    for (int idx = tid; idx < U * H; idx += GF_NT) {
-        const int ii = idx / H, cu = idx % H;
-        WcT_s[ii * KP + cu] = __float2bfloat16(__ldg(Wc + (long long)(rank * U + ii) * H + cu));
+    for (int base = tid; base < U * H; base += GF_NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; v[u] = idx < U * H ? __ldg(Wc + (long long)(rank * U + idx / H) * H + idx % H) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; if (idx < U * H) WcT_s[(idx / H) * KP + idx % H] = __float2bfloat16(v[u]); }
     }
-    for (int idx = tid; idx < U * 2 * H; idx += GF_NT) {
-        const int ii = idx / (2 * H), gcol = idx % (2 * H);
-        WgT_s[ii * KP2 + gcol] = __float2bfloat16(__ldg(Wg + (long long)(rank * U + ii) * 2 * H + gcol));
+    for (int base = tid; base < U * 2 * H; base += GF_NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; v[u] = idx < U * 2 * H ? __ldg(Wg + (long long)(rank * U + idx / (2 * H)) * 2 * H + idx % (2 * H)) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; if (idx < U * 2 * H) WgT_s[(idx / (2 * H)) * KP2 + idx % (2 * H)] = __float2bfloat16(v[u]); }
     }
     if (tid == 0) {
         gf_mbar_init(bar_c, 1); gf_mbar_init(bar_g, 1);
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     }
     const int unit = rank * U + i;
     const long long st_base = ((long long)d * a.N + n) * a.T;
-    float dh_carry = 0.f;
+    float dh_carry = (act && a.dh_in && n < a.N) ? a.dh_in[(long long)n * a.ndir * H + d * H + unit] : 0.f;
     __syncthreads();
     cluster.sync();
 
@@ -362,16 +379,17 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
             dout = a.dout[((long long)n * a.T + t) * a.dout_ld + d * H + unit];
         }
     };
-    load_step(Lmax - 1);
+    const int s_begin = a.t_begin, s_end = a.t_end > 0 ? min(a.t_end, Lmax) : Lmax;      // chunked: steps [t_begin, t_end)
+    load_step(s_end - 1);
     int it = 0;
-    for (int s = Lmax - 1; s >= 0; s--, it++) {
+    for (int s = s_end - 1; s >= s_begin; s--, it++) {
         const uint32_t par = it & 1;
         const bool valid = act && (s < L);
         const int t = (d == 0) ? s : (L - 1 - s);
         const float r_ = rg, u_ = ug, c_ = cc, hp_ = hp;
         float dh = dh_carry + (valid ? dout : 0.f);
         if (tid == 0) { gf_mbar_expect_tx(bar_c, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_g, 2 * GF_C * Cfg::BLK_BYTES); }
-        load_step(s - 1);
+        if (s - 1 >= s_begin) load_step(s - 1);
         float du_pre = 0.f, dc_pre = 0.f;
         if (valid) {
             du_pre = dh * (hp_ - c_) * u_ * (1.f - u_);
@@ -465,10 +483,14 @@ static int launch_gru_fast_t(const GruArgs& a, bool bwd, cudaStream_t s) {
 
 int launch_gru_fast_fwd(const GruArgs& a, cudaStream_t s) {
     TACO_REQUIRE(a.H == 128 || a.H == 256, TACO_ESHAPE, "gru: hidden size %d not instantiated (128, 256)", a.H);
+    TACO_REQUIRE((a.t_begin == 0 && a.t_end == 0) || (a.ndir == 1 && !a.lengths && a.t_begin >= 0 && a.t_begin < a.t_end && a.t_end <= a.T),
+                 TACO_EINVAL, "gru: time chunks need ndir == 1, no lengths and 0 <= t_begin < t_end <= T");
     return a.H == 128 ? launch_gru_fast_t<128>(a, false, s) : launch_gru_fast_t<256>(a, false, s);
 }
 int launch_gru_fast_bwd(const GruArgs& a, cudaStream_t s) {
     TACO_REQUIRE(a.H == 128 || a.H == 256, TACO_ESHAPE, "gru: hidden size %d not instantiated (128, 256)", a.H);
+    TACO_REQUIRE((a.t_begin == 0 && a.t_end == 0) || (a.ndir == 1 && !a.lengths && a.t_begin >= 0 && a.t_begin < a.t_end && a.t_end <= a.T),
+                 TACO_EINVAL, "gru: time chunks need ndir == 1, no lengths and 0 <= t_begin < t_end <= T");
     return a.H == 128 ? launch_gru_fast_t<128>(a, true, s) : launch_gru_fast_t<256>(a, true, s);
 }
 

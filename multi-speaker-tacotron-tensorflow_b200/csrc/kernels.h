@@ -60,6 +60,11 @@ struct GruArgs {
     float* dgx;                           // grad wrt gx, same indexing as gx (pre-zeroed)
     float* dh0;                           // [N, ndir*H] or NULL
     float* hfinal;                        // forward: final state [N, ndir*H] or NULL
+    // time-chunked execution (decoder wavefront, model_decoder.cu; fast kernels only, ndir == 1, no lengths): the launch
+    // covers steps [t_begin, t_end) of the T-step sequence (t_end == 0: all of it); all buffers keep their full-T indexing.
+    // Forward chunks chain through h0 / hfinal, backward chunks (run last to first) through dh_in (carry in) / dh0 (out).
+    int t_begin, t_end;
+    const float* dh_in;                   // backward: gradient wrt the state after step t_end-1, [N, ndir*H] or NULL (zero)
 };
 int launch_gru_fwd(const GruArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruArgs& a, cudaStream_t s);
@@ -95,12 +100,23 @@ struct AttArgs {
     const float* dy0;       // [N*Td, Y]
     const float *W1cT, *W2T, *WgT, *WcT, *WqT, *WoT;   // transposed weights
     float *d_G, *d_zp, *d_z1p, *d_ctx, *d_gq, *d_ge, *d_ha0, *d_score_bias;
+    // time-chunked execution (fast kernels, training): steps [t_begin, t_end) (t_end == 0: all).  A forward chunk with
+    // t_begin > 0 restores its state (ha, context, previous alignments) from the stash rows of step t_begin-1; backward
+    // chunks run last to first and hand the carried gradients (wrt ha, context, alignments) over in c_dha [N,HA], c_dctx
+    // [N,E], c_dac [N, 16*ceil(Ti/16)]: every launch writes them at its end, a launch with c_in != 0 reads them first.
+    int t_begin, t_end, c_in;
+    float *c_dha, *c_dctx, *c_dac;
+    // pre-built operand images of the fast kernels (att_fast.cu: launch_att_fast_pack), or NULL: weight slices per cluster
+    // rank and key / memory slices per CTA, in the kernels' shared-memory layout, pulled in with bulk async copies
+    const uint8_t *img_w, *img_km;
 };
 int launch_att_fwd(const AttArgs& a, cudaStream_t s);
 int launch_att_bwd(const AttArgs& a, cudaStream_t s);
 bool att_fast_supported(const AttArgs& a);
 int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s);   // TACO_ENOTSUP when 16-CTA clusters cannot be launched
 int launch_att_fast_bwd(const AttArgs& a, cudaStream_t s);
+void att_fast_image_bytes(int Ti, bool bwd, size_t* w_bytes, size_t* km_bytes_per_cta);
+int launch_att_fast_pack(const AttArgs& a, bool bwd, int what, uint8_t* img_w, uint8_t* img_km, cudaStream_t s);
 int launch_att_keys_bwd(const float* keys, const float* q, const float* ge, const float* v_eff, float* dkeys, float* gv,
                         int N, int Ti, int Td, int A, int fast, cudaStream_t s);
 // forward (gveff == NULL): v_eff = g v/||v||;  backward: gv += d v_eff/d v . gveff, gg += d v_eff/d g . gveff

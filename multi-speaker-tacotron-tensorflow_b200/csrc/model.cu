@@ -63,7 +63,7 @@ struct StreamSet {
 };
 static StreamSet g_set[2];                 // 0: chain (high priority), 1: leaves (low priority)
 static cudaStream_t g_crit = nullptr, g_side = nullptr;
-static cudaEvent_t g_ev_in, g_ev_out, g_ev_fork, g_ev_side, g_ev_prep;
+static cudaEvent_t g_ev_in, g_ev_out, g_ev_fork, g_ev_side, g_ev_prep, g_ev_leaf, g_ev_img[2];
 static bool g_sched_ready = false;
 static int g_overlap = -1;
 static bool g_prof_keep_overlap = false;     // TACO_PROF_OVERLAP=1: timeline of the real two-stream schedule (tools/timeline.py)
@@ -80,7 +80,8 @@ static int sched_init() {
     }
     TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_crit, cudaStreamNonBlocking, hi));
     TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, lo));
-    for (cudaEvent_t* e : {&g_ev_in, &g_ev_out, &g_ev_fork, &g_ev_side, &g_ev_prep}) TACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&g_ev_in, &g_ev_out, &g_ev_fork, &g_ev_side, &g_ev_prep, &g_ev_leaf, &g_ev_img[0], &g_ev_img[1]})
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     const char* env = getenv("TACO_OVERLAP");
     g_overlap = (env && env[0] == '0') ? 0 : 1;
     const char* env2 = getenv("TACO_PROF_OVERLAP");
@@ -89,6 +90,46 @@ static int sched_init() {
     return TACO_OK;
 }
 static bool overlap_on() { return g_sched_ready && g_overlap == 1 && (!g_prof_on || g_prof_keep_overlap); }
+
+// Decoder wavefront: two more high-priority streams (one per residual GRU layer) and per-chunk events, so that the GRU
+// layers of time chunk c run while the attention recurrence is already on chunk c+1 (and the reverse in BPTT).
+static WaveCtx g_wave;
+static bool g_wave_ready = false;
+static int g_wave_chunks = -1;
+int wave_get(WaveCtx** out) {
+    *out = nullptr;
+    if (!overlap_on()) return TACO_OK;
+    if (g_wave_chunks < 0) {
+        const char* env = getenv("TACO_DEC_CHUNKS");
+        g_wave_chunks = env ? atoi(env) : 4;
+        if (g_wave_chunks > WaveCtx::kMaxChunks) g_wave_chunks = WaveCtx::kMaxChunks;
+    }
+    if (g_wave_chunks <= 1) return TACO_OK;
+    if (!g_wave_ready) {
+        int lo = 0, hi = 0;
+        TACO_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < 2; i++) TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_wave.w[i], cudaStreamNonBlocking, hi));
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < WaveCtx::kMaxChunks; c++) TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_wave.ev[k][c], cudaEventDisableTiming));
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_wave.start, cudaEventDisableTiming));
+        g_wave_ready = true;
+    }
+    g_wave.chunks = g_wave_chunks;
+    *out = &g_wave;
+    return TACO_OK;
+}
+// Leaf stream for work whose operands were produced on `producer` (any stream): the side stream waits for what is
+// enqueued there so far.  Falls back to `producer` itself when the two-stream schedule is off.
+cudaStream_t fork_side_after(cudaStream_t producer) {
+    if (!overlap_on()) return producer;
+    if (cudaEventRecord(g_ev_leaf, producer) != cudaSuccess || cudaStreamWaitEvent(g_side, g_ev_leaf, 0) != cudaSuccess) return producer;
+    return g_side;
+}
+// Hand-over of the attention operand images between streams: which = 0 weight images (built beside the encoder), 1 the
+// backward key / memory image (built beside the forward decoder).  image_ready records, image_wait orders `s` behind it.
+int image_ready(int which, cudaStream_t producer) { TACO_CHECK_CUDA(cudaEventRecord(g_ev_img[which], producer)); return TACO_OK; }
+int image_wait(int which, cudaStream_t s) { TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_ev_img[which], 0)); return TACO_OK; }
+
 
 // Stream for leaf work whose operands were produced by what is already enqueued on `main`.
 cudaStream_t fork_side(cudaStream_t main) {
@@ -275,6 +316,16 @@ void Model::plan(const Shape& s) {
                 const std::string rp = "dec/g" + std::to_string(l) + "_";
                 for (const char* nm : {"st_r", "st_u", "st_c", "st_hprev"}) add(rp + nm, {rows, Y});
                 add(rp + "dgx", {rows, 3 * Y}); add(rp + "dh0", {N, Y}); add(rp + "wxcat", {Y, 3 * Y});
+                // decoder wavefront (model_decoder.cu): gathered chunk operands and the state / gradient carried between chunks
+                add(rp + "wv_x", {rows, Y}); add(rp + "wv_g", {rows, 3 * Y}); add(rp + "wv_h", {N, Y});
+            }
+            add("dec/c_dha", {N, HA}); add("dec/c_dctx", {N, E}); add("dec/c_dac", {N, (int64_t)((s.Ti + 15) / 16 * 16)});
+            // operand images of the fast attention kernels (att_fast.cu: launch_att_fast_pack), sized in floats
+            for (int bwd = 0; bwd < 2; bwd++) {
+                size_t wb = 0, kmb = 0;
+                att_fast_image_bytes(s.Ti, bwd != 0, &wb, &kmb);
+                add(bwd ? "dec/img_bw" : "dec/img_fw", {(int64_t)(wb / 4)});
+                add(bwd ? "dec/img_bkm" : "dec/img_fkm", {(int64_t)(kmb / 4) * 16 * ((N + 7) / 8)});
             }
             add("dec/d_dec", {rows, M * r}); add("dec/d_y2", {rows, Y}); add("dec/d_y1", {rows, Y}); add("dec/d_y0", {rows, Y});
             const int64_t ZS = Z + SPK, KIN = ZS + HA, KO = HA + E + SPK;
@@ -736,10 +787,13 @@ int taco_forward(taco_model h, const taco_batch* b, void* stream) {
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     TACO_TRY(sched_init());
     m.prep_done = false;
+    m.img_w_state = 0; m.img_bkm_state = 0;
     if (s.training && overlap_on()) {
         // parameter-only operands of the backward pass are packed on the leaf stream while the forward pass runs
         TACO_CHECK_CUDA(cudaEventRecord(g_ev_in, user));
         TACO_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_in, 0));
+        m.img_w_state = 0;
+        TACO_TRY(decoder_pack_weight_images(m, g_side));          // sets img_w_state = 2 (ready behind g_ev_img[0]) when it applies
         TACO_TRY(backward_prep(m, g_side));
         TACO_CHECK_CUDA(cudaEventRecord(g_ev_prep, g_side));
         m.prep_done = true;
@@ -879,7 +933,7 @@ int taco_profile(int32_t enable, double ms_out[4], int64_t count_out[4]) {
 
 // debug: per-span listing of the last profile window, one line per span:
 //   "cls ms tag0 tag1 tag2 tag3 start_ms stream name"   (GEMM spans: M N K n_problems; start relative to the first span;
-//   stream 1 = the low-priority leaf stream; class 9 = stage markers)
+//   stream 1 = the low-priority leaf stream, 2 / 3 = the wavefront streams of GRU layer 1 / 2; class 9 = stage markers)
 int taco_debug_profile_spans(char* buf, int64_t cap) {
     std::string out;
     for (auto& sp : g_prof_spans) {
@@ -888,7 +942,8 @@ int taco_debug_profile_spans(char* buf, int64_t cap) {
         if (cudaEventElapsedTime(&t0, g_prof_spans.front().a, sp.a) != cudaSuccess) t0 = -1.f;
         char line[192];
         snprintf(line, sizeof line, "%d %.4f %d %d %d %d %.4f %d %s\n", sp.cls, ms, sp.tag[0], sp.tag[1], sp.tag[2], sp.tag[3], t0,
-                 sp.stream == g_side ? 1 : 0, sp.name[0] ? sp.name : "-");
+                 sp.stream == g_side ? 1 : (g_wave_ready && sp.stream == g_wave.w[0]) ? 2 : (g_wave_ready && sp.stream == g_wave.w[1]) ? 3 : 0,
+                 sp.name[0] ? sp.name : "-");
         out += line;
     }
     if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", out.c_str()); }
@@ -898,6 +953,14 @@ int taco_debug_profile_spans(char* buf, int64_t cap) {
 int taco_gemm(const taco_gemm_desc* d, int32_t n_problems, int32_t precision, void* stream) {
     TACO_REQUIRE(d && n_problems > 0, TACO_EINVAL, "taco_gemm: null argument");
     return launch_gemm(d, n_problems, precision, static_cast<cudaStream_t>(stream));
+}
+
+// Debug hook (not part of the ABI header, like the other taco_debug_* entries): number of time chunks of the decoder
+// wavefront; <= 1 turns it off.  The default comes from TACO_DEC_CHUNKS (4).  Returns the previous value.
+int taco_debug_set_dec_chunks(int32_t n) {
+    const int prev = taco::g_wave_chunks;
+    taco::g_wave_chunks = n > taco::WaveCtx::kMaxChunks ? taco::WaveCtx::kMaxChunks : n;
+    return prev;
 }
 
 }  // extern "C"

@@ -45,6 +45,9 @@ struct Model {
     CbhgGeom enc, post;
     // backward operands that depend only on the parameters (model.cu: backward_prep)
     bool prep_done = false;          // produced beside the current forward pass on the leaf stream
+    // attention operand images of the current step: 0 not built, 1 built on the consumer's own stream, 2 built on another
+    // stream (consumer must image_wait first)
+    int img_w_state = 0, img_bkm_state = 0;
     bool tables_ready = false;       // bank tap tables uploaded for the current plan / workspace
     std::vector<int> taps_enc, taps_post;
 
@@ -65,6 +68,20 @@ struct Model {
 // the low-priority side stream when taco_backward runs its two-stream schedule, otherwise `main` itself.
 cudaStream_t fork_side(cudaStream_t main);
 
+// Streams / events of the decoder wavefront (model.cu).  wave_get yields nullptr when the schedule is off (TACO_OVERLAP=0,
+// TACO_DEC_CHUNKS<=1, or a taco_profile window, whose per-launch timings must not overlap).
+struct WaveCtx {
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t w[2];                       // one per residual GRU layer
+    cudaEvent_t ev[3][kMaxChunks];           // [stage][chunk]: 0 attention, 1 GRU layer 1, 2 GRU layer 2
+    cudaEvent_t start;
+    int chunks;
+};
+int wave_get(WaveCtx** out);
+cudaStream_t fork_side_after(cudaStream_t producer);
+int image_ready(int which, cudaStream_t producer);
+int image_wait(int which, cudaStream_t s);
+
 void prof_mark(const char* name, cudaStream_t s);   // timeline stage marker (no-op unless taco_profile is collecting)
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s);
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s);
@@ -78,6 +95,7 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
 
 // model_decoder.cu
 int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s);
+int decoder_pack_weight_images(Model& m, cudaStream_t s);     // forward + backward weight images of the fast attention kernels
 int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s);
 
 }  // namespace taco

@@ -49,6 +49,30 @@ static void fill_att_weights(const Model& m, const DecDims& D, AttArgs& a) {
     a.Wo = m.P("concat_proj/kernel"); a.bo = m.P("concat_proj/bias");
 }
 
+// The fast attention kernels pull their operands (bf16 weight slices per cluster rank, key / memory slices per CTA) as
+// ready-made shared-memory images (att_fast.cu).  Weight images depend on the parameters only: both directions are built
+// once per step, beside the encoder when the side stream is available.  Images exist in training plans only.
+static bool images_applicable(const Model& m, const AttArgs& a) {
+    return m.shape.training && a.fast && !a.free_run && att_fast_supported(a) && m.has_region("dec/img_fw");
+}
+static AttArgs att_dims(const Model& m, const DecDims& D) {
+    AttArgs a{};
+    a.N = D.N; a.Ti = D.Ti; a.Td = D.Td; a.E = D.E; a.A = D.A; a.HA = D.HA; a.Z1 = D.Z1; a.Z = D.Z; a.SPK = D.SPK; a.Y = D.Y;
+    a.att_type = m.cfg.attention_type; a.fast = (m.cfg.precision != TACO_PREC_FP32);
+    return a;
+}
+int decoder_pack_weight_images(Model& m, cudaStream_t s) {
+    const DecDims D = dec_dims(m);
+    AttArgs a = att_dims(m, D);
+    if (!images_applicable(m, a)) return TACO_OK;
+    fill_att_weights(m, D, a);
+    TACO_TRY(launch_att_fast_pack(a, false, 0, reinterpret_cast<uint8_t*>(m.W("dec/img_fw")), nullptr, s));
+    TACO_TRY(launch_att_fast_pack(a, true, 0, reinterpret_cast<uint8_t*>(m.W("dec/img_bw")), nullptr, s));
+    TACO_TRY(image_ready(0, s));
+    m.img_w_state = 2;
+    return TACO_OK;
+}
+
 static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, float* y, int training, const float* h0, cudaStream_t s) {
     const std::string gn = "dec_gru_" + std::to_string(layer);
     const std::string rp = "dec/g" + std::to_string(layer) + "_";
@@ -65,6 +89,68 @@ static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, 
     a.h0 = h0; a.res = x; a.res_ld = Y; a.out = y; a.out_ld = Y;
     if (training) { a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev"); }
     return prof_launch_gru(a, false, s);
+}
+
+// ---- decoder wavefront ---------------------------------------------------------------------------------------------
+// Teacher forcing makes the attention recurrence independent of the two residual GRU layers, and each of the three
+// recurrences occupies only a fraction of the SMs (64 / 32 / 32) for a latency-bound time.  Run back to back they cost
+// t_att + t_gru1 + t_gru2; cut into time chunks they pipeline: while the attention kernel works on chunk c+1, GRU layer 1
+// runs chunk c and layer 2 chunk c-1, each on its own high-priority stream (the reverse order in BPTT).  A chunk launch
+// covers steps [t0, t1) and chains to the next through the kernels' carry arguments (kernels.h).  The hoisted x-side
+// GEMM of a chunk reads its rows (n, t0..t1) gathered into a contiguous operand and writes straight into the full
+// [N, Td, 3Y] layout through the GEMM's row remap, so every other consumer keeps its indexing.
+struct Chunk { int t0, t1; };
+static std::vector<Chunk> wave_chunks(int Td, int want) {
+    std::vector<Chunk> out;
+    const int n = std::max(1, std::min(want, Td / 8));            // keep chunks >= 8 steps
+    const int len = cdiv(Td, n);
+    for (int t0 = 0; t0 < Td; t0 += len) out.push_back({t0, std::min(Td, t0 + len)});
+    return out;
+}
+static bool wave_applicable(const Model& m, const AttArgs& a, const taco_batch* b) {
+    return m.shape.training && !b->rnn_decoder_test_mode && b->mel_targets && a.fast && !a.free_run && att_fast_supported(a) &&
+           m.cfg.dec_rnn_size == 256 && m.shape.Td >= 16;
+}
+
+// one chunk of a residual GRU layer, forward: gather x rows -> x-side GEMM (remapped into gx) -> recurrence over [t0, t1)
+static int dec_gru_chunk_fwd(Model& m, const DecDims& D, int layer, const float* x, float* y, const float* h0, Chunk c, cudaStream_t s) {
+    const std::string gn = "dec_gru_" + std::to_string(layer);
+    const std::string rp = "dec/g" + std::to_string(layer) + "_";
+    const int Y = D.Y, Tc = c.t1 - c.t0, rows = D.N * Tc;
+    float* gx = m.W(rp + "gx"); float* xc = m.W(rp + "wv_x"); float* carry = m.W(rp + "wv_h");
+    TACO_TRY(launch_copy2d(xc, x + (long long)c.t0 * Y, D.N, Tc * Y, (long long)Tc * Y, (long long)D.Td * Y, s));
+    taco_gemm_desc d[2];
+    d[0] = gd(xc, m.P(gn + "/gates_kernel"), gx + (long long)c.t0 * 3 * Y, rows, 2 * Y, Y, Y, 2 * Y, 3 * Y); d[0].bias = m.P(gn + "/gates_bias");
+    d[1] = gd(xc, m.P(gn + "/cand_kernel"), gx + (long long)c.t0 * 3 * Y + 2 * Y, rows, Y, Y, Y, Y, 3 * Y); d[1].bias = m.P(gn + "/cand_bias");
+    for (taco_gemm_desc& g : d) { g.remap_period = Tc; g.remap_outer = (long long)D.Td * 3 * Y; g.remap_inner = 3 * Y; }
+    TACO_TRY(launch_gemm(d, 2, m.cfg.precision, s));
+    GruArgs a{};
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1; a.fast = 1;
+    a.gx = gx; a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
+    a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
+    a.h0 = (c.t0 == 0) ? h0 : carry; a.hfinal = carry;
+    a.res = x; a.res_ld = Y; a.out = y; a.out_ld = Y;
+    a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
+    a.t_begin = c.t0; a.t_end = c.t1;
+    return prof_launch_gru(a, false, s);
+}
+
+static int decoder_forward_wave(Model& m, const DecDims& D, AttArgs a, const float* h1, const float* h2, WaveCtx& wv, cudaStream_t s) {
+    const std::vector<Chunk> ch = wave_chunks(D.Td, wv.chunks);
+    const int C = (int)ch.size();
+    for (int c = 0; c < C; c++) {
+        a.t_begin = ch[c].t0; a.t_end = ch[c].t1;
+        TACO_TRY(prof_launch_att(a, false, s));
+        TACO_CHECK_CUDA(cudaEventRecord(wv.ev[0][c], s));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(wv.w[0], wv.ev[0][c], 0));
+        TACO_TRY(dec_gru_chunk_fwd(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), h1, ch[c], wv.w[0]));
+        TACO_CHECK_CUDA(cudaEventRecord(wv.ev[1][c], wv.w[0]));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(wv.w[1], wv.ev[1][c], 0));
+        TACO_TRY(dec_gru_chunk_fwd(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), h2, ch[c], wv.w[1]));
+    }
+    TACO_CHECK_CUDA(cudaEventRecord(wv.ev[2][0], wv.w[1]));        // layer 2 is ordered behind layer 1, which is behind attention
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(s, wv.ev[2][0], 0));
+    return TACO_OK;
 }
 
 int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
@@ -114,11 +200,28 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         a.s_haprev = m.W("dec/s_haprev"); a.s_ha = m.W("dec/s_ha"); a.s_q = m.W("dec/s_q"); a.s_ctxin = m.W("dec/s_ctxin");
         a.s_ctx = m.W("dec/s_ctx"); a.s_e = m.W("dec/s_e"); a.s_a = m.W("dec/s_a");
     }
-    TACO_TRY(prof_launch_att(a, false, s));
-    prof_mark("dec_f:gru", s);
-    // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
-    TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
-    TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
+    if (images_applicable(m, a)) {
+        if (m.img_w_state == 0) { TACO_TRY(decoder_pack_weight_images(m, s)); m.img_w_state = 1; }
+        else if (m.img_w_state == 2) TACO_TRY(image_wait(0, s));
+        uint8_t* fkm = reinterpret_cast<uint8_t*>(m.W("dec/img_fkm"));
+        TACO_TRY(launch_att_fast_pack(a, false, 1, nullptr, fkm, s));
+        a.img_w = reinterpret_cast<const uint8_t*>(m.W("dec/img_fw")); a.img_km = fkm;
+        // the backward pass's key / memory image: same inputs, needed much later -> leaf stream
+        cudaStream_t side = fork_side_after(s);
+        TACO_TRY(launch_att_fast_pack(a, true, 1, nullptr, reinterpret_cast<uint8_t*>(m.W("dec/img_bkm")), side));
+        if (side != s) { TACO_TRY(image_ready(1, side)); m.img_bkm_state = 2; } else m.img_bkm_state = 1;
+    }
+    WaveCtx* wv = nullptr;
+    if (wave_applicable(m, a, b)) TACO_TRY(wave_get(&wv));
+    if (wv) {
+        TACO_TRY(decoder_forward_wave(m, D, a, h1, h2, *wv, s));
+    } else {
+        TACO_TRY(prof_launch_att(a, false, s));
+        prof_mark("dec_f:gru", s);
+        // two ResidualWrapper(GRUCell) layers   tacotron.py:171-175
+        TACO_TRY(dec_gru_layer(m, D, 1, m.W("dec/y0"), m.W("dec/y1"), training, h1, s));
+        TACO_TRY(dec_gru_layer(m, D, 2, m.W("dec/y1"), m.W("dec/y2"), training, h2, s));
+    }
     // r-frame mel projection, written straight into the post-net's padded input (= mel_outputs)   tacotron.py:178-179,213-214
     {
         const CbhgGeom& g = m.post;
@@ -162,6 +265,48 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     return TACO_OK;
 }
 
+// one chunk of a residual GRU layer, backward: BPTT over [t0, t1) (downwards), then dx rows = dy rows + dgx rows . Wx^T
+static int dec_gru_chunk_bwd(Model& m, const DecDims& D, int layer, const float* dy, float* dx, bool last_chunk, bool want_dh0, Chunk c, cudaStream_t s) {
+    const std::string gn = "dec_gru_" + std::to_string(layer);
+    const std::string rp = "dec/g" + std::to_string(layer) + "_";
+    const int Y = D.Y, Tc = c.t1 - c.t0, rows = D.N * Tc, prec = m.cfg.precision;
+    float* dgx = m.W(rp + "dgx"); float* carry = m.W(rp + "wv_h");
+    GruArgs a{};
+    a.N = D.N; a.T = D.Td; a.H = Y; a.ndir = 1; a.fast = 1;
+    a.gx = m.W(rp + "gx"); a.gx_ld = 3 * Y; a.gx_rs_n = D.Td; a.gx_row0 = 0;
+    a.Wg[0] = m.P(gn + "/gates_kernel") + (long long)Y * 2 * Y; a.Wc[0] = m.P(gn + "/cand_kernel") + (long long)Y * Y;
+    a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
+    a.dout = dy; a.dout_ld = Y; a.dgx = dgx;
+    a.t_begin = c.t0; a.t_end = c.t1;
+    a.dh_in = last_chunk ? nullptr : carry;                              // the chunk at the end of the sequence starts from zero
+    a.dh0 = (c.t0 == 0) ? (want_dh0 ? m.W(rp + "dh0") : nullptr) : carry;
+    TACO_TRY(prof_launch_gru(a, true, s));
+    float* gc = m.W(rp + "wv_g"); float* dc = m.W(rp + "wv_x");
+    TACO_TRY(launch_copy2d(gc, dgx + (long long)c.t0 * 3 * Y, D.N, Tc * 3 * Y, (long long)Tc * 3 * Y, (long long)D.Td * 3 * Y, s));
+    TACO_TRY(launch_copy2d(dc, dy + (long long)c.t0 * Y, D.N, Tc * Y, (long long)Tc * Y, (long long)D.Td * Y, s));
+    taco_gemm_desc e = gd(gc, m.W(rp + "wxcat"), dc, rows, Y, 3 * Y, 3 * Y, 3 * Y, Y); e.transB = 1; e.accumulate = 1;
+    TACO_TRY(launch_gemm(&e, 1, prec, s));
+    TACO_TRY(launch_copy2d(dx + (long long)c.t0 * Y, dc, D.N, Tc * Y, (long long)D.Td * Y, (long long)Tc * Y, s));
+    return TACO_OK;
+}
+// weight / bias gradients of one residual GRU layer over the whole sequence (leaves; operands complete on `producer`)
+static int dec_gru_wgrads(Model& m, const DecDims& D, int layer, const float* x, cudaStream_t producer) {
+    const std::string gn = "dec_gru_" + std::to_string(layer);
+    const std::string rp = "dec/g" + std::to_string(layer) + "_";
+    const int Y = D.Y, rows = D.N * D.Td, prec = m.cfg.precision;
+    float* dgx = m.W(rp + "dgx");
+    taco_gemm_desc w[4];
+    w[0] = wgrad(x, Y, dgx, 3 * Y, m.G(gn + "/gates_kernel"), Y, 2 * Y, rows);
+    w[1] = wgrad(x, Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel"), Y, Y, rows);
+    w[2] = wgrad(m.W(rp + "st_hprev"), Y, dgx, 3 * Y, m.G(gn + "/gates_kernel") + (long long)Y * 2 * Y, Y, 2 * Y, rows);
+    w[3] = wgrad(m.W(rp + "st_r"), Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel") + (long long)Y * Y, Y, Y, rows);
+    cudaStream_t leaf = fork_side_after(producer);
+    TACO_TRY(launch_gemm(w, 4, prec, leaf));
+    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, leaf));
+    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, leaf));
+    return TACO_OK;
+}
+
 // Input: "post_cbhg/d_xin_p" (grad wrt mel outputs in the padded layout, mel-loss term already added).
 // Output: "enc_cbhg/d_rnn_out" (grad wrt encoder memory) and all decoder parameter gradients.
 int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
@@ -181,11 +326,20 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         taco_gemm_desc e = gd(d_dec, m.P("mel_proj/kernel"), m.W("dec/d_y2"), rows, Y, MR, MR, MR, Y); e.transB = 1;
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
-    prof_mark("dec_b:gru2", s);
-    TACO_TRY(dec_gru_layer_bwd(m, D, 2, m.W("dec/y1"), m.W("dec/d_y2"), m.W("dec/d_y1"), deepvoice, s));
-    prof_mark("dec_b:gru1", s);
-    TACO_TRY(dec_gru_layer_bwd(m, D, 1, m.W("dec/y0"), m.W("dec/d_y1"), m.W("dec/d_y0"), deepvoice, s));
-    prof_mark("dec_b:attention", s);
+    WaveCtx* wv = nullptr;
+    {
+        AttArgs probe{};
+        probe.E = D.E; probe.A = D.A; probe.HA = D.HA; probe.Z1 = D.Z1; probe.Z = D.Z; probe.SPK = D.SPK; probe.Y = D.Y; probe.Ti = D.Ti;
+        probe.att_type = m.cfg.attention_type; probe.fast = (prec != TACO_PREC_FP32);
+        if (wave_applicable(m, probe, b)) TACO_TRY(wave_get(&wv));
+    }
+    if (!wv) {
+        prof_mark("dec_b:gru2", s);
+        TACO_TRY(dec_gru_layer_bwd(m, D, 2, m.W("dec/y1"), m.W("dec/d_y2"), m.W("dec/d_y1"), deepvoice, s));
+        prof_mark("dec_b:gru1", s);
+        TACO_TRY(dec_gru_layer_bwd(m, D, 1, m.W("dec/y0"), m.W("dec/d_y1"), m.W("dec/d_y0"), deepvoice, s));
+        prof_mark("dec_b:attention", s);
+    }
 
     // (the transposed weight copies the attention BPTT reads are produced by backward_prep, model.cu)
     const int ZS = D.Z + D.SPK;
@@ -204,7 +358,38 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     a.d_gq = m.W("dec/d_gq"); a.d_ge = m.W("dec/d_ge");
     a.d_ha0 = deepvoice ? m.W("dec/d_ha0") : nullptr;
     a.d_score_bias = m.has("attention/score_bias") ? m.G("attention/score_bias") : nullptr;
-    TACO_TRY(prof_launch_att(a, true, s));
+    if (images_applicable(m, a) && m.img_w_state != 0 && m.img_bkm_state != 0) {
+        if (m.img_bkm_state == 2) TACO_TRY(image_wait(1, s));
+        a.img_w = reinterpret_cast<const uint8_t*>(m.W("dec/img_bw")); a.img_km = reinterpret_cast<const uint8_t*>(m.W("dec/img_bkm"));
+    }
+    if (!wv) {
+        TACO_TRY(prof_launch_att(a, true, s));
+    } else {
+        // wavefront BPTT, last chunk first: GRU layer 2 -> GRU layer 1 -> attention, one stream each (see decoder_forward_wave)
+        const std::vector<Chunk> ch = wave_chunks(D.Td, wv->chunks);
+        const int C = (int)ch.size();
+        for (int l = 1; l <= 2; l++)
+            TACO_CHECK_CUDA(cudaMemsetAsync(m.W("dec/g" + std::to_string(l) + "_dgx"), 0, sizeof(float) * (size_t)rows * 3 * Y, s));
+        TACO_CHECK_CUDA(cudaEventRecord(wv->start, s));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(wv->w[1], wv->start, 0));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(wv->w[0], wv->start, 0));
+        a.c_dha = m.W("dec/c_dha"); a.c_dctx = m.W("dec/c_dctx"); a.c_dac = m.W("dec/c_dac");
+        for (int c = C - 1; c >= 0; c--) {
+            const bool last = (c == C - 1);
+            TACO_TRY(dec_gru_chunk_bwd(m, D, 2, m.W("dec/d_y2"), m.W("dec/d_y1"), last, deepvoice, ch[c], wv->w[1]));
+            TACO_CHECK_CUDA(cudaEventRecord(wv->ev[2][c], wv->w[1]));
+            TACO_CHECK_CUDA(cudaStreamWaitEvent(wv->w[0], wv->ev[2][c], 0));
+            TACO_TRY(dec_gru_chunk_bwd(m, D, 1, m.W("dec/d_y1"), m.W("dec/d_y0"), last, deepvoice, ch[c], wv->w[0]));
+            TACO_CHECK_CUDA(cudaEventRecord(wv->ev[1][c], wv->w[0]));
+            TACO_CHECK_CUDA(cudaStreamWaitEvent(s, wv->ev[1][c], 0));
+            a.t_begin = ch[c].t0; a.t_end = ch[c].t1; a.c_in = last ? 0 : 1;
+            TACO_TRY(prof_launch_att(a, true, s));
+        }
+        a.t_begin = 0; a.t_end = 0; a.c_in = 0;
+        // parameter gradients of the two GRU layers: leaves, ready as soon as their layer's last chunk is done
+        TACO_TRY(dec_gru_wgrads(m, D, 2, m.W("dec/y1"), wv->w[1]));
+        TACO_TRY(dec_gru_wgrads(m, D, 1, m.W("dec/y0"), wv->w[0]));
+    }
 
     // hoisted parameter gradients of the attention part
     {

@@ -806,3 +806,46 @@ def test_generate_data_on_gpu_writes_the_reference_schema(tb, tmp_path):
     path, frames, ntok = df._frame_info(str(root / "data" / "u1.npz"))
     assert frames == n_frames[1] and ntok == 4
     assert gd.build_from_path(cfg, hp=tb.hparams, log=lines.append) == n_frames      # second run: everything is found on disk
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_decoder_wavefront_equals_unchunked_schedule(tb, chunks):
+    """The time-chunked decoder schedule (attention / GRU layer 1 / GRU layer 2 pipelined over chunks on three streams,
+    model_decoder.cu) must compute what the one-launch-per-recurrence schedule computes: forward bit-identical (a chunk
+    restores exactly the fp32 state the loop carries), gradients equal up to the order of atomic split-K accumulation.
+    deepvoice (initial states + their gradients), 9 rows (a partly filled row group), 37 decoder steps (uneven chunks)."""
+    hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice")
+    S, N, Ti, Td = 3, 9, 21, 37
+    named = tb.params.init_params(hp, S, seed=51, randomize_bn_state=True)
+    b = _batch(N, Ti, Td * 5, [21, 9, 15, 21, 3, 12, 20, 7, 18], seed=27)
+    spk = torch.tensor([0, 2, 1, 1, 0, 2, 2, 0, 1], dtype=torch.int32)
+    lib = tb.capi.load()
+    lib.taco_debug_set_dec_chunks.argtypes = [C.c_int32]
+    res = {}
+    prev = lib.taco_debug_set_dec_chunks(1)
+    try:
+        for n in (1, chunks):
+            lib.taco_debug_set_dec_chunks(n)
+            eng = tb.Engine(hp, S, precision="tf32", named_params=named)
+            out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
+            o = {k: v.clone() for k, v in out.items()}
+            eng.backward()
+            res[n] = (o, eng.scalars()["loss"], eng.grads.clone(), {k: v.clone() for k, v in eng.named_gradients().items()})
+            eng.close()
+    finally:
+        lib.taco_debug_set_dec_chunks(prev)
+    (o1, l1, g1, ng1), (o2, l2, g2, ng2) = res[1], res[chunks]
+    # (a chunk's x-side GEMM covers N*Tc rows instead of N*Td: a different tile / split-K plan, and below the tensor-core
+    # kernel's size threshold the exact fp32 kernel takes it - so the two schedules differ by TF32 rounding, not more)
+    for k in o1:
+        err = (o1[k] - o2[k]).abs().max().item()
+        assert err <= 5e-3, (k, err)
+    assert abs(l1 - l2) <= 1e-4
+    cos = float((g1.double() @ g2.double()) / (g1.double().norm() * g2.double().norm()))
+    assert cos >= 0.9999, cos
+    # and against the oracle, like every other tf32 case
+    ref, ref_g, names = _oracle_grads(named, hp, b, S, spk, "deepvoice")
+    for k in ("mel_outputs", "linear_outputs", "alignments"):
+        assert (o2[k].cpu() - ref[k].detach()).abs().max().item() <= TOL["tf32"]["out"], k
+    c2, na, nb = _cosine(ng2, ref_g, sorted(ref_g))
+    assert c2 >= TOL["tf32"]["cos"] and abs(na - nb) <= TOL["tf32"]["gn"] * nb

@@ -42,7 +42,7 @@ rows.sort(key=lambda r: r["t0"])
 print("step %.3f ms (events around train_step, profiling events included); host issue time %.3f ms; class totals ms %s" % (e0.elapsed_time(e1), _host_ms, list(ms)))
 names = {0: "gemm", 1: "gru", 2: "att", 9: "mark"}
 for r in rows:
-    lane = "side" if r["side"] else "main"
+    lane = {0: "main", 1: "side", 2: "gru1", 3: "gru2"}[r["side"]]
     if r["cls"] == 9:
         print("%9.3f            %s  ---- %s" % (r["t0"], lane, r["name"]))
     elif r["cls"] == 0:
