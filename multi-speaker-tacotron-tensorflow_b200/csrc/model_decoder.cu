@@ -100,11 +100,24 @@ static int dec_gru_layer(Model& m, const DecDims& D, int layer, const float* x, 
 // GEMM of a chunk reads its rows (n, t0..t1) gathered into a contiguous operand and writes straight into the full
 // [N, Td, 3Y] layout through the GEMM's row remap, so every other consumer keeps its indexing.
 struct Chunk { int t0, t1; };
+// Chunk boundaries.  The pipeline is bound by the attention stage (a GRU chunk takes about a third of an attention chunk),
+// so what is left to trim is its fill / drain: the chunk at the END of the sequence is the one whose GRU layers trail the
+// last attention chunk in the forward pass and lead the first one in BPTT.  It is made short (and the one before it twice
+// as long); the rest of the sequence is split evenly.
 static std::vector<Chunk> wave_chunks(int Td, int want) {
     std::vector<Chunk> out;
     const int n = std::max(1, std::min(want, Td / 8));            // keep chunks >= 8 steps
-    const int len = cdiv(Td, n);
-    for (int t0 = 0; t0 < Td; t0 += len) out.push_back({t0, std::min(Td, t0 + len)});
+    if (n == 1) { out.push_back({0, Td}); return out; }
+    const int last = std::max(8, (2 * Td) / (5 * n));
+    std::vector<int> len(n, 0);
+    len[n - 1] = last;
+    int rest = Td - last;
+    if (n >= 3) { len[n - 2] = std::min(2 * last, rest - 8 * (n - 2)); if (len[n - 2] < 8) len[n - 2] = 8; rest -= len[n - 2]; }
+    const int even = n >= 3 ? n - 2 : 1;
+    for (int i = 0; i < even; i++) len[i] = rest / even + (i < rest % even ? 1 : 0);
+    int t0 = 0;
+    for (int i = 0; i < n; i++) { if (len[i] <= 0) continue; out.push_back({t0, t0 + len[i]}); t0 += len[i]; }
+    out.back().t1 = Td;
     return out;
 }
 static bool wave_applicable(const Model& m, const AttArgs& a, const taco_batch* b) {
