@@ -458,6 +458,23 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         const int HA = D.HA, E = D.E, A = D.A;
         (void)HA;
         float* d_mem = m.W("enc_cbhg/d_rnn_out");
+        // d_memory[n] = a_seq[n]^T . d_ctx[n] needs only what the attention BPTT left behind, the keys path below needs the
+        // score gradients: with the wavefront streams at hand the two run side by side and the keys GEMM accumulates on top
+        std::vector<taco_gemm_desc> pm;
+        for (int n = 0; n < D.N; n++) {
+            taco_gemm_desc d = gd(a.s_a + (long long)n * D.Td * D.Ti, a.d_ctx + (long long)n * D.Td * E, d_mem + (long long)n * D.Ti * E,
+                                  D.Ti, E, D.Td, D.Ti, E, E);
+            d.transA = 1; d.accumulate = 1;
+            pm.push_back(d);
+        }
+        const bool pm_first = wv != nullptr && !b->manual_alignments;
+        if (pm_first) {
+            for (taco_gemm_desc& d : pm) d.accumulate = 0;
+            TACO_CHECK_CUDA(cudaEventRecord(wv->start, s));
+            TACO_CHECK_CUDA(cudaStreamWaitEvent(wv->w[0], wv->start, 0));
+            TACO_TRY(launch_gemm(pm.data(), (int)pm.size(), prec, wv->w[0]));
+            TACO_CHECK_CUDA(cudaEventRecord(wv->ev[1][0], wv->w[0]));
+        }
         if (!b->manual_alignments) {
             if (m.cfg.attention_type == TACO_ATT_BAH_NORM) {
                 // e = sum_u (g v_u/||v||) tanh(k + q + b): keys see the normalised vector; its gradient chains to v and g
@@ -473,19 +490,13 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
             taco_gemm_desc w = wgrad(a.memory, E, m.W("dec/d_keys"), A, m.G("attention/memory_kernel"), E, A, (long long)D.N * D.Ti);
             TACO_TRY(launch_gemm(&w, 1, prec, fork_side(s)));
             taco_gemm_desc e = gd(m.W("dec/d_keys"), m.P("attention/memory_kernel"), d_mem, D.N * D.Ti, E, A, A, A, E); e.transB = 1;
+            if (pm_first) { TACO_CHECK_CUDA(cudaStreamWaitEvent(s, wv->ev[1][0], 0)); e.accumulate = 1; }
             TACO_TRY(launch_gemm(&e, 1, prec, s));
         } else {
             TACO_CHECK_CUDA(cudaMemsetAsync(d_mem, 0, sizeof(float) * (size_t)D.N * D.Ti * E, s));
         }
         // d_memory[n] += a_seq[n]^T . d_ctx[n]
-        std::vector<taco_gemm_desc> pm;
-        for (int n = 0; n < D.N; n++) {
-            taco_gemm_desc d = gd(a.s_a + (long long)n * D.Td * D.Ti, a.d_ctx + (long long)n * D.Td * E, d_mem + (long long)n * D.Ti * E,
-                                  D.Ti, E, D.Td, D.Ti, E, E);
-            d.transA = 1; d.accumulate = 1;
-            pm.push_back(d);
-        }
-        TACO_TRY(launch_gemm(pm.data(), (int)pm.size(), prec, s));
+        if (!pm_first) TACO_TRY(launch_gemm(pm.data(), (int)pm.size(), prec, s));
     }
     return TACO_OK;
 }
