@@ -188,14 +188,23 @@ def run_ours(args):
 
     def e2e_loop(n):
         # the loop of train.py:217-226 with one step of run-ahead: step i's scalars are copied to pinned host memory behind
-        # step i and read on the host once step i+1 has been enqueued (every step's loss is read inside the timed region)
+        # step i and read on the host once step i+1 has been enqueued (every step's loss is read inside the timed region).
+        # The copy of batch i+1 is issued behind step i's FORWARD pass (an event gates the copy stream): H2D traffic beside
+        # the forward pass slows it by 0.7 ms, beside the backward pass by 0.08 ms (tools/e2e_diag.py).
         free_ev[0] = free_ev[1] = None
         ready = stage(0)
         losses, pending = [], None
         for i in range(n):
             torch.cuda.current_stream().wait_event(ready)
-            nxt = stage(i + 1) if i + 1 < n else None
-            eng.train_step(bufs[i % 2], allreduce=allreduce)
+            box = [None]
+
+            def prefetch(i=i):
+                if i + 1 < n:
+                    gate = torch.cuda.Event(); gate.record(torch.cuda.current_stream())
+                    stream_copy.wait_event(gate)
+                    box[0] = stage(i + 1)
+            eng.train_step(bufs[i % 2], allreduce=allreduce, after_forward=prefetch)
+            nxt = box[0]
             cur = eng.scalars_async()
             free_ev[i % 2] = torch.cuda.Event(); free_ev[i % 2].record(torch.cuda.current_stream())
             if pending is not None:
@@ -229,7 +238,7 @@ def run_ours(args):
                        "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
                        "timing": "CUDA events per step on the compute stream, max over ranks"},
             "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96,
-                    "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream) + every step's loss read back to the host (pinned, one step of run-ahead)"},
+                    "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream, the next batch's copy issued behind the forward pass) + every step's loss read back to the host (pinned, one step of run-ahead)"},
             "gpu_launches": launches,
             "clocks": clocks,
             # dominant kernel class by device time: the tcgen05 GEMM (all GEMM-shaped work of the step)

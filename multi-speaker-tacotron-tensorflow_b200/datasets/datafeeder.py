@@ -329,9 +329,13 @@ class DataFeeder(threading.Thread):
         if prev is not None:
             self._free.put(prev)
 
-    def next_device_batch(self, compute_stream=None) -> Dict[str, "object"]:
+    def next_device_batch(self, compute_stream=None, after=None, defer_wait: bool = False) -> Dict[str, "object"]:
         """Next batch on the device: async copies from the pinned slot on a dedicated copy stream; the compute stream is
-        made to wait on them (so the copy of batch k+1 overlaps step k when called right after launching step k)."""
+        made to wait on them (so the copy of batch k+1 overlaps step k when called right after launching step k).
+        ``after``: a CUDA event the copies are ordered behind (train.py passes "forward pass of step k enqueued": the DMA then
+        runs beside the backward pass, where it costs 0.08 ms instead of 0.7 ms beside a forward pass).  ``defer_wait``: do not
+        make the compute stream wait now — the event comes back as ``batch["_ready"]`` for the caller to wait on when it
+        starts using the batch (otherwise work enqueued after this call would stall behind the copy)."""
         import torch
         if self._device is None:
             raise RuntimeError("DataFeeder was created without a device")
@@ -341,14 +345,19 @@ class DataFeeder(threading.Thread):
         host = self._views(slot, shapes)
         dev = {}
         with torch.cuda.stream(self._copy_stream):
+            if after is not None:
+                self._copy_stream.wait_event(after)
             for k, v in host.items():
                 dev[k] = v.to(self._device, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._copy_stream)
         cs = compute_stream or torch.cuda.current_stream(self._device)
-        cs.wait_event(done)
+        if not defer_wait:
+            cs.wait_event(done)
         for v in dev.values():
             v.record_stream(cs)
+        if defer_wait:
+            dev["_ready"] = done
         slot["event"] = done
         prev, self._inflight = self._inflight, slot
         if prev is not None:

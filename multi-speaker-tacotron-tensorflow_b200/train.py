@@ -136,6 +136,9 @@ def train(log_dir, config, hp=hparams):
         first = True
         while True:
             start_time = time.time()
+            ready = batch.pop("_ready", None)
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)       # the batch staged behind the previous step's forward pass
             model.initialize(batch["inputs"], batch["input_lengths"], num_speakers, batch.get("speaker_id"), batch["mel_targets"],
                              batch["linear_targets"], batch["loss_coeff"], is_randomly_initialized=is_randomly_initialized)
             if first and restore:
@@ -149,8 +152,9 @@ def train(log_dir, config, hp=hparams):
             elif first:
                 log("Starting new training run", slack=True)
             first = False
+            fwd_done = torch.cuda.Event(); fwd_done.record(torch.cuda.current_stream())
+            nxt = train_feeder.next_device_batch(after=fwd_done, defer_wait=True)   # the next batch's DMA runs beside the backward pass
             model.add_loss()
-            nxt = train_feeder.next_device_batch()          # the next batch's DMA overlaps the optimizer and the next forward
             model.add_optimizer(allreduce=allreduce)
             step = model.engine.global_step                 # value AFTER the update, as sess.run([global_step, ...]) returns
             loss = model.loss_without_coeff
