@@ -30,8 +30,8 @@ WORKLOAD = "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel,
 ALGO_BYTES_PER_STEP = 486.6e6
 # algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
 ALGO_FLOPS_PER_STEP = 784.8e9
-# ncu (profiles/r1_step_metrics_v6.summary.txt): 4678.3 MB of DRAM traffic over the 165 gemm_tc_kernel launches of one step
-GEMM_DRAM_BYTES_PER_LAUNCH = 4678.3e6 / 165
+# ncu (profiles/r1_step_metrics_v7.summary.txt): 4697.5 MB of DRAM traffic over the 183 gemm_tc_kernel launches of one step
+GEMM_DRAM_BYTES_PER_LAUNCH = 4697.5e6 / 183
 
 
 def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
@@ -245,7 +245,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed; fp32 SIMT in fp32 mode)",
                          "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                          "unit": "TFLOP/s", "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v6.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
                          "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
                          "launches_per_step": int(prof_n[0] // PROF_STEPS), "problems_per_step": int(prof_n[3] // PROF_STEPS), "ms_per_step": gemm_ms,
                          "algorithmic_flops_per_step": gemm_flops, "algorithmic_flops_per_launch": gemm_flops / max(1, prof_n[3] // PROF_STEPS),
