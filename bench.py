@@ -112,7 +112,13 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner (and NCCL_DEBUG output) on the C-level stdout when the communicator is created; the
+        # contract is ONE JSON line on stdout, so file descriptor 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hp = tb.hparams.override(reduction_factor=CFG["r"], batch_size=CFG["N"])
     eng = Engine(hp, 1, precision=args.precision, device=local, seed=4321)
@@ -264,6 +270,9 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(sample_steps=1)
             if args.synth and world == 1:
                 line["cpu_baseline"]["synth_rtf"] = synth_rtf_cpu()
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
