@@ -37,16 +37,28 @@ template <bool FAST> __device__ __forceinline__ float sigm_(float x) {
 }
 
 // acc[r] += sum_{k in [k0,k1)} Wcol[k*ld] * v_s[k*R + r]      (Wcol already points at this thread's column)
+// The weights stream from L2 on every call (nothing is resident in these exact kernels), so the loop is bound by how many
+// loads a thread keeps in flight: MV_LB weights are fetched back to back before the first is used (with 4 in flight the
+// free-running decoder step took 97 us, almost all of it L2 latency).  The accumulation order is unchanged.
+constexpr int MV_LB = 16;
+__device__ __forceinline__ void mv_fma(float acc[AT_R], float w, const float* __restrict__ v_s, int k) {
+    const float4 a = *reinterpret_cast<const float4*>(v_s + k * AT_R);
+    const float4 b = *reinterpret_cast<const float4*>(v_s + k * AT_R + 4);
+    acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+    acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+}
 __device__ __forceinline__ void mv_acc(float acc[AT_R], const float* __restrict__ Wcol, long long ld, const float* __restrict__ v_s,
                                        int k0, int k1) {
-#pragma unroll 4
-    for (int k = k0; k < k1; k++) {
-        const float w = __ldg(Wcol + (long long)k * ld);
-        const float4 a = *reinterpret_cast<const float4*>(v_s + k * AT_R);
-        const float4 b = *reinterpret_cast<const float4*>(v_s + k * AT_R + 4);
-        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
-        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    int k = k0;
+    for (; k + MV_LB <= k1; k += MV_LB) {
+        float w[MV_LB];
+#pragma unroll
+        for (int u = 0; u < MV_LB; u++) w[u] = __ldg(Wcol + (long long)(k + u) * ld);
+#pragma unroll
+        for (int u = 0; u < MV_LB; u++) mv_fma(acc, w[u], v_s, k + u);
     }
+#pragma unroll 4
+    for (; k < k1; k++) mv_fma(acc, __ldg(Wcol + (long long)k * ld), v_s, k);
 }
 __device__ __forceinline__ void red_store(float* red, int tid, const float acc[AT_R]) {
 #pragma unroll
@@ -291,15 +303,42 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_rm(cl, q_rm, A, stage, rank, Ua, tid);
         cl.sync();
         // ===== P6: scores of the own memory slice: e[r][j] = sum_u v_u tanh(keys[n,j,u] + q[r,u]) =====
-        for (int p = warp; p < R * TJ; p += AT_NT / 32) {
-            const int r = p % R, jj = p / R, j = rank * TJ + jj, n = grp * R + r;
-            float s = 0.f;
-            if (j < Ti && n < a.N) {
-                const float* kp = a.keys + ((long long)n * Ti + j) * A;
-                for (int u = lane; u < A; u += 32) s = fmaf(v_s[u], tanh_<FAST>(__ldg(kp + u) + q_rm[r * A + u]), s);
+        // (row-major pair index: with few valid rows - batch-1 synthesis - the positions of a row still spread over all warps;
+        //  the keys of the next pair are fetched while the current one is reduced)
+        {
+            auto pair_ok = [&](int p) { return p < R * TJ && rank * TJ + (p % TJ) < Ti && grp * R + (p / TJ) < a.N; };
+            auto pair_keys = [&](int p) { return a.keys + ((long long)(grp * R + p / TJ) * Ti + rank * TJ + (p % TJ)) * A; };
+            float kn[8];
+            if (A == 256 && pair_ok(warp)) {
+                const float* kp = pair_keys(warp);
+#pragma unroll
+                for (int q8 = 0; q8 < 8; q8++) kn[q8] = __ldg(kp + lane + 32 * q8);
             }
-            s = warp_sum(s);
-            if (lane == 0) stage[r * TJ + jj] = s + score_bias;
+            for (int p = warp; p < R * TJ; p += AT_NT / 32) {
+                const int r = p / TJ, jj = p % TJ;
+                const bool ok = pair_ok(p);
+                float s = 0.f;
+                if (A == 256) {
+                    float kv[8];
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; q8++) kv[q8] = kn[q8];
+                    const int pn = p + AT_NT / 32;
+                    if (pair_ok(pn)) {
+                        const float* kp = pair_keys(pn);
+#pragma unroll
+                        for (int q8 = 0; q8 < 8; q8++) kn[q8] = __ldg(kp + lane + 32 * q8);
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int q8 = 0; q8 < 8; q8++) { const int u = lane + 32 * q8; s = fmaf(v_s[u], tanh_<FAST>(kv[q8] + q_rm[r * A + u]), s); }
+                    }
+                } else if (ok) {
+                    const float* kp = pair_keys(p);
+                    for (int u = lane; u < A; u += 32) s = fmaf(v_s[u], tanh_<FAST>(__ldg(kp + u) + q_rm[r * A + u]), s);
+                }
+                s = warp_sum(s);
+                if (lane == 0) stage[r * TJ + jj] = s + score_bias;
+            }
         }
         __syncthreads();
         push_rm(cl, e_s, Tip, stage, rank, TJ, tid);
@@ -365,8 +404,15 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
             if (row_ok32) {
                 const float* mp = a.memory + (long long)n32 * Ti * E + unit;
                 const float* ar = a_s + r32 * Tip;
-#pragma unroll 4
-                for (int j = 0; j < Ti; j++) cx = fmaf(ar[j], __ldg(mp + (long long)j * E), cx);
+                int j = 0;
+                for (; j + MV_LB <= Ti; j += MV_LB) {               // memory rows fetched MV_LB at a time (see mv_acc); same summation order
+                    float mv[MV_LB];
+#pragma unroll
+                    for (int u = 0; u < MV_LB; u++) mv[u] = __ldg(mp + (long long)(j + u) * E);
+#pragma unroll
+                    for (int u = 0; u < MV_LB; u++) cx = fmaf(ar[j + u], mv[u], cx);
+                }
+                for (; j < Ti; j++) cx = fmaf(ar[j], __ldg(mp + (long long)j * E), cx);
                 if (a.s_ctx) a.s_ctx[row32 * E + unit] = cx;
             }
             stage[i32 * R + r32] = cx;
