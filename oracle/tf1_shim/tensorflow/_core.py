@@ -1296,12 +1296,19 @@ def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, stair
 
 
 class AdamOptimizer:
-    """python/training/adam.py: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; var -= lr_t*m/(sqrt(v)+eps), eps=1e-8."""
+    """python/training/adam.py: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; var -= lr_t*m/(sqrt(v)+eps), eps=1e-8.
+    As in TF the optimizer's state lives in the graph's variable store, not in the Python object: slots ``<var>/Adam`` and
+    ``<var>/Adam_1`` and the accumulators ``beta1_power`` / ``beta2_power`` (created in the scope apply_gradients runs in).
+    Re-building the model against the same store therefore continues the optimisation, like a second ``sess.run``."""
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, **_kw):
         self._lr, self._b1, self._b2, self._eps = learning_rate, beta1, beta2, epsilon
-        self._slots: Dict[str, Dict[str, torch.Tensor]] = {}
-        self._b1p, self._b2p = beta1, beta2
+
+    @staticmethod
+    def _state_var(full, value):
+        if full not in _S.vars:
+            _S.vars[full] = Variable(value, name=full, trainable=False)
+        return _S.vars[full]
 
     def compute_gradients(self, loss, var_list=None):
         vs_ = var_list or trainable_variables()
@@ -1309,22 +1316,25 @@ class AdamOptimizer:
         return [(None if g is None else Tensor(g), v) for g, v in zip(gs, vs_)]
 
     def get_slot(self, var, name):
-        return self._slots[var.name][name]
+        return _S.vars[var.name + {"m": "/Adam", "v": "/Adam_1"}[name]]
 
     def apply_gradients(self, grads_and_vars, global_step=None, name=None):
         lr = float(_c(self._lr))
-        lr_t = lr * math.sqrt(1 - self._b2p) / (1 - self._b1p)
+        b1p = self._state_var("/".join(_S.scope + ["beta1_power"]), torch.tensor(self._b1, dtype=torch.float64))
+        b2p = self._state_var("/".join(_S.scope + ["beta2_power"]), torch.tensor(self._b2, dtype=torch.float64))
+        lr_t = lr * math.sqrt(1 - float(b2p.t)) / (1 - float(b1p.t))
         with torch.no_grad():
             for g, v in grads_and_vars:
                 if g is None:
                     continue
                 gt = _c(g)
-                s = self._slots.setdefault(v.name, dict(m=torch.zeros_like(v.t), v=torch.zeros_like(v.t)))
-                s["m"].mul_(self._b1).add_(gt * (1 - self._b1))
-                s["v"].mul_(self._b2).add_(gt * gt * (1 - self._b2))
-                v.t.sub_(lr_t * s["m"] / (s["v"].sqrt() + self._eps))
-        self._b1p *= self._b1
-        self._b2p *= self._b2
+                m = self._state_var(v.name + "/Adam", torch.zeros_like(v.t)).t
+                s = self._state_var(v.name + "/Adam_1", torch.zeros_like(v.t)).t
+                m.mul_(self._b1).add_(gt * (1 - self._b1))
+                s.mul_(self._b2).add_(gt * gt * (1 - self._b2))
+                v.t.sub_(lr_t * m / (s.sqrt() + self._eps))
+            b1p.t.mul_(self._b1)
+            b2p.t.mul_(self._b2)
         if global_step is not None:
             global_step.assign(_c(global_step) + 1)
         return None

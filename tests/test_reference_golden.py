@@ -37,6 +37,12 @@ def _oracle_case(tb, name):
             out = O.forward(named, hp, b["inputs"], b["input_lengths"], S, b.get("speaker_id"), manual_alignments=ma, max_iters=hp.max_iters)
         return dict(outputs=out)
     names = [k for k in named if not k.endswith(("moving_mean", "moving_var"))]
+    m = {k: torch.zeros_like(named[k]) for k in names}
+    v = {k: torch.zeros_like(named[k]) for k in names}
+    step = 0
+    if mode == "train_x2":                       # the fixture describes the SECOND of two consecutive steps
+        first = O.train_step({k: t.clone() for k, t in named.items()}, m, v, hp, b, 0, True, S)
+        named, m, v, step = first["params"], first["m"], first["v"], 1
     leaf = {k: (named[k].clone().requires_grad_(True) if k in names else named[k]) for k in named}
     out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, b.get("speaker_id"), b["mel_targets"], b["linear_targets"],
                     rnn_decoder_test_mode=(mode == "train_test_mode"))
@@ -44,14 +50,12 @@ def _oracle_case(tb, name):
     gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
     grads = {k: (g if g is not None else torch.zeros_like(named[k])) for k, g in zip(names, gl)}
     clipped, gn = O.clip_by_global_norm(grads, 1.0)
-    lr = O.learning_rate(hp, 0, True)
+    lr = O.learning_rate(hp, step, True)
     P = {k: named[k].detach().clone() for k in names}
-    m = {k: torch.zeros_like(P[k]) for k in names}
-    v = {k: torch.zeros_like(P[k]) for k in names}
-    P, m, v = O.adam_step(P, clipped, m, v, 1, lr, hp.adam_beta1, hp.adam_beta2)
+    P, m, v = O.adam_step(P, clipped, m, v, step + 1, lr, hp.adam_beta1, hp.adam_beta2)
     after = dict(P)
     after.update({k: t.detach() for k, t in out["new_bn_state"].items()})
-    return dict(outputs=out, losses={k: float(x) for k, x in ls.items()}, grads=grads, grad_norm=gn, lr=lr, after=after)
+    return dict(outputs=out, losses={k: float(x) for k, x in ls.items()}, grads=grads, grad_norm=gn, lr=lr, after=after, steps=step + 1)
 
 
 @pytest.mark.parametrize("name", sorted(mr.CASES))
@@ -80,7 +84,7 @@ def test_oracle_reproduces_reference_run(tb, name):
             assert d <= 2e-5 * max(np.linalg.norm(ref), 1e-3), (key, d)
         elif key.startswith("after:"):
             assert np.abs(res["after"][key[6:]].numpy() - g[key]).max() <= 2e-6, key
-    assert int(g["global_step_after"]) == 1
+    assert int(g["global_step_after"]) == res["steps"]
 
 
 def test_existing_oracle_fixture_equals_reference_run(tb):

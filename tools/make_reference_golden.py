@@ -34,6 +34,9 @@ CASES = {
     "ref_train_prioritize_lr1": (dict(prioritize_loss=True, decay_learning_rate_mode=1), 1, dict(), "train"),
     "ref_infer_manual_attention": (dict(max_iters=5), 1, dict(), "infer_manual"),
     "ref_train_ragged": (dict(), 1, dict(N=3, Ti=13, To=20, lengths=[13, 9, 5], seed=77), "train"),
+    # two consecutive training steps (the train op run twice): Adam slots / beta powers, BN statistics and the global step
+    # carry over in the variable store; the fixture holds the SECOND step's outputs, loss, gradients and the state after it
+    "ref_train_two_steps": (dict(model_type="deepvoice"), 3, dict(speakers=[1, 2]), "train_x2"),
 }
 
 
@@ -125,17 +128,28 @@ def run_reference(tb, hp_over, num_speakers, batch, named, mode, double=False):
     res = {}
     try:
         global_step = tf.Variable(0, name="global_step", trainable=False)          # train.py:143
-        with tf.variable_scope("model"):                                            # train.py:145 / synthesizer.py:49
-            model = create_model(ref_hp)
-            spk = T(batch["speaker_id"]) if num_speakers > 1 else None
-            if is_train:
-                model.initialize(T(batch["inputs"]), T(batch["input_lengths"]), num_speakers, spk,
-                                 T(batch["mel_targets"]), T(batch["linear_targets"]), T(batch["loss_coeff"]),
-                                 rnn_decoder_test_mode=(mode == "train_test_mode"), is_randomly_initialized=True)
-                model.add_loss()
-                model.add_optimizer(global_step)
-            else:
-                model.initialize(T(batch["inputs"]), T(batch["input_lengths"]), num_speakers, spk)
+
+        def build():
+            with tf.variable_scope("model"):                                        # train.py:145 / synthesizer.py:49
+                model = create_model(ref_hp)
+                spk = T(batch["speaker_id"]) if num_speakers > 1 else None
+                if is_train:
+                    model.initialize(T(batch["inputs"]), T(batch["input_lengths"]), num_speakers, spk,
+                                     T(batch["mel_targets"]), T(batch["linear_targets"]), T(batch["loss_coeff"]),
+                                     rnn_decoder_test_mode=(mode == "train_test_mode"), is_randomly_initialized=True)
+                    model.add_loss()
+                    model.add_optimizer(global_step)
+                else:
+                    model.initialize(T(batch["inputs"]), T(batch["input_lengths"]), num_speakers, spk)
+            return model
+        model = build()
+        if mode == "train_x2":
+            # "sess.run(train_op)" a second time: the eager stand-in evaluates while it builds, so the graph is built again over
+            # the SAME variable store (parameters, Adam slots, beta powers, BN statistics, global step all persist); only the
+            # naming counters and the already-executed update ops of the first trace are dropped
+            st0 = tf.shim_state()
+            st0.opened.clear(); st0.collections.clear()
+            model = build()
         missing = set(name_map) - used
         assert not missing, "parameters the reference never created: %s" % sorted(missing)
         res.update(mel_outputs=model.mel_outputs.numpy(), linear_outputs=model.linear_outputs.numpy(),
