@@ -5,8 +5,9 @@ executed over ``oracle/tf1_shim`` (an eager stand-in for the TF r1.4 API — Ten
 This is what pins ``oracle/tacotron_oracle.py``: every output, loss, gradient, Adam update and batch-norm statistic the
 reference's code produces on seeded inputs must be reproduced by the oracle restatement.
 
-Tolerances (fp32 on both sides, different summation orders): outputs 5e-6 max-abs, scalars 1e-6, per-tensor gradient
-norms 1e-4 relative (absolute 1e-7 for mathematically-zero gradients such as a conv bias in front of batch norm), full
+Tolerances (fp32 on both sides, different summation orders): outputs 5e-6 max-abs, scalars 1e-6 (global gradient norm 2e-5), per-tensor gradient
+norms 1e-4 relative (with a floor of 1e-6 of the global norm: gradients that are mathematically zero or sums of nearly
+cancelling terms, such as a conv bias in front of batch norm, are rounding noise), full
 gradient tensors 2e-5 relative L2, post-step parameters / BN statistics 2e-6 max-abs.
 """
 import os
@@ -27,7 +28,7 @@ HAVE_REF = os.path.isdir(os.path.join(mr.REF, "models"))
 
 
 def _oracle_case(tb, name):
-    over, S, bk, mode = mr.CASES[name]
+    over, S, bk, mode = (mr.CASES.get(name) or mr.C1_CASES[name])
     hp = mr.our_hparams(tb, over)
     named = mr.golden_params(tb, hp, S)
     b = mr.golden_batch(**bk)
@@ -58,12 +59,15 @@ def _oracle_case(tb, name):
     return dict(outputs=out, losses={k: float(x) for k, x in ls.items()}, grads=grads, grad_norm=gn, lr=lr, after=after, steps=step + 1)
 
 
-@pytest.mark.parametrize("name", sorted(mr.CASES))
+@pytest.mark.parametrize("name", sorted(mr.CASES) + sorted(mr.C1_CASES))
 def test_oracle_reproduces_reference_run(tb, name):
+    """(ref_c1_*: BASELINE.json configs[0] at its exact size — batch 2, 50 tokens, 200 mel frames, r=5; linear bins strided.)"""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     res = _oracle_case(tb, name)
     for k in ("mel_outputs", "linear_outputs", "alignments"):
         got = res["outputs"][k].detach().numpy()
+        if k == "linear_outputs" and name in mr.C1_CASES:
+            got = got[:, :, ::mr.C1_LINEAR_STRIDE]
         assert got.shape == g[k].shape, (k, got.shape, g[k].shape)
         assert np.abs(got - g[k]).max() <= 5e-6, (k, np.abs(got - g[k]).max())
     if "scalars" not in g.files:
@@ -72,16 +76,18 @@ def test_oracle_reproduces_reference_run(tb, name):
     want = g["scalars"]
     got = [ls["loss"], ls["mel_loss"], ls["linear_loss"], ls["loss_without_coeff"], res["grad_norm"], res["lr"]]
     for a, b_, what in zip(got, want, ("loss", "mel_loss", "linear_loss", "loss_without_coeff", "grad_norm", "lr")):
-        assert abs(a - b_) <= 1e-6 * max(1.0, abs(b_)), (what, a, b_)
+        rel = 2e-5 if what == "grad_norm" else 1e-6          # the norm sums 9 M fp32 gradient entries computed in a different order
+        assert abs(a - b_) <= rel * max(1.0, abs(b_)), (what, a, b_)
     assert sorted(res["grads"]) == list(g["grad_names"])                  # the reference trains exactly our parameter set
     for k, n in zip(g["grad_names"], g["grad_norms"]):
         mine = float(res["grads"][k].double().norm())
-        assert abs(mine - n) <= max(1e-4 * n, 1e-7), (k, mine, n)
+        rel_n = 5e-4 if name in mr.C1_CASES else 1e-4        # 200-frame reductions in front of batch norm cancel more
+        assert abs(mine - n) <= max(rel_n * n, 1e-6 * float(want[4])), (k, mine, n)     # floor: 1e-6 of the global gradient norm
     for key in g.files:
         if key.startswith("grad:"):
             ref = g[key]
             d = np.linalg.norm(res["grads"][key[5:]].numpy() - ref)
-            assert d <= 2e-5 * max(np.linalg.norm(ref), 1e-3), (key, d)
+            assert d <= (5e-4 if name in mr.C1_CASES else 2e-5) * max(np.linalg.norm(ref), 1e-3), (key, d)
         elif key.startswith("after:"):
             assert np.abs(res["after"][key[6:]].numpy() - g[key]).max() <= 2e-6, key
     assert int(g["global_step_after"]) == res["steps"]
@@ -132,9 +138,11 @@ def test_fixtures_regenerate_from_the_reference(tb, name):
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
-def test_reference_run_in_float64_matches_oracle_in_float64(tb):
-    """Rounding-free structural check: the reference's code over the shim in float64 against the oracle in float64."""
-    over, S, bk, mode = mr.CASES["ref_train_deepvoice"]
+@pytest.mark.parametrize("case", ["ref_train_deepvoice", "ref_c1_train"])
+def test_reference_run_in_float64_matches_oracle_in_float64(tb, case):
+    """Rounding-free structural check: the reference's code over the shim in float64 against the oracle in float64 (also at
+    the BASELINE configs[0] size, where the fp32 fixtures differ from the fp32 oracle by up to 1e-4 in some gradients)."""
+    over, S, bk, mode = (mr.CASES.get(case) or mr.C1_CASES[case])
     hp = mr.our_hparams(tb, over)
     named = mr.golden_params(tb, hp, S)
     b = mr.golden_batch(**bk)
@@ -142,7 +150,7 @@ def test_reference_run_in_float64_matches_oracle_in_float64(tb):
     P = {k: v.double() for k, v in named.items()}
     names = [k for k in P if not k.endswith(("moving_mean", "moving_var"))]
     leaf = {k: (P[k].clone().requires_grad_(True) if k in names else P[k]) for k in P}
-    out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, b["speaker_id"], b["mel_targets"].double(), b["linear_targets"].double())
+    out = O.forward(leaf, hp, b["inputs"], b["input_lengths"], S, b.get("speaker_id"), b["mel_targets"].double(), b["linear_targets"].double())
     ls = O.losses(out, b["mel_targets"].double(), b["linear_targets"].double(), b["loss_coeff"].double(), hp)
     gl = torch.autograd.grad(ls["loss"], [leaf[k] for k in names], allow_unused=True)
     for k in ("mel_outputs", "linear_outputs", "alignments"):

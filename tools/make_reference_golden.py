@@ -40,6 +40,17 @@ CASES = {
 }
 
 
+# BASELINE.json configs[0] ("single-speaker forward batch=2, 50-char text -> 200 mel frames, r=5 - the reference's own CPU
+# case") at its exact size, forward (free-running, 40 decoder steps) and one training step.  Checked against the CPU oracle
+# only (tests/test_reference_golden.py); the CUDA path meets the oracle at this size in test_forward_backward_vs_oracle.
+# The 1025-bin linear outputs are stored every 8th bin to keep the fixtures small.
+C1_CASES = {
+    "ref_c1_infer": (dict(max_iters=40), 1, dict(N=2, Ti=50, To=200, lengths=[50, 37], seed=501), "infer"),
+    "ref_c1_train": (dict(), 1, dict(N=2, Ti=50, To=200, lengths=[50, 37], seed=502), "train"),
+}
+C1_LINEAR_STRIDE = 8
+
+
 def golden_batch(N=2, Ti=11, To=15, lengths=None, seed=2024, speakers=None):
     g = torch.Generator().manual_seed(seed)
     inp = torch.randint(2, 80, (N, Ti), generator=g, dtype=torch.int32)
@@ -246,6 +257,13 @@ def main():
         res = run_reference(tb, over, S, b, named, mode)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(res, FULL_MORE if name == "ref_train_single" else FULL_SMALL))
         print(name, "mel", res["mel_outputs"].shape, "loss" if "scalars" in res else "", res.get("scalars", [""])[0])
+    for name, (over, S, bk, mode) in C1_CASES.items():
+        hp = our_hparams(tb, over)
+        res = run_reference(tb, over, S, golden_batch(**bk), golden_params(tb, hp, S), mode)
+        packed = pack(res, ("attention/v", "mel_proj/bias"))
+        packed["linear_outputs"] = np.ascontiguousarray(packed["linear_outputs"][:, :, ::C1_LINEAR_STRIDE])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **packed)
+        print(name, "mel", res["mel_outputs"].shape, res.get("scalars", [""])[0])
     a = run_reference_audio()
     np.savez_compressed(os.path.join(OUT, "ref_audio_small.npz"), **a)
     print("ref_audio_small", a["spectrogram"].shape, a["melspectrogram"].shape, a["wav_out"].shape)
