@@ -7,6 +7,7 @@ from .hparams import HParams, hparams, hparams_debug_string, load_hparams, save_
 from . import params  # noqa: F401
 from . import tf_names  # noqa: F401
 from . import tf_checkpoint  # noqa: F401
+from . import text  # noqa: F401
 from . import capi  # noqa: F401   (ctypes binding; the shared library is only loaded on first use)
 from .engine import Engine  # noqa: F401
 from .models import Tacotron, create_model, get_most_recent_checkpoint  # noqa: F401

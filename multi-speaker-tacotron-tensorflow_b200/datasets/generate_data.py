@@ -10,9 +10,9 @@ What changes is where the work happens: the reference fans utterances out to a `
 (``taco_audio_spectrogram``: pre-emphasis, reflect-padded STFT, magnitude, mel projection, dB, normalise) and the worker
 pool is gone (``--num_workers`` is accepted and ignored).
 
-Not reproduced: the matplotlib histograms (:109-140), and the Korean text front end — ``text_to_sequence`` needs the
-``jamo`` package, so the tokenizer is a parameter (``text_to_sequence=``); metadata whose values are already token-id lists
-is used as is.  Audio decoding: 16-bit / 32-bit / float PCM ``.wav`` through ``scipy.io.wavfile`` (librosa's audioread
+Not reproduced: the matplotlib histograms (:109-140) and the normalisation half of the Korean text front end — the tokenizer
+is a parameter (``text_to_sequence=``; the command line passes ``text.text_to_sequence``, the jamo decomposition without the
+reference's dictionary / number / English read-outs); metadata whose values are already token-id lists is used as is.  Audio decoding: 16-bit / 32-bit / float PCM ``.wav`` through ``scipy.io.wavfile`` (librosa's audioread
 back ends are not here); a file at another rate is resampled with a polyphase filter, which is NOT sample-identical to
 librosa 0.5.1's resampy kernel — prepare audio at ``hparams.sample_rate`` when exact parity with the reference's features
 matters.
@@ -148,7 +148,8 @@ def main(argv=None):
     parser.add_argument("metadata_path", type=str)
     parser.add_argument("--data_dirname", type=str, default="data")
     parser.add_argument("--num_workers", type=int, default=None)       # accepted for command-line compatibility; unused
-    build_from_path(parser.parse_args(argv))
+    from ..text import text_to_sequence           # jamo decomposition without the reference's text normalisation (see text.py)
+    build_from_path(parser.parse_args(argv), text_to_sequence=text_to_sequence)
 
 
 if __name__ == "__main__":

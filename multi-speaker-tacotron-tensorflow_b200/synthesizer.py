@@ -223,7 +223,8 @@ def main(argv=None):
     parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     config = parser.parse_args(argv)
     os.makedirs(config.sample_path, exist_ok=True)
-    synthesizer = Synthesizer(precision=config.precision)
+    from .text import text_to_sequence            # jamo decomposition without the reference's text normalisation (see text.py)
+    synthesizer = Synthesizer(precision=config.precision, text_to_sequence=text_to_sequence)
     synthesizer.load(config.load_path, config.num_speakers, config.checkpoint_step)
     kw = dict(tokens=[[int(t) for t in config.tokens.split()]]) if config.tokens else dict(texts=[config.text])
     return synthesizer.synthesize(base_path=config.sample_path, speaker_ids=[config.speaker_id], attention_trim=False, **kw)[0]

@@ -1,1 +1,1 @@
-from . import _absent as _jamo_char_to_hcj  # noqa: F401
+from . import _jamo_char_to_hcj  # noqa: F401

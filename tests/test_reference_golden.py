@@ -185,3 +185,30 @@ def test_audio_fixture_regenerates_from_the_reference():
     b = mr.run_reference_audio()
     for k in ("spectrogram", "melspectrogram", "wav_out", "phase"):
         assert np.array_equal(a[k], b[k]), k
+
+
+# ---- text: the reference's text front end over the `jamo` stand-in (ref_text_small.json) -----------------------------
+def test_tokenizer_matches_reference_text_front_end(tb):
+    import json
+    with open(os.path.join(GOLD, "ref_text_small.json"), encoding="utf-8") as f:
+        ref = json.load(f)
+    T = tb.text
+    assert T.symbols == ref["symbols"] and len(T.symbols) == tb.params.NUM_SYMBOLS == 80
+    assert T.symbols[tb.params.PAD_ID] == "_" and T.symbols[tb.params.EOS_ID] == "~"
+    for case in ref["cases"]:
+        seq = T.text_to_sequence(case["text"])
+        assert seq.dtype == np.int32 and list(seq) == case["sequence"], case["text"]
+        assert seq[-1] == tb.params.EOS_ID and (seq[:-1] > 1).all()
+        assert T.sequence_to_text(seq, skip_eos_and_pad=True, combine_jamo=True) == case["round_trip"]
+    batch, L = T.texts_to_batch([c["text"] for c in ref["cases"][:3]])
+    assert batch.shape == (3, max(len(c["sequence"]) for c in ref["cases"][:3])) and list(L) == [len(c["sequence"]) for c in ref["cases"][:3]]
+    assert (batch[0, L[0]:] == tb.params.PAD_ID).all()
+    # symbols outside the table (digits, Latin letters: the reference would read them out, see text.py) are dropped
+    assert list(T.text_to_sequence("A1 가")) == [T._symbol_to_id[" "], T._symbol_to_id["ᄀ"], T._symbol_to_id["ᅡ"], 1]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_text_fixture_regenerates_from_the_reference():
+    import json
+    with open(os.path.join(GOLD, "ref_text_small.json"), encoding="utf-8") as f:
+        assert json.load(f) == mr.run_reference_text()

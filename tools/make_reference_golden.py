@@ -246,6 +246,29 @@ def run_reference_audio(gl_iters=4, seed=7):
                 wav_out=wav.astype(np.float32), n_iters=gl_iters, mel_basis=ref_audio._build_mel_basis().astype(np.float32))
 
 
+TEXT_SAMPLES = ["안녕하세요, 반갑습니다.", "오늘 날씨가 참 좋네요!", "값이 얼마예요? 읽다, 앉아; 닭: 삶 (괜찮아) - 끝.", "  앞뒤 공백  ",
+                "그리고 그는 천천히 걸어갔다.", "뭐라고요? 아니, 괜찮아요... 정말로!"]
+
+
+def run_reference_text():
+    """The reference's text front end (text/__init__.py text_to_sequence / sequence_to_text), unmodified, over the `jamo`
+    stand-in, on sentences that need no normalisation (plain Hangul + the punctuation of the symbol table)."""
+    shim = os.path.join(ROOT, "oracle", "tf1_shim")
+    for p in (REF, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    import tensorflow  # noqa: F401  (hparams.py, imported by text/__init__.py, needs the name)
+    from text import text_to_sequence, sequence_to_text
+    from text.symbols import symbols
+    out = {"symbols": symbols, "cases": []}
+    for s in TEXT_SAMPLES:
+        seq = [int(v) for v in text_to_sequence(s)]
+        out["cases"].append({"text": s, "sequence": seq, "round_trip": sequence_to_text(seq, skip_eos_and_pad=True, combine_jamo=True)})
+    return out
+
+
 def main():
     sys.path.insert(0, ROOT)
     import tacotron_b200 as tb
@@ -264,6 +287,10 @@ def main():
         packed["linear_outputs"] = np.ascontiguousarray(packed["linear_outputs"][:, :, ::C1_LINEAR_STRIDE])
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **packed)
         print(name, "mel", res["mel_outputs"].shape, res.get("scalars", [""])[0])
+    import json
+    with open(os.path.join(OUT, "ref_text_small.json"), "w", encoding="utf-8") as f:
+        json.dump(run_reference_text(), f, ensure_ascii=False, indent=1)
+    print("ref_text_small", len(TEXT_SAMPLES), "sentences")
     a = run_reference_audio()
     np.savez_compressed(os.path.join(OUT, "ref_audio_small.npz"), **a)
     print("ref_audio_small", a["spectrogram"].shape, a["melspectrogram"].shape, a["wav_out"].shape)
