@@ -266,3 +266,56 @@ def test_librosa_trim_end_matches_framewise_definition(tb):
     assert got == want and 24000 < got < 31000
     assert syn.librosa_trim_end(np.zeros(100, np.float32)) == 100                 # shorter than a frame: untouched
     assert syn.librosa_trim_end(rng.randn(20000).astype(np.float32)) >= 20000 - fl   # no silence: (almost) nothing cut
+
+
+def test_generate_endpoint_md5_cache_and_errors(tb, tmp_path):
+    """app.py mirror: /generate?text=&speaker_id= -> wav, cached under <root>/<model>/<md5>.<speaker>.0.wav (app.py:55-99)."""
+    import hashlib
+    import threading
+    import urllib.error
+    import urllib.parse
+    import urllib.request
+    from importlib import import_module
+    app = import_module("multi-speaker-tacotron-tensorflow_b200.app")
+
+    class FakeSynthesizer:
+        calls = []
+
+        def synthesize(self, texts=None, tokens=None, paths=None, speaker_ids=None, attention_trim=False, **_kw):
+            self.calls.append((texts, tokens, speaker_ids, attention_trim))
+            if texts and "fail" in texts[0]:
+                raise RuntimeError("synthesis failed")
+            os.makedirs(os.path.dirname(paths[0]), exist_ok=True)
+            with open(paths[0], "wb") as f:
+                f.write(b"RIFF" + (texts[0] if texts else " ".join(map(str, tokens[0]))).encode("utf-8"))
+            return [True]
+
+    syn = FakeSynthesizer()
+    server = app.make_server(syn, str(tmp_path / "logs" / "son_2017"), port=0, audio_root=str(tmp_path / "audio"), host="127.0.0.1")
+    port = server.server_address[1]
+    th = threading.Thread(target=server.serve_forever, daemon=True)
+    th.start()
+    try:
+        text = "안녕하세요"
+        url = "http://127.0.0.1:%d/generate?text=%s&speaker_id=1" % (port, urllib.parse.quote(text))
+        for _ in range(2):
+            with urllib.request.urlopen(url) as r:
+                assert r.status == 200 and r.headers["Content-Type"] == "audio/wav"
+                md5 = hashlib.md5(text.encode("utf-8")).hexdigest()
+                assert md5 in r.headers["Content-Disposition"] and r.read() == b"RIFF" + text.encode("utf-8")
+        assert len(syn.calls) == 1 and syn.calls[0] == ([text], None, [1], True)             # second request came from the cache
+        assert os.path.exists(str(tmp_path / "audio" / "son_2017" / ("%s.1.0.wav" % md5)))
+        with urllib.request.urlopen("http://127.0.0.1:%d/generate?tokens=5+9+1" % port) as r:   # speaker_id defaults to 0
+            assert r.read() == b"RIFF5 9 1"
+        with urllib.request.urlopen("http://127.0.0.1:%d/generate?speaker_id=0" % port) as r:
+            assert json.loads(r.read()) == {}
+        for bad in ("/generate?text=fail&speaker_id=0", "/generate?text=x&speaker_id=abc"):
+            with pytest.raises(urllib.error.HTTPError) as e:
+                urllib.request.urlopen("http://127.0.0.1:%d%s" % (port, bad))
+            assert e.value.code == 400 and json.loads(e.value.read()) == {"success": False}
+        with pytest.raises(urllib.error.HTTPError) as e:
+            urllib.request.urlopen("http://127.0.0.1:%d/" % port)
+        assert e.value.code == 404
+    finally:
+        server.shutdown()
+        server.server_close()
