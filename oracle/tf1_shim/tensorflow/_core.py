@@ -1352,6 +1352,10 @@ class HParams:
     def values(self):
         return {k: getattr(self, k) for k in self._names}
 
+    def to_json(self, **kw):
+        import json
+        return json.dumps(self.values(), **kw)
+
     def set_hparam(self, name, value):
         if name not in self._names:
             self._names.append(name)

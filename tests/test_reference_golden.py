@@ -212,3 +212,69 @@ def test_text_fixture_regenerates_from_the_reference():
     import json
     with open(os.path.join(GOLD, "ref_text_small.json"), encoding="utf-8") as f:
         assert json.load(f) == mr.run_reference_text()
+
+
+# ---- input pipeline: the reference's _prepare_batch (datasets/datafeeder.py:289-328) ---------------------------------
+def test_prepare_batch_matches_reference_datafeeder(tb):
+    from importlib import import_module
+    df = import_module("multi-speaker-tacotron-tensorflow_b200.datasets.datafeeder")
+    g = np.load(os.path.join(GOLD, "ref_batch_small.npz"))
+    for tag, data_type in (("plain", None), ("train", "train")):
+        feed = df.prepare_batch(mr.batch_examples(), 5, np.random.RandomState(11), data_type)
+        for name in ("inputs", "input_lengths", "loss_coeff", "mel_targets", "linear_targets", "speaker_id"):
+            ref = g["%s:%s" % (tag, name)]
+            assert feed[name].shape == ref.shape and feed[name].dtype == ref.dtype, (tag, name, feed[name].shape, ref.shape)
+            assert np.array_equal(feed[name], ref), (tag, name)
+        assert feed["mel_targets"].shape[1] % 5 == 0 and feed["mel_targets"].shape[1] > max(x[5] for x in mr.batch_examples())
+    assert [df._round_up(x, 5) for x in range(0, 13)] == list(g["round_up"])
+    # written in place into staging buffers (the pinned ring of the DataFeeder): same values, views into the buffers
+    big = {k: np.full(v.size + 7, -1, v.dtype) for k, v in feed.items()}
+    feed2 = df.prepare_batch(mr.batch_examples(), 5, np.random.RandomState(11), "train", out=big)
+    for k in feed:
+        assert np.array_equal(feed2[k], feed[k]) and np.shares_memory(feed2[k], big[k]), k
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_batch_fixture_regenerates_from_the_reference():
+    g = np.load(os.path.join(GOLD, "ref_batch_small.npz"))
+    again = mr.run_reference_batch()
+    assert sorted(g.files) == sorted(again) and all(np.array_equal(g[k], again[k]) for k in g.files)
+
+
+# ---- hyper-parameters: defaults and the params.json contract (hparams.py, utils/__init__.py:100-126) -------------------
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_hparams_defaults_and_params_json_interoperate_with_the_reference(tb, tmp_path):
+    shim = os.path.join(ROOT, "oracle", "tf1_shim")
+    for p in (mr.REF, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    import tensorflow  # noqa: F401  (the stand-in; reference/hparams.py builds a tf.contrib.training.HParams)
+    from hparams import hparams as ref_hp
+    import utils as ref_utils
+    ref_values = ref_hp.values()
+    mine = tb.hparams.values()
+    assert sorted(ref_values) == sorted(mine), set(ref_values) ^ set(mine)           # same keys ...
+    for k, v in ref_values.items():
+        assert mine[k] == v, (k, mine[k], v)                                         # ... same defaults (active override block included)
+    # the reference writes params.json, we read it
+    d1 = str(tmp_path / "ref_run")
+    os.makedirs(d1)
+    ref_hp.set_hparam("batch_size", 24); ref_hp.set_hparam("model_type", "deepvoice")
+    try:
+        ref_utils.save_hparams(d1, ref_hp)
+    finally:
+        ref_hp.set_hparam("batch_size", ref_values["batch_size"]); ref_hp.set_hparam("model_type", ref_values["model_type"])
+    hp = tb.hparams.override()
+    tb.load_hparams(hp, d1)
+    assert hp.batch_size == 24 and hp.model_type == "deepvoice" and hp.enc_prenet_sizes == ref_values["enc_prenet_sizes"]
+    # we write params.json, the reference reads it
+    d2 = str(tmp_path / "our_run")
+    tb.save_hparams(d2, tb.hparams.override(reduction_factor=5, attention_type="bah_norm"))
+    try:
+        ref_utils.load_hparams(ref_hp, d2)
+        assert ref_hp.reduction_factor == 5 and ref_hp.attention_type == "bah_norm"
+    finally:
+        for k, v in ref_values.items():
+            ref_hp.set_hparam(k, v)

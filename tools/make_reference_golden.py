@@ -269,6 +269,39 @@ def run_reference_text():
     return out
 
 
+def batch_examples(seed=5, n=5, n_mel=4, n_lin=6):
+    """Examples as DataFeeder hands them to _prepare_batch: (tokens, loss_coeff, mel[T, n_mel], linear[T, n_lin], speaker, T)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        T, L = int(rng.randint(7, 23)), int(rng.randint(3, 12))
+        tok = rng.randint(2, 80, L).astype(np.int32); tok[-1] = 1
+        out.append((tok, float(rng.choice([1.0, 0.2])), rng.rand(T, n_mel).astype(np.float32), rng.rand(T, n_lin).astype(np.float32),
+                    int(rng.randint(0, 3)), T))
+    return out
+
+
+def run_reference_batch(reduction_factor=5):
+    """The reference's datasets/datafeeder.py `_prepare_batch` (and its padding helpers, :289-328), unmodified, imported over
+    the stand-ins (tensorflow / librosa / jamo / tinytag are only touched at import time on this path)."""
+    shim = os.path.join(ROOT, "oracle", "tf1_shim")
+    for p in (REF, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    if not hasattr(np, "complex"):
+        np.complex = complex
+    import datasets.datafeeder as ref_df
+    out = {}
+    for tag, data_type in (("plain", None), ("train", "train")):
+        res = ref_df._prepare_batch(batch_examples(), reduction_factor, np.random.RandomState(11), data_type)
+        for name, arr in zip(("inputs", "input_lengths", "loss_coeff", "mel_targets", "linear_targets", "speaker_id"), res):
+            out["%s:%s" % (tag, name)] = np.asarray(arr)
+    out["round_up"] = np.array([ref_df._round_up(x, 5) for x in range(0, 13)])
+    return out
+
+
 def main():
     sys.path.insert(0, ROOT)
     import tacotron_b200 as tb
@@ -291,6 +324,8 @@ def main():
     with open(os.path.join(OUT, "ref_text_small.json"), "w", encoding="utf-8") as f:
         json.dump(run_reference_text(), f, ensure_ascii=False, indent=1)
     print("ref_text_small", len(TEXT_SAMPLES), "sentences")
+    np.savez_compressed(os.path.join(OUT, "ref_batch_small.npz"), **run_reference_batch())
+    print("ref_batch_small")
     a = run_reference_audio()
     np.savez_compressed(os.path.join(OUT, "ref_audio_small.npz"), **a)
     print("ref_audio_small", a["spectrogram"].shape, a["melspectrogram"].shape, a["wav_out"].shape)
