@@ -1,11 +1,17 @@
 """CPU ORACLE (test infrastructure only) for the reference's spectrogram inversion.
 
-PARITY UNPINNED: the arithmetic lives in librosa 0.5.1 (requirements.txt:61) and scipy, neither importable here; this
-restates librosa 0.5.1's ``stft``/``istft`` from its published source as called by the reference:
+PARITY PINNING: the arithmetic lives in librosa 0.5.1 (requirements.txt:61, not installable here) and scipy (installed).
+This file restates librosa 0.5.1's ``stft``/``istft``/``filters.mel`` from its published source as called by the reference:
     audio/__init__.py:54-56  inv_spectrogram     audio/__init__.py:76-84   _griffin_lim (60 iterations)
     audio/__init__.py:99-106 _stft/_istft        audio/__init__.py:118-122 _stft_parameters
     audio/__init__.py:149    _db_to_amp          :158-159 inv_preemphasis  :164-165 _denormalize
-Pinned by tests/test_oracle.py: STFT->iSTFT round trip, spectral convergence, the scipy.signal.lfilter recurrence.
+    audio/__init__.py:48-51  spectrogram         :64-67 melspectrogram     :141-143 _build_mel_basis
+It is pinned by (1) tests/golden/ref_audio_small.npz — the reference's OWN audio/__init__.py executed unmodified over a
+librosa stand-in (oracle/tf1_shim/librosa, written independently of this file) and the real scipy.signal
+(tools/make_reference_golden.py; tests/test_reference_golden.py requires this oracle to reproduce its spectrogram,
+melspectrogram and seeded 4-iteration inv_spectrogram), which pins the reference's glue (dB / normalise / power / loop /
+pre-emphasis filters through scipy) but not librosa's own kernels, restated twice and cross-checked; and (2) tests/test_oracle.py:
+STFT->iSTFT round trip, spectral convergence, the scipy.signal.lfilter recurrence.
 
 librosa 0.5.x quirk kept on purpose: ``stft`` stores conj(FFT) and ``istft`` conjugates again (the "match phase from
 DPWE code" comment in its source).  The reference draws its initial phase from an UNSEEDED np.random.rand
