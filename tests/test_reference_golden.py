@@ -278,3 +278,25 @@ def test_hparams_defaults_and_params_json_interoperate_with_the_reference(tb, tm
     finally:
         for k, v in ref_values.items():
             ref_hp.set_hparam(k, v)
+
+
+# ---- synthesis post-processing: the end-trimming rule of synthesizer.py:242-262 ---------------------------------------
+def test_attention_trim_matches_reference_synthesizer(tb):
+    import json
+    from importlib import import_module
+    syn = import_module("multi-speaker-tacotron-tensorflow_b200.synthesizer")
+    with open(os.path.join(GOLD, "ref_trim_small.json")) as f:
+        ref = json.load(f)
+    als = mr.trim_alignments()
+    assert len(ref["cases"]) == 2 * len(als)
+    for c in ref["cases"]:
+        al = als[c["alignment"]]
+        keep = syn.attention_trim_frames(al, c["sequence_len"], ref["r"])
+        assert min(keep, al.shape[1] * ref["r"]) == c["frames"], c        # spec[:keep] as the reference slices wav[:spec_end_idx]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference tree is only mounted in the build container")
+def test_trim_fixture_regenerates_from_the_reference():
+    import json
+    with open(os.path.join(GOLD, "ref_trim_small.json")) as f:
+        assert json.load(f) == mr.run_reference_trim()

@@ -302,6 +302,51 @@ def run_reference_batch(reduction_factor=5):
     return out
 
 
+def trim_alignments(Ti=12, Td=14):
+    """Attention matrices [T_in, T_dec] covering the branches of the end-trimming rule (synthesizer.py:242-262)."""
+    rng = np.random.RandomState(4)
+    def diag(stop, hold):                      # attention walks forward, then sits on position `stop` for `hold` steps
+        a = np.full((Ti, Td), 0.01)
+        pos = [min(stop, t) for t in range(Td)]
+        for t in range(Td):
+            a[pos[t] if t < stop + hold else min(Ti - 1, stop + 1 + (t - stop - hold) // 2), t] = 1.0
+        return a
+    return [diag(8, 2), diag(8, 7), diag(Ti - 1, 3), diag(5, 1), rng.rand(Ti, Td), np.eye(Ti, Td) + 0.001]
+
+
+def run_reference_trim(r=5):
+    """The reference's synthesizer.plot_graph_and_save_audio (attention_trim=True, end_of_sentence=True), unmodified, over
+    the stand-ins; its `save_audio` is replaced by a recorder, so the number of spectrogram frames that survive the trim can
+    be read off the waveform length (hop * (frames - 1))."""
+    shim = os.path.join(ROOT, "oracle", "tf1_shim")
+    for p in (REF, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    if not hasattr(np, "complex"):
+        np.complex = complex
+    import synthesizer as ref_syn
+    from hparams import hparams as ref_hp
+    saved = (ref_hp.reduction_factor, ref_hp.griffin_lim_iters)
+    ref_hp.set_hparam("reduction_factor", r); ref_hp.set_hparam("griffin_lim_iters", 0)
+    got = []
+    ref_syn.save_audio = lambda audio, path, sample_rate=None: got.append(len(audio))
+    out = []
+    try:
+        rng = np.random.RandomState(9)
+        for k, al in enumerate(trim_alignments()):
+            Td = al.shape[1]
+            for seq_len in (al.shape[0], al.shape[0] - 3):
+                spec = rng.rand(Td * r, ref_hp.num_freq).astype(np.float32)
+                ref_syn.plot_graph_and_save_audio((0, (spec, al, None, "text", list(range(seq_len)))), attention_trim=True,
+                                                  end_of_sentence=True)
+                out.append({"alignment": k, "sequence_len": seq_len, "frames": got[-1] // 300 + 1})
+    finally:
+        ref_hp.set_hparam("reduction_factor", saved[0]); ref_hp.set_hparam("griffin_lim_iters", saved[1])
+    return {"r": r, "cases": out}
+
+
 def main():
     sys.path.insert(0, ROOT)
     import tacotron_b200 as tb
@@ -324,6 +369,9 @@ def main():
     with open(os.path.join(OUT, "ref_text_small.json"), "w", encoding="utf-8") as f:
         json.dump(run_reference_text(), f, ensure_ascii=False, indent=1)
     print("ref_text_small", len(TEXT_SAMPLES), "sentences")
+    with open(os.path.join(OUT, "ref_trim_small.json"), "w") as f:
+        json.dump(run_reference_trim(), f, indent=1)
+    print("ref_trim_small")
     np.savez_compressed(os.path.join(OUT, "ref_batch_small.npz"), **run_reference_batch())
     print("ref_batch_small")
     a = run_reference_audio()
