@@ -319,3 +319,35 @@ def test_generate_endpoint_md5_cache_and_errors(tb, tmp_path):
     finally:
         server.shutdown()
         server.server_close()
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle (and the TF / librosa / jamo stand-ins under it) is test infrastructure: no module of the shipped package,
+    the command-line wrappers or the C sources may import, load or link anything under oracle/ (bench.py's cpu_baseline /
+    --impl reference legs and __graft_entry__.smoke() are the two allowed callers outside tests/)."""
+    import ast
+    pkg = os.path.join(ROOT, "multi-speaker-tacotron-tensorflow_b200")
+    files = [os.path.join(d, f) for d, _, fs in os.walk(pkg) for f in fs if f.endswith(".py")]
+    files += [os.path.join(ROOT, f) for f in ("train.py", "synthesizer.py", "app.py", "tacotron_b200.py")]
+    for path in files:
+        tree = ast.parse(open(path, encoding="utf-8").read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            elif isinstance(node, ast.Call) and getattr(node.func, "id", getattr(node.func, "attr", "")) == "import_module" and node.args \
+                    and isinstance(node.args[0], ast.Constant):
+                names = [str(node.args[0].value)]
+            for n in names:
+                assert not (n == "oracle" or n.startswith("oracle.") or n.split(".")[0] in ("tensorflow", "librosa", "jamo")), (path, n)
+    for d, _, fs in os.walk(os.path.join(pkg, "csrc")):
+        for f in fs:
+            assert "oracle" not in open(os.path.join(d, f), encoding="utf-8").read(), f
+    # bench.py: the oracle only inside the CPU legs
+    src = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    tree = ast.parse(src)
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
+        assert uses == (fn.name in ("cpu_baseline", "synth_rtf_cpu")), fn.name
