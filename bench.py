@@ -57,7 +57,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -140,10 +140,12 @@ def run_ours(args):
     flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=eng.dev)   # > 126 MB L2
 
     # ---- device-resident timing ----
+    # (the clock sampler is started before the warm-up so that nvidia-smi is already streaming when the short timed region
+    #  begins; only rows stamped inside the timed region are used)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         eng.train_step(dev, allreduce=allreduce)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.time()
