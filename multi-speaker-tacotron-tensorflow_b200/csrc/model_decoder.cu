@@ -501,4 +501,15 @@ int decoder_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     return TACO_OK;
 }
 
+int debug_wave_chunks(int Td, int want, int* bounds, int cap) {
+    const std::vector<Chunk> ch = wave_chunks(Td, want);
+    int n = 0;
+    for (const Chunk& c : ch) { if (2 * n + 1 < cap) { bounds[2 * n] = c.t0; bounds[2 * n + 1] = c.t1; } n++; }
+    return n;
+}
+
 }  // namespace taco
+
+// Debug hook (not part of the ABI header, like the other taco_debug_* entries): the time-chunk boundaries the decoder
+// wavefront would use for Td decoder steps and a requested chunk count; returns the number of chunks, writes (t0, t1) pairs.
+extern "C" int taco_debug_wave_chunks(int32_t Td, int32_t want, int32_t* bounds, int32_t cap) { return taco::debug_wave_chunks(Td, want, bounds, cap); }

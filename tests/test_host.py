@@ -351,3 +351,22 @@ def test_product_path_never_touches_the_oracle():
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
         assert uses == (fn.name in ("cpu_baseline", "synth_rtf_cpu")), fn.name
+
+
+def test_decoder_wavefront_chunk_boundaries(tb):
+    """The time chunks of the decoder wavefront (model_decoder.cu: wave_chunks) partition [0, Td) in order, keep every chunk
+    >= 8 steps, never exceed the requested count, and end with the short chunk that trims the pipeline's fill / drain."""
+    lib = tb.capi.load()
+    lib.taco_debug_wave_chunks.restype = ctypes.c_int
+    lib.taco_debug_wave_chunks.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
+    buf = (ctypes.c_int32 * 64)()
+    for Td in list(range(1, 70)) + [160, 161, 200, 999, 1000]:
+        for want in (1, 2, 3, 4, 5, 8, 16):
+            n = lib.taco_debug_wave_chunks(Td, want, buf, 64)
+            ch = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+            assert 1 <= n <= max(1, want) and ch[0][0] == 0 and ch[-1][1] == Td, (Td, want, ch)
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(t1 > t0 for t0, t1 in ch), (Td, want, ch)
+            if n > 1:
+                assert min(t1 - t0 for t0, t1 in ch) >= 8 or Td < 16, (Td, want, ch)
+                assert ch[-1][1] - ch[-1][0] <= max(t1 - t0 for t0, t1 in ch[:-1]), (Td, want, ch)      # the last chunk is the short one
+    assert lib.taco_debug_wave_chunks(160, 4, buf, 64) == 4 and [buf[i] for i in range(8)] == [0, 56, 56, 112, 112, 144, 144, 160]
