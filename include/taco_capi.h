@@ -36,7 +36,7 @@ extern "C" {
 #define TACO_ENOMEM   (-4)
 #define TACO_ESTATE   (-5)
 
-#define TACO_ABI_VERSION 3
+#define TACO_ABI_VERSION 4
 
 /* attention_type (reference: models/tacotron.py:132-152; only these three are reachable) */
 #define TACO_ATT_BAH_MON  0
@@ -51,9 +51,13 @@ extern "C" {
 
 /* compute precision of the contraction kernels (state, statistics, scans stay fp32):
  *   FP32: every contraction in fp32 FMA (exact-parity mode)
- *   TF32: GEMM-shaped work on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM), fast tanh/sigmoid in the recurrences */
+ *   TF32: GEMM-shaped work on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM), fast tanh/sigmoid in the recurrences
+ *   BF16: as TF32, but every large contraction reads bf16 operands (kind::f16, fp32 accumulate in TMEM): the producing
+ *         kernels write bf16 mirrors of the activations / gradients that feed a GEMM, parameters get a bf16 mirror per step
+ *         (BASELINE.json configs[1] names bf16 as the training precision) */
 #define TACO_PREC_FP32 0
 #define TACO_PREC_TF32 1
+#define TACO_PREC_BF16 2
 
 /* POD mirror of the hparams the hot path reads (reference: hparams.py:31-69,83-94). */
 typedef struct taco_config {
@@ -231,6 +235,12 @@ typedef struct taco_gemm_desc {
      * of different widths that read column blocks of one activation matrix (the conv-bank data gradient).  tap_rows =
      * number of rows addressable from A (rows beyond it read as zero). */
     const int32_t* tap_table; int32_t tap_rows;
+    /* bf16 path (precision TACO_PREC_BF16; kind::f16 tensor-core kernel): A16 / B16 are bf16 mirrors of A / B with the same
+     * logical layout and pitches (lda / ldb in elements, multiples of 8); when both are given and 16-byte aligned the bf16
+     * kernel runs (tap tables then hold one pair per 64-wide k-tile, K % 64 == 0), otherwise the fp32 operands are used.
+     * C16 (optional) receives a bf16 copy of the stored values, laid out like C with row pitch ldc16 (0: ldc); C may then be
+     * NULL (bf16-only output).  Atomic accumulation (split_k > 1, accumulate == 2) writes fp32 only. */
+    const void* A16; const void* B16; void* C16; int32_t ldc16;
 } taco_gemm_desc;
 int taco_gemm(const taco_gemm_desc* d, int32_t n_problems, int32_t precision, void* stream);
 

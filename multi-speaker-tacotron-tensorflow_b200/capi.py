@@ -12,11 +12,11 @@ from typing import Dict, Optional, Sequence, Tuple
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtaco_b200.so")
 
-TACO_ABI_VERSION = 3
+TACO_ABI_VERSION = 4
 TACO_SCALARS_RAW_BYTES = 128
 ATT_TYPES = {"bah_mon": 0, "bah": 1, "bah_norm": 2}
 SPK_MODES = {"none": 0, "simple": 1, "deepvoice": 2, "deepvoice_table": 3}
-PREC = {"fp32": 0, "tf32": 1}
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 
 class TacoConfig(C.Structure):
@@ -65,6 +65,7 @@ class TacoGemmDesc(C.Structure):
         ("remap_period", C.c_int32), ("remap_outer", C.c_int64), ("remap_inner", C.c_int64),
         ("colsum", C.c_void_p), ("colsumsq", C.c_void_p), ("split_k", C.c_int32),
         ("tap_table", C.c_void_p), ("tap_rows", C.c_int32),
+        ("A16", C.c_void_p), ("B16", C.c_void_p), ("C16", C.c_void_p), ("ldc16", C.c_int32),
     ]
 
 

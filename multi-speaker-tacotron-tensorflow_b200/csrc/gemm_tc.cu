@@ -9,9 +9,9 @@
 //   A^T    stored [K(rows), M]  -> MN-major SW128 tile  (four TMA boxes {32 m, 32 k})     (weight gradients)
 //   B[k*ldb+n] (TF [in,out])    -> MN-major SW128 tile  (four TMA boxes {32 n, 32 k})
 //   B[n*ldb+k]                  -> K-major  SW128 tile  (one TMA box  {32 k, 128 n})     (data gradients)
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue (one TMEM
-// lane quarter each).  4-stage mbarrier ring; one 128x128 output tile (x one K split) per CTA.
-#include "common.cuh"
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue (two per TMEM
+// lane quarter).  3-stage mbarrier ring; one 128x128 output tile (x one K split) per CTA, two CTAs per SM.
+#include "tc_common.cuh"
 #include "kernels.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -39,64 +39,6 @@ struct TcParams {
     int split_k, vecC;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only swizzled layout for MN-major 32-bit
-// operands: 128 B x 4-row atoms, Swizzle<2,5,2>; TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
 // lane l ends with sum over the warp's lanes of v[l]
 __device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
 #pragma unroll
@@ -110,15 +52,6 @@ __device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
         }
     }
     return v[0];
-}
-
-template <int ACT> __device__ __forceinline__ float act_ct(float x) {
-    if (ACT == ACT_RELU) return fmaxf(x, 0.f);
-    // MUFU-based forms: this kernel only runs in TF32 mode, whose stated tolerance covers approximate transcendentals
-    if (ACT == ACT_SIGMOID) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x)); return fmaf(0.5f, t, 0.5f); }
-    if (ACT == ACT_TANH) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
-    if (ACT == ACT_SOFTSIGN) return __fdividef(x, 1.0f + fabsf(x));
-    return x;
 }
 
 // One 32x32 chunk of the output tile: rows {4i+lr}, columns gn..gn+3 per lane, read back from the staging buffer.

@@ -11,6 +11,8 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
 bool gemm_tc_eligible(const taco_gemm_desc& g);
 int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s);   // TACO_ENOTSUP: caller falls back to SIMT
 constexpr int TACO_ENOTSUP = -100;
+bool gemm_bf16_eligible(const taco_gemm_desc& g);              // gemm_bf16.cu: both bf16 mirrors given and TMA-addressable
+int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s);
 
 // elementwise.cu
 int launch_fill(float* p, long long n, float v, cudaStream_t s);

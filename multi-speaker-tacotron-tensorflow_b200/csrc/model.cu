@@ -154,8 +154,13 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
     if (precision == TACO_PREC_FP32) return launch_gemm_simt(d, n_problems, s);
     std::vector<taco_gemm_desc> rest;
     std::vector<int> tc;
+    std::vector<char> is16;
     for (int i = 0; i < n_problems; i++) {
-        if (gemm_tc_eligible(d[i])) tc.push_back(i); else rest.push_back(d[i]);
+        const bool have16 = precision == TACO_PREC_BF16 && d[i].A16 && d[i].B16;
+        if (have16 && gemm_bf16_eligible(d[i])) { tc.push_back(i); is16.push_back(1); continue; }
+        TACO_REQUIRE(d[i].A && d[i].B && d[i].C, TACO_EINVAL, "gemm: problem %d (M=%d N=%d K=%d) has bf16-only operands the bf16 kernel cannot address",
+                     i, d[i].M, d[i].N, d[i].K);
+        if (gemm_tc_eligible(d[i])) { tc.push_back(i); is16.push_back(0); } else rest.push_back(d[i]);
     }
     const bool fan_out = tc.size() >= 2;
     TACO_TRY(sched_init());
@@ -167,7 +172,7 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
     int rc_all = TACO_OK;
     for (size_t k = 0; k < tc.size(); k++) {
         cudaStream_t st = fan_out ? set.aux[k % kAuxStreams] : s;
-        int rc = launch_gemm_tc(d[tc[k]], st);
+        int rc = is16[k] ? launch_gemm_bf16(d[tc[k]], st) : launch_gemm_tc(d[tc[k]], st);
         if (rc == TACO_ENOTSUP) rest.push_back(d[tc[k]]);
         else if (rc != TACO_OK && rc_all == TACO_OK) rc_all = rc;
     }
@@ -178,7 +183,10 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
         }
     }
     if (rc_all != TACO_OK) return rc_all;
-    if (!rest.empty()) return launch_gemm_simt(rest.data(), (int)rest.size(), s);
+    if (!rest.empty()) {
+        for (taco_gemm_desc& r : rest) TACO_REQUIRE(r.C16 == nullptr, TACO_EINVAL, "gemm: a bf16 mirror output needs the bf16 kernel (M=%d N=%d K=%d)", r.M, r.N, r.K);
+        return launch_gemm_simt(rest.data(), (int)rest.size(), s);
+    }
     return TACO_OK;
 }
 
