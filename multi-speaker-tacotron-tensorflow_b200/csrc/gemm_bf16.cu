@@ -27,19 +27,22 @@
 
 namespace taco {
 
-constexpr int BF_BM = 128, BF_BK = 64, BF_BN_MAX = 256, BF_STAGES = 4, BF_THREADS = 192;
+constexpr int BF_BM = 128, BF_BK = 64, BF_BN_MAX = 256, BF_MAX_STAGES = 6, BF_EPI_WARPS = 8, BF_THREADS = 64 + 32 * BF_EPI_WARPS;
 constexpr int BF_A_BYTES = BF_BM * BF_BK * 2;                    // 16 KB
-constexpr int BF_B_BYTES = BF_BN_MAX * BF_BK * 2;                // 32 KB (stage pitch; a narrower tile uses its front part)
 constexpr int BF_STG_FLOATS = 32 * 36;                           // per epilogue warp: 32x32 transpose buffer, pitch 36
-constexpr int BF_SMEM = BF_STAGES * (BF_A_BYTES + BF_B_BYTES) + 4 * BF_STG_FLOATS * 4 + 4 * 2 * BF_BN_MAX * 4 + 256 + 1024;
+constexpr int BF_FIXED_SMEM = BF_EPI_WARPS * BF_STG_FLOATS * 4 + 4 * 2 * BF_BN_MAX * 4 + 256;   // staging + statistics partials + barriers
+constexpr int BF_SMEM = 227 * 1024;                              // all of it: the stage ring takes what the fixed part leaves
+constexpr int BF_RING_BYTES = BF_SMEM - 1024 - BF_FIXED_SMEM;    // 1024: alignment slack
 constexpr int BF_SCHED_SLOTS = 256;
 
 struct BfParams {
     float* C; __nv_bfloat16* C16;
     int M, N, K, ldc, ldc16;
     int BN, tilesN, units, split_k, kt_per, ktiles;
+    int stages, b_stage_bytes;           // ring depth and B stage pitch: ceil(BN/64) x 8 KB
+    int fast_ok;                         // the lean epilogue applies to interior chunks (vector stores, aligned bias, no read-modify-write)
     int a_mn_major, b_mn_major;
-    int a_tap, a_ctap, tap_inner;
+    int a_tap, a_ctap, tap_inner, tap_group;   // tap_inner: number of taps (0: tap-major walk); tap_group: channel blocks per group
     const int2* tap_table;
     float alpha; int accumulate;
     const float* bias; int act;
@@ -57,7 +60,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // One 32x32 chunk of the output tile: rows {4i+lr}, columns gn..gn+3 per lane, read back from the staging buffer.
 template <int ACT, bool ATOMIC>
-__device__ __forceinline__ void bf_epi_chunk(const BfParams& p, const float* stg, const long long rowoff[8], const long long rowoff16[8], uint32_t okmask, uint32_t maskmask,
+__device__ __forceinline__ void bf_epi_chunk(const BfParams& p, uint32_t stg, const long long rowoff[8], const long long rowoff16[8], uint32_t okmask, uint32_t maskmask,
                                              int lr, int lc, int gn, bool add_bias, float cs[4], float cq[4]) {
     const bool full4 = gn + 3 < p.N;
     const bool vec = p.vecC && full4;
@@ -71,7 +74,7 @@ __device__ __forceinline__ void bf_epi_chunk(const BfParams& p, const float* stg
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if (!((okmask >> i) & 1u)) continue;
-        const float4 t4 = *reinterpret_cast<const float4*>(stg + (i * 4 + lr) * 36 + lc);
+        const float4 t4 = lds_v4(stg + (uint32_t)(((i * 4 + lr) * 36 + lc) * 4));
         const bool msk = (maskmask >> i) & 1u;
         float x[4];
         x[0] = act_ct<ACT>(fmaf(alpha, t4.x, bz[0])); x[1] = act_ct<ACT>(fmaf(alpha, t4.y, bz[1]));
@@ -90,8 +93,8 @@ __device__ __forceinline__ void bf_epi_chunk(const BfParams& p, const float* stg
             if (p.C) {
                 float* dst = p.C + rowoff[i] + gn;
                 if (vec) {
-                    if (p.accumulate == 1) { const float4 o = *reinterpret_cast<const float4*>(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
-                    *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                    if (p.accumulate == 1) { const float4 o = ldg_v4(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
+                    stg_v4(dst, x[0], x[1], x[2], x[3]);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; e++)
@@ -103,7 +106,7 @@ __device__ __forceinline__ void bf_epi_chunk(const BfParams& p, const float* stg
             }
             if (p.C16) {
                 __nv_bfloat16* d16 = p.C16 + rowoff16[i] + gn;
-                if (vec16) *reinterpret_cast<uint2*>(d16) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+                if (vec16) stg_v2_b32(d16, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
                 else {
 #pragma unroll
                     for (int e = 0; e < 4; e++) if (gn + e < p.N) d16[e] = __float2bfloat16_rn(x[e]);
@@ -115,17 +118,63 @@ __device__ __forceinline__ void bf_epi_chunk(const BfParams& p, const float* stg
     }
 }
 
+// Lean epilogue of an interior 32x32 chunk (all rows valid, all columns inside N, 128-bit stores): ~25 instructions per row.
+// The epilogue is instruction-bound - each epilogue warp runs alone or in pairs on its scheduler, so every dependent
+// instruction costs its full latency (measured: the general path below took ~3 000 clk per chunk).
+template <int ACT, bool STATS>
+__device__ __forceinline__ void bf_epi_fast(const BfParams& p, uint32_t stg_lane, float* const crow[8], __nv_bfloat16* const crow16[8], uint32_t maskmask,
+                                            int gn, float4 bz, float cs[4], float cq[4]) {
+    const float alpha = p.alpha;
+    const bool hc = p.C != nullptr, hc16 = p.C16 != nullptr;       // kernel-uniform
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float4 t4 = lds_v4(stg_lane + (uint32_t)(i * 4 * 36 * 4));
+        float x0 = act_ct<ACT>(fmaf(alpha, t4.x, bz.x)), x1 = act_ct<ACT>(fmaf(alpha, t4.y, bz.y));
+        float x2 = act_ct<ACT>(fmaf(alpha, t4.z, bz.z)), x3 = act_ct<ACT>(fmaf(alpha, t4.w, bz.w));
+        if ((maskmask >> i) & 1u) { x0 = 0.f; x1 = 0.f; x2 = 0.f; x3 = 0.f; }
+        if (hc) stg_v4(crow[i] + gn, x0, x1, x2, x3);
+        if (hc16) stg_v2_b32(crow16[i] + gn, pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+        if (STATS) {
+            cs[0] += x0; cs[1] += x1; cs[2] += x2; cs[3] += x3;
+            cq[0] = fmaf(x0, x0, cq[0]); cq[1] = fmaf(x1, x1, cq[1]); cq[2] = fmaf(x2, x2, cq[2]); cq[3] = fmaf(x3, x3, cq[3]);
+        }
+    }
+}
+// atomic variant (split-K / accumulate == 2): fp32 vector reductions, masked rows contribute nothing
+__device__ __forceinline__ void bf_epi_fast_atomic(const BfParams& p, uint32_t stg_lane, float* const crow[8], uint32_t maskmask, int gn, float4 bz) {
+    const float alpha = p.alpha;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float4 t4 = lds_v4(stg_lane + (uint32_t)(i * 4 * 36 * 4));
+        if ((maskmask >> i) & 1u) continue;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow[i] + gn), "f"(fmaf(alpha, t4.x, bz.x)), "f"(fmaf(alpha, t4.y, bz.y)),
+                     "f"(fmaf(alpha, t4.z, bz.z)), "f"(fmaf(alpha, t4.w, bz.w)) : "memory");
+    }
+}
+
+// debug timeline (ns, %globaltimer) of CTA 0: 0 start, 1 setup done, then per local tile lt < 15: 2+4lt first operands landed,
+// 3+4lt last MMA issued, 4+4lt accumulator ready (epilogue warp 2), 5+4lt epilogue done.  Read with taco_debug_timeline_bf16().
+__device__ unsigned long long g_bf_stamp[64];
+#define BF_STAMP(i)                                                                                       \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < 64) {                                     \
+            unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                  \
+            g_bf_stamp[i] = _t;                                                                           \
+        }                                                                                                 \
+    } while (0)
+
 __global__ void __launch_bounds__(BF_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const BfParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SW128 tiles need 1024-byte alignment
+    const int STAGES = p.stages;
     uint8_t* sA = smem;                                          // [STAGES][16 KB]
-    uint8_t* sB = smem + BF_STAGES * BF_A_BYTES;                 // [STAGES][32 KB]
-    float* stg_all = reinterpret_cast<float*>(smem + BF_STAGES * (BF_A_BYTES + BF_B_BYTES));
-    float* red = stg_all + 4 * BF_STG_FLOATS;                    // [4 quarters][2 stats][256]
+    uint8_t* sB = smem + STAGES * BF_A_BYTES;                    // [STAGES][b_stage_bytes]
+    float* stg_all = reinterpret_cast<float*>(smem + BF_RING_BYTES);
+    float* red = stg_all + BF_EPI_WARPS * BF_STG_FLOATS;         // [4 quarters][2 stats][256]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 4 * 2 * BF_BN_MAX);
-    uint64_t* empty_bar = full_bar + BF_STAGES;
-    uint64_t* tmem_full = empty_bar + BF_STAGES;                 // [2]
+    uint64_t* empty_bar = full_bar + BF_MAX_STAGES;
+    uint64_t* tmem_full = empty_bar + BF_MAX_STAGES;             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                        // [2]
     uint64_t* sched_full = tmem_empty + 2;                       // [2]
     uint64_t* sched_empty = sched_full + 2;                      // [2]
@@ -134,12 +183,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
+    if (warp == 0) BF_STAMP(0);
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
-        for (int i = 0; i < BF_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], BF_EPI_WARPS); mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 1 + BF_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -150,6 +200,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) BF_STAMP(1);
 
     // work unit u -> (m tile, n tile, k split); n fastest so that concurrently running CTAs share A row slabs in L2
     auto decode = [&](int u, int& m0, int& n0, int& kt0, int& nkt) {
@@ -180,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int m0, n0, kt0, nkt;
             decode(u, m0, n0, kt0, nkt);
             for (int j = 0; j < nkt; j++, it++) {
-                const int stage = it % BF_STAGES, round = it / BF_STAGES;
+                const int stage = it % STAGES, round = it / STAGES;
                 if (lane == 0) {
                     if (round > 0) mbar_wait_bounded(&empty_bar[stage], (round - 1) & 1);
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
@@ -189,12 +240,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int kt = kt0 + j;
                 int k0 = kt * BF_BK;
                 if (p.tap_inner) {
-                    // convolution taps innermost: consecutive k-tiles read the same activation rows shifted by one frame (L2 hits)
-                    const int cb = kt / p.tap_inner, tj = kt - cb * p.tap_inner;
+                    // K walk of a convolution: (group of G channel blocks, tap, block in group).  The first tap of a group
+                    // streams G x 128 contiguous bytes of every activation row from DRAM, the other taps re-read the same rows
+                    // shifted by one frame while they are still in L2 (tap-major order re-reads a row slab only after the
+                    // whole wave streamed all channels: 3x the DRAM traffic on the post-net projections).
+                    const int per = p.tap_inner * p.tap_group;
+                    const int gq = kt / per, rem = kt - gq * per, tj = rem / p.tap_group, cb = gq * p.tap_group + (rem - tj * p.tap_group);
                     k0 = tj * p.a_ctap + cb * BF_BK;
                 }
                 uint8_t* a = sA + stage * BF_A_BYTES;
-                uint8_t* b = sB + stage * BF_B_BYTES;
+                uint8_t* b = sB + stage * p.b_stage_bytes;
                 if (lane < 2) {
                     if (!p.a_mn_major) {
                         if (lane == 0) {
@@ -242,11 +297,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(slot * BF_BN_MAX);
             for (int j = 0; j < nkt; j++, it++) {
-                const int stage = it % BF_STAGES, round = it / BF_STAGES;
+                const int stage = it % STAGES, round = it / STAGES;
                 mbar_wait_bounded(&full_bar[stage], round & 1);
+                if (j == 0) BF_STAMP(2 + 4 * lt);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t a = smem_u32(sA + stage * BF_A_BYTES), b = smem_u32(sB + stage * BF_B_BYTES);
+                    const uint32_t a = smem_u32(sA + stage * BF_A_BYTES), b = smem_u32(sB + stage * p.b_stage_bytes);
 #pragma unroll
                     for (int kk = 0; kk < BF_BK / 16; kk++) {
                         // K-major: 16 bf16 = 32 B along the swizzled 128 B row, 8-row groups 1024 B apart (SBO).
@@ -258,17 +314,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                     umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
                     if (j == nkt - 1) umma_commit(&tmem_full[slot]); // accumulator complete
+                    if (j == nkt - 1) BF_STAMP(3 + 4 * lt);
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         // TMEM -> registers (row per lane) -> 32x32 transpose through shared memory -> coalesced 128-byte row segments.
-        // Warp w may touch TMEM lanes 32*(w%4)..+31.
-        const int q = warp & 3;
-        float* stg = stg_all + (warp - 2) * BF_STG_FLOATS;
+        // Warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter take alternate 32-column chunks.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t stg = smem_u32(stg_all + (warp - 2) * BF_STG_FLOATS);
+        const uint32_t red_s = smem_u32(red);
         const int lr = lane >> 3, lc = (lane & 7) * 4;
+        const uint32_t stg_lane = stg + (uint32_t)((lr * 36 + lc) * 4);
         const bool atomic = (p.split_k > 1) || (p.accumulate == 2);
         for (int lt = 0;; lt++) {
             const int slot = lt & 1, use = lt >> 1;
@@ -281,6 +340,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             decode(u, m0, n0, kt0, nkt);
             // the bf16 mirror keeps the fp32 buffer's element layout (same remap); only its row pitch may differ
             long long rowoff[8], rowoff16[8];
+            float* crow[8]; __nv_bfloat16* crow16[8];
             uint32_t okmask = 0, maskmask = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -294,23 +354,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         : (long long)gm * p.ldc;
                     rowoff16[i] = p.remap_period > 0 ? rowoff[i] : (long long)gm * p.ldc16;
                 }
+                crow[i] = p.C + rowoff[i]; crow16[i] = p.C16 + rowoff16[i];
             }
+            const bool rows_full = (m0 + q * 32 + 31 < p.M) && p.fast_ok;     // warp-uniform
+            const bool with_bias = p.bias != nullptr && (!atomic || kt0 == 0);
             mbar_wait_bounded(&tmem_full[slot], use & 1);
+            if (warp == 2) BF_STAMP(4 + 4 * lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(slot * BF_BN_MAX) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 if (n0 + c0 >= p.N) break;                           // warp-uniform
+                const int gn = n0 + c0 + lc;
+                const bool fast = rows_full && (n0 + c0 + 32 <= p.N);
+                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fast && with_bias) bz = __ldg(reinterpret_cast<const float4*>(p.bias + gn));   // in flight across the TMEM load
                 {
                     float v[32];
                     tmem_ld32(tacc + (uint32_t)c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; j += 4) sts_v4(stg + (uint32_t)((lane * 36 + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
                 __syncwarp();
-                const int gn = n0 + c0 + lc;
                 float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-                if (atomic) bf_epi_chunk<ACT_NONE, true>(p, stg, rowoff, rowoff16, okmask, maskmask, lr, lc, gn, kt0 == 0, cs, cq);
+                if (fast) {
+                    if (atomic) bf_epi_fast_atomic(p, stg_lane, crow, maskmask, gn, bz);
+                    else if (p.colsum) {
+                        if (p.act == ACT_RELU) bf_epi_fast<ACT_RELU, true>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq);
+                        else if (p.act == ACT_NONE) bf_epi_fast<ACT_NONE, true>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq);
+                        else bf_epi_chunk<ACT_NONE, false>(p, stg, rowoff, rowoff16, 0u, maskmask, lr, lc, gn, true, cs, cq);   // rejected on the host
+                    } else switch (p.act) {                          // kernel-uniform
+                        case ACT_RELU:     bf_epi_fast<ACT_RELU, false>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq); break;
+                        case ACT_SIGMOID:  bf_epi_fast<ACT_SIGMOID, false>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq); break;
+                        case ACT_TANH:     bf_epi_fast<ACT_TANH, false>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq); break;
+                        case ACT_SOFTSIGN: bf_epi_fast<ACT_SOFTSIGN, false>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq); break;
+                        default:           bf_epi_fast<ACT_NONE, false>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq); break;
+                    }
+                } else if (atomic) bf_epi_chunk<ACT_NONE, true>(p, stg, rowoff, rowoff16, okmask, maskmask, lr, lc, gn, kt0 == 0, cs, cq);
                 else switch (p.act) {                                // kernel-uniform
                     case ACT_RELU:     bf_epi_chunk<ACT_RELU, false>(p, stg, rowoff, rowoff16, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
                     case ACT_SIGMOID:  bf_epi_chunk<ACT_SIGMOID, false>(p, stg, rowoff, rowoff16, okmask, maskmask, lr, lc, gn, true, cs, cq); break;
@@ -326,9 +405,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
                     }
                     if (lane < 8) {                                  // per-quarter partials, reduced over the CTA below
-                        float* r = red + q * (2 * BF_BN_MAX) + c0 + lc;
-                        *reinterpret_cast<float4*>(r) = make_float4(cs[0], cs[1], cs[2], cs[3]);
-                        *reinterpret_cast<float4*>(r + BF_BN_MAX) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+                        const uint32_t r = red_s + (uint32_t)((q * (2 * BF_BN_MAX) + c0 + lc) * 4);
+                        sts_v4(r, cs[0], cs[1], cs[2], cs[3]);
+                        sts_v4(r + BF_BN_MAX * 4, cq[0], cq[1], cq[2], cq[3]);
                     }
                 }
             }
@@ -336,20 +415,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+            if (warp == 2) BF_STAMP(5 + 4 * lt);
             if (p.colsum) {
                 // one double atomic per column and statistic per CTA (the four lane quarters are summed here first: the
                 // statistics land on a few hundred addresses, so their atomics serialise in L2)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int et = threadIdx.x - 64;
-                for (int idx = et; idx < 2 * BN; idx += 128) {
+                for (int idx = et; idx < 2 * BN; idx += 32 * BF_EPI_WARPS) {
                     const int which = idx >= BN ? 1 : 0, col = idx - which * BN;
                     if (n0 + col < p.N) {
-                        const float* r = red + which * BF_BN_MAX + col;
-                        const float v = (r[0] + r[2 * BF_BN_MAX]) + (r[4 * BF_BN_MAX] + r[6 * BF_BN_MAX]);
+                        const uint32_t r = red_s + (uint32_t)((which * BF_BN_MAX + col) * 4);
+                        const float v = (lds_f32(r) + lds_f32(r + 2 * BF_BN_MAX * 4)) + (lds_f32(r + 4 * BF_BN_MAX * 4) + lds_f32(r + 6 * BF_BN_MAX * 4));
                         atomicAdd((which ? p.colsumsq : p.colsum) + n0 + col, (double)v);
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");       // partials are rewritten by the next tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");       // partials are rewritten by the next tile
             }
         }
     }
@@ -488,10 +568,21 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     p.C = g.C; p.C16 = static_cast<__nv_bfloat16*>(g.C16);
     p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldc16 = g.ldc16 > 0 ? g.ldc16 : g.ldc;
     p.BN = BN; p.tilesN = cdiv(g.N, BN);
+    p.b_stage_bytes = cdiv(BN, 64) * 8192;
+    p.stages = BF_RING_BYTES / (BF_A_BYTES + p.b_stage_bytes);
+    if (p.stages > BF_MAX_STAGES) p.stages = BF_MAX_STAGES;
+    { static const int cap = [] { const char* e = getenv("TACO_BF16_STAGES"); return e ? atoi(e) : 0; }(); if (cap > 0 && p.stages > cap) p.stages = cap; }
     p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1;
     p.a_tap = tap ? 1 : 0; p.a_ctap = tap ? g.ctap : 1;
     p.tap_table = reinterpret_cast<const int2*>(g.tap_table);
     p.tap_inner = (tap && !g.transA && !g.tap_table && g.ctap % BF_BK == 0 && g.K % g.ctap == 0 && g.K / g.ctap > 1) ? g.K / g.ctap : 0;
+    {
+        static const int want = [] { const char* e = getenv("TACO_BF16_TAPG"); return e ? atoi(e) : 4; }();
+        const int blocks = g.ctap > 0 ? g.ctap / BF_BK : 1;
+        p.tap_group = 1;
+        for (int gsz = want; gsz >= 1; gsz--) if (blocks % gsz == 0) { p.tap_group = gsz; break; }
+        if (want <= 0) p.tap_inner = 0;
+    }
     p.alpha = g.alpha; p.accumulate = g.accumulate; p.bias = g.bias; p.act = g.act;
     p.mask_period = g.mask_period; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
     p.remap_period = g.remap_period; p.remap_outer = g.remap_outer; p.remap_inner = g.remap_inner;
@@ -516,6 +607,9 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
     p.vecC = g.C ? (g.remap_period > 0 ? (al(g.C, 16) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al(g.C, 16) && g.ldc % 4 == 0)) : 0;
     p.vecC16 = g.C16 ? (g.remap_period > 0 ? (al(g.C16, 8) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al(g.C16, 8) && p.ldc16 % 4 == 0)) : 0;
+    // lean epilogue: 128-bit stores on every output, 16-byte aligned bias, no read-modify-write, statistics only with relu / none
+    p.fast_ok = (!g.C || p.vecC) && (!g.C16 || p.vecC16) && (!g.bias || al(g.bias, 16)) && g.accumulate != 1 &&
+                (!g.colsum || g.act == ACT_RELU || g.act == ACT_NONE) ? 1 : 0;
     {
         std::lock_guard<std::mutex> lk(g_sched_mu);
         p.sched = g_sched_ring + 2 * (g_sched_next++ % BF_SCHED_SLOTS);
@@ -526,4 +620,11 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     return TACO_OK;
 }
 
+int debug_timeline_bf16(unsigned long long out[64]) {
+    TACO_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_bf_stamp, sizeof(unsigned long long) * 64));
+    return TACO_OK;
+}
+
 }  // namespace taco
+
+extern "C" int taco_debug_timeline_bf16(unsigned long long out[64]) { return taco::debug_timeline_bf16(out); }

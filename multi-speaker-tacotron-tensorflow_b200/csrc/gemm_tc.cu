@@ -56,7 +56,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float v[32], int lane) {
 
 // One 32x32 chunk of the output tile: rows {4i+lr}, columns gn..gn+3 per lane, read back from the staging buffer.
 template <int ACT, bool ATOMIC>
-__device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, float* const crow[8], uint32_t okmask, uint32_t maskmask,
+__device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t stg, float* const crow[8], uint32_t okmask, uint32_t maskmask,
                                           int lr, int lc, int gn, bool add_bias, float cs[4], float cq[4]) {
     const bool full4 = gn + 3 < p.N;
     const bool vec = p.vecC && full4;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, f
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if (!((okmask >> i) & 1u)) continue;
-        const float4 t4 = *reinterpret_cast<const float4*>(stg + (i * 4 + lr) * 36 + lc);
+        const float4 t4 = lds_v4(stg + (uint32_t)(((i * 4 + lr) * 36 + lc) * 4));
         const bool msk = (maskmask >> i) & 1u;
         float x[4];
         x[0] = act_ct<ACT>(fmaf(alpha, t4.x, bz[0])); x[1] = act_ct<ACT>(fmaf(alpha, t4.y, bz[1]));
@@ -86,8 +86,8 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const float* stg, f
             }
         } else {
             if (vec) {
-                if (p.accumulate == 1) { const float4 o = *reinterpret_cast<const float4*>(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
-                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                if (p.accumulate == 1) { const float4 o = ldg_v4(dst); x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w; }
+                stg_v4(dst, x[0], x[1], x[2], x[3]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; e++)
@@ -225,7 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(tmem_full, 0);
         if (warp == 4) TC_STAMP(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* stg = reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 36);   // pipeline smem is idle once the accumulator is complete
+        const uint32_t stg = smem_u32(reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 36));   // pipeline smem is idle once the accumulator is complete
+        const uint32_t red_s = smem_u32(sB);
         const int lr = lane >> 3, lc = (lane & 7) * 4;
         const bool atomic = (p.split_k > 1) || (p.accumulate == 2);
         float* crow[8];
@@ -249,8 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) sts_v4(stg + (uint32_t)((lane * 36 + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
             __syncwarp();
             const int gn = n0 + c0 + lc;
@@ -271,9 +271,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
                 }
                 if (lane < 8) {                                  // per-quarter partials, reduced over the CTA below
-                    float* red = reinterpret_cast<float*>(sB) + q * (2 * TC_BN) + c0 + lc;
-                    *reinterpret_cast<float4*>(red) = make_float4(cs[0], cs[1], cs[2], cs[3]);
-                    *reinterpret_cast<float4*>(red + TC_BN) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+                    const uint32_t r = red_s + (uint32_t)((q * (2 * TC_BN) + c0 + lc) * 4);
+                    sts_v4(r, cs[0], cs[1], cs[2], cs[3]);
+                    sts_v4(r + TC_BN * 4, cq[0], cq[1], cq[2], cq[3]);
                 }
             }
         }
@@ -283,8 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int et = threadIdx.x - 64, col = et & (TC_BN - 1), which = et >> 7;
             if (n0 + col < p.N) {
-                const float* red = reinterpret_cast<const float*>(sB) + which * TC_BN + col;
-                const float v = (red[0] + red[2 * TC_BN]) + (red[4 * TC_BN] + red[6 * TC_BN]);
+                const uint32_t r = red_s + (uint32_t)((which * TC_BN + col) * 4);
+                const float v = (lds_f32(r) + lds_f32(r + 2 * TC_BN * 4)) + (lds_f32(r + 4 * TC_BN * 4) + lds_f32(r + 6 * TC_BN * 4));
                 atomicAdd((which ? p.colsumsq : p.colsum) + n0 + col, (double)v);
             }
         }
