@@ -148,7 +148,8 @@ int taco_workspace_bytes(taco_model m, int32_t N, int32_t T_in, int32_t T_out_or
                          int32_t training, size_t* bytes);
 int taco_bind_workspace(taco_model m, void* ws, size_t bytes);
 /* Named region lookup inside the bound workspace (for tests / zero-copy output views).
- * Valid after a forward with the same shape.  offset in bytes; dims up to 4. */
+ * Valid after a forward with the same shape.  offset in bytes; dims up to 4.  *ndim encodes the element type: n = fp32,
+ * -n = double, 100 + n = bf16 (the "<name>.h" mirrors of the bf16 precision mode). */
 int taco_ws_region(taco_model m, const char* name, size_t* offset_bytes, int64_t* numel,
                    int64_t dims[4], int64_t strides[4], int32_t* ndim);
 

@@ -89,7 +89,7 @@ def main(argv=None):
     parser.add_argument("--checkpoint_step", default=None, type=int)
     parser.add_argument("--num_speakers", default=1, type=int)
     parser.add_argument("--port", default=5000, type=int)
-    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     config = parser.parse_args(argv)
     if not os.path.exists(config.load_path):
         print(" [!] load_path not found: {}".format(config.load_path))

@@ -15,6 +15,21 @@
 namespace taco {
 
 constexpr int EW_THREADS = 256;
+typedef __nv_bfloat16 bf16;
+
+// bf16 mirrors (TACO_PREC_BF16): the producers of every tensor that feeds a large GEMM also write it as bf16 (round to nearest
+// even), so the contraction kernels never read fp32 activations; a NULL mirror pointer turns the extra store off.
+__device__ __forceinline__ void st_bf16x4(bf16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 
 static inline int ew_blocks(long long work, int per_block = EW_THREADS, int cap = 148 * 16) {
     long long b = (work + per_block - 1) / per_block;
@@ -34,7 +49,7 @@ int launch_fill(float* p, long long n, float v, cudaStream_t s) {
 }
 
 // out[m,:] = valid(m) ? table[idx[n, t], :] : 0    (embedding/prenet lookup into the padded layout)
-__global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out,
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, bf16* __restrict__ out16,
                                    int N, int T, int Tp, int PL, int C, int n_rows_table) {
     const int c4 = C / 4;
     long long total = (long long)N * Tp * c4;
@@ -48,10 +63,11 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int* _
             v = __ldg(reinterpret_cast<const float4*>(table + (long long)id * C) + c);
         }
         reinterpret_cast<float4*>(out)[i] = v;
+        if (out16) st_bf16x4(out16 + 4 * i, v);
     }
 }
-int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s) {
-    gather_rows_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(table, idx, out, N, T, Tp, PL, C, n_rows_table);
+int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s, void* out16) {
+    gather_rows_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(table, idx, out, static_cast<bf16*>(out16), N, T, Tp, PL, C, n_rows_table);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -120,7 +136,7 @@ int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* 
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ res, const float* __restrict__ rowvec,
-                                float* __restrict__ out, int N, int T, int Tp, int PL, int C, int mode) {
+                                float* __restrict__ out, bf16* __restrict__ out16, int N, int T, int Tp, int PL, int C, int mode) {
     const int c4 = C / 4;
     long long total = (long long)N * Tp * c4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -149,12 +165,14 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
         }
-        reinterpret_cast<float4*>(out)[i] = o;
+        if (out) reinterpret_cast<float4*>(out)[i] = o;
+        if (out16) st_bf16x4(out16 + 4 * i, o);
     }
 }
 int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s) {
-    bn_apply_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, N, T, Tp, PL, C, mode);
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16) {
+    TACO_REQUIRE(out || out16, TACO_EINVAL, "bn_apply: no output");
+    bn_apply_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, static_cast<bf16*>(out16), N, T, Tp, PL, C, mode);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -191,6 +209,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const float* __restrict_
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
+                                                     bf16* __restrict__ dx16, float* __restrict__ dbias,
                                                      int N, int T, int Tp, int PL, int C, int relu_mask, int chunks, int c_off) {
     const int tx = blockDim.x, ty = blockDim.y;
     const int c = c_off + (blockIdx.x * tx + threadIdx.x) * 4;
@@ -260,8 +279,20 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const float* __restrict_
                         if (!(xc.w > 0.f)) o.w = 0.f;
                     }
                 }
-                *reinterpret_cast<float4*>(dx + base + (long long)tp * C) = o;
+                if (dx) *reinterpret_cast<float4*>(dx + base + (long long)tp * C) = o;
+                if (dx16) st_bf16x4(dx16 + base + (long long)tp * C, o);
+                s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;       // column sums of dx = gradient of the convolution bias
             }
+        }
+    }
+    if (APPLY && dbias) {
+        __shared__ float4 redb[256];
+        const int tid = threadIdx.y * tx + threadIdx.x;
+        redb[tid] = s1;
+        __syncthreads();
+        if (threadIdx.y == 0 && cok) {
+            for (int y = 1; y < ty; y++) { const float4 a = redb[y * tx + threadIdx.x]; s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w; }
+            atomicAdd(dbias + c, s1.x); atomicAdd(dbias + c + 1, s1.y); atomicAdd(dbias + c + 2, s1.z); atomicAdd(dbias + c + 3, s1.w);
         }
     }
     if (!APPLY) {
@@ -289,8 +320,11 @@ static inline void lanes_2d(int C4, int& tx, int& ty) {
 }
 
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s) {
+                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s,
+                  void* dx16v, float* dbias) {
     TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "bn_bwd: channel count %d must be a multiple of 4", C);
+    TACO_REQUIRE(dx || dx16v, TACO_EINVAL, "bn_bwd: no output");
+    bf16* dx16 = static_cast<bf16*>(dx16v);
     int tx, ty; lanes_2d(C / 4, tx, ty);
     const int chunks = cdiv(Tp, ty * BNB_R);
     const int gx = cdiv(C / 4, tx);
@@ -302,11 +336,11 @@ int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const flo
     for (int gi = 0; gi < ngroups; gi++) {
         const int c_off = gi * 4 * tx;
         if (mode == 1) {
-            bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-            bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
         } else {
-            bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-            bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
+            bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
         }
     }
     TACO_CHECK_LAUNCH();
@@ -316,17 +350,18 @@ int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const flo
 // ---------------------------------------------------------------------------------------
 // highway combine: y = H*T + x*(1-T)
 __global__ void highway_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Tg, const float* __restrict__ x,
-                                   float* __restrict__ y, long long n4) {
+                                   float* __restrict__ y, bf16* __restrict__ y16, long long n4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 h = reinterpret_cast<const float4*>(H)[i], t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
         float4 o;
         o.x = h.x * t.x + v.x * (1.f - t.x); o.y = h.y * t.y + v.y * (1.f - t.y);
         o.z = h.z * t.z + v.z * (1.f - t.z); o.w = h.w * t.w + v.w * (1.f - t.w);
         reinterpret_cast<float4*>(y)[i] = o;
+        if (y16) st_bf16x4(y16 + 4 * i, o);
     }
 }
-int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s) {
-    highway_fwd_kernel<<<ew_blocks(n / 4), EW_THREADS, 0, s>>>(H, Tg, x, y, n / 4);
+int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s, void* y16) {
+    highway_fwd_kernel<<<ew_blocks(n / 4), EW_THREADS, 0, s>>>(H, Tg, x, y, static_cast<bf16*>(y16), n / 4);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -334,7 +369,7 @@ int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y
 // The two pre-activation gradients are written side by side into one [rows, 2C] matrix (dHpre | dTpre) so that the data
 // gradient dx += dHpre.WH^T + dTpre.WT^T is ONE GEMM with K = 2C against the packed [C, 2C] weight (model_cbhg.cu).
 __global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ H, const float* __restrict__ Tg,
-                                   const float* __restrict__ x, float* __restrict__ dHT, float* __restrict__ dx, long long n4, int c4) {
+                                   const float* __restrict__ x, float* __restrict__ dHT, bf16* __restrict__ dHT16, float* __restrict__ dx, long long n4, int c4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 d = reinterpret_cast<const float4*>(dy)[i], h = reinterpret_cast<const float4*>(H)[i];
         const float4 t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
@@ -345,16 +380,17 @@ __global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __
         b.x = d.x * (h.x - v.x) * t.x * (1.f - t.x); b.y = d.y * (h.y - v.y) * t.y * (1.f - t.y);
         b.z = d.z * (h.z - v.z) * t.z * (1.f - t.z); b.w = d.w * (h.w - v.w) * t.w * (1.f - t.w);
         o.x = d.x * (1.f - t.x); o.y = d.y * (1.f - t.y); o.z = d.z * (1.f - t.z); o.w = d.w * (1.f - t.w);
-        float4* out = reinterpret_cast<float4*>(dHT) + row * (2 * c4) + cq;
-        out[0] = a; out[c4] = b;
+        if (dHT) { float4* out = reinterpret_cast<float4*>(dHT) + row * (2 * c4) + cq; out[0] = a; out[c4] = b; }
+        if (dHT16) { bf16* o16 = dHT16 + (row * (2 * c4) + cq) * 4; st_bf16x4(o16, a); st_bf16x4(o16 + 4 * c4, b); }
         reinterpret_cast<float4*>(dx)[i] = o;
     }
 }
 int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT, float* dx,
-                       long long rows, int C, cudaStream_t s) {
+                       long long rows, int C, cudaStream_t s, void* dHT16) {
     TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "highway_bwd: width %d must be a multiple of 4", C);
+    TACO_REQUIRE(dHT || dHT16, TACO_EINVAL, "highway_bwd: no pre-activation gradient output");
     const long long n4 = rows * (C / 4);
-    highway_bwd_kernel<<<ew_blocks(n4), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHT, dx, n4, C / 4);
+    highway_bwd_kernel<<<ew_blocks(n4), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHT, static_cast<bf16*>(dHT16), dx, n4, C / 4);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -419,6 +455,87 @@ int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaSt
         dim3 grid(cdiv(C, 128), (unsigned)cdiv64(M, rows_per_block));
         colsum_kernel<<<grid, 128, 0, s>>>(x, out, M, C, ld, rows_per_block);
     }
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// bf16 input variant (bias gradients over a bf16 gradient mirror): 8 columns (16 bytes) per thread, (tx column lanes) x
+// (ty row lanes), four row loads in flight per thread; one fp32 atomic per column and block.
+__global__ void __launch_bounds__(256) colsum16_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long M, int C, long long ld,
+                                                       int rows_per_block) {
+    const int tx = blockDim.x, ty = blockDim.y;
+    const int c = (blockIdx.x * tx + threadIdx.x) * 8;
+    const bool cok = c < C;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cok) {
+        auto add = [&](const uint4 u) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h[e]); s[2 * e] += f.x; s[2 * e + 1] += f.y; }
+        };
+        long long r = r0 + threadIdx.y;
+        for (; r + 3LL * ty < r1; r += 4LL * ty) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(x + (r + ty) * ld + c));
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(x + (r + 2LL * ty) * ld + c));
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(x + (r + 3LL * ty) * ld + c));
+            add(a); add(b); add(d); add(e);
+        }
+        for (; r < r1; r += ty) add(__ldg(reinterpret_cast<const uint4*>(x + r * ld + c)));
+    }
+    __shared__ float red[256][9];
+    const int tid = threadIdx.y * tx + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 8; e++) red[tid][e] = s[e];
+    __syncthreads();
+    if (threadIdx.y == 0 && cok) {
+        for (int y = 1; y < ty; y++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) s[e] += red[y * tx + threadIdx.x][e];
+#pragma unroll
+        for (int e = 0; e < 8; e++) if (c + e < C) atomicAdd(out + c + e, s[e]);
+    }
+}
+// out[c] += sum_m x[m*ld + c], x bf16 with 16-byte aligned rows (ld % 8 == 0, base aligned, ld >= 8*ceil(C/8))
+int launch_colsum16(const void* x, float* out, long long M, int C, long long ld, cudaStream_t s) {
+    TACO_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld >= 8LL * cdiv(C, 8), TACO_EINVAL, "colsum16: rows must be 16-byte aligned");
+    const int C8 = cdiv(C, 8);
+    int tx = 1; while (tx < C8 && tx < 32) tx <<= 1;
+    if (tx < 4) tx = 4;
+    const int ty = 256 / tx;
+    const int bx = cdiv(C8, tx);
+    long long by = cdiv64(148 * 8, bx);
+    long long rpb = cdiv64(M, by);
+    if (rpb < 4LL * ty) rpb = 4LL * ty;
+    rpb = cdiv64(rpb, ty) * ty;
+    dim3 block(tx, ty), grid(bx, (unsigned)cdiv64(M, rpb));
+    colsum16_kernel<<<grid, block, 0, s>>>(static_cast<const bf16*>(x), out, M, C, ld, (int)rpb);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
+// fp32 -> bf16 strided 2-D cast: dst[r*ldd + c] = bf16(src[r*lds + c])   (parameter mirror, packed weights, recurrence outputs)
+__global__ void cast2d_kernel(bf16* __restrict__ dst, const float* __restrict__ src, long long rows, int cols, long long ldd, long long lds) {
+    long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / cols; int c = (int)(i % cols);
+        dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+    }
+}
+__global__ void cast2d_v4_kernel(bf16* __restrict__ dst, const float* __restrict__ src, long long rows, int cols4, long long ldd, long long lds) {
+    long long total = rows * cols4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / cols4; int c = (int)(i % cols4) * 4;
+        st_bf16x4(dst + r * ldd + c, __ldg(reinterpret_cast<const float4*>(src + r * lds + c)));
+    }
+}
+int launch_cast2d_bf16(void* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return TACO_OK;
+    if (cols % 4 == 0 && ldd % 4 == 0 && lds % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+        cast2d_v4_kernel<<<ew_blocks(rows * (cols / 4)), EW_THREADS, 0, s>>>(static_cast<bf16*>(dst), src, rows, cols / 4, ldd, lds);
+    else
+        cast2d_kernel<<<ew_blocks(rows * cols), EW_THREADS, 0, s>>>(static_cast<bf16*>(dst), src, rows, cols, ldd, lds);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -535,7 +652,7 @@ int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaS
 // grad[(n,t),c] = sign(out - tgt) * coeff[n] * (w_all + w_band*[lo<=c<hi])     (pad rows of grad untouched)
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
                                const float* __restrict__ tgt, const float* __restrict__ coeff,
-                               float* __restrict__ grad, long long grad_bs, long long grad_ts,
+                               float* __restrict__ grad, bf16* __restrict__ grad16, long long grad_bs, long long grad_ts,
                                int N, int T, int C, float w_all, float w_band, int lo, int hi, double* __restrict__ scalars) {
     // block = (tx column lanes) x (ty rows); rows (n,t) are strided over the grid, columns over tx: no per-element division
     const int tx = blockDim.x, ty = blockDim.y, rows = N * T;
@@ -545,6 +662,7 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
         const float* op = out + n * out_bs + t * out_ts;
         const float* tp = tgt + (long long)row * C;
         float* gp = grad ? grad + n * grad_bs + t * grad_ts : nullptr;
+        bf16* gp16 = grad16 ? grad16 + n * grad_bs + t * grad_ts : nullptr;
         const float cf = coeff ? __ldg(coeff + n) : 1.f;
         float rw = 0.f;
         for (int c0 = threadIdx.x; c0 < C; c0 += 4 * tx) {       // four columns per trip: all eight loads issued before the arithmetic
@@ -563,7 +681,9 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
                     const bool band = (c >= lo && c < hi);
                     const float w = w_all + (band ? w_band : 0.f);
                     rw = fmaf(a, w, rw); acc_all += a; if (band) acc_band += a;
-                    if (gp) gp[c] = ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f)) * cf * w;
+                    const float gv = ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f)) * cf * w;
+                    if (gp) gp[c] = gv;
+                    if (gp16) gp16[c] = __float2bfloat16_rn(gv);
                 }
             }
         }
@@ -582,11 +702,11 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 }
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
-                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s) {
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16) {
     int tx = 32; while (tx < C && tx < 256) tx <<= 1;
     const int ty = 256 / tx;
     int blocks = cdiv(N * T, ty); if (blocks > 148 * 8) blocks = 148 * 8;
-    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, grad_bs, grad_ts,
+    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, static_cast<bf16*>(grad16), grad_bs, grad_ts,
                                                    N, T, C, w_all, w_band, lo, hi, scalars);
     TACO_CHECK_LAUNCH();
     return TACO_OK;

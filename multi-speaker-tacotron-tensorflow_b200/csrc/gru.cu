@@ -328,8 +328,9 @@ static int check_gru_args(const GruArgs& a, bool bwd) {
     TACO_REQUIRE(a.ndir == 1 || a.ndir == 2, TACO_EINVAL, "gru: ndir must be 1 or 2");
     TACO_REQUIRE(a.H == 128 || a.H == 256, TACO_ESHAPE, "gru: hidden size %d not instantiated (128, 256)", a.H);
     TACO_REQUIRE(a.gx && a.Wg[0] && a.Wc[0], TACO_EINVAL, "gru: null operand");
-    if (bwd) TACO_REQUIRE(a.dout && a.dgx && a.st_r && a.st_u && a.st_c && a.st_hprev, TACO_EINVAL, "gru bwd: missing stash/grad buffers");
+    if (bwd) TACO_REQUIRE(a.dout && (a.dgx || (a.fast && a.dgx16)) && a.st_r && a.st_u && a.st_c && a.st_hprev, TACO_EINVAL, "gru bwd: missing stash/grad buffers");
     else TACO_REQUIRE(a.out, TACO_EINVAL, "gru fwd: null output");
+    TACO_REQUIRE(a.fast || !(a.out16 || a.st_hprev16 || a.dgx16 || a.dgx16_dense || a.st_rh16), TACO_EINVAL, "gru: bf16 mirrors are written by the fast kernels only");
     return TACO_OK;
 }
 

@@ -285,9 +285,11 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         if (valid) {      // output and stash stores ride in the shadow of the exchange
             const long long o = (long long)n * a.T + t;
             a.out[o * a.out_ld + d * H + unit] = h_own + cres;
+            if (a.out16) static_cast<__nv_bfloat16*>(a.out16)[o * a.out_ld + d * H + unit] = __float2bfloat16_rn(h_own + cres);
             if (a.st_r) {
                 const long long so = (st_base + t) * H + unit;
                 a.st_r[so] = rg; a.st_u[so] = ug; a.st_c[so] = cnd; a.st_hprev[so] = hprev;
+                if (a.st_hprev16) static_cast<__nv_bfloat16*>(a.st_hprev16)[so] = __float2bfloat16_rn(hprev);
             }
         }
 #else
@@ -428,9 +430,16 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_r, dg_s + rank * R * U, bar_g, tid);
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, tid);
         if (valid) {      // gradient / stash stores in the shadow of the exchange
-            float* g = a.dgx + ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
-            g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre;
+            const long long go = ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
+            if (a.dgx) { float* g = a.dgx + go; g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre; }
+            const __nv_bfloat16 br = __float2bfloat16_rn(dr_pre), bu = __float2bfloat16_rn(du_pre), bc = __float2bfloat16_rn(dc_pre);
+            if (a.dgx16) { __nv_bfloat16* g = static_cast<__nv_bfloat16*>(a.dgx16) + go; g[0] = br; g[H] = bu; g[2 * H] = bc; }
+            if (a.dgx16_dense) {
+                __nv_bfloat16* g = static_cast<__nv_bfloat16*>(a.dgx16_dense) + (st_base + t) * 3 * H + unit;
+                g[0] = br; g[H] = bu; g[2 * H] = bc;
+            }
             a.st_r[(st_base + t) * H + unit] = r_ * hp_;
+            if (a.st_rh16) static_cast<__nv_bfloat16*>(a.st_rh16)[(st_base + t) * H + unit] = __float2bfloat16_rn(r_ * hp_);
         }
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

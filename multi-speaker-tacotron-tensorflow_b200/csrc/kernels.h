@@ -16,7 +16,8 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s);
 
 // elementwise.cu
 int launch_fill(float* p, long long n, float v, cudaStream_t s);
-int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s);
+// (trailing `void* ...16` arguments: optional bf16 mirror of the output, see elementwise.cu)
+int launch_gather_rows(const float* table, const int* idx, float* out, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s, void* out16 = nullptr);
 int launch_scatter_add_rows(const float* dx, const int* idx, float* dtable, int N, int T, int Tp, int PL, int C, int n_rows_table, cudaStream_t s);
 int launch_bn_finalize(const double* sum, const double* sumsq, double count, float* mean, float* rstd, float* var,
                        const float* moving_mean, const float* moving_var, int C, int training, cudaStream_t s);
@@ -24,23 +25,26 @@ int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* 
 int launch_unpad(float* dst, const float* src, int N, int T, int Tp, int PL, int C, long long ld, cudaStream_t s);
 int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaStream_t s);
 int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s);
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16 = nullptr);
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s);
-int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s);
+                  float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s,
+                  void* dx16 = nullptr, float* dbias = nullptr /* += column sums of dx: the convolution's bias gradient */);
+int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s, void* y16 = nullptr);
 int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT /*[rows,2C]: dHpre | dTpre*/, float* dx,
-                       long long rows, int C, cudaStream_t s);
+                       long long rows, int C, cudaStream_t s, void* dHT16 = nullptr);
 int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
 int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s);
+int launch_colsum16(const void* x_bf16, float* out, long long M, int C, long long ld, cudaStream_t s);
+int launch_cast2d_bf16(void* dst_bf16, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
 int launch_bcast_rows(const float* src, float* dst, int N, int T, int C, long long ld, cudaStream_t s);
 int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int C, cudaStream_t s);
 int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s);
 int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
-                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s);
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16 = nullptr);
 
 // gru.cu — cluster-persistent GRU recurrences (TF GRUCell semantics)
 struct GruArgs {
@@ -67,6 +71,10 @@ struct GruArgs {
     // Forward chunks chain through h0 / hfinal, backward chunks (run last to first) through dh_in (carry in) / dh0 (out).
     int t_begin, t_end;
     const float* dh_in;                   // backward: gradient wrt the state after step t_end-1, [N, ndir*H] or NULL (zero)
+    // bf16 mirrors (fast kernels, TACO_PREC_BF16; each optional): forward: out16 indexed like out, st_hprev16 like st_hprev;
+    // backward: dgx16 indexed like dgx (dgx itself may then be NULL), dgx16_dense [ndir][N*T][3H] (the valid rows, dense: the
+    // operand of the recurrent weight gradients), st_rh16 [ndir][N][T][H] = r * h_prev
+    void* out16; void* st_hprev16; void* dgx16; void* dgx16_dense; void* st_rh16;
 };
 int launch_gru_fwd(const GruArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruArgs& a, cudaStream_t s);

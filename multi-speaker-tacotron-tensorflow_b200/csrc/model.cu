@@ -213,6 +213,16 @@ float* Model::W(const std::string& name) const {
     return reinterpret_cast<float*>(ws + it->second.offset);
 }
 double* Model::Wd(const std::string& name) const { return reinterpret_cast<double*>(W(name)); }
+void* Model::W16(const std::string& name) const {
+    auto it = regions.find(name + ".h");
+    return it == regions.end() ? nullptr : static_cast<void*>(ws + it->second.offset);
+}
+void* Model::P16(const std::string& name) const {
+    auto it = table.find(name);
+    auto r = regions.find("params16");
+    if (it == table.end() || !it->second.trainable || r == regions.end()) return nullptr;
+    return ws + r->second.offset + (size_t)it->second.offset * 2;
+}
 
 static CbhgGeom make_geom(const std::string& prefix, int N, int T, int Cin, int Kb, int Cb, int P1, int P2, int pw, int depth, int H) {
     CbhgGeom g;
@@ -225,15 +235,15 @@ static CbhgGeom make_geom(const std::string& prefix, int N, int T, int Cin, int 
 void Model::plan(const Shape& s) {
     regions.clear();
     size_t off = 0;
-    auto add = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems = 0, bool dbl = false) {
+    auto add_e = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems, bool dbl, bool half) {
         Region r{};
-        r.ndim = (int)dims.size(); r.is_double = dbl;
+        r.ndim = (int)dims.size(); r.is_double = dbl; r.is_half = half;
         int64_t n = 1; int i = 0;
         for (int64_t d : dims) { r.dims[i++] = d; n *= d; }
         int64_t st = 1;
         for (int k = r.ndim - 1; k >= 0; k--) { r.strides[k] = st; st *= r.dims[k]; }
         r.numel = n;
-        const size_t esz = dbl ? 8 : 4;
+        const size_t esz = dbl ? 8 : (half ? 2 : 4);
         off = (off + 255) / 256 * 256;
         off += (size_t)slack_elems * esz;
         off = (off + 255) / 256 * 256;
@@ -241,6 +251,12 @@ void Model::plan(const Shape& s) {
         off += (size_t)n * esz + (size_t)slack_elems * esz;
         regions[name] = r;
     };
+    auto add = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems = 0, bool dbl = false) { add_e(name, dims, slack_elems, dbl, false); };
+    const bool h16 = use16();
+    // bf16 mirror "<name>.h" of an fp32 region (same dims and slack), only in the bf16 precision mode
+    auto add16 = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems = 0) { if (h16) add_e(name + ".h", dims, slack_elems, false, true); };
+    // fp32 region that the bf16 mode replaces by its mirror alone
+    auto add32 = [&](const std::string& name, std::initializer_list<int64_t> dims, int64_t slack_elems = 0) { if (!h16) add(name, dims, slack_elems); };
     const taco_config& c = cfg;
     const int N = s.N, tr = s.training;
     enc = make_geom("enc_cbhg", N, s.Ti, c.enc_prenet_sizes[1], c.enc_bank_size, c.enc_bank_channels, c.enc_proj_sizes[0],
@@ -251,52 +267,58 @@ void Model::plan(const Shape& s) {
         const CbhgGeom& g = *gp;
         const std::string p = g.prefix + "/";
         const int64_t rows = g.rows, KC = (int64_t)g.Kb * g.Cb, H = g.H;
-        add(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin);
+        add(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin); add16(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin);
         add(p + "bank_raw", {rows, KC});
         add(p + "bank_stats", {2 * KC}, 0, true);
         add(p + "bank_mean", {KC}); add(p + "bank_rstd", {KC}); add(p + "bank_var", {KC});
-        add(p + "pooled_p", {rows, KC}, (int64_t)g.slack * KC);
+        // tensors only contractions read live as bf16 alone in the bf16 mode (add32 / add16 pairs)
+        add32(p + "pooled_p", {rows, KC}, (int64_t)g.slack * KC); add16(p + "pooled_p", {rows, KC}, (int64_t)g.slack * KC);
         add(p + "p1_raw", {rows, g.P1}); add(p + "p1_stats", {2 * (int64_t)g.P1}, 0, true);
         add(p + "p1_mean", {g.P1}); add(p + "p1_rstd", {g.P1}); add(p + "p1_var", {g.P1});
-        add(p + "p1_p", {rows, g.P1}, (int64_t)g.slack * g.P1);
+        add32(p + "p1_p", {rows, g.P1}, (int64_t)g.slack * g.P1); add16(p + "p1_p", {rows, g.P1}, (int64_t)g.slack * g.P1);
         add(p + "p2_raw", {rows, g.P2}); add(p + "p2_stats", {2 * (int64_t)g.P2}, 0, true);
         add(p + "p2_mean", {g.P2}); add(p + "p2_rstd", {g.P2}); add(p + "p2_var", {g.P2});
-        add(p + "hw0", {rows, g.P2});
-        if (g.has_hin) add(p + "hw_0", {rows, H});
+        add(p + "hw0", {rows, g.P2}); add16(p + "hw0", {rows, g.P2});
+        if (g.has_hin) { add(p + "hw_0", {rows, H}); add16(p + "hw_0", {rows, H}); }
         for (int i = 1; i <= g.depth; i++) {
-            add(p + "hw_" + std::to_string(i), {rows, H});
+            add(p + "hw_" + std::to_string(i), {rows, H}); add16(p + "hw_" + std::to_string(i), {rows, H});
             add(p + "hwH_" + std::to_string(i), {rows, H});
             add(p + "hwT_" + std::to_string(i), {rows, H});
         }
         add(p + "gx", {rows, 6 * H});
-        add(p + "rnn_out", {(int64_t)g.N * g.T, 2 * H});
+        add(p + "rnn_out", {(int64_t)g.N * g.T, 2 * H}); add16(p + "rnn_out", {(int64_t)g.N * g.T, 2 * H});
         if (tr) {
             const int64_t st = 2 * (int64_t)g.N * g.T * H;
             add(p + "st_r", {st}); add(p + "st_u", {st}); add(p + "st_c", {st}); add(p + "st_hprev", {st});
+            add16(p + "st_hprev", {st}); add16(p + "st_rh", {st});
             add(p + "d_rnn_out", {(int64_t)g.N * g.T, 2 * H});
-            add(p + "dgx", {rows, 6 * H});
-            add(p + "dgx_dense", {2, (int64_t)g.N * g.T, 3 * H});
+            add32(p + "dgx", {rows, 6 * H}); add16(p + "dgx", {rows, 6 * H});
+            add32(p + "dgx_dense", {2, (int64_t)g.N * g.T, 3 * H}); add16(p + "dgx_dense", {2, (int64_t)g.N * g.T, 3 * H});
             add(p + "d_hwA", {rows, H}); add(p + "d_hwB", {rows, H});
             // per layer: (dHpre | dTpre) side by side and the packed [H, 2H] weight their shared data gradient uses
-            for (int i = 1; i <= g.depth; i++) { add(p + "d_HT_" + std::to_string(i), {rows, 2 * H}); add(p + "hw_wcat_" + std::to_string(i), {H, 2 * H}); }
-            add(p + "gru_wxcat", {H, 6 * H});                   // x-side rows of the four GRU kernels: fw r|u, fw c, bw r|u, bw c
+            for (int i = 1; i <= g.depth; i++) {
+                add32(p + "d_HT_" + std::to_string(i), {rows, 2 * H}); add16(p + "d_HT_" + std::to_string(i), {rows, 2 * H});
+                add(p + "hw_wcat_" + std::to_string(i), {H, 2 * H}); add16(p + "hw_wcat_" + std::to_string(i), {H, 2 * H});
+            }
+            add(p + "gru_wxcat", {H, 6 * H}); add16(p + "gru_wxcat", {H, 6 * H});   // x-side rows of the four GRU kernels: fw r|u, fw c, bw r|u, bw c
             if (g.has_hin) add(p + "d_hw0", {rows, g.P2});
-            add(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2);
+            add32(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2); add16(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2);
             add(p + "d_p1p", {rows, g.P1});
-            add(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1);
+            add32(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1); add16(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1);
             add(p + "d_pooled", {rows, KC});
-            add(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC);
+            add32(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC); add16(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC);
             add(p + "d_xin_p", {rows, g.Cin});
             add(p + "d_before", {g.N, g.P2});
             add(p + "d_h0", {g.N, 2 * H});
             // flipped + transposed bank kernels, stored back to back ([sum_k k*Cb, Cin]) so that the bank's data gradient is
             // ONE GEMM; "bank_taps" is its per-k-tile (column, row offset) table (int32 pairs)
-            add(p + "bank_wd", {(int64_t)g.Cb * g.Kb * (g.Kb + 1) / 2, g.Cin});
+            add(p + "bank_wd", {(int64_t)g.Cb * g.Kb * (g.Kb + 1) / 2, g.Cin}); add16(p + "bank_wd", {(int64_t)g.Cb * g.Kb * (g.Kb + 1) / 2, g.Cin});
             add(p + "bank_taps", {(int64_t)2 * (g.Cb / 32 + 1) * g.Kb * (g.Kb + 1) / 2});
-            add(p + "proj_1/wd", {(int64_t)g.pw * g.P1, KC});
-            add(p + "proj_2/wd", {(int64_t)g.pw * g.P2, g.P1});
+            add(p + "proj_1/wd", {(int64_t)g.pw * g.P1, KC}); add16(p + "proj_1/wd", {(int64_t)g.pw * g.P1, KC});
+            add(p + "proj_2/wd", {(int64_t)g.pw * g.P2, g.P1}); add16(p + "proj_2/wd", {(int64_t)g.pw * g.P2, g.P1});
         }
     }
+    if (h16) add_e("params16", {(n_trainable + 7) / 8 * 8}, 0, false, true);       // bf16 mirror of the flat trainable buffer
     // encoder prenet as lookup tables over the symbol set (the prenet is position-wise: 80 distinct rows)
     add("enc/table1", {c.num_symbols, c.enc_prenet_sizes[0]});
     add("enc/table2", {c.num_symbols, c.enc_prenet_sizes[1]});
@@ -345,18 +367,19 @@ void Model::plan(const Shape& s) {
             add("dec/v_eff", {A}); add("dec/g_veff", {A});
         }
     }
-    // The linear-spectrogram tensors use a row pitch rounded up to 4 floats (1025 -> 1028) so TMA can address them
-    // (16-byte pitches); the pad columns stay zero.  "linear_outputs" is exposed as a strided [N,To,F] view.
+    // The linear-spectrogram tensors use a row pitch rounded up to 8 elements (1025 -> 1032) so TMA can address them and
+    // their bf16 mirrors (16-byte pitches); the pad columns stay zero.  "linear_outputs" is exposed as a strided [N,To,F] view.
     {
-        const int64_t Fp = (c.num_freq + 3) / 4 * 4;
+        const int64_t Fp = (c.num_freq + 7) / 8 * 8;
         add("linear_buf", {(int64_t)N * s.To, Fp});
         Region r = regions["linear_buf"];
         r.ndim = 3; r.dims[0] = N; r.dims[1] = s.To; r.dims[2] = c.num_freq;
         r.strides[0] = (int64_t)s.To * Fp; r.strides[1] = Fp; r.strides[2] = 1;
         r.numel = (int64_t)N * s.To * c.num_freq;
         regions["linear_outputs"] = r;
-        add("linear/w_pad", {2 * (int64_t)c.post_rnn_size + ((c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0), Fp});
-        if (tr) add("d_linear", {(int64_t)N * s.To, Fp});
+        const int64_t wrows = 2 * (int64_t)c.post_rnn_size + ((c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0);
+        add("linear/w_pad", {wrows, Fp}); add16("linear/w_pad", {wrows, Fp});
+        if (tr) { add("d_linear", {(int64_t)N * s.To, Fp}); add16("d_linear", {(int64_t)N * s.To, Fp}); }
     }
     if (tr) add("post_cbhg/d_mel_loss", {post.rows, c.num_mels});
     if (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE) {
@@ -367,7 +390,7 @@ void Model::plan(const Shape& s) {
         if (tr) { add("spk/d_pre", {N, 2 * (int64_t)c.enc_rnn_size + c.attention_state_size + Y}); add("spk/d_embed", {N, S}); }
     }
     if (c.speaker_mode == TACO_SPK_SIMPLE) {
-        const int64_t S = c.speaker_embedding_size, Fp = (c.num_freq + 3) / 4 * 4;
+        const int64_t S = c.speaker_embedding_size, Fp = (c.num_freq + 7) / 8 * 8;
         add("spk/embed", {N, S}); add("spk/lin_bias", {N, Fp});
         if (tr) {
             add("spk/d_embed", {N, S}); add("spk/s_lin", {N, Fp});
@@ -447,15 +470,25 @@ static int backward_prep(Model& m, cudaStream_t s) {
             TACO_TRY(launch_copy2d(wc, m.P(hn + "/H_kernel"), H, H, 2 * H, H, s));
             TACO_TRY(launch_copy2d(wc + H, m.P(hn + "/T_kernel"), H, H, 2 * H, H, s));
         }
-        if (!m.tables_ready && g.Cb % 32 == 0) {
-            // k-tile i of the merged bank data gradient: member k, tap j, 32-channel block q  ->  column (k-1)*Cb + 32q of
+        if (m.use16()) {
+            // bf16 mirrors of the packed operands (the contraction kernels of the bf16 mode read nothing else)
+            auto mirror = [&](const std::string& name) -> int {
+                auto it = m.regions.find(name);
+                return launch_cast2d_bf16(m.W16(name), m.W(name), 1, (int)it->second.numel, it->second.numel, it->second.numel, s);
+            };
+            TACO_TRY(mirror(p + "bank_wd")); TACO_TRY(mirror(p + "proj_1/wd")); TACO_TRY(mirror(p + "proj_2/wd")); TACO_TRY(mirror(p + "gru_wxcat"));
+            for (int i = 1; i <= g.depth; i++) TACO_TRY(mirror(p + "hw_wcat_" + std::to_string(i)));
+        }
+        const int tb = m.use16() ? 64 : 32;          // k-tile width of the kernel that walks the table
+        if (!m.tables_ready && g.Cb % tb == 0) {
+            // k-tile i of the merged bank data gradient: member k, tap j, channel block q  ->  column (k-1)*Cb + tb*q of
             // d_bank, row offset j - r_k (+ Kb: the operand base sits Kb slack rows before the buffer)
             std::vector<int>& tab = (gp == &m.enc) ? m.taps_enc : m.taps_post;
             tab.clear();
             for (int k = 1; k <= g.Kb; k++) {
                 const int l = (k - 1) / 2, r = k - 1 - l;
                 for (int j = 0; j < k; j++)
-                    for (int q = 0; q < g.Cb / 32; q++) { tab.push_back((k - 1) * g.Cb + 32 * q); tab.push_back(j - r + g.Kb); }
+                    for (int q = 0; q < g.Cb / tb; q++) { tab.push_back((k - 1) * g.Cb + tb * q); tab.push_back(j - r + g.Kb); }
             }
             TACO_CHECK_CUDA(cudaMemcpyAsync(m.W(p + "bank_taps"), tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
         }
@@ -486,6 +519,8 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const taco_config& c = m.cfg;
     const int prec = c.precision, tr = m.shape.training;
     const bool simple = (c.speaker_mode == TACO_SPK_SIMPLE);
+    if (m.use16())     // bf16 mirror of every trainable tensor (18.7 MB written per step; the GEMM B operands of this pass and the next backward pass)
+        TACO_TRY(launch_cast2d_bf16(m.W16("params16") ? m.W16("params16") : nullptr, m.params, 1, (int)m.n_trainable, m.n_trainable, m.n_trainable, s));
     if (simple) {
         // 'simple' injection: one embedding row per utterance, concatenated at three sites (tacotron.py:44-49,82-86)
         TACO_REQUIRE(b->speaker_id != nullptr, TACO_EINVAL, "speaker_id is required when num_speakers > 1");
@@ -522,20 +557,24 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         d.bias = m.P("enc_prenet/dense_2/bias"); d.act = ACT_RELU;
         TACO_TRY(launch_gemm(&d, 1, prec, s));
     }
-    TACO_TRY(launch_gather_rows(m.W("enc/table2"), b->inputs, m.W("enc_cbhg/xin_p"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s));
+    TACO_TRY(launch_gather_rows(m.W("enc/table2"), b->inputs, m.W("enc_cbhg/xin_p"), m.enc.N, m.enc.T, m.enc.Tp, m.enc.PL, E2, V, s, m.W16("enc_cbhg/xin_p")));
     prof_mark("fwd:enc_cbhg", s);
     TACO_TRY(cbhg_forward(m, m.enc, b->input_lengths, spk ? m.W("spk/before") : nullptr, spk ? m.W("spk/enc_init") : nullptr, tr, s));
     prof_mark("fwd:decoder", s);
     TACO_TRY(decoder_forward(m, b, s));
     prof_mark("fwd:post_cbhg", s);
+    if (m.use16())     // the decoder's small GEMMs stay on the fp32-operand kernels: mirror the mel frames they wrote (pad rows stay zero)
+        TACO_TRY(launch_cast2d_bf16(m.W16("post_cbhg/xin_p"), m.W("post_cbhg/xin_p"), m.post.rows, c.num_mels, c.num_mels, c.num_mels, s));
     TACO_TRY(cbhg_forward(m, m.post, nullptr, nullptr, nullptr, tr, s));
     prof_mark("fwd:linear", s);
     // ---- linear-spectrogram projection (tacotron.py:235) ----
     {
-        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 3) / 4 * 4;
+        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 7) / 8 * 8;
         const int S = simple ? c.speaker_embedding_size : 0;
         TACO_TRY(launch_copy2d(m.W("linear/w_pad"), m.P("linear/kernel"), Hp2 + S, F, Fp, F, s));     // 16-byte row pitch for TMA
+        if (m.use16()) TACO_TRY(launch_cast2d_bf16(m.W16("linear/w_pad"), m.P("linear/kernel"), Hp2 + S, F, Fp, F, s));
         taco_gemm_desc d = gd0(m.W("post_cbhg/rnn_out"), m.W("linear/w_pad") + (long long)S * Fp, m.W("linear_buf"), m.shape.N * m.shape.To, F, Hp2, Hp2, Fp, Fp);
+        if (m.use16()) { d.A16 = m.W16("post_cbhg/rnn_out"); d.B16 = static_cast<uint16_t*>(m.W16("linear/w_pad")) + (long long)S * Fp; }
         if (simple) {
             // concat([tiled speaker_embed, post_outputs]) . W  ==  post . W[S:] + (embed . W[:S] + b) tiled over time   tacotron.py:226-235
             taco_gemm_desc e = gd0(m.W("spk/embed"), m.W("linear/w_pad"), m.W("spk/lin_bias"), m.shape.N, F, S, S, Fp, Fp);
@@ -577,9 +616,9 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         lo = c.priority_lo; hi = c.priority_hi;
         w_all = (float)(0.5 / cnt_lin); w_band = (float)(0.5 / ((double)N * To * (hi - lo)));
     }
-    const int Fp = (F + 3) / 4 * 4;
+    const int Fp = (F + 7) / 8 * 8;
     TACO_TRY(launch_l1_loss(m.W("linear_buf"), (long long)To * Fp, Fp, b->linear_targets, b->loss_coeff,
-                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s));
+                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear")));
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
                             m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
                             (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
@@ -590,6 +629,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         const int S = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
         taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel") + (long long)S * F, Hp2, F, (int)rows, Hp2, Fp, F);
         w.transA = 1; w.accumulate = 1; w.split_k = 8;
+        w.A16 = m.W16("post_cbhg/rnn_out"); w.B16 = m.W16("d_linear");
         cudaStream_t leaf = fork_side(s);
         TACO_TRY(launch_gemm(&w, 1, prec, leaf));
         TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, leaf));
@@ -607,6 +647,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         }
         taco_gemm_desc e = gd0(m.W("d_linear"), m.W("linear/w_pad") + (long long)S * Fp, m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
         e.transB = 1;
+        if (m.use16()) { e.A16 = m.W16("d_linear"); e.B16 = static_cast<uint16_t*>(m.W16("linear/w_pad")) + (long long)S * Fp; }
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
     prof_mark("bwd:post_cbhg", s);
@@ -689,6 +730,7 @@ int64_t taco_launch_count(void) { return g_launch_count; }
 int taco_create(taco_model* out, const taco_config* cfg) {
     TACO_REQUIRE(out && cfg, TACO_EINVAL, "taco_create: null argument");
     TACO_REQUIRE(cfg->abi_version == TACO_ABI_VERSION, TACO_EINVAL, "taco_create: ABI version %d != %d", cfg->abi_version, TACO_ABI_VERSION);
+    TACO_REQUIRE(cfg->precision >= TACO_PREC_FP32 && cfg->precision <= TACO_PREC_BF16, TACO_EINVAL, "taco_create: unknown precision %d", cfg->precision);
     TACO_REQUIRE(cfg->attention_type >= 0 && cfg->attention_type <= 2, TACO_EINVAL, " [!] Unkown attention type: %d", cfg->attention_type);
     TACO_REQUIRE(cfg->speaker_mode >= 0 && cfg->speaker_mode <= 3, TACO_EINVAL, " [!] Unkown multi-speaker model type: %d", cfg->speaker_mode);
     TACO_REQUIRE(cfg->reduction_factor >= 1 && cfg->num_mels > 0 && cfg->num_freq > 0, TACO_EINVAL, "taco_create: bad sizes");
@@ -722,6 +764,10 @@ int taco_bind_params(taco_model h, const taco_param_entry* table, int32_t n_entr
     m.n_trainable = n_trainable; m.n_state = n_state;
     // every tensor the kernels will dereference must be present with the expected size
     const taco_config& c = m.cfg;
+    if (c.precision == TACO_PREC_BF16)
+        for (const auto& kv : m.table)
+            TACO_REQUIRE(!kv.second.trainable || kv.second.offset % 8 == 0, TACO_EINVAL,
+                         "taco_bind_params: bf16 mode needs 16-byte aligned bf16 mirrors: offset of '%s' must be a multiple of 8 elements", kv.first.c_str());
     auto need = [&](const std::string& name, int64_t numel) -> int {
         auto it = m.table.find(name);
         TACO_REQUIRE(it != m.table.end(), TACO_EINVAL, "taco_bind_params: missing tensor '%s'", name.c_str());
@@ -779,7 +825,7 @@ int taco_ws_region(taco_model h, const char* name, size_t* offset_bytes, int64_t
     const Region& r = it->second;
     if (offset_bytes) *offset_bytes = r.offset;
     if (numel) *numel = r.numel;
-    if (ndim) *ndim = r.is_double ? -r.ndim : r.ndim;
+    if (ndim) *ndim = r.is_double ? -r.ndim : (r.is_half ? 100 + r.ndim : r.ndim);      // sign / offset encode the element type
     for (int i = 0; i < 4; i++) { if (dims) dims[i] = i < r.ndim ? r.dims[i] : 1; if (strides) strides[i] = i < r.ndim ? r.strides[i] : 0; }
     return TACO_OK;
 }

@@ -16,6 +16,7 @@ struct Region {
     int64_t numel;      // elements (fp32 unless is_double)
     int ndim; int64_t dims[4]; int64_t strides[4];
     bool is_double;
+    bool is_half;       // bf16 mirror region (TACO_PREC_BF16)
 };
 
 // Geometry of one CBHG block in the zero-padded time layout.
@@ -60,6 +61,12 @@ struct Model {
     // workspace
     void plan(const Shape& s);
     float* W(const std::string& name) const;   // region pointer (fp32)
+    // bf16 mirrors (TACO_PREC_BF16): region "<name>.h" next to (or instead of) the fp32 region; W16 yields nullptr when the plan
+    // has no such mirror (other precisions), so call sites can pass it straight to the optional kernel arguments.  P16: the
+    // parameter's slot in the bf16 mirror of the flat trainable buffer (region "params16", refreshed by every forward pass).
+    void* W16(const std::string& name) const;
+    void* P16(const std::string& name) const;
+    bool use16() const { return cfg.precision == TACO_PREC_BF16; }
     double* Wd(const std::string& name) const; // region pointer (double)
     bool has_region(const std::string& name) const { return regions.count(name) != 0; }
 };

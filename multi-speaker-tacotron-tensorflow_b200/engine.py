@@ -118,8 +118,12 @@ class Engine:
         off, numel, ndim = C.c_size_t(), C.c_int64(), C.c_int32()
         dims, strides = (C.c_int64 * 4)(), (C.c_int64 * 4)()
         capi.check(self.lib.taco_ws_region(self._h, name.encode(), C.byref(off), C.byref(numel), dims, strides, C.byref(ndim)))
-        nd = abs(ndim.value)
-        dt, esz = (torch.float64, 8) if ndim.value < 0 else (torch.float32, 4)
+        nv = ndim.value                       # sign / offset encode the element type: -n double, 100+n bf16 mirror, n fp32
+        if nv >= 100:
+            nd, dt, esz = nv - 100, torch.bfloat16, 2
+        else:
+            nd = abs(nv)
+            dt, esz = (torch.float64, 8) if nv < 0 else (torch.float32, 4)
         base = self._ws.view(dt)
         return torch.as_strided(base, [dims[i] for i in range(nd)], [strides[i] for i in range(nd)], off.value // esz)
 

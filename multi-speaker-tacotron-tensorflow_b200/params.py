@@ -23,7 +23,7 @@ import torch
 NUM_SYMBOLS = 80  # reference: text/symbols.py:13 (PAD, EOS + jamo + punctuation + space)
 PAD_ID, EOS_ID = 0, 1
 
-ALIGN = 4  # elements
+ALIGN = 8  # elements (16 bytes in the bf16 mirror of the flat buffer)
 
 
 @dataclass(frozen=True)

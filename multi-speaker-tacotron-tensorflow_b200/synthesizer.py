@@ -220,7 +220,7 @@ def main(argv=None):
     parser.add_argument("--num_speakers", default=1, type=int)
     parser.add_argument("--speaker_id", default=0, type=int)
     parser.add_argument("--checkpoint_step", default=None, type=int)
-    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     config = parser.parse_args(argv)
     os.makedirs(config.sample_path, exist_ok=True)
     from .text import text_to_sequence            # jamo decomposition without the reference's text normalisation (see text.py)

@@ -207,7 +207,7 @@ def build_parser():
     parser.add_argument("--slack_url", help="(accepted for compatibility; Slack reporting is not implemented)")
     parser.add_argument("--git", action="store_true", help="(accepted for compatibility)")
     # additions of this implementation
-    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    parser.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     parser.add_argument("--max_steps", type=int, default=0, help="stop after this many steps (0 = run until interrupted)")
     parser.add_argument("--test_audio", type=str2bool, default=False, help="write Griffin-Lim audio of the periodic test step")
     parser.add_argument("--hparams", default="", help="comma separated name=value overrides")
