@@ -409,7 +409,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-synth", dest="synth", action="store_false", help="skip the C4 synthesis real-time-factor leg (N=1 only)")
     args = ap.parse_args()

@@ -27,10 +27,11 @@
 
 namespace taco {
 
-constexpr int BF_BM = 128, BF_BK = 64, BF_BN_MAX = 256, BF_MAX_STAGES = 6, BF_EPI_WARPS = 8, BF_THREADS = 64 + 32 * BF_EPI_WARPS;
+constexpr int BF_BM = 128, BF_BK = 64, BF_BN_MAX = 256, BF_MAX_STAGES = 6, BF_PROD_WARPS = 3, BF_EPI_WARPS = 8;
+constexpr int BF_EPI_WARP0 = BF_PROD_WARPS + 1, BF_THREADS = 32 * (BF_PROD_WARPS + 1 + BF_EPI_WARPS);     // warps 0-2 TMA, warp 3 MMA, warps 4-11 epilogue
 constexpr int BF_A_BYTES = BF_BM * BF_BK * 2;                    // 16 KB
 constexpr int BF_STG_FLOATS = 32 * 36;                           // per epilogue warp: 32x32 transpose buffer, pitch 36
-constexpr int BF_FIXED_SMEM = BF_EPI_WARPS * BF_STG_FLOATS * 4 + 4 * 2 * BF_BN_MAX * 4 + 256;   // staging + statistics partials + barriers
+constexpr int BF_FIXED_SMEM = BF_EPI_WARPS * BF_STG_FLOATS * 4 + 4 * 2 * BF_BN_MAX * 4 + 512;   // staging + statistics partials + barriers
 constexpr int BF_SMEM = 227 * 1024;                              // all of it: the stage ring takes what the fixed part leaves
 constexpr int BF_RING_BYTES = BF_SMEM - 1024 - BF_FIXED_SMEM;    // 1024: alignment slack
 constexpr int BF_SCHED_SLOTS = 256;
@@ -42,6 +43,7 @@ struct BfParams {
     int stages, b_stage_bytes;           // ring depth and B stage pitch: ceil(BN/64) x 8 KB
     int fast_ok;                         // the lean epilogue applies to interior chunks (vector stores, aligned bias, no read-modify-write)
     int a_mn_major, b_mn_major;
+    int b_3d;                            // MN-major B tile through ONE 3-D box {64 n, 64 k, BN/64 n-blocks}
     int a_tap, a_ctap, tap_inner, tap_group;   // tap_inner: number of taps (0: tap-major walk); tap_group: channel blocks per group
     const int2* tap_table;
     float alpha; int accumulate;
@@ -53,6 +55,10 @@ struct BfParams {
     unsigned int* sched;                 // [0] next work unit, [1] CTAs done (the last one resets both)
 };
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -121,7 +127,7 @@ __device__ __forceinline__ void bf_epi_chunk(const BfParams& p, uint32_t stg, co
 // Lean epilogue of an interior 32x32 chunk (all rows valid, all columns inside N, 128-bit stores): ~25 instructions per row.
 // The epilogue is instruction-bound - each epilogue warp runs alone or in pairs on its scheduler, so every dependent
 // instruction costs its full latency (measured: the general path below took ~3 000 clk per chunk).
-template <int ACT, bool STATS>
+template <int ACT, bool STATS, bool ACC = false>
 __device__ __forceinline__ void bf_epi_fast(const BfParams& p, uint32_t stg_lane, float* const crow[8], __nv_bfloat16* const crow16[8], uint32_t maskmask,
                                             int gn, float4 bz, float cs[4], float cq[4]) {
     const float alpha = p.alpha;
@@ -132,6 +138,7 @@ __device__ __forceinline__ void bf_epi_fast(const BfParams& p, uint32_t stg_lane
         float x0 = act_ct<ACT>(fmaf(alpha, t4.x, bz.x)), x1 = act_ct<ACT>(fmaf(alpha, t4.y, bz.y));
         float x2 = act_ct<ACT>(fmaf(alpha, t4.z, bz.z)), x3 = act_ct<ACT>(fmaf(alpha, t4.w, bz.w));
         if ((maskmask >> i) & 1u) { x0 = 0.f; x1 = 0.f; x2 = 0.f; x3 = 0.f; }
+        if (ACC) { const float4 o = ldg_v4(crow[i] + gn); x0 += o.x; x1 += o.y; x2 += o.z; x3 += o.w; }
         if (hc) stg_v4(crow[i] + gn, x0, x1, x2, x3);
         if (hc16) stg_v2_b32(crow16[i] + gn, pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
         if (STATS) {
@@ -150,6 +157,15 @@ __device__ __forceinline__ void bf_epi_fast_atomic(const BfParams& p, uint32_t s
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow[i] + gn), "f"(fmaf(alpha, t4.x, bz.x)), "f"(fmaf(alpha, t4.y, bz.y)),
                      "f"(fmaf(alpha, t4.z, bz.z)), "f"(fmaf(alpha, t4.w, bz.w)) : "memory");
     }
+}
+
+// bytes producer warp w lands per k-tile (see the producer section of the kernel for the box assignment)
+__device__ __forceinline__ uint32_t prod_bytes(const BfParams& p, int w) {
+    const uint32_t nboxB = p.b_mn_major ? (uint32_t)((p.BN + 63) >> 6) : 0u;
+    const bool b2d = p.b_mn_major && !p.b_3d;
+    if (w == 0) return p.a_mn_major ? 8192u : (uint32_t)BF_A_BYTES;
+    if (w == 1) return (p.a_mn_major ? 8192u : 0u) + (b2d ? (nboxB / 2) * 8192u : 0u);
+    return !p.b_mn_major ? (uint32_t)p.BN * 128u : (p.b_3d ? nboxB * 8192u : ((nboxB + 1) / 2) * 8192u);
 }
 
 // debug timeline (ns, %globaltimer) of CTA 0: 0 start, 1 setup done, then per local tile lt < 15: 2+4lt first operands landed,
@@ -172,8 +188,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* sB = smem + STAGES * BF_A_BYTES;                    // [STAGES][b_stage_bytes]
     float* stg_all = reinterpret_cast<float*>(smem + BF_RING_BYTES);
     float* red = stg_all + BF_EPI_WARPS * BF_STG_FLOATS;         // [4 quarters][2 stats][256]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 4 * 2 * BF_BN_MAX);
-    uint64_t* empty_bar = full_bar + BF_MAX_STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 4 * 2 * BF_BN_MAX);      // [producer warp][stage]: one barrier per issuing warp
+    uint64_t* empty_bar = full_bar + BF_PROD_WARPS * BF_MAX_STAGES;
     uint64_t* tmem_full = empty_bar + BF_MAX_STAGES;             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                        // [2]
     uint64_t* sched_full = tmem_empty + 2;                       // [2]
@@ -188,11 +204,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
-        for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], BF_EPI_WARPS); mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 1 + BF_EPI_WARPS); }
+        for (int i = 0; i < STAGES; i++) { for (int w = 0; w < BF_PROD_WARPS; w++) mbar_init(&full_bar[w * BF_MAX_STAGES + i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], BF_EPI_WARPS); mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], (BF_PROD_WARPS - 1) + 1 + BF_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == BF_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BF_BN_MAX));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -209,81 +225,97 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         kt0 = sp * p.kt_per; nkt = min(p.ktiles, kt0 + p.kt_per) - kt0;
     };
 
-    if (warp == 0) {
-        // ===================== scheduler + TMA producer =====================
+    if (warp < BF_PROD_WARPS) {
+        // ===================== scheduler (warp 0) + TMA producers (warps 0-2) =====================
+        // Measured on B200 (tools/tma_bench*.cu): ONE issuing thread gets a cp.async.bulk.tensor instruction through every
+        // ~770 clk whatever the box holds (8 KB or 64 KB), different warps overlap fully (4 warps x 16 KB boxes: 81 B/clk/SM).
+        // A k-tile's boxes are therefore spread over three warps - A (or A's first half) on warp 0, A's second half on
+        // warp 1, B on warp 2 as one 2-D (K-major) or 3-D (MN-major: all 64-column blocks at once) box; a B tile that
+        // needs several 2-D boxes alternates them between warps 2 and 1.
+        // Each producer warp completes its boxes on its OWN full barrier (boxes of different warps on one barrier were measured
+        // to serialise again); the MMA warp waits for the barriers of all warps that carry bytes in this configuration.
         const uint32_t nboxB = p.b_mn_major ? (uint32_t)((BN + 63) >> 6) : 0u;
-        const uint32_t stage_bytes = (uint32_t)BF_A_BYTES + (p.b_mn_major ? nboxB * 8192u : (uint32_t)BN * 128u);
+        const uint32_t my_bytes = prod_bytes(p, warp);
+        uint64_t* my_full = full_bar + warp * BF_MAX_STAGES;
         int it = 0;
         int next = 0;
-        if (lane == 0) next = (int)atomicAdd(p.sched, 1u);
+        if (warp == 0 && lane == 0) next = (int)atomicAdd(p.sched, 1u);
         for (int lt = 0;; lt++) {
             const int slot = lt & 1, use = lt >> 1;
             int u = 0;
-            if (lane == 0) {
-                u = next;
-                if (use > 0) mbar_wait_bounded(&sched_empty[slot], (use - 1) & 1);
-                sched_unit[slot] = u;
-                mbar_arrive(&sched_full[slot]);
-                if (u < p.units) next = (int)atomicAdd(p.sched, 1u);      // fetched one tile ahead: its latency hides behind this tile's loads
+            if (warp == 0) {
+                if (lane == 0) {
+                    u = next;
+                    if (use > 0) mbar_wait_bounded(&sched_empty[slot], (use - 1) & 1);
+                    sched_unit[slot] = u;
+                    mbar_arrive(&sched_full[slot]);
+                    if (u < p.units) next = (int)atomicAdd(p.sched, 1u);  // fetched one tile ahead: its latency hides behind this tile's loads
+                }
+                u = __shfl_sync(0xffffffffu, u, 0);
+            } else {
+                mbar_wait_bounded(&sched_full[slot], use & 1);
+                u = sched_unit[slot];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sched_empty[slot]);
             }
-            u = __shfl_sync(0xffffffffu, u, 0);
             if (u >= p.units) break;
             int m0, n0, kt0, nkt;
             decode(u, m0, n0, kt0, nkt);
-            for (int j = 0; j < nkt; j++, it++) {
-                const int stage = it % STAGES, round = it / STAGES;
-                if (lane == 0) {
+            if (lane == 0) {
+                for (int j = 0; j < nkt; j++, it++) {
+                    const int stage = it % STAGES, round = it / STAGES;
                     if (round > 0) mbar_wait_bounded(&empty_bar[stage], (round - 1) & 1);
-                    mbar_expect_tx(&full_bar[stage], stage_bytes);
-                }
-                __syncwarp();
-                const int kt = kt0 + j;
-                int k0 = kt * BF_BK;
-                if (p.tap_inner) {
-                    // K walk of a convolution: (group of G channel blocks, tap, block in group).  The first tap of a group
-                    // streams G x 128 contiguous bytes of every activation row from DRAM, the other taps re-read the same rows
-                    // shifted by one frame while they are still in L2 (tap-major order re-reads a row slab only after the
-                    // whole wave streamed all channels: 3x the DRAM traffic on the post-net projections).
-                    const int per = p.tap_inner * p.tap_group;
-                    const int gq = kt / per, rem = kt - gq * per, tj = rem / p.tap_group, cb = gq * p.tap_group + (rem - tj * p.tap_group);
-                    k0 = tj * p.a_ctap + cb * BF_BK;
-                }
-                uint8_t* a = sA + stage * BF_A_BYTES;
-                uint8_t* b = sB + stage * p.b_stage_bytes;
-                if (lane < 2) {
-                    if (!p.a_mn_major) {
-                        if (lane == 0) {
-                            if (p.tap_table) { const int2 tc = __ldg(p.tap_table + kt); tma_load_2d(a, &mapA, tc.x, m0 + tc.y, &full_bar[stage]); }
-                            else if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &full_bar[stage]);
-                            else tma_load_2d(a, &mapA, k0, m0, &full_bar[stage]);
-                        }
-                    } else {
-                        const int mm = m0 + lane * 64;
-                        if (p.a_tap) tma_load_2d(a + lane * 8192, &mapA, mm % p.a_ctap, k0 + mm / p.a_ctap, &full_bar[stage]);
-                        else tma_load_2d(a + lane * 8192, &mapA, mm, k0, &full_bar[stage]);
+                    if (my_bytes) mbar_expect_tx(&my_full[stage], my_bytes);
+                    const int kt = kt0 + j;
+                    int k0 = kt * BF_BK;
+                    if (p.tap_inner) {
+                        // optional K walk of a convolution: (group of G channel blocks, tap, block in group) - re-reads hit L2, but the
+                        // plain tap-major walk measured faster (post proj_1: 160 vs 187 us) and is the default (TACO_BF16_TAPG)
+                        const int per = p.tap_inner * p.tap_group;
+                        const int gq = kt / per, rem = kt - gq * per, tj = rem / p.tap_group, cb = gq * p.tap_group + (rem - tj * p.tap_group);
+                        k0 = tj * p.a_ctap + cb * BF_BK;
                     }
-                } else if (lane >= 4 && lane < 8) {
-                    const int g = lane - 4;
-                    if (!p.b_mn_major) {
-                        if (g == 0) tma_load_2d(b, &mapB, k0, n0, &full_bar[stage]);
-                    } else if (g < (int)nboxB) {
-                        tma_load_2d(b + g * 8192, &mapB, n0 + g * 64, k0, &full_bar[stage]);
+                    uint8_t* a = sA + stage * BF_A_BYTES;
+                    uint8_t* b = sB + stage * p.b_stage_bytes;
+                    if (warp == 0) {
+                        if (!p.a_mn_major) {
+                            if (p.tap_table) { const int2 tc = __ldg(p.tap_table + kt); tma_load_2d(a, &mapA, tc.x, m0 + tc.y, &my_full[stage]); }
+                            else if (p.a_tap) tma_load_2d(a, &mapA, k0 % p.a_ctap, m0 + k0 / p.a_ctap, &my_full[stage]);
+                            else tma_load_2d(a, &mapA, k0, m0, &my_full[stage]);
+                        } else {
+                            if (p.a_tap) tma_load_2d(a, &mapA, m0 % p.a_ctap, k0 + m0 / p.a_ctap, &my_full[stage]);
+                            else tma_load_2d(a, &mapA, m0, k0, &my_full[stage]);
+                        }
+                    } else if (warp == 1) {
+                        if (p.a_mn_major) {
+                            const int mm = m0 + 64;
+                            if (p.a_tap) tma_load_2d(a + 8192, &mapA, mm % p.a_ctap, k0 + mm / p.a_ctap, &my_full[stage]);
+                            else tma_load_2d(a + 8192, &mapA, mm, k0, &my_full[stage]);
+                        }
+                        if (p.b_mn_major && !p.b_3d)
+                            for (uint32_t g = 1; g < nboxB; g += 2) tma_load_2d(b + g * 8192, &mapB, n0 + (int)g * 64, k0, &my_full[stage]);
+                    } else {
+                        if (!p.b_mn_major) tma_load_2d(b, &mapB, k0, n0, &my_full[stage]);
+                        else if (p.b_3d) tma_load_3d(b, &mapB, 0, k0, n0 >> 6, &my_full[stage]);
+                        else for (uint32_t g = 0; g < nboxB; g += 2) tma_load_2d(b + g * 8192, &mapB, n0 + (int)g * 64, k0, &my_full[stage]);
                     }
                 }
             }
+            __syncwarp();
         }
-        if (lane == 0) {
+        if (warp == 0 && lane == 0) {
             // self-cleaning work counter: the last CTA to leave resets the slot for a later launch
             __threadfence();
             const unsigned int done = atomicAdd(p.sched + 1, 1u);
             if (done == gridDim.x - 1) { p.sched[0] = 0u; p.sched[1] = 0u; __threadfence(); }
         }
-    } else if (warp == 1) {
+    } else if (warp == BF_PROD_WARPS) {
         // ===================== MMA issuer =====================
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=BF16 [7,10)/[10,13), majors [15],[16], N>>3 [17,23), M>>4 [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) | ((uint32_t)p.b_mn_major << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BF_BM >> 4) << 24);
         int it = 0;
+        const uint32_t pbytes[BF_PROD_WARPS] = {prod_bytes(p, 0), prod_bytes(p, 1), prod_bytes(p, 2)};
         for (int lt = 0;; lt++) {
             const int slot = lt & 1, use = lt >> 1;
             mbar_wait_bounded(&sched_full[slot], use & 1);
@@ -298,7 +330,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t tacc = tmem_base + (uint32_t)(slot * BF_BN_MAX);
             for (int j = 0; j < nkt; j++, it++) {
                 const int stage = it % STAGES, round = it / STAGES;
-                mbar_wait_bounded(&full_bar[stage], round & 1);
+#pragma unroll
+                for (int w = 0; w < BF_PROD_WARPS; w++)
+                    if (pbytes[w]) mbar_wait_bounded(&full_bar[w * BF_MAX_STAGES + stage], round & 1);
                 if (j == 0) BF_STAMP(2 + 4 * lt);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
@@ -320,11 +354,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 4..11) =====================
         // TMEM -> registers (row per lane) -> 32x32 transpose through shared memory -> coalesced 128-byte row segments.
         // Warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter take alternate 32-column chunks.
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t stg = smem_u32(stg_all + (warp - 2) * BF_STG_FLOATS);
+        const int q = warp & 3, half = (warp - BF_EPI_WARP0) >> 2;
+        const uint32_t stg = smem_u32(stg_all + (warp - BF_EPI_WARP0) * BF_STG_FLOATS);
         const uint32_t red_s = smem_u32(red);
         const int lr = lane >> 3, lc = (lane & 7) * 4;
         const uint32_t stg_lane = stg + (uint32_t)((lr * 36 + lc) * 4);
@@ -359,7 +393,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const bool rows_full = (m0 + q * 32 + 31 < p.M) && p.fast_ok;     // warp-uniform
             const bool with_bias = p.bias != nullptr && (!atomic || kt0 == 0);
             mbar_wait_bounded(&tmem_full[slot], use & 1);
-            if (warp == 2) BF_STAMP(4 + 4 * lt);
+            if (warp == BF_EPI_WARP0) BF_STAMP(4 + 4 * lt);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(slot * BF_BN_MAX) + ((uint32_t)(q * 32) << 16);
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
@@ -378,6 +412,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
                 if (fast) {
                     if (atomic) bf_epi_fast_atomic(p, stg_lane, crow, maskmask, gn, bz);
+                    else if (p.accumulate == 1) bf_epi_fast<ACT_NONE, false, true>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq);   // C += A.B (data gradients)
                     else if (p.colsum) {
                         if (p.act == ACT_RELU) bf_epi_fast<ACT_RELU, true>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq);
                         else if (p.act == ACT_NONE) bf_epi_fast<ACT_NONE, true>(p, stg_lane, crow, crow16, maskmask, gn, bz, cs, cq);
@@ -415,12 +450,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[slot]);
-            if (warp == 2) BF_STAMP(5 + 4 * lt);
+            if (warp == BF_EPI_WARP0) BF_STAMP(5 + 4 * lt);
             if (p.colsum) {
                 // one double atomic per column and statistic per CTA (the four lane quarters are summed here first: the
                 // statistics land on a few hundred addresses, so their atomics serialise in L2)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int et = threadIdx.x - 64;
+                const int et = threadIdx.x - 32 * BF_EPI_WARP0;
                 for (int idx = et; idx < 2 * BN; idx += 32 * BF_EPI_WARPS) {
                     const int which = idx >= BN ? 1 : 0, col = idx - which * BN;
                     if (n0 + col < p.N) {
@@ -435,7 +470,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == BF_PROD_WARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BF_BN_MAX));
     }
@@ -492,6 +527,28 @@ static int make_map16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
                  base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
     std::lock_guard<std::mutex> lk(g_maps_mu);
     if (g_maps.size() > 8192) g_maps.clear();
+    g_maps.emplace(key, *map);
+    return TACO_OK;
+}
+
+// 3-D view of a row-major [K, ld] bf16 matrix as {64 columns, K rows, column blocks of 64}: box {64, bk, nblk}
+static int make_map16_3d(CUtensorMap* map, const void* base, uint64_t K, uint64_t nblocks, uint64_t ld, uint32_t bk, uint32_t nblk) {
+    const MapKey key{base, K | (1ull << 62), nblocks, ld, bk, nblk};
+    {
+        std::lock_guard<std::mutex> lk(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *map = it->second; return TACO_OK; }
+    }
+    cuuint64_t dims[3] = {64, K, nblocks};
+    cuuint64_t strides[2] = {ld * 2, 128};
+    cuuint32_t box[3] = {64, bk, nblk};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode16(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACO_REQUIRE(r == CUDA_SUCCESS, TACO_ECUDA, "cuTensorMapEncodeTiled (bf16, 3-D) failed (%d): base=%p K=%llu blocks=%llu ld=%llu", (int)r,
+                 base, (unsigned long long)K, (unsigned long long)nblocks, (unsigned long long)ld);
+    std::lock_guard<std::mutex> lk(g_maps_mu);
     g_maps.emplace(key, *map);
     return TACO_OK;
 }
@@ -563,7 +620,11 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
         if (tap) TACO_TRY(make_map16(&mapA, A, (uint64_t)g.ctap, (uint64_t)g.K + ntaps - 1, (uint64_t)g.lda, 64, BF_BK));
         else TACO_TRY(make_map16(&mapA, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 64, BF_BK));
     }
-    if (!g.transB) TACO_TRY(make_map16(&mapB, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, BF_BK));            // MN-major
+    // MN-major B wider than two 64-column blocks: one 3-D box {64 n, 64 k, BN/64 blocks} per k-tile when the blocks stay inside
+    // the row pitch (N a multiple of 64, or the pitch padded to one)
+    const bool b3d = !g.transB && BN > 128 && (g.N % 64 == 0 || g.ldb >= (g.N + 63) / 64 * 64);
+    if (b3d) TACO_TRY(make_map16_3d(&mapB, B, (uint64_t)g.K, (uint64_t)cdiv(g.N, 64), (uint64_t)g.ldb, BF_BK, (uint32_t)cdiv(BN, 64)));
+    else if (!g.transB) TACO_TRY(make_map16(&mapB, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, BF_BK));            // MN-major
     else TACO_TRY(make_map16(&mapB, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, BF_BK, (uint32_t)BN));           // K-major
     p.C = g.C; p.C16 = static_cast<__nv_bfloat16*>(g.C16);
     p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.ldc16 = g.ldc16 > 0 ? g.ldc16 : g.ldc;
@@ -572,12 +633,12 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     p.stages = BF_RING_BYTES / (BF_A_BYTES + p.b_stage_bytes);
     if (p.stages > BF_MAX_STAGES) p.stages = BF_MAX_STAGES;
     { static const int cap = [] { const char* e = getenv("TACO_BF16_STAGES"); return e ? atoi(e) : 0; }(); if (cap > 0 && p.stages > cap) p.stages = cap; }
-    p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1;
+    p.a_mn_major = g.transA ? 1 : 0; p.b_mn_major = g.transB ? 0 : 1; p.b_3d = b3d ? 1 : 0;
     p.a_tap = tap ? 1 : 0; p.a_ctap = tap ? g.ctap : 1;
     p.tap_table = reinterpret_cast<const int2*>(g.tap_table);
     p.tap_inner = (tap && !g.transA && !g.tap_table && g.ctap % BF_BK == 0 && g.K % g.ctap == 0 && g.K / g.ctap > 1) ? g.K / g.ctap : 0;
     {
-        static const int want = [] { const char* e = getenv("TACO_BF16_TAPG"); return e ? atoi(e) : 4; }();
+        static const int want = [] { const char* e = getenv("TACO_BF16_TAPG"); return e ? atoi(e) : 0; }();
         const int blocks = g.ctap > 0 ? g.ctap / BF_BK : 1;
         p.tap_group = 1;
         for (int gsz = want; gsz >= 1; gsz--) if (blocks % gsz == 0) { p.tap_group = gsz; break; }
@@ -608,8 +669,8 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     p.vecC = g.C ? (g.remap_period > 0 ? (al(g.C, 16) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al(g.C, 16) && g.ldc % 4 == 0)) : 0;
     p.vecC16 = g.C16 ? (g.remap_period > 0 ? (al(g.C16, 8) && g.remap_outer % 4 == 0 && g.remap_inner % 4 == 0) : (al(g.C16, 8) && p.ldc16 % 4 == 0)) : 0;
     // lean epilogue: 128-bit stores on every output, 16-byte aligned bias, no read-modify-write, statistics only with relu / none
-    p.fast_ok = (!g.C || p.vecC) && (!g.C16 || p.vecC16) && (!g.bias || al(g.bias, 16)) && g.accumulate != 1 &&
-                (!g.colsum || g.act == ACT_RELU || g.act == ACT_NONE) ? 1 : 0;
+    p.fast_ok = (!g.C || p.vecC) && (!g.C16 || p.vecC16) && (!g.bias || al(g.bias, 16)) &&
+                (g.accumulate != 1 || (g.act == ACT_NONE && !g.colsum)) && (!g.colsum || g.act == ACT_RELU || g.act == ACT_NONE) ? 1 : 0;
     {
         std::lock_guard<std::mutex> lk(g_sched_mu);
         p.sched = g_sched_ring + 2 * (g_sched_next++ % BF_SCHED_SLOTS);

@@ -367,10 +367,10 @@ void Model::plan(const Shape& s) {
             add("dec/v_eff", {A}); add("dec/g_veff", {A});
         }
     }
-    // The linear-spectrogram tensors use a row pitch rounded up to 8 elements (1025 -> 1032) so TMA can address them and
+    // The linear-spectrogram tensors use a row pitch rounded up to 64 elements (1025 -> 1088) so TMA can address them (one 3-D box per weight tile) and
     // their bf16 mirrors (16-byte pitches); the pad columns stay zero.  "linear_outputs" is exposed as a strided [N,To,F] view.
     {
-        const int64_t Fp = (c.num_freq + 7) / 8 * 8;
+        const int64_t Fp = (c.num_freq + 63) / 64 * 64;
         add("linear_buf", {(int64_t)N * s.To, Fp});
         Region r = regions["linear_buf"];
         r.ndim = 3; r.dims[0] = N; r.dims[1] = s.To; r.dims[2] = c.num_freq;
@@ -390,7 +390,7 @@ void Model::plan(const Shape& s) {
         if (tr) { add("spk/d_pre", {N, 2 * (int64_t)c.enc_rnn_size + c.attention_state_size + Y}); add("spk/d_embed", {N, S}); }
     }
     if (c.speaker_mode == TACO_SPK_SIMPLE) {
-        const int64_t S = c.speaker_embedding_size, Fp = (c.num_freq + 7) / 8 * 8;
+        const int64_t S = c.speaker_embedding_size, Fp = (c.num_freq + 63) / 64 * 64;
         add("spk/embed", {N, S}); add("spk/lin_bias", {N, Fp});
         if (tr) {
             add("spk/d_embed", {N, S}); add("spk/s_lin", {N, Fp});
@@ -520,7 +520,11 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const int prec = c.precision, tr = m.shape.training;
     const bool simple = (c.speaker_mode == TACO_SPK_SIMPLE);
     if (m.use16())     // bf16 mirror of every trainable tensor (18.7 MB written per step; the GEMM B operands of this pass and the next backward pass)
-        TACO_TRY(launch_cast2d_bf16(m.W16("params16") ? m.W16("params16") : nullptr, m.params, 1, (int)m.n_trainable, m.n_trainable, m.n_trainable, s));
+    {
+        auto it = m.regions.find("params16");
+        TACO_REQUIRE(it != m.regions.end() && it->second.numel >= m.n_trainable, TACO_ESTATE, "bf16 mode: bind the parameters before sizing the workspace");
+        TACO_TRY(launch_cast2d_bf16(m.ws + it->second.offset, m.params, 1, (int)m.n_trainable, m.n_trainable, m.n_trainable, s));
+    }
     if (simple) {
         // 'simple' injection: one embedding row per utterance, concatenated at three sites (tacotron.py:44-49,82-86)
         TACO_REQUIRE(b->speaker_id != nullptr, TACO_EINVAL, "speaker_id is required when num_speakers > 1");
@@ -569,7 +573,7 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     prof_mark("fwd:linear", s);
     // ---- linear-spectrogram projection (tacotron.py:235) ----
     {
-        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 7) / 8 * 8;
+        const int Hp2 = 2 * c.post_rnn_size, F = c.num_freq, Fp = (F + 63) / 64 * 64;
         const int S = simple ? c.speaker_embedding_size : 0;
         TACO_TRY(launch_copy2d(m.W("linear/w_pad"), m.P("linear/kernel"), Hp2 + S, F, Fp, F, s));     // 16-byte row pitch for TMA
         if (m.use16()) TACO_TRY(launch_cast2d_bf16(m.W16("linear/w_pad"), m.P("linear/kernel"), Hp2 + S, F, Fp, F, s));
@@ -616,7 +620,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         lo = c.priority_lo; hi = c.priority_hi;
         w_all = (float)(0.5 / cnt_lin); w_band = (float)(0.5 / ((double)N * To * (hi - lo)));
     }
-    const int Fp = (F + 7) / 8 * 8;
+    const int Fp = (F + 63) / 64 * 64;
     TACO_TRY(launch_l1_loss(m.W("linear_buf"), (long long)To * Fp, Fp, b->linear_targets, b->loss_coeff,
                             m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear")));
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
