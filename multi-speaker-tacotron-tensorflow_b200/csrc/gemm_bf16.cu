@@ -565,23 +565,25 @@ bool gemm_bf16_eligible(const taco_gemm_desc& g) {
     return true;
 }
 
-static unsigned int* g_sched_ring = nullptr;     // BF_SCHED_SLOTS x {next unit, CTAs done}; self-cleaning (see the kernel)
+static unsigned int* g_sched_ring[16] = {};      // per device: BF_SCHED_SLOTS x {next unit, CTAs done}; self-cleaning (see the kernel)
 static unsigned int g_sched_next = 0;
+static int g_n_sm[16] = {};
 static std::mutex g_sched_mu;
 
 int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     TACO_TRY(get_encode16());
-    static int n_sm = 0;
+    int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev));
+    TACO_REQUIRE(dev >= 0 && dev < 16, TACO_ECUDA, "gemm: device ordinal %d out of range", dev);
     {
         std::lock_guard<std::mutex> lk(g_sched_mu);
-        if (n_sm == 0) {
-            int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev));
-            TACO_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (g_n_sm[dev] == 0) {
+            TACO_CHECK_CUDA(cudaDeviceGetAttribute(&g_n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
             TACO_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
-            TACO_CHECK_CUDA(cudaMalloc(&g_sched_ring, sizeof(unsigned int) * 2 * BF_SCHED_SLOTS));
-            TACO_CHECK_CUDA(cudaMemset(g_sched_ring, 0, sizeof(unsigned int) * 2 * BF_SCHED_SLOTS));
+            TACO_CHECK_CUDA(cudaMalloc(&g_sched_ring[dev], sizeof(unsigned int) * 2 * BF_SCHED_SLOTS));
+            TACO_CHECK_CUDA(cudaMemset(g_sched_ring[dev], 0, sizeof(unsigned int) * 2 * BF_SCHED_SLOTS));
         }
     }
+    const int n_sm = g_n_sm[dev];
     TACO_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, TACO_ESHAPE, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
     TACO_REQUIRE(!((g.split_k > 1 || g.accumulate == 2) && (g.act != 0 || g.colsum != nullptr || g.C16 != nullptr)), TACO_EINVAL,
                  "gemm: atomic accumulation cannot carry an activation, column statistics or a bf16 mirror");
@@ -673,7 +675,7 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
                 (g.accumulate != 1 || (g.act == ACT_NONE && !g.colsum)) && (!g.colsum || g.act == ACT_RELU || g.act == ACT_NONE) ? 1 : 0;
     {
         std::lock_guard<std::mutex> lk(g_sched_mu);
-        p.sched = g_sched_ring + 2 * (g_sched_next++ % BF_SCHED_SLOTS);
+        p.sched = g_sched_ring[dev] + 2 * (g_sched_next++ % BF_SCHED_SLOTS);
     }
     const int grid = p.units < n_sm ? p.units : n_sm;
     gemm_bf16_kernel<<<grid, BF_THREADS, BF_SMEM, s>>>(mapA, mapB, p);

@@ -344,10 +344,14 @@ bool gemm_tc_eligible(const taco_gemm_desc& g) {
 
 int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     TACO_TRY(get_encode());
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev));
+    TACO_REQUIRE(dev >= 0 && dev < 16, TACO_ECUDA, "gemm: device ordinal %d out of range", dev);
+    static bool configured[16] = {};       // function attributes and SM counts are per device
+    static int n_sm_dev[16] = {};
+    if (!configured[dev]) {
         TACO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-        configured = true;
+        TACO_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+        configured[dev] = true;
     }
     TACO_REQUIRE(!((g.split_k > 1 || g.accumulate == 2) && (g.act != 0 || g.colsum != nullptr)), TACO_EINVAL,
                  "gemm: atomic accumulation cannot carry an activation or column statistics");
@@ -389,8 +393,7 @@ int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s) {
     p.colsum = g.colsum; p.colsumsq = g.colsumsq;
     const int ktiles = cdiv(g.K, TC_BK);
     const int tiles = cdiv(g.M, TC_BM) * cdiv(g.N, TC_BN);
-    static int n_sm = 0;
-    if (n_sm == 0) { int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev)); TACO_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int n_sm = n_sm_dev[dev];
     // A caller that allows K splitting (split_k > 1: C is accumulated atomically) gets the split that balances whole waves
     // of CTAs (two resident per SM): waves x (k-blocks per CTA + a fixed per-CTA cost in k-block units).
     p.split_k = 1;

@@ -58,43 +58,69 @@ int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s) { ProfScope p(2,
 // of taco_backward.  Priorities make the block scheduler hand freed SMs to the chain first, so leaves only fill idle SMs.
 // TACO_OVERLAP=0 (or an active taco_profile window, whose per-launch times must not overlap) runs everything in order.
 static constexpr int kAuxStreams = 4;
+static constexpr int kMaxDevices = 16;
 struct StreamSet {
     cudaStream_t aux[kAuxStreams]; cudaEvent_t fork, join[kAuxStreams];
 };
-static StreamSet g_set[2];                 // 0: chain (high priority), 1: leaves (low priority)
-static cudaStream_t g_crit = nullptr, g_side = nullptr;
-static cudaEvent_t g_ev_in, g_ev_out, g_ev_fork, g_ev_side, g_ev_prep, g_ev_leaf, g_ev_img[2];
-static bool g_sched_ready = false;
+// Streams and events belong to a device: one scheduler state per CUDA ordinal, selected through the device that the C-ABI
+// entry made current (DeviceGuard below), so engines on different devices in one process never share them.
+struct DevSched {
+    StreamSet set[2];                   // 0: chain (high priority), 1: leaves (low priority)
+    cudaStream_t crit = nullptr, side = nullptr;
+    cudaEvent_t ev_in, ev_out, ev_fork, ev_side, ev_prep, ev_leaf, ev_img[2];
+    bool ready = false;
+    WaveCtx wave; bool wave_ready = false;
+};
+static DevSched g_dev[kMaxDevices];
+static DevSched& ds() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return g_dev[d];
+}
+// RAII: make the model's device current for the duration of a C-ABI call (the caller's current device is restored)
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (dev >= 0 && dev != prev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { int cur = -1; if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); }
+};
+#define TACO_ON_DEVICE(dev)                                                                     \
+    DeviceGuard _guard(dev);                                                                    \
+    TACO_REQUIRE(_guard.ok && (dev) < kMaxDevices, TACO_ECUDA, "cannot make CUDA device %d current", (int)(dev))
+
 static int g_overlap = -1;
 static bool g_prof_keep_overlap = false;     // TACO_PROF_OVERLAP=1: timeline of the real two-stream schedule (tools/timeline.py)
 static int sched_init() {
-    if (g_sched_ready) return TACO_OK;
+    DevSched& D = ds();
+    if (D.ready) return TACO_OK;
     int lo = 0, hi = 0;
     TACO_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically greatest)
     for (int k = 0; k < 2; k++) {
         for (int i = 0; i < kAuxStreams; i++) {
-            TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_set[k].aux[i], cudaStreamNonBlocking, k == 0 ? hi : lo));
-            TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_set[k].join[i], cudaEventDisableTiming));
+            TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.set[k].aux[i], cudaStreamNonBlocking, k == 0 ? hi : lo));
+            TACO_CHECK_CUDA(cudaEventCreateWithFlags(&D.set[k].join[i], cudaEventDisableTiming));
         }
-        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_set[k].fork, cudaEventDisableTiming));
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&D.set[k].fork, cudaEventDisableTiming));
     }
-    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_crit, cudaStreamNonBlocking, hi));
-    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, lo));
-    for (cudaEvent_t* e : {&g_ev_in, &g_ev_out, &g_ev_fork, &g_ev_side, &g_ev_prep, &g_ev_leaf, &g_ev_img[0], &g_ev_img[1]})
+    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.crit, cudaStreamNonBlocking, hi));
+    TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.side, cudaStreamNonBlocking, lo));
+    for (cudaEvent_t* e : {&D.ev_in, &D.ev_out, &D.ev_fork, &D.ev_side, &D.ev_prep, &D.ev_leaf, &D.ev_img[0], &D.ev_img[1]})
         TACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    const char* env = getenv("TACO_OVERLAP");
-    g_overlap = (env && env[0] == '0') ? 0 : 1;
-    const char* env2 = getenv("TACO_PROF_OVERLAP");
-    g_prof_keep_overlap = (env2 && env2[0] == '1');
-    g_sched_ready = true;
+    if (g_overlap < 0) {
+        const char* env = getenv("TACO_OVERLAP");
+        g_overlap = (env && env[0] == '0') ? 0 : 1;
+        const char* env2 = getenv("TACO_PROF_OVERLAP");
+        g_prof_keep_overlap = (env2 && env2[0] == '1');
+    }
+    D.ready = true;
     return TACO_OK;
 }
-static bool overlap_on() { return g_sched_ready && g_overlap == 1 && (!g_prof_on || g_prof_keep_overlap); }
+static bool overlap_on() { return ds().ready && g_overlap == 1 && (!g_prof_on || g_prof_keep_overlap); }
 
 // Decoder wavefront: two more high-priority streams (one per residual GRU layer) and per-chunk events, so that the GRU
 // layers of time chunk c run while the attention recurrence is already on chunk c+1 (and the reverse in BPTT).
-static WaveCtx g_wave;
-static bool g_wave_ready = false;
 static int g_wave_chunks = -1;
 int wave_get(WaveCtx** out) {
     *out = nullptr;
@@ -105,37 +131,38 @@ int wave_get(WaveCtx** out) {
         if (g_wave_chunks > WaveCtx::kMaxChunks) g_wave_chunks = WaveCtx::kMaxChunks;
     }
     if (g_wave_chunks <= 1) return TACO_OK;
-    if (!g_wave_ready) {
+    DevSched& D = ds();
+    if (!D.wave_ready) {
         int lo = 0, hi = 0;
         TACO_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        for (int i = 0; i < 2; i++) TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&g_wave.w[i], cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 2; i++) TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.wave.w[i], cudaStreamNonBlocking, hi));
         for (int k = 0; k < 3; k++)
-            for (int c = 0; c < WaveCtx::kMaxChunks; c++) TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_wave.ev[k][c], cudaEventDisableTiming));
-        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_wave.start, cudaEventDisableTiming));
-        g_wave_ready = true;
+            for (int c = 0; c < WaveCtx::kMaxChunks; c++) TACO_CHECK_CUDA(cudaEventCreateWithFlags(&D.wave.ev[k][c], cudaEventDisableTiming));
+        TACO_CHECK_CUDA(cudaEventCreateWithFlags(&D.wave.start, cudaEventDisableTiming));
+        D.wave_ready = true;
     }
-    g_wave.chunks = g_wave_chunks;
-    *out = &g_wave;
+    D.wave.chunks = g_wave_chunks;
+    *out = &D.wave;
     return TACO_OK;
 }
 // Leaf stream for work whose operands were produced on `producer` (any stream): the side stream waits for what is
 // enqueued there so far.  Falls back to `producer` itself when the two-stream schedule is off.
 cudaStream_t fork_side_after(cudaStream_t producer) {
     if (!overlap_on()) return producer;
-    if (cudaEventRecord(g_ev_leaf, producer) != cudaSuccess || cudaStreamWaitEvent(g_side, g_ev_leaf, 0) != cudaSuccess) return producer;
-    return g_side;
+    if (cudaEventRecord(ds().ev_leaf, producer) != cudaSuccess || cudaStreamWaitEvent(ds().side, ds().ev_leaf, 0) != cudaSuccess) return producer;
+    return ds().side;
 }
 // Hand-over of the attention operand images between streams: which = 0 weight images (built beside the encoder), 1 the
 // backward key / memory image (built beside the forward decoder).  image_ready records, image_wait orders `s` behind it.
-int image_ready(int which, cudaStream_t producer) { TACO_CHECK_CUDA(cudaEventRecord(g_ev_img[which], producer)); return TACO_OK; }
-int image_wait(int which, cudaStream_t s) { TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_ev_img[which], 0)); return TACO_OK; }
+int image_ready(int which, cudaStream_t producer) { TACO_CHECK_CUDA(cudaEventRecord(ds().ev_img[which], producer)); return TACO_OK; }
+int image_wait(int which, cudaStream_t s) { TACO_CHECK_CUDA(cudaStreamWaitEvent(s, ds().ev_img[which], 0)); return TACO_OK; }
 
 
 // Stream for leaf work whose operands were produced by what is already enqueued on `main`.
 cudaStream_t fork_side(cudaStream_t main) {
-    if (!overlap_on() || main != g_crit) return main;
-    if (cudaEventRecord(g_ev_fork, main) != cudaSuccess || cudaStreamWaitEvent(g_side, g_ev_fork, 0) != cudaSuccess) return main;
-    return g_side;
+    if (!overlap_on() || main != ds().crit) return main;
+    if (cudaEventRecord(ds().ev_fork, main) != cudaSuccess || cudaStreamWaitEvent(ds().side, ds().ev_fork, 0) != cudaSuccess) return main;
+    return ds().side;
 }
 
 // Route each problem: tcgen05/TMA kernel in TF32 mode when its operands satisfy TMA's alignment rules, otherwise
@@ -164,7 +191,7 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
     }
     const bool fan_out = tc.size() >= 2;
     TACO_TRY(sched_init());
-    StreamSet& set = g_set[(s == g_side) ? 1 : 0];
+    StreamSet& set = ds().set[(s == ds().side) ? 1 : 0];
     if (fan_out) {
         TACO_CHECK_CUDA(cudaEventRecord(set.fork, s));
         for (int i = 0; i < kAuxStreams; i++) TACO_CHECK_CUDA(cudaStreamWaitEvent(set.aux[i], set.fork, 0));
@@ -606,7 +633,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     double* sc = m.Wd("scalars");
     TACO_CHECK_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, s));
     if (m.prep_done) {
-        TACO_CHECK_CUDA(cudaStreamWaitEvent(s, g_ev_prep, 0));   // packed operands were produced beside the forward pass
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(s, ds().ev_prep, 0));   // packed operands were produced beside the forward pass
     } else {
         TACO_TRY(backward_prep(m, s));
     }
@@ -734,6 +761,7 @@ int64_t taco_launch_count(void) { return g_launch_count; }
 int taco_create(taco_model* out, const taco_config* cfg) {
     TACO_REQUIRE(out && cfg, TACO_EINVAL, "taco_create: null argument");
     TACO_REQUIRE(cfg->abi_version == TACO_ABI_VERSION, TACO_EINVAL, "taco_create: ABI version %d != %d", cfg->abi_version, TACO_ABI_VERSION);
+    TACO_REQUIRE(cfg->device >= 0 && cfg->device < kMaxDevices, TACO_EINVAL, "taco_create: device ordinal %d out of range", cfg->device);
     TACO_REQUIRE(cfg->precision >= TACO_PREC_FP32 && cfg->precision <= TACO_PREC_BF16, TACO_EINVAL, "taco_create: unknown precision %d", cfg->precision);
     TACO_REQUIRE(cfg->attention_type >= 0 && cfg->attention_type <= 2, TACO_EINVAL, " [!] Unkown attention type: %d", cfg->attention_type);
     TACO_REQUIRE(cfg->speaker_mode >= 0 && cfg->speaker_mode <= 3, TACO_EINVAL, " [!] Unkown multi-speaker model type: %d", cfg->speaker_mode);
@@ -755,6 +783,7 @@ int taco_destroy(taco_model h) {
 int taco_bind_params(taco_model h, const taco_param_entry* table, int32_t n_entries, float* params, float* grads,
                      float* adam_m, float* adam_v, float* bn_state, int64_t n_trainable, int64_t n_state) {
     TACO_REQUIRE(h && table && params && bn_state, TACO_EINVAL, "taco_bind_params: null argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     m.table.clear();
     for (int i = 0; i < n_entries; i++) {
@@ -836,6 +865,7 @@ int taco_ws_region(taco_model h, const char* name, size_t* offset_bytes, int64_t
 
 int taco_forward(taco_model h, const taco_batch* b, void* stream) {
     TACO_REQUIRE(h && b, TACO_EINVAL, "taco_forward: null argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     TACO_REQUIRE(m.params != nullptr, TACO_ESTATE, "taco_forward: parameters not bound");
     TACO_REQUIRE(b->inputs && b->input_lengths, TACO_EINVAL, "taco_forward: inputs / input_lengths are required");
@@ -848,12 +878,12 @@ int taco_forward(taco_model h, const taco_batch* b, void* stream) {
     m.img_w_state = 0; m.img_bkm_state = 0;
     if (s.training && overlap_on()) {
         // parameter-only operands of the backward pass are packed on the leaf stream while the forward pass runs
-        TACO_CHECK_CUDA(cudaEventRecord(g_ev_in, user));
-        TACO_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_in, 0));
+        TACO_CHECK_CUDA(cudaEventRecord(ds().ev_in, user));
+        TACO_CHECK_CUDA(cudaStreamWaitEvent(ds().side, ds().ev_in, 0));
         m.img_w_state = 0;
-        TACO_TRY(decoder_pack_weight_images(m, g_side));          // sets img_w_state = 2 (ready behind g_ev_img[0]) when it applies
-        TACO_TRY(backward_prep(m, g_side));
-        TACO_CHECK_CUDA(cudaEventRecord(g_ev_prep, g_side));
+        TACO_TRY(decoder_pack_weight_images(m, ds().side));          // sets img_w_state = 2 (ready behind ds().ev_img[0]) when it applies
+        TACO_TRY(backward_prep(m, ds().side));
+        TACO_CHECK_CUDA(cudaEventRecord(ds().ev_prep, ds().side));
         m.prep_done = true;
     }
     return model_forward(m, b, user);
@@ -861,6 +891,7 @@ int taco_forward(taco_model h, const taco_batch* b, void* stream) {
 
 int taco_backward(taco_model h, const taco_batch* b, void* stream) {
     TACO_REQUIRE(h && b, TACO_EINVAL, "taco_backward: null argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     TACO_REQUIRE(m.grads != nullptr, TACO_ESTATE, "taco_backward: gradient buffer not bound");
     Shape s;
@@ -871,21 +902,22 @@ int taco_backward(taco_model h, const taco_batch* b, void* stream) {
     if (!overlap_on()) return model_backward(m, b, user);
     // chain on the high-priority stream, leaves on the low-priority one (see "stream scheduler"); both are ordered
     // after everything already enqueued on the caller's stream and joined back into it before returning
-    TACO_CHECK_CUDA(cudaEventRecord(g_ev_in, user));
-    TACO_CHECK_CUDA(cudaStreamWaitEvent(g_crit, g_ev_in, 0));
-    TACO_CHECK_CUDA(cudaStreamWaitEvent(g_side, g_ev_in, 0));
-    const int rc = model_backward(m, b, g_crit);
-    prof_mark("side:end", g_side);
-    TACO_CHECK_CUDA(cudaEventRecord(g_ev_side, g_side));
-    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, g_ev_side, 0));
-    TACO_CHECK_CUDA(cudaEventRecord(g_ev_out, g_crit));
-    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, g_ev_out, 0));
+    TACO_CHECK_CUDA(cudaEventRecord(ds().ev_in, user));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(ds().crit, ds().ev_in, 0));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(ds().side, ds().ev_in, 0));
+    const int rc = model_backward(m, b, ds().crit);
+    prof_mark("side:end", ds().side);
+    TACO_CHECK_CUDA(cudaEventRecord(ds().ev_side, ds().side));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, ds().ev_side, 0));
+    TACO_CHECK_CUDA(cudaEventRecord(ds().ev_out, ds().crit));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(user, ds().ev_out, 0));
     return rc;
 }
 
 int taco_optimizer_step(taco_model h, int64_t global_step, int64_t adam_step, int32_t is_randomly_initialized, float initial_learning_rate,
                         int32_t decay_mode, float beta1, float beta2, float grad_scale, void* stream) {
     TACO_REQUIRE(h, TACO_EINVAL, "taco_optimizer_step: null model");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     TACO_REQUIRE(m.grads && m.adam_m && m.adam_v, TACO_ESTATE, "taco_optimizer_step: optimizer buffers not bound");
     TACO_REQUIRE(m.planned && m.shape.training, TACO_ESTATE, "taco_optimizer_step: no training step in flight");
@@ -935,6 +967,7 @@ static void finish_scalars(const Model& m, const double sc[8], const float scf[8
 
 int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
     TACO_REQUIRE(h && out, TACO_EINVAL, "taco_read_scalars: null argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_read_scalars: nothing has run");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -948,6 +981,7 @@ int taco_read_scalars(taco_model h, taco_step_scalars* out, void* stream) {
 
 int taco_copy_scalars_async(taco_model h, void* pinned_raw, void* stream) {
     TACO_REQUIRE(h && pinned_raw, TACO_EINVAL, "taco_copy_scalars_async: null argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
     Model& m = h->m;
     TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "taco_copy_scalars_async: nothing has run");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1000,7 +1034,7 @@ int taco_debug_profile_spans(char* buf, int64_t cap) {
         if (cudaEventElapsedTime(&t0, g_prof_spans.front().a, sp.a) != cudaSuccess) t0 = -1.f;
         char line[192];
         snprintf(line, sizeof line, "%d %.4f %d %d %d %d %.4f %d %s\n", sp.cls, ms, sp.tag[0], sp.tag[1], sp.tag[2], sp.tag[3], t0,
-                 sp.stream == g_side ? 1 : (g_wave_ready && sp.stream == g_wave.w[0]) ? 2 : (g_wave_ready && sp.stream == g_wave.w[1]) ? 3 : 0,
+                 sp.stream == ds().side ? 1 : (ds().wave_ready && sp.stream == ds().wave.w[0]) ? 2 : (ds().wave_ready && sp.stream == ds().wave.w[1]) ? 3 : 0,
                  sp.name[0] ? sp.name : "-");
         out += line;
     }

@@ -76,6 +76,24 @@ def wav_bytes(wav: np.ndarray, sample_rate: int) -> bytes:
     return buf.getvalue()
 
 
+def manual_alignments_from(alignments: np.ndarray, mode: int) -> np.ndarray:
+    """The second-pass alignments of ``manual_attention_mode`` (reference: synthesizer.py:171-196), [N, T_dec, T_in].
+
+    ``alignments`` is the first pass's [N, T_in, T_dec] history.  The reference takes ``alignments[idx].argmax(1)`` - for every
+    INPUT position the decoder step that attended it most - and writes a one at (that step, position):
+      mode 1 ("argmax one hot"): into zeros;  mode 3 ("prunning"): into the transposed soft alignments themselves.
+    Mode 2 ("sharpening") calls ``np.pow``, which does not exist, and overwrites its own accumulator; it cannot run there."""
+    if mode not in (1, 3):
+        raise NotImplementedError("manual_attention_mode=2 calls np.pow in the reference (synthesizer.py:188), which does not exist")
+    alignments = np.asarray(alignments, np.float32)
+    alignments_T = np.transpose(alignments, [0, 2, 1])
+    new = np.zeros_like(alignments_T) if mode == 1 else np.array(alignments_T, copy=True)
+    for idx in range(len(alignments)):
+        argmax = alignments[idx].argmax(1)                       # [T_in]: decoder step per input position
+        new[idx][(argmax, np.arange(len(argmax)))] = 1
+    return np.ascontiguousarray(new)
+
+
 class Synthesizer:
     def __init__(self, hparams=None, precision: str = "tf32", device: int = 0,
                  text_to_sequence: Optional[Callable[[str], Sequence[int]]] = None):
@@ -173,13 +191,7 @@ class Synthesizer:
         self._librosa_trim = bool(librosa_trim)
         results = self._save(spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, manual is not None)
         if manual_attention_mode > 0:
-            if manual_attention_mode not in (1, 3):
-                raise NotImplementedError("manual_attention_mode=2 calls np.pow in the reference (synthesizer.py:188), which does not exist")
-            # argmax one-hot re-run (synthesizer.py:171-178,191-196): [N, T_dec, T_in] indexed [:, time, :]
-            new = np.zeros((n, alignments.shape[2], alignments.shape[1]), np.float32)
-            for i in range(n):
-                am = alignments[i].argmax(0)                             # attended input position per decoder step
-                new[i, np.arange(len(am)), am] = 1
+            new = manual_alignments_from(alignments, manual_attention_mode)
             spectrograms, alignments = self._run(seq, input_lengths, speaker_ids, new)
             results = self._save(spectrograms, alignments, paths, sequences, base_path, end_of_sentence, attention_trim, True)
         return results

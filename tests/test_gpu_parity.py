@@ -2,11 +2,22 @@
 path with the CPU oracle on identical seeded inputs, with the committed golden fixtures, or through size-independent
 properties at the full BASELINE size.
 
-Stated tolerances (values are O(1): normalised spectrogram range [0,1]):
+Stated tolerances (values are O(1): normalised spectrogram range [0,1]).  The reduced-precision bounds are set to <= 2x the
+largest error MEASURED on the B200 over the cases below (tests/measure_precision_errors.py -> profiles/r2_precision_errors.txt):
   fp32 mode : outputs max-abs <= 1e-4, loss 1e-5, per-tensor gradient rel-L2 <= 1e-2 (argmax/ReLU routing flips) with the
               whole-gradient cosine >= 0.99999, Adam update 1e-6
-  tf32 mode : (TF32 tensor-core GEMMs, bf16 recurrent weights, fast tanh/sigmoid) outputs max-abs <= 3e-2, loss rel 1e-3,
-              whole-gradient cosine >= 0.995, grad-norm rel 2e-2
+  tf32 mode : (TF32 tensor-core GEMMs, bf16 recurrent weights, fast tanh/sigmoid)   measured: max-abs 6.8e-3, rel-L2 5.9e-3,
+              1-cos 2.8e-4, loss 1.6e-4, |g| 3.3e-3, free-running 1.7e-3
+              bounds: outputs max-abs <= 1.3e-2, rel-L2 <= 1.2e-2, loss rel 4e-4, gradient cosine >= 0.9994, |g| rel 7e-3,
+              free-running decoder outputs <= 5e-3
+  bf16 mode : (as tf32, plus bf16 operands - activations, gradients, weights - in every large contraction; the benchmarked
+              precision, BASELINE.json configs[1])                                  measured: max-abs 9.9e-3, rel-L2 8.2e-3,
+              1-cos 1.6e-3, loss 1.2e-4, |g| 4.5e-3, free-running 2.6e-3
+              bounds: outputs max-abs <= 2e-2, rel-L2 <= 1.6e-2, loss rel 4e-4, gradient cosine >= 0.9967, |g| rel 9e-3,
+              free-running decoder outputs <= 8e-3
+  attended position (alignment argmax over the input axis per decoder step) agrees with the oracle on 100 % of the steps at the
+  small sizes and >= 97 % at the full BASELINE sizes (random-initialised weights give nearly flat alignments there: measured
+  97.9 % .. 99.7 %).
 """
 import ctypes as C
 import os
@@ -23,7 +34,29 @@ pytestmark = pytest.mark.gpu
 from oracle import tacotron_oracle as O  # noqa: E402
 from oracle import griffin_lim_oracle as G  # noqa: E402
 
-TOL = {"fp32": dict(out=1e-4, loss=1e-5, cos=0.99999, gn=1e-4), "tf32": dict(out=3e-2, loss=1e-3, cos=0.995, gn=2e-2)}
+TOL = {"fp32": dict(out=1e-4, rel=5e-5, loss=1e-5, cos=0.99999, gn=1e-4, free=2e-4, grad_rel=2e-3),
+       "tf32": dict(out=1.3e-2, rel=1.2e-2, loss=4e-4, cos=0.9994, gn=7e-3, free=5e-3, grad_rel=1e-1),
+       "bf16": dict(out=2e-2, rel=1.6e-2, loss=4e-4, cos=0.9967, gn=9e-3, free=8e-3, grad_rel=3e-1)}
+FAST = ["tf32", "bf16"]          # the two tensor-core precision modes
+ALL_PREC = ["fp32"] + FAST
+
+
+def _check_outputs(out, ref, tol, keys=("mel_outputs", "linear_outputs", "alignments"), bound="out", argmax_min=None):
+    """max-abs and rel-L2 of the three model outputs against a reference dict (numpy arrays or tensors)."""
+    errs = {}
+    for k in keys:
+        a = out[k].detach().cpu().double() if torch.is_tensor(out[k]) else torch.from_numpy(np.asarray(out[k])).double()
+        r = ref[k].detach().cpu().double() if torch.is_tensor(ref[k]) else torch.from_numpy(np.asarray(ref[k])).double()
+        errs[k] = (float((a - r).abs().max()), float((a - r).norm() / max(float(r.norm()), 1e-30)))
+        assert errs[k][0] <= tol[bound], (k, "max-abs", errs[k][0])
+        assert errs[k][1] <= tol["rel"], (k, "rel-L2", errs[k][1])
+    if argmax_min is not None:
+        a = out["alignments"].detach().cpu() if torch.is_tensor(out["alignments"]) else torch.from_numpy(np.asarray(out["alignments"]))
+        r = ref["alignments"].detach().cpu() if torch.is_tensor(ref["alignments"]) else torch.from_numpy(np.asarray(ref["alignments"]))
+        agree = float((a.argmax(1) == r.argmax(1)).float().mean())
+        assert agree >= argmax_min, ("alignment argmax agreement", agree)
+        errs["argmax_agree"] = agree
+    return errs
 
 
 def _batch(N, Ti, To, lengths, seed=1234):
@@ -59,7 +92,7 @@ def golden_setup(tb, hp5):
     return mg.golden_params(hp5), mg.golden_batch()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ALL_PREC)
 def test_train_step_matches_golden_fixture(tb, hp5, golden_setup, prec):
     named, b = golden_setup
     gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_train_small.npz"))
@@ -68,16 +101,14 @@ def test_train_step_matches_golden_fixture(tb, hp5, golden_setup, prec):
     out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
     eng.backward()
     sc = eng.scalars()
-    assert np.abs(out["mel_outputs"].cpu().numpy() - gold["mel_outputs"]).max() <= tol["out"]
-    assert np.abs(out["linear_outputs"].cpu().numpy() - gold["linear_outputs"]).max() <= tol["out"]
-    assert np.abs(out["alignments"].cpu().numpy() - gold["alignments"]).max() <= tol["out"]
+    _check_outputs(out, gold, tol, argmax_min=1.0)
     assert abs(sc["loss"] - gold["scalars"][0]) <= tol["loss"] * max(1, gold["scalars"][0])
     assert abs(sc["mel_loss"] - gold["scalars"][1]) <= tol["loss"] and abs(sc["linear_loss"] - gold["scalars"][2]) <= tol["loss"]
     g = eng.named_gradients()
     for key, name in (("grad_attention_v", "attention/v"), ("grad_mel_proj_bias", "mel_proj/bias"), ("grad_embedding", "embedding")):
         ref = gold[key]
         rel = np.linalg.norm(g[name].cpu().numpy() - ref) / np.linalg.norm(ref)
-        assert rel <= (2e-3 if prec == "fp32" else 1e-1), (name, rel)
+        assert rel <= tol["grad_rel"], (name, rel)
     eng.optimizer_step(True)
     sc = eng.scalars()
     assert abs(sc["grad_norm"] - gold["scalars"][4]) <= tol["gn"] * gold["scalars"][4]
@@ -94,7 +125,7 @@ def _ref_cases():
     return sorted(mr.CASES)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ALL_PREC)
 @pytest.mark.parametrize("name", _ref_cases())
 def test_cuda_path_matches_reference_run_fixtures(tb, name, prec):
     """tests/golden/ref_*.npz were produced by the reference's own model code (tools/make_reference_golden.py: unmodified
@@ -113,19 +144,14 @@ def test_cuda_path_matches_reference_run_fixtures(tb, name, prec):
     if not mode.startswith("train"):
         ma = mr.manual_alignments(b["inputs"].shape[0], hp.max_iters, b["inputs"].shape[1]) if mode == "infer_manual" else None
         out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=hp.max_iters, manual_alignments=ma)
-        for k in ("mel_outputs", "linear_outputs", "alignments"):
-            err = np.abs(out[k].cpu().numpy() - g[k]).max()
-            assert err <= (2e-4 if prec == "fp32" else 6e-2), (k, err)      # free-running: errors feed back through the decoder
+        _check_outputs(out, g, tol, bound="free", argmax_min=1.0)         # free-running: errors feed back through the decoder
         eng.close()
         return
     if mode == "train_x2":                       # the fixture describes the second of two consecutive steps
         eng.train_step(b)
     out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"],
                       rnn_decoder_test_mode=(mode == "train_test_mode"))
-    lim = tol["out"] if mode != "train_test_mode" else (2e-4 if prec == "fp32" else 6e-2)
-    for k in ("mel_outputs", "linear_outputs", "alignments"):
-        err = np.abs(out[k].cpu().numpy() - g[k]).max()
-        assert err <= lim, (k, err)
+    _check_outputs(out, g, tol, bound="out" if mode != "train_test_mode" else "free")
     if mode == "train_test_mode":
         eng.close()
         return
@@ -146,7 +172,7 @@ def test_cuda_path_matches_reference_run_fixtures(tb, name, prec):
             dn = np.linalg.norm(ref)
             if dn > 1e-7:
                 rel = np.linalg.norm(got[key[5:]].cpu().numpy() - ref) / dn
-                assert rel <= (2e-3 if prec == "fp32" else 1e-1), (key, rel)
+                assert rel <= tol["grad_rel"], (key, rel)
     eng.optimizer_step(True)
     sc = eng.scalars()
     assert abs(sc["grad_norm"] - want[4]) <= tol["gn"] * want[4]
@@ -161,7 +187,9 @@ def test_cuda_path_matches_reference_run_fixtures(tb, name, prec):
 
 
 @pytest.mark.parametrize("prec,shape", [("fp32", (3, 13, 20, [13, 9, 5])), ("fp32", (9, 17, 10, [17, 1, 2, 17, 8, 9, 16, 3, 5])),
-                                        ("fp32", (1, 8, 5, [8])), ("tf32", (3, 13, 20, [13, 9, 5])), ("fp32", (2, 50, 200, [50, 50]))])
+                                        ("fp32", (1, 8, 5, [8])), ("tf32", (3, 13, 20, [13, 9, 5])), ("bf16", (3, 13, 20, [13, 9, 5])),
+                                        ("bf16", (9, 17, 10, [17, 1, 2, 17, 8, 9, 16, 3, 5])), ("bf16", (1, 8, 5, [8])),
+                                        ("fp32", (2, 50, 200, [50, 50])), ("tf32", (2, 50, 200, [50, 50])), ("bf16", (2, 50, 200, [50, 50]))])
 def test_forward_backward_vs_oracle(tb, hp5, prec, shape):
     """Ragged lengths, batch sizes that do not fill a row group, T_in not a multiple of the cluster size, one decoder step."""
     import make_golden as mg
@@ -172,9 +200,7 @@ def test_forward_backward_vs_oracle(tb, hp5, prec, shape):
     tol = TOL[prec]
     eng = tb.Engine(hp5, 1, precision=prec, named_params=named)
     out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
-    for k in ("mel_outputs", "linear_outputs", "alignments"):
-        err = (out[k].cpu() - ref_out[k].detach()).abs().max().item()
-        assert err <= tol["out"], (k, err)
+    _check_outputs(out, ref_out, tol, argmax_min=1.0)
     mem = eng.region("enc_cbhg/rnn_out").view(N, Ti, -1).cpu()
     for n, L in enumerate(lengths):
         assert mem[n, L:].abs().max().item() == 0 if L < Ti else True      # padded encoder steps emit exact zeros (modules.py:92)
@@ -249,53 +275,59 @@ def test_loss_is_linear_in_loss_coeff_full_size(tb, hp5):
     eng.close()
 
 
-def test_baseline_config_c3_multispeaker_train_full_size_vs_oracle(tb):
-    """BASELINE.json configs[2] per GPU: deepvoice, 3 speakers, batch 32, text 128, 800 mel frames, r=5 — one whole training
-    forward/backward in the benchmarked precision (tf32 mode) against the CPU oracle at the SAME size (the oracle takes a few
-    seconds per step on the host cores).  160 teacher-forced decoder steps and an 800-step post-net GRU with bf16 recurrent
-    weights: outputs <= 5e-2 max-abs (normalised spectrogram units), loss 2e-3 relative, whole-gradient cosine >= 0.99."""
-    hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice", batch_size=32)
-    S, N, Ti, To = 3, 32, 128, 800
+@pytest.mark.parametrize("prec", FAST)
+@pytest.mark.parametrize("config", ["C2", "C3"])
+def test_baseline_configs_c2_c3_train_full_size_vs_oracle(tb, config, prec):
+    """BASELINE.json configs[1] (C2: single speaker) and configs[2] per GPU (C3: deepvoice, 3 speakers): batch 32, text 128,
+    800 mel frames, r=5 - one whole training forward/backward in both tensor-core precisions (bf16 is the benchmarked one)
+    against the CPU oracle at the SAME size (the oracle takes a few seconds per step on the host cores).  160 teacher-forced
+    decoder steps and an 800-step post-net GRU.  Bounds: the per-mode table at the top of this file."""
+    multi = config == "C3"
+    hp = tb.hparams.override(reduction_factor=5, batch_size=32, **(dict(model_type="deepvoice") if multi else {}))
+    S, N, Ti, To = (3 if multi else 1), 32, 128, 800
     named = tb.params.init_params(hp, S, seed=41, randomize_bn_state=True)
     g = torch.Generator().manual_seed(6)
     lengths = torch.randint(96, Ti + 1, (N,), generator=g).tolist(); lengths[0] = Ti
     b = _batch(N, Ti, To, lengths, seed=21)
-    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32)
+    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32) if multi else None
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    ref, ref_g, names = _oracle_grads(named, hp, b, S, spk, "deepvoice")
+    ref, ref_g, names = _oracle_grads(named, hp, b, S, spk, "deepvoice" if multi else "none")
     ls = O.losses(ref, b["mel_targets"], b["linear_targets"], b["loss_coeff"], hp)
-    eng = tb.Engine(hp, S, precision="tf32", named_params=named)
+    tol = TOL[prec]
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
     out = eng.forward(b["inputs"], b["input_lengths"], spk, b["mel_targets"], b["linear_targets"], b["loss_coeff"])
-    errs = {k: (out[k].cpu() - ref[k].detach()).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
+    errs = _check_outputs(out, ref, tol, argmax_min=0.97)
     eng.backward()
     sc = eng.scalars()
     cos, na, nb = _cosine(eng.named_gradients(), ref_g, sorted(ref_g))
-    print("C3 full size: errs", errs, "loss", sc["loss"], float(ls["loss"]), "cos", cos, "norms", na, nb)
-    assert max(errs.values()) <= 5e-2, errs
-    assert abs(sc["loss"] - float(ls["loss"])) <= 2e-3 * float(ls["loss"])
-    assert cos >= 0.99 and abs(na - nb) <= 5e-2 * nb
-    spk_g = [k for k in names if k.startswith("speaker")]
-    assert spk_g and all(eng.named_gradients()[k].abs().max().item() > 0 for k in spk_g)
+    print("%s full size (%s): errs" % (config, prec), errs, "loss", sc["loss"], float(ls["loss"]), "1-cos", 1 - cos, "norms", na, nb)
+    assert abs(sc["loss"] - float(ls["loss"])) <= tol["loss"] * float(ls["loss"])
+    assert cos >= tol["cos"] and abs(na - nb) <= tol["gn"] * nb
+    if multi:
+        spk_g = [k for k in names if k.startswith("speaker")]
+        assert spk_g and all(eng.named_gradients()[k].abs().max().item() > 0 for k in spk_g)
     eng.close()
 
 
-def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb):
-    """configs[3]: batch 1, 200 free-running decoder steps (1000 frames) + post-net, single speaker; configs[4]: batch 64,
-    4 speakers, text 200 (20 free-running steps here to bound the oracle's time; the step count does not change the code
-    path).  fp32 mode against the oracle: a free-running decoder feeds its own outputs back, so the bound is 2e-3."""
+@pytest.mark.parametrize("prec", ALL_PREC)
+def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb, prec):
+    """configs[3] (C4): batch 1, 200 free-running decoder steps (1000 frames) + post-net, single speaker; configs[4] (C5):
+    batch 64, 4 speakers, text 200, 200 free-running steps - both at their full size against the oracle in every precision
+    (C4 in bf16 is what bench.py's synth_rtf leg times).  A free-running decoder feeds its own outputs back: bounds `free`."""
+    tol = TOL[prec]
+    lim = dict(tol, free=max(tol["free"], 2e-3))          # fp32: 200 fed-back steps accumulate to ~4e-6; keep the round-1 bound
     hp = tb.hparams.override(reduction_factor=5)
     named = tb.params.init_params(hp, 1, seed=43, randomize_bn_state=True)
     g = torch.Generator().manual_seed(7)
     tok = torch.randint(2, 80, (1, 128), generator=g, dtype=torch.int32); tok[0, -1] = 1
     L = torch.tensor([128], dtype=torch.int32)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     with torch.no_grad():
         ref = O.forward(named, hp, tok, L, 1, None, max_iters=200, speaker_mode="none")
-    eng = tb.Engine(hp, 1, precision="fp32", named_params=named)
+    eng = tb.Engine(hp, 1, precision=prec, named_params=named)
     out = eng.forward(tok, L, decoder_steps=200)
     assert out["mel_outputs"].shape == (1, 1000, 80) and out["linear_outputs"].shape == (1, 1000, 1025)
-    errs = {k: (out[k].cpu() - ref[k]).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
-    print("C4 full size: errs", errs)
-    assert max(errs.values()) <= 2e-3, errs
+    print("C4 full size (%s):" % prec, _check_outputs(out, ref, lim, bound="free", argmax_min=0.98))
     eng.close()
     hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice")
     S, N, Ti = 4, 64, 200
@@ -304,15 +336,12 @@ def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb):
     b = _batch(N, Ti, 5, lengths, seed=23)
     spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32)
     with torch.no_grad():
-        ref = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, max_iters=20, speaker_mode="deepvoice")
-    for prec, lim in (("fp32", 2e-3), ("tf32", 8e-2)):
-        eng = tb.Engine(hp, S, precision=prec, named_params=named)
-        out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=20)
-        assert out["linear_outputs"].shape == (N, 100, 1025) and out["alignments"].shape == (N, Ti, 20)
-        errs = {k: (out[k].cpu() - ref[k]).abs().max().item() for k in ("mel_outputs", "linear_outputs", "alignments")}
-        print("C5 full size (%s): errs" % prec, errs)
-        assert max(errs.values()) <= lim, (prec, errs)
-        eng.close()
+        ref = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, max_iters=200, speaker_mode="deepvoice")
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=200)
+    assert out["linear_outputs"].shape == (N, 1000, 1025) and out["alignments"].shape == (N, Ti, 200)
+    print("C5 full size (%s):" % prec, _check_outputs(out, ref, lim, bound="free", argmax_min=0.99))
+    eng.close()
 
 
 def test_free_running_inference_matches_golden_and_oracle(tb, hp5, golden_setup):
@@ -424,7 +453,7 @@ def test_audio_front_end_and_inversion_match_reference_audio_code(tb):
     gl.close(); g2.close()
 
 
-@pytest.mark.parametrize("prec,emb", [("fp32", 16), ("fp32", 1), ("tf32", 16)])
+@pytest.mark.parametrize("prec,emb", [("fp32", 16), ("fp32", 1), ("tf32", 16), ("bf16", 16), ("bf16", 1)])
 def test_deepvoice_speaker_injection_vs_oracle(tb, prec, emb):
     """model_type='deepvoice' (tacotron.py:41-81,183-197): before_highway, encoder / attention / decoder initial states."""
     hp = tb.hparams.override(reduction_factor=5, model_type="deepvoice", speaker_embedding_size=emb)
@@ -474,7 +503,7 @@ def _oracle_grads(named, hp, b, S, spk, mode):
     return ref, {k: (gg if gg is not None else torch.zeros_like(named[k])) for k, gg in zip(names, gl)}, names
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ALL_PREC)
 def test_simple_speaker_concat_vs_oracle(tb, prec):
     """model_type='simple' (tacotron.py:44-49,82-86,226-233; rnn_wrappers.py:372-376,408-413): the speaker embedding is
     concatenated at the attention-GRU input, the concat projection and (first) before the linear projection."""
@@ -511,12 +540,11 @@ def test_simple_speaker_concat_vs_oracle(tb, prec):
     with torch.no_grad():
         inf = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, None, None, speaker_mode=mode, max_iters=4)
     out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=4)
-    for k in ("mel_outputs", "linear_outputs", "alignments"):
-        assert (out[k].cpu() - inf[k]).abs().max().item() <= (2e-3 if prec == "fp32" else 6e-2), k
+    _check_outputs(out, inf, dict(tol, free=max(tol["free"], 2e-3)), bound="free")
     eng.close()
 
 
-@pytest.mark.parametrize("prec,att", [("fp32", "bah"), ("fp32", "bah_norm"), ("tf32", "bah"), ("tf32", "bah_norm")])
+@pytest.mark.parametrize("prec,att", [("fp32", "bah"), ("fp32", "bah_norm"), ("tf32", "bah"), ("tf32", "bah_norm"), ("bf16", "bah"), ("bf16", "bah_norm")])
 def test_attention_variants_vs_oracle(tb, prec, att):
     """attention_type 'bah' (softmax BahdanauAttention) and 'bah_norm' (normalize=True: g, b) — tacotron.py:136-146."""
     hp = tb.hparams.override(reduction_factor=5, attention_type=att)
@@ -546,7 +574,7 @@ def test_attention_variants_vs_oracle(tb, prec, att):
     eng.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ALL_PREC)
 def test_manual_attention_override_vs_oracle(tb, hp5, prec):
     """is_manual_attention: alignments = manual[:, t, :] (rnn_wrappers.py:313-317; synthesizer.py:171-205), training and
     free-running; the override also cuts the score/keys gradient path."""
@@ -579,8 +607,7 @@ def test_manual_attention_override_vs_oracle(tb, hp5, prec):
         inf = O.forward(named, hp5, b["inputs"], b["input_lengths"], 1, None, None, None, manual_alignments=manual,
                         max_iters=Td, speaker_mode="none")
     out = eng.forward(b["inputs"], b["input_lengths"], None, decoder_steps=Td, manual_alignments=manual)
-    for k in ("mel_outputs", "linear_outputs"):
-        assert (out[k].cpu() - inf[k]).abs().max().item() <= (2e-3 if prec == "fp32" else 6e-2), k
+    _check_outputs(out, inf, dict(tol, free=max(tol["free"], 2e-3)), keys=("mel_outputs", "linear_outputs"), bound="free")
     eng.close()
 
 

@@ -36,7 +36,7 @@ def test_hparams_defaults_and_roundtrip(tb, tmp_path):
 def test_layout_alignment_and_bank_contiguity(tb, hp5):
     specs = tb.params.param_specs(hp5, 1)
     lay = tb.params.make_layout(specs)
-    assert all(o % 4 == 0 for o in lay.offsets.values())
+    assert all(o % 8 == 0 for o in lay.offsets.values())      # 16 bytes in the bf16 mirror of the flat buffer
     for pf, Kb, Cb in (("enc_cbhg", 16, 128), ("post_cbhg", 8, 256)):
         for f in ("bias", "gamma", "beta", "moving_mean", "moving_var"):
             offs = [lay.offsets["%s/bank_%d/%s" % (pf, k, f)] for k in range(1, Kb + 1)]
@@ -370,3 +370,33 @@ def test_decoder_wavefront_chunk_boundaries(tb):
                 assert min(t1 - t0 for t0, t1 in ch) >= 8 or Td < 16, (Td, want, ch)
                 assert ch[-1][1] - ch[-1][0] <= max(t1 - t0 for t0, t1 in ch[:-1]), (Td, want, ch)      # the last chunk is the short one
     assert lib.taco_debug_wave_chunks(160, 4, buf, 64) == 4 and [buf[i] for i in range(8)] == [0, 56, 56, 112, 112, 144, 144, 160]
+
+
+def test_manual_attention_second_pass_matches_the_reference_indexing(tb):
+    """synthesizer.py:171-196 of the reference, restated literally (its own variable names), against manual_alignments_from:
+    mode 1 = zeros + a one at (argmax decoder step of every INPUT position, that position); mode 3 = the same ones written into
+    the transposed soft alignments; mode 2 cannot run in the reference (np.pow)."""
+    from importlib import import_module
+    syn = import_module("multi-speaker-tacotron-tensorflow_b200.synthesizer")
+    rng = np.random.RandomState(5)
+    alignments = rng.rand(3, 7, 11).astype(np.float32)             # [N, T_in (E), T_dec (D)]
+    alignments /= alignments.sum(1, keepdims=True)
+    # --- the reference's lines for mode 1
+    alignments_T = np.transpose(alignments, [0, 2, 1])
+    new_alignments = np.zeros_like(alignments_T)
+    for idx in range(len(alignments)):
+        argmax = alignments[idx].argmax(1)
+        new_alignments[idx][(argmax, range(len(argmax)))] = 1
+    got = syn.manual_alignments_from(alignments, 1)
+    assert got.shape == (3, 11, 7) and np.array_equal(got, new_alignments)
+    assert got.sum() <= 3 * 7 and (got.sum(1) <= 1).all()            # at most one decoder step per input position
+    # --- mode 3
+    new_alignments = np.transpose(alignments, [0, 2, 1]).copy()
+    for idx in range(len(alignments)):
+        argmax = alignments[idx].argmax(1)
+        new_alignments[idx][(argmax, range(len(argmax)))] = 1
+    got3 = syn.manual_alignments_from(alignments, 3)
+    assert np.array_equal(got3, new_alignments) and not np.array_equal(got3, got)
+    assert np.array_equal(alignments_T, np.transpose(alignments, [0, 2, 1]))   # the input is not modified
+    with pytest.raises(NotImplementedError, match="np.pow"):
+        syn.manual_alignments_from(alignments, 2)
