@@ -30,8 +30,23 @@ WORKLOAD = "C2: train step, batch=32/GPU, text_len=128, mel_len=800, 80-bin mel,
 ALGO_BYTES_PER_STEP = 486.6e6
 # algorithmic FLOPs of one training step per GPU (3 x the 261.6 GFLOP forward; 30.66 MFLOP per mel frame)
 ALGO_FLOPS_PER_STEP = 784.8e9
-# ncu (profiles/r1_step_metrics_v7.summary.txt): 4697.5 MB of DRAM traffic over the 183 gemm_tc_kernel launches of one step
-GEMM_DRAM_BYTES_PER_LAUNCH = 4697.5e6 / 183
+DTYPE_LABEL = {"bf16": "bf16", "tf32": "tf32+bf16-recurrent", "fp32": "fp32"}
+DTYPE_NOTE = {
+    "bf16": "bf16 operands (activations, gradients, weights) with fp32 accumulation in the CBHG / linear contractions (tcgen05 kind::f16), "
+            "tf32 in the small decoder contractions, bf16 recurrent weights with fp32 state, MUFU tanh/sigmoid; parameters, Adam and batch-norm statistics fp32",
+    "tf32": "fp32 operands rounded to tf32 inside the tensor core (tcgen05 kind::tf32), bf16 recurrent weights with fp32 state, MUFU tanh/sigmoid",
+    "fp32": "exact-parity mode: fp32 FMA everywhere",
+}
+
+
+def gemm_traffic(precision):
+    """DRAM bytes per GEMM launch from the committed ncu capture of this build (profiles/r2_gemm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")) as f:
+            t = json.load(f).get(precision)
+        return (t["dram_bytes_per_launch"], t["source"]) if t else (None, "no ncu capture of this precision mode is committed")
+    except (OSError, ValueError, KeyError):
+        return None, "profiles/r2_gemm_traffic.json missing"
 
 
 def synth_batch(rank: int, N=CFG["N"], Ti=CFG["T_in"], To=CFG["T_out"]):
@@ -233,15 +248,25 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    extra = {}
+    if args.legs:
+        eng.close()
+        del dev, bufs, flush
+        torch.cuda.empty_cache()
+        extra["c3"] = leg_c3(tb, Engine, args.precision, local, rank, world, allreduce, barrier)
+        extra["c5"] = leg_c5(tb, Engine, args.precision, local, rank, world, barrier)
+
     frames = world * CFG["N"] * CFG["T_out"] * args.steps
     if rank == 0:
         peaks, which = measured_peaks()
+        traffic, traffic_src = gemm_traffic(args.precision)
+        n_gemm = int(prof_n[3] // PROF_STEPS)
         ms_step = total_ms / args.steps
         ach = ALGO_BYTES_PER_STEP / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
+            "dtype": DTYPE_LABEL[args.precision], "dtype_note": DTYPE_NOTE[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
                        "timing": "CUDA events per step on the compute stream, max over ranks"},
@@ -249,27 +274,32 @@ def run_ours(args):
                     "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream, the next batch's copy issued behind the forward pass) + every step's loss read back to the host (pinned, one step of run-ahead)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            # dominant kernel class by device time: the tcgen05 GEMM (all GEMM-shaped work of the step)
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed; fp32 SIMT in fp32 mode)",
+            # dominant kernel class by device time: the tcgen05 GEMMs (all GEMM-shaped work of the step)
+            "roofline": {"bound": "tensor",
+                         "kernel": {"bf16": "gemm_bf16_kernel (tcgen05.mma kind::f16, bf16 operands, TMA-fed, persistent) + gemm_tc_kernel (kind::tf32) for the small decoder problems",
+                                    "tf32": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA-fed)", "fp32": "gemm_simt_kernel (fp32 FMA)"}[args.precision],
                          "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                          "unit": "TFLOP/s", "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
-                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r1_step_metrics_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum over the step's gemm_tc_kernel launches / launches",
-                         "peak_source": which + " (dense bf16 cuBLAS, sustained; TF32 nominal peak is half of it)",
-                         "launches_per_step": int(prof_n[0] // PROF_STEPS), "problems_per_step": int(prof_n[3] // PROF_STEPS), "ms_per_step": gemm_ms,
-                         "algorithmic_flops_per_step": gemm_flops, "algorithmic_flops_per_launch": gemm_flops / max(1, prof_n[3] // PROF_STEPS),
-                         "avg_launch_us": 1e3 * gemm_ms / max(1, prof_n[3] // PROF_STEPS),
-                         "note": "algorithmic FLOPs (2MNK summed over the GEMM problems of one step, counted where they are launched) / summed GEMM device time per step; CUDA events around every GEMM call on its launching stream, taken in a serialised window (the two-stream backward schedule is off while profiling)"},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": which + " (dense bf16 cuBLAS, sustained)",
+                         "launches_per_step": n_gemm, "ms_per_step": gemm_ms,
+                         "algorithmic_flops_per_step": gemm_flops, "algorithmic_flops_per_launch": gemm_flops / max(1, n_gemm),
+                         "avg_launch_us": 1e3 * gemm_ms / max(1, n_gemm),
+                         "note": "one denominator: launches_per_step = GEMM problems of one step = GEMM kernel launches (each problem is one launch of a tensor-core kernel; "
+                                 "the few sub-tile problems are batched into grouped fp32 launches); algorithmic FLOPs = sum of 2MNK over them, counted where they are launched; "
+                                 "time = CUDA events around every GEMM call on its launching stream, summed, in a serialised window (the multi-stream schedule is off while profiling)"},
             "recurrence_ms_per_step": {"gru_fwd_bwd": prof_ms[1] / PROF_STEPS, "attention_fwd_bwd": prof_ms[2] / PROF_STEPS,
                                        "note": "serial chains: 2 656 dependent recurrence steps per training step (latency bound)"},
             "roofline_step_hbm": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                                   "note": "whole-step algorithmic bytes (486.6 MB, SURVEY.md 8d) / step time"},
             "loss": sc["loss"],
         }
+        line.update(extra)
         if args.synth and world == 1:
             eng.close()
             line["synth_rtf"] = synth_rtf_ours(hp, local, args.precision)
         if args.cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+            line["cpu_baseline"] = cpu_baseline(sample_steps=3, warmup=1)
             if args.synth and world == 1:
                 line["cpu_baseline"]["synth_rtf"] = synth_rtf_cpu()
         if saved_stdout is not None:
@@ -278,6 +308,72 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def leg_c3(tb, Engine, precision, local, rank, world, allreduce, barrier, steps=5, warmup=3):
+    """BASELINE.json configs[2]: the same training step with model_type=deepvoice, 3 speakers (batch 32 per GPU) - device-timed."""
+    import torch
+    import torch.distributed as dist
+    hp = tb.hparams.override(reduction_factor=CFG["r"], batch_size=CFG["N"], model_type="deepvoice")
+    eng = Engine(hp, 3, precision=precision, device=local, seed=4321)
+    b = synth_batch(rank)
+    g = torch.Generator().manual_seed(99 + rank)
+    b["speaker_id"] = torch.randint(0, 3, (CFG["N"],), generator=g, dtype=torch.int32)
+    dev = {k: v.to(eng.dev) for k, v in b.items()}
+    for _ in range(warmup):
+        eng.train_step(dev, allreduce=allreduce)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record(); eng.train_step(dev, allreduce=allreduce); ev[i][1].record()
+    barrier()
+    t = torch.tensor([sum(a.elapsed_time(c) for a, c in ev)], dtype=torch.float64, device=eng.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    loss = eng.scalars()["loss"]
+    eng.close()
+    ms = float(t.item()) / steps
+    return {"workload": "C3: train step, model_type=deepvoice, 3 speakers, batch=32/GPU, text_len=128, mel_len=800, r=5", "ms_per_step": ms,
+            "value": world * CFG["N"] * CFG["T_out"] / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup, "loss": loss,
+            "note": "device-timed (CUDA events, max over ranks), inputs resident, L2 not flushed"}
+
+
+def leg_c5(tb, Engine, precision, local, rank, world, barrier, reps=5):
+    """BASELINE.json configs[4]: batched inference, 64 utterances, 4 speakers, text_len=200, 200 free-running decoder steps ->
+    1000 frames + post-net + linear projection.  The 64 rows are sharded over the ranks (replicas only, no collective)."""
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    shard_rows = import_module("multi-speaker-tacotron-tensorflow_b200.dist").shard_rows
+    hp = tb.hparams.override(reduction_factor=CFG["r"], model_type="deepvoice")
+    S, N, Ti, steps = 4, 64, 200, 200
+    eng = Engine(hp, S, precision=precision, device=local, seed=4321, randomize_bn_state=True)
+    g = torch.Generator().manual_seed(77)
+    L = torch.randint(120, Ti + 1, (N,), generator=g, dtype=torch.int32); L[3] = Ti
+    tok = torch.randint(2, 80, (N, Ti), generator=g, dtype=torch.int32)
+    for n in range(N):
+        tok[n, L[n] - 1] = 1; tok[n, L[n]:] = 0
+    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32)
+    r0, r1 = shard_rows(N, rank, world)
+    tok, L, spk = tok[r0:r1].to(eng.dev), L[r0:r1].to(eng.dev), spk[r0:r1].to(eng.dev)
+    for _ in range(2):
+        eng.forward(tok, L, spk, decoder_steps=steps)
+    barrier()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = eng.forward(tok, L, spk, decoder_steps=steps); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = torch.tensor([sorted(ts)[len(ts) // 2]], dtype=torch.float64, device=eng.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    finite = bool(torch.isfinite(out["linear_outputs"]).all())
+    eng.close()
+    ms = float(t.item())
+    return {"workload": "C5: batched inference, 64 utterances (sharded over the ranks), 4 speakers, text_len=200, 200 free-running steps -> 1000 frames, post-net, linear projection",
+            "ms_per_batch": ms, "rows_per_s": N / (ms * 1e-3), "frames_per_s": N * steps * CFG["r"] / (ms * 1e-3), "rows_per_rank": r1 - r0, "finite": finite,
+            "note": "device-timed median of %d calls, max over ranks; tokens resident" % reps}
 
 
 SYNTH = dict(N=1, T_in=128, steps=200, gl_iters=60)      # config C4 (SURVEY.md 8d): 200 free-running steps -> 1000 frames
@@ -358,8 +454,9 @@ def synth_rtf_cpu(threads: int = 0):
             "sample": "one full C4 synthesis (oracle forward on torch-CPU + numpy/pocketfft Griffin-Lim, 60 iterations)"}
 
 
-def cpu_baseline(sample_steps: int = 1, threads: int = 0):
-    """The CPU oracle restatement (torch-CPU, all host cores) timed on one full C2 training step."""
+def cpu_baseline(sample_steps: int = 1, threads: int = 0, warmup: int = 0):
+    """The CPU oracle restatement (torch-CPU, all host cores) timed on full C2 training steps: `warmup` untimed steps, then
+    `sample_steps` timed ones; the MEDIAN step time is reported (the first step pays allocator / thread-pool start-up)."""
     import torch
     import tacotron_b200 as tb
     from oracle import tacotron_oracle as O
@@ -372,14 +469,17 @@ def cpu_baseline(sample_steps: int = 1, threads: int = 0):
     v = {k: torch.zeros_like(P[k]) for k in names}
     b = synth_batch(0)
     times = []
-    for i in range(sample_steps):
+    for i in range(warmup + sample_steps):
         t0 = time.perf_counter()
         res = O.train_step(P, m, v, hp, b, i, True, 1, "none")
-        times.append(time.perf_counter() - t0)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
         P, m, v = res["params"], res["m"], res["v"]
-    sec = sum(times) / len(times)
-    return {"value": CFG["N"] * CFG["T_out"] / sec, "unit": UNIT, "cores": n, "kind": "port",
-            "sample": "%d full C2 training step(s) (fwd+bwd+clip+Adam, fp32) of the TF-semantics oracle on torch-CPU, %.1f s/step" % (sample_steps, sec)}
+    sec = sorted(times)[len(times) // 2]
+    return {"value": CFG["N"] * CFG["T_out"] / sec, "unit": UNIT, "cores": n, "kind": "port", "steps": sample_steps, "warmup": warmup,
+            "step_seconds": [round(t, 3) for t in times],
+            "sample": "%d warm-up + %d timed full C2 training steps (fwd+bwd+clip+Adam, fp32) of the TF-semantics oracle on torch-CPU, median %.2f s/step"
+                      % (warmup, sample_steps, sec)}
 
 
 def run_reference(args):
@@ -390,10 +490,11 @@ def run_reference(args):
     ncpu = str(os.cpu_count() or 1)
     os.environ["OMP_NUM_THREADS"] = ncpu
     os.environ["MKL_NUM_THREADS"] = ncpu
-    steps = max(1, min(args.steps, 3))
-    base = cpu_baseline(sample_steps=steps)
+    # one warm-up step and >= 3 timed ones at every N (each step is a bounded sample: one full C2 batch, ~2.5 s on 16 cores)
+    steps = max(3, min(args.steps, 5))
+    base = cpu_baseline(sample_steps=steps, warmup=1)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": 0, "ms_per_step": 1e3 * CFG["N"] * CFG["T_out"] / base["value"], "higher_is_better": True, "scaling": "weak",
+            "warmup": 1, "ms_per_step": 1e3 * CFG["N"] * CFG["T_out"] / base["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": CFG["N"], "parallelism": "cpu",
                        "note": "the reference's train step restated on torch-CPU (oracle/tacotron_oracle.py, pinned to the reference's own "
@@ -409,9 +510,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-synth", dest="synth", action="store_false", help="skip the C4 synthesis real-time-factor leg (N=1 only)")
+    ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the C3 (deepvoice training) and C5 (batched inference) legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
