@@ -89,6 +89,74 @@ __device__ __forceinline__ void push_rm(cg::cluster_group& cl, float* mat_s, int
     }
 }
 
+
+// ---- fragment-packed bf16 weights of the free-running decoder (inference; tensor-core precision modes) --------------------
+// The exact kernels stream fp32 weights from L2 with scalar loads and multiply on the FMA pipe: 75 us per decoder step, bound by
+// load latency (4-byte loads in flight) and, at 8 rows, by 25 M FMAs per step.  For synthesis the step's 1.57 M weights are
+// packed ONCE per call as bf16 mma.m16n8k16 A fragments, per cluster rank, m-tile (16 output columns) and k-tile: a warp then
+// fetches a whole 16x16 weight tile with one coalesced 512-byte load (16 bytes per lane) and multiplies it with the 8 batch
+// rows of the cluster on the tensor cores.  Thread/slot layout of the partial sums (`red`) is the one of the scalar path, so
+// the activation code of every phase is shared.
+constexpr int WF_N = 18;
+enum WfId { WF_W1C = 0, WF_W1X, WF_W2, WF_WG_Z, WF_WG_H, WF_WC_Z, WF_WC_H, WF_WQWO, WF_WO_C,
+            WF_G1_GX, WF_G1_GH, WF_G1_CX, WF_G1_CH, WF_G2_GX, WF_G2_GH, WF_G2_CX, WF_G2_CH, WF_MEL };
+struct WfSpec { const float* WA; const float* WB; int ldA, ldB, UA, UB, offA, offB, split, row0, K, ncols, valid; };
+struct WfTable { WfSpec s[WF_N]; long long off[WF_N + 1]; };     // off: start of each image in uint4 units
+
+__device__ __forceinline__ uint32_t wf_pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// image index: ((rank * MT + mt) * nkt + kt) * 32 + lane;  lane (g = lane>>2, t = lane&3) holds A[g][2t..], A[g+8][2t..], A[g][2t+8..], A[g+8][2t+8..]
+__global__ void wf_pack_kernel(const __grid_constant__ WfTable tab, uint4* __restrict__ img) {
+    const WfSpec& sp = tab.s[blockIdx.y];
+    const int MT = sp.ncols / 16, nkt = (sp.K + 15) / 16;
+    const long long total = (long long)AT_C * MT * nkt * 32;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(idx & 31); long long q = idx >> 5;
+        const int kt = (int)(q % nkt); q /= nkt;
+        const int mt = (int)(q % MT), rank = (int)(q / MT);
+        const int g = lane >> 2, t = lane & 3;
+        auto W = [&](int m, int k) -> float {
+            const int col = mt * 16 + m, kk = kt * 16 + k;
+            if (col >= sp.valid || kk >= sp.K) return 0.f;
+            if (col < sp.split) return __ldg(sp.WA + (long long)(sp.row0 + kk) * sp.ldA + rank * sp.UA + sp.offA + col);
+            return __ldg(sp.WB + (long long)(sp.row0 + kk) * sp.ldB + rank * sp.UB + sp.offB + (col - sp.split));
+        };
+        uint4 o;
+        o.x = wf_pack2(W(g, 2 * t), W(g, 2 * t + 1));         o.y = wf_pack2(W(g + 8, 2 * t), W(g + 8, 2 * t + 1));
+        o.z = wf_pack2(W(g, 2 * t + 8), W(g, 2 * t + 9));     o.w = wf_pack2(W(g + 8, 2 * t + 8), W(g + 8, 2 * t + 9));
+        img[tab.off[blockIdx.y] + idx] = o;
+    }
+}
+__device__ __forceinline__ void wf_mma(float c[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// acc += W_tile(mt; k-tiles ks, ks+KS, ...) . v      img_mt: image of this rank's m-tile ([kt][32] uint4); v_s: fp32 [K][R]
+__device__ __forceinline__ void wf_seg(float acc[4], const uint4* __restrict__ img_mt, int nkt, int KS, int ks, const float* __restrict__ v_s, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int kt0 = ks; kt0 < nkt; kt0 += 4 * KS) {
+        uint4 af[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int kt = kt0 + u * KS; if (kt < nkt) af[u] = __ldg(img_mt + kt * 32 + lane); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int kt = kt0 + u * KS;
+            if (kt < nkt) {
+                const float* vp = v_s + (kt * 16 + 2 * t) * AT_R + g;
+                wf_mma(acc, af[u], wf_pack2(vp[0], vp[AT_R]), wf_pack2(vp[8 * AT_R], vp[9 * AT_R]));
+            }
+        }
+    }
+}
+// fragment -> red[r][ks*ncols + col]  (the slot the scalar path's thread (col, ks) writes)
+__device__ __forceinline__ void wf_store(float* red, const float acc[4], int ncols, int ks, int mt, int lane) {
+    const int g = lane >> 2, t = lane & 3, base = ks * ncols + mt * 16 + g;
+    red[(2 * t) * AT_NT + base] = acc[0]; red[(2 * t + 1) * AT_NT + base] = acc[1];
+    red[(2 * t) * AT_NT + base + 8] = acc[2]; red[(2 * t + 1) * AT_NT + base + 8] = acc[3];
+}
+
 static inline size_t att_fwd_smem_floats(const AttArgs& a, int Tip) {
     const size_t fr = a.free_run ? (size_t)AT_R * (a.M + 6 * a.Y) : 0;
     return fr + (size_t)AT_R * (a.E + a.Z1 + (a.Z + a.SPK) + 2 * a.HA + a.A) + (size_t)4 * AT_R * Tip + (size_t)2 * AT_R * AT_NT + 1024 + a.A;
@@ -172,10 +240,22 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
     __syncthreads();
     cl.sync();
 
+    // fragment-packed weights (free-running decoder of the tensor-core modes, see wf_pack_kernel): image of matrix `id`, this rank, m-tile mt
+    const bool WFP = FAST && a.wfrag != nullptr;
+    auto wf = [&](int id, int MT, int nkt, int mt) { return reinterpret_cast<const uint4*>(a.wfrag) + a.wf_off[id] + ((long long)(rank * MT + mt) * nkt) * 32; };
+
     for (int t = 0; t < Td; t++) {
         const long long row32 = (long long)n32 * Td + t;
         // ===== P1: z1 (own Uz1 units) = relu(px + ctx.W1c) =====
-        {
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {          // 2 m-tiles x 8 k-slices
+                const int mt = task & 1, ks = task >> 1;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                wf_seg(acc, wf(WF_W1C, 2, 16, mt), 16, 8, ks, ctx_s, lane);
+                wf_seg(acc, wf(WF_W1X, 2, 5, mt), 5, 8, ks, x_s, lane);
+                wf_store(red, acc, 32, ks, mt, lane);
+            }
+        } else {
             const int ncols = Uz1, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kl = E / KS;
@@ -207,7 +287,13 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_um(cl, z1_s, stage, rank, Uz1, tid);
         cl.sync();
         // ===== P2: z (own Uz units) = relu(z1.W2 + b2) =====
-        {
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {          // 1 m-tile x 16 k-slices
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                wf_seg(acc, wf(WF_W2, 1, 16, 0), 16, 16, task, z1_s, lane);
+                wf_store(red, acc, 16, task, 0, lane);
+            }
+        } else {
             const int ncols = Uz, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kl = Z1 / KS;
@@ -228,22 +314,40 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_um(cl, z_s, stage, rank, Uz, tid);
         cl.sync();
         // ===== P3: gates r|u (own 2*Uh columns) and the z-part of the candidate =====
-        {
-            const int ncols = 2 * Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
-            const int gcol = (col < Uh) ? rank * Uh + col : HA + rank * Uh + (col - Uh);
-            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int kl = ZS / KS;
-            mv_acc(acc, a.Wg + gcol, 2 * HA, z_s, ks * kl, (ks + 1) * kl);
-            kl = HA / KS;
-            mv_acc(acc, a.Wg + (long long)ZS * 2 * HA + gcol, 2 * HA, ha_s, ks * kl, (ks + 1) * kl);
-            red_store(red, tid, acc);
-        }
-        {
-            const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
-            float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const int kl = ZS / KS;
-            mv_acc(acc, a.Wc + rank * Uh + col, HA, z_s, ks * kl, (ks + 1) * kl);
-            red_store(red2, tid, acc);
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {
+                {   // gates: 4 m-tiles (r | u columns) x 4 k-slices over [z ; ha]
+                    const int mt = task & 3, ks = task >> 2;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    wf_seg(acc, wf(WF_WG_Z, 4, 8, mt), 8, 4, ks, z_s, lane);
+                    wf_seg(acc, wf(WF_WG_H, 4, 16, mt), 16, 4, ks, ha_s, lane);
+                    wf_store(red, acc, 64, ks, mt, lane);
+                }
+                {   // z part of the candidate: 2 m-tiles x 8 k-slices
+                    const int mt = task & 1, ks = task >> 1;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    wf_seg(acc, wf(WF_WC_Z, 2, 8, mt), 8, 8, ks, z_s, lane);
+                    wf_store(red2, acc, 32, ks, mt, lane);
+                }
+            }
+        } else {
+            {
+                const int ncols = 2 * Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                const int gcol = (col < Uh) ? rank * Uh + col : HA + rank * Uh + (col - Uh);
+                float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                int kl = ZS / KS;
+                mv_acc(acc, a.Wg + gcol, 2 * HA, z_s, ks * kl, (ks + 1) * kl);
+                kl = HA / KS;
+                mv_acc(acc, a.Wg + (long long)ZS * 2 * HA + gcol, 2 * HA, ha_s, ks * kl, (ks + 1) * kl);
+                red_store(red, tid, acc);
+            }
+            {
+                const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const int kl = ZS / KS;
+                mv_acc(acc, a.Wc + rank * Uh + col, HA, z_s, ks * kl, (ks + 1) * kl);
+                red_store(red2, tid, acc);
+            }
         }
         __syncthreads();
         float rg = 0.f, ug = 0.f, cz = 0.f;
@@ -259,7 +363,14 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_um(cl, rha_s, stage, rank, Uh, tid);
         cl.sync();
         // ===== P4: candidate, new attention-GRU state =====
-        {
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {
+                const int mt = task & 1, ks = task >> 1;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                wf_seg(acc, wf(WF_WC_H, 2, 16, mt), 16, 8, ks, rha_s, lane);
+                wf_store(red, acc, 32, ks, mt, lane);
+            }
+        } else {
             const int ncols = Uh, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kl = HA / KS;
@@ -282,7 +393,14 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_um(cl, ha_s, stage, rank, Uh, tid);
         cl.sync();
         // ===== P5: query (own Ua columns) and the ha-part of the concat projection (own Uy columns) =====
-        {
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {          // 4 m-tiles (Wq | Wo_h columns) x 4 k-slices
+                const int mt = task & 3, ks = task >> 2;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                wf_seg(acc, wf(WF_WQWO, 4, 16, mt), 16, 4, ks, ha_s, lane);
+                wf_store(red, acc, 64, ks, mt, lane);
+            }
+        } else {
             const int ncols = Ua + Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kl = HA / KS;
@@ -421,7 +539,14 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
         push_um(cl, ctx_s, stage, rank, Ue, tid);
         cl.sync();
         // ===== P8: y0 (own Uy columns) = yh + ctx.Wo_c (+ spk.Wo_s) + bo =====
-        {
+        if (WFP) {
+            for (int task = warp; task < 16; task += AT_NT / 32) {
+                const int mt = task & 1, ks = task >> 1;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                wf_seg(acc, wf(WF_WO_C, 2, 16, mt), 16, 8, ks, ctx_s, lane);
+                wf_store(red2, acc, 32, ks, mt, lane);
+            }
+        } else {
             const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
             float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             int kl = E / KS;
@@ -449,21 +574,40 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
                 const float* Wc_ = layer ? a.Wc2 : a.Wc1; const float* bc_ = layer ? a.bc2 : a.bc1;
                 float* xin_s = layer ? y1_s : y0_s; float* hst_s = layer ? h2_s : h1_s; float* yout_s = layer ? y2_s : y1_s;
                 float& h_own = layer ? h2_own : h1_own;
-                {   // gates over [x ; h]
-                    const int ncols = 2 * Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
-                    const int gcol = (col < Uy) ? rank * Uy + col : Y + rank * Uy + (col - Uy);
-                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    const int kl = Y / KS;
-                    mv_acc(acc, Wg_ + gcol, 2 * Y, xin_s, ks * kl, (ks + 1) * kl);
-                    mv_acc(acc, Wg_ + (long long)Y * 2 * Y + gcol, 2 * Y, hst_s, ks * kl, (ks + 1) * kl);
-                    red_store(red, tid, acc);
-                }
-                {   // x part of the candidate
-                    const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
-                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    const int kl = Y / KS;
-                    mv_acc(acc, Wc_ + rank * Uy + col, Y, xin_s, ks * kl, (ks + 1) * kl);
-                    red_store(red2, tid, acc);
+                const int wf0 = layer ? WF_G2_GX : WF_G1_GX;
+                if (WFP) {
+                    for (int task = warp; task < 16; task += AT_NT / 32) {
+                        {   // gates over [x ; h]: 4 m-tiles (r | u) x 4 k-slices
+                            const int mt = task & 3, ks = task >> 2;
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            wf_seg(acc, wf(wf0, 4, 16, mt), 16, 4, ks, xin_s, lane);
+                            wf_seg(acc, wf(wf0 + 1, 4, 16, mt), 16, 4, ks, hst_s, lane);
+                            wf_store(red, acc, 64, ks, mt, lane);
+                        }
+                        {   // x part of the candidate: 2 m-tiles x 8 k-slices
+                            const int mt = task & 1, ks = task >> 1;
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            wf_seg(acc, wf(wf0 + 2, 2, 16, mt), 16, 8, ks, xin_s, lane);
+                            wf_store(red2, acc, 32, ks, mt, lane);
+                        }
+                    }
+                } else {
+                    {   // gates over [x ; h]
+                        const int ncols = 2 * Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                        const int gcol = (col < Uy) ? rank * Uy + col : Y + rank * Uy + (col - Uy);
+                        float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const int kl = Y / KS;
+                        mv_acc(acc, Wg_ + gcol, 2 * Y, xin_s, ks * kl, (ks + 1) * kl);
+                        mv_acc(acc, Wg_ + (long long)Y * 2 * Y + gcol, 2 * Y, hst_s, ks * kl, (ks + 1) * kl);
+                        red_store(red, tid, acc);
+                    }
+                    {   // x part of the candidate
+                        const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
+                        float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const int kl = Y / KS;
+                        mv_acc(acc, Wc_ + rank * Uy + col, Y, xin_s, ks * kl, (ks + 1) * kl);
+                        red_store(red2, tid, acc);
+                    }
                 }
                 __syncthreads();
                 const int unit = rank * Uy + i32;
@@ -474,7 +618,14 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
                 __syncthreads();
                 push_um(cl, rhd_s, stage, rank, Uy, tid);
                 cl.sync();
-                {
+                if (WFP) {
+                    for (int task = warp; task < 16; task += AT_NT / 32) {
+                        const int mt = task & 1, ks = task >> 1;
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        wf_seg(acc, wf(wf0 + 3, 2, 16, mt), 16, 8, ks, rhd_s, lane);
+                        wf_store(red, acc, 32, ks, mt, lane);
+                    }
+                } else {
                     const int ncols = Uy, col = tid % ncols, ks = tid / ncols, KS = AT_NT / ncols;
                     float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     const int kl = Y / KS;
@@ -495,11 +646,20 @@ __global__ void __launch_bounds__(AT_NT, 1) att_fwd_kernel(const AttArgs a) {
             }
             {   // r-frame mel projection (own MR/C columns, padded to 64 for the thread mapping)
                 const int MR = a.M * a.r, UO = MR / AT_C;
-                const int col = tid % 64, ks = tid / 64;
-                float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const int kl = Y / 4;
-                if (col < UO) mv_acc(acc, a.Wmel + rank * UO + col, MR, y2_s, ks * kl, (ks + 1) * kl);
-                red_store(red, tid, acc);
+                if (WFP) {
+                    for (int task = warp; task < 16; task += AT_NT / 32) {      // 4 m-tiles (UO columns padded to 64) x 4 k-slices
+                        const int mt = task & 3, ks = task >> 2;
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        wf_seg(acc, wf(WF_MEL, 4, 16, mt), 16, 4, ks, y2_s, lane);
+                        wf_store(red, acc, 64, ks, mt, lane);
+                    }
+                } else {
+                    const int col = tid % 64, ks = tid / 64;
+                    float acc[AT_R] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const int kl = Y / 4;
+                    if (col < UO) mv_acc(acc, a.Wmel + rank * UO + col, MR, y2_s, ks * kl, (ks + 1) * kl);
+                    red_store(red, tid, acc);
+                }
                 __syncthreads();
                 for (int idx = tid; idx < UO * R; idx += AT_NT) {
                     const int i = idx % UO, r = idx / UO, n = grp * R + r;
@@ -952,6 +1112,69 @@ static int att_launch(K kern, const AttArgs& a, bool bwd, cudaStream_t s) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     TACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     g_launch_count++;
+    return TACO_OK;
+}
+
+
+// ---- fragment-packed weights: host side ----------------------------------------------------------------------------------
+bool att_wfrag_supported(const AttArgs& a) {
+    return a.free_run && a.fast && a.SPK == 0 && a.E == 256 && a.A == 256 && a.HA == 256 && a.Z1 == 256 && a.Z == 128 && a.Y == 256 &&
+           a.M == 80 && (a.M * a.r) % AT_C == 0 && (a.M * a.r) / AT_C <= 64;
+}
+static void wf_table(const AttArgs& a, WfTable& tb) {
+    const int U32 = 32, MR = a.M * a.r, UO = MR / AT_C, Y = a.Y, HA = a.HA, E = a.E, Z = a.Z, Z1 = a.Z1, A = a.A, M = a.M;
+    auto one = [](const float* W, int ld, int U, int off, int row0, int K, int ncols, int valid) {
+        WfSpec s{}; s.WA = W; s.WB = W; s.ldA = ld; s.ldB = ld; s.UA = U; s.UB = U; s.offA = off; s.offB = off; s.split = ncols; s.row0 = row0; s.K = K; s.ncols = ncols; s.valid = valid;
+        return s;
+    };
+    // gate matrices: own r columns [rank*U, +U) then own u columns [H + rank*U, +U)
+    auto gates = [](const float* W, int ld, int U, int H, int row0, int K) {
+        WfSpec s{}; s.WA = W; s.WB = W; s.ldA = ld; s.ldB = ld; s.UA = U; s.UB = U; s.offA = 0; s.offB = H; s.split = U; s.row0 = row0; s.K = K; s.ncols = 2 * U; s.valid = 2 * U;
+        return s;
+    };
+    const float* W1 = a.W1x;                       // dense_1 kernel [M + E, Z1]: rows [0, M) take the frame, rows [M, M + E) the context
+    tb.s[WF_W1C] = one(W1, Z1, U32, 0, M, E, 32, 32);
+    tb.s[WF_W1X] = one(W1, Z1, U32, 0, 0, M, 32, 32);
+    tb.s[WF_W2] = one(a.W2, Z, 16, 0, 0, Z1, 16, 16);
+    tb.s[WF_WG_Z] = gates(a.Wg, 2 * HA, U32, HA, 0, Z);
+    tb.s[WF_WG_H] = gates(a.Wg, 2 * HA, U32, HA, Z, HA);
+    tb.s[WF_WC_Z] = one(a.Wc, HA, U32, 0, 0, Z, 32, 32);
+    tb.s[WF_WC_H] = one(a.Wc, HA, U32, 0, Z, HA, 32, 32);
+    {   // query columns, then the ha rows of the concat projection
+        WfSpec s{}; s.WA = a.Wq; s.ldA = A; s.UA = U32; s.offA = 0; s.WB = a.Wo; s.ldB = Y; s.UB = U32; s.offB = 0; s.split = 32; s.row0 = 0; s.K = HA; s.ncols = 64; s.valid = 64;
+        tb.s[WF_WQWO] = s;
+    }
+    tb.s[WF_WO_C] = one(a.Wo, Y, U32, 0, HA, E, 32, 32);
+    const float* Wg_[2] = {a.Wg1, a.Wg2}; const float* Wc_[2] = {a.Wc1, a.Wc2};
+    for (int l = 0; l < 2; l++) {
+        const int b = l ? WF_G2_GX : WF_G1_GX;
+        tb.s[b] = gates(Wg_[l], 2 * Y, U32, Y, 0, Y);
+        tb.s[b + 1] = gates(Wg_[l], 2 * Y, U32, Y, Y, Y);
+        tb.s[b + 2] = one(Wc_[l], Y, U32, 0, 0, Y, 32, 32);
+        tb.s[b + 3] = one(Wc_[l], Y, U32, 0, Y, Y, 32, 32);
+    }
+    tb.s[WF_MEL] = one(a.Wmel, MR, UO, 0, 0, Y, 64, UO);
+    long long off = 0;
+    for (int i = 0; i < WF_N; i++) {
+        tb.off[i] = off;
+        off += (long long)AT_C * (tb.s[i].ncols / 16) * ((tb.s[i].K + 15) / 16) * 32;
+    }
+    tb.off[WF_N] = off;
+}
+size_t att_wfrag_bytes(const AttArgs& a) {
+    if (!att_wfrag_supported(a)) return 0;
+    AttArgs b = a;
+    WfTable tb; wf_table(b, tb);
+    return (size_t)tb.off[WF_N] * sizeof(uint4);
+}
+// packs the step's weights into `buf` (att_wfrag_bytes) and points the arguments at the image
+int launch_att_wfrag_pack(AttArgs& a, void* buf, cudaStream_t s) {
+    TACO_REQUIRE(att_wfrag_supported(a) && buf, TACO_EINVAL, "attention: fragment-packed weights do not apply to this configuration");
+    WfTable tb; wf_table(a, tb);
+    wf_pack_kernel<<<dim3(64, WF_N), 256, 0, s>>>(tb, static_cast<uint4*>(buf));
+    TACO_CHECK_LAUNCH();
+    a.wfrag = buf;
+    for (int i = 0; i < WF_N; i++) a.wf_off[i] = tb.off[i];
     return TACO_OK;
 }
 

@@ -7,6 +7,7 @@
 // convention, so the kernels use the plain FFT and the caller-supplied initial phase is negated to match.
 #include "common.cuh"
 #include <cufft.h>
+#include <cstdlib>
 #include <new>
 
 namespace taco {
@@ -23,6 +24,9 @@ struct GlState {
     float* y = nullptr;          // [n_fft + hop*(max_frames-1)] untrimmed signal
     float* carry = nullptr;      // IIR chunk states
     size_t bytes = 0;
+    // The iteration loop (5 launches x n_iters of ~3 us kernels) is launch-bound: it is captured once per (T, n_iters) into a
+    // CUDA graph and replayed (TACO_GL_GRAPH=0 issues the launches one by one).
+    cudaGraphExec_t graph = nullptr; int graph_T = 0, graph_iters = -1; cudaStream_t capture_stream = nullptr;
 };
 
 #define TACO_CHECK_CUFFT(expr)                                                                    \
@@ -209,6 +213,8 @@ int taco_gl_create(taco_gl* out, int32_t n_fft, int32_t hop, int32_t win, int32_
 int taco_gl_destroy(taco_gl h) {
     if (!h) return TACO_OK;
     GlState& g = h->st;
+    if (g.graph) cudaGraphExecDestroy(g.graph);
+    if (g.capture_stream) cudaStreamDestroy(g.capture_stream);
     if (g.c2r) cufftDestroy(g.c2r);
     if (g.r2c) cufftDestroy(g.r2c);
     if (g.ana_r2c) cufftDestroy(g.ana_r2c);
@@ -230,6 +236,7 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int len = g.n_fft + L;
     if (g.planned_T != T) {
+        if (g.graph) { cudaGraphExecDestroy(g.graph); g.graph = nullptr; }       // the graph references the old plans
         if (g.c2r) { cufftDestroy(g.c2r); g.c2r = 0; }
         if (g.r2c) { cufftDestroy(g.r2c); g.r2c = 0; }
         int n[1] = {g.n_fft};
@@ -239,25 +246,46 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
         gl_wsum_kernel<<<cdiv(len, 256), 256, 0, s>>>(g.window, g.wsum, g.n_fft, g.hop, T, len);
         TACO_CHECK_LAUNCH();
     }
-    TACO_CHECK_CUFFT(cufftSetStream(g.c2r, s));
-    TACO_CHECK_CUFFT(cufftSetStream(g.r2c, s));
     const long long nb = (long long)T * g.nbins;
     gl_init_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, s>>>(linear_spec, init_phase, g.mag, g.spec, nb, min_level_db, ref_level_db, power);
     TACO_CHECK_LAUNCH();
     const float inv_nfft = 1.0f / (float)g.n_fft;
-    for (int it = 0; it <= n_iters; it++) {
-        TACO_CHECK_CUFFT(cufftExecC2R(g.c2r, g.spec, g.frames));
-        g_launch_count++;
-        gl_ola_kernel<<<cdiv(len, 256), 256, 0, s>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
-        TACO_CHECK_LAUNCH();
-        if (it == n_iters) break;
-        gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, s>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
-        TACO_CHECK_LAUNCH();
-        TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
-        g_launch_count++;
-        gl_phase_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, s>>>(g.spec, g.mag, nb);
-        TACO_CHECK_LAUNCH();
+    auto iterate = [&](cudaStream_t st) -> int {
+        TACO_CHECK_CUFFT(cufftSetStream(g.c2r, st));
+        TACO_CHECK_CUFFT(cufftSetStream(g.r2c, st));
+        for (int it = 0; it <= n_iters; it++) {
+            TACO_CHECK_CUFFT(cufftExecC2R(g.c2r, g.spec, g.frames));
+            gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
+            TACO_CHECK_CUDA(cudaGetLastError());
+            if (it == n_iters) break;
+            gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, st>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
+            TACO_CHECK_CUDA(cudaGetLastError());
+            TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
+            gl_phase_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, st>>>(g.spec, g.mag, nb);
+            TACO_CHECK_CUDA(cudaGetLastError());
+        }
+        return TACO_OK;
+    };
+    static const bool use_graph = [] { const char* e = getenv("TACO_GL_GRAPH"); return !(e && e[0] == '0'); }();
+    if (use_graph) {
+        if (!g.graph || g.graph_T != T || g.graph_iters != n_iters) {
+            if (g.graph) { cudaGraphExecDestroy(g.graph); g.graph = nullptr; }
+            if (!g.capture_stream) TACO_CHECK_CUDA(cudaStreamCreateWithFlags(&g.capture_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            TACO_CHECK_CUDA(cudaStreamBeginCapture(g.capture_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = iterate(g.capture_stream);
+            const cudaError_t ce = cudaStreamEndCapture(g.capture_stream, &graph);
+            if (rc != TACO_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            TACO_CHECK_CUDA(ce);
+            TACO_CHECK_CUDA(cudaGraphInstantiate(&g.graph, graph, 0));
+            TACO_CHECK_CUDA(cudaGraphDestroy(graph));
+            g.graph_T = T; g.graph_iters = n_iters;
+        }
+        TACO_CHECK_CUDA(cudaGraphLaunch(g.graph, s));
+    } else {
+        TACO_TRY(iterate(s));
     }
+    g_launch_count += 5LL * n_iters + 2;           // kernels of the loop (cuFFT counts as one launch per transform)
     // inverse pre-emphasis on the trimmed signal
     const int nchunks = cdiv(L, IIR_CHUNK);
     iir_local_kernel<<<cdiv(nchunks, 128), 128, 0, s>>>(g.y + g.n_fft / 2, wav_out, g.carry, L, preemphasis);

@@ -119,8 +119,13 @@ struct AttArgs {
     // pre-built operand images of the fast kernels (att_fast.cu: launch_att_fast_pack), or NULL: weight slices per cluster
     // rank and key / memory slices per CTA, in the kernels' shared-memory layout, pulled in with bulk async copies
     const uint8_t *img_w, *img_km;
+    // free-running decoder of the tensor-core modes: the step's weights as bf16 mma fragments (attention.cu: launch_att_wfrag_pack)
+    const void* wfrag; long long wf_off[18];
 };
 int launch_att_fwd(const AttArgs& a, cudaStream_t s);
+bool att_wfrag_supported(const AttArgs& a);
+size_t att_wfrag_bytes(const AttArgs& a);
+int launch_att_wfrag_pack(AttArgs& a, void* buf, cudaStream_t s);
 int launch_att_bwd(const AttArgs& a, cudaStream_t s);
 bool att_fast_supported(const AttArgs& a);
 int launch_att_fast_fwd(const AttArgs& a, cudaStream_t s);   // TACO_ENOTSUP when 16-CTA clusters cannot be launched

@@ -364,6 +364,14 @@ void Model::plan(const Shape& s) {
         add("dec/y0", {rows, Y}); add("dec/y1", {rows, Y}); add("dec/y2", {rows, Y});
         add("dec/g1_gx", {rows, 3 * Y}); add("dec/g2_gx", {rows, 3 * Y});
         add("alignments", {N, s.Ti, s.Td});
+        if (c.precision != TACO_PREC_FP32) {
+            // free-running decoder (inference, rnn_decoder_test_mode): fragment-packed bf16 weights of one decoder step
+            AttArgs pa{};
+            pa.free_run = 1; pa.fast = 1; pa.SPK = (int)SPK; pa.E = (int)E; pa.A = (int)A; pa.HA = (int)HA; pa.Z1 = (int)Z1; pa.Z = (int)Z; pa.Y = (int)Y;
+            pa.M = (int)M; pa.r = (int)r;
+            const size_t wb = att_wfrag_bytes(pa);
+            if (wb) add("dec/wfrag", {(int64_t)(wb / 4)});
+        }
         if (tr) {
             add("dec/s_z1", {rows, Z1}); add("dec/s_z", {rows, Z});
             for (const char* nm : {"dec/s_r", "dec/s_u", "dec/s_c", "dec/s_haprev", "dec/s_ha"}) add(nm, {rows, HA});

@@ -198,7 +198,7 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     if (free_run) {
         // the whole decoder step (prenet x-part, both residual GRUs, mel projection) runs inside the recurrence kernel
         const CbhgGeom& g = m.post;
-        a.free_run = 1; a.M = D.M; a.r = D.r; a.fast = 0;
+        a.free_run = 1; a.M = D.M; a.r = D.r;
         a.W1x = m.P("dec_prenet/dense_1/kernel"); a.b1 = m.P("dec_prenet/dense_1/bias");
         a.Wg1 = m.P("dec_gru_1/gates_kernel"); a.bg1 = m.P("dec_gru_1/gates_bias"); a.Wc1 = m.P("dec_gru_1/cand_kernel"); a.bc1 = m.P("dec_gru_1/cand_bias");
         a.Wg2 = m.P("dec_gru_2/gates_kernel"); a.bg2 = m.P("dec_gru_2/gates_bias"); a.Wc2 = m.P("dec_gru_2/cand_kernel"); a.bc2 = m.P("dec_gru_2/cand_bias");
@@ -206,6 +206,8 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         a.h1_0 = h1; a.h2_0 = h2;
         a.mel_out = m.W("post_cbhg/xin_p") + (long long)g.PL * D.M; a.mel_bs = (long long)g.Tp * D.M;
         a.y0 = nullptr;
+        // tensor-core modes: the step's weights are packed once per call as bf16 mma fragments (attention.cu)
+        if (att_wfrag_supported(a) && m.has_region("dec/wfrag")) TACO_TRY(launch_att_wfrag_pack(a, m.W("dec/wfrag"), s));
         return prof_launch_att(a, false, s);
     }
     if (training) {
