@@ -138,14 +138,15 @@ def run_ours(args):
     hp = tb.hparams.override(reduction_factor=CFG["r"], batch_size=CFG["N"])
     eng = Engine(hp, 1, precision=args.precision, device=local, seed=4321)
     host = synth_batch(rank)
+    if args.targets == "bf16":
+        # linear targets travel (and stay) as bf16: 105 -> 52 MB of host->device copies per step; the loss is taken against them
+        host["linear_targets"] = host["linear_targets"].to(torch.bfloat16)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     dev = {k: v.to(eng.dev) for k, v in host.items()}
 
-    def allreduce(flat):
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            return 1.0 / world
-        return 1.0
+    # the step's one collective: gradient all-reduce in two buckets, the larger one beside the encoder's backward pass (dist.py)
+    OverlappedAllReduce = import_module("multi-speaker-tacotron-tensorflow_b200.dist").OverlappedAllReduce
+    allreduce = OverlappedAllReduce(eng)
 
     def barrier():
         if world > 1:
@@ -253,7 +254,7 @@ def run_ours(args):
         eng.close()
         del dev, bufs, flush
         torch.cuda.empty_cache()
-        extra["c3"] = leg_c3(tb, Engine, args.precision, local, rank, world, allreduce, barrier)
+        extra["c3"] = leg_c3(tb, Engine, args.precision, local, rank, world, OverlappedAllReduce, barrier, args.targets)
         extra["c5"] = leg_c5(tb, Engine, args.precision, local, rank, world, barrier)
 
     frames = world * CFG["N"] * CFG["T_out"] * args.steps
@@ -269,6 +270,8 @@ def run_ours(args):
             "dtype": DTYPE_LABEL[args.precision], "dtype_note": DTYPE_NOTE[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "global_batch": world * CFG["N"], "parallelism": "dp%d" % world, "l2": "flushed between timed steps (160 MB write)",
+                       "linear_targets": args.targets + (" (stored and copied as bf16; the loss is taken against the bf16 values)" if args.targets == "bf16" else ""),
+                       "collective": "one gradient all-reduce per step (NCCL), in two buckets: decoder/post-net/linear gradients beside the encoder's backward pass",
                        "timing": "CUDA events per step on the compute stream, max over ranks"},
             "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96,
                     "note": "Engine.train_step with inputs staged from pinned host memory (double-buffered copy stream, the next batch's copy issued behind the forward pass) + every step's loss read back to the host (pinned, one step of run-ahead)"},
@@ -310,7 +313,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def leg_c3(tb, Engine, precision, local, rank, world, allreduce, barrier, steps=5, warmup=3):
+def leg_c3(tb, Engine, precision, local, rank, world, make_allreduce, barrier, targets, steps=5, warmup=3):
     """BASELINE.json configs[2]: the same training step with model_type=deepvoice, 3 speakers (batch 32 per GPU) - device-timed."""
     import torch
     import torch.distributed as dist
@@ -319,7 +322,10 @@ def leg_c3(tb, Engine, precision, local, rank, world, allreduce, barrier, steps=
     b = synth_batch(rank)
     g = torch.Generator().manual_seed(99 + rank)
     b["speaker_id"] = torch.randint(0, 3, (CFG["N"],), generator=g, dtype=torch.int32)
+    if targets == "bf16":
+        b["linear_targets"] = b["linear_targets"].to(torch.bfloat16)
     dev = {k: v.to(eng.dev) for k, v in b.items()}
+    allreduce = make_allreduce(eng)
     for _ in range(warmup):
         eng.train_step(dev, allreduce=allreduce)
     barrier()
@@ -511,12 +517,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TACO_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--targets", default=None, choices=["fp32", "bf16"], help="storage type of the linear-spectrogram targets (default: bf16 in bf16 mode)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-synth", dest="synth", action="store_false", help="skip the C4 synthesis real-time-factor leg (N=1 only)")
     ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the C3 (deepvoice training) and C5 (batched inference) legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.targets is None:
+        args.targets = "bf16" if args.precision == "bf16" else "fp32"
     if args.impl == "reference":
         run_reference(args)
     else:

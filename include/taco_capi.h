@@ -117,6 +117,9 @@ typedef struct taco_batch {
     const float*   manual_alignments; /* [N,T_dec,T_in] or NULL (rnn_wrappers.py:313-317) */
     int32_t        decoder_steps;  /* inference: number of steps (max_iters); training: 0 => T_out/r */
     int32_t        rnn_decoder_test_mode; /* helpers.py:63-66 */
+    int32_t        linear_targets_bf16;   /* 1: linear_targets points at bf16 values (same [N,T_out,num_freq] layout): halves the
+                                           * host->device bytes of a step (105 -> 52 MB at batch 32 x 800 frames); the loss is then
+                                           * taken against the bf16-rounded targets */
 } taco_batch;
 
 /* Scalars produced by a step (device-resident copy lives in the workspace; this is the host copy). */
@@ -172,6 +175,16 @@ int taco_backward(taco_model m, const taco_batch* b, void* stream);
 int taco_optimizer_step(taco_model m, int64_t global_step, int64_t adam_step, int32_t is_randomly_initialized,
                         float initial_learning_rate, int32_t decay_mode,
                         float beta1, float beta2, float grad_scale, void* stream);
+
+/* ---- data parallel (replaces nothing in the reference, which is single-device; SURVEY.md 8e: ONE gradient all-reduce per step) ----
+ * The flat gradient is reduced in two buckets so that the larger one overlaps the encoder's backward pass:
+ *   bucket 0 ("early"): decoder, post-net and linear-projection gradients = the tail [offset, offset + numel) of the flat buffer,
+ *                       complete when the decoder's backward pass and its weight-gradient leaves are;
+ *   bucket 1 ("late") : embedding, speaker and encoder gradients = the head of the buffer, complete when taco_backward is.
+ * taco_dp_wait_bucket makes `stream` (the caller's communication stream) wait for a bucket of the backward pass that was
+ * enqueued last; the caller then issues its all-reduce (NCCL) on that stream and orders taco_optimizer_step behind it. */
+int taco_dp_bucket(taco_model m, int32_t bucket, int64_t* offset, int64_t* numel);
+int taco_dp_wait_bucket(taco_model m, int32_t bucket, void* stream);
 
 /* Copies the device scalars to host (synchronises the stream). */
 int taco_read_scalars(taco_model m, taco_step_scalars* out, void* stream);

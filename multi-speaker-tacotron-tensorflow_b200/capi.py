@@ -45,6 +45,7 @@ class TacoBatch(C.Structure):
         ("inputs", C.c_void_p), ("input_lengths", C.c_void_p), ("speaker_id", C.c_void_p),
         ("mel_targets", C.c_void_p), ("linear_targets", C.c_void_p), ("loss_coeff", C.c_void_p),
         ("manual_alignments", C.c_void_p), ("decoder_steps", C.c_int32), ("rnn_decoder_test_mode", C.c_int32),
+        ("linear_targets_bf16", C.c_int32),
     ]
 
 
@@ -86,6 +87,8 @@ _SIGNATURES = {
     "taco_backward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p]),
     "taco_optimizer_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
+    "taco_dp_bucket": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "taco_dp_wait_bucket": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "taco_read_scalars": (C.c_int, [C.c_void_p, C.POINTER(TacoStepScalars), C.c_void_p]),
     "taco_copy_scalars_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "taco_finish_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TacoStepScalars)]),

@@ -651,7 +651,7 @@ int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaS
 // scalars[0] += sum |d|*coeff*w ; scalars[1] += sum |d| (unweighted, all bins) ; scalars[2] += sum |d| over the priority band.
 // grad[(n,t),c] = sign(out - tgt) * coeff[n] * (w_all + w_band*[lo<=c<hi])     (pad rows of grad untouched)
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
-                               const float* __restrict__ tgt, const float* __restrict__ coeff,
+                               const float* __restrict__ tgt, const bf16* __restrict__ tgt16, const float* __restrict__ coeff,
                                float* __restrict__ grad, bf16* __restrict__ grad16, long long grad_bs, long long grad_ts,
                                int N, int T, int C, float w_all, float w_band, int lo, int hi, double* __restrict__ scalars) {
     // block = (tx column lanes) x (ty rows); rows (n,t) are strided over the grid, columns over tx: no per-element division
@@ -660,7 +660,8 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
     for (int row = blockIdx.x * ty + threadIdx.y; row < rows; row += gridDim.x * ty) {
         const int n = row / T, t = row - n * T;
         const float* op = out + n * out_bs + t * out_ts;
-        const float* tp = tgt + (long long)row * C;
+        const float* tp = tgt ? tgt + (long long)row * C : nullptr;
+        const bf16* tp16 = tgt16 ? tgt16 + (long long)row * C : nullptr;
         float* gp = grad ? grad + n * grad_bs + t * grad_ts : nullptr;
         bf16* gp16 = grad16 ? grad16 + n * grad_bs + t * grad_ts : nullptr;
         const float cf = coeff ? __ldg(coeff + n) : 1.f;
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int c = c0 + e * tx; const bool ok = c < C;
-                ov[e] = ok ? op[c] : 0.f; tv[e] = ok ? __ldg(tp + c) : 0.f;
+                ov[e] = ok ? op[c] : 0.f; tv[e] = ok ? (tp16 ? __bfloat162float(tp16[c]) : __ldg(tp + c)) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) {
@@ -702,11 +703,12 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 }
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
-                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16) {
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16, int tgt_is_bf16) {
     int tx = 32; while (tx < C && tx < 256) tx <<= 1;
     const int ty = 256 / tx;
     int blocks = cdiv(N * T, ty); if (blocks > 148 * 8) blocks = 148 * 8;
-    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt, coeff, grad, static_cast<bf16*>(grad16), grad_bs, grad_ts,
+    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt_is_bf16 ? nullptr : tgt, tgt_is_bf16 ? reinterpret_cast<const bf16*>(tgt) : nullptr,
+                                                   coeff, grad, static_cast<bf16*>(grad16), grad_bs, grad_ts,
                                                    N, T, C, w_all, w_band, lo, hi, scalars);
     TACO_CHECK_LAUNCH();
     return TACO_OK;

@@ -44,7 +44,8 @@ int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s);
 int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
-                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16 = nullptr);
+                   float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16 = nullptr,
+                   int tgt_is_bf16 = 0 /* tgt points at bf16 values */);
 
 // gru.cu — cluster-persistent GRU recurrences (TF GRUCell semantics)
 struct GruArgs {

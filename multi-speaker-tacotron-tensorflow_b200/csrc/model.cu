@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 
 namespace taco {
 
@@ -67,7 +68,7 @@ struct StreamSet {
 struct DevSched {
     StreamSet set[2];                   // 0: chain (high priority), 1: leaves (low priority)
     cudaStream_t crit = nullptr, side = nullptr;
-    cudaEvent_t ev_in, ev_out, ev_fork, ev_side, ev_prep, ev_leaf, ev_img[2];
+    cudaEvent_t ev_in, ev_out, ev_fork, ev_side, ev_prep, ev_leaf, ev_img[2], ev_early[2];     // ev_early: gradients of the early bucket complete (chain / leaves)
     bool ready = false;
     WaveCtx wave; bool wave_ready = false;
 };
@@ -106,7 +107,7 @@ static int sched_init() {
     }
     TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.crit, cudaStreamNonBlocking, hi));
     TACO_CHECK_CUDA(cudaStreamCreateWithPriority(&D.side, cudaStreamNonBlocking, lo));
-    for (cudaEvent_t* e : {&D.ev_in, &D.ev_out, &D.ev_fork, &D.ev_side, &D.ev_prep, &D.ev_leaf, &D.ev_img[0], &D.ev_img[1]})
+    for (cudaEvent_t* e : {&D.ev_in, &D.ev_out, &D.ev_fork, &D.ev_side, &D.ev_prep, &D.ev_leaf, &D.ev_img[0], &D.ev_img[1], &D.ev_early[0], &D.ev_early[1]})
         TACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (g_overlap < 0) {
         const char* env = getenv("TACO_OVERLAP");
@@ -657,7 +658,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     }
     const int Fp = (F + 63) / 64 * 64;
     TACO_TRY(launch_l1_loss(m.W("linear_buf"), (long long)To * Fp, Fp, b->linear_targets, b->loss_coeff,
-                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear")));
+                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear"), b->linear_targets_bf16));
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
                             m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
                             (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
@@ -694,6 +695,12 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     TACO_TRY(launch_axpy(m.W("post_cbhg/d_xin_p"), m.W("post_cbhg/d_mel_loss"), 1.f, (long long)g.rows * M, s));
     prof_mark("bwd:decoder", s);
     TACO_TRY(decoder_backward(m, b, s));
+    // Data parallel: every gradient of the "early" bucket (decoder, post-net, linear: the tail of the flat buffer) is enqueued by
+    // now - on this stream and, for the leaves, on the side stream.  taco_dp_wait_bucket lets a communication stream start that
+    // bucket's all-reduce here, beside the encoder's backward pass.
+    TACO_CHECK_CUDA(cudaEventRecord(ds().ev_early[0], s));
+    TACO_CHECK_CUDA(cudaEventRecord(ds().ev_early[1], overlap_on() ? ds().side : s));
+    m.early_recorded = true;
     prof_mark("bwd:enc_cbhg", s);
     const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
     TACO_TRY(cbhg_backward(m, m.enc, b->input_lengths, spk, spk, s));
@@ -803,6 +810,19 @@ int taco_bind_params(taco_model h, const taco_param_entry* table, int32_t n_entr
     }
     m.params = params; m.grads = grads; m.adam_m = adam_m; m.adam_v = adam_v; m.bn_state = bn_state;
     m.n_trainable = n_trainable; m.n_state = n_state;
+    // data-parallel buckets: the gradients of embedding / speaker / encoder tensors are produced last and sit at the head of the
+    // flat buffer (params.py); everything behind them forms the early bucket.  If a caller orders the table differently the
+    // early bucket is empty and the whole gradient is reduced after the backward pass.
+    {
+        auto late = [](const std::string& n) { return n.rfind("embedding", 0) == 0 || n.rfind("speaker", 0) == 0 || n.rfind("enc_", 0) == 0; };
+        int64_t first_early = n_trainable, end_late = 0;
+        for (const auto& kv : m.table) {
+            if (!kv.second.trainable) continue;
+            if (late(kv.first)) end_late = std::max<int64_t>(end_late, kv.second.offset + kv.second.numel);
+            else first_early = std::min<int64_t>(first_early, kv.second.offset);
+        }
+        m.early_offset = (first_early >= end_late) ? first_early : n_trainable;
+    }
     // every tensor the kernels will dereference must be present with the expected size
     const taco_config& c = m.cfg;
     if (c.precision == TACO_PREC_BF16)
@@ -1006,6 +1026,26 @@ int taco_finish_scalars(taco_model h, const void* pinned_raw, taco_step_scalars*
     double sc[8]; float scf[8];
     memcpy(sc, raw, sizeof sc); memcpy(scf, raw + sizeof sc, sizeof scf);
     finish_scalars(h->m, sc, scf, out);
+    return TACO_OK;
+}
+
+int taco_dp_bucket(taco_model h, int32_t bucket, int64_t* offset, int64_t* numel) {
+    TACO_REQUIRE(h && offset && numel && (bucket == 0 || bucket == 1), TACO_EINVAL, "taco_dp_bucket: bad argument");
+    const Model& m = h->m;
+    TACO_REQUIRE(m.grads != nullptr, TACO_ESTATE, "taco_dp_bucket: parameters not bound");
+    if (bucket == 0) { *offset = m.early_offset; *numel = m.n_trainable - m.early_offset; }
+    else { *offset = 0; *numel = m.early_offset; }
+    return TACO_OK;
+}
+
+int taco_dp_wait_bucket(taco_model h, int32_t bucket, void* stream) {
+    TACO_REQUIRE(h && (bucket == 0 || bucket == 1), TACO_EINVAL, "taco_dp_wait_bucket: bad argument");
+    TACO_ON_DEVICE(h->m.cfg.device);
+    if (bucket == 1) return TACO_OK;          // complete once taco_backward has joined its streams into the caller's
+    TACO_REQUIRE(h->m.early_recorded, TACO_ESTATE, "taco_dp_wait_bucket: call taco_backward first");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(s, ds().ev_early[0], 0));
+    TACO_CHECK_CUDA(cudaStreamWaitEvent(s, ds().ev_early[1], 0));
     return TACO_OK;
 }
 

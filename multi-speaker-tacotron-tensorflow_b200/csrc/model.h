@@ -37,6 +37,8 @@ struct Model {
     taco_config cfg;
     float* params = nullptr; float* grads = nullptr; float* adam_m = nullptr; float* adam_v = nullptr; float* bn_state = nullptr;
     int64_t n_trainable = 0, n_state = 0;
+    int64_t early_offset = 0;        // data-parallel buckets: gradients [early_offset, n_trainable) are complete before the encoder's backward pass
+    bool early_recorded = false;
     std::unordered_map<std::string, Entry> table;
 
     char* ws = nullptr; size_t ws_bytes = 0;

@@ -165,7 +165,7 @@ class DataFeeder(threading.Thread):
         self.is_multi_speaker = len(self.data_dirs) > 1                                             # :149
         depth = depth or (8 if data_type == "train" else 1)                                         # :156-157
         self._queue: "queue.Queue" = queue.Queue(maxsize=depth)
-        self._stop = threading.Event()
+        self._stop_event = threading.Event()
         self._error: Optional[BaseException] = None
         self._device = device
         self._slots: List[dict] = []
@@ -218,11 +218,11 @@ class DataFeeder(threading.Thread):
         self.start()
 
     def stop(self):
-        self._stop.set()
+        self._stop_event.set()
 
     def run(self):                                                                                  # :202-208
         try:
-            while not self._stop.is_set():
+            while not self._stop_event.is_set():
                 self._enqueue_next_group()
         except BaseException as e:      # surfaced to the consumer by next_batch()
             self._error = e
@@ -255,7 +255,7 @@ class DataFeeder(threading.Thread):
         r = self._hp.reduction_factor
         for batch in batches:
             slot = None
-            while slot is None and not self._stop.is_set():
+            while slot is None and not self._stop_event.is_set():
                 try:
                     slot = self._free.get(timeout=0.1)
                 except queue.Empty:
@@ -264,7 +264,7 @@ class DataFeeder(threading.Thread):
                 return
             feed = prepare_batch(batch, r, self.rng, self.data_type, out=slot["numpy"], multi_speaker=self.is_multi_speaker)
             shapes = {k: v.shape for k, v in feed.items()}
-            while not self._stop.is_set():
+            while not self._stop_event.is_set():
                 try:
                     self._queue.put((slot, shapes), timeout=0.1)
                     break

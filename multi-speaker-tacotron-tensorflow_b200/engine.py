@@ -140,7 +140,10 @@ class Engine:
     def forward(self, inputs, input_lengths, speaker_id=None, mel_targets=None, linear_targets=None, loss_coeff=None,
                 decoder_steps: int = 0, rnn_decoder_test_mode: bool = False, manual_alignments=None):
         inputs, input_lengths, speaker_id = self._i32(inputs), self._i32(input_lengths), self._i32(speaker_id)
-        mel_targets, linear_targets = self._f32(mel_targets), self._f32(linear_targets)
+        # linear targets may arrive as bfloat16 (half the host->device bytes of a step); everything else is fp32
+        lin16 = linear_targets is not None and linear_targets.dtype == torch.bfloat16
+        mel_targets = self._f32(mel_targets)
+        linear_targets = linear_targets.to(device=self.dev).contiguous() if lin16 else self._f32(linear_targets)
         loss_coeff, manual_alignments = self._f32(loss_coeff), self._f32(manual_alignments)
         N, T_in = inputs.shape
         training = linear_targets is not None
@@ -154,6 +157,7 @@ class Engine:
         b.manual_alignments = ptr(manual_alignments)
         b.decoder_steps = decoder_steps
         b.rnn_decoder_test_mode = 1 if rnn_decoder_test_mode else 0
+        b.linear_targets_bf16 = 1 if lin16 else 0
         self._batch = b
         self._keep = [inputs, input_lengths, speaker_id, mel_targets, linear_targets, loss_coeff, manual_alignments]
         capi.check(self.lib.taco_forward(self._h, C.byref(b), self._stream()))

@@ -146,10 +146,23 @@ class HParams:
         return new
 
     def parse(self, spec: str) -> "HParams":
-        """``name=value,name=value`` overrides, values parsed as JSON scalars."""
+        """``name=value,name=value`` overrides, values parsed as JSON (lists such as ``enc_proj_sizes=[128,128]`` included:
+        only commas outside brackets separate items)."""
         if not spec:
             return self
-        for item in spec.split(","):
+        items, depth, cur = [], 0, ""
+        for ch in spec:
+            if ch in "[{(":
+                depth += 1
+            elif ch in "]})":
+                depth -= 1
+            if ch == "," and depth == 0:
+                items.append(cur); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            items.append(cur)
+        for item in items:
             name, _, raw = item.partition("=")
             name = name.strip()
             if name not in self._v:

@@ -125,11 +125,17 @@ def train(log_dir, config, hp=hparams):
     elif config.initialize_path:
         restore = get_most_recent_checkpoint(config.initialize_path)
 
+    restored_state = None
+    if restore and config.load_path:
+        # the reference starts its feeders from the restored global_step (train.py:207-210): it decides the initial
+        # data-greedy / equal-ratio sampling phase, so a resumed run must not replay it
+        restored_state = load_any(restore, hp, num_speakers)
+        start_step = int(restored_state.get("global_step", 0))
     train_feeder.start_in_session(None, start_step)
     if test_feeder is not None:
         test_feeder.start_in_session(None, start_step)
     time_window, loss_window = ValueWindow(100), ValueWindow(100)
-    allreduce = dp.allreduce_sum_ if world > 1 else None
+    allreduce = None        # data parallel: created with the engine (two-bucket all-reduce, dist.OverlappedAllReduce)
     step = 0
     try:
         batch = train_feeder.next_device_batch()
@@ -142,7 +148,7 @@ def train(log_dir, config, hp=hparams):
             model.initialize(batch["inputs"], batch["input_lengths"], num_speakers, batch.get("speaker_id"), batch["mel_targets"],
                              batch["linear_targets"], batch["loss_coeff"], is_randomly_initialized=is_randomly_initialized)
             if first and restore:
-                sd = load_any(restore, hp, num_speakers)        # our .pt state or a reference TensorFlow checkpoint
+                sd = restored_state if restored_state is not None else load_any(restore, hp, num_speakers)    # our .pt state or a reference TensorFlow checkpoint
                 model.load_state_dict(sd, reset_step=bool(config.initialize_path))         # train.py:189-205
                 log(("Resuming from checkpoint: %s" if config.load_path else "Initialized from checkpoint: %s") % restore, slack=True)
                 if config.initialize_path:
@@ -155,6 +161,8 @@ def train(log_dir, config, hp=hparams):
             fwd_done = torch.cuda.Event(); fwd_done.record(torch.cuda.current_stream())
             nxt = train_feeder.next_device_batch(after=fwd_done, defer_wait=True)   # the next batch's DMA runs beside the backward pass
             model.add_loss()
+            if world > 1 and allreduce is None:
+                allreduce = dp.OverlappedAllReduce(model.engine)
             model.add_optimizer(allreduce=allreduce)
             step = model.engine.global_step                 # value AFTER the update, as sess.run([global_step, ...]) returns
             loss = model.loss_without_coeff

@@ -39,9 +39,10 @@ def main():
     spk = lambda r: torch.tensor([0, 2, 1, r % S], dtype=torch.int32)
     mine = dict(batch(rank), speaker_id=spk(rank))
 
-    def allreduce(flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        return 1.0 / world
+    # the product's collective: two-bucket all-reduce, the early bucket beside the encoder's backward pass (dist.py)
+    from importlib import import_module
+    allreduce = import_module("multi-speaker-tacotron-tensorflow_b200.dist").OverlappedAllReduce(eng)
+    assert allreduce.early[0] > 0 and allreduce.early[1] > 0 and sum(allreduce.early) == eng.layout.n_trainable
 
     first_grad = None
     for i in range(steps):

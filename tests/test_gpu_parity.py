@@ -614,6 +614,28 @@ def test_manual_attention_override_vs_oracle(tb, hp5, prec):
     eng.close()
 
 
+def test_bf16_linear_targets_equal_the_oracle_on_the_same_rounded_targets(tb, hp5):
+    """taco_batch.linear_targets_bf16: the linear-spectrogram targets travel as bf16 (half the host->device bytes of a step).
+    On IDENTICAL inputs - the oracle fed with the bf16-rounded targets - loss and gradients match as in every fp32-mode test."""
+    import make_golden as mg
+    named = mg.golden_params(hp5, seed=31)
+    b = _batch(3, 13, 20, [13, 9, 5])
+    lin16 = b["linear_targets"].to(torch.bfloat16)
+    rb = dict(b, linear_targets=lin16.float())
+    ref_out, ref_ls, ref_g = _oracle_step(named, hp5, rb)
+    eng = tb.Engine(hp5, 1, precision="fp32", named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], None, b["mel_targets"], lin16, b["loss_coeff"])
+    _check_outputs(out, ref_out, TOL["fp32"])
+    eng.backward()
+    sc = eng.scalars()
+    assert abs(sc["loss"] - ref_ls["loss"]) <= 1e-5 and abs(sc["linear_loss"] - ref_ls["linear_loss"]) <= 1e-5
+    exact = _oracle_step(named, hp5, b)[1]
+    assert abs(exact["linear_loss"] - ref_ls["linear_loss"]) > 1e-6            # the rounding is visible: the test distinguishes the two
+    cos, na, nb = _cosine(eng.named_gradients(), ref_g, sorted(ref_g))
+    assert cos >= 0.99999 and abs(na - nb) <= 1e-4 * nb
+    eng.close()
+
+
 def test_prioritize_loss_band_vs_oracle(tb):
     """prioritize_loss (tacotron.py:283-295): 0.5*mean|.| over all bins + 0.5*mean|.| over the 165 Hz..5 kHz band."""
     hp = tb.hparams.override(reduction_factor=5, prioritize_loss=True)

@@ -400,3 +400,23 @@ def test_manual_attention_second_pass_matches_the_reference_indexing(tb):
     assert np.array_equal(alignments_T, np.transpose(alignments, [0, 2, 1]))   # the input is not modified
     with pytest.raises(NotImplementedError, match="np.pow"):
         syn.manual_alignments_from(alignments, 2)
+
+
+def test_hparams_parse_keeps_list_values_and_feeder_thread_joins(tb, tmp_path):
+    hp = tb.hparams.override()
+    hp.parse("enc_proj_sizes=[128,128],reduction_factor=5,post_proj_sizes=[256, 80]")
+    assert hp.enc_proj_sizes == [128, 128] and hp.post_proj_sizes == [256, 80] and hp.reduction_factor == 5
+    with pytest.raises(KeyError):
+        hp.parse("no_such_hparam=1")
+    # threading.Thread has a private _stop() on Python 3.12: the feeder's stop flag must not shadow it (join() would raise)
+    from importlib import import_module
+    df = import_module("multi-speaker-tacotron-tensorflow_b200.datasets.datafeeder")
+    import types
+    d = _write_examples(tmp_path, "spk", 24, np.random.RandomState(0))
+    feeder = df.DataFeeder([d], tb.hparams.override(reduction_factor=5, initial_phase_step=0), types.SimpleNamespace(random_seed=1, skip_path_filter=False),
+                           batches_per_group=2, data_type="train", batch_size=4, log=lambda *_: None)
+    assert not callable(getattr(feeder, "_stop_event", None)) and callable(feeder._stop)
+    feeder.start_in_session(None, 0)
+    feeder.stop()
+    feeder.join(timeout=30)
+    assert not feeder.is_alive()
