@@ -133,10 +133,11 @@ int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* 
 
 // BN apply.  mode 0: out = bn(x); mode 1: out = max(bn(x[t]), bn(x[t+1])) (maxpool);
 // optional residual res[m,:] and per-batch-row vector rowvec[n,:] are added after.  Pad rows -> 0.
+template <bool IN16>
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ res, const float* __restrict__ rowvec,
-                                float* __restrict__ out, bf16* __restrict__ out16, int N, int T, int Tp, int PL, int C, int mode) {
+                                float* __restrict__ out, bf16* __restrict__ out16, const bf16* __restrict__ x16, int N, int T, int Tp, int PL, int C, int mode) {
     const int c4 = C / 4;
     long long total = (long long)N * Tp * c4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -148,11 +149,11 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
             float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
             float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
             float4 b = __ldg(reinterpret_cast<const float4*>(beta) + cq);
-            float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+            float4 v = IN16 ? ld_bf16x4(x16 + 4 * i) : __ldg(reinterpret_cast<const float4*>(x) + i);
             o.x = (v.x - mu.x) * rs.x * g.x + b.x; o.y = (v.y - mu.y) * rs.y * g.y + b.y;
             o.z = (v.z - mu.z) * rs.z * g.z + b.z; o.w = (v.w - mu.w) * rs.w * g.w + b.w;
             if (mode == 1 && t + 1 < T) {
-                float4 w = __ldg(reinterpret_cast<const float4*>(x) + i + c4);
+                float4 w = IN16 ? ld_bf16x4(x16 + 4 * (i + c4)) : __ldg(reinterpret_cast<const float4*>(x) + i + c4);
                 o.x = fmaxf(o.x, (w.x - mu.x) * rs.x * g.x + b.x); o.y = fmaxf(o.y, (w.y - mu.y) * rs.y * g.y + b.y);
                 o.z = fmaxf(o.z, (w.z - mu.z) * rs.z * g.z + b.z); o.w = fmaxf(o.w, (w.w - mu.w) * rs.w * g.w + b.w);
             }
@@ -170,9 +171,13 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16) {
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16, const void* x16) {
     TACO_REQUIRE(out || out16, TACO_EINVAL, "bn_apply: no output");
-    bn_apply_kernel<<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, static_cast<bf16*>(out16), N, T, Tp, PL, C, mode);
+    TACO_REQUIRE(x || x16, TACO_EINVAL, "bn_apply: no input");
+    if (x16) bn_apply_kernel<true><<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, static_cast<bf16*>(out16),
+                                                                                          static_cast<const bf16*>(x16), N, T, Tp, PL, C, mode);
+    else bn_apply_kernel<false><<<ew_blocks((long long)N * Tp * C / 4), EW_THREADS, 0, s>>>(x, mean, rstd, gamma, beta, res, rowvec, out, static_cast<bf16*>(out16),
+                                                                                        nullptr, N, T, Tp, PL, C, mode);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -204,12 +209,15 @@ __device__ __forceinline__ float4 f4_bn(float4 x, float4 mu, float4 rs, float4 g
     return make_float4((x.x - mu.x) * rs.x * g.x + b.x, (x.y - mu.y) * rs.y * g.y + b.y, (x.z - mu.z) * rs.z * g.z + b.z, (x.w - mu.w) * rs.w * g.w + b.w);
 }
 
-template <int MODE, bool APPLY>
+// IN16: x and dy are read from their bf16 mirrors (compile time: a run-time choice per load turned the 19 batched loads of a
+// thread into 19 dependent branches and doubled the kernel's time)
+template <int MODE, bool APPLY, bool IN16>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const float* __restrict__ dyp, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
                                                      bf16* __restrict__ dx16, float* __restrict__ dbias,
+                                                     const bf16* __restrict__ x16, const bf16* __restrict__ dyp16,
                                                      int N, int T, int Tp, int PL, int C, int relu_mask, int chunks, int c_off) {
     const int tx = blockDim.x, ty = blockDim.y;
     const int c = c_off + (blockIdx.x * tx + threadIdx.x) * 4;
@@ -226,13 +234,15 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const float* __restrict_
         for (int j = 0; j < BNB_R + 2; j++) {
             const int tp = tp0 - 1 + j, t = tp - PL;
             const bool need = (MODE == 1) ? (t >= 0 && t < T) : (j >= 1 && j <= BNB_R && t >= 0 && t < T);
-            xv[j] = need ? f4_ld(x + base + (long long)tp * C) : f4_zero();
+            if (IN16) xv[j] = need ? ld_bf16x4(x16 + base + (long long)tp * C) : f4_zero();
+            else xv[j] = need ? f4_ld(x + base + (long long)tp * C) : f4_zero();
         }
 #pragma unroll
         for (int j = 0; j < BNB_R + 1; j++) {
             const int tp = tp0 - 1 + j, t = tp - PL;
             const bool need = (t >= 0 && t < T) && (MODE == 1 || j >= 1);
-            dv[j] = need ? f4_ld(dyp + base + (long long)tp * C) : f4_zero();
+            if (IN16) dv[j] = need ? ld_bf16x4(dyp16 + base + (long long)tp * C) : f4_zero();
+            else dv[j] = need ? f4_ld(dyp + base + (long long)tp * C) : f4_zero();
         }
         float4 dg4 = f4_zero(), db4 = f4_zero();
         if (APPLY) { dg4 = f4_ld(dgamma + c); db4 = f4_ld(dbeta + c); }
@@ -321,10 +331,13 @@ static inline void lanes_2d(int C4, int& tx, int& ty) {
 
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s,
-                  void* dx16v, float* dbias) {
+                  void* dx16v, float* dbias, const void* x16v, const void* dyp16v) {
     TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "bn_bwd: channel count %d must be a multiple of 4", C);
     TACO_REQUIRE(dx || dx16v, TACO_EINVAL, "bn_bwd: no output");
     bf16* dx16 = static_cast<bf16*>(dx16v);
+    const bf16* x16 = static_cast<const bf16*>(x16v); const bf16* dyp16 = static_cast<const bf16*>(dyp16v);
+    TACO_REQUIRE((x && dyp && !x16 && !dyp16) || (x16 && dyp16), TACO_EINVAL, "bn_bwd: inputs must be both fp32 or both bf16");
+    const bool in16 = x16 != nullptr;
     int tx, ty; lanes_2d(C / 4, tx, ty);
     const int chunks = cdiv(Tp, ty * BNB_R);
     const int gx = cdiv(C / 4, tx);
@@ -335,13 +348,14 @@ int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const flo
     dim3 block(tx, ty), grid(grouped ? 1 : gx, (unsigned)(N * chunks));
     for (int gi = 0; gi < ngroups; gi++) {
         const int c_off = gi * 4 * tx;
-        if (mode == 1) {
-            bn_bwd_kernel<1, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-            bn_bwd_kernel<1, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-        } else {
-            bn_bwd_kernel<0, false><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-            bn_bwd_kernel<0, true><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, N, T, Tp, PL, C, relu_mask, chunks, c_off);
-        }
+#define BN_BWD_LAUNCH(MODE_, APPLY_, IN16_)                                                                                             \
+        bn_bwd_kernel<MODE_, APPLY_, IN16_><<<grid, block, 0, s>>>(dyp, x, mean, rstd, gamma, beta, dgamma, dbeta, dx, dx16, dbias, x16, dyp16, \
+                                                                    N, T, Tp, PL, C, relu_mask, chunks, c_off)
+        if (mode == 1 && in16) { BN_BWD_LAUNCH(1, false, true); BN_BWD_LAUNCH(1, true, true); }
+        else if (mode == 1) { BN_BWD_LAUNCH(1, false, false); BN_BWD_LAUNCH(1, true, false); }
+        else if (in16) { BN_BWD_LAUNCH(0, false, true); BN_BWD_LAUNCH(0, true, true); }
+        else { BN_BWD_LAUNCH(0, false, false); BN_BWD_LAUNCH(0, true, false); }
+#undef BN_BWD_LAUNCH
     }
     TACO_CHECK_LAUNCH();
     return TACO_OK;
@@ -368,29 +382,61 @@ int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y
 // backward: dHpre = dy*T*[H>0]; dTpre = dy*(H-x)*T*(1-T); dx_direct = dy*(1-T)
 // The two pre-activation gradients are written side by side into one [rows, 2C] matrix (dHpre | dTpre) so that the data
 // gradient dx += dHpre.WH^T + dTpre.WT^T is ONE GEMM with K = 2C against the packed [C, 2C] weight (model_cbhg.cu).
-__global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ H, const float* __restrict__ Tg,
-                                   const float* __restrict__ x, float* __restrict__ dHT, bf16* __restrict__ dHT16, float* __restrict__ dx, long long n4, int c4) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 d = reinterpret_cast<const float4*>(dy)[i], h = reinterpret_cast<const float4*>(H)[i];
-        const float4 t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
-        const long long row = i / c4; const int cq = (int)(i - row * c4);
-        float4 a, b, o;
-        a.x = (h.x > 0.f) ? d.x * t.x : 0.f; a.y = (h.y > 0.f) ? d.y * t.y : 0.f;
-        a.z = (h.z > 0.f) ? d.z * t.z : 0.f; a.w = (h.w > 0.f) ? d.w * t.w : 0.f;
-        b.x = d.x * (h.x - v.x) * t.x * (1.f - t.x); b.y = d.y * (h.y - v.y) * t.y * (1.f - t.y);
-        b.z = d.z * (h.z - v.z) * t.z * (1.f - t.z); b.w = d.w * (h.w - v.w) * t.w * (1.f - t.w);
-        o.x = d.x * (1.f - t.x); o.y = d.y * (1.f - t.y); o.z = d.z * (1.f - t.z); o.w = d.w * (1.f - t.w);
-        if (dHT) { float4* out = reinterpret_cast<float4*>(dHT) + row * (2 * c4) + cq; out[0] = a; out[c4] = b; }
-        if (dHT16) { bf16* o16 = dHT16 + (row * (2 * c4) + cq) * 4; st_bf16x4(o16, a); st_bf16x4(o16 + 4 * c4, b); }
-        reinterpret_cast<float4*>(dx)[i] = o;
+__global__ void __launch_bounds__(256) highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ H, const float* __restrict__ Tg,
+                                   const float* __restrict__ x, float* __restrict__ dHT, bf16* __restrict__ dHT16, float* __restrict__ dx,
+                                   float* __restrict__ dbH, float* __restrict__ dbT, long long rows, int c4, int rows_per_block) {
+    // block = (tx float4 channel lanes) x (ty rows); a block walks its row chunk, every thread keeps its 4 channels: the column sums
+    // of the two pre-activation gradients (= the H / T bias gradients) come out of the same pass
+    const int tx = blockDim.x, ty = blockDim.y;
+    const int cq = blockIdx.x * tx + threadIdx.x;
+    const bool cok = cq < c4;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok) {
+        for (long long row = r0 + threadIdx.y; row < r1; row += ty) {
+            const long long i = row * c4 + cq;
+            const float4 d = reinterpret_cast<const float4*>(dy)[i], h = reinterpret_cast<const float4*>(H)[i];
+            const float4 t = reinterpret_cast<const float4*>(Tg)[i], v = reinterpret_cast<const float4*>(x)[i];
+            float4 a, b, o;
+            a.x = (h.x > 0.f) ? d.x * t.x : 0.f; a.y = (h.y > 0.f) ? d.y * t.y : 0.f;
+            a.z = (h.z > 0.f) ? d.z * t.z : 0.f; a.w = (h.w > 0.f) ? d.w * t.w : 0.f;
+            b.x = d.x * (h.x - v.x) * t.x * (1.f - t.x); b.y = d.y * (h.y - v.y) * t.y * (1.f - t.y);
+            b.z = d.z * (h.z - v.z) * t.z * (1.f - t.z); b.w = d.w * (h.w - v.w) * t.w * (1.f - t.w);
+            o.x = d.x * (1.f - t.x); o.y = d.y * (1.f - t.y); o.z = d.z * (1.f - t.z); o.w = d.w * (1.f - t.w);
+            if (dHT) { float4* out = reinterpret_cast<float4*>(dHT) + row * (2 * c4) + cq; out[0] = a; out[c4] = b; }
+            if (dHT16) { bf16* o16 = dHT16 + (row * (2 * c4) + cq) * 4; st_bf16x4(o16, a); st_bf16x4(o16 + 4 * c4, b); }
+            reinterpret_cast<float4*>(dx)[i] = o;
+            sa.x += a.x; sa.y += a.y; sa.z += a.z; sa.w += a.w; sb.x += b.x; sb.y += b.y; sb.z += b.z; sb.w += b.w;
+        }
+    }
+    if (dbH) {        // kernel-uniform
+        __shared__ float4 red[2][256];
+        const int tid = threadIdx.y * tx + threadIdx.x;
+        red[0][tid] = sa; red[1][tid] = sb;
+        __syncthreads();
+        if (threadIdx.y == 0 && cok) {
+            for (int y = 1; y < ty; y++) {
+                const float4 p = red[0][y * tx + threadIdx.x], q = red[1][y * tx + threadIdx.x];
+                sa.x += p.x; sa.y += p.y; sa.z += p.z; sa.w += p.w; sb.x += q.x; sb.y += q.y; sb.z += q.z; sb.w += q.w;
+            }
+            const int c = cq * 4;
+            atomicAdd(dbH + c, sa.x); atomicAdd(dbH + c + 1, sa.y); atomicAdd(dbH + c + 2, sa.z); atomicAdd(dbH + c + 3, sa.w);
+            atomicAdd(dbT + c, sb.x); atomicAdd(dbT + c + 1, sb.y); atomicAdd(dbT + c + 2, sb.z); atomicAdd(dbT + c + 3, sb.w);
+        }
     }
 }
 int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT, float* dx,
-                       long long rows, int C, cudaStream_t s, void* dHT16) {
+                       long long rows, int C, cudaStream_t s, void* dHT16, float* dbH, float* dbT) {
     TACO_REQUIRE(C % 4 == 0, TACO_ESHAPE, "highway_bwd: width %d must be a multiple of 4", C);
     TACO_REQUIRE(dHT || dHT16, TACO_EINVAL, "highway_bwd: no pre-activation gradient output");
-    const long long n4 = rows * (C / 4);
-    highway_bwd_kernel<<<ew_blocks(n4), EW_THREADS, 0, s>>>(dy, H, Tg, x, dHT, static_cast<bf16*>(dHT16), dx, n4, C / 4);
+    TACO_REQUIRE((dbH == nullptr) == (dbT == nullptr), TACO_EINVAL, "highway_bwd: give both bias gradients or none");
+    int tx, ty; lanes_2d(C / 4, tx, ty);
+    const int bx = cdiv(C / 4, tx);
+    long long by = cdiv64(148 * 8, bx);
+    long long rpb = cdiv64(rows, by);
+    if (rpb < ty) rpb = ty;
+    dim3 block(tx, ty), grid(bx, (unsigned)cdiv64(rows, rpb));
+    highway_bwd_kernel<<<grid, block, 0, s>>>(dy, H, Tg, x, dHT, static_cast<bf16*>(dHT16), dx, dbH, dbT, rows, C / 4, (int)rpb);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }
@@ -650,6 +696,7 @@ int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaS
 // L1 loss + gradient.  out/target rows: out row (n,t) at out + (n*out_bs + t*out_ts), target at tgt + (n*T + t)*C.
 // scalars[0] += sum |d|*coeff*w ; scalars[1] += sum |d| (unweighted, all bins) ; scalars[2] += sum |d| over the priority band.
 // grad[(n,t),c] = sign(out - tgt) * coeff[n] * (w_all + w_band*[lo<=c<hi])     (pad rows of grad untouched)
+template <bool TGT16>
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ out, long long out_bs, long long out_ts,
                                const float* __restrict__ tgt, const bf16* __restrict__ tgt16, const float* __restrict__ coeff,
                                float* __restrict__ grad, bf16* __restrict__ grad16, long long grad_bs, long long grad_ts,
@@ -671,7 +718,7 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int c = c0 + e * tx; const bool ok = c < C;
-                ov[e] = ok ? op[c] : 0.f; tv[e] = ok ? (tp16 ? __bfloat162float(tp16[c]) : __ldg(tp + c)) : 0.f;
+                ov[e] = ok ? op[c] : 0.f; tv[e] = ok ? (TGT16 ? __bfloat162float(tp16[c]) : __ldg(tp + c)) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) {
@@ -707,9 +754,12 @@ int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const f
     int tx = 32; while (tx < C && tx < 256) tx <<= 1;
     const int ty = 256 / tx;
     int blocks = cdiv(N * T, ty); if (blocks > 148 * 8) blocks = 148 * 8;
-    l1_loss_kernel<<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt_is_bf16 ? nullptr : tgt, tgt_is_bf16 ? reinterpret_cast<const bf16*>(tgt) : nullptr,
-                                                   coeff, grad, static_cast<bf16*>(grad16), grad_bs, grad_ts,
-                                                   N, T, C, w_all, w_band, lo, hi, scalars);
+    if (tgt_is_bf16)
+        l1_loss_kernel<true><<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, nullptr, reinterpret_cast<const bf16*>(tgt), coeff, grad, static_cast<bf16*>(grad16),
+                                                             grad_bs, grad_ts, N, T, C, w_all, w_band, lo, hi, scalars);
+    else
+        l1_loss_kernel<false><<<blocks, dim3(tx, ty), 0, s>>>(out, out_bs, out_ts, tgt, nullptr, coeff, grad, static_cast<bf16*>(grad16),
+                                                              grad_bs, grad_ts, N, T, C, w_all, w_band, lo, hi, scalars);
     TACO_CHECK_LAUNCH();
     return TACO_OK;
 }

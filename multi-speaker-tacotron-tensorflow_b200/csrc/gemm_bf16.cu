@@ -20,6 +20,7 @@
 #include "tc_common.cuh"
 #include "kernels.h"
 #include <cudaTypedefs.h>
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 #include <cstdlib>
@@ -41,6 +42,7 @@ struct BfParams {
     int M, N, K, ldc, ldc16;
     int BN, tilesN, units, split_k, kt_per, ktiles;
     int stages, b_stage_bytes;           // ring depth and B stage pitch: ceil(BN/64) x 8 KB
+    int one_shot;                        // 1: grid = units, every CTA computes the unit of its index and exits (leaf GEMMs, see launch_gemm_bf16)
     int fast_ok;                         // the lean epilogue applies to interior chunks (vector stores, aligned bias, no read-modify-write)
     int a_mn_major, b_mn_major;
     int b_3d;                            // MN-major B tile through ONE 3-D box {64 n, 64 k, BN/64 n-blocks}
@@ -239,7 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint64_t* my_full = full_bar + warp * BF_MAX_STAGES;
         int it = 0;
         int next = 0;
-        if (warp == 0 && lane == 0) next = (int)atomicAdd(p.sched, 1u);
+        if (warp == 0 && lane == 0) next = p.one_shot ? (int)blockIdx.x : (int)atomicAdd(p.sched, 1u);
         for (int lt = 0;; lt++) {
             const int slot = lt & 1, use = lt >> 1;
             int u = 0;
@@ -249,7 +251,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (use > 0) mbar_wait_bounded(&sched_empty[slot], (use - 1) & 1);
                     sched_unit[slot] = u;
                     mbar_arrive(&sched_full[slot]);
-                    if (u < p.units) next = (int)atomicAdd(p.sched, 1u);  // fetched one tile ahead: its latency hides behind this tile's loads
+                    if (u < p.units) next = p.one_shot ? p.units : (int)atomicAdd(p.sched, 1u);  // fetched one tile ahead: its latency hides behind this tile's loads
                 }
                 u = __shfl_sync(0xffffffffu, u, 0);
             } else {
@@ -303,7 +305,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             __syncwarp();
         }
-        if (warp == 0 && lane == 0) {
+        if (warp == 0 && lane == 0 && !p.one_shot) {
             // self-cleaning work counter: the last CTA to leave resets the slot for a later launch
             __threadfence();
             const unsigned int done = atomicAdd(p.sched + 1, 1u);
@@ -570,7 +572,7 @@ static unsigned int g_sched_next = 0;
 static int g_n_sm[16] = {};
 static std::mutex g_sched_mu;
 
-int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
+int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s, bool leaf) {
     TACO_TRY(get_encode16());
     int dev = 0; TACO_CHECK_CUDA(cudaGetDevice(&dev));
     TACO_REQUIRE(dev >= 0 && dev < 16, TACO_ECUDA, "gemm: device ordinal %d out of range", dev);
@@ -654,8 +656,18 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
     const int tiles = cdiv(g.M, BF_BM) * p.tilesN;
     // A caller that allows K splitting (split_k > 1: C is accumulated atomically) gets the split that balances whole waves
     // of persistent CTAs: waves x (k-blocks per unit + a fixed per-unit cost in k-block units).
+    // Leaf GEMMs (weight gradients on the low-priority stream of the backward schedule) must not hold the machine: a persistent
+    // CTA owns its SM (225 KB of shared memory, 63 K registers) until its tile loop ends, so the high-priority chain - cluster
+    // launches of the recurrences included - would wait behind it (measured: bn_bwd of the post-net bank 0.31 -> 0.60 ms).  They
+    // run one short unit per CTA instead (<= 24 k-tiles, grid = units): SMs come free every ~20 us and go to the chain first.
+    static const int leaf_mode = [] { const char* e = getenv("TACO_BF16_LEAF"); return e ? atoi(e) : 1; }();
+    p.one_shot = (leaf && leaf_mode == 1) ? 1 : 0;
     p.split_k = 1;
-    if (g.split_k > 1) {
+    if (g.split_k > 1 && p.one_shot) {
+        const int cap = p.ktiles / 4 > 0 ? p.ktiles / 4 : 1;
+        p.split_k = std::min(cap, cdiv(p.ktiles, 24));
+        if (p.split_k < 1) p.split_k = 1;
+    } else if (g.split_k > 1) {
         double best = 1e30;
         for (int sp = 1; sp <= 128 && sp <= p.ktiles; sp++) {
             const int per = cdiv(p.ktiles, sp);
@@ -677,7 +689,7 @@ int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s) {
         std::lock_guard<std::mutex> lk(g_sched_mu);
         p.sched = g_sched_ring[dev] + 2 * (g_sched_next++ % BF_SCHED_SLOTS);
     }
-    const int grid = p.units < n_sm ? p.units : n_sm;
+    const int grid = p.one_shot ? p.units : (p.units < n_sm ? p.units : n_sm);
     gemm_bf16_kernel<<<grid, BF_THREADS, BF_SMEM, s>>>(mapA, mapB, p);
     TACO_CHECK_LAUNCH();
     return TACO_OK;

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     const int unit = rank * U + i;
     const long long st_base = ((long long)d * a.N + n) * a.T;
     float dh_carry = (act && a.dh_in && n < a.N) ? a.dh_in[(long long)n * a.ndir * H + d * H + unit] : 0.f;
+    float sb_r = 0.f, sb_u = 0.f, sb_c = 0.f;        // bias gradients: this thread's (unit, row) sums of the gate gradients over time
     __syncthreads();
     cluster.sync();
 
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_r, dg_s + rank * R * U, bar_g, tid);
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, tid);
         if (valid) {      // gradient / stash stores in the shadow of the exchange
+            sb_r += dr_pre; sb_u += du_pre; sb_c += dc_pre;
             const long long go = ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
             if (a.dgx) { float* g = a.dgx + go; g[0] = dr_pre; g[H] = du_pre; g[2 * H] = dc_pre; }
             const __nv_bfloat16 br = __float2bfloat16_rn(dr_pre), bu = __float2bfloat16_rn(du_pre), bc = __float2bfloat16_rn(dc_pre);
@@ -467,6 +469,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         __syncthreads();      // `red` / stages are rewritten at the top of the next iteration
     }
     if (act && a.dh0 && n < a.N) a.dh0[(long long)n * a.ndir * H + d * H + unit] = dh_carry;
+    if (act && a.dbg[d] && n < a.N) {                // gate / candidate bias gradients (8 rows per unit and cluster: a handful of atomics)
+        atomicAdd(a.dbg[d] + unit, sb_r); atomicAdd(a.dbg[d] + H + unit, sb_u); atomicAdd(a.dbc[d] + unit, sb_c);
+    }
     cluster.sync();
 }
 

@@ -12,7 +12,7 @@ bool gemm_tc_eligible(const taco_gemm_desc& g);
 int launch_gemm_tc(const taco_gemm_desc& g, cudaStream_t s);   // TACO_ENOTSUP: caller falls back to SIMT
 constexpr int TACO_ENOTSUP = -100;
 bool gemm_bf16_eligible(const taco_gemm_desc& g);              // gemm_bf16.cu: both bf16 mirrors given and TMA-addressable
-int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s);
+int launch_gemm_bf16(const taco_gemm_desc& g, cudaStream_t s, bool leaf = false);   // leaf: short one-unit CTAs instead of persistent ones
 
 // elementwise.cu
 int launch_fill(float* p, long long n, float v, cudaStream_t s);
@@ -25,13 +25,15 @@ int launch_bn_update_moving(float* moving_mean, float* moving_var, const float* 
 int launch_unpad(float* dst, const float* src, int N, int T, int Tp, int PL, int C, long long ld, cudaStream_t s);
 int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaStream_t s);
 int launch_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16 = nullptr);
+                    const float* res, const float* rowvec, float* out, int N, int T, int Tp, int PL, int C, int mode, cudaStream_t s, void* out16 = nullptr,
+                    const void* x16 = nullptr /* x as bf16 instead of fp32 */);
 int launch_bn_bwd(const float* dyp, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   float* dgamma, float* dbeta, float* dx, int N, int T, int Tp, int PL, int C, int mode, int relu_mask, cudaStream_t s,
-                  void* dx16 = nullptr, float* dbias = nullptr /* += column sums of dx: the convolution's bias gradient */);
+                  void* dx16 = nullptr, float* dbias = nullptr /* += column sums of dx: the convolution's bias gradient */,
+                  const void* x16 = nullptr, const void* dyp16 = nullptr /* bf16 inputs instead of the fp32 ones */);
 int launch_highway_fwd(const float* H, const float* Tg, const float* x, float* y, long long n, cudaStream_t s, void* y16 = nullptr);
 int launch_highway_bwd(const float* dy, const float* H, const float* Tg, const float* x, float* dHT /*[rows,2C]: dHpre | dTpre*/, float* dx,
-                       long long rows, int C, cudaStream_t s, void* dHT16 = nullptr);
+                       long long rows, int C, cudaStream_t s, void* dHT16 = nullptr, float* dbH = nullptr, float* dbT = nullptr /* += column sums of dHpre / dTpre */);
 int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
@@ -76,6 +78,8 @@ struct GruArgs {
     // backward: dgx16 indexed like dgx (dgx itself may then be NULL), dgx16_dense [ndir][N*T][3H] (the valid rows, dense: the
     // operand of the recurrent weight gradients), st_rh16 [ndir][N][T][H] = r * h_prev
     void* out16; void* st_hprev16; void* dgx16; void* dgx16_dense; void* st_rh16;
+    // backward, fast kernels: bias gradients accumulated in the kernel (+= over the launch's steps): gates_bias [2H] and cand_bias [H] per direction, or NULL
+    float* dbg[2]; float* dbc[2];
 };
 int launch_gru_fwd(const GruArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruArgs& a, cudaStream_t s);

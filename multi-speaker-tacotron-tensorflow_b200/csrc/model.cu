@@ -200,7 +200,7 @@ int launch_gemm(const taco_gemm_desc* d, int n_problems, int precision, cudaStre
     int rc_all = TACO_OK;
     for (size_t k = 0; k < tc.size(); k++) {
         cudaStream_t st = fan_out ? set.aux[k % kAuxStreams] : s;
-        int rc = is16[k] ? launch_gemm_bf16(d[tc[k]], st) : launch_gemm_tc(d[tc[k]], st);
+        int rc = is16[k] ? launch_gemm_bf16(d[tc[k]], st, s == ds().side) : launch_gemm_tc(d[tc[k]], st);
         if (rc == TACO_ENOTSUP) rest.push_back(d[tc[k]]);
         else if (rc != TACO_OK && rc_all == TACO_OK) rc_all = rc;
     }
@@ -296,7 +296,7 @@ void Model::plan(const Shape& s) {
         const std::string p = g.prefix + "/";
         const int64_t rows = g.rows, KC = (int64_t)g.Kb * g.Cb, H = g.H;
         add(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin); add16(p + "xin_p", {rows, g.Cin}, (int64_t)g.slack * g.Cin);
-        add(p + "bank_raw", {rows, KC});
+        add32(p + "bank_raw", {rows, KC}); add16(p + "bank_raw", {rows, KC});
         add(p + "bank_stats", {2 * KC}, 0, true);
         add(p + "bank_mean", {KC}); add(p + "bank_rstd", {KC}); add(p + "bank_var", {KC});
         // tensors only contractions read live as bf16 alone in the bf16 mode (add32 / add16 pairs)
@@ -333,7 +333,7 @@ void Model::plan(const Shape& s) {
             add32(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2); add16(p + "d_p2raw", {rows, g.P2}, (int64_t)g.slack * g.P2);
             add(p + "d_p1p", {rows, g.P1});
             add32(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1); add16(p + "d_p1raw", {rows, g.P1}, (int64_t)g.slack * g.P1);
-            add(p + "d_pooled", {rows, KC});
+            add32(p + "d_pooled", {rows, KC}); add16(p + "d_pooled", {rows, KC});
             add32(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC); add16(p + "d_bank", {rows, KC}, (int64_t)g.slack * KC);
             add(p + "d_xin_p", {rows, g.Cin});
             add(p + "d_before", {g.N, g.P2});
@@ -415,7 +415,8 @@ void Model::plan(const Shape& s) {
         regions["linear_outputs"] = r;
         const int64_t wrows = 2 * (int64_t)c.post_rnn_size + ((c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0);
         add("linear/w_pad", {wrows, Fp}); add16("linear/w_pad", {wrows, Fp});
-        if (tr) { add("d_linear", {(int64_t)N * s.To, Fp}); add16("d_linear", {(int64_t)N * s.To, Fp}); }
+        // (bf16 mode: the loss gradient exists as bf16 only, except under 'simple' speaker injection, whose time sums read fp32)
+        if (tr) { if (!h16 || c.speaker_mode == TACO_SPK_SIMPLE) add("d_linear", {(int64_t)N * s.To, Fp}); add16("d_linear", {(int64_t)N * s.To, Fp}); }
     }
     if (tr) add("post_cbhg/d_mel_loss", {post.rows, c.num_mels});
     if (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE) {
@@ -657,8 +658,9 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
         w_all = (float)(0.5 / cnt_lin); w_band = (float)(0.5 / ((double)N * To * (hi - lo)));
     }
     const int Fp = (F + 63) / 64 * 64;
+    float* d_lin32 = m.has_region("d_linear") ? m.W("d_linear") : nullptr;
     TACO_TRY(launch_l1_loss(m.W("linear_buf"), (long long)To * Fp, Fp, b->linear_targets, b->loss_coeff,
-                            m.W("d_linear"), (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear"), b->linear_targets_bf16));
+                            d_lin32, (long long)To * Fp, Fp, N, To, F, w_all, w_band, lo, hi, sc + 3, s, m.W16("d_linear"), b->linear_targets_bf16));
     TACO_TRY(launch_l1_loss(m.W("mel_outputs"), (long long)g.Tp * M, M, b->mel_targets, b->loss_coeff,
                             m.W("post_cbhg/d_mel_loss") + (long long)g.PL * M, (long long)g.Tp * M, M, N, To, M,
                             (float)(1.0 / cnt_mel), 0.f, 0, 0, sc + 0, s));
@@ -667,12 +669,13 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
     {
         const int Hp2 = 2 * c.post_rnn_size; const long long rows = (long long)N * To;
         const int S = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
-        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), m.W("d_linear"), m.G("linear/kernel") + (long long)S * F, Hp2, F, (int)rows, Hp2, Fp, F);
+        taco_gemm_desc w = gd0(m.W("post_cbhg/rnn_out"), d_lin32, m.G("linear/kernel") + (long long)S * F, Hp2, F, (int)rows, Hp2, Fp, F);
         w.transA = 1; w.accumulate = 1; w.split_k = 8;
         w.A16 = m.W16("post_cbhg/rnn_out"); w.B16 = m.W16("d_linear");
         cudaStream_t leaf = fork_side(s);
         TACO_TRY(launch_gemm(&w, 1, prec, leaf));
-        TACO_TRY(launch_colsum(m.W("d_linear"), m.G("linear/bias"), rows, F, Fp, leaf));
+        if (d_lin32) TACO_TRY(launch_colsum(d_lin32, m.G("linear/bias"), rows, F, Fp, leaf));
+        else TACO_TRY(launch_colsum16(m.W16("d_linear"), m.G("linear/bias"), rows, F, Fp, leaf));
         if (S) {
             // speaker rows of the kernel and the embedding gradient see d_linear only through its sum over time
             TACO_CHECK_CUDA(cudaMemsetAsync(m.W("spk/s_lin"), 0, sizeof(float) * (size_t)N * Fp, s));
@@ -685,7 +688,7 @@ static int model_backward(Model& m, const taco_batch* b, cudaStream_t s) {
             es.transB = 1; es.accumulate = 1;
             TACO_TRY(launch_gemm(&es, 1, TACO_PREC_FP32, s));
         }
-        taco_gemm_desc e = gd0(m.W("d_linear"), m.W("linear/w_pad") + (long long)S * Fp, m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
+        taco_gemm_desc e = gd0(d_lin32, m.W("linear/w_pad") + (long long)S * Fp, m.W("post_cbhg/d_rnn_out"), (int)rows, Hp2, F, Fp, Fp, Hp2);
         e.transB = 1;
         if (m.use16()) { e.A16 = m.W16("d_linear"); e.B16 = static_cast<uint16_t*>(m.W16("linear/w_pad")) + (long long)S * Fp; }
         TACO_TRY(launch_gemm(&e, 1, prec, s));

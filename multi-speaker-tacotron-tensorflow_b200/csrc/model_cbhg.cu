@@ -48,8 +48,11 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
         for (int k = 1; k <= g.Kb; k++) {
             const int l = (k - 1) / 2;
             const std::string b = px + "bank_" + std::to_string(k);
-            taco_gemm_desc d = gemm_desc(xin_p - (long long)l * g.Cin, m.P(b + "/kernel"), R("bank_raw") + (k - 1) * g.Cb,
+            // (bf16 mode: the [rows, Kb*Cb] bank output - the widest tensor of the block - exists as bf16 only; the batch-norm
+            //  statistics are still taken from the fp32 accumulators in the GEMM epilogue)
+            taco_gemm_desc d = gemm_desc(xin_p - (long long)l * g.Cin, m.P(b + "/kernel"), h16 ? nullptr : R("bank_raw") + (k - 1) * g.Cb,
                                          rows, g.Cb, k * g.Cin, g.Cin, g.Cb, KC);
+            d.C16 = off16(R16("bank_raw"), (k - 1) * g.Cb);
             d.ctap = g.Cin; d.bias = m.P(b + "/bias"); d.act = ACT_RELU; set_mask(d, g);
             d.A16 = off16(R16("xin_p"), -(long long)l * g.Cin); d.B16 = m.P16(b + "/kernel");
             if (training) { d.colsum = bstats + (k - 1) * g.Cb; d.colsumsq = bstats + KC + (k - 1) * g.Cb; }
@@ -60,8 +63,8 @@ int cbhg_forward(Model& m, const CbhgGeom& g, const int* lengths, const float* b
     TACO_TRY(launch_bn_finalize(bstats, bstats + KC, count, R("bank_mean"), R("bank_rstd"), R("bank_var"),
                                 m.P(px + "bank_1/moving_mean"), m.P(px + "bank_1/moving_var"), KC, training, s));
     // BN + max-pool(2,1,'same')  (modules.py:47-51)
-    TACO_TRY(launch_bn_apply(R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
-                             nullptr, nullptr, h16 ? nullptr : R("pooled_p"), g.N, g.T, g.Tp, g.PL, KC, 1, s, R16("pooled_p")));
+    TACO_TRY(launch_bn_apply(h16 ? nullptr : R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
+                             nullptr, nullptr, h16 ? nullptr : R("pooled_p"), g.N, g.T, g.Tp, g.PL, KC, 1, s, R16("pooled_p"), R16("bank_raw")));
 
     prof_mark("cbhg_f:proj", s);
     // ---- projection 1: conv k=pw, ReLU, BN (modules.py:54-59) ----
@@ -187,6 +190,10 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         a.st_r = R("st_r"); a.st_u = R("st_u"); a.st_c = R("st_c"); a.st_hprev = R("st_hprev");
         a.dout = R("d_rnn_out"); a.dout_ld = 2 * H; a.dgx = h16 ? nullptr : R("dgx");
         a.dgx16 = R16("dgx"); a.dgx16_dense = R16("dgx_dense"); a.st_rh16 = R16("st_rh");
+        if (a.fast) {      // the fast kernels accumulate the gate / candidate bias gradients themselves
+            a.dbg[0] = m.G(px + "gru_fw/gates_bias"); a.dbc[0] = m.G(px + "gru_fw/cand_bias");
+            a.dbg[1] = m.G(px + "gru_bw/gates_bias"); a.dbc[1] = m.G(px + "gru_bw/cand_bias");
+        }
         a.dh0 = want_dh0 ? R("d_h0") : nullptr;
         TACO_TRY(prof_launch_gru(a, true, s));
     }
@@ -224,7 +231,7 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
             d.transA = 1; d.accumulate = 1; d.split_k = wgrad_split(H, H, NT); ds.push_back(d);
         }
         TACO_TRY(launch_gemm(ds.data(), (int)ds.size(), prec, leaf));
-        for (int dd = 0; dd < 2; dd++) {
+        for (int dd = 0; dd < 2 && prec == TACO_PREC_FP32; dd++) {       // (exact kernels: bias gradients as column sums of dgx)
             const std::string gn = px + dirs[dd];
             if (h16) {
                 TACO_TRY(launch_colsum16(off16(dgx16, dd * 3 * H), m.G(gn + "/gates_bias"), rows, 2 * H, 6 * H, leaf));
@@ -256,20 +263,13 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         float* dHT = h16 ? nullptr : m.W(px + "d_HT_" + std::to_string(i));
         void* dHT16 = m.W16(px + "d_HT_" + std::to_string(i));
         void* xin16 = (i == 1) ? (g.has_hin ? R16("hw_0") : R16("hw0")) : m.W16(px + "hw_" + std::to_string(i - 1));
-        TACO_TRY(launch_highway_bwd(dcur, Hb, Tb, xin, dHT, dnext, rows, H, s, dHT16));
+        TACO_TRY(launch_highway_bwd(dcur, Hb, Tb, xin, dHT, dnext, rows, H, s, dHT16, m.G(hn + "/H_bias"), m.G(hn + "/T_bias")));    // bias gradients ride along
         cudaStream_t lf = fork_side(s);
         taco_gemm_desc d[2];
         d[0] = gemm_desc(xin, dHT, m.G(hn + "/H_kernel"), H, H, rows, H, 2 * H, H); d[0].transA = 1; d[0].accumulate = 1; d[0].split_k = wgrad_split(H, H, rows);
         d[1] = gemm_desc(xin, h16 ? nullptr : dHT + H, m.G(hn + "/T_kernel"), H, H, rows, H, 2 * H, H); d[1].transA = 1; d[1].accumulate = 1; d[1].split_k = d[0].split_k;
         d[0].A16 = xin16; d[0].B16 = dHT16; d[1].A16 = xin16; d[1].B16 = off16(dHT16, H);
         TACO_TRY(launch_gemm(d, 2, prec, lf));
-        if (h16) {
-            TACO_TRY(launch_colsum16(dHT16, m.G(hn + "/H_bias"), rows, H, 2 * H, lf));
-            TACO_TRY(launch_colsum16(off16(dHT16, H), m.G(hn + "/T_bias"), rows, H, 2 * H, lf));
-        } else {
-            TACO_TRY(launch_colsum(dHT, m.G(hn + "/H_bias"), rows, H, 2 * H, lf));
-            TACO_TRY(launch_colsum(dHT + H, m.G(hn + "/T_bias"), rows, H, 2 * H, lf));
-        }
         // dx += dHpre.WH^T + dTpre.WT^T: one GEMM with K = 2H against the packed [H, 2H] weight
         taco_gemm_desc e = gemm_desc(dHT, m.W(px + "hw_wcat_" + std::to_string(i)), dnext, rows, H, 2 * H, 2 * H, 2 * H, H);
         e.A16 = dHT16; e.B16 = m.W16(px + "hw_wcat_" + std::to_string(i));
@@ -326,17 +326,18 @@ int cbhg_backward(Model& m, const CbhgGeom& g, const int* lengths, bool want_dbe
         d.transA = 1; d.ctap = KC; d.accumulate = 1; d.split_k = wgrad_split(g.pw * KC, g.P1, rows);
         cudaStream_t lf = fork_side(s);
         TACO_TRY(launch_gemm(&d, 1, prec, lf));
-        taco_gemm_desc e = gemm_desc(h16 ? nullptr : R("d_p1raw") - (long long)rp * g.P1, m.W(px + "proj_1/wd"), R("d_pooled"),
+        taco_gemm_desc e = gemm_desc(h16 ? nullptr : R("d_p1raw") - (long long)rp * g.P1, m.W(px + "proj_1/wd"), h16 ? nullptr : R("d_pooled"),
                                      rows, KC, g.pw * g.P1, g.P1, KC, KC);
+        e.C16 = R16("d_pooled");
         e.A16 = off16(R16("d_p1raw"), -(long long)rp * g.P1); e.B16 = R16("proj_1/wd");
         e.ctap = g.P1; set_mask(e, g);
         TACO_TRY(launch_gemm(&e, 1, prec, s));
     }
     prof_mark("cbhg_b:bank", s);
     // ---- max-pool + BN + ReLU backward of the bank ----
-    TACO_TRY(launch_bn_bwd(R("d_pooled"), R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
+    TACO_TRY(launch_bn_bwd(h16 ? nullptr : R("d_pooled"), h16 ? nullptr : R("bank_raw"), R("bank_mean"), R("bank_rstd"), m.P(px + "bank_1/gamma"), m.P(px + "bank_1/beta"),
                            m.G(px + "bank_1/gamma"), m.G(px + "bank_1/beta"), h16 ? nullptr : R("d_bank"), g.N, g.T, g.Tp, g.PL, KC, 1, 1, s,
-                           R16("d_bank"), m.G(px + "bank_1/bias")));
+                           R16("d_bank"), m.G(px + "bank_1/bias"), R16("bank_raw"), R16("d_pooled")));
     cudaStream_t lfb = fork_side(s);
     {
         std::vector<taco_gemm_desc> wg, dg;

@@ -263,6 +263,7 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
     a.dout = dy; a.dout_ld = Y; a.dgx = dgx;
     a.dh0 = want_dh0 ? m.W(rp + "dh0") : nullptr;
+    if (a.fast) { a.dbg[0] = m.G(gn + "/gates_bias"); a.dbc[0] = m.G(gn + "/cand_bias"); }      // bias gradients accumulated in the kernel
     TACO_TRY(prof_launch_gru(a, true, s));
     taco_gemm_desc w[4];
     w[0] = wgrad(x, Y, dgx, 3 * Y, m.G(gn + "/gates_kernel"), Y, 2 * Y, rows);
@@ -271,8 +272,10 @@ static int dec_gru_layer_bwd(Model& m, const DecDims& D, int layer, const float*
     w[3] = wgrad(m.W(rp + "st_r"), Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel") + (long long)Y * Y, Y, Y, rows);
     cudaStream_t leaf = fork_side(s);       // parameter gradients are leaves of the backward graph (model.cu: stream scheduler)
     TACO_TRY(launch_gemm(w, 4, prec, leaf));
-    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, leaf));
-    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, leaf));
+    if (!a.fast) {
+        TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, leaf));
+        TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, leaf));
+    }
     TACO_CHECK_CUDA(cudaMemcpyAsync(dx, dy, sizeof(float) * (size_t)rows * Y, cudaMemcpyDeviceToDevice, s));
     // dx += dgx . Wx^T in one GEMM (K = 3Y) against the packed x-side rows of both kernels (model.cu: backward_prep)
     taco_gemm_desc e = gd(dgx, m.W(rp + "wxcat"), dx, rows, Y, 3 * Y, 3 * Y, 3 * Y, Y); e.transB = 1; e.accumulate = 1;
@@ -293,6 +296,7 @@ static int dec_gru_chunk_bwd(Model& m, const DecDims& D, int layer, const float*
     a.st_r = m.W(rp + "st_r"); a.st_u = m.W(rp + "st_u"); a.st_c = m.W(rp + "st_c"); a.st_hprev = m.W(rp + "st_hprev");
     a.dout = dy; a.dout_ld = Y; a.dgx = dgx;
     a.t_begin = c.t0; a.t_end = c.t1;
+    a.dbg[0] = m.G(gn + "/gates_bias"); a.dbc[0] = m.G(gn + "/cand_bias");      // bias gradients: accumulated over the chunks in the kernel
     a.dh_in = last_chunk ? nullptr : carry;                              // the chunk at the end of the sequence starts from zero
     a.dh0 = (c.t0 == 0) ? (want_dh0 ? m.W(rp + "dh0") : nullptr) : carry;
     TACO_TRY(prof_launch_gru(a, true, s));
@@ -317,8 +321,6 @@ static int dec_gru_wgrads(Model& m, const DecDims& D, int layer, const float* x,
     w[3] = wgrad(m.W(rp + "st_r"), Y, dgx + 2 * Y, 3 * Y, m.G(gn + "/cand_kernel") + (long long)Y * Y, Y, Y, rows);
     cudaStream_t leaf = fork_side_after(producer);
     TACO_TRY(launch_gemm(w, 4, prec, leaf));
-    TACO_TRY(launch_colsum(dgx, m.G(gn + "/gates_bias"), rows, 2 * Y, 3 * Y, leaf));
-    TACO_TRY(launch_colsum(dgx + 2 * Y, m.G(gn + "/cand_bias"), rows, Y, 3 * Y, leaf));
     return TACO_OK;
 }
 
