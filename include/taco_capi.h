@@ -176,6 +176,37 @@ int taco_optimizer_step(taco_model m, int64_t global_step, int64_t adam_step, in
                         float initial_learning_rate, int32_t decay_mode,
                         float beta1, float beta2, float grad_scale, void* stream);
 
+/* ---- block level: the model's own code paths, one block at a time, for operator-level parity tests -------------
+ * All tensors are device fp32, row-major; the model's workspace must be planned for the batch (taco_workspace_bytes) and
+ * bound.  Parameter gradients ACCUMULATE into the bound gradient buffer (zero it first).
+ *
+ * taco_cbhg_forward  replaces models/modules.py:27-96 cbhg(): conv1d bank (:35-44,123-131) -> max-pool (:47-51) -> two
+ *   projections (:54-59) -> residual (+ before_highway, :62-69) -> [dense] -> 4x highwaynet (:72-77,105-120) -> bidirectional GRU
+ *   (:82-96).  which: 0 = encoder CBHG (inputs [N,T,enc_prenet_sizes[1]]), 1 = post-net CBHG (inputs [N,T,num_mels]);
+ *   input_lengths [N] or NULL (the post-net passes none); before_highway [N,proj_sizes[1]] / rnn_init_state [N,2*rnn] or NULL;
+ *   outputs [N,T,2*rnn].  is_training selects batch statistics (tf.layers.batch_normalization(training=...)).
+ * taco_cbhg_backward: d_outputs [N,T,2*rnn] -> d_inputs [N,T,Cin] (+ optional d_before_highway, d_rnn_init_state); call after
+ *   taco_cbhg_forward(is_training = 1) on the same inputs. */
+int taco_cbhg_forward(taco_model m, int32_t which, const float* inputs, const int32_t* input_lengths, const float* before_highway,
+                      const float* rnn_init_state, int32_t N, int32_t T, int32_t is_training, float* outputs, void* stream);
+int taco_cbhg_backward(taco_model m, int32_t which, const float* d_outputs, const int32_t* input_lengths, int32_t N, int32_t T,
+                       float* d_inputs, float* d_before_highway, float* d_rnn_init_state, void* stream);
+/* taco_decoder_forward replaces models/tacotron.py:127-214 (attention mechanism, DecoderPrenetWrapper / AttentionWrapper /
+ *   ConcatOutputAndAttentionWrapper / 2x ResidualWrapper(GRUCell) / r-frame projection of models/rnn_wrappers.py:218-415, the
+ *   helpers of models/helpers.py) on a given encoder memory [N,T_in,2*enc_rnn]: the batch supplies the token shape, the targets
+ *   (teacher forcing) or decoder_steps (free running), speaker ids and manual alignments exactly as for taco_forward.  Results:
+ *   workspace regions "mel_outputs" [N,T_out,M] and "alignments" [N,T_in,T_dec].
+ * taco_decoder_backward: d_mel_outputs [N,T_out,M] -> d_memory [N,T_in,2*enc_rnn], decoder parameter gradients accumulated. */
+int taco_decoder_forward(taco_model m, const taco_batch* b, const float* memory, void* stream);
+int taco_decoder_backward(taco_model m, const taco_batch* b, const float* d_mel_outputs, float* d_memory, void* stream);
+/* Element-wise halves of highwaynet (models/modules.py:105-120: y = H*T + x*(1-T); the two dense layers are taco_gemm calls with
+ * relu / sigmoid epilogues) and conv1d (:123-131: tf.layers.batch_normalization over the last axis, eps 1e-3; the convolution is
+ * a taco_gemm call with tap addressing).  scratch: 4*C doubles of device memory. */
+int taco_highway_combine(const float* H, const float* T, const float* x, float* y, int64_t rows, int32_t C, void* stream);
+int taco_batch_norm(const float* x, const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                    int32_t N, int32_t T, int32_t C, int32_t is_training, float* y, float* batch_mean, float* batch_var,
+                    void* scratch, void* stream);
+
 /* ---- data parallel (replaces nothing in the reference, which is single-device; SURVEY.md 8e: ONE gradient all-reduce per step) ----
  * The flat gradient is reduced in two buckets so that the larger one overlaps the encoder's backward pass:
  *   bucket 0 ("early"): decoder, post-net and linear-projection gradients = the tail [offset, offset + numel) of the flat buffer,

@@ -87,6 +87,13 @@ _SIGNATURES = {
     "taco_backward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p]),
     "taco_optimizer_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
+    "taco_cbhg_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "taco_cbhg_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taco_decoder_forward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p, C.c_void_p]),
+    "taco_decoder_backward": (C.c_int, [C.c_void_p, C.POINTER(TacoBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taco_highway_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "taco_batch_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "taco_dp_bucket": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "taco_dp_wait_bucket": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "taco_read_scalars": (C.c_int, [C.c_void_p, C.POINTER(TacoStepScalars), C.c_void_p]),

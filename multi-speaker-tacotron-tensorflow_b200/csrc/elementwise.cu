@@ -561,6 +561,23 @@ int launch_colsum16(const void* x, float* out, long long M, int C, long long ld,
     return TACO_OK;
 }
 
+// per-column sum and sum of squares of a dense [rows, C] matrix in double (stand-alone batch-norm statistics, taco_batch_norm)
+__global__ void colstats_kernel(const float* __restrict__ x, double* __restrict__ sum, double* __restrict__ sumsq, long long rows, int C, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+    double s = 0.0, q = 0.0;
+    for (long long r = r0; r < r1; r++) { const double v = x[r * C + c]; s += v; q += v * v; }
+    atomicAdd(sum + c, s); atomicAdd(sumsq + c, q);
+}
+int launch_colstats(const float* x, double* sum, double* sumsq, long long rows, int C, cudaStream_t s) {
+    const int rpb = 64;
+    dim3 grid(cdiv(C, 128), (unsigned)cdiv64(rows, rpb));
+    colstats_kernel<<<grid, 128, 0, s>>>(x, sum, sumsq, rows, C, rpb);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 // fp32 -> bf16 strided 2-D cast: dst[r*ldd + c] = bf16(src[r*lds + c])   (parameter mirror, packed weights, recurrence outputs)
 __global__ void cast2d_kernel(bf16* __restrict__ dst, const float* __restrict__ src, long long rows, int cols, long long ldd, long long lds) {
     long long total = rows * cols;

@@ -38,6 +38,7 @@ int launch_softsign_bwd(const float* dy, const float* y, float* dx, long long n,
 int launch_relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t s);
 int launch_teacher_inputs(const float* tgt, float* x, int N, int Td, int To, int r, int M, cudaStream_t s);
 int launch_colsum(const float* x, float* out, long long M, int C, int ld, cudaStream_t s);
+int launch_colstats(const float* x, double* sum, double* sumsq, long long rows, int C, cudaStream_t s);
 int launch_colsum16(const void* x_bf16, float* out, long long M, int C, long long ld, cudaStream_t s);
 int launch_cast2d_bf16(void* dst_bf16, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
 int launch_bcast_rows(const float* src, float* dst, int N, int T, int C, long long ld, cudaStream_t s);

@@ -552,16 +552,18 @@ static int backward_prep(Model& m, cudaStream_t s) {
     return TACO_OK;
 }
 
-static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
+// bf16 mirror of every trainable tensor (18.7 MB written per step; the GEMM B operands of this pass and the next backward pass)
+static int refresh_params16(Model& m, cudaStream_t s) {
+    if (!m.use16()) return TACO_OK;
+    auto it = m.regions.find("params16");
+    TACO_REQUIRE(it != m.regions.end() && it->second.numel >= m.n_trainable, TACO_ESTATE, "bf16 mode: bind the parameters before sizing the workspace");
+    return launch_cast2d_bf16(m.ws + it->second.offset, m.params, 1, (int)m.n_trainable, m.n_trainable, m.n_trainable, s);
+}
+
+// speaker injection vectors of the batch (tacotron.py:41-94): regions spk/*
+static int speaker_forward(Model& m, const taco_batch* b, cudaStream_t s) {
     const taco_config& c = m.cfg;
-    const int prec = c.precision, tr = m.shape.training;
     const bool simple = (c.speaker_mode == TACO_SPK_SIMPLE);
-    if (m.use16())     // bf16 mirror of every trainable tensor (18.7 MB written per step; the GEMM B operands of this pass and the next backward pass)
-    {
-        auto it = m.regions.find("params16");
-        TACO_REQUIRE(it != m.regions.end() && it->second.numel >= m.n_trainable, TACO_ESTATE, "bf16 mode: bind the parameters before sizing the workspace");
-        TACO_TRY(launch_cast2d_bf16(m.ws + it->second.offset, m.params, 1, (int)m.n_trainable, m.n_trainable, m.n_trainable, s));
-    }
     if (simple) {
         // 'simple' injection: one embedding row per utterance, concatenated at three sites (tacotron.py:44-49,82-86)
         TACO_REQUIRE(b->speaker_id != nullptr, TACO_EINVAL, "speaker_id is required when num_speakers > 1");
@@ -588,6 +590,16 @@ static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
                 TACO_TRY(launch_gather_rows(m.P(std::string("speaker/") + st.name + "/table"), b->speaker_id, m.W(st.region), m.shape.N, 1, 1, 0, st.dim, c.num_speakers, s));
         }
     }
+    return TACO_OK;
+}
+
+static int model_forward(Model& m, const taco_batch* b, cudaStream_t s) {
+    const taco_config& c = m.cfg;
+    const int prec = c.precision, tr = m.shape.training;
+    const bool simple = (c.speaker_mode == TACO_SPK_SIMPLE);
+    const bool spk = (c.speaker_mode == TACO_SPK_DEEPVOICE || c.speaker_mode == TACO_SPK_DEEPVOICE_TABLE);
+    TACO_TRY(refresh_params16(m, s));
+    TACO_TRY(speaker_forward(m, b, s));
     // ---- encoder prenet over the symbol table, then lookup (tacotron.py:34-39,101-103; modules.py:18-25; dropout = identity) ----
     const int V = c.num_symbols, E0 = c.embedding_size, E1 = c.enc_prenet_sizes[0], E2 = c.enc_prenet_sizes[1];
     {
@@ -1029,6 +1041,123 @@ int taco_finish_scalars(taco_model h, const void* pinned_raw, taco_step_scalars*
     double sc[8]; float scf[8];
     memcpy(sc, raw, sizeof sc); memcpy(scf, raw + sizeof sc, sizeof scf);
     finish_scalars(h->m, sc, scf, out);
+    return TACO_OK;
+}
+
+
+// ---- block-level entry points: the same code paths the model runs, reachable one block at a time --------------
+static int block_geom(Model& m, int which, int N, int T, const CbhgGeom** g) {
+    TACO_REQUIRE(which == 0 || which == 1, TACO_EINVAL, "cbhg: which must be 0 (encoder) or 1 (post-net)");
+    TACO_REQUIRE(m.planned && m.ws, TACO_ESTATE, "cbhg: size and bind a workspace first (taco_workspace_bytes / taco_bind_workspace)");
+    const CbhgGeom& gg = which ? m.post : m.enc;
+    TACO_REQUIRE(gg.N == N && gg.T == T, TACO_ESHAPE, "cbhg: the workspace is planned for N=%d T=%d, not N=%d T=%d", gg.N, gg.T, N, T);
+    *g = &gg;
+    return TACO_OK;
+}
+
+int taco_cbhg_forward(taco_model h, int32_t which, const float* inputs, const int32_t* input_lengths, const float* before_highway,
+                      const float* rnn_init_state, int32_t N, int32_t T, int32_t is_training, float* outputs, void* stream) {
+    TACO_REQUIRE(h && inputs && outputs, TACO_EINVAL, "taco_cbhg_forward: null argument");
+    Model& m = h->m;
+    TACO_ON_DEVICE(m.cfg.device);
+    const CbhgGeom* gp = nullptr;
+    TACO_TRY(block_geom(m, which, N, T, &gp));
+    const CbhgGeom& g = *gp;
+    TACO_REQUIRE(!is_training || m.shape.training, TACO_ESTATE, "taco_cbhg_forward: training statistics need a training plan");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TACO_TRY(sched_init());
+    TACO_TRY(refresh_params16(m, s));
+    const std::string px = g.prefix + "/";
+    float* xin = m.W(px + "xin_p");
+    // [N,T,Cin] -> zero-padded time layout [N,Tp,Cin] (pad frames are never written: they stay zero)
+    TACO_TRY(launch_copy2d(xin + (long long)g.PL * g.Cin, inputs, N, T * g.Cin, (long long)g.Tp * g.Cin, (long long)T * g.Cin, s));
+    if (m.use16()) TACO_TRY(launch_cast2d_bf16(static_cast<uint16_t*>(m.W16(px + "xin_p")) + (long long)g.PL * g.Cin, inputs, N, T * g.Cin,
+                                               (long long)g.Tp * g.Cin, (long long)T * g.Cin, s));
+    TACO_TRY(cbhg_forward(m, g, input_lengths, before_highway, rnn_init_state, is_training, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(outputs, m.W(px + "rnn_out"), sizeof(float) * (size_t)N * T * 2 * g.H, cudaMemcpyDeviceToDevice, s));
+    return TACO_OK;
+}
+
+int taco_cbhg_backward(taco_model h, int32_t which, const float* d_outputs, const int32_t* input_lengths, int32_t N, int32_t T,
+                       float* d_inputs, float* d_before_highway, float* d_rnn_init_state, void* stream) {
+    TACO_REQUIRE(h && d_outputs && d_inputs, TACO_EINVAL, "taco_cbhg_backward: null argument");
+    Model& m = h->m;
+    TACO_ON_DEVICE(m.cfg.device);
+    const CbhgGeom* gp = nullptr;
+    TACO_TRY(block_geom(m, which, N, T, &gp));
+    const CbhgGeom& g = *gp;
+    TACO_REQUIRE(m.shape.training && m.grads, TACO_ESTATE, "taco_cbhg_backward: needs a training plan and a bound gradient buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TACO_TRY(sched_init());
+    const std::string px = g.prefix + "/";
+    TACO_TRY(backward_prep(m, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(m.W(px + "d_rnn_out"), d_outputs, sizeof(float) * (size_t)N * T * 2 * g.H, cudaMemcpyDeviceToDevice, s));
+    TACO_TRY(cbhg_backward(m, g, input_lengths, d_before_highway != nullptr, d_rnn_init_state != nullptr, s));
+    TACO_TRY(launch_copy2d(d_inputs, m.W(px + "d_xin_p") + (long long)g.PL * g.Cin, N, T * g.Cin, (long long)T * g.Cin, (long long)g.Tp * g.Cin, s));
+    if (d_before_highway) TACO_CHECK_CUDA(cudaMemcpyAsync(d_before_highway, m.W(px + "d_before"), sizeof(float) * (size_t)N * g.P2, cudaMemcpyDeviceToDevice, s));
+    if (d_rnn_init_state) TACO_CHECK_CUDA(cudaMemcpyAsync(d_rnn_init_state, m.W(px + "d_h0"), sizeof(float) * (size_t)N * 2 * g.H, cudaMemcpyDeviceToDevice, s));
+    return TACO_OK;
+}
+
+int taco_decoder_forward(taco_model h, const taco_batch* b, const float* memory, void* stream) {
+    TACO_REQUIRE(h && b && memory, TACO_EINVAL, "taco_decoder_forward: null argument");
+    Model& m = h->m;
+    TACO_ON_DEVICE(m.cfg.device);
+    Shape sh;
+    TACO_TRY(shape_of(m, b, sh));
+    TACO_TRY(ensure_plan(m, sh));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TACO_TRY(sched_init());
+    m.img_w_state = 0; m.img_bkm_state = 0; m.prep_done = false;
+    TACO_TRY(refresh_params16(m, s));
+    TACO_TRY(speaker_forward(m, b, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(m.W("enc_cbhg/rnn_out"), memory, sizeof(float) * (size_t)sh.N * sh.Ti * 2 * m.cfg.enc_rnn_size, cudaMemcpyDeviceToDevice, s));
+    return decoder_forward(m, b, s);
+}
+
+int taco_decoder_backward(taco_model h, const taco_batch* b, const float* d_mel_outputs, float* d_memory, void* stream) {
+    TACO_REQUIRE(h && b && d_mel_outputs && d_memory, TACO_EINVAL, "taco_decoder_backward: null argument");
+    Model& m = h->m;
+    TACO_ON_DEVICE(m.cfg.device);
+    Shape sh;
+    TACO_TRY(shape_of(m, b, sh));
+    TACO_REQUIRE(m.planned && m.shape == sh && sh.training && m.grads, TACO_ESTATE, "taco_decoder_backward: call taco_decoder_forward with the same training batch first");
+    TACO_REQUIRE(!b->rnn_decoder_test_mode, TACO_ESTATE, "backward through the free-running decoder is not defined");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const CbhgGeom& g = m.post;
+    const int M = m.cfg.num_mels;
+    TACO_TRY(backward_prep(m, s));
+    // gradient wrt the mel outputs, in the post-net's padded input layout (pad frames stay zero)
+    TACO_TRY(launch_copy2d(m.W("post_cbhg/d_xin_p") + (long long)g.PL * M, d_mel_outputs, sh.N, sh.To * M, (long long)g.Tp * M, (long long)sh.To * M, s));
+    TACO_TRY(decoder_backward(m, b, s));
+    TACO_CHECK_CUDA(cudaMemcpyAsync(d_memory, m.W("enc_cbhg/d_rnn_out"), sizeof(float) * (size_t)sh.N * sh.Ti * 2 * m.cfg.enc_rnn_size, cudaMemcpyDeviceToDevice, s));
+    return TACO_OK;
+}
+
+// y = H*T + x*(1-T) on [rows, C] fp32 matrices (the element-wise half of highwaynet, modules.py:105-120)
+int taco_highway_combine(const float* H, const float* T, const float* x, float* y, int64_t rows, int32_t C, void* stream) {
+    TACO_REQUIRE(H && T && x && y && rows > 0 && C > 0 && C % 4 == 0, TACO_EINVAL, "taco_highway_combine: bad argument (C must be a multiple of 4)");
+    return launch_highway_fwd(H, T, x, y, (long long)rows * C, static_cast<cudaStream_t>(stream));
+}
+
+// tf.layers.batch_normalization over the last axis of x [N,T,C] (eps 1e-3; modules.py:131): training: biased batch moments over all
+// N*T frames (written to batch_mean / batch_var); otherwise the given moving statistics
+int taco_batch_norm(const float* x, const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                    int32_t N, int32_t T, int32_t C, int32_t is_training, float* y, float* batch_mean, float* batch_var, void* scratch, void* stream) {
+    TACO_REQUIRE(x && gamma && beta && moving_mean && moving_var && y && scratch && N > 0 && T > 0 && C > 0 && C % 4 == 0, TACO_EINVAL,
+                 "taco_batch_norm: bad argument (C must be a multiple of 4; scratch: 4*C doubles)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double* st = static_cast<double*>(scratch);                    // [2C] sums, then [C] mean | [C] rstd | [C] var as floats behind them
+    float* mean = reinterpret_cast<float*>(st + 2 * C); float* rstd = mean + C; float* var = rstd + C;
+    if (is_training) {
+        // statistics through the GEMM-free path: x . I is not needed - a [rows, C] column sum / sum of squares in double
+        TACO_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(double) * 2 * C, s));
+        TACO_TRY(launch_colstats(x, st, st + C, (long long)N * T, C, s));
+    }
+    TACO_TRY(launch_bn_finalize(st, st + C, (double)N * T, mean, rstd, var, moving_mean, moving_var, C, is_training, s));
+    TACO_TRY(launch_bn_apply(x, mean, rstd, gamma, beta, nullptr, nullptr, y, N, T, T, 0, C, 0, s));
+    if (is_training && batch_mean) TACO_CHECK_CUDA(cudaMemcpyAsync(batch_mean, mean, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
+    if (is_training && batch_var) TACO_CHECK_CUDA(cudaMemcpyAsync(batch_var, var, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
     return TACO_OK;
 }
 

@@ -127,6 +127,71 @@ class Engine:
         base = self._ws.view(dt)
         return torch.as_strided(base, [dims[i] for i in range(nd)], [strides[i] for i in range(nd)], off.value // esz)
 
+    # ---- block level (taco_cbhg_* / taco_decoder_*: SURVEY.md 8b) -------------------------------------------
+    def plan(self, N: int, T_in: int, T_out: int, training: bool = True) -> None:
+        """Size and bind the workspace for a batch shape without running anything (block-level calls need a planned shape)."""
+        self._ensure_workspace(N, T_in, T_out if training else T_out // self.hp.reduction_factor, training)
+
+    def cbhg_forward(self, which: int, inputs, input_lengths=None, before_highway=None, rnn_init_state=None, is_training: bool = True):
+        x = self._f32(inputs)
+        N, T, _ = x.shape
+        H2 = 2 * (self.hp.post_rnn_size if which else self.hp.enc_rnn_size)
+        out = torch.empty(N, T, H2, device=self.dev, dtype=torch.float32)
+        L, bh, h0 = self._i32(input_lengths), self._f32(before_highway), self._f32(rnn_init_state)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._blk_keep = [x, L, bh, h0]
+        capi.check(self.lib.taco_cbhg_forward(self._h, which, x.data_ptr(), ptr(L), ptr(bh), ptr(h0), N, T, 1 if is_training else 0,
+                                              out.data_ptr(), self._stream()))
+        return out
+
+    def cbhg_backward(self, which: int, d_outputs, input_lengths=None, want_before: bool = False, want_init_state: bool = False):
+        """Gradients accumulate into ``self.grads`` (zero it first); returns (d_inputs, d_before_highway, d_rnn_init_state)."""
+        dy = self._f32(d_outputs)
+        N, T, _ = dy.shape
+        cin = self.hp.num_mels if which else self.hp.enc_prenet_sizes[-1]
+        p2 = self.hp.post_proj_sizes[-1] if which else self.hp.enc_proj_sizes[-1]
+        H2 = 2 * (self.hp.post_rnn_size if which else self.hp.enc_rnn_size)
+        dx = torch.empty(N, T, cin, device=self.dev, dtype=torch.float32)
+        db = torch.empty(N, p2, device=self.dev) if want_before else None
+        dh = torch.empty(N, H2, device=self.dev) if want_init_state else None
+        L = self._i32(input_lengths)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        capi.check(self.lib.taco_cbhg_backward(self._h, which, dy.data_ptr(), ptr(L), N, T, dx.data_ptr(), ptr(db), ptr(dh), self._stream()))
+        return dx, db, dh
+
+    def _batch_struct(self, inputs, input_lengths, speaker_id, mel_targets, linear_targets, decoder_steps, manual_alignments, test_mode):
+        b = capi.TacoBatch()
+        N, T_in = inputs.shape
+        b.N, b.T_in, b.T_out = N, T_in, (mel_targets.shape[1] if mel_targets is not None else 0)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        b.inputs, b.input_lengths, b.speaker_id = ptr(inputs), ptr(input_lengths), ptr(speaker_id)
+        b.mel_targets, b.linear_targets, b.loss_coeff = ptr(mel_targets), ptr(linear_targets), None
+        b.manual_alignments, b.decoder_steps, b.rnn_decoder_test_mode = ptr(manual_alignments), decoder_steps, 1 if test_mode else 0
+        return b
+
+    def decoder_forward(self, memory, inputs, input_lengths, speaker_id=None, mel_targets=None, linear_targets=None, decoder_steps: int = 0,
+                        manual_alignments=None, rnn_decoder_test_mode: bool = False):
+        """The attention decoder on a given encoder memory [N,T_in,2*enc_rnn] (``taco_decoder_forward``): teacher-forced when targets
+        are given (pass ``linear_targets`` - any tensor of the right shape - to select the training plan), free-running otherwise."""
+        mem = self._f32(memory)
+        inputs, input_lengths, speaker_id = self._i32(inputs), self._i32(input_lengths), self._i32(speaker_id)
+        mel_targets, linear_targets, manual_alignments = self._f32(mel_targets), self._f32(linear_targets), self._f32(manual_alignments)
+        training = linear_targets is not None
+        T_out = mel_targets.shape[1] if mel_targets is not None else 0
+        self._ensure_workspace(inputs.shape[0], inputs.shape[1], T_out if training else (decoder_steps or T_out // self.hp.reduction_factor), training)
+        b = self._batch_struct(inputs, input_lengths, speaker_id, mel_targets, linear_targets, decoder_steps, manual_alignments, rnn_decoder_test_mode)
+        self._batch = b
+        self._keep = [mem, inputs, input_lengths, speaker_id, mel_targets, linear_targets, manual_alignments]
+        capi.check(self.lib.taco_decoder_forward(self._h, C.byref(b), mem.data_ptr(), self._stream()))
+        return dict(mel_outputs=self.region("mel_outputs"), alignments=self.region("alignments"))
+
+    def decoder_backward(self, d_mel_outputs):
+        dm = self._f32(d_mel_outputs)
+        N, T_in = self._batch.N, self._batch.T_in
+        d_mem = torch.empty(N, T_in, 2 * self.hp.enc_rnn_size, device=self.dev, dtype=torch.float32)
+        capi.check(self.lib.taco_decoder_backward(self._h, C.byref(self._batch), dm.data_ptr(), d_mem.data_ptr(), self._stream()))
+        return d_mem
+
     # ---- hot path ---------------------------------------------------------------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream
