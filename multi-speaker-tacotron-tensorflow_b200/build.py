@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtaco_b200.so")
-SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "gemm_bf16.cu", "elementwise.cu", "gru.cu", "gru_fast.cu", "attention.cu", "att_fast.cu", "optim.cu", "model_cbhg.cu", "model_decoder.cu",
+SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "gemm_bf16.cu", "elementwise.cu", "gru.cu", "gru_fast.cu", "attention.cu", "att_fast.cu", "att_free.cu", "optim.cu", "model_cbhg.cu", "model_decoder.cu",
            "model.cu", "griffin_lim.cu", "hostutil.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

@@ -77,8 +77,21 @@ __device__ __forceinline__ void af_mma_run(float acc[4], const bf16* Wt, int KP,
         bfr[kk][0] = *reinterpret_cast<const uint32_t*>(vec + ((ka / UB) * AF_R + g) * UB + (ka % UB));
         bfr[kk][1] = *reinterpret_cast<const uint32_t*>(vec + ((kb / UB) * AF_R + g) * UB + (kb % UB));
     }
+    // one accumulator per k-tile, summed afterwards: a DEPENDENT mma.sync costs ~100 clk here (tools/gru_phase_prof.py), so a chain
+    // of NK (or, over two calls on one accumulator, of 6) set the phase time rather than the issue rate
+    float c[NK][4];
 #pragma unroll
-    for (int kk = 0; kk < NK; kk++) af_mma(acc, af[kk][0], af[kk][1], af[kk][2], af[kk][3], bfr[kk][0], bfr[kk][1]);
+    for (int kk = 0; kk < NK; kk++) {
+        c[kk][0] = 0.f; c[kk][1] = 0.f; c[kk][2] = 0.f; c[kk][3] = 0.f;
+        af_mma(c[kk], af[kk][0], af[kk][1], af[kk][2], af[kk][3], bfr[kk][0], bfr[kk][1]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        float t = c[0][e];
+#pragma unroll
+        for (int kk = 1; kk < NK; kk++) t += c[kk][e];
+        acc[e] += t;
+    }
 }
 // fragment -> red[slot][m][r]  (16 rows x 8 batch rows per slot)
 __device__ __forceinline__ void af_red_store(float* red, int slot, const float acc[4], int lane) {

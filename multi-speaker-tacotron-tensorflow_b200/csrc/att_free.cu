@@ -1,0 +1,564 @@
+// Free-running decoder step for low-batch synthesis (BASELINE C4: batch 1, 200 steps -> 1000 frames) as ONE persistent
+// kernel with every weight of the step resident in shared memory.
+//   reference: models/rnn_wrappers.py:218-341 (AttentionWrapper), :367-378 (DecoderPrenetWrapper), :405-415 (concat
+//   wrapper); models/tacotron.py:127-179 (cell stack, mel projection); models/helpers.py:9-32 (TacoTestHelper: the last of
+//   the r frames of step t is the input of step t+1; <GO> frame of zeros).
+//
+// Why another kernel: the general free-running path (attention.cu) streams the step's 3 MB of bf16 weights from L2 in every
+// one of its 13 phases and separates the phases with full cluster barriers - 42 us per decoder step, almost all of it L2 and
+// barrier latency on 8 SMs (profiles/r2_synth_launches.summary.txt: 8.6 of the 10.8 ms C4 forward).  With ONE utterance per
+// cluster nothing but latency matters, so the mapping is chosen for the dependent chain alone:
+//   * one non-portable cluster of 16 CTAs per utterance; CTA `rank` owns 1/16 of every layer's output units and holds
+//     its slice of ALL weights of the step (attention cell, both residual GRUs, mel projection: 187 KB of bf16 rows) in
+//     shared memory for all steps, beside its slice of the attention keys / memory;
+//   * a batch row of one makes every product a matrix-VECTOR product: plain fp32 FMAs over bf16 weight rows - a half-warp
+//     per output unit, 16-byte shared-memory loads, butterfly reduction - instead of tensor-core tiles that would be
+//     7/8 padding (mma N = 8) and need a cross-warp reduction through shared memory;
+//   * activations travel as fp32 (no operand rounding at all) with st.async DSMEM stores that complete on the receiver's
+//     mbarrier; there is NO __syncthreads and no cluster barrier inside the step: every warp computes its two units,
+//     pushes 8 bytes to each peer and waits for the next vector on its own.  Single receive buffers are safe by the
+//     argument of DESIGN.md 3.2 applied per warp: a vector of step t+1 can only be complete once every warp of every CTA has
+//     contributed to the vector before it, i.e. has finished reading the step-t copy.
+// Alignments (monotonic scan / softmax) are recomputed by every warp from the exchanged scores, so their state lives in
+// registers and the context needs no further synchronisation.
+#include "common.cuh"
+#include "kernels.h"
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cfloat>
+
+namespace cg = cooperative_groups;
+
+namespace taco {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int FR_C = 16, FR_NT = 256;
+constexpr int FR_E = 256, FR_A = 256, FR_HA = 256, FR_Z1 = 256, FR_Z = 128, FR_Y = 256, FR_M = 80;     // instantiated sizes
+constexpr int FR_U = 16, FR_UZ = 8;            // units per CTA of the 256- / 128-wide layers
+constexpr int FR_UO_PAD = 32;                  // mel-projection columns per CTA (<= 32: M*r <= 512)
+constexpr int FR_CHM = 8;                      // alignment positions per lane (T_in <= 256)
+
+// ---- weight image of one cluster rank: bf16 rows [unit][K], element offsets ---------------------------------------------
+enum FrW { FRW_W1C = 0, FRW_W1X, FRW_W2, FRW_WG, FRW_WCZ, FRW_WCH, FRW_WQ, FRW_WOH, FRW_WOC,
+           FRW_G1G, FRW_G1CX, FRW_G1CH, FRW_G2G, FRW_G2CX, FRW_G2CH, FRW_MEL, FRW_N };
+struct FrOff {
+    static constexpr int W1c = 0;                               // [16][256]  dense_1, context rows
+    static constexpr int W1x = W1c + FR_U * FR_E;               // [16][80]   dense_1, frame rows
+    static constexpr int W2 = W1x + FR_U * FR_M;                // [8][256]
+    static constexpr int Wg = W2 + FR_UZ * FR_Z1;               // [32][384]  r units | u units; k over [z ; ha]
+    static constexpr int Wcz = Wg + 2 * FR_U * (FR_Z + FR_HA);  // [16][128]
+    static constexpr int Wch = Wcz + FR_U * FR_Z;               // [16][256]
+    static constexpr int Wq = Wch + FR_U * FR_HA;               // [16][256]
+    static constexpr int Woh = Wq + FR_U * FR_HA;               // [16][256]
+    static constexpr int Woc = Woh + FR_U * FR_HA;              // [16][256]
+    static constexpr int G1g = Woc + FR_U * FR_E;               // [32][512]  r | u; k over [x ; h]
+    static constexpr int G1cx = G1g + 2 * FR_U * 2 * FR_Y;      // [16][256]
+    static constexpr int G1ch = G1cx + FR_U * FR_Y;             // [16][256]
+    static constexpr int G2g = G1ch + FR_U * FR_Y;
+    static constexpr int G2cx = G2g + 2 * FR_U * 2 * FR_Y;
+    static constexpr int G2ch = G2cx + FR_U * FR_Y;
+    static constexpr int Wmel = G2ch + FR_U * FR_Y;             // [32][256]  rows past this CTA's columns are zero
+    static constexpr int end = Wmel + FR_UO_PAD * FR_Y;
+};
+constexpr size_t FR_W_BYTES = (size_t)FrOff::end * 2;           // 190 976
+
+// row i of matrix `m`, rank `rank`: column  (i < split ? offA + rank*UA + i : offB + rank*UB + i - split)  of W[(row0 + k)*ld + col]
+struct FrSpec { const float* W; int ld, row0, K, rows, split, offA, UA, offB, UB, own, col_limit, off; };
+struct FrTable { FrSpec s[FRW_N]; };
+
+__global__ void __launch_bounds__(256) fr_pack_kernel(const __grid_constant__ FrTable tb, bf16* __restrict__ img) {
+    const FrSpec& sp = tb.s[blockIdx.y];
+    const int rank = blockIdx.x;
+    bf16* dst = img + (size_t)rank * FrOff::end + sp.off;
+    for (int idx = threadIdx.x; idx < sp.rows * sp.K; idx += blockDim.x) {
+        const int k = idx / sp.rows, i = idx % sp.rows;         // consecutive threads read consecutive columns of one weight row
+        const int col = i < sp.split ? sp.offA + rank * sp.UA + i : sp.offB + rank * sp.UB + (i - sp.split);
+        const bool ok = (i < sp.split ? i < sp.own : true) && col < sp.col_limit;
+        dst[(size_t)i * sp.K + k] = __float2bfloat16(ok ? __ldg(sp.W + (long long)(sp.row0 + k) * sp.ld + col) : 0.f);
+    }
+}
+
+// ---- device helpers ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fr_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fr_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(fr_u32(bar)), "r"(parity) : "memory");
+}
+// lanes 0..15 of the calling warp: store 8 / 4 bytes at `dst` (own-CTA address of the slot) in peer `lane`, completing on its `bar`
+__device__ __forceinline__ void fr_push2(float v0, float v1, const float* dst, uint64_t* bar, int lane) {
+    if (lane < FR_C) {
+        uint32_t d, b;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(lane));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(lane));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                     ::"r"(d), "r"(__float_as_uint(v0)), "r"(__float_as_uint(v1)), "r"(b) : "memory");
+    }
+}
+__device__ __forceinline__ void fr_push1(float v, const float* dst, uint64_t* bar, int peer, bool on) {
+    if (on) {
+        uint32_t d, b;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(peer));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                     ::"r"(d), "r"(__float_as_uint(v)), "r"(b) : "memory");
+    }
+}
+__device__ __forceinline__ float fr_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fr_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fr_lo(uint32_t w) { return __uint_as_float(w << 16); }            // bf16 pair -> fp32
+__device__ __forceinline__ float fr_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float fr_half_sum(float v) {      // sum over the 16 lanes of a half-warp (every lane gets it)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// 8 weights (one 16-byte chunk of a bf16 row) . 8 operand values;  the operand is the elementwise sum of NV fp32 vectors
+template <int NV>
+__device__ __forceinline__ float fr_dot8(const bf16* wrow, const float* v0, const float* v1, const float* v2, int ch) {
+    const uint4 w = *reinterpret_cast<const uint4*>(wrow + 8 * ch);
+    float4 a = *reinterpret_cast<const float4*>(v0 + 8 * ch), b = *reinterpret_cast<const float4*>(v0 + 8 * ch + 4);
+    if (NV > 1) {
+        const float4 c = *reinterpret_cast<const float4*>(v1 + 8 * ch), d = *reinterpret_cast<const float4*>(v1 + 8 * ch + 4);
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    if (NV > 2) {
+        const float4 c = *reinterpret_cast<const float4*>(v2 + 8 * ch), d = *reinterpret_cast<const float4*>(v2 + 8 * ch + 4);
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    float s0 = fr_lo(w.x) * a.x, s1 = fr_hi(w.x) * a.y;
+    s0 = fmaf(fr_lo(w.y), a.z, s0); s1 = fmaf(fr_hi(w.y), a.w, s1);
+    s0 = fmaf(fr_lo(w.z), b.x, s0); s1 = fmaf(fr_hi(w.z), b.y, s1);
+    s0 = fmaf(fr_lo(w.w), b.z, s0); s1 = fmaf(fr_hi(w.w), b.w, s1);
+    return s0 + s1;
+}
+// partial dot product of one bf16 weight row of length K with the operand, split over LANES lanes (l = lane index in the group):
+// lane l takes the 16-byte chunks l, l + LANES, ... (consecutive lanes read consecutive chunks: conflict-free)
+template <int K, int NV, int LANES>
+__device__ __forceinline__ float fr_dot(const bf16* wrow, const float* v0, const float* v1, const float* v2, int l) {
+    constexpr int CHUNKS = K / 8, IT = (CHUNKS + LANES - 1) / LANES;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < IT; c++) {
+        const int ch = c * LANES + l;
+        if (CHUNKS % LANES == 0 || ch < CHUNKS) s += fr_dot8<NV>(wrow, v0, v1, v2, ch);
+    }
+    return s;
+}
+
+struct FrSmem {      // byte offsets behind the weight image; Tip = 16*ceil(Ti/16), MP = 32*ceil(Tip/32)
+    int keys, mem, vec, bars, total;
+    __host__ __device__ FrSmem(int Ti) {
+        const int TJ = (Ti + FR_C - 1) / FR_C, Tip = TJ * FR_C, MP = (Tip + 31) / 32 * 32;
+        keys = (int)FR_W_BYTES;                                  // bf16 [TJ][256]   own memory positions
+        mem = keys + TJ * FR_A * 2;                              // bf16 [16][MP]    own context units, position-contiguous
+        vec = mem + FR_U * MP * 2;                               // fp32 vectors (see the kernel)
+        const int nvec = FR_Z1 + FR_Z + 2 * FR_HA + FR_A + MP + FR_E + 5 * FR_Y + 96;
+        bars = vec + nvec * 4;
+        total = bars + 16 * 8;
+    }
+};
+
+__global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, const uint8_t* __restrict__ img) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int n = blockIdx.x / FR_C;                              // utterance of this cluster
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l16 = lane & 15, hw = warp * 2 + (lane >> 4);       // half-warp hw owns unit hw of this CTA's 16
+    const int Ti = a.Ti, Td = a.Td;
+    const int TJ = (Ti + FR_C - 1) / FR_C, Tip = TJ * FR_C, MP = (Tip + 31) / 32 * 32, CH = MP / 32;
+    const int MR = a.M * a.r, UO = (MR + FR_C - 1) / FR_C;
+    const FrSmem L(Ti);
+
+    extern __shared__ __align__(128) uint8_t sm[];
+    const bf16* Wt = reinterpret_cast<const bf16*>(sm);
+    bf16* keys_s = reinterpret_cast<bf16*>(sm + L.keys);
+    bf16* mem_s = reinterpret_cast<bf16*>(sm + L.mem);
+    float* fp = reinterpret_cast<float*>(sm + L.vec);
+    float* z1_s = fp;  fp += FR_Z1;
+    float* z_s = fp;   fp += FR_Z;
+    float* ha_s = fp;  fp += FR_HA;
+    float* rha_s = fp; fp += FR_HA;
+    float* q_s = fp;   fp += FR_A;
+    float* e_s = fp;   fp += MP;
+    float* ctx_s = fp; fp += FR_E;
+    float* y0_s = fp;  fp += FR_Y;
+    float* rh1_s = fp; fp += FR_Y;
+    float* h1_s = fp;  fp += FR_Y;
+    float* rh2_s = fp; fp += FR_Y;
+    float* h2_s = fp;  fp += FR_Y;
+    float* x_s = fp;                                              // [80] (+16 pad)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint64_t *b_z1 = bars, *b_z = bars + 1, *b_rha = bars + 2, *b_ha = bars + 3, *b_q = bars + 4, *b_e = bars + 5, *b_ctx = bars + 6,
+             *b_y0 = bars + 7, *b_rh1 = bars + 8, *b_h1 = bars + 9, *b_rh2 = bars + 10, *b_h2 = bars + 11, *b_x = bars + 12, *b_img = bars + 13;
+
+    // ---- prologue: weight image (bulk async copies), key / memory slices, initial state ---------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < 13; i++) fr_mbar_init(bars + i, 1);
+        fr_mbar_init(b_img, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fr_expect(b_img, (uint32_t)FR_W_BYTES);
+        const uint8_t* src = img + (size_t)rank * FR_W_BYTES;
+        for (size_t off = 0; off < FR_W_BYTES; off += 32768) {
+            const uint32_t nb = (uint32_t)((FR_W_BYTES - off) < 32768 ? (FR_W_BYTES - off) : 32768);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(fr_u32(sm + off)), "l"(src + off), "r"(nb), "r"(fr_u32(b_img)) : "memory");
+        }
+    }
+    for (int idx = tid; idx < TJ * FR_A; idx += FR_NT) {
+        const int jj = idx / FR_A, u = idx % FR_A, j = rank * TJ + jj;
+        keys_s[idx] = __float2bfloat16(j < Ti ? __ldg(a.keys + ((long long)n * Ti + j) * FR_A + u) : 0.f);
+    }
+    for (int idx = tid; idx < FR_U * MP; idx += FR_NT) {
+        const int j = idx / FR_U, i = idx % FR_U;                 // consecutive threads read consecutive units of one position
+        mem_s[i * MP + j] = __float2bfloat16(j < Ti ? __ldg(a.memory + ((long long)n * Ti + j) * FR_E + rank * FR_U + i) : 0.f);
+    }
+    for (int k = tid; k < FR_HA; k += FR_NT) {
+        ha_s[k] = a.ha0 ? a.ha0[(long long)n * FR_HA + k] : 0.f;
+        h1_s[k] = a.h1_0 ? a.h1_0[(long long)n * FR_Y + k] : 0.f;
+        h2_s[k] = a.h2_0 ? a.h2_0[(long long)n * FR_Y + k] : 0.f;
+        ctx_s[k] = 0.f;
+    }
+    for (int k = tid; k < 96; k += FR_NT) x_s[k] = 0.f;           // <GO> frame (helpers.py:70-72)
+    for (int k = tid; k < MP; k += FR_NT) e_s[k] = 0.f;
+    const uint32_t e_bytes = (uint32_t)Tip * 4, x_bytes = (uint32_t)a.M * 4;
+    if (tid == 0) {
+        fr_expect(b_z1, FR_Z1 * 4); fr_expect(b_z, FR_Z * 4); fr_expect(b_rha, FR_HA * 4); fr_expect(b_ha, FR_HA * 4);
+        fr_expect(b_q, FR_A * 4); fr_expect(b_e, e_bytes); fr_expect(b_ctx, FR_E * 4); fr_expect(b_y0, FR_Y * 4);
+        fr_expect(b_rh1, FR_Y * 4); fr_expect(b_h1, FR_Y * 4); fr_expect(b_rh2, FR_Y * 4); fr_expect(b_h2, FR_Y * 4);
+        fr_expect(b_x, x_bytes);
+    }
+    // per-unit constants of this half-warp (unit = rank*16 + hw) and of this warp (z unit = rank*8 + warp)
+    const int unit = rank * FR_U + hw;
+    float ha_own = a.ha0 ? a.ha0[(long long)n * FR_HA + unit] : 0.f;
+    float h1_own = a.h1_0 ? a.h1_0[(long long)n * FR_Y + unit] : 0.f;
+    float h2_own = a.h2_0 ? a.h2_0[(long long)n * FR_Y + unit] : 0.f;
+    const float b1_own = __ldg(a.b1 + unit), b2_own = __ldg(a.b2 + rank * FR_UZ + warp);
+    const float bgr = __ldg(a.bg + unit), bgu = __ldg(a.bg + FR_HA + unit), bc_own = __ldg(a.bc + unit), bo_own = __ldg(a.bo + unit);
+    const float bg1r = __ldg(a.bg1 + unit), bg1u = __ldg(a.bg1 + FR_Y + unit), bc1 = __ldg(a.bc1 + unit);
+    const float bg2r = __ldg(a.bg2 + unit), bg2u = __ldg(a.bg2 + FR_Y + unit), bc2 = __ldg(a.bc2 + unit);
+    const float score_bias = (a.att_type == TACO_ATT_BAH_MON) ? a.score_bias[0] : 0.f;
+    float vreg[8];                                                // attention vector v, units [8*lane, 8*lane + 8)
+#pragma unroll
+    for (int k = 0; k < 8; k++) vreg[k] = __ldg(a.v + 8 * lane + k);
+    // mel projection: this half-warp's columns in the two rounds (UO <= 32)
+    const int mi0 = hw, mi1 = FR_U + hw;
+    const int mc0 = rank * UO + mi0, mc1 = rank * UO + mi1;
+    const bool mok0 = mi0 < UO && mc0 < MR, mok1 = mi1 < UO && mc1 < MR;
+    const float bm0 = mok0 ? __ldg(a.bmel + mc0) : 0.f, bm1 = mok1 ? __ldg(a.bmel + mc1) : 0.f;
+    // previous alignments of this lane's positions [lane*CH, lane*CH + CH)   (every warp keeps the same copy)
+    float av[FR_CHM];
+#pragma unroll
+    for (int k = 0; k < FR_CHM; k++) av[k] = (a.att_type == TACO_ATT_BAH_MON && lane * CH + k == 0 && k < CH) ? 1.f : 0.f;
+    __syncthreads();
+    fr_wait(b_img, 0);
+    cl.sync();
+
+    const bf16* W1c = Wt + FrOff::W1c + hw * FR_E;   const bf16* W1x = Wt + FrOff::W1x + hw * FR_M;
+    const bf16* W2 = Wt + FrOff::W2 + warp * FR_Z1;
+    const bf16* Wgr = Wt + FrOff::Wg + hw * (FR_Z + FR_HA); const bf16* Wgu = Wt + FrOff::Wg + (FR_U + hw) * (FR_Z + FR_HA);
+    const bf16* Wcz = Wt + FrOff::Wcz + hw * FR_Z;   const bf16* Wch = Wt + FrOff::Wch + hw * FR_HA;
+    const bf16* Wq = Wt + FrOff::Wq + hw * FR_HA;    const bf16* Woh = Wt + FrOff::Woh + hw * FR_HA;
+    const bf16* Woc = Wt + FrOff::Woc + hw * FR_E;
+    const bf16* G1r = Wt + FrOff::G1g + hw * 2 * FR_Y;  const bf16* G1u = Wt + FrOff::G1g + (FR_U + hw) * 2 * FR_Y;
+    const bf16* G1cx = Wt + FrOff::G1cx + hw * FR_Y;    const bf16* G1ch = Wt + FrOff::G1ch + hw * FR_Y;
+    const bf16* G2r = Wt + FrOff::G2g + hw * 2 * FR_Y;  const bf16* G2u = Wt + FrOff::G2g + (FR_U + hw) * 2 * FR_Y;
+    const bf16* G2cx = Wt + FrOff::G2cx + hw * FR_Y;    const bf16* G2ch = Wt + FrOff::G2ch + hw * FR_Y;
+    const bf16* Wm0 = Wt + FrOff::Wmel + mi0 * FR_Y;    const bf16* Wm1 = Wt + FrOff::Wmel + mi1 * FR_Y;
+    const bool armer = (tid == 0);
+    // the warp's two units as one 8-byte slot: lanes < 16 hold the first half-warp's value in `mine`, the second's in `other`
+    auto pair_push = [&](float val, float* vec, uint64_t* bar) {
+        const float oth = __shfl_xor_sync(0xffffffffu, val, 16);
+        fr_push2(val, oth, vec + rank * FR_U + 2 * warp, bar, lane);
+    };
+    // wait for a vector of this step; thread 0 re-arms its barrier for the next step right behind its own wait
+    auto recv = [&](uint64_t* bar, uint32_t par, uint32_t bytes, bool more) {
+        fr_wait(bar, par);
+        if (armer && more) fr_expect(bar, bytes);
+    };
+
+    for (int t = 0; t < Td; t++) {
+        const uint32_t par = t & 1;
+        const bool more = t + 1 < Td;
+        // ===== P1: z1 = relu(b1 + W1x.x + W1c.ctx)   (x, ctx of the previous step; rnn_wrappers.py:367-378) =====
+        if (t > 0) recv(b_x, (t - 1) & 1, x_bytes, more);
+        {
+            float s = fr_dot<FR_E, 1, 16>(W1c, ctx_s, nullptr, nullptr, l16) + fr_dot<FR_M, 1, 16>(W1x, x_s, nullptr, nullptr, l16);
+            s = fr_half_sum(s);
+            pair_push(fmaxf(s + b1_own, 0.f), z1_s, b_z1);
+        }
+        recv(b_z1, par, FR_Z1 * 4, more);
+        // ===== P2: z = relu(W2.z1 + b2)   (one unit per warp) =====
+        {
+            float s = warp_sum(fr_dot<FR_Z1, 1, 32>(W2, z1_s, nullptr, nullptr, lane));
+            fr_push1(fmaxf(s + b2_own, 0.f), z_s + rank * FR_UZ + warp, b_z, lane, lane < FR_C);
+        }
+        recv(b_z, par, FR_Z * 4, more);
+        // ===== P3: attention-GRU gates over [z ; ha] and the z part of the candidate =====
+        float ug, cz;
+        {
+            float sr = fr_dot<FR_Z, 1, 16>(Wgr, z_s, nullptr, nullptr, l16) + fr_dot<FR_HA, 1, 16>(Wgr + FR_Z, ha_s, nullptr, nullptr, l16);
+            float su = fr_dot<FR_Z, 1, 16>(Wgu, z_s, nullptr, nullptr, l16) + fr_dot<FR_HA, 1, 16>(Wgu + FR_Z, ha_s, nullptr, nullptr, l16);
+            float sc = fr_dot<FR_Z, 1, 16>(Wcz, z_s, nullptr, nullptr, l16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o); su += __shfl_xor_sync(0xffffffffu, su, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            }
+            const float rg = fr_sigmoid(sr + bgr);
+            ug = fr_sigmoid(su + bgu); cz = sc;
+            pair_push(rg * ha_own, rha_s, b_rha);
+        }
+        recv(b_rha, par, FR_HA * 4, more);
+        // ===== P4: candidate and new attention-GRU state =====
+        {
+            const float s = fr_half_sum(fr_dot<FR_HA, 1, 16>(Wch, rha_s, nullptr, nullptr, l16));
+            const float cc = fr_tanh(s + cz + bc_own);
+            ha_own = ug * ha_own + (1.f - ug) * cc;
+            pair_push(ha_own, ha_s, b_ha);
+        }
+        recv(b_ha, par, FR_HA * 4, more);
+        // ===== P5: query and the ha part of the concat projection =====
+        float yh;
+        {
+            float sq = fr_dot<FR_HA, 1, 16>(Wq, ha_s, nullptr, nullptr, l16), sy = fr_dot<FR_HA, 1, 16>(Woh, ha_s, nullptr, nullptr, l16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+            yh = sy;
+            pair_push(sq, q_s, b_q);
+        }
+        recv(b_q, par, FR_A * 4, more);
+        // ===== P6: scores of the own TJ memory positions (a warp per position): e_j = sum_u v_u tanh(keys_ju + q_u) + b =====
+        {
+            const float4 q0 = *reinterpret_cast<const float4*>(q_s + 8 * lane), q1 = *reinterpret_cast<const float4*>(q_s + 8 * lane + 4);
+            for (int jj = warp; jj < TJ; jj += FR_NT / 32) {
+                const uint4 kk = *reinterpret_cast<const uint4*>(keys_s + (size_t)jj * FR_A + 8 * lane);
+                float s0 = vreg[0] * fr_tanh(fr_lo(kk.x) + q0.x), s1 = vreg[1] * fr_tanh(fr_hi(kk.x) + q0.y);
+                s0 = fmaf(vreg[2], fr_tanh(fr_lo(kk.y) + q0.z), s0); s1 = fmaf(vreg[3], fr_tanh(fr_hi(kk.y) + q0.w), s1);
+                s0 = fmaf(vreg[4], fr_tanh(fr_lo(kk.z) + q1.x), s0); s1 = fmaf(vreg[5], fr_tanh(fr_hi(kk.z) + q1.y), s1);
+                s0 = fmaf(vreg[6], fr_tanh(fr_lo(kk.w) + q1.z), s0); s1 = fmaf(vreg[7], fr_tanh(fr_hi(kk.w) + q1.w), s1);
+                const float e = warp_sum(s0 + s1) + score_bias;
+                fr_push1(e, e_s + rank * TJ + jj, b_e, lane, lane < FR_C);
+            }
+        }
+        recv(b_e, par, e_bytes, more);
+        // ===== P7: alignments (recomputed by every warp: no shared state), then the warp's two context units =====
+        {
+            const int j0 = lane * CH;
+            if (a.manual) {
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) av[k] = (k < CH && j0 + k < Ti) ? __ldg(a.manual + ((long long)n * Td + t) * Ti + j0 + k) : 0.f;
+            } else if (a.att_type == TACO_ATT_BAH_MON) {
+                // p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1))
+                float pv[FR_CHM], lv[FR_CHM], wv[FR_CHM], cpv[FR_CHM];
+                float ls = 0.f;
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) {
+                    const bool ok = (k < CH) && (j0 + k < Ti);
+                    const float pk = fr_sigmoid(ok ? e_s[j0 + k] : 0.f);
+                    pv[k] = ok ? pk : 0.f;
+                    lv[k] = ok ? __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)) : 0.f;
+                    ls += lv[k];
+                }
+                float run = ls;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += v; }
+                run -= ls;
+                float ws = 0.f;
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) {
+                    cpv[k] = __expf(run);
+                    run += lv[k];
+                    wv[k] = __fdividef(av[k], fminf(fmaxf(cpv[k], 1e-10f), 1.f));
+                    ws += wv[k];
+                }
+                float run2 = ws;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, run2, o); if (lane >= o) run2 += v; }
+                run2 -= ws;
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) { run2 += wv[k]; av[k] = pv[k] * cpv[k] * run2; }
+            } else {       // softmax over the Ti positions (no length mask: tacotron.py:133-134)
+                float ex[FR_CHM], mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) { ex[k] = (k < CH && j0 + k < Ti) ? e_s[j0 + k] : -INFINITY; mx = fmaxf(mx, ex[k]); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float smv = 0.f;
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) { ex[k] = (k < CH && j0 + k < Ti) ? __expf(ex[k] - mx) : 0.f; smv += ex[k]; }
+                smv = warp_sum(smv);
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++) av[k] = __fdividef(ex[k], smv);
+            }
+            // context units 2*warp, 2*warp + 1:  sum_j a_j memory[j][unit]
+            const bf16* m0 = mem_s + (size_t)(2 * warp) * MP + j0; const bf16* m1 = m0 + MP;
+            float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < FR_CHM; k++)
+                if (k < CH) { c0 = fmaf(av[k], __bfloat162float(m0[k]), c0); c1 = fmaf(av[k], __bfloat162float(m1[k]), c1); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+            fr_push2(c0, c1, ctx_s + rank * FR_U + 2 * warp, b_ctx, lane);
+            if (rank == 0 && warp == 0) {                                  // alignment history [N, Ti, Td]
+#pragma unroll
+                for (int k = 0; k < FR_CHM; k++)
+                    if (k < CH && j0 + k < Ti) a.align[((long long)n * Ti + j0 + k) * Td + t] = av[k];
+            }
+        }
+        recv(b_ctx, par, FR_E * 4, more);
+        // ===== P8: y0 = yh + Wo_c.ctx + bo   (rnn_wrappers.py:405-415) =====
+        {
+            const float s = fr_half_sum(fr_dot<FR_E, 1, 16>(Woc, ctx_s, nullptr, nullptr, l16));
+            pair_push(yh + s + bo_own, y0_s, b_y0);
+        }
+        recv(b_y0, par, FR_Y * 4, more);
+        // ===== P9 / P10: residual GRU 1 over x = y0   (tacotron.py:171-175) =====
+        float u1, cx1;
+        {
+            float sr = fr_dot<FR_Y, 1, 16>(G1r, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G1r + FR_Y, h1_s, nullptr, nullptr, l16);
+            float su = fr_dot<FR_Y, 1, 16>(G1u, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G1u + FR_Y, h1_s, nullptr, nullptr, l16);
+            float sc = fr_dot<FR_Y, 1, 16>(G1cx, y0_s, nullptr, nullptr, l16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o); su += __shfl_xor_sync(0xffffffffu, su, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            }
+            const float rg = fr_sigmoid(sr + bg1r);
+            u1 = fr_sigmoid(su + bg1u); cx1 = sc;
+            pair_push(rg * h1_own, rh1_s, b_rh1);
+        }
+        recv(b_rh1, par, FR_Y * 4, more);
+        {
+            const float s = fr_half_sum(fr_dot<FR_Y, 1, 16>(G1ch, rh1_s, nullptr, nullptr, l16));
+            const float cc = fr_tanh(s + cx1 + bc1);
+            h1_own = u1 * h1_own + (1.f - u1) * cc;
+            pair_push(h1_own, h1_s, b_h1);
+        }
+        recv(b_h1, par, FR_Y * 4, more);
+        // ===== P11 / P12: residual GRU 2 over x = y1 = y0 + h1 =====
+        float u2, cx2;
+        {
+            float sr = fr_dot<FR_Y, 2, 16>(G2r, y0_s, h1_s, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2r + FR_Y, h2_s, nullptr, nullptr, l16);
+            float su = fr_dot<FR_Y, 2, 16>(G2u, y0_s, h1_s, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2u + FR_Y, h2_s, nullptr, nullptr, l16);
+            float sc = fr_dot<FR_Y, 2, 16>(G2cx, y0_s, h1_s, nullptr, l16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o); su += __shfl_xor_sync(0xffffffffu, su, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            }
+            const float rg = fr_sigmoid(sr + bg2r);
+            u2 = fr_sigmoid(su + bg2u); cx2 = sc;
+            pair_push(rg * h2_own, rh2_s, b_rh2);
+        }
+        recv(b_rh2, par, FR_Y * 4, more);
+        {
+            const float s = fr_half_sum(fr_dot<FR_Y, 1, 16>(G2ch, rh2_s, nullptr, nullptr, l16));
+            const float cc = fr_tanh(s + cx2 + bc2);
+            h2_own = u2 * h2_own + (1.f - u2) * cc;
+            pair_push(h2_own, h2_s, b_h2);
+        }
+        recv(b_h2, par, FR_Y * 4, more);
+        // ===== P13: r-frame mel projection over y2 = y0 + h1 + h2; its last frame is the next step's input (helpers.py:26-32) =====
+        {
+            float s0 = fr_dot<FR_Y, 3, 16>(Wm0, y0_s, h1_s, h2_s, l16), s1 = fr_dot<FR_Y, 3, 16>(Wm1, y0_s, h1_s, h2_s, l16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+            const float o0 = s0 + bm0, o1 = s1 + bm1;
+            float* out = a.mel_out + (long long)n * a.mel_bs + (long long)t * MR;
+            if (l16 == 0) { if (mok0) out[mc0] = o0; if (mok1) out[mc1] = o1; }
+            if (more) {
+                fr_push1(o0, x_s + (mc0 - (MR - a.M)), b_x, l16, mok0 && mc0 >= MR - a.M);
+                fr_push1(o1, x_s + (mc1 - (MR - a.M)), b_x, l16, mok1 && mc1 >= MR - a.M);
+            }
+        }
+    }
+    if (a.ha_final && l16 == 0) a.ha_final[(long long)n * FR_HA + unit] = ha_own;
+    cl.sync();      // no CTA may exit while a peer's store into it could still be in flight
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------------
+bool att_free_supported(const AttArgs& a) {
+    if (!(a.free_run && a.fast && a.SPK == 0 && a.E == FR_E && a.A == FR_A && a.HA == FR_HA && a.Z1 == FR_Z1 && a.Z == FR_Z && a.Y == FR_Y &&
+          a.M == FR_M && a.att_type != TACO_ATT_BAH_NORM)) return false;
+    const int MR = a.M * a.r, UO = (MR + FR_C - 1) / FR_C;
+    if (UO > FR_UO_PAD || a.r < 1) return false;
+    if (a.N < 1 || a.N > 8 || a.Ti < 1 || a.Ti > 32 * FR_CHM) return false;       // one 16-CTA cluster per utterance: 8 x 16 <= 148 SMs
+    if (a.s_z1 || a.s_a || a.y0) return false;                                     // no training stash on this path
+    return FrSmem(a.Ti).total <= 227 * 1024;
+}
+size_t att_free_image_bytes() { return (size_t)FR_C * FR_W_BYTES; }
+
+static void fr_table(const AttArgs& a, FrTable& tb) {
+    const int MR = a.M * a.r, UO = (MR + FR_C - 1) / FR_C, M = a.M;
+    auto one = [](const float* W, int ld, int row0, int K, int rows, int U, int col0, int off) {
+        FrSpec s{}; s.W = W; s.ld = ld; s.row0 = row0; s.K = K; s.rows = rows; s.split = rows; s.offA = col0; s.UA = U; s.offB = 0; s.UB = 0; s.own = rows;
+        s.col_limit = 1 << 30; s.off = off; return s;
+    };
+    auto gates = [](const float* W, int H, int row0, int K, int off) {      // rows 0..15: r columns, rows 16..31: u columns
+        FrSpec s{}; s.W = W; s.ld = 2 * H; s.row0 = row0; s.K = K; s.rows = 2 * FR_U; s.split = FR_U; s.offA = 0; s.UA = FR_U; s.offB = H; s.UB = FR_U; s.own = FR_U;
+        s.col_limit = 1 << 30; s.off = off; return s;
+    };
+    const float* W1 = a.W1x;      // dense_1 kernel [M + E, Z1]: rows [0, M) take the frame, rows [M, M + E) the context
+    tb.s[FRW_W1C] = one(W1, FR_Z1, M, FR_E, FR_U, FR_U, 0, FrOff::W1c);
+    tb.s[FRW_W1X] = one(W1, FR_Z1, 0, M, FR_U, FR_U, 0, FrOff::W1x);
+    tb.s[FRW_W2] = one(a.W2, FR_Z, 0, FR_Z1, FR_UZ, FR_UZ, 0, FrOff::W2);
+    tb.s[FRW_WG] = gates(a.Wg, FR_HA, 0, FR_Z + FR_HA, FrOff::Wg);
+    tb.s[FRW_WCZ] = one(a.Wc, FR_HA, 0, FR_Z, FR_U, FR_U, 0, FrOff::Wcz);
+    tb.s[FRW_WCH] = one(a.Wc, FR_HA, FR_Z, FR_HA, FR_U, FR_U, 0, FrOff::Wch);
+    tb.s[FRW_WQ] = one(a.Wq, FR_A, 0, FR_HA, FR_U, FR_U, 0, FrOff::Wq);
+    tb.s[FRW_WOH] = one(a.Wo, FR_Y, 0, FR_HA, FR_U, FR_U, 0, FrOff::Woh);
+    tb.s[FRW_WOC] = one(a.Wo, FR_Y, FR_HA, FR_E, FR_U, FR_U, 0, FrOff::Woc);
+    tb.s[FRW_G1G] = gates(a.Wg1, FR_Y, 0, 2 * FR_Y, FrOff::G1g);
+    tb.s[FRW_G1CX] = one(a.Wc1, FR_Y, 0, FR_Y, FR_U, FR_U, 0, FrOff::G1cx);
+    tb.s[FRW_G1CH] = one(a.Wc1, FR_Y, FR_Y, FR_Y, FR_U, FR_U, 0, FrOff::G1ch);
+    tb.s[FRW_G2G] = gates(a.Wg2, FR_Y, 0, 2 * FR_Y, FrOff::G2g);
+    tb.s[FRW_G2CX] = one(a.Wc2, FR_Y, 0, FR_Y, FR_U, FR_U, 0, FrOff::G2cx);
+    tb.s[FRW_G2CH] = one(a.Wc2, FR_Y, FR_Y, FR_Y, FR_U, FR_U, 0, FrOff::G2ch);
+    {   // mel projection: rank owns columns [rank*UO, rank*UO + UO) of [Y, M*r]; image rows past UO (and columns past M*r) are zero
+        FrSpec s = one(a.Wmel, MR, 0, FR_Y, FR_UO_PAD, UO, 0, FrOff::Wmel);
+        s.own = UO; s.col_limit = MR;
+        tb.s[FRW_MEL] = s;
+    }
+}
+
+// packs the step's weights into `img` (att_free_image_bytes) and runs all Td decoder steps
+int launch_att_free(const AttArgs& a, void* img, cudaStream_t s) {
+    TACO_REQUIRE(att_free_supported(a) && img, TACO_EINVAL, "free-running decoder: the resident-weight kernel does not apply to this configuration");
+    TACO_REQUIRE(a.W1x && a.b1 && a.Wg1 && a.Wg2 && a.Wc1 && a.Wc2 && a.Wmel && a.bmel && a.mel_out && a.align, TACO_EINVAL, "free-running decoder: missing weights / outputs");
+    static int configured = 0;       // 0 unknown, 1 ok, -1 a cluster of 16 CTAs is not launchable here
+    if (configured == 0) {
+        cudaError_t e1 = cudaFuncSetAttribute(att_free_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e2 = cudaFuncSetAttribute(att_free_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : -1;
+        if (configured < 0) cudaGetLastError();
+    }
+    if (configured < 0) return TACO_ENOTSUP;
+    FrTable tb; fr_table(a, tb);
+    fr_pack_kernel<<<dim3(FR_C, FRW_N), 256, 0, s>>>(tb, static_cast<bf16*>(img));
+    TACO_CHECK_LAUNCH();
+    g_launch_count++;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(FR_C * a.N);
+    cfg.blockDim = dim3(FR_NT);
+    cfg.dynamicSmemBytes = (size_t)FrSmem(a.Ti).total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FR_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, att_free_kernel, a, static_cast<const uint8_t*>(img));
+    if (e != cudaSuccess) { cudaGetLastError(); configured = -1; return TACO_ENOTSUP; }
+    g_launch_count++;
+    return TACO_OK;
+}
+
+}  // namespace taco

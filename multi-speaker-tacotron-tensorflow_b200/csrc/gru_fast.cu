@@ -87,14 +87,15 @@ __device__ __forceinline__ void gf_mma_regs(float acc[4], const uint32_t (&af)[N
         b[kk][0] = *reinterpret_cast<const uint32_t*>(v + ((ka / U) * GF_R + g) * U + (ka % U));
         b[kk][1] = *reinterpret_cast<const uint32_t*>(v + ((kb / U) * GF_R + g) * U + (kb % U));
     }
-    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    // four independent accumulator chains: a dependent mma.sync costs ~100 clk on sm_100a (gate phase, NK = 8: 569 clk with
+    // two chains of four - tools/gru_phase_prof.py), so the chain depth, not the issue rate, sets the phase time
+    float c[4][4];
 #pragma unroll
-    for (int kk = 0; kk < NK; kk++) {
-        if (kk & 1) gf_mma(acc2, af[kk][0], af[kk][1], af[kk][2], af[kk][3], b[kk][0], b[kk][1]);
-        else gf_mma(acc, af[kk][0], af[kk][1], af[kk][2], af[kk][3], b[kk][0], b[kk][1]);
-    }
-    acc[0] += acc2[0]; acc[1] += acc2[1]; acc[2] += acc2[2]; acc[3] += acc2[3];
+    for (int q = 0; q < 4; q++) { c[q][0] = 0.f; c[q][1] = 0.f; c[q][2] = 0.f; c[q][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) gf_mma(c[kk & 3], af[kk][0], af[kk][1], af[kk][2], af[kk][3], b[kk][0], b[kk][1]);
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[e] = (c[0][e] + c[1][e]) + (c[2][e] + c[3][e]);
 }
 __device__ __forceinline__ float gf_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gf_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -225,7 +226,6 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         const int t = (d == 0) ? s : (L - 1 - s);
         const float cgr = gr, cgu = gu, cgc = gc, cres = gres;
         if (tid == 0) { gf_mbar_expect_tx(bar_rh, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h, GF_C * Cfg::BLK_BYTES); }
-        load_gx(s + 1);                                          // prefetch next step's x-side pre-activations
         GF_T(0);
         // ---- gate phase ----
         {
@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         __syncthreads();
         GF_T(4);
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_rh, rhb_s + rank * R * U, bar_rh, tid);
+        load_gx(s + 1);      // next step's x-side pre-activations: issued in the shadow of the exchange (at the top of the step the
+                             // address arithmetic and four load issues cost ~200 clk on the serial path)
         GF_T(5);
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -392,7 +394,6 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         const float r_ = rg, u_ = ug, c_ = cc, hp_ = hp;
         float dh = dh_carry + (valid ? dout : 0.f);
         if (tid == 0) { gf_mbar_expect_tx(bar_c, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_g, 2 * GF_C * Cfg::BLK_BYTES); }
-        if (s - 1 >= s_begin) load_step(s - 1);
         float du_pre = 0.f, dc_pre = 0.f;
         if (valid) {
             du_pre = dh * (hp_ - c_) * u_ * (1.f - u_);
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
 #if GF_USE_STASYNC
         __syncthreads();
         gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_c, dcp_s + rank * R * U, bar_c, tid);
+        if (s - 1 >= s_begin) load_step(s - 1);      // next step's stash values: five loads issued in the shadow of the exchange
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();

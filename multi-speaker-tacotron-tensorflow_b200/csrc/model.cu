@@ -49,6 +49,7 @@ void prof_mark(const char* name, cudaStream_t s) {
     g_prof_spans.push_back(sp);
 }
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s) { ProfScope p(1, s); return bwd ? launch_gru_bwd(a, s) : launch_gru_fwd(a, s); }
+int prof_launch_att_free(const AttArgs& a, void* img, cudaStream_t s) { ProfScope p(2, s); return launch_att_free(a, img, s); }
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s) { ProfScope p(2, s); return bwd ? launch_att_bwd(a, s) : launch_att_fwd(a, s); }
 
 // ---- stream scheduler --------------------------------------------------------------------------------------
@@ -372,6 +373,9 @@ void Model::plan(const Shape& s) {
             pa.M = (int)M; pa.r = (int)r;
             const size_t wb = att_wfrag_bytes(pa);
             if (wb) add("dec/wfrag", {(int64_t)(wb / 4)});
+            // low-batch synthesis: per-rank shared-memory weight images of the resident-weight decoder kernel (att_free.cu)
+            pa.N = N; pa.Ti = s.Ti; pa.Td = s.Td; pa.att_type = c.attention_type;
+            if (!tr && att_free_supported(pa)) add("dec/frimg", {(int64_t)(att_free_image_bytes() / 4)});
         }
         if (tr) {
             add("dec/s_z1", {rows, Z1}); add("dec/s_z", {rows, Z});

@@ -94,6 +94,7 @@ int image_wait(int which, cudaStream_t s);
 void prof_mark(const char* name, cudaStream_t s);   // timeline stage marker (no-op unless taco_profile is collecting)
 int prof_launch_gru(const GruArgs& a, bool bwd, cudaStream_t s);
 int prof_launch_att(const AttArgs& a, bool bwd, cudaStream_t s);
+int prof_launch_att_free(const AttArgs& a, void* img, cudaStream_t s);
 
 float* bank_wd(const Model& m, const CbhgGeom& g, int k);   // flipped + transposed kernel of bank member k (packed, contiguous over k)
 

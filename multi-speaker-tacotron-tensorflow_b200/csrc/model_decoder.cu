@@ -206,6 +206,13 @@ int decoder_forward(Model& m, const taco_batch* b, cudaStream_t s) {
         a.h1_0 = h1; a.h2_0 = h2;
         a.mel_out = m.W("post_cbhg/xin_p") + (long long)g.PL * D.M; a.mel_bs = (long long)g.Tp * D.M;
         a.y0 = nullptr;
+        // low-batch synthesis in the tensor-core modes: every weight of the step resident in the shared memory of one 16-CTA
+        // cluster per utterance (att_free.cu); falls through to the general kernel when such a cluster cannot be launched
+        static const int use_free = [] { const char* e = getenv("TACO_ATT_FREE"); return e ? atoi(e) : 1; }();
+        if (use_free && att_free_supported(a) && m.has_region("dec/frimg")) {
+            const int rc = prof_launch_att_free(a, m.W("dec/frimg"), s);
+            if (rc != TACO_ENOTSUP) return rc;
+        }
         // tensor-core modes: the step's weights are packed once per call as bf16 mma fragments (attention.cu)
         if (att_wfrag_supported(a) && m.has_region("dec/wfrag")) TACO_TRY(launch_att_wfrag_pack(a, m.W("dec/wfrag"), s));
         return prof_launch_att(a, false, s);

@@ -1,8 +1,11 @@
 """Summarise an `ncu --metrics ... --csv` per-launch log (long format) into a per-kernel table.
 
 usage: python tools/summarize_metrics.py gpurun_out/step_metrics_v4.csv [top_n]
+       python tools/summarize_metrics.py <csv> --traffic-json <precision> <out.json>    # DRAM bytes per GEMM launch for bench.py
 """
-import csv, sys, collections, re
+import csv, json, os, sys, collections, re
+
+GEMM_KERNELS = ("gemm_bf16_kernel", "gemm_tc_kernel")       # the tensor-core GEMM launches bench.py's roofline counts
 
 def load(path):
     rows = []
@@ -27,7 +30,25 @@ def load(path):
         d[r["Metric Name"]] = v
     return list(per.values())
 
+def traffic_json(rows, precision, out, src):
+    """profiles/r2_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the tensor-core GEMM launches of ONE step."""
+    sel = [r for r in rows if any(k in r["name"] for k in GEMM_KERNELS)]
+    b = sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in sel)
+    doc = {}
+    if os.path.exists(out):
+        with open(out) as f:
+            doc = json.load(f)
+    doc[precision] = {"dram_bytes_per_launch": b / max(1, len(sel)), "launches": len(sel), "dram_bytes_per_step": b,
+                      "source": "%s: dram__bytes_read.sum + dram__bytes_write.sum over the %d %s launches of one C2 step (ncu, cold caches, serialised)"
+                                % (src, len(sel), " / ".join(GEMM_KERNELS))}
+    with open(out, "w") as f:
+        json.dump(doc, f, indent=1)
+    print(json.dumps(doc[precision]))
+
+
 def main():
+    if len(sys.argv) > 4 and sys.argv[2] == "--traffic-json":
+        return traffic_json(load(sys.argv[1]), sys.argv[3], sys.argv[4], os.path.relpath(sys.argv[1]))
     rows = load(sys.argv[1]); top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     agg = collections.OrderedDict()
     for r in rows:
