@@ -20,6 +20,10 @@ constexpr int AF_C = 16, AF_R = 8, AF_NT = 256;
 constexpr int AF_E = 256, AF_A = 256, AF_HA = 256, AF_Z1 = 256, AF_Z = 128, AF_Y = 256;   // instantiated sizes
 constexpr int AF_U = 16;                 // units per CTA of the 256-wide layers
 constexpr int AF_UZ = AF_Z / AF_C;       // 8
+// Score / alignment-gradient exchange buffers are blocked [C][R*TJ (+ AF_EPAD)] floats.  Dense blocks (64 words at T_in = 128) put
+// every block on the same banks: the alignment scan, whose lanes walk the blocks, saw 16-way conflicts on each load
+// (profiles/r1_ncu_full_att_fast.summary.txt).  With 8 words of padding a quarter-warp's 16-byte loads cover all 32 banks.
+constexpr int AF_EPAD = 8;
 
 typedef __nv_bfloat16 bf16;
 
@@ -138,14 +142,23 @@ __device__ long long g_af_prof[40];
 // Monotonic attention forward for one row by one warp, lane owns the CH contiguous positions [lane*CH, lane*CH+CH):
 // p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1))   (in place in ar_)
 template <int CH>
-__device__ __forceinline__ void af_mono_scan_fwd(const float* e_s, const int* eoff, float* ar_, int lane, int Ti) {
+__device__ __forceinline__ void af_mono_scan_fwd(const float* e_s, const int* eoff, bool vec4, float* ar_, int lane, int Ti) {
     const int j0 = lane * CH;
-    float pv[CH], lv[CH], av[CH], wv[CH], cpv[CH];
+    float pv[CH], lv[CH], av[CH], wv[CH], cpv[CH], ev[CH];
+    // the lane's CH = 4 scores are contiguous inside one exchange block when TJ % 4 == 0: one 16-byte load (conflict-free with the
+    // padded block pitch, see AF_EPAD) instead of four 16-way conflicted scalar ones
+    if (CH == 4 && vec4) {
+        const float4 e4 = *reinterpret_cast<const float4*>(e_s + eoff[0]);
+        ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; k++) ev[k] = e_s[eoff[k]];
+    }
     float ls = 0.f;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
         const bool ok = j0 + k < Ti;
-        const float pk = af_sigmoid(ok ? e_s[eoff[k]] : 0.f);
+        const float pk = af_sigmoid(ok ? ev[k] : 0.f);
         av[k] = ok ? ar_[j0 + k] : 0.f;
         pv[k] = ok ? pk : 0.f;
         lv[k] = ok ? __logf(fminf(fmaxf(1.f - pk, FLT_MIN), 1.f)) : 0.f;
@@ -279,7 +292,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     bf16* ha_s = reinterpret_cast<bf16*>(p);  p += R * HA * 2;
     bf16* rha_s = reinterpret_cast<bf16*>(p); p += R * HA * 2;
     float* q_s = reinterpret_cast<float*>(p); p += R * A * 4;                        // fp32 blocked [C][R][U]
-    float* e_s = reinterpret_cast<float*>(p); p += (size_t)R * Tip * 4;              // fp32 blocked [C][R][TJ]
+    const int EB = R * TJ + AF_EPAD;          // block pitch (floats) of the score exchange buffer
+    float* e_s = reinterpret_cast<float*>(p); p += (size_t)AF_C * EB * 4;            // fp32 blocked [C][R][TJ] (+pad)
     float* a_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;             // [R][Tip+4]
     float* p_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
     float* cp_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
@@ -348,7 +362,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     const int CH = (Tip + 31) / 32;
     int eoff[CHM];
 #pragma unroll
-    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = ((j / TJ) * R + warp) * TJ + (j % TJ); }
+    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = (j / TJ) * EB + warp * TJ + (j % TJ); }
+    const bool evec4 = (TJ % 4 == 0);
     const bool writer = (rank == (warp % AF_C)) && (grp * R + warp < a.N);     // this warp stores row `warp`'s alignments / stash
     for (int t = t_lo; t < t_hi; t++) {
         const uint32_t par = (t - t_lo) & 1;
@@ -499,7 +514,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             }
         }
         __syncthreads();
-        af_push(stage, e_s + rank * R * TJ, b_e, R * TJ * 4, tid);
+        af_push(stage, e_s + rank * EB, b_e, R * TJ * 4, tid);
         AF_T(10);
         af_wait(b_e, par);
         AF_T(11);
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             if (a.manual) {
                 for (int j = lane; j < Ti; j += 32) ar_[j] = (n < a.N) ? a.manual[((long long)n * Td + t) * Ti + j] : 0.f;
             } else if (a.att_type == TACO_ATT_BAH_MON && CH == 4) {
-                af_mono_scan_fwd<4>(e_s, eoff, ar_, lane, Ti);
+                af_mono_scan_fwd<4>(e_s, eoff, evec4, ar_, lane, Ti);
             } else if (a.att_type == TACO_ATT_BAH_MON && CH <= CHM) {
                 // p = sigmoid(e); cp = exp(cumsum_excl(log(clip(1-p, tiny, 1)))); a = p*cp*cumsum(a_prev/clip(cp,1e-10,1)), fully unrolled
                 const int j0 = lane * CH;
@@ -551,7 +566,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             } else if (a.att_type == TACO_ATT_BAH_MON) {
                 const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
                 float* pr_ = p_s + r * TipP; float* cr_ = cp_s + r * TipP;
-                auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+                auto E_ = [&](int j) -> float { return e_s[(j / TJ) * EB + r * TJ + (j % TJ)]; };
                 float ls = 0.f;
                 for (int j = j0; j < j1; j++) {
                     const float pk = af_sigmoid(E_(j));
@@ -579,7 +594,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
                 }
             } else {
                 float* pr_ = p_s + r * TipP;
-                auto E_ = [&](int j) -> float { return e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+                auto E_ = [&](int j) -> float { return e_s[(j / TJ) * EB + r * TJ + (j % TJ)]; };
                 float mx = -INFINITY;
                 for (int j = lane; j < Ti; j += 32) mx = fmaxf(mx, E_(j));
 #pragma unroll
@@ -625,7 +640,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
             for (int j = lane; j < Ti; j += 32) {
                 const float av = ar_[j];
                 a.align[((long long)n * Ti + j) * Td + t] = av;
-                if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = e_s[((j / TJ) * R + r) * TJ + (j % TJ)]; }
+                if (a.s_a) { a.s_a[((long long)n * Td + t) * Ti + j] = av; a.s_e[((long long)n * Td + t) * Ti + j] = e_s[(j / TJ) * EB + r * TJ + (j % TJ)]; }
             }
         }
         AF_T(12);
@@ -744,7 +759,8 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     bf16* keyu_s = reinterpret_cast<bf16*>(p); p += (size_t)R * KRS * 2;             // [R][Ti][U] (+pad)   own attention units
     p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
     float* dctx_s = reinterpret_cast<float*>(p); p += R * E * 4;                     // fp32 blocked [C][R][U]
-    float* da_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;           // fp32 blocked [C][R][TJ]
+    const int EB = R * TJ + AF_EPAD;          // block pitch (floats) of the alignment-gradient exchange buffer
+    float* da_s = reinterpret_cast<float*>(p);   p += (size_t)AF_C * EB * 4;         // fp32 blocked [C][R][TJ] (+pad)
     bf16* gq_s = reinterpret_cast<bf16*>(p);   p += R * A * 2;                       // bf16 blocked [C][R][U]
     bf16* dcp_s = reinterpret_cast<bf16*>(p);  p += R * HA * 2;
     bf16* dg_s = reinterpret_cast<bf16*>(p);   p += 2 * R * HA * 2;                  // [2C][R][U]
@@ -805,7 +821,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     const int CH = (Tip + 31) / 32;
     int eoff[CHM];
 #pragma unroll
-    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = ((j / TJ) * R + warp) * TJ + (j % TJ); }
+    for (int k = 0; k < CHM; k++) { const int j = min(lane * CH + k, Tip - 1); eoff[k] = (j / TJ) * EB + warp * TJ + (j % TJ); }
     const int wn = grp * R + warp;                                // batch row of this warp in the scan phases
     const bool wok = wn < a.N;
     const bool writer = (rank == (warp % AF_C)) && wok;
@@ -907,7 +923,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
             }
         }
         __syncthreads();
-        af_push(stage, da_s + rank * R * TJ, b_da, R * TJ * 4, tid);
+        af_push(stage, da_s + rank * EB, b_da, R * TJ * 4, tid);
         AF_T(2);
         af_wait(b_da, par);
         AF_T(3);
@@ -1001,7 +1017,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                 const int j0 = min(lane * CH, Ti), j1 = min(j0 + CH, Ti);
                 float* pr_ = p_s + r * Tip; float* cr_ = cp_s + r * Tip; float* sr_ = s_s + r * Tip;
                 float* t1 = ge; float* t2 = sr_;
-                auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+                auto GA = [&](int j) -> float { return da_s[(j / TJ) * EB + r * TJ + (j % TJ)]; };
                 const float* e_row = a.s_e + ((long long)n * Td + t) * Ti;
                 const float* ap_row = (t > 0) ? a.s_a + ((long long)n * Td + (t - 1)) * Ti : nullptr;
                 float ls = 0.f;
@@ -1068,7 +1084,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                 gb = warp_sum(gb);
                 if (rank == 0 && lane == 0) gbias_acc += gb;
             } else {
-                auto GA = [&](int j) -> float { return da_s[((j / TJ) * R + r) * TJ + (j % TJ)]; };
+                auto GA = [&](int j) -> float { return da_s[(j / TJ) * EB + r * TJ + (j % TJ)]; };
                 const float* a_row = a.s_a + ((long long)wn * Td + t) * Ti;
                 float dot = 0.f;
                 for (int j = lane; j < Ti; j += 32) dot += a_row[j] * GA(j);
@@ -1237,7 +1253,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
 static size_t af_bwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
     size_t b = AfBwdSmem::w_end + (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16 + (size_t)AF_R * 4 * 4;
-    b += (size_t)AF_R * AF_E * 4 + (size_t)AF_R * Tip * 4 + (size_t)AF_R * (AF_A + AF_HA + 2 * AF_HA + AF_Z + AF_Z1 + AF_Y) * 2;
+    b += (size_t)AF_R * AF_E * 4 + (size_t)(AF_R * Tip + AF_C * AF_EPAD) * 4 + (size_t)AF_R * (AF_A + AF_HA + 2 * AF_HA + AF_Z + AF_Z1 + AF_Y) * 2;
     b += (size_t)5 * AF_R * Tip * 4 + 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
 }
@@ -1245,7 +1261,7 @@ static size_t af_bwd_smem(int Ti) {
 static size_t af_fwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
     size_t b = AfFwdSmem::w_end + (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16;
-    b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * (Tip + 4) * 4;
+    b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * (Tip + 4) * 4 + (size_t)AF_C * AF_EPAD * 4;
     b += 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
 }

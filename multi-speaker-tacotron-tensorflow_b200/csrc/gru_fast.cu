@@ -46,13 +46,15 @@ __device__ __forceinline__ void gf_push(const void* src_local, void* dst_local_a
 }
 // Exchange variant 2: every thread forwards 16 bytes of the staged block to one peer with st.async (data + tx-count in
 // one DSMEM transaction, no async-proxy fence needed).  NQ = 16-byte chunks per block; threads [0, C*NQ) participate.
-template <int NQ>
+// The staged block is dense [R][U]; the receive buffers keep rows U + 8 elements apart (QR = 16-byte chunks per dense row,
+// ROWB = bytes per padded row): see GfCfg::UP.
+template <int NQ, int QR, int ROWB>
 __device__ __forceinline__ void gf_push_stasync(const void* stage, void* dst_local_alias, uint64_t* bar_local_alias, int tid) {
     if (tid < GF_C * NQ) {
         const uint32_t peer = tid / NQ, q = tid % NQ;
         const uint4 v = *(reinterpret_cast<const uint4*>(stage) + q);
         uint32_t dst, bar;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias) + q * 16), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias) + (q / QR) * ROWB + (q % QR) * 16), "r"(peer));
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                      ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
@@ -80,12 +82,13 @@ __device__ __forceinline__ void gf_load_afrags(uint32_t (&af)[NK][4], const __nv
 template <int U, int NK>
 __device__ __forceinline__ void gf_mma_regs(float acc[4], const uint32_t (&af)[NK][4], const __nv_bfloat16* v, int k0, int lane) {
     const int g = lane >> 2, t = lane & 3;
+    constexpr int UP = U + 8;      // padded row pitch of the exchanged blocks (GfCfg::UP): the 8 rows g of a fragment load hit 8 different bank groups
     uint32_t b[NK][2];
 #pragma unroll
     for (int kk = 0; kk < NK; kk++) {
         const int ka = k0 + kk * 16 + 2 * t, kb = ka + 8;
-        b[kk][0] = *reinterpret_cast<const uint32_t*>(v + ((ka / U) * GF_R + g) * U + (ka % U));
-        b[kk][1] = *reinterpret_cast<const uint32_t*>(v + ((kb / U) * GF_R + g) * U + (kb % U));
+        b[kk][0] = *reinterpret_cast<const uint32_t*>(v + ((ka / U) * GF_R + g) * UP + (ka % U));
+        b[kk][1] = *reinterpret_cast<const uint32_t*>(v + ((kb / U) * GF_R + g) * UP + (kb % U));
     }
     // four independent accumulator chains: a dependent mma.sync costs ~100 clk on sm_100a (gate phase, NK = 8: 569 clk with
     // two chains of four - tools/gru_phase_prof.py), so the chain depth, not the issue rate, sets the phase time
@@ -121,11 +124,19 @@ template <int H>
 struct GfCfg {
     static constexpr int U = H / GF_C, GC = 2 * U, KP = H + 8, KP2 = 2 * H + 8;
     static constexpr int ACT = U * GF_R;
-    static constexpr int BLK_BYTES = GF_R * U * 2;                 // one CTA's bf16 slice of a vector
+    static constexpr int BLK_BYTES = GF_R * U * 2;                 // one CTA's bf16 slice of a vector (dense, as staged and sent)
+    // Receive buffers [C][R][UP]: rows U + 8 elements apart.  With dense rows (64 B at U = 32) the 8 batch rows of an mma B-fragment
+    // load fall on 2 bank groups - a 4-way conflict on every one of the 16 loads of the gate phase, ~500 LSU cycles per step over
+    // the 8 warps (tools/gru_phase_prof.py: 570 clk for 8 mma + their operand loads); 80 B (48 B at U = 16) rows are conflict-free.
+    static constexpr int UP = U + 8;
+    static constexpr int VEC = GF_C * GF_R * UP;                   // elements of one received vector
+    // k-split partial sums: [ks][R][cols + 4] floats (row = batch row) so that the activation threads (consecutive units of one
+    // batch row) read consecutive words; [ks][col][R] made those reads 8-way conflicted
+    static constexpr int RED_FLOATS = 1280;
     // forward: Wg [GC][KP] + Wc [U][KP]; backward: WcT [U][KP] + WgT [U][KP2]
     static constexpr size_t w_bytes = (size_t)3 * U * KP2 * 2;     // upper bound for both directions
-    static constexpr size_t smem_bytes = w_bytes + (size_t)3 * GF_R * H * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
-                                         4096 /*red*/ + 64 /*barriers*/ + 256;
+    static constexpr size_t smem_bytes = w_bytes + (size_t)3 * VEC * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
+                                         RED_FLOATS * 4 /*red*/ + 64 /*barriers*/ + 256;
 };
 
 __device__ long long g_gf_prof[16];
@@ -134,7 +145,9 @@ __device__ long long g_gf_prof[16];
 template <int H>
 __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a) {
     using Cfg = GfCfg<H>;
-    constexpr int U = Cfg::U, GC = Cfg::GC, KP = Cfg::KP, R = GF_R;
+    constexpr int U = Cfg::U, GC = Cfg::GC, KP = Cfg::KP, R = GF_R, UP = Cfg::UP;
+    constexpr int RPG = GC + 4, RPC = U + 4;                      // row pitches of the partial sums (gate / candidate phase)
+    constexpr int QR = U / 8, ROWB = UP * 2;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / GF_C;
@@ -145,12 +158,12 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     __nv_bfloat16* Wg_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [GC][KP]
     __nv_bfloat16* Wc_s = Wg_s + GC * KP;                                         // [U][KP]
     __nv_bfloat16* hb_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);   // [C][R][U]
-    __nv_bfloat16* rhb_s = hb_s + R * H;
-    __nv_bfloat16* spare = rhb_s + R * H;
-    __nv_bfloat16* stage_rh = spare + R * H;                                      // [R][U]
+    __nv_bfloat16* rhb_s = hb_s + Cfg::VEC;
+    __nv_bfloat16* spare = rhb_s + Cfg::VEC;
+    __nv_bfloat16* stage_rh = spare + Cfg::VEC;                                   // [R][U]
     __nv_bfloat16* stage_h = stage_rh + R * U;
-    float* red = reinterpret_cast<float*>(stage_h + 2 * R * U);                   // 1024 floats
-    uint64_t* bar_rh = reinterpret_cast<uint64_t*>(red + 1024);
+    float* red = reinterpret_cast<float*>(stage_h + 2 * R * U);                   // RED_FLOATS
+    uint64_t* bar_rh = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);
     uint64_t* bar_h = bar_rh + 1;
 
     const float* __restrict__ Wg = a.Wg[d];
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     for (int idx = tid; idx < R * H; idx += GF_NT) {       // hb_s[(k/U)][r][k%U]
         const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
         const int k = blk * U + i;
-        hb_s[idx] = __float2bfloat16((a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + k] : 0.f);
+        hb_s[(blk * R + r) * UP + i] = __float2bfloat16((a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + k] : 0.f);
     }
     if (tid == 0) {
         gf_mbar_init(bar_rh, 1); gf_mbar_init(bar_h, 1);
@@ -232,9 +245,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
             float acc[4];
             const int mt = warp % MT_G, ks = warp / MT_G;
             gf_mma_regs<U, NK_G>(acc, afG, hb_s, ks * NK_G * 16, lane);
-            float* rp = red + ks * (GC * R);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+            float* rp = red + ks * (R * RPG) + mt * 16 + g4;
+            rp[(2 * t4) * RPG] = acc[0]; rp[(2 * t4 + 1) * RPG] = acc[1];
+            rp[(2 * t4) * RPG + 8] = acc[2]; rp[(2 * t4 + 1) * RPG + 8] = acc[3];
         }
         GF_T(1);
         __syncthreads();
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         if (act) {
             float sr = cgr, su = cgu;
 #pragma unroll
-            for (int ks = 0; ks < KS_G; ks++) { sr += red[ks * (GC * R) + i * R + r]; su += red[ks * (GC * R) + (U + i) * R + r]; }
+            for (int ks = 0; ks < KS_G; ks++) { sr += red[ks * (R * RPG) + r * RPG + i]; su += red[ks * (R * RPG) + r * RPG + U + i]; }
             rg = gf_sigmoid(sr); ug = gf_sigmoid(su);
             stage_rh[r * U + i] = __float2bfloat16(rg * h_own);
         }
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
 #if GF_USE_STASYNC
         __syncthreads();
         GF_T(4);
-        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_rh, rhb_s + rank * R * U, bar_rh, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_rh, rhb_s + rank * R * UP, bar_rh, tid);
         load_gx(s + 1);      // next step's x-side pre-activations: issued in the shadow of the exchange (at the top of the step the
                              // address arithmetic and four load issues cost ~200 clk on the serial path)
         GF_T(5);
@@ -267,23 +280,23 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
             float acc[4];
             const int mt = warp % MT_C, ks = warp / MT_C;
             gf_mma_regs<U, NK_C>(acc, afC, rhb_s, ks * NK_C * 16, lane);
-            float* rp = red + ks * (U * R);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+            float* rp = red + ks * (R * RPC) + mt * 16 + g4;
+            rp[(2 * t4) * RPC] = acc[0]; rp[(2 * t4 + 1) * RPC] = acc[1];
+            rp[(2 * t4) * RPC + 8] = acc[2]; rp[(2 * t4 + 1) * RPC + 8] = acc[3];
         }
         __syncthreads();
         float cnd = 0.f, hprev = h_own;
         if (act) {
             float sc = cgc;
 #pragma unroll
-            for (int ks = 0; ks < KS_C; ks++) sc += red[ks * (U * R) + i * R + r];
+            for (int ks = 0; ks < KS_C; ks++) sc += red[ks * (R * RPC) + r * RPC + i];
             cnd = gf_tanh(sc);
             if (valid) h_own = ug * h_own + (1.f - ug) * cnd;
             stage_h[r * U + i] = __float2bfloat16(h_own);
         }
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_h, hb_s + rank * R * U, bar_h, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_h, hb_s + rank * R * UP, bar_h, tid);
         if (valid) {      // output and stash stores ride in the shadow of the exchange
             const long long o = (long long)n * a.T + t;
             a.out[o * a.out_ld + d * H + unit] = h_own + cres;
@@ -312,7 +325,9 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
 template <int H>
 __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a) {
     using Cfg = GfCfg<H>;
-    constexpr int U = Cfg::U, KP = Cfg::KP, KP2 = Cfg::KP2, R = GF_R;
+    constexpr int U = Cfg::U, KP = Cfg::KP, KP2 = Cfg::KP2, R = GF_R, UP = Cfg::UP;
+    constexpr int RP = U + 4;                                      // row pitch of the partial sums
+    constexpr int QR = U / 8, ROWB = UP * 2;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / GF_C;
@@ -323,12 +338,12 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     __nv_bfloat16* WcT_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [U][KP]   WcT_s[i][cu] = Wc[unit_i][cu]
     __nv_bfloat16* WgT_s = WcT_s + U * KP;                                        // [U][KP2]  WgT_s[i][gc] = Wg[unit_i][gc]
     __nv_bfloat16* dcp_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);  // [C][R][U]       dc_pre, all units
-    __nv_bfloat16* dg_s = dcp_s + R * H;                                          // [2C][R][U]      [dr_pre ; du_pre]
-    __nv_bfloat16* stage_c = dg_s + 2 * R * H;                                    // [R][U]
+    __nv_bfloat16* dg_s = dcp_s + Cfg::VEC;                                       // [2C][R][UP]     [dr_pre ; du_pre]
+    __nv_bfloat16* stage_c = dg_s + 2 * Cfg::VEC;                                 // [R][U]
     __nv_bfloat16* stage_r = stage_c + R * U;
     __nv_bfloat16* stage_u = stage_r + R * U;
-    float* red = reinterpret_cast<float*>(stage_u + R * U);                       // 1024 floats
-    uint64_t* bar_c = reinterpret_cast<uint64_t*>(red + 1024);
+    float* red = reinterpret_cast<float*>(stage_u + R * U);                       // RED_FLOATS
+    uint64_t* bar_c = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);
     uint64_t* bar_g = bar_c + 1;
 
     const float* __restrict__ Wg = a.Wg[d];
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         if (act) stage_c[r * U + i] = __float2bfloat16(dc_pre);
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_c, dcp_s + rank * R * U, bar_c, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_c, dcp_s + rank * R * UP, bar_c, tid);
         if (s - 1 >= s_begin) load_step(s - 1);      // next step's stash values: five loads issued in the shadow of the exchange
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -415,23 +430,23 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
             float acc[4];
             const int mt = warp % MT, ks = warp / MT;
             gf_mma_regs<U, NK_C>(acc, afC, dcp_s, ks * NK_C * 16, lane);
-            float* rp = red + ks * (U * R);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+            float* rp = red + ks * (R * RP) + mt * 16 + g4;
+            rp[(2 * t4) * RP] = acc[0]; rp[(2 * t4 + 1) * RP] = acc[1];
+            rp[(2 * t4) * RP + 8] = acc[2]; rp[(2 * t4 + 1) * RP + 8] = acc[3];
         }
         __syncthreads();
         float d_rh = 0.f, dr_pre = 0.f;
         if (act) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) d_rh += red[ks * (U * R) + i * R + r];
+            for (int ks = 0; ks < KS; ks++) d_rh += red[ks * (R * RP) + r * RP + i];
             if (valid) dr_pre = d_rh * hp_ * r_ * (1.f - r_);
             stage_r[r * U + i] = __float2bfloat16(dr_pre);
             stage_u[r * U + i] = __float2bfloat16(du_pre);
         }
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_r, dg_s + rank * R * U, bar_g, tid);
-        gf_push_stasync<Cfg::BLK_BYTES / 16>(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_r, dg_s + rank * R * UP, bar_g, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_u, dg_s + (GF_C + rank) * R * UP, bar_g, tid);
         if (valid) {      // gradient / stash stores in the shadow of the exchange
             sb_r += dr_pre; sb_u += du_pre; sb_c += dc_pre;
             const long long go = ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
@@ -457,15 +472,15 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
             float acc[4];
             const int mt = warp % MT, ks = warp / MT;
             gf_mma_regs<U, NK_G>(acc, afG, dg_s, ks * NK_G * 16, lane);
-            float* rp = red + ks * (U * R);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4) * R + 2 * t4) = make_float2(acc[0], acc[1]);
-            *reinterpret_cast<float2*>(rp + (mt * 16 + g4 + 8) * R + 2 * t4) = make_float2(acc[2], acc[3]);
+            float* rp = red + ks * (R * RP) + mt * 16 + g4;
+            rp[(2 * t4) * RP] = acc[0]; rp[(2 * t4 + 1) * RP] = acc[1];
+            rp[(2 * t4) * RP + 8] = acc[2]; rp[(2 * t4 + 1) * RP + 8] = acc[3];
         }
         __syncthreads();
         if (act) {
             float sg = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) sg += red[ks * (U * R) + i * R + r];
+            for (int ks = 0; ks < KS; ks++) sg += red[ks * (R * RP) + r * RP + i];
             if (valid) dh_carry = dh * u_ + d_rh * r_ + sg;
         }
         __syncthreads();      // `red` / stages are rewritten at the top of the next iteration
