@@ -97,16 +97,19 @@ __device__ __forceinline__ void af_mma_run(float acc[4], const bf16* Wt, int KP,
         acc[e] += t;
     }
 }
-// fragment -> red[slot][m][r]  (16 rows x 8 batch rows per slot)
+// fragment -> red[slot][r][m]  (8 batch rows x 16 output rows per slot, batch rows AF_RP floats apart).  The activation threads -
+// 16 consecutive output rows of one batch row per half-warp - then read consecutive words; the [m][r] order this replaces made
+// each of their (up to 8) reads per phase a 4-way bank conflict.  Stores: (2t)*20 + g covers 32 different banks.
+constexpr int AF_RP = 20, AF_RSLOT = AF_R * AF_RP;
 __device__ __forceinline__ void af_red_store(float* red, int slot, const float acc[4], int lane) {
     const int g = lane >> 2, t = lane & 3;
-    float* rp = red + slot * 128;
-    *reinterpret_cast<float2*>(rp + g * 8 + 2 * t) = make_float2(acc[0], acc[1]);
-    *reinterpret_cast<float2*>(rp + (g + 8) * 8 + 2 * t) = make_float2(acc[2], acc[3]);
+    float* rp = red + slot * AF_RSLOT + g;
+    rp[(2 * t) * AF_RP] = acc[0]; rp[(2 * t + 1) * AF_RP] = acc[1];
+    rp[(2 * t) * AF_RP + 8] = acc[2]; rp[(2 * t + 1) * AF_RP + 8] = acc[3];
 }
 __device__ __forceinline__ float af_red_sum(const float* red, int slot0, int nslots, int stride, int m, int r) {
     float s = 0.f;
-    for (int k = 0; k < nslots; k++) s += red[(slot0 + k * stride) * 128 + m * 8 + r];
+    for (int k = 0; k < nslots; k++) s += red[(slot0 + k * stride) * AF_RSLOT + r * AF_RP + m];
     return s;
 }
 // One-time operand loads (weights, keys, memory -> bf16 shared memory).  AF_LB loads are issued back to back before the first
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
     float* a_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;             // [R][Tip+4]
     float* p_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
     float* cp_s = reinterpret_cast<float*>(p); p += (size_t)R * TipP * 4;
-    float* red = reinterpret_cast<float*>(p); p += 16 * 128 * 4;                     // 16 slots of [16][8]
+    float* red = reinterpret_cast<float*>(p); p += 16 * AF_RSLOT * 4;                // 16 slots of [8][16 (+4)]
     float* v_s = reinterpret_cast<float*>(p); p += A * 4;
     uint8_t* stage = p; p += 1024;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);                                 // 7 barriers
@@ -620,8 +623,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_fwd_kernel(const AttArgs a)
                 c0 = fmaf(av0, m2.x, c0); c1 = fmaf(av0, m2.y, c1); c2 = fmaf(av1, m3.x, c2); c3 = fmaf(av1, m3.y, c3);
             }
             if (j < jb) { const float2 m2 = __bfloat1622float2(mp[(size_t)j * (U / 2)]); c0 = fmaf(arow[j], m2.x, c0); c1 = fmaf(arow[j], m2.y, c1); }
-            red[jq * 128 + (2 * ip) * 8 + r] = c0 + c2;
-            red[jq * 128 + (2 * ip + 1) * 8 + r] = c1 + c3;
+            *reinterpret_cast<float2*>(red + jq * AF_RSLOT + r * AF_RP + 2 * ip) = make_float2(c0 + c2, c1 + c3);
         }
         __syncthreads();
         float cx = 0.f;
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
     float* p_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;
     float* cp_s = reinterpret_cast<float*>(p);  p += (size_t)R * Tip * 4;
     float* s_s = reinterpret_cast<float*>(p);   p += (size_t)R * Tip * 4;            // (also scratch t2)
-    float* red = reinterpret_cast<float*>(p);   p += 16 * 128 * 4;
+    float* red = reinterpret_cast<float*>(p);   p += 16 * AF_RSLOT * 4;
     float* v_s = reinterpret_cast<float*>(p);   p += A * 4;
     uint8_t* stage = p; p += 1024;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
@@ -873,7 +875,6 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         for (int k = 0; k < CHM; k++) { ev[k] = n_e[k]; apv[k] = n_ap[k]; }
 #pragma unroll
         for (int r = 0; r < R; r++) dy_s[((tid >> 4) * R + r) * 16 + (tid & 15)] = __float2bfloat16(n_dy[r]);
-        prefetch(t - 1);                                          // next iteration's inputs are in flight during this whole step
         __syncthreads();
         // ===== Bp1: dha += dy0.Wo_h^T (own U ha units), dctx = carry + dy0.Wo_c^T (own U ctx units) =====
         {
@@ -891,6 +892,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
         }
         __syncthreads();
         af_push(stage, dctx_s + rank * R * U, b_dctx, R * U * 4, tid);
+        prefetch(t - 1);      // next iteration's inputs (~25 loads and their address arithmetic) are issued in the shadow of the first exchange
         if (aok) a.d_ctx[row * E + unit] = dctx;
         AF_T(0);
         af_wait(b_dctx, par);
@@ -1114,8 +1116,7 @@ __global__ void __launch_bounds__(AF_NT, 1) att_fast_bwd_kernel(const AttArgs a)
                     c0 = fmaf(ger[j], 1.f - ta * ta, c0); c1 = fmaf(ger[j], 1.f - tb * tb, c1);
                 }
             }
-            red[jq * 128 + (2 * jip) * 8 + jr] = c0 + c2;
-            red[jq * 128 + (2 * jip + 1) * 8 + jr] = c1 + c3;
+            *reinterpret_cast<float2*>(red + jq * AF_RSLOT + jr * AF_RP + 2 * jip) = make_float2(c0 + c2, c1 + c3);
         }
         __syncthreads();
         float gq = 0.f;
@@ -1254,7 +1255,7 @@ static size_t af_bwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
     size_t b = AfBwdSmem::w_end + (size_t)AF_R * TJ * AF_E * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16 + (size_t)AF_R * 4 * 4;
     b += (size_t)AF_R * AF_E * 4 + (size_t)(AF_R * Tip + AF_C * AF_EPAD) * 4 + (size_t)AF_R * (AF_A + AF_HA + 2 * AF_HA + AF_Z + AF_Z1 + AF_Y) * 2;
-    b += (size_t)5 * AF_R * Tip * 4 + 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
+    b += (size_t)5 * AF_R * Tip * 4 + 16 * AF_RSLOT * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
 }
 
@@ -1262,7 +1263,7 @@ static size_t af_fwd_smem(int Ti) {
     const int TJ = (Ti + AF_C - 1) / AF_C, Tip = TJ * AF_C;
     size_t b = AfFwdSmem::w_end + (size_t)AF_R * TJ * AF_A * 2 + (size_t)AF_R * (Ti * AF_U + 16) * 2 + 16;
     b += (size_t)AF_R * (AF_E + AF_Z1 + AF_Z + 2 * AF_HA) * 2 + (size_t)AF_R * AF_A * 4 + (size_t)4 * AF_R * (Tip + 4) * 4 + (size_t)AF_C * AF_EPAD * 4;
-    b += 16 * 128 * 4 + AF_A * 4 + 1024 + 64 + 128;
+    b += 16 * AF_RSLOT * 4 + AF_A * 4 + 1024 + 64 + 128;
     return b;
 }
 

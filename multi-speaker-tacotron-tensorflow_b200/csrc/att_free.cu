@@ -292,9 +292,12 @@ __global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, con
         const uint32_t par = t & 1;
         const bool more = t + 1 < Td;
         // ===== P1: z1 = relu(b1 + W1x.x + W1c.ctx)   (x, ctx of the previous step; rnn_wrappers.py:367-378) =====
-        if (t > 0) recv(b_x, (t - 1) & 1, x_bytes, more);
+        // (everywhere below: the part of a product whose operand arrived in an EARLIER phase is computed before the wait for the
+        //  new operand, i.e. in the shadow of the exchange; only the dot product with the new vector stays on the serial path)
         {
-            float s = fr_dot<FR_E, 1, 16>(W1c, ctx_s, nullptr, nullptr, l16) + fr_dot<FR_M, 1, 16>(W1x, x_s, nullptr, nullptr, l16);
+            float s = fr_dot<FR_E, 1, 16>(W1c, ctx_s, nullptr, nullptr, l16);
+            if (t > 0) recv(b_x, (t - 1) & 1, x_bytes, more);
+            s += fr_dot<FR_M, 1, 16>(W1x, x_s, nullptr, nullptr, l16);
             s = fr_half_sum(s);
             pair_push(fmaxf(s + b1_own, 0.f), z1_s, b_z1);
         }
@@ -304,12 +307,14 @@ __global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, con
             float s = warp_sum(fr_dot<FR_Z1, 1, 32>(W2, z1_s, nullptr, nullptr, lane));
             fr_push1(fmaxf(s + b2_own, 0.f), z_s + rank * FR_UZ + warp, b_z, lane, lane < FR_C);
         }
-        recv(b_z, par, FR_Z * 4, more);
         // ===== P3: attention-GRU gates over [z ; ha] and the z part of the candidate =====
         float ug, cz;
         {
-            float sr = fr_dot<FR_Z, 1, 16>(Wgr, z_s, nullptr, nullptr, l16) + fr_dot<FR_HA, 1, 16>(Wgr + FR_Z, ha_s, nullptr, nullptr, l16);
-            float su = fr_dot<FR_Z, 1, 16>(Wgu, z_s, nullptr, nullptr, l16) + fr_dot<FR_HA, 1, 16>(Wgu + FR_Z, ha_s, nullptr, nullptr, l16);
+            float sr = fr_dot<FR_HA, 1, 16>(Wgr + FR_Z, ha_s, nullptr, nullptr, l16);       // ha of the previous step
+            float su = fr_dot<FR_HA, 1, 16>(Wgu + FR_Z, ha_s, nullptr, nullptr, l16);
+            recv(b_z, par, FR_Z * 4, more);
+            sr += fr_dot<FR_Z, 1, 16>(Wgr, z_s, nullptr, nullptr, l16);
+            su += fr_dot<FR_Z, 1, 16>(Wgu, z_s, nullptr, nullptr, l16);
             float sc = fr_dot<FR_Z, 1, 16>(Wcz, z_s, nullptr, nullptr, l16);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
@@ -422,12 +427,14 @@ __global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, con
             const float s = fr_half_sum(fr_dot<FR_E, 1, 16>(Woc, ctx_s, nullptr, nullptr, l16));
             pair_push(yh + s + bo_own, y0_s, b_y0);
         }
-        recv(b_y0, par, FR_Y * 4, more);
         // ===== P9 / P10: residual GRU 1 over x = y0   (tacotron.py:171-175) =====
         float u1, cx1;
         {
-            float sr = fr_dot<FR_Y, 1, 16>(G1r, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G1r + FR_Y, h1_s, nullptr, nullptr, l16);
-            float su = fr_dot<FR_Y, 1, 16>(G1u, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G1u + FR_Y, h1_s, nullptr, nullptr, l16);
+            float sr = fr_dot<FR_Y, 1, 16>(G1r + FR_Y, h1_s, nullptr, nullptr, l16);        // h1 of the previous step
+            float su = fr_dot<FR_Y, 1, 16>(G1u + FR_Y, h1_s, nullptr, nullptr, l16);
+            recv(b_y0, par, FR_Y * 4, more);
+            sr += fr_dot<FR_Y, 1, 16>(G1r, y0_s, nullptr, nullptr, l16);
+            su += fr_dot<FR_Y, 1, 16>(G1u, y0_s, nullptr, nullptr, l16);
             float sc = fr_dot<FR_Y, 1, 16>(G1cx, y0_s, nullptr, nullptr, l16);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
@@ -444,13 +451,17 @@ __global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, con
             h1_own = u1 * h1_own + (1.f - u1) * cc;
             pair_push(h1_own, h1_s, b_h1);
         }
-        recv(b_h1, par, FR_Y * 4, more);
         // ===== P11 / P12: residual GRU 2 over x = y1 = y0 + h1 =====
         float u2, cx2;
         {
-            float sr = fr_dot<FR_Y, 2, 16>(G2r, y0_s, h1_s, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2r + FR_Y, h2_s, nullptr, nullptr, l16);
-            float su = fr_dot<FR_Y, 2, 16>(G2u, y0_s, h1_s, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2u + FR_Y, h2_s, nullptr, nullptr, l16);
-            float sc = fr_dot<FR_Y, 2, 16>(G2cx, y0_s, h1_s, nullptr, l16);
+            // y0 and the previous h2 are here already: W.(y0 + h1) = W.y0 + W.h1
+            float sr = fr_dot<FR_Y, 1, 16>(G2r, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2r + FR_Y, h2_s, nullptr, nullptr, l16);
+            float su = fr_dot<FR_Y, 1, 16>(G2u, y0_s, nullptr, nullptr, l16) + fr_dot<FR_Y, 1, 16>(G2u + FR_Y, h2_s, nullptr, nullptr, l16);
+            float sc = fr_dot<FR_Y, 1, 16>(G2cx, y0_s, nullptr, nullptr, l16);
+            recv(b_h1, par, FR_Y * 4, more);
+            sr += fr_dot<FR_Y, 1, 16>(G2r, h1_s, nullptr, nullptr, l16);
+            su += fr_dot<FR_Y, 1, 16>(G2u, h1_s, nullptr, nullptr, l16);
+            sc += fr_dot<FR_Y, 1, 16>(G2cx, h1_s, nullptr, nullptr, l16);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
                 sr += __shfl_xor_sync(0xffffffffu, sr, o); su += __shfl_xor_sync(0xffffffffu, su, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
@@ -466,10 +477,11 @@ __global__ void __launch_bounds__(FR_NT, 1) att_free_kernel(const AttArgs a, con
             h2_own = u2 * h2_own + (1.f - u2) * cc;
             pair_push(h2_own, h2_s, b_h2);
         }
-        recv(b_h2, par, FR_Y * 4, more);
         // ===== P13: r-frame mel projection over y2 = y0 + h1 + h2; its last frame is the next step's input (helpers.py:26-32) =====
         {
-            float s0 = fr_dot<FR_Y, 3, 16>(Wm0, y0_s, h1_s, h2_s, l16), s1 = fr_dot<FR_Y, 3, 16>(Wm1, y0_s, h1_s, h2_s, l16);
+            float s0 = fr_dot<FR_Y, 2, 16>(Wm0, y0_s, h1_s, nullptr, l16), s1 = fr_dot<FR_Y, 2, 16>(Wm1, y0_s, h1_s, nullptr, l16);
+            recv(b_h2, par, FR_Y * 4, more);
+            s0 += fr_dot<FR_Y, 1, 16>(Wm0, h2_s, nullptr, nullptr, l16); s1 += fr_dot<FR_Y, 1, 16>(Wm1, h2_s, nullptr, nullptr, l16);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
             const float o0 = s0 + bm0, o1 = s1 + bm1;
