@@ -64,7 +64,16 @@ struct FrOff {
 constexpr size_t FR_W_BYTES = (size_t)FrOff::end * 2;           // 190 976
 
 // row i of matrix `m`, rank `rank`: column  (i < split ? offA + rank*UA + i : offB + rank*UB + i - split)  of W[(row0 + k)*ld + col]
+// Rows whose length is a multiple of 128 are stored in the order the dot product walks them: 16-byte chunk l of a 128-block
+// holds k = 4l..4l+3 and 64+4l..64+4l+3, so that the lanes' two 16-byte operand loads per chunk are CONSECUTIVE (with 8
+// consecutive k per lane the operand loads were 32 bytes apart: a 2-way bank conflict on every one - a third of all
+// shared-memory wavefronts in the first ncu capture).
 struct FrSpec { const float* W; int ld, row0, K, rows, split, offA, UA, offB, UB, own, col_limit, off; };
+__host__ __device__ __forceinline__ int fr_perm(int k, int K) {       // source k -> position in the image row
+    if (K % 128 != 0) return k;
+    const int blk = k >> 7, w = k & 127;
+    return (blk << 7) + (w < 64 ? 8 * (w >> 2) + (w & 3) : 8 * ((w - 64) >> 2) + 4 + (w & 3));
+}
 struct FrTable { FrSpec s[FRW_N]; };
 
 __global__ void __launch_bounds__(256) fr_pack_kernel(const __grid_constant__ FrTable tb, bf16* __restrict__ img) {
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(256) fr_pack_kernel(const __grid_constant__ Fr
         const int k = idx / sp.rows, i = idx % sp.rows;         // consecutive threads read consecutive columns of one weight row
         const int col = i < sp.split ? sp.offA + rank * sp.UA + i : sp.offB + rank * sp.UB + (i - sp.split);
         const bool ok = (i < sp.split ? i < sp.own : true) && col < sp.col_limit;
-        dst[(size_t)i * sp.K + k] = __float2bfloat16(ok ? __ldg(sp.W + (long long)(sp.row0 + k) * sp.ld + col) : 0.f);
+        dst[(size_t)i * sp.K + fr_perm(k, sp.K)] = __float2bfloat16(ok ? __ldg(sp.W + (long long)(sp.row0 + k) * sp.ld + col) : 0.f);
     }
 }
 
@@ -125,16 +134,18 @@ __device__ __forceinline__ float fr_half_sum(float v) {      // sum over the 16 
     return v;
 }
 // 8 weights (one 16-byte chunk of a bf16 row) . 8 operand values;  the operand is the elementwise sum of NV fp32 vectors
-template <int NV>
+template <int NV, bool PERM>
 __device__ __forceinline__ float fr_dot8(const bf16* wrow, const float* v0, const float* v1, const float* v2, int ch) {
     const uint4 w = *reinterpret_cast<const uint4*>(wrow + 8 * ch);
-    float4 a = *reinterpret_cast<const float4*>(v0 + 8 * ch), b = *reinterpret_cast<const float4*>(v0 + 8 * ch + 4);
+    // operand elements of chunk ch: PERM (see fr_perm) k = 128*(ch/16) + 4*(ch%16) + {0..3} and the same + 64; else 8*ch + {0..7}
+    const int oa = PERM ? ((ch >> 4) << 7) + 4 * (ch & 15) : 8 * ch, ob = PERM ? oa + 64 : oa + 4;
+    float4 a = *reinterpret_cast<const float4*>(v0 + oa), b = *reinterpret_cast<const float4*>(v0 + ob);
     if (NV > 1) {
-        const float4 c = *reinterpret_cast<const float4*>(v1 + 8 * ch), d = *reinterpret_cast<const float4*>(v1 + 8 * ch + 4);
+        const float4 c = *reinterpret_cast<const float4*>(v1 + oa), d = *reinterpret_cast<const float4*>(v1 + ob);
         a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
     }
     if (NV > 2) {
-        const float4 c = *reinterpret_cast<const float4*>(v2 + 8 * ch), d = *reinterpret_cast<const float4*>(v2 + 8 * ch + 4);
+        const float4 c = *reinterpret_cast<const float4*>(v2 + oa), d = *reinterpret_cast<const float4*>(v2 + ob);
         a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
     }
     float s0 = fr_lo(w.x) * a.x, s1 = fr_hi(w.x) * a.y;
@@ -152,7 +163,7 @@ __device__ __forceinline__ float fr_dot(const bf16* wrow, const float* v0, const
 #pragma unroll
     for (int c = 0; c < IT; c++) {
         const int ch = c * LANES + l;
-        if (CHUNKS % LANES == 0 || ch < CHUNKS) s += fr_dot8<NV>(wrow, v0, v1, v2, ch);
+        if (CHUNKS % LANES == 0 || ch < CHUNKS) s += fr_dot8<NV, K % 128 == 0>(wrow, v0, v1, v2, ch);
     }
     return s;
 }

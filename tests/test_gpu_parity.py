@@ -347,6 +347,35 @@ def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb, prec):
     eng.close()
 
 
+@pytest.mark.parametrize("prec", FAST)
+@pytest.mark.parametrize("case", ["n1_t37_mon", "n3_t130_mon", "n8_t16_bah", "n2_t64_deepvoice", "n9_general"])
+def test_low_batch_free_running_decoder_vs_oracle(tb, prec, case):
+    """The resident-weight free-running decoder (csrc/att_free.cu: one 16-CTA cluster per utterance, N <= 8) against the oracle:
+    text lengths that are not multiples of 16 / 32 (position slices and lane chunks partly filled), 1 / 3 / 8 clusters, softmax
+    attention, deepvoice initial states of all three recurrences; `n9_general` is one row more than the kernel takes and runs the
+    general kernel (csrc/attention.cu) through the same call.  rnn_wrappers.py:218-341, helpers.py:9-32, tacotron.py:127-179."""
+    N, Ti, att, multi = {"n1_t37_mon": (1, 37, "bah_mon", False), "n3_t130_mon": (3, 130, "bah_mon", False), "n8_t16_bah": (8, 16, "bah", False),
+                         "n2_t64_deepvoice": (2, 64, "bah_mon", True), "n9_general": (9, 21, "bah_mon", False)}[case]
+    steps = 12
+    hp = tb.hparams.override(reduction_factor=5, attention_type=att, **({"model_type": "deepvoice"} if multi else {}))
+    S = 3 if multi else 1
+    named = tb.params.init_params(hp, S, seed=61, randomize_bn_state=True)
+    g = torch.Generator().manual_seed(17)
+    lengths = [Ti] + torch.randint(max(2, Ti // 2), Ti + 1, (N - 1,), generator=g).tolist()
+    b = _batch(N, Ti, 5, lengths, seed=31)
+    spk = torch.randint(0, S, (N,), generator=g, dtype=torch.int32) if multi else None
+    with torch.no_grad():
+        ref = O.forward(named, hp, b["inputs"], b["input_lengths"], S, spk, max_iters=steps, speaker_mode="deepvoice" if multi else "none")
+    eng = tb.Engine(hp, S, precision=prec, named_params=named)
+    out = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=steps)
+    assert out["mel_outputs"].shape == (N, steps * 5, 80) and out["alignments"].shape == (N, Ti, steps)
+    print("free-running %s (%s):" % (case, prec), _check_outputs(out, ref, TOL[prec], bound="free", argmax_min=0.93))
+    first = {k: out[k].clone() for k in ("mel_outputs", "linear_outputs", "alignments")}     # (outputs are views of the workspace)
+    out2 = eng.forward(b["inputs"], b["input_lengths"], spk, decoder_steps=steps)          # same call again: bit-identical
+    assert all(torch.equal(first[k], out2[k]) for k in first)
+    eng.close()
+
+
 def test_free_running_inference_matches_golden_and_oracle(tb, hp5, golden_setup):
     named, b = golden_setup
     gold = np.load(os.path.join(ROOT, "tests", "golden", "tacotron_infer_small.npz"))
