@@ -50,8 +50,8 @@ __device__ __forceinline__ void af_push(const void* stage, void* dst, uint64_t* 
         const uint32_t peer = idx / nq, q = idx % nq;
         const uint4 v = *(reinterpret_cast<const uint4*>(stage) + q);
         uint32_t d, b;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(af_u32(dst) + q * 16), "r"(peer));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(af_u32(bar)), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(af_u32(dst) + q * 16), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(af_u32(bar)), "r"(peer));
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                      ::"r"(d), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(b) : "memory");
     }

@@ -109,8 +109,8 @@ __device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fr_push2(float v0, float v1, const float* dst, uint64_t* bar, int lane) {
     if (lane < FR_C) {
         uint32_t d, b;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(lane));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(lane));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(lane));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(lane));
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
                      ::"r"(d), "r"(__float_as_uint(v0)), "r"(__float_as_uint(v1)), "r"(b) : "memory");
     }
@@ -118,8 +118,8 @@ __device__ __forceinline__ void fr_push2(float v0, float v1, const float* dst, u
 __device__ __forceinline__ void fr_push1(float v, const float* dst, uint64_t* bar, int peer, bool on) {
     if (on) {
         uint32_t d, b;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(peer));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(fr_u32(dst)), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(b) : "r"(fr_u32(bar)), "r"(peer));
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                      ::"r"(d), "r"(__float_as_uint(v)), "r"(b) : "memory");
     }

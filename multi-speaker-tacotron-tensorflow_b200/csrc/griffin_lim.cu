@@ -20,12 +20,11 @@ struct GlState {
     float* wsum = nullptr;       // [n_fft + hop*(max_frames-1)] sum of squared windows
     float* mag = nullptr;        // [max_frames, nbins] target magnitudes (S^power)
     cufftComplex* spec = nullptr;// [max_frames, nbins]
-    float* frames = nullptr;     // [max_frames, n_fft]   inverse-FFT frames
-    float* frames2 = nullptr;    // [max_frames, n_fft]   re-windowed frames of the next forward transform (gl_ola_frame_kernel)
+    float* frames = nullptr;     // [max_frames, n_fft]
     float* y = nullptr;          // [n_fft + hop*(max_frames-1)] untrimmed signal
     float* carry = nullptr;      // IIR chunk states
     size_t bytes = 0;
-    // The iteration loop (4 launches x n_iters of ~3 us kernels) is launch-bound: it is captured once per (T, n_iters) into a
+    // The iteration loop (5 launches x n_iters of ~3 us kernels) is launch-bound: it is captured once per (T, n_iters) into a
     // CUDA graph and replayed (TACO_GL_GRAPH=0 issues the launches one by one).
     cudaGraphExec_t graph = nullptr; int graph_T = 0, graph_iters = -1; cudaStream_t capture_stream = nullptr;
 };
@@ -96,34 +95,6 @@ __global__ void gl_frame_kernel(const float* __restrict__ y, const float* __rest
     if (j >= L) j = 2 * (L - 1) - j;
     j = min(max(j, 0), L - 1);
     frames[idx] = w[k] * y[n_fft / 2 + j];
-}
-// gl_ola_kernel + gl_frame_kernel in one pass for the iterations that feed another transform: the next frames are written
-// straight from the inverse-FFT frames, y never goes through memory (each sample is rebuilt by the <= 4 frames that overlap
-// it - the same loop, in the same order, as gl_ola_kernel, so the result is bit-identical; the 41 % of taps outside the Hann
-// window are written as zeros without any load).  `in` and `out` must be different buffers.
-__global__ void gl_ola_frame_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ wsum,
-                                    float* __restrict__ out, int n_fft, int hop, int T, int L, float inv_nfft, float tiny) {
-    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= (long long)T * n_fft) return;
-    const int k = (int)(idx % n_fft), i = (int)(idx / n_fft);
-    const float wk = w[k];
-    float v = 0.f;
-    if (wk != 0.f) {
-        int j = i * hop + k - n_fft / 2;          // index into ytrim (see gl_frame_kernel)
-        if (j < 0) j = -j;
-        if (j >= L) j = 2 * (L - 1) - j;
-        j = min(max(j, 0), L - 1);
-        const int s = n_fft / 2 + j;
-        float acc = 0.f;
-        for (int f = min(T - 1, s / hop); f >= 0; f--) {
-            const int kk = s - f * hop;
-            if (kk >= n_fft) break;
-            acc += w[kk] * in[(long long)f * n_fft + kk] * inv_nfft;
-        }
-        const float ws = wsum[s];
-        v = wk * ((ws > tiny) ? acc / ws : acc);
-    }
-    out[idx] = v;
 }
 // spec <- mag * spec / |spec|   (angle(0) = 0 -> unit phase 1)
 __global__ void gl_phase_kernel(cufftComplex* __restrict__ spec, const float* __restrict__ mag, long long n) {
@@ -229,10 +200,9 @@ int taco_gl_create(taco_gl* out, int32_t n_fft, int32_t hop, int32_t win, int32_
     TACO_CHECK_CUDA(cudaMalloc(&g.mag, sizeof(float) * nb));
     TACO_CHECK_CUDA(cudaMalloc(&g.spec, sizeof(cufftComplex) * nb));
     TACO_CHECK_CUDA(cudaMalloc(&g.frames, sizeof(float) * (size_t)max_frames * n_fft));
-    TACO_CHECK_CUDA(cudaMalloc(&g.frames2, sizeof(float) * (size_t)max_frames * n_fft));
     TACO_CHECK_CUDA(cudaMalloc(&g.y, sizeof(float) * len));
     TACO_CHECK_CUDA(cudaMalloc(&g.carry, sizeof(float) * (len / IIR_CHUNK + 2)));
-    g.bytes = sizeof(float) * (n_fft + 2 * len + nb + 2 * (size_t)max_frames * n_fft) + sizeof(cufftComplex) * nb;
+    g.bytes = sizeof(float) * (n_fft + 2 * len + nb + (size_t)max_frames * n_fft) + sizeof(cufftComplex) * nb;
     gl_window_kernel<<<cdiv(n_fft, 256), 256>>>(g.window, n_fft, win);
     TACO_CHECK_LAUNCH();
     TACO_CHECK_CUDA(cudaDeviceSynchronize());
@@ -248,7 +218,7 @@ int taco_gl_destroy(taco_gl h) {
     if (g.c2r) cufftDestroy(g.c2r);
     if (g.r2c) cufftDestroy(g.r2c);
     if (g.ana_r2c) cufftDestroy(g.ana_r2c);
-    cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.frames2); cudaFree(g.y); cudaFree(g.carry);
+    cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.y); cudaFree(g.carry);
     delete h;
     return TACO_OK;
 }
@@ -285,15 +255,12 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
         TACO_CHECK_CUFFT(cufftSetStream(g.r2c, st));
         for (int it = 0; it <= n_iters; it++) {
             TACO_CHECK_CUFFT(cufftExecC2R(g.c2r, g.spec, g.frames));
-            if (it == n_iters) {      // the last inverse transform produces the waveform
-                gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
-                TACO_CHECK_CUDA(cudaGetLastError());
-                break;
-            }
-            gl_ola_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.frames2, g.n_fft, g.hop, T, L,
-                                                                                              inv_nfft, 1.17549435e-38f);
+            gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
             TACO_CHECK_CUDA(cudaGetLastError());
-            TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames2, g.spec));
+            if (it == n_iters) break;
+            gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, st>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
+            TACO_CHECK_CUDA(cudaGetLastError());
+            TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
             gl_phase_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, st>>>(g.spec, g.mag, nb);
             TACO_CHECK_CUDA(cudaGetLastError());
         }
@@ -318,7 +285,7 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
     } else {
         TACO_TRY(iterate(s));
     }
-    g_launch_count += 4LL * n_iters + 2;           // kernels of the loop (cuFFT counts as one launch per transform)
+    g_launch_count += 5LL * n_iters + 2;           // kernels of the loop (cuFFT counts as one launch per transform)
     // inverse pre-emphasis on the trimmed signal
     const int nchunks = cdiv(L, IIR_CHUNK);
     iir_local_kernel<<<cdiv(nchunks, 128), 128, 0, s>>>(g.y + g.n_fft / 2, wav_out, g.carry, L, preemphasis);

@@ -39,8 +39,8 @@ __device__ __forceinline__ void gf_mbar_wait(uint64_t* bar, uint32_t parity) {
 // bulk copy local shared -> peer CTA's shared (same offsets), completing `bytes` on the peer's mbarrier
 __device__ __forceinline__ void gf_push(const void* src_local, void* dst_local_alias, uint64_t* bar_local_alias, uint32_t bytes, uint32_t peer) {
     uint32_t dst, bar;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias)), "r"(peer));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias)), "r"(peer));
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "r"(gf_smem_u32(src_local)), "r"(bytes), "r"(bar) : "memory");
 }
@@ -54,8 +54,8 @@ __device__ __forceinline__ void gf_push_stasync(const void* stage, void* dst_loc
         const uint32_t peer = tid / NQ, q = tid % NQ;
         const uint4 v = *(reinterpret_cast<const uint4*>(stage) + q);
         uint32_t dst, bar;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias) + (q / QR) * ROWB + (q % QR) * 16), "r"(peer));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(gf_smem_u32(dst_local_alias) + (q / QR) * ROWB + (q % QR) * 16), "r"(peer));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(gf_smem_u32(bar_local_alias)), "r"(peer));
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                      ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
     }
