@@ -133,7 +133,7 @@ bool att_wfrag_supported(const AttArgs& a);
 size_t att_wfrag_bytes(const AttArgs& a);
 int launch_att_wfrag_pack(AttArgs& a, void* buf, cudaStream_t s);
 int launch_att_bwd(const AttArgs& a, cudaStream_t s);
-// att_free.cu: resident-weight free-running decoder for low-batch synthesis (one 16-CTA cluster per utterance, N <= 8)
+// att_free.cu: resident-weight free-running decoder for low-batch synthesis (one 16-CTA cluster per utterance, N <= 32)
 bool att_free_supported(const AttArgs& a);
 size_t att_free_image_bytes();
 int launch_att_free(const AttArgs& a, void* img, cudaStream_t s);   // TACO_ENOTSUP when 16-CTA clusters cannot be launched

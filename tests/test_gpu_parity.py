@@ -348,14 +348,14 @@ def test_baseline_configs_c4_c5_inference_full_size_vs_oracle(tb, prec):
 
 
 @pytest.mark.parametrize("prec", FAST)
-@pytest.mark.parametrize("case", ["n1_t37_mon", "n3_t130_mon", "n8_t16_bah", "n2_t64_deepvoice", "n9_general"])
+@pytest.mark.parametrize("case", ["n1_t37_mon", "n3_t130_mon", "n8_t16_bah", "n2_t64_deepvoice", "n11_waves", "n33_general"])
 def test_low_batch_free_running_decoder_vs_oracle(tb, prec, case):
-    """The resident-weight free-running decoder (csrc/att_free.cu: one 16-CTA cluster per utterance, N <= 8) against the oracle:
+    """The resident-weight free-running decoder (csrc/att_free.cu: one 16-CTA cluster per utterance, N <= 32) against the oracle:
     text lengths that are not multiples of 16 / 32 (position slices and lane chunks partly filled), 1 / 3 / 8 clusters, softmax
-    attention, deepvoice initial states of all three recurrences; `n9_general` is one row more than the kernel takes and runs the
-    general kernel (csrc/attention.cu) through the same call.  rnn_wrappers.py:218-341, helpers.py:9-32, tacotron.py:127-179."""
+    attention, deepvoice initial states of all three recurrences, more clusters than fit the machine at once (`n11_waves`);
+    `n33_general` is one row more than the kernel takes and runs the general kernel (csrc/attention.cu) through the same call.  rnn_wrappers.py:218-341, helpers.py:9-32, tacotron.py:127-179."""
     N, Ti, att, multi = {"n1_t37_mon": (1, 37, "bah_mon", False), "n3_t130_mon": (3, 130, "bah_mon", False), "n8_t16_bah": (8, 16, "bah", False),
-                         "n2_t64_deepvoice": (2, 64, "bah_mon", True), "n9_general": (9, 21, "bah_mon", False)}[case]
+                         "n2_t64_deepvoice": (2, 64, "bah_mon", True), "n11_waves": (11, 21, "bah_mon", False), "n33_general": (33, 21, "bah_mon", False)}[case]
     steps = 12
     hp = tb.hparams.override(reduction_factor=5, attention_type=att, **({"model_type": "deepvoice"} if multi else {}))
     S = 3 if multi else 1
