@@ -571,7 +571,6 @@ int launch_att_free(const AttArgs& a, void* img, cudaStream_t s) {
     FrTable tb; fr_table(a, tb);
     fr_pack_kernel<<<dim3(FR_C, FRW_N), 256, 0, s>>>(tb, static_cast<bf16*>(img));
     TACO_CHECK_LAUNCH();
-    g_launch_count++;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(FR_C * a.N);
     cfg.blockDim = dim3(FR_NT);

@@ -709,6 +709,39 @@ int launch_pack_dgrad(const float* W, float* Wd, int k, int Cin, int Cout, cudaS
     return TACO_OK;
 }
 
+// ---- table-driven operand preparation ----------------------------------------------------------------------------------
+// The backward pass reads ~80 small parameter-only operands (flipped / transposed convolution kernels, concatenated GRU and
+// highway weights, transposed attention weights; in bf16 mode also their bf16 mirrors).  One launch per operand and per mirror
+// was 78 launches of ~5 us per step beside the forward pass; a table of gather descriptors runs them in one launch per block
+// of the model (grid.y = operand), each element written as fp32 and - where the operand has a mirror - as bf16 in the same pass.
+__global__ void __launch_bounds__(256) prep_ops_kernel(const __grid_constant__ PrepTable tb) {
+    const PrepOp& o = tb.op[blockIdx.y];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < o.total; i += (long long)gridDim.x * blockDim.x) {
+        long long si, di;
+        if (o.kind == PREP_PACK_DGRAD) {            // Wd[j'][co][ci] = W[k-1-j'][ci][co]       a = k, b = Cin, c = Cout
+            const int ci = (int)(i % o.b); const long long r = i / o.b;
+            const int co = (int)(r % o.c), jp = (int)(r / o.c);
+            si = ((long long)(o.a - 1 - jp) * o.b + ci) * o.c + co; di = i;
+        } else if (o.kind == PREP_COPY2D) {          // dst[r*ldd + c] = src[r*lds + c]         b = cols
+            const long long r = i / o.b; const int c = (int)(i % o.b);
+            si = r * o.lds + c; di = r * o.ldd + c;
+        } else {                                     // transpose: out[c*rows + r] = in[r*cols + c]   a = rows, b = cols
+            const int c = (int)(i / o.a), r = (int)(i % o.a);
+            si = (long long)r * o.b + c; di = i;
+        }
+        const float v = __ldg(o.src + si);
+        o.dst[di] = v;
+        if (o.dst16) static_cast<bf16*>(o.dst16)[di] = __float2bfloat16_rn(v);
+    }
+}
+int launch_prep_ops(const PrepTable& tb, cudaStream_t s) {
+    if (tb.n <= 0) return TACO_OK;
+    TACO_REQUIRE(tb.n <= PREP_MAX_OPS, TACO_EINVAL, "prep table: %d operands exceed %d", tb.n, PREP_MAX_OPS);
+    prep_ops_kernel<<<dim3(96, tb.n), 256, 0, s>>>(tb);
+    TACO_CHECK_LAUNCH();
+    return TACO_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // L1 loss + gradient.  out/target rows: out row (n,t) at out + (n*out_bs + t*out_ts), target at tgt + (n*T + t)*C.
 // scalars[0] += sum |d|*coeff*w ; scalars[1] += sum |d| (unweighted, all bins) ; scalars[2] += sum |d| over the priority band.

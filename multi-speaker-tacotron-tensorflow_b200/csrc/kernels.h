@@ -45,6 +45,26 @@ int launch_bcast_rows(const float* src, float* dst, int N, int T, int C, long lo
 int launch_timesum(const float* x, float* out, int N, int T, int Tp, int PL, int C, cudaStream_t s);
 int launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t s);
 int launch_copy2d(float* dst, const float* src, long long rows, int cols, long long ldd, long long lds, cudaStream_t s);
+// table-driven operand preparation (elementwise.cu: prep_ops_kernel): gather descriptors, one launch for all of them
+enum { PREP_PACK_DGRAD = 0, PREP_COPY2D = 1, PREP_TRANSPOSE = 2, PREP_MAX_OPS = 40 };
+struct PrepOp { const float* src; float* dst; void* dst16; int kind, a, b, c; long long ldd, lds, total; };
+struct PrepTable {
+    PrepOp op[PREP_MAX_OPS]; int n = 0;
+    bool add(const PrepOp& o) { if (n >= PREP_MAX_OPS) return false; op[n++] = o; return true; }
+    // Wd[j'][co][ci] = W[k-1-j'][ci][co]
+    bool pack_dgrad(const float* W, float* Wd, void* Wd16, int k, int Cin, int Cout) {
+        return add(PrepOp{W, Wd, Wd16, PREP_PACK_DGRAD, k, Cin, Cout, 0, 0, (long long)k * Cin * Cout});
+    }
+    // dst[r*ldd + c] = src[r*lds + c]
+    bool copy2d(float* dst, void* dst16, const float* src, long long rows, int cols, long long ldd, long long lds) {
+        return add(PrepOp{src, dst, dst16, PREP_COPY2D, 0, cols, 0, ldd, lds, rows * cols});
+    }
+    // out[c*rows + r] = in[r*cols + c]
+    bool transpose(const float* in, float* out, int rows, int cols) {
+        return add(PrepOp{in, out, nullptr, PREP_TRANSPOSE, rows, cols, 0, 0, 0, (long long)rows * cols});
+    }
+};
+int launch_prep_ops(const PrepTable& tb, cudaStream_t s);
 int launch_l1_loss(const float* out, long long out_bs, long long out_ts, const float* tgt, const float* coeff,
                    float* grad, long long grad_bs, long long grad_ts, int N, int T, int C,
                    float w_all, float w_band, int lo, int hi, double* scalars, cudaStream_t s, void* grad16 = nullptr,

@@ -492,44 +492,44 @@ float* bank_wd(const Model& m, const CbhgGeom& g, int k) {
 // forward pass (taco_forward), or in line at the start of the backward pass when the two-stream schedule is off.
 static int backward_prep(Model& m, cudaStream_t s) {
     const taco_config& c = m.cfg;
+    auto off16 = [](void* p, long long elems) -> void* { return p ? static_cast<void*>(static_cast<uint16_t*>(p) + elems) : nullptr; };
     for (const CbhgGeom* gp : {&m.enc, &m.post}) {
         const CbhgGeom& g = *gp; const std::string p = g.prefix + "/";
         const int H = g.H;
-        for (int k = 1; k <= g.Kb; k++)
-            TACO_TRY(launch_pack_dgrad(m.P(p + "bank_" + std::to_string(k) + "/kernel"), bank_wd(m, g, k), k, g.Cin, g.Cb, s));
-        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_1/kernel"), m.W(p + "proj_1/wd"), g.pw, g.Kb * g.Cb, g.P1, s));
-        TACO_TRY(launch_pack_dgrad(m.P(p + "proj_2/kernel"), m.W(p + "proj_2/wd"), g.pw, g.P1, g.P2, s));
-        float* wx = m.W(p + "gru_wxcat");
+        // one table per CBHG (prep_ops_kernel): every packed operand and, in bf16 mode, its mirror in the same pass (the
+        // contraction kernels of the bf16 mode read nothing else)
+        PrepTable tb;
+        bool ok = true;
+        for (int k = 1; k <= g.Kb; k++) {
+            const long long o = (long long)g.Cb * g.Cin * (k - 1) * k / 2;
+            ok = ok && tb.pack_dgrad(m.P(p + "bank_" + std::to_string(k) + "/kernel"), bank_wd(m, g, k), off16(m.W16(p + "bank_wd"), o), k, g.Cin, g.Cb);
+        }
+        ok = ok && tb.pack_dgrad(m.P(p + "proj_1/kernel"), m.W(p + "proj_1/wd"), m.W16(p + "proj_1/wd"), g.pw, g.Kb * g.Cb, g.P1);
+        ok = ok && tb.pack_dgrad(m.P(p + "proj_2/kernel"), m.W(p + "proj_2/wd"), m.W16(p + "proj_2/wd"), g.pw, g.P1, g.P2);
+        float* wx = m.W(p + "gru_wxcat"); void* wx16 = m.W16(p + "gru_wxcat");
         const char* dirs[2] = {"gru_fw", "gru_bw"};
         for (int dd = 0; dd < 2; dd++) {
-            TACO_TRY(launch_copy2d(wx + dd * 3 * H, m.P(p + dirs[dd] + "/gates_kernel"), H, 2 * H, 6 * H, 2 * H, s));
-            TACO_TRY(launch_copy2d(wx + dd * 3 * H + 2 * H, m.P(p + dirs[dd] + "/cand_kernel"), H, H, 6 * H, H, s));
+            ok = ok && tb.copy2d(wx + dd * 3 * H, off16(wx16, dd * 3 * H), m.P(p + dirs[dd] + "/gates_kernel"), H, 2 * H, 6 * H, 2 * H);
+            ok = ok && tb.copy2d(wx + dd * 3 * H + 2 * H, off16(wx16, dd * 3 * H + 2 * H), m.P(p + dirs[dd] + "/cand_kernel"), H, H, 6 * H, H);
         }
         for (int i = 1; i <= g.depth; i++) {
             const std::string hn = p + "highway_" + std::to_string(i);
-            float* wc = m.W(p + "hw_wcat_" + std::to_string(i));
-            TACO_TRY(launch_copy2d(wc, m.P(hn + "/H_kernel"), H, H, 2 * H, H, s));
-            TACO_TRY(launch_copy2d(wc + H, m.P(hn + "/T_kernel"), H, H, 2 * H, H, s));
+            float* wc = m.W(p + "hw_wcat_" + std::to_string(i)); void* wc16 = m.W16(p + "hw_wcat_" + std::to_string(i));
+            ok = ok && tb.copy2d(wc, wc16, m.P(hn + "/H_kernel"), H, H, 2 * H, H);
+            ok = ok && tb.copy2d(wc + H, off16(wc16, H), m.P(hn + "/T_kernel"), H, H, 2 * H, H);
         }
-        if (m.use16()) {
-            // bf16 mirrors of the packed operands (the contraction kernels of the bf16 mode read nothing else)
-            auto mirror = [&](const std::string& name) -> int {
-                auto it = m.regions.find(name);
-                return launch_cast2d_bf16(m.W16(name), m.W(name), 1, (int)it->second.numel, it->second.numel, it->second.numel, s);
-            };
-            TACO_TRY(mirror(p + "bank_wd")); TACO_TRY(mirror(p + "proj_1/wd")); TACO_TRY(mirror(p + "proj_2/wd")); TACO_TRY(mirror(p + "gru_wxcat"));
-            for (int i = 1; i <= g.depth; i++) TACO_TRY(mirror(p + "hw_wcat_" + std::to_string(i)));
-        }
-        const int tb = m.use16() ? 64 : 32;          // k-tile width of the kernel that walks the table
-        if (!m.tables_ready && g.Cb % tb == 0) {
-            // k-tile i of the merged bank data gradient: member k, tap j, channel block q  ->  column (k-1)*Cb + tb*q of
+        TACO_REQUIRE(ok, TACO_EINVAL, "backward_prep: operand table of %s overflows", g.prefix.c_str());
+        TACO_TRY(launch_prep_ops(tb, s));
+        const int tb_w = m.use16() ? 64 : 32;          // k-tile width of the kernel that walks the table
+        if (!m.tables_ready && g.Cb % tb_w == 0) {
+            // k-tile i of the merged bank data gradient: member k, tap j, channel block q  ->  column (k-1)*Cb + tb_w*q of
             // d_bank, row offset j - r_k (+ Kb: the operand base sits Kb slack rows before the buffer)
             std::vector<int>& tab = (gp == &m.enc) ? m.taps_enc : m.taps_post;
             tab.clear();
             for (int k = 1; k <= g.Kb; k++) {
                 const int l = (k - 1) / 2, r = k - 1 - l;
                 for (int j = 0; j < k; j++)
-                    for (int q = 0; q < g.Cb / tb; q++) { tab.push_back((k - 1) * g.Cb + tb * q); tab.push_back(j - r + g.Kb); }
+                    for (int q = 0; q < g.Cb / tb_w; q++) { tab.push_back((k - 1) * g.Cb + tb_w * q); tab.push_back(j - r + g.Kb); }
             }
             TACO_CHECK_CUDA(cudaMemcpyAsync(m.W(p + "bank_taps"), tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
         }
@@ -540,18 +540,22 @@ static int backward_prep(Model& m, cudaStream_t s) {
         const int Z1 = c.dec_prenet_sizes[0], Z = c.dec_prenet_sizes[1], Y = c.dec_rnn_size;
         const int SPK = (c.speaker_mode == TACO_SPK_SIMPLE) ? c.speaker_embedding_size : 0;
         const int KIN = Z + SPK + HA, KO = HA + E + SPK;
-        TACO_TRY(launch_transpose(m.P("dec_prenet/dense_1/kernel") + (long long)M * Z1, m.W("dec/W1cT"), E, Z1, s));
-        TACO_TRY(launch_transpose(m.P("dec_prenet/dense_2/kernel"), m.W("dec/W2T"), Z1, Z, s));
-        TACO_TRY(launch_transpose(m.P("attention_gru/gates_kernel"), m.W("dec/WgT"), KIN, 2 * HA, s));
-        TACO_TRY(launch_transpose(m.P("attention_gru/cand_kernel"), m.W("dec/WcT"), KIN, HA, s));
-        TACO_TRY(launch_transpose(m.P("attention/query_kernel"), m.W("dec/WqT"), HA, A, s));
-        TACO_TRY(launch_transpose(m.P("concat_proj/kernel"), m.W("dec/WoT"), KO, Y, s));
+        PrepTable tb;
+        bool ok = true;
+        ok = ok && tb.transpose(m.P("dec_prenet/dense_1/kernel") + (long long)M * Z1, m.W("dec/W1cT"), E, Z1);
+        ok = ok && tb.transpose(m.P("dec_prenet/dense_2/kernel"), m.W("dec/W2T"), Z1, Z);
+        ok = ok && tb.transpose(m.P("attention_gru/gates_kernel"), m.W("dec/WgT"), KIN, 2 * HA);
+        ok = ok && tb.transpose(m.P("attention_gru/cand_kernel"), m.W("dec/WcT"), KIN, HA);
+        ok = ok && tb.transpose(m.P("attention/query_kernel"), m.W("dec/WqT"), HA, A);
+        ok = ok && tb.transpose(m.P("concat_proj/kernel"), m.W("dec/WoT"), KO, Y);
         for (int l = 1; l <= 2; l++) {
             const std::string gn = "dec_gru_" + std::to_string(l);
             float* wx = m.W("dec/g" + std::to_string(l) + "_wxcat");
-            TACO_TRY(launch_copy2d(wx, m.P(gn + "/gates_kernel"), Y, 2 * Y, 3 * Y, 2 * Y, s));
-            TACO_TRY(launch_copy2d(wx + 2 * Y, m.P(gn + "/cand_kernel"), Y, Y, 3 * Y, Y, s));
+            ok = ok && tb.copy2d(wx, nullptr, m.P(gn + "/gates_kernel"), Y, 2 * Y, 3 * Y, 2 * Y);
+            ok = ok && tb.copy2d(wx + 2 * Y, nullptr, m.P(gn + "/cand_kernel"), Y, Y, 3 * Y, Y);
         }
+        TACO_REQUIRE(ok, TACO_EINVAL, "backward_prep: decoder operand table overflows");
+        TACO_TRY(launch_prep_ops(tb, s));
     }
     return TACO_OK;
 }
