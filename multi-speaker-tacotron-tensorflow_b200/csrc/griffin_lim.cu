@@ -20,7 +20,9 @@ struct GlState {
     float* wsum = nullptr;       // [n_fft + hop*(max_frames-1)] sum of squared windows
     float* mag = nullptr;        // [max_frames, nbins] target magnitudes (S^power)
     cufftComplex* spec = nullptr;// [max_frames, nbins]
-    float* frames = nullptr;     // [max_frames, n_fft]
+    float* frames = nullptr;     // [max_frames, n_fft]   inverse-FFT frames
+    float* frames2 = nullptr;    // [max_frames, n_fft]   re-windowed frames of the next forward transform (gl_ola_scatter_kernel); taps
+                                 //                       outside the window stay zero from plan time
     float* y = nullptr;          // [n_fft + hop*(max_frames-1)] untrimmed signal
     float* carry = nullptr;      // IIR chunk states
     size_t bytes = 0;
@@ -95,6 +97,52 @@ __global__ void gl_frame_kernel(const float* __restrict__ y, const float* __rest
     if (j >= L) j = 2 * (L - 1) - j;
     j = min(max(j, 0), L - 1);
     frames[idx] = w[k] * y[n_fft / 2 + j];
+}
+// gl_ola_kernel + gl_frame_kernel in one pass, for the iterations that feed another forward transform: the thread that rebuilds
+// sample s (the same loop, in the same order, as gl_ola_kernel - bit-identical) scatters w[k]*y[s] into every frame tap that reads
+// it, so y never goes through memory and the 41 % of taps outside the Hann window (zero once, at plan time) are never touched.
+// A tap (i, k) reads ytrim[reflect(i*hop + k - n_fft/2)], ytrim = y[n_fft/2 : n_fft/2 + L]: directly, mirrored at the start
+// (index -j) or mirrored at the end (index 2(L-1) - j); L > n_fft/2 (checked by the caller) rules out double reflections.
+__global__ void gl_ola_scatter_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ wsum,
+                                      float* __restrict__ out, int n_fft, int hop, int T, int L, float inv_nfft, float tiny) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;      // index into ytrim
+    if (j >= L) return;
+    const int half = n_fft / 2, s = half + j;
+    float acc = 0.f;
+    for (int f = min(T - 1, s / hop); f >= 0; f--) {
+        const int k = s - f * hop;
+        if (k >= n_fft) break;
+        acc += w[k] * in[(long long)f * n_fft + k] * inv_nfft;
+    }
+    const float ws = wsum[s];
+    const float y = (ws > tiny) ? acc / ws : acc;
+    // direct readers: i*hop + k - half = j
+    for (int i = min(T - 1, s / hop); i >= 0; i--) {
+        const int k = s - i * hop;
+        if (k >= n_fft) break;
+        const float wk = w[k];
+        if (wk != 0.f) out[(long long)i * n_fft + k] = wk * y;
+    }
+    // readers mirrored at the start: i*hop + k - half = -j  (j > 0)
+    if (j > 0 && j <= half) {
+        for (int i = 0; i * hop <= half - j; i++) {
+            const int k = half - j - i * hop;
+            if (i >= T) break;
+            const float wk = w[k];
+            if (wk != 0.f) out[(long long)i * n_fft + k] = wk * y;
+        }
+    }
+    // readers mirrored at the end: i*hop + k - half = 2(L-1) - j  (>= L)
+    if (j <= L - 2) {
+        const int jr = 2 * (L - 1) - j + half;                 // = i*hop + k
+        for (int i = T - 1; i >= 0; i--) {
+            const int k = jr - i * hop;
+            if (k >= n_fft) break;
+            if (k < 0) continue;
+            const float wk = w[k];
+            if (wk != 0.f) out[(long long)i * n_fft + k] = wk * y;
+        }
+    }
 }
 // spec <- mag * spec / |spec|   (angle(0) = 0 -> unit phase 1)
 __global__ void gl_phase_kernel(cufftComplex* __restrict__ spec, const float* __restrict__ mag, long long n) {
@@ -200,9 +248,10 @@ int taco_gl_create(taco_gl* out, int32_t n_fft, int32_t hop, int32_t win, int32_
     TACO_CHECK_CUDA(cudaMalloc(&g.mag, sizeof(float) * nb));
     TACO_CHECK_CUDA(cudaMalloc(&g.spec, sizeof(cufftComplex) * nb));
     TACO_CHECK_CUDA(cudaMalloc(&g.frames, sizeof(float) * (size_t)max_frames * n_fft));
+    TACO_CHECK_CUDA(cudaMalloc(&g.frames2, sizeof(float) * (size_t)max_frames * n_fft));
     TACO_CHECK_CUDA(cudaMalloc(&g.y, sizeof(float) * len));
     TACO_CHECK_CUDA(cudaMalloc(&g.carry, sizeof(float) * (len / IIR_CHUNK + 2)));
-    g.bytes = sizeof(float) * (n_fft + 2 * len + nb + (size_t)max_frames * n_fft) + sizeof(cufftComplex) * nb;
+    g.bytes = sizeof(float) * (n_fft + 2 * len + nb + 2 * (size_t)max_frames * n_fft) + sizeof(cufftComplex) * nb;
     gl_window_kernel<<<cdiv(n_fft, 256), 256>>>(g.window, n_fft, win);
     TACO_CHECK_LAUNCH();
     TACO_CHECK_CUDA(cudaDeviceSynchronize());
@@ -218,7 +267,7 @@ int taco_gl_destroy(taco_gl h) {
     if (g.c2r) cufftDestroy(g.c2r);
     if (g.r2c) cufftDestroy(g.r2c);
     if (g.ana_r2c) cufftDestroy(g.ana_r2c);
-    cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.y); cudaFree(g.carry);
+    cudaFree(g.window); cudaFree(g.wsum); cudaFree(g.mag); cudaFree(g.spec); cudaFree(g.frames); cudaFree(g.frames2); cudaFree(g.y); cudaFree(g.carry);
     delete h;
     return TACO_OK;
 }
@@ -245,22 +294,35 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
         g.planned_T = T;
         gl_wsum_kernel<<<cdiv(len, 256), 256, 0, s>>>(g.window, g.wsum, g.n_fft, g.hop, T, len);
         TACO_CHECK_LAUNCH();
+        TACO_CHECK_CUDA(cudaMemsetAsync(g.frames2, 0, sizeof(float) * (size_t)g.max_frames * g.n_fft, s));
     }
     const long long nb = (long long)T * g.nbins;
     gl_init_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, s>>>(linear_spec, init_phase, g.mag, g.spec, nb, min_level_db, ref_level_db, power);
     TACO_CHECK_LAUNCH();
     const float inv_nfft = 1.0f / (float)g.n_fft;
+    // TACO_GL_FUSE=0: overlap-add and re-framing as two kernels (five launches per iteration instead of four)
+    static const bool fused = [] { const char* e = getenv("TACO_GL_FUSE"); return !(e && e[0] == '0'); }();
     auto iterate = [&](cudaStream_t st) -> int {
         TACO_CHECK_CUFFT(cufftSetStream(g.c2r, st));
         TACO_CHECK_CUFFT(cufftSetStream(g.r2c, st));
         for (int it = 0; it <= n_iters; it++) {
             TACO_CHECK_CUFFT(cufftExecC2R(g.c2r, g.spec, g.frames));
-            gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
-            TACO_CHECK_CUDA(cudaGetLastError());
-            if (it == n_iters) break;
-            gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, st>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
-            TACO_CHECK_CUDA(cudaGetLastError());
-            TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
+            if (it == n_iters) {      // the last inverse transform produces the waveform
+                gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
+                TACO_CHECK_CUDA(cudaGetLastError());
+                break;
+            }
+            if (fused) {
+                gl_ola_scatter_kernel<<<cdiv(L, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.frames2, g.n_fft, g.hop, T, L, inv_nfft, 1.17549435e-38f);
+                TACO_CHECK_CUDA(cudaGetLastError());
+                TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames2, g.spec));
+            } else {
+                gl_ola_kernel<<<cdiv(len, 256), 256, 0, st>>>(g.frames, g.window, g.wsum, g.y, g.n_fft, g.hop, T, len, inv_nfft, 1.17549435e-38f);
+                TACO_CHECK_CUDA(cudaGetLastError());
+                gl_frame_kernel<<<(unsigned)cdiv64((long long)T * g.n_fft, 256), 256, 0, st>>>(g.y, g.window, g.frames, g.n_fft, g.hop, T, L);
+                TACO_CHECK_CUDA(cudaGetLastError());
+                TACO_CHECK_CUFFT(cufftExecR2C(g.r2c, g.frames, g.spec));
+            }
             gl_phase_kernel<<<(unsigned)cdiv64(nb, 256), 256, 0, st>>>(g.spec, g.mag, nb);
             TACO_CHECK_CUDA(cudaGetLastError());
         }
@@ -285,7 +347,7 @@ int taco_gl_inv_spectrogram(taco_gl h, const float* linear_spec, const float* in
     } else {
         TACO_TRY(iterate(s));
     }
-    g_launch_count += 5LL * n_iters + 2;           // kernels of the loop (cuFFT counts as one launch per transform)
+    g_launch_count += (fused ? 4LL : 5LL) * n_iters + 2;           // kernels of the loop (cuFFT counts as one launch per transform)
     // inverse pre-emphasis on the trimmed signal
     const int nchunks = cdiv(L, IIR_CHUNK);
     iir_local_kernel<<<cdiv(nchunks, 128), 128, 0, s>>>(g.y + g.n_fft / 2, wav_out, g.carry, L, preemphasis);
