@@ -254,8 +254,18 @@ def run_ours(args):
         eng.close()
         del dev, bufs, flush
         torch.cuda.empty_cache()
-        extra["c3"] = leg_c3(tb, Engine, args.precision, local, rank, world, OverlappedAllReduce, barrier, args.targets)
-        extra["c5"] = leg_c5(tb, Engine, args.precision, local, rank, world, barrier)
+        if world == 1:
+            extra["c3"] = leg_c3(tb, Engine, args.precision, local, rank, world, OverlappedAllReduce, barrier, args.targets)
+            extra["c5"] = leg_c5(tb, Engine, args.precision, local, rank, world, barrier)
+        else:
+            # Multi-GPU: the two extra legs run as a SEPARATE job after this one has given its process group up, so that
+            # whatever happens in them (an 8-GPU run of the C3 leg died once with a launch failure on one rank that no
+            # single- or two-GPU run reproduces) cannot take the headline measurement with it.
+            barrier()
+            dist.destroy_process_group()
+            if rank != 0:
+                return
+            extra.update(run_legs_job(args, world))
 
     frames = world * CFG["N"] * CFG["T_out"] * args.steps
     if rank == 0:
@@ -309,6 +319,61 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+    if world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def run_legs_job(args, world):
+    """Rank 0 of a multi-GPU run: the C3 / C5 legs as a child job (`bench.py --legs-only` under its own torch.distributed.run on
+    the same GPUs), bounded by a timeout; returns {"c3": ..., "c5": ...} or an error record in their place."""
+    env = {k: v for k, v in os.environ.items()
+           if not (k.startswith("TORCHELASTIC") or k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE",
+                                                         "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"))}
+    port = int(os.environ.get("MASTER_PORT", "29500")) + 17
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__), "--legs-only", "--gpus", str(world), "--precision", args.precision, "--targets", args.targets]
+    try:
+        p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        for line in reversed(p.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        lines = [l.strip() for l in (p.stderr or "").splitlines() if "rror" in l]
+        err = "legs job exited with %d: %s" % (p.returncode, lines[-1][:300] if lines else "no error line on stderr")
+    except subprocess.TimeoutExpired:
+        err = "legs job timed out after 300 s"
+    except Exception as e:      # noqa: BLE001 - the legs are optional extras of the line
+        err = "legs job failed: %r" % (e,)
+    return {"c3": {"error": err}, "c5": {"error": err}}
+
+
+def run_legs_only(args):
+    """`bench.py --legs-only` (internal): the C3 and C5 legs alone, one JSON object on rank 0's stdout."""
+    import torch
+    import torch.distributed as dist
+    import tacotron_b200 as tb
+    from importlib import import_module
+    Engine = import_module("multi-speaker-tacotron-tensorflow_b200.engine").Engine
+    OverlappedAllReduce = import_module("multi-speaker-tacotron-tensorflow_b200.dist").OverlappedAllReduce
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    saved_stdout = None
+    if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)                       # NCCL's banner goes to stderr (see run_ours)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    out = {"c3": leg_c3(tb, Engine, args.precision, local, rank, world, OverlappedAllReduce, barrier, args.targets),
+           "c5": leg_c5(tb, Engine, args.precision, local, rank, world, barrier)}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -326,8 +391,12 @@ def leg_c3(tb, Engine, precision, local, rank, world, make_allreduce, barrier, t
         b["linear_targets"] = b["linear_targets"].to(torch.bfloat16)
     dev = {k: v.to(eng.dev) for k, v in b.items()}
     allreduce = make_allreduce(eng)
-    for _ in range(warmup):
+    trace = os.environ.get("TACO_BENCH_TRACE") == "1"      # per-step synchronisation + progress lines on stderr (diagnosis only)
+    for i in range(warmup):
         eng.train_step(dev, allreduce=allreduce)
+        if trace:
+            torch.cuda.synchronize()
+            print("[c3 trace] rank %d warm-up step %d done, loss %.6f" % (rank, i, eng.scalars()["loss"]), file=sys.stderr, flush=True)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for i in range(steps):
@@ -521,12 +590,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-synth", dest="synth", action="store_false", help="skip the C4 synthesis real-time-factor leg (N=1 only)")
     ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the C3 (deepvoice training) and C5 (batched inference) legs")
+    ap.add_argument("--legs-only", action="store_true", help="(internal) run only the C3 / C5 legs and print them as one JSON object")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.targets is None:
         args.targets = "bf16" if args.precision == "bf16" else "fp32"
-    if args.impl == "reference":
+    if args.legs_only:
+        run_legs_only(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
