@@ -420,3 +420,16 @@ def test_hparams_parse_keeps_list_values_and_feeder_thread_joins(tb, tmp_path):
     feeder.stop()
     feeder.join(timeout=30)
     assert not feeder.is_alive()
+
+
+def test_bench_legs_job_reports_a_failed_child_instead_of_raising():
+    """bench.py runs the C3 / C5 legs of a multi-GPU run as a child job; whatever happens in it must come back as an error
+    record in the JSON line, never as an exception that loses the headline measurement (here: no GPU, so the child fails)."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    out = bench.run_legs_job(argparse.Namespace(precision="bf16", targets="bf16"), 2)
+    assert set(out) == {"c3", "c5"}
+    if not __import__("torch").cuda.is_available():
+        assert "error" in out["c3"] and "error" in out["c5"] and "legs job" in out["c3"]["error"]
