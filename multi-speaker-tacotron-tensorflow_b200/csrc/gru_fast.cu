@@ -135,7 +135,9 @@ struct GfCfg {
     static constexpr int RED_FLOATS = 1280;
     // forward: Wg [GC][KP] + Wc [U][KP]; backward: WcT [U][KP] + WgT [U][KP2]
     static constexpr size_t w_bytes = (size_t)3 * U * KP2 * 2;     // upper bound for both directions
-    static constexpr size_t smem_bytes = w_bytes + (size_t)3 * VEC * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
+    // receive vectors: every exchanged vector exists twice (even / odd steps, see the kernels): forward 2 x {h, r*h}, backward
+    // 2 x {dc_pre, [dr_pre ; du_pre]} = 6 x VEC
+    static constexpr size_t smem_bytes = w_bytes + (size_t)6 * VEC * 2 /*recv vectors*/ + 3 * BLK_BYTES /*stages*/ +
                                          RED_FLOATS * 4 /*red*/ + 64 /*barriers*/ + 256;
 };
 
@@ -157,14 +159,17 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __nv_bfloat16* Wg_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [GC][KP]
     __nv_bfloat16* Wc_s = Wg_s + GC * KP;                                         // [U][KP]
-    __nv_bfloat16* hb_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);   // [C][R][U]
-    __nv_bfloat16* rhb_s = hb_s + Cfg::VEC;
-    __nv_bfloat16* spare = rhb_s + Cfg::VEC;
-    __nv_bfloat16* stage_rh = spare + Cfg::VEC;                                   // [R][U]
+    // Exchange buffers and barriers alternate with the step parity: bytes of step s+2 are the earliest that can meet the barrier
+    // of step s, and a peer can only send those after it has my step-(s+1) data, which I send after my step-s waits - so the
+    // protocol holds under ANY delivery order of the remote stores (with one buffer per vector it assumed that a store is never
+    // overtaken by a whole exchange phase).
+    __nv_bfloat16* hb_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);   // [2][C][R][UP]
+    __nv_bfloat16* rhb_s = hb_s + 2 * Cfg::VEC;                                   // [2][C][R][UP]
+    __nv_bfloat16* stage_rh = rhb_s + 2 * Cfg::VEC;                               // [R][U]
     __nv_bfloat16* stage_h = stage_rh + R * U;
     float* red = reinterpret_cast<float*>(stage_h + 2 * R * U);                   // RED_FLOATS
-    uint64_t* bar_rh = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);
-    uint64_t* bar_h = bar_rh + 1;
+    uint64_t* bar_rh = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);      // [2]
+    uint64_t* bar_h = bar_rh + 2;                                                 // [2]
 
     const float* __restrict__ Wg = a.Wg[d];
     const float* __restrict__ Wc = a.Wc[d];
@@ -190,10 +195,11 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     for (int idx = tid; idx < R * H; idx += GF_NT) {       // hb_s[(k/U)][r][k%U]
         const int blk = idx / (R * U), r = (idx / U) % R, i = idx % U, n = grp * R + r;
         const int k = blk * U + i;
-        hb_s[(blk * R + r) * UP + i] = __float2bfloat16((a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + k] : 0.f);
+        hb_s[Cfg::VEC + (blk * R + r) * UP + i] = __float2bfloat16(      // the first step (parity 0) reads buffer 1
+            (a.h0 && n < a.N) ? a.h0[(long long)n * a.ndir * H + d * H + k] : 0.f);
     }
     if (tid == 0) {
-        gf_mbar_init(bar_rh, 1); gf_mbar_init(bar_h, 1);
+        gf_mbar_init(bar_rh, 1); gf_mbar_init(bar_rh + 1, 1); gf_mbar_init(bar_h, 1); gf_mbar_init(bar_h + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool act = tid < Cfg::ACT;
@@ -234,17 +240,20 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
     const int s_begin = a.t_begin, s_end = a.t_end > 0 ? min(a.t_end, Lmax) : Lmax;      // chunked: steps [t_begin, t_end)
     load_gx(s_begin);
     for (int s = s_begin; s < s_end; s++) {
-        const uint32_t par = (s - s_begin) & 1;
+        const uint32_t par = (s - s_begin) & 1, ph = ((s - s_begin) >> 1) & 1;      // buffer / barrier of this step, and its phase
+        __nv_bfloat16* h_in = hb_s + (par ^ 1) * Cfg::VEC;                            // h of the previous step
+        __nv_bfloat16* h_out = hb_s + par * Cfg::VEC;
+        __nv_bfloat16* rh_io = rhb_s + par * Cfg::VEC;
         const bool valid = act && (s < L);
         const int t = (d == 0) ? s : (L - 1 - s);
         const float cgr = gr, cgu = gu, cgc = gc, cres = gres;
-        if (tid == 0) { gf_mbar_expect_tx(bar_rh, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h, GF_C * Cfg::BLK_BYTES); }
+        if (tid == 0) { gf_mbar_expect_tx(bar_rh + par, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_h + par, GF_C * Cfg::BLK_BYTES); }
         GF_T(0);
         // ---- gate phase ----
         {
             float acc[4];
             const int mt = warp % MT_G, ks = warp / MT_G;
-            gf_mma_regs<U, NK_G>(acc, afG, hb_s, ks * NK_G * 16, lane);
+            gf_mma_regs<U, NK_G>(acc, afG, h_in, ks * NK_G * 16, lane);
             float* rp = red + ks * (R * RPG) + mt * 16 + g4;
             rp[(2 * t4) * RPG] = acc[0]; rp[(2 * t4 + 1) * RPG] = acc[1];
             rp[(2 * t4) * RPG + 8] = acc[2]; rp[(2 * t4 + 1) * RPG + 8] = acc[3];
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
 #if GF_USE_STASYNC
         __syncthreads();
         GF_T(4);
-        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_rh, rhb_s + rank * R * UP, bar_rh, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_rh, rh_io + rank * R * UP, bar_rh + par, tid);
         load_gx(s + 1);      // next step's x-side pre-activations: issued in the shadow of the exchange (at the top of the step the
                              // address arithmetic and four load issues cost ~200 clk on the serial path)
         GF_T(5);
@@ -273,13 +282,13 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         __syncthreads();
         if (tid < GF_C) gf_push(stage_rh, rhb_s + rank * R * U, bar_rh, Cfg::BLK_BYTES, tid);
 #endif
-        gf_mbar_wait(bar_rh, par);
+        gf_mbar_wait(bar_rh + par, ph);
         GF_T(6);
         // ---- candidate phase ----
         {
             float acc[4];
             const int mt = warp % MT_C, ks = warp / MT_C;
-            gf_mma_regs<U, NK_C>(acc, afC, rhb_s, ks * NK_C * 16, lane);
+            gf_mma_regs<U, NK_C>(acc, afC, rh_io, ks * NK_C * 16, lane);
             float* rp = red + ks * (R * RPC) + mt * 16 + g4;
             rp[(2 * t4) * RPC] = acc[0]; rp[(2 * t4 + 1) * RPC] = acc[1];
             rp[(2 * t4) * RPC + 8] = acc[2]; rp[(2 * t4 + 1) * RPC + 8] = acc[3];
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         }
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_h, hb_s + rank * R * UP, bar_h, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_h, h_out + rank * R * UP, bar_h + par, tid);
         if (valid) {      // output and stash stores ride in the shadow of the exchange
             const long long o = (long long)n * a.T + t;
             a.out[o * a.out_ld + d * H + unit] = h_own + cres;
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_fwd_kernel(const GruArgs a)
         __syncthreads();
         if (tid < GF_C) gf_push(stage_h, hb_s + rank * R * U, bar_h, Cfg::BLK_BYTES, tid);
 #endif
-        gf_mbar_wait(bar_h, par);
+        gf_mbar_wait(bar_h + par, ph);
         GF_T(7);
     }
     if (prof) { for (int q = 0; q < 10; q++) g_gf_prof[q] = pacc[q]; g_gf_prof[10] = Lmax; }
@@ -338,13 +347,13 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     __nv_bfloat16* WcT_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [U][KP]   WcT_s[i][cu] = Wc[unit_i][cu]
     __nv_bfloat16* WgT_s = WcT_s + U * KP;                                        // [U][KP2]  WgT_s[i][gc] = Wg[unit_i][gc]
     __nv_bfloat16* dcp_s = reinterpret_cast<__nv_bfloat16*>(smem_raw + Cfg::w_bytes);  // [C][R][U]       dc_pre, all units
-    __nv_bfloat16* dg_s = dcp_s + Cfg::VEC;                                       // [2C][R][UP]     [dr_pre ; du_pre]
-    __nv_bfloat16* stage_c = dg_s + 2 * Cfg::VEC;                                 // [R][U]
+    __nv_bfloat16* dg_s = dcp_s + 2 * Cfg::VEC;                                   // [2][2C][R][UP]  [dr_pre ; du_pre]   (both alternate with the
+    __nv_bfloat16* stage_c = dg_s + 4 * Cfg::VEC;                                 // [R][U]            iteration parity, as in the forward kernel)
     __nv_bfloat16* stage_r = stage_c + R * U;
     __nv_bfloat16* stage_u = stage_r + R * U;
     float* red = reinterpret_cast<float*>(stage_u + R * U);                       // RED_FLOATS
-    uint64_t* bar_c = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);
-    uint64_t* bar_g = bar_c + 1;
+    uint64_t* bar_c = reinterpret_cast<uint64_t*>(red + Cfg::RED_FLOATS);       // [2]
+    uint64_t* bar_g = bar_c + 2;                                                  // [2]
 
     const float* __restrict__ Wg = a.Wg[d];
     const float* __restrict__ Wc = a.Wc[d];
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         for (int u = 0; u < 8; u++) { const int idx = base + u * GF_NT; if (idx < U * 2 * H) WgT_s[(idx / (2 * H)) * KP2 + idx % (2 * H)] = __float2bfloat16(v[u]); }
     }
     if (tid == 0) {
-        gf_mbar_init(bar_c, 1); gf_mbar_init(bar_g, 1);
+        gf_mbar_init(bar_c, 1); gf_mbar_init(bar_c + 1, 1); gf_mbar_init(bar_g, 1); gf_mbar_init(bar_g + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool act = tid < Cfg::ACT;
@@ -403,12 +412,14 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
     load_step(s_end - 1);
     int it = 0;
     for (int s = s_end - 1; s >= s_begin; s--, it++) {
-        const uint32_t par = it & 1;
+        const uint32_t par = it & 1, ph = (it >> 1) & 1;
+        __nv_bfloat16* dcp_io = dcp_s + par * Cfg::VEC;
+        __nv_bfloat16* dg_io = dg_s + par * 2 * Cfg::VEC;
         const bool valid = act && (s < L);
         const int t = (d == 0) ? s : (L - 1 - s);
         const float r_ = rg, u_ = ug, c_ = cc, hp_ = hp;
         float dh = dh_carry + (valid ? dout : 0.f);
-        if (tid == 0) { gf_mbar_expect_tx(bar_c, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_g, 2 * GF_C * Cfg::BLK_BYTES); }
+        if (tid == 0) { gf_mbar_expect_tx(bar_c + par, GF_C * Cfg::BLK_BYTES); gf_mbar_expect_tx(bar_g + par, 2 * GF_C * Cfg::BLK_BYTES); }
         float du_pre = 0.f, dc_pre = 0.f;
         if (valid) {
             du_pre = dh * (hp_ - c_) * u_ * (1.f - u_);
@@ -417,19 +428,19 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         if (act) stage_c[r * U + i] = __float2bfloat16(dc_pre);
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_c, dcp_s + rank * R * UP, bar_c, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_c, dcp_io + rank * R * UP, bar_c + par, tid);
         if (s - 1 >= s_begin) load_step(s - 1);      // next step's stash values: five loads issued in the shadow of the exchange
 #else
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid < GF_C) gf_push(stage_c, dcp_s + rank * R * U, bar_c, Cfg::BLK_BYTES, tid);
 #endif
-        gf_mbar_wait(bar_c, par);
+        gf_mbar_wait(bar_c + par, ph);
         // d(r*h)[own units] = sum_cu dc_pre[cu] * Wc[unit][cu]
         {
             float acc[4];
             const int mt = warp % MT, ks = warp / MT;
-            gf_mma_regs<U, NK_C>(acc, afC, dcp_s, ks * NK_C * 16, lane);
+            gf_mma_regs<U, NK_C>(acc, afC, dcp_io, ks * NK_C * 16, lane);
             float* rp = red + ks * (R * RP) + mt * 16 + g4;
             rp[(2 * t4) * RP] = acc[0]; rp[(2 * t4 + 1) * RP] = acc[1];
             rp[(2 * t4) * RP + 8] = acc[2]; rp[(2 * t4 + 1) * RP + 8] = acc[3];
@@ -445,8 +456,8 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         }
 #if GF_USE_STASYNC
         __syncthreads();
-        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_r, dg_s + rank * R * UP, bar_g, tid);
-        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_u, dg_s + (GF_C + rank) * R * UP, bar_g, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_r, dg_io + rank * R * UP, bar_g + par, tid);
+        gf_push_stasync<Cfg::BLK_BYTES / 16, QR, ROWB>(stage_u, dg_io + (GF_C + rank) * R * UP, bar_g + par, tid);
         if (valid) {      // gradient / stash stores in the shadow of the exchange
             sb_r += dr_pre; sb_u += du_pre; sb_c += dc_pre;
             const long long go = ((long long)n * a.gx_rs_n + t + a.gx_row0) * a.gx_ld + (long long)d * 3 * H + unit;
@@ -466,12 +477,12 @@ __global__ void __launch_bounds__(GF_NT, 1) gru_fast_bwd_kernel(const GruArgs a)
         if (tid < GF_C) gf_push(stage_r, dg_s + rank * R * U, bar_g, Cfg::BLK_BYTES, tid);
         else if (tid < 2 * GF_C) gf_push(stage_u, dg_s + (GF_C + rank) * R * U, bar_g, Cfg::BLK_BYTES, tid - GF_C);
 #endif
-        gf_mbar_wait(bar_g, par);
+        gf_mbar_wait(bar_g + par, ph);
         // dh_prev += sum_gc [dr_pre;du_pre][gc] * Wg[unit][gc]      (dg_s is blocked [2C][R][U]: k = gc, K = 2H)
         {
             float acc[4];
             const int mt = warp % MT, ks = warp / MT;
-            gf_mma_regs<U, NK_G>(acc, afG, dg_s, ks * NK_G * 16, lane);
+            gf_mma_regs<U, NK_G>(acc, afG, dg_io, ks * NK_G * 16, lane);
             float* rp = red + ks * (R * RP) + mt * 16 + g4;
             rp[(2 * t4) * RP] = acc[0]; rp[(2 * t4 + 1) * RP] = acc[1];
             rp[(2 * t4) * RP + 8] = acc[2]; rp[(2 * t4 + 1) * RP + 8] = acc[3];
